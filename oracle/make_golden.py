@@ -1,0 +1,184 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz from the real reference.
+
+Run in the build container (the only place /root/reference exists):
+
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden
+
+The reference is imported read-only with the recipe of SURVEY.md section 8(c): a namespace
+stub for ``meta_arch`` (its __init__ pulls timm via cgi) and stubs for ``opt_einsum``/``timm``.
+Nothing here is imported by the product, and the GPU box never runs this file (it only reads
+the committed vectors).  Each vector stores inputs + reference outputs for one hot-path
+function so that (a) the oracle restatement is pinned on CPU and (b) the CUDA path is checked
+against the *reference's* numbers, not just against our own restatement.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import sys
+import types
+from argparse import Namespace
+
+import numpy as np
+import torch
+
+REF = os.environ.get("DKT_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def import_reference():
+    if not os.path.isdir(REF):
+        raise SystemExit(f"reference checkout not found at {REF}")
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    if "meta_arch" not in sys.modules:
+        pkg = types.ModuleType("meta_arch")
+        pkg.__path__ = [os.path.join(REF, "meta_arch")]
+        sys.modules["meta_arch"] = pkg
+    if "opt_einsum" not in sys.modules:
+        oe = types.ModuleType("opt_einsum")
+        oe.contract = torch.einsum
+        sys.modules["opt_einsum"] = oe
+    if "timm" not in sys.modules:
+        sys.modules["timm"] = types.ModuleType("timm")
+    mods = dict(
+        corr=importlib.import_module("meta_arch.raft_stereo.corr"),
+        update=importlib.import_module("meta_arch.raft_stereo.update"),
+        raft=importlib.import_module("meta_arch.raft_stereo.raft_stereo"),
+        geometry=importlib.import_module("meta_arch.igev_stereo.geometry"),
+        igev_update=importlib.import_module("meta_arch.igev_stereo.update"),
+        igev_sub=importlib.import_module("meta_arch.igev_stereo.submodule"),
+    )
+    return mods
+
+
+def raft_cfg():
+    with open(os.path.join(REF, "configs/raft_stereo/base.json")) as f:
+        return json.load(f)
+
+
+def igev_cfg():
+    with open(os.path.join(REF, "configs/igev_stereo/base.json")) as f:
+        return json.load(f)
+
+
+def save(name: str, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v))
+                                  for k, v in arrays.items()})
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def golden_corr(m):
+    """CorrBlock1D build + lookup incl. out-of-range coordinates and an odd W2."""
+    g = torch.Generator().manual_seed(11)
+    for tag, (B, D, H, W) in {"a": (2, 32, 5, 40), "b": (1, 64, 3, 53)}.items():
+        f1 = torch.randn(B, D, H, W, generator=g)
+        f2 = torch.randn(B, D, H, W, generator=g)
+        blk = m["corr"].CorrBlock1D(f1, f2, num_levels=4, radius=4)
+        xs = torch.arange(W).float().view(1, 1, 1, W).expand(B, 1, H, W)
+        coords = torch.cat([xs + (torch.rand(B, 1, H, W, generator=g) * (W + 20) - W / 2 - 10),
+                            torch.zeros(B, 1, H, W)], 1)
+        coords[0, 0, 0, :6] = torch.tensor([-1.0, -0.5, 0.0, W - 1.0, W - 0.5, float(W)])
+        out = blk(coords)
+        pyr = [p.reshape(B, H, W, -1) for p in blk.corr_pyramid[:4]]
+        save(f"corr1d_{tag}", fmap1=f1, fmap2=f2, coords=coords, out=out,
+             **{f"pyr{i}": p for i, p in enumerate(pyr)})
+
+
+def golden_geo(m):
+    g = torch.Generator().manual_seed(12)
+    B, D, H, W, C, Dd = 2, 24, 4, 36, 8, 12
+    f1 = torch.randn(B, D, H, W, generator=g)
+    f2 = torch.randn(B, D, H, W, generator=g)
+    gev = torch.randn(B, C, Dd, H, W, generator=g)
+    fn = m["geometry"].Combined_Geo_Encoding_Volume(f1, f2, gev, num_levels=2, radius=4)
+    disp = torch.rand(B, 1, H, W, generator=g) * (Dd + 6) - 3
+    disp[0, 0, 0, :4] = torch.tensor([0.0, -1.0, Dd - 1.0, float(Dd)])
+    coords = torch.arange(W).float().reshape(1, 1, W, 1).repeat(B, H, 1, 1)
+    out = fn(disp, coords)
+    save("geo_a", fmap1=f1, fmap2=f2, gev=gev, disp=disp, out=out)
+
+
+def _ns(cfg):
+    return Namespace(mixed_precision=False, **cfg)
+
+
+def golden_update(m):
+    """One BasicMultiUpdateBlock step (RAFT and IGEV flavours) + upsampling."""
+    from dkt_stereo_b200.synthetic import synthetic_state_dict, shapes_of
+    g = torch.Generator().manual_seed(13)
+    B, h, w = 1, 16, 24
+    for tag, mod, cfg, cp, fc in (("raft", m["update"], raft_cfg(), 36, 2), ("igev", m["igev_update"], igev_cfg(), 162, 1)):
+        blk = mod.BasicMultiUpdateBlock(_ns(cfg), hidden_dims=cfg["hidden_dims"]).eval()
+        sd = synthetic_state_dict(shapes_of(blk.state_dict()), seed=3)
+        blk.load_state_dict(sd)
+        net = [torch.tanh(torch.randn(B, 128, h >> i, w >> i, generator=g)) for i in range(3)]
+        inp = [[torch.randn(B, 128, h >> i, w >> i, generator=g) * 0.5 for _ in range(3)] for i in range(3)]
+        corr = torch.randn(B, cp, h, w, generator=g)
+        flow = torch.randn(B, fc, h, w, generator=g) * 3
+        with torch.no_grad():
+            net_o, mask, delta = blk([t.clone() for t in net], inp, corr, flow)
+        arrays = dict(corr=corr, flow=flow, mask=mask, delta=delta, keys=np.array(sorted(sd.keys())),
+                      key_shapes=np.array([json.dumps(list(sd[k].shape)) for k in sorted(sd.keys())]))
+        for i in range(3):
+            arrays[f"net{i}"] = net[i]
+            arrays[f"net_out{i}"] = net_o[i]
+            for j, n in enumerate("zrq"):
+                arrays[f"c{n}{i}"] = inp[i][j]
+        save(f"update_{tag}", **arrays)
+    # convex upsample (raft_stereo.py:70-82) via an instance with only args
+    R = m["raft"].RAFTStereo
+    flow = torch.randn(2, 2, 6, 9, generator=g) * 5
+    mask = torch.randn(2, 144, 6, 9, generator=g)
+    dummy = types.SimpleNamespace(args=_ns(raft_cfg()))
+    up = R.upsample_flow(dummy, flow, mask)
+    save("convex_upsample", flow=flow, mask=mask, out=up)
+    # IGEV context_upsample (submodule.py:242-254)
+    disp = torch.rand(2, 1, 5, 7, generator=g) * 30
+    wts = torch.softmax(torch.randn(2, 9, 20, 28, generator=g), 1)
+    save("context_upsample", disp=disp, weights=wts, out=m["igev_sub"].context_upsample(disp, wts))
+
+
+def golden_raft_forward(m, height=64, width=96, iters=4, tag="raft_fwd_small", batch=1, mode="noise"):
+    """Full RAFTStereo.forward(test_mode=True) with name-seeded synthetic weights."""
+    from dkt_stereo_b200.synthetic import synthetic_state_dict, shapes_of, synthetic_pair
+    cfg = raft_cfg()
+    model = m["raft"].RAFTStereo(_ns(cfg)).eval()
+    sd = synthetic_state_dict(shapes_of(model.state_dict()), seed=0)
+    model.load_state_dict(sd, strict=True)
+    im1, im2 = synthetic_pair(batch, height, width, seed=1234, mode=mode)
+    with torch.no_grad():
+        flow_lr, flow_up = model(im1, im2, iters=iters, test_mode=True)
+    save(tag, flow_lr=flow_lr, flow_up=flow_up, meta=np.array([batch, height, width, iters]),
+         mode=np.array(mode), keys=np.array(sorted(sd.keys())),
+         key_shapes=np.array([json.dumps(list(sd[k].shape)) for k in sorted(sd.keys())]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    m = import_reference()
+    jobs = {
+        "corr": lambda: golden_corr(m),
+        "geo": lambda: golden_geo(m),
+        "update": lambda: golden_update(m),
+        "raft_small": lambda: golden_raft_forward(m),
+        "raft_shift": lambda: golden_raft_forward(m, 64, 96, 6, "raft_fwd_shift", 1, "shift"),
+        "raft_cfg1": lambda: golden_raft_forward(m, 256, 512, 12, "raft_fwd_cfg1", 1, "noise"),
+    }
+    for k, fn in jobs.items():
+        if not args.only or k in args.only.split(","):
+            fn()
+
+
+if __name__ == "__main__":
+    main()

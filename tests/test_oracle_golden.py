@@ -1,0 +1,69 @@
+"""CPU: the oracle restatement is pinned against vectors produced by the real reference
+(oracle/make_golden.py).  Tolerances are fp32 round-off of a different summation order."""
+import torch
+
+from oracle import hotpath as O
+from dkt_stereo_b200.synthetic import synthetic_state_dict, synthetic_pair
+from helpers import load_golden, golden_shapes, stats, RAFT_CFG, IGEV_CFG
+
+
+def test_corr1d_build_and_lookup():
+    for tag in ("a", "b"):
+        g = load_golden(f"corr1d_{tag}")
+        pyr = O.corr1d_pyramid(g["fmap1"], g["fmap2"], 4)
+        for i in range(4):
+            assert pyr[i].shape == g[f"pyr{i}"].shape
+            assert stats(pyr[i], g[f"pyr{i}"])[1] < 2e-5
+        out = O.corr1d_lookup(pyr, g["coords"][:, 0], 4)
+        assert out.shape == g["out"].shape
+        assert stats(out, g["out"])[1] < 2e-5
+
+
+def test_geo_lookup():
+    g = load_golden("geo_a")
+    geo, init = O.geo_pyramids(g["fmap1"], g["fmap2"], g["gev"], 2)
+    out = O.geo_lookup(geo, init, g["disp"], 4)
+    assert out.shape == g["out"].shape == (2, 162, 4, 36)
+    assert stats(out, g["out"])[1] < 2e-5
+
+
+def _update(tag, igev):
+    g = load_golden(f"update_{tag}")
+    sd = synthetic_state_dict(golden_shapes(g), seed=3)
+    sd = {"update_block." + k: v for k, v in sd.items()}
+    net = [g[f"net{i}"] for i in range(3)]
+    inp = [[g[f"c{n}{i}"] for n in "zrq"] for i in range(3)]
+    with torch.no_grad():
+        net_o, mask, delta = O.update_block(sd, "update_block.", net, inp, g["corr"], g["flow"], igev=igev)
+    for i in range(3):
+        assert stats(net_o[i], g[f"net_out{i}"])[1] < 1e-5
+    assert stats(mask, g["mask"])[1] < 1e-5
+    assert stats(delta, g["delta"])[1] < 1e-5
+
+
+def test_update_block_raft():
+    _update("raft", False)
+
+
+def test_update_block_igev():
+    _update("igev", True)
+
+
+def test_upsamplers():
+    g = load_golden("convex_upsample")
+    assert stats(O.convex_upsample(g["flow"], g["mask"], 4), g["out"])[1] < 1e-5
+    g = load_golden("context_upsample")
+    assert stats(O.context_upsample(g["disp"], g["weights"]), g["out"])[1] < 1e-5
+
+
+def test_raft_forward_small_and_shift():
+    for tag in ("raft_fwd_small", "raft_fwd_shift"):
+        g = load_golden(tag)
+        B, H, W, iters = [int(v) for v in g["meta"]]
+        sd = synthetic_state_dict(golden_shapes(g), seed=0)
+        im1, im2 = synthetic_pair(B, H, W, seed=1234, mode=str(g["mode"]))
+        lr, up = O.raft_forward(sd, im1, im2, iters, RAFT_CFG)
+        assert up.shape == g["flow_up"].shape == (B, 1, H, W)
+        mean, mx = stats(up, g["flow_up"])
+        assert mean < 1e-4, (tag, mean, mx)
+        assert stats(lr, g["flow_lr"])[0] < 1e-4
