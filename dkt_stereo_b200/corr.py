@@ -1,0 +1,47 @@
+"""Correlation-volume operators behind the reference's ``corr_implementation`` plug-in point.
+
+Every class keeps the reference call shape (reference meta_arch/raft_stereo/raft_stereo.py:118-142):
+``Block(fmap1, fmap2, num_levels=, radius=)`` then ``block(coords (B,2,h,w)) -> (B, L*(2r+1), h, w)``.
+
+* ``B200CorrBlock1D``      replaces ``CorrBlock1D`` (reference core/corr.py:110-156)
+* ``corr_sampler_forward`` replaces the un-vendored ``corr_sampler.forward`` extension that
+  ``CorrBlockFast1D`` binds (reference core/corr.py:17-29,49): ``(volume, coords, radius) -> (out,)``
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Tuple
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+class B200CorrBlock1D:
+    def __init__(self, fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int = 4, radius: int = 4,
+                 impl: str = "tc", scale: float | None = None):
+        L.require_device(fmap1)
+        self.num_levels, self.radius = num_levels, radius
+        D = fmap1.shape[1]
+        # the reference divides by sqrt(D) (core/corr.py:155); IGEV's variant does not (geometry.py:67-69)
+        self.scale = (1.0 / math.sqrt(D)) if scale is None else scale
+        self.corr_pyramid: List[torch.Tensor] = ops.corr1d_build(fmap1.float(), fmap2.float(), num_levels,
+                                                                 self.scale, impl=impl)
+
+    def __call__(self, coords: torch.Tensor) -> torch.Tensor:
+        B, _, H, W = coords.shape
+        cx = coords[:, 0].contiguous().float()
+        out = torch.empty(B, self.num_levels * (2 * self.radius + 1), H, W, device=coords.device, dtype=torch.float32)
+        ops.corr1d_lookup(self.corr_pyramid, cx, self.radius, out, out_layout="nchw")
+        return out
+
+
+def corr_sampler_forward(volume: torch.Tensor, coords: torch.Tensor, radius: int) -> Tuple[torch.Tensor]:
+    """Drop-in for ``corr_sampler.forward``: volume (B,H,W1,W2_l) one pyramid level, coords (B,1,H,W1)
+    already divided by 2^l  ->  ((B, 2r+1, H, W1),)."""
+    L.require_device(volume)
+    B, H, W1, _ = volume.shape
+    out = torch.empty(B, 2 * radius + 1, H, W1, device=volume.device, dtype=torch.float32)
+    ops.corr1d_lookup([volume.contiguous().float()], coords[:, 0].contiguous().float(), radius, out, out_layout="nchw")
+    return (out,)

@@ -1,0 +1,73 @@
+// Shared device/host helpers for libdkt_stereo_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/dkt_stereo_b200.h"
+
+#define DKT_CHECK_ARG(cond)  do { if (!(cond)) return DKT_E_INVALID; } while (0)
+#define DKT_RETURN_LAST()    do { cudaError_t e__ = cudaGetLastError(); return e__ == cudaSuccess ? 0 : (int)e__; } while (0)
+
+namespace dkt {
+
+constexpr int kNumSMs = 148;
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- bf16 (hi, lo) split: hi = rn(x), lo = rn(x - hi).  hi + lo carries 16 mantissa bits ----
+__device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) {
+    __nv_bfloat16 h = __float2bfloat16_rn(x);
+    float r = x - __bfloat162float(h);
+    __nv_bfloat16 l = __float2bfloat16_rn(r);
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
+}
+
+// pack two consecutive channels
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    uint16_t ah, al, bh, bl;
+    split_bf16(a, ah, al);
+    split_bf16(b, bh, bl);
+    hi = (uint32_t)ah | ((uint32_t)bh << 16);
+    lo = (uint32_t)al | ((uint32_t)bl << 16);
+}
+
+// ---- activations.  expf / tanhf (not the __ intrinsics): the recurrence is sensitive ----
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    switch (act) {
+        case DKT_ACT_RELU:    return fmaxf(x, 0.0f);
+        case DKT_ACT_SIGMOID: return sigmoidf_acc(x);
+        case DKT_ACT_TANH:    return tanhf(x);
+        default:              return x;
+    }
+}
+
+// Write one value to every non-null precision of an NHWC tensor slice.
+__device__ __forceinline__ void store_all(const dkt_tensor& t, int64_t pixel, int c, float v) {
+    int64_t off = pixel * t.C + t.c_begin + c;
+    if (t.f32) t.f32[off] = v;
+    if (t.hi) {
+        uint16_t h, l;
+        split_bf16(v, h, l);
+        t.hi[off] = h;
+        if (t.lo) t.lo[off] = l;
+    }
+}
+
+// 4 consecutive channels (c % 4 == 0 and slice 4-aligned by construction of the callers)
+__device__ __forceinline__ void store_all4(const dkt_tensor& t, int64_t pixel, int c, float4 v) {
+    int64_t off = pixel * t.C + t.c_begin + c;
+    if (t.f32) *reinterpret_cast<float4*>(t.f32 + off) = v;
+    if (t.hi) {
+        uint32_t h0, l0, h1, l1;
+        split_bf16x2(v.x, v.y, h0, l0);
+        split_bf16x2(v.z, v.w, h1, l1);
+        *reinterpret_cast<uint2*>(t.hi + off) = make_uint2(h0, h1);
+        if (t.lo) *reinterpret_cast<uint2*>(t.lo + off) = make_uint2(l0, l1);
+    }
+}
+
+}  // namespace dkt

@@ -1,0 +1,298 @@
+// K3 / tensor-core variant: implicit-GEMM convolution on tcgen05 with TMEM accumulators.
+//
+//   M = 128 output pixels (an 8 x 16 patch of one image), N = all output channels (<= 256),
+//   K = taps x input channels, walked as (tap, 64-channel block) steps.
+//
+// No im2col buffer exists anywhere: for filter tap (ky,kx) the A tile is the SAME 8x16 patch
+// shifted by (ky-pad, kx-pad), fetched by one 4-D TMA box {64 ch, 16, 8, 1} from the NHWC
+// activation; pixels that fall outside the image are zero-filled by the TMA unit, which is
+// exactly the conv's zero padding.  The box lands in shared memory as 128 rows of 128 bytes
+// with the 128-byte swizzle, i.e. already in the canonical K-major UMMA layout.
+//
+// Precision: activations and weights are bf16 (hi, lo) pairs; each K step issues
+// hi*hi + lo*hi + hi*lo into the same fp32 TMEM accumulator (3-term split, ~16 mantissa bits).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> fused bias/context/activation/GRU algebra ->
+// NHWC global stores in fp32 and/or split bf16).
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace dkt {
+
+using namespace tc;
+
+constexpr int TC_TILE_W = 16, TC_TILE_H = 8, TC_BLOCK_K = 64;
+constexpr int TC_MAX_STAGES = 4;
+constexpr uint32_t TC_A_BYTES = 128 * 128;          // 128 pixels x 64 bf16
+constexpr int TC_THREADS = 192;
+
+struct TcConvParams {
+    CUtensorMap act[DKT_MAX_SRCS][2];   // [source][hi/lo], 4-D (C, W, H, B)
+    CUtensorMap wgt[2];                 // hi/lo, 2-D (Cin_total, taps*Npad)
+    int nsrc;
+    int c_begin[DKT_MAX_SRCS];
+    int kblocks[DKT_MAX_SRCS];
+    int ksize, pad, taps;
+    int N, Npad;
+    int H, W, tiles_x, tiles_y;
+    int stages;
+    uint32_t tmem_cols;
+    dkt_epilogue epi;
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// one group of 4 consecutive output channels of one pixel
+__device__ __forceinline__ void tc_epilogue4(const dkt_epilogue& e, int N, int64_t p, int n, float4 a) {
+    if (e.kind == DKT_EPI_LINEAR) {
+        if (e.bias) { float4 b = ld4(e.bias + n); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+        if (e.ctx) { float4 c = ld4(e.ctx + p * e.ctx_C + e.ctx_c0 + n); a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; }
+        a.x = apply_act(a.x, e.act) * e.scale; a.y = apply_act(a.y, e.act) * e.scale;
+        a.z = apply_act(a.z, e.act) * e.scale; a.w = apply_act(a.w, e.act) * e.scale;
+        store_all4(e.out, p, n, a);
+    } else if (e.kind == DKT_EPI_GRU_ZR) {
+        const int Nh = N >> 1;
+        float4 c = ld4(e.ctx + p * e.ctx_C + e.ctx_c0 + n);
+        float4 s = make_float4(sigmoidf_acc(a.x + c.x), sigmoidf_acc(a.y + c.y),
+                               sigmoidf_acc(a.z + c.z), sigmoidf_acc(a.w + c.w));
+        if (n < Nh) {
+            *reinterpret_cast<float4*>(e.z.f32 + p * e.z.C + e.z.c_begin + n) = s;
+        } else {
+            const int ch = n - Nh;
+            float4 h = ld4(e.h.f32 + p * e.h.C + e.h.c_begin + ch);
+            store_all4(e.out, p, ch, make_float4(s.x * h.x, s.y * h.y, s.z * h.z, s.w * h.w));
+        }
+    } else {
+        float4 c = ld4(e.ctx + p * e.ctx_C + e.ctx_c0 + n);
+        float4 z = ld4(e.z.f32 + p * e.z.C + e.z.c_begin + n);
+        float4 h = ld4(e.h.f32 + p * e.h.C + e.h.c_begin + n);
+        float4 o;
+        o.x = (1.f - z.x) * h.x + z.x * tanhf(a.x + c.x);
+        o.y = (1.f - z.y) * h.y + z.y * tanhf(a.y + c.y);
+        o.z = (1.f - z.z) * h.z + z.z * tanhf(a.z + c.z);
+        o.w = (1.f - z.w) * h.w + z.w * tanhf(a.w + c.w);
+        store_all4(e.out, p, n, o);
+    }
+}
+
+// scalar tail of a partially valid 4-group (only LINEAR convs have N % 4 != 0)
+__device__ __forceinline__ void tc_epilogue1(const dkt_epilogue& e, int64_t p, int n, float a) {
+    if (e.bias) a += e.bias[n];
+    if (e.ctx) a += e.ctx[p * e.ctx_C + e.ctx_c0 + n];
+    store_all(e.out, p, n, apply_act(a, e.act) * e.scale);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    const uint32_t b_bytes = (uint32_t)prm.Npad * 128u;
+    const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)prm.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + TC_MAX_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int tx_t = tile % prm.tiles_x;
+    const int ty_t = (tile / prm.tiles_x) % prm.tiles_y;
+    const int b = tile / (prm.tiles_x * prm.tiles_y);
+    const int x0 = tx_t * TC_TILE_W, y0 = ty_t * TC_TILE_H;
+
+    int kb_total = 0;
+    for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
+    const int iters = prm.taps * kb_total;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < prm.nsrc; ++s) { tma_prefetch_desc(&prm.act[s][0]); tma_prefetch_desc(&prm.act[s][1]); }
+        tma_prefetch_desc(&prm.wgt[0]);
+        tma_prefetch_desc(&prm.wgt[1]);
+        for (int s = 0; s < prm.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, prm.tmem_cols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int it = 0;
+            for (int tap = 0; tap < prm.taps; ++tap) {
+                const int ky = tap / prm.ksize, kx = tap - ky * prm.ksize;
+                const int xs = x0 + kx - prm.pad, ys = y0 + ky - prm.pad;
+                int kofs = 0;
+                for (int s = 0; s < prm.nsrc; ++s) {
+                    for (int kb = 0; kb < prm.kblocks[s]; ++kb, ++it) {
+                        const int stage = it % prm.stages;
+                        const uint32_t phase = (uint32_t)(it / prm.stages) & 1u;
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        uint8_t* st = smem + (size_t)stage * stage_bytes;
+                        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+                        const int c = prm.c_begin[s] + kb * TC_BLOCK_K;
+                        tma_load_4d(st, &prm.act[s][0], &full_bar[stage], c, xs, ys, b);
+                        tma_load_4d(st + TC_A_BYTES, &prm.act[s][1], &full_bar[stage], c, xs, ys, b);
+                        tma_load_2d(st + 2 * TC_A_BYTES, &prm.wgt[0], &full_bar[stage], kofs + kb * TC_BLOCK_K, tap * prm.Npad);
+                        tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &prm.wgt[1], &full_bar[stage], kofs + kb * TC_BLOCK_K, tap * prm.Npad);
+                    }
+                    kofs += prm.kblocks[s] * TC_BLOCK_K;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = idesc_bf16_m128((uint32_t)prm.Npad);
+            for (int it = 0; it < iters; ++it) {
+                const int stage = it % prm.stages;
+                const uint32_t phase = (uint32_t)(it / prm.stages) & 1u;
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t a_lo = a_hi + TC_A_BYTES;
+                const uint32_t w_hi = a_hi + 2 * TC_A_BYTES;
+                const uint32_t w_lo = w_hi + b_bytes;
+#pragma unroll
+                for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+                    const uint64_t dah = smem_desc_sw128(a_hi + k * 32), dal = smem_desc_sw128(a_lo + k * 32);
+                    const uint64_t dwh = smem_desc_sw128(w_hi + k * 32), dwl = smem_desc_sw128(w_lo + k * 32);
+                    umma_bf16(tmem_base, dah, dwh, idesc, (it | k) != 0);
+                    umma_bf16(tmem_base, dal, dwh, idesc, 1u);
+                    umma_bf16(tmem_base, dah, dwl, idesc, 1u);
+                }
+                umma_commit(&empty_bar[stage]);       // smem slot reusable once these MMAs retire
+            }
+            umma_commit(tmem_full_bar);               // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
+        const bool valid = (y < prm.H) && (x < prm.W);
+        const int64_t p = ((int64_t)b * prm.H + y) * prm.W + x;
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+        const dkt_epilogue& e = prm.epi;
+        const int N = prm.N;
+        for (int c0 = 0; c0 < prm.Npad; c0 += 32) {
+            float v[32];
+            const int ncols = (prm.Npad - c0 >= 32) ? 32 : 16;
+            __syncwarp();                       // tcgen05.ld is .sync.aligned: reconverge first
+            if (ncols == 32) tmem_ld32(tbase + c0, v); else tmem_ld16(tbase + c0, v);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (j < ncols) {
+                        const int n = c0 + j;
+                        if (n + 3 < N) {
+                            tc_epilogue4(e, N, p, n, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) if (n + t < N) tc_epilogue1(e, p, n + t, v[j + t]);
+                        }
+                    }
+                }
+            }
+        }
+        if (valid && e.tail) {
+            for (int t = 0; t < e.tail_C; ++t) store_all(e.out, p, N + t, __ldg(e.tail + p * e.tail_C + t));
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, prm.tmem_cols);
+}
+
+}  // namespace dkt
+
+using namespace dkt;
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int dkt_conv2d_tc(const dkt_tensor* srcs, int nsrc, const uint16_t* w_hi, const uint16_t* w_lo,
+                             int ksize, int N, const dkt_epilogue* epi, int B, int H, int W, void* stream) {
+    DKT_CHECK_ARG(srcs && w_hi && w_lo && epi);
+    DKT_CHECK_ARG(nsrc >= 1 && nsrc <= DKT_MAX_SRCS);
+    DKT_CHECK_ARG(B > 0 && H > 0 && W > 0 && N > 0);
+    if (ksize != 1 && ksize != 3) return DKT_E_UNSUPPORTED;
+    if (N > 256) return DKT_E_UNSUPPORTED;
+    // epilogue sanity (vector accesses need 4-channel granularity)
+    const dkt_epilogue& e = *epi;
+    if (e.kind == DKT_EPI_LINEAR) {
+        DKT_CHECK_ARG(e.out.f32 || e.out.hi);
+    } else {
+        DKT_CHECK_ARG(e.ctx && e.z.f32 && e.h.f32 && (e.out.f32 || e.out.hi));
+        if (N % 8) return DKT_E_ALIGNMENT;
+        if ((e.z.C % 4) || (e.z.c_begin % 4) || (e.h.C % 4) || (e.h.c_begin % 4)) return DKT_E_ALIGNMENT;
+    }
+    if (N >= 4 && ((e.out.C % 4) || (e.out.c_begin % 4))) return DKT_E_ALIGNMENT;
+    if (e.ctx && ((e.ctx_C % 4) || (e.ctx_c0 % 4) || !aligned16(e.ctx))) return DKT_E_ALIGNMENT;
+    if (e.bias && !aligned16(e.bias)) return DKT_E_ALIGNMENT;
+    if (!aligned16(e.out.f32) || !aligned16(e.out.hi) || !aligned16(e.out.lo)) return DKT_E_ALIGNMENT;
+
+    TcConvParams prm{};
+    prm.nsrc = nsrc;
+    int cin_total = 0;
+    for (int s = 0; s < nsrc; ++s) {
+        const dkt_tensor& t = srcs[s];
+        DKT_CHECK_ARG(t.hi && t.lo && t.c_count > 0 && t.c_begin >= 0 && t.c_begin + t.c_count <= t.C);
+        if ((t.c_begin % 64) || (t.c_count % 64) || (t.C % 8) || !aligned16(t.hi) || !aligned16(t.lo))
+            return DKT_E_ALIGNMENT;
+        prm.c_begin[s] = t.c_begin;
+        prm.kblocks[s] = t.c_count / 64;
+        cin_total += t.c_count;
+        const uint64_t dims[4] = {(uint64_t)t.C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        const uint64_t strides[4] = {1, (uint64_t)t.C, (uint64_t)t.C * W, (uint64_t)t.C * W * H};
+        const uint32_t box[4] = {64, TC_TILE_W, TC_TILE_H, 1};
+        if (!make_tmap_bf16(&prm.act[s][0], t.hi, 4, dims, strides, box)) return DKT_E_DRIVER;
+        if (!make_tmap_bf16(&prm.act[s][1], t.lo, 4, dims, strides, box)) return DKT_E_DRIVER;
+    }
+    prm.ksize = ksize;
+    prm.pad = ksize / 2;
+    prm.taps = ksize * ksize;
+    prm.N = N;
+    prm.Npad = (N + 15) / 16 * 16;
+    {
+        const uint64_t dims[2] = {(uint64_t)cin_total, (uint64_t)prm.taps * prm.Npad};
+        const uint64_t strides[2] = {1, (uint64_t)cin_total};
+        const uint32_t box[2] = {64, (uint32_t)prm.Npad};
+        if (!aligned16(w_hi) || !aligned16(w_lo)) return DKT_E_ALIGNMENT;
+        if (!make_tmap_bf16(&prm.wgt[0], w_hi, 2, dims, strides, box)) return DKT_E_DRIVER;
+        if (!make_tmap_bf16(&prm.wgt[1], w_lo, 2, dims, strides, box)) return DKT_E_DRIVER;
+    }
+    prm.H = H;
+    prm.W = W;
+    prm.tiles_x = ceil_div(W, TC_TILE_W);
+    prm.tiles_y = ceil_div(H, TC_TILE_H);
+    const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * (uint32_t)prm.Npad * 128u;
+    int stages = (int)((200u * 1024u) / stage_bytes);
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 2) return DKT_E_UNSUPPORTED;
+    prm.stages = stages;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)prm.Npad) cols <<= 1;
+    prm.tmem_cols = cols;
+    prm.epi = e;
+
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align*/ + 128 /*barriers*/;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce != cudaSuccess) return (int)ce;
+        attr_set = true;
+    }
+    const int64_t tiles = (int64_t)prm.tiles_x * prm.tiles_y * B;
+    if (tiles > 0x7fffffff) return DKT_E_UNSUPPORTED;
+    conv_tc_kernel<<<(unsigned)tiles, TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
+    DKT_RETURN_LAST();
+}

@@ -1,0 +1,286 @@
+// Cross-scale plumbing of the multi-level GRU (pool2x / interp), final upsamplers (K4) and
+// layout / precision conversions.  All HBM-bound elementwise kernels over NHWC activations.
+// Contracts and reference citations: include/dkt_stereo_b200.h.
+#include "common.cuh"
+
+namespace dkt {
+
+// ---- pool2x: 3x3 / stride 2 / pad 1 average, divisor 9 (count_include_pad) -----------------
+__global__ void __launch_bounds__(256)
+pool2x_kernel(const float* __restrict__ src, int sC, int sc0, dkt_tensor dst, int C4,
+              int Hs, int Ws, int Hd, int Wd, int64_t total) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int q = (int)(t % C4);
+    int64_t p = t / C4;
+    const int xo = (int)(p % Wd);
+    int64_t r = p / Wd;
+    const int yo = (int)(r % Hd);
+    const int64_t b = r / Hd;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int y = 2 * yo + dy;
+        if (y < 0 || y >= Hs) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int x = 2 * xo + dx;
+            if (x < 0 || x >= Ws) continue;
+            float4 v = __ldg(reinterpret_cast<const float4*>(src + ((b * Hs + y) * (int64_t)Ws + x) * sC + sc0 + q * 4));
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    }
+    // ATen divides the window sum by 9; keep a true division for bit-level agreement
+    s.x /= 9.f; s.y /= 9.f; s.z /= 9.f; s.w /= 9.f;
+    store_all4(dst, p, q * 4, s);
+}
+
+// ---- bilinear resize, align_corners=True ------------------------------------------------------
+__global__ void __launch_bounds__(256)
+interp_kernel(const float* __restrict__ src, int sC, int sc0, dkt_tensor dst, int C4,
+              int Hs, int Ws, int Hd, int Wd, float sy, float sx, int64_t total) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int q = (int)(t % C4);
+    int64_t p = t / C4;
+    const int xo = (int)(p % Wd);
+    int64_t r = p / Wd;
+    const int yo = (int)(r % Hd);
+    const int64_t b = r / Hd;
+    const float fy = sy * yo, fx = sx * xo;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < Hs - 1), x1 = x0 + (x0 < Ws - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float* base = src + b * Hs * (int64_t)Ws * sC + sc0 + q * 4;
+    float4 v00 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y0 * Ws + x0) * sC));
+    float4 v01 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y0 * Ws + x1) * sC));
+    float4 v10 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y1 * Ws + x0) * sC));
+    float4 v11 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y1 * Ws + x1) * sC));
+    float4 o;
+    o.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
+    o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
+    o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
+    o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
+    store_all4(dst, p, q * 4, o);
+}
+
+// ---- K4 RAFT: convex combination upsampling ---------------------------------------------------
+// one thread per (low-res pixel, sub-position ij); mask channel = k*f*f + ij
+__global__ void __launch_bounds__(256)
+convex_upsample_kernel(const float* __restrict__ flow, int flow_C, const float* __restrict__ mask,
+                       float* __restrict__ out, int H, int W, int f, int64_t total) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int ff = f * f;
+    const int ij = (int)(t % ff);
+    const int64_t p = t / ff;
+    const int x = (int)(p % W);
+    int64_t r = p / W;
+    const int y = (int)(r % H);
+    const int64_t b = r / H;
+    const float* m = mask + p * (9 * ff) + ij;
+    float w[9];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { w[k] = __ldg(m + k * ff); mx = fmaxf(mx, w[k]); }
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { w[k] = expf(w[k] - mx); den += w[k]; }
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+        float v = 0.f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+            v = (float)f * __ldg(flow + ((b * H + yy) * (int64_t)W + xx) * flow_C);
+        acc += (w[k] / den) * v;
+    }
+    const int i = ij / f, j = ij % f;
+    out[(b * (H * f) + (y * f + i)) * (int64_t)(W * f) + x * f + j] = acc;
+}
+
+// ---- K4 IGEV: learned-weight upsampling (weights already softmaxed) ----------------------------
+__global__ void __launch_bounds__(256)
+context_upsample_kernel(const float* __restrict__ disp, const float* __restrict__ wts, float* __restrict__ out,
+                        float in_scale, float out_scale, int H, int W, int64_t total) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int W4 = W * 4, H4 = H * 4;
+    const int X = (int)(t % W4);
+    int64_t r = t / W4;
+    const int Y = (int)(r % H4);
+    const int64_t b = r / H4;
+    const int y = Y >> 2, x = X >> 2;
+    const int64_t plane = (int64_t)H4 * W4;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+        float v = 0.f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = in_scale * __ldg(disp + (b * H + yy) * (int64_t)W + xx);
+        acc += v * __ldg(wts + (b * 9 + k) * plane + (int64_t)Y * W4 + X);
+    }
+    out[t] = out_scale * acc;
+}
+
+// ---- layout conversions ------------------------------------------------------------------------
+// generic strided (b, c, y, x) fp32 source -> NHWC slice, 32x32 smem transpose over (c, x) of one (b,y)
+__global__ void __launch_bounds__(256)
+to_nhwc_kernel(const float* __restrict__ src, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+               const float* __restrict__ bias, dkt_tensor dst, int C, int H, int W) {
+    __shared__ float tile[32][33];
+    const int by = blockIdx.z;
+    const int y = by % H;
+    const int64_t b = by / H;
+    const int c0 = blockIdx.y * 32, x0 = blockIdx.x * 32;
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+    const float* base = src + b * sb + y * sh;
+    if (sw == 1 || sc != 1) {
+        for (int i = ty; i < 32; i += 8) {     // rows = c, fast = x
+            int c = c0 + i, x = x0 + tx;
+            tile[i][tx] = (c < C && x < W) ? __ldg(base + c * sc + x * sw) : 0.f;
+        }
+    } else {
+        for (int i = ty; i < 32; i += 8) {     // rows = x, fast = c (channels_last source)
+            int x = x0 + i, c = c0 + tx;
+            tile[tx][i] = (c < C && x < W) ? __ldg(base + c * sc + x * sw) : 0.f;
+        }
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        int x = x0 + i, c = c0 + tx;
+        if (x < W && c < C) {
+            float v = tile[tx][i];
+            if (bias) v += __ldg(bias + c);
+            store_all(dst, (b * H + y) * (int64_t)W + x, c, v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+to_nchw_kernel(const float* __restrict__ src, int sC, int sc0, float* __restrict__ dst, int C, int H, int W) {
+    __shared__ float tile[32][33];
+    const int by = blockIdx.z;
+    const int y = by % H;
+    const int64_t b = by / H;
+    const int c0 = blockIdx.y * 32, x0 = blockIdx.x * 32;
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+    for (int i = ty; i < 32; i += 8) {
+        int x = x0 + i, c = c0 + tx;
+        tile[i][tx] = (x < W && c < C) ? __ldg(src + ((b * H + y) * (int64_t)W + x) * sC + sc0 + c) : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        int c = c0 + i, x = x0 + tx;
+        if (c < C && x < W) dst[((b * C + c) * H + y) * (int64_t)W + x] = tile[tx][i];
+    }
+}
+
+}  // namespace dkt
+
+using namespace dkt;
+
+static int check_slice(const dkt_tensor* t, bool need_f32) {
+    if (!t) return DKT_E_INVALID;
+    if (need_f32 && !t->f32) return DKT_E_INVALID;
+    if (!t->f32 && !t->hi) return DKT_E_INVALID;
+    if (t->c_count <= 0 || t->c_begin < 0 || t->c_begin + t->c_count > t->C) return DKT_E_INVALID;
+    return 0;
+}
+
+static int check_vec4(const dkt_tensor* t) {
+    if ((t->C % 4) || (t->c_begin % 4) || (t->c_count % 4)) return DKT_E_ALIGNMENT;
+    if ((reinterpret_cast<uintptr_t>(t->f32) & 15) || (reinterpret_cast<uintptr_t>(t->hi) & 7) ||
+        (reinterpret_cast<uintptr_t>(t->lo) & 7))
+        return DKT_E_ALIGNMENT;
+    return 0;
+}
+
+extern "C" int dkt_pool2x(const dkt_tensor* src, const dkt_tensor* dst, int B, int Hs, int Ws, int Hd, int Wd,
+                          void* stream) {
+    int rc;
+    if ((rc = check_slice(src, true)) || (rc = check_slice(dst, false))) return rc;
+    if ((rc = check_vec4(src)) || (rc = check_vec4(dst))) return rc;
+    DKT_CHECK_ARG(B > 0 && Hs > 0 && Ws > 0);
+    DKT_CHECK_ARG(src->c_count == dst->c_count);
+    DKT_CHECK_ARG(Hd == (Hs - 1) / 2 + 1 && Wd == (Ws - 1) / 2 + 1);
+    const int C4 = src->c_count / 4;
+    const int64_t total = (int64_t)B * Hd * Wd * C4;
+    pool2x_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        src->f32, src->C, src->c_begin, *dst, C4, Hs, Ws, Hd, Wd, total);
+    DKT_RETURN_LAST();
+}
+
+extern "C" int dkt_interp(const dkt_tensor* src, const dkt_tensor* dst, int B, int Hs, int Ws, int Hd, int Wd,
+                          void* stream) {
+    int rc;
+    if ((rc = check_slice(src, true)) || (rc = check_slice(dst, false))) return rc;
+    if ((rc = check_vec4(src)) || (rc = check_vec4(dst))) return rc;
+    DKT_CHECK_ARG(B > 0 && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0);
+    DKT_CHECK_ARG(src->c_count == dst->c_count);
+    const int C4 = src->c_count / 4;
+    const int64_t total = (int64_t)B * Hd * Wd * C4;
+    const float sy = Hd > 1 ? (float)(Hs - 1) / (float)(Hd - 1) : 0.f;
+    const float sx = Wd > 1 ? (float)(Ws - 1) / (float)(Wd - 1) : 0.f;
+    interp_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        src->f32, src->C, src->c_begin, *dst, C4, Hs, Ws, Hd, Wd, sy, sx, total);
+    DKT_RETURN_LAST();
+}
+
+extern "C" int dkt_convex_upsample(const float* flow, int flow_C, const float* mask, float* out,
+                                   int B, int H, int W, int factor, void* stream) {
+    DKT_CHECK_ARG(flow && mask && out && flow_C > 0);
+    DKT_CHECK_ARG(B > 0 && H > 0 && W > 0 && factor > 0);
+    const int64_t total = (int64_t)B * H * W * factor * factor;
+    convex_upsample_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        flow, flow_C, mask, out, H, W, factor, total);
+    DKT_RETURN_LAST();
+}
+
+extern "C" int dkt_context_upsample(const float* disp, const float* weights, float* out, float in_scale,
+                                    float out_scale, int B, int H, int W, void* stream) {
+    DKT_CHECK_ARG(disp && weights && out);
+    DKT_CHECK_ARG(B > 0 && H > 0 && W > 0);
+    const int64_t total = (int64_t)B * H * W * 16;
+    context_upsample_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        disp, weights, out, in_scale, out_scale, H, W, total);
+    DKT_RETURN_LAST();
+}
+
+static int launch_to_nhwc(const float* src, int64_t sb, int64_t sc, int64_t sh, int64_t sw, const float* bias,
+                          const dkt_tensor& dst, int B, int C, int H, int W, void* stream) {
+    if ((int64_t)B * H > 65535) return DKT_E_UNSUPPORTED;
+    dim3 grid(ceil_div(W, 32), ceil_div(C, 32), B * H);
+    to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, sb, sc, sh, sw, bias, dst, C, H, W);
+    DKT_RETURN_LAST();
+}
+
+extern "C" int dkt_nchw_to_nhwc(const float* src, const float* bias, const dkt_tensor* dst, int B, int C, int H,
+                                int W, void* stream) {
+    DKT_CHECK_ARG(src);
+    int rc = check_slice(dst, false);
+    if (rc) return rc;
+    DKT_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && dst->c_count == C);
+    return launch_to_nhwc(src, (int64_t)C * H * W, (int64_t)H * W, W, 1, bias, *dst, B, C, H, W, stream);
+}
+
+extern "C" int dkt_nhwc_to_nchw(const dkt_tensor* src, float* dst, int B, int C, int H, int W, void* stream) {
+    DKT_CHECK_ARG(dst);
+    int rc = check_slice(src, true);
+    if (rc) return rc;
+    DKT_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && src->c_count == C);
+    if ((int64_t)B * H > 65535) return DKT_E_UNSUPPORTED;
+    dim3 grid(ceil_div(W, 32), ceil_div(C, 32), B * H);
+    to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src->f32, src->C, src->c_begin, dst, C, H, W);
+    DKT_RETURN_LAST();
+}
+
+extern "C" int dkt_split_nchw_to_nhwc_bf16x2(const float* src, int64_t sb, int64_t sd, int64_t sh, int64_t sw,
+                                             uint16_t* hi, uint16_t* lo, int B, int D, int H, int W,
+                                             void* stream) {
+    DKT_CHECK_ARG(src && hi && lo);
+    DKT_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0);
+    dkt_tensor dst{nullptr, hi, lo, D, 0, D};
+    return launch_to_nhwc(src, sb, sd, sh, sw, nullptr, dst, B, D, H, W, stream);
+}

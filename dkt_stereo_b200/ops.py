@@ -1,0 +1,250 @@
+"""Functional wrappers over the C ABI (one Python function per entry point family).
+
+Tensors are NHWC unless a wrapper says otherwise.  ``impl`` selects between the two CUDA
+implementations that exist for the GEMM-shaped kernels: ``"tc"`` (tcgen05 tensor cores,
+3-term bf16 split) and ``"simt"`` (exact fp32 CUDA cores).  Neither is a CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from ._lib import DktEpilogue, DktTensor, tensor_slice, null_tensor
+
+
+def split_bf16(x: torch.Tensor):
+    """x (fp32) -> (hi, lo) bf16 with hi + lo ~= x to 16 mantissa bits (same rule as csrc/common.cuh)."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+# ---------------------------------------------------------------------------------------------
+# K1
+# ---------------------------------------------------------------------------------------------
+def pyramid_widths(w2: int, levels: int) -> List[int]:
+    out = []
+    for _ in range(levels):
+        out.append(w2)
+        w2 //= 2
+    return out
+
+
+def alloc_pyramid(B: int, H: int, W1: int, W2: int, levels: int, device) -> List[torch.Tensor]:
+    return [torch.empty(B, H, W1, w, device=device, dtype=torch.float32) for w in pyramid_widths(W2, levels)]
+
+
+def corr1d_build(fmap1: torch.Tensor, fmap2: torch.Tensor, levels: int, scale: float,
+                 impl: str = "tc", pyr: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
+    """fmap (B,D,H,W) fp32 logical NCHW with any strides -> pyramid [(B,H,W1,W2>>l)]."""
+    L.require_device(fmap1)
+    lib = L.load()
+    assert fmap1.dtype == torch.float32 and fmap2.dtype == torch.float32
+    B, D, H, W1 = fmap1.shape
+    W2 = fmap2.shape[3]
+    if fmap2.stride() != fmap1.stride():
+        fmap2 = fmap2.contiguous()
+        fmap1 = fmap1.contiguous()
+    if pyr is None:
+        pyr = alloc_pyramid(B, H, W1, W2, levels, fmap1.device)
+    ptrs = L.pointer_array(pyr)
+    sb, sd, sh, sw = fmap1.stride()
+    if impl == "tc" and D % 64 == 0 and W2 % 16 == 0 and W2 <= 256:
+        hi1 = torch.empty(B, H, W1, D, device=fmap1.device, dtype=torch.bfloat16)
+        lo1, hi2, lo2 = torch.empty_like(hi1), torch.empty(B, H, W2, D, device=fmap1.device, dtype=torch.bfloat16), None
+        lo2 = torch.empty_like(hi2)
+        s = L.stream_ptr()
+        L.check(lib.dkt_split_nchw_to_nhwc_bf16x2(fmap1.data_ptr(), sb, sd, sh, sw, hi1.data_ptr(), lo1.data_ptr(),
+                                                  B, D, H, W1, s), "split fmap1")
+        L.check(lib.dkt_split_nchw_to_nhwc_bf16x2(fmap2.data_ptr(), sb, sd, sh, sw, hi2.data_ptr(), lo2.data_ptr(),
+                                                  B, D, H, W2, s), "split fmap2")
+        L.check(lib.dkt_corr1d_build_tc(hi1.data_ptr(), lo1.data_ptr(), hi2.data_ptr(), lo2.data_ptr(), ptrs,
+                                        B, D, H, W1, W2, levels, float(scale), s), "corr1d_build_tc")
+    else:
+        L.check(lib.dkt_corr1d_build_f32(fmap1.data_ptr(), fmap2.data_ptr(), sb, sd, sh, sw, ptrs,
+                                         B, D, H, W1, W2, levels, float(scale), L.stream_ptr()), "corr1d_build_f32")
+    return pyr
+
+
+# ---------------------------------------------------------------------------------------------
+# K2
+# ---------------------------------------------------------------------------------------------
+def corr1d_lookup(pyr: Sequence[torch.Tensor], coords_x: torch.Tensor, radius: int,
+                  out: Optional[torch.Tensor], out_layout: str = "nhwc",
+                  out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None,
+                  delta: Optional[torch.Tensor] = None, flow: Optional[torch.Tensor] = None) -> None:
+    """coords_x (B,H,W) fp32, updated in place by delta[...,0] when given.  out: NHWC (B,H,W,Cpad)
+    or NCHW (B,C,H,W); None -> only the coordinate / flow bookkeeping runs."""
+    lib = L.load()
+    L.require_device(coords_x)
+    B, H, W1 = coords_x.shape
+    levels = len(pyr) if out is not None else 0
+    W2 = pyr[0].shape[-1] if levels else 1
+    if out is not None:
+        if out_layout == "nhwc":
+            Cp = out.shape[-1]
+            ob, oc, op = H * W1 * Cp, 1, Cp
+        else:
+            Cc = out.shape[1]
+            ob, oc, op = Cc * H * W1, H * W1, 1
+    else:
+        ob = oc = op = 0
+    ptrs = L.pointer_array(pyr) if levels else None
+    L.check(lib.dkt_corr1d_lookup(ptrs, levels, radius, coords_x.data_ptr(),
+                                  L.ptr(delta), delta.shape[-1] if delta is not None else 0, L.ptr(flow),
+                                  L.ptr(out), L.ptr(out_hi), L.ptr(out_lo), ob, oc, op,
+                                  B, H, W1, W2, L.stream_ptr()), "corr1d_lookup")
+
+
+def geo_pool(gev: torch.Tensor):
+    """(B,C,D,H,W) -> (B,H,W,C,D), (B,H,W,C,D//2)"""
+    lib = L.load()
+    L.require_device(gev)
+    gev = gev.contiguous().float()
+    B, Cc, D, H, W = gev.shape
+    g0 = torch.empty(B, H, W, Cc, D, device=gev.device, dtype=torch.float32)
+    g1 = torch.empty(B, H, W, Cc, D // 2, device=gev.device, dtype=torch.float32)
+    L.check(lib.dkt_geo_pool(gev.data_ptr(), g0.data_ptr(), g1.data_ptr(), B, Cc, D, H, W, L.stream_ptr()), "geo_pool")
+    return g0, g1
+
+
+def geo_lookup(geo: Sequence[torch.Tensor], init: Sequence[torch.Tensor], disp: torch.Tensor, radius: int,
+               out: torch.Tensor, out_layout: str = "nhwc",
+               out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None) -> None:
+    lib = L.load()
+    B, H, W, Cc, D = geo[0].shape
+    if out_layout == "nhwc":
+        Cp = out.shape[-1]
+        ob, oc, op = H * W * Cp, 1, Cp
+    else:
+        ob, oc, op = out.shape[1] * H * W, H * W, 1
+    L.check(lib.dkt_geo_lookup(geo[0].data_ptr(), geo[1].data_ptr(), init[0].data_ptr(), init[1].data_ptr(),
+                               disp.data_ptr(), radius, Cc, D, out.data_ptr(), L.ptr(out_hi), L.ptr(out_lo),
+                               ob, oc, op, B, H, W, L.stream_ptr()), "geo_lookup")
+
+
+# ---------------------------------------------------------------------------------------------
+# K3
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class ConvWeights:
+    """A conv layer repacked for the engine (done once per checkpoint load)."""
+    ksize: int
+    cin: int                 # padded input channels the kernel iterates over
+    n: int                   # real output channels
+    w_simt: torch.Tensor     # fp32 [taps][cin][n]
+    w_hi: Optional[torch.Tensor]   # bf16 [taps][npad][cin]
+    w_lo: Optional[torch.Tensor]
+    bias: Optional[torch.Tensor]   # fp32 [n] (None when folded into a context term)
+
+
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], cin_pad: Optional[int] = None,
+              tc: bool = True, keep_bias: bool = True) -> ConvWeights:
+    """weight (N, Cin, k, k) fp32 (PyTorch OIHW) -> engine layouts.  cin_pad zero-pads the
+    reduction dimension (e.g. 36 correlation channels carried in a 64-channel buffer)."""
+    N, Cin, k, _ = weight.shape
+    w = weight.detach().float()
+    if cin_pad is not None and cin_pad > Cin:
+        w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, cin_pad - Cin))
+        Cin = cin_pad
+    taps = k * k
+    w_tkn = w.permute(2, 3, 1, 0).reshape(taps, Cin, N).contiguous()          # [tap][cin][n]
+    w_hi = w_lo = None
+    if tc:
+        npad = (N + 15) // 16 * 16
+        w_tnk = w.permute(2, 3, 0, 1).reshape(taps, N, Cin)
+        if npad != N:
+            w_tnk = torch.nn.functional.pad(w_tnk, (0, 0, 0, npad - N))
+        w_tnk = w_tnk.contiguous()
+        w_hi, w_lo = split_bf16(w_tnk)
+        w_hi, w_lo = w_hi.contiguous(), w_lo.contiguous()
+    b = bias.detach().float().contiguous() if (bias is not None and keep_bias) else None
+    return ConvWeights(k, Cin, N, w_tkn, w_hi, w_lo, b)
+
+
+def pack_conv_cat(weights: Sequence[torch.Tensor], tc: bool = True) -> ConvWeights:
+    """Stack several convs with identical input along N (convz || convr -> one N=256 GEMM)."""
+    return pack_conv(torch.cat([w.detach() for w in weights], dim=0), None, tc=tc)
+
+
+def make_epilogue(kind: int, out: DktTensor, act: int = L.ACT_NONE, scale: float = 1.0,
+                  bias: Optional[torch.Tensor] = None, ctx: Optional[torch.Tensor] = None, ctx_c0: int = 0,
+                  z: Optional[DktTensor] = None, h: Optional[DktTensor] = None,
+                  tail: Optional[torch.Tensor] = None) -> DktEpilogue:
+    e = DktEpilogue()
+    e.kind, e.act, e.scale = kind, act, scale
+    e.bias = L.ptr(bias)
+    e.ctx = L.ptr(ctx)
+    e.ctx_C = ctx.shape[-1] if ctx is not None else 0
+    e.ctx_c0 = ctx_c0
+    e.out = out
+    e.z = z if z is not None else null_tensor()
+    e.h = h if h is not None else null_tensor()
+    e.tail = L.ptr(tail)
+    e.tail_C = tail.shape[-1] if tail is not None else 0
+    return e
+
+
+def conv2d(srcs: Sequence[DktTensor], w: ConvWeights, epi: DktEpilogue, B: int, H: int, W: int,
+           impl: str = "tc") -> None:
+    lib = L.load()
+    n = len(srcs)
+    arr = (DktTensor * n)(*srcs)
+    cin = sum(s.c_count for s in srcs)
+    assert cin == w.cin, (cin, w.cin)
+    if impl == "tc":
+        L.check(lib.dkt_conv2d_tc(arr, n, w.w_hi.data_ptr(), w.w_lo.data_ptr(), w.ksize, w.n, C.byref(epi),
+                                  B, H, W, L.stream_ptr()), "conv2d_tc")
+    else:
+        L.check(lib.dkt_conv2d_simt(arr, n, w.w_simt.data_ptr(), w.ksize, w.n, C.byref(epi),
+                                    B, H, W, L.stream_ptr()), "conv2d_simt")
+
+
+# ---------------------------------------------------------------------------------------------
+# a8 / K4 / layout
+# ---------------------------------------------------------------------------------------------
+def pool2x(src: DktTensor, dst: DktTensor, B: int, Hs: int, Ws: int) -> None:
+    Hd, Wd = (Hs - 1) // 2 + 1, (Ws - 1) // 2 + 1
+    L.check(L.load().dkt_pool2x(C.byref(src), C.byref(dst), B, Hs, Ws, Hd, Wd, L.stream_ptr()), "pool2x")
+
+
+def interp(src: DktTensor, dst: DktTensor, B: int, Hs: int, Ws: int, Hd: int, Wd: int) -> None:
+    L.check(L.load().dkt_interp(C.byref(src), C.byref(dst), B, Hs, Ws, Hd, Wd, L.stream_ptr()), "interp")
+
+
+def convex_upsample(flow: torch.Tensor, mask: torch.Tensor, factor: int) -> torch.Tensor:
+    """flow NHWC (B,H,W,Cf) (channel 0 used), mask NHWC (B,H,W,9*f*f) -> (B,1,f*H,f*W)."""
+    B, H, W, Cf = flow.shape
+    out = torch.empty(B, 1, H * factor, W * factor, device=flow.device, dtype=torch.float32)
+    L.check(L.load().dkt_convex_upsample(flow.data_ptr(), Cf, mask.data_ptr(), out.data_ptr(), B, H, W, factor,
+                                         L.stream_ptr()), "convex_upsample")
+    return out
+
+
+def context_upsample(disp: torch.Tensor, weights: torch.Tensor, in_scale: float = 4.0,
+                     out_scale: float = 1.0) -> torch.Tensor:
+    """disp (B,H,W) fp32, weights (B,9,4H,4W) NCHW (softmaxed) -> (B,1,4H,4W)."""
+    B, H, W = disp.shape
+    weights = weights.contiguous().float()
+    out = torch.empty(B, 1, 4 * H, 4 * W, device=disp.device, dtype=torch.float32)
+    L.check(L.load().dkt_context_upsample(disp.data_ptr(), weights.data_ptr(), out.data_ptr(), in_scale, out_scale,
+                                          B, H, W, L.stream_ptr()), "context_upsample")
+    return out
+
+
+def nchw_to_nhwc(src: torch.Tensor, dst: DktTensor, bias: Optional[torch.Tensor] = None) -> None:
+    src = src.contiguous().float()
+    B, Cc, H, W = src.shape
+    L.check(L.load().dkt_nchw_to_nhwc(src.data_ptr(), L.ptr(bias), C.byref(dst), B, Cc, H, W, L.stream_ptr()),
+            "nchw_to_nhwc")
+
+
+def nhwc_to_nchw(src: DktTensor, B: int, H: int, W: int, device) -> torch.Tensor:
+    out = torch.empty(B, src.c_count, H, W, device=device, dtype=torch.float32)
+    L.check(L.load().dkt_nhwc_to_nchw(C.byref(src), out.data_ptr(), B, src.c_count, H, W, L.stream_ptr()),
+            "nhwc_to_nchw")
+    return out

@@ -1,0 +1,275 @@
+"""Update block of RAFT-Stereo / IGEV-Stereo served by the B200 kernels.
+
+``BasicMultiUpdateBlock`` below is a *parameter container* with exactly the reference's
+state-dict keys (reference core/update.py:97-113 and meta_arch/igev_stereo/update.py:104-119),
+so DKT checkpoints load unchanged.  The arithmetic of ``forward`` (reference core/update.py:115-138)
+is executed by ``UpdateEngine``: NHWC buffers resident in HBM for the whole GRU loop and a fixed
+sequence of fused kernels per iteration ("Data layout" and "Iteration schedule").
+
+Channel-concatenations of the reference (``torch.cat``) never materialise: producers write
+directly into channel slices of the per-scale buffers
+
+    X0 = [ h0 | motion(126)+flow(2) | up(h1) ]   384 ch   (gru08 input "hx")
+    X1 = [ h1 | pool(h0)            | up(h2) ]   384 ch   (gru16)
+    X2 = [ h2 | pool(h1)                     ]   256 ch   (gru32)
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from ._lib import tensor_slice as TS
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter containers (names == reference)
+# ---------------------------------------------------------------------------------------------
+class _Head(nn.Module):
+    def __init__(self, input_dim=128, hidden_dim=256, output_dim=2):
+        super().__init__()
+        self.conv1 = nn.Conv2d(input_dim, hidden_dim, 3, padding=1)
+        self.conv2 = nn.Conv2d(hidden_dim, output_dim, 3, padding=1)
+
+
+class ConvGRU(nn.Module):
+    def __init__(self, hidden_dim, input_dim, kernel_size=3):
+        super().__init__()
+        for n in ("convz", "convr", "convq"):
+            setattr(self, n, nn.Conv2d(hidden_dim + input_dim, hidden_dim, kernel_size, padding=kernel_size // 2))
+
+
+class BasicMotionEncoder(nn.Module):
+    def __init__(self, args, igev: bool):
+        super().__init__()
+        taps = 2 * args.corr_radius + 1
+        cor_planes = args.corr_levels * taps * (9 if igev else 1)
+        stem = ("convd1", "convd2") if igev else ("convf1", "convf2")
+        nflow = 1 if igev else 2
+        self.convc1 = nn.Conv2d(cor_planes, 64, 1)
+        self.convc2 = nn.Conv2d(64, 64, 3, padding=1)
+        setattr(self, stem[0], nn.Conv2d(nflow, 64, 7, padding=3))
+        setattr(self, stem[1], nn.Conv2d(64, 64, 3, padding=1))
+        self.conv = nn.Conv2d(128, 128 - nflow, 3, padding=1)
+
+
+class BasicMultiUpdateBlock(nn.Module):
+    """Same parameters as the reference block; forward runs on the engine."""
+
+    def __init__(self, args, hidden_dims: Sequence[int] = (), igev: bool = False):
+        super().__init__()
+        self.args = args
+        self.igev = igev
+        hd = list(hidden_dims)
+        assert hd == [128, 128, 128] and args.n_gru_layers == 3, \
+            "the B200 engine is built for the shipped configs (3 GRU levels, 128 hidden channels)"
+        self.encoder = BasicMotionEncoder(args, igev)
+        names = ("gru04", "gru08", "gru16") if igev else ("gru08", "gru16", "gru32")
+        setattr(self, names[0], ConvGRU(hd[2], 128 + hd[1]))
+        setattr(self, names[1], ConvGRU(hd[1], hd[0] + hd[2]))
+        setattr(self, names[2], ConvGRU(hd[0], hd[1]))
+        self.gru_names = names
+        if igev:
+            self.disp_head = _Head(hd[2], 256, 1)
+            self.mask_feat_4 = nn.Sequential(nn.Conv2d(hd[2], 32, 3, padding=1), nn.ReLU(inplace=True))
+        else:
+            self.flow_head = _Head(hd[2], 256, 2)
+            factor = 2 ** args.n_downsample
+            self.mask = nn.Sequential(nn.Conv2d(hd[2], 256, 3, padding=1), nn.ReLU(inplace=True),
+                                      nn.Conv2d(256, factor ** 2 * 9, 1, padding=0))
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("BasicMultiUpdateBlock.forward is executed by UpdateEngine (B200 kernels); "
+                           "there is no PyTorch fallback")
+
+
+# ---------------------------------------------------------------------------------------------
+# engine
+# ---------------------------------------------------------------------------------------------
+def _pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+class UpdateEngine:
+    """Holds packed weights + per-shape activation buffers and runs update-block iterations."""
+
+    def __init__(self, block: BasicMultiUpdateBlock, impl: str = "tc"):
+        assert impl in ("tc", "simt")
+        self.block = block
+        self.impl = impl
+        self.igev = block.igev
+        self.weights: Optional[Dict[str, ops.ConvWeights]] = None
+        self._wsig = None
+        self.shape = None
+
+    # ---- weights -------------------------------------------------------------------------------
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.block.parameters())
+
+    def pack_weights(self) -> None:
+        sig = self._signature()
+        if self.weights is not None and sig == self._wsig:
+            return
+        b, tc = self.block, self.impl == "tc"
+        enc = b.encoder
+        w: Dict[str, ops.ConvWeights] = {}
+        self.corr_planes = enc.convc1.in_channels
+        self.corr_pad = _pad64(self.corr_planes)
+        w["convc1"] = ops.pack_conv(enc.convc1.weight, enc.convc1.bias, cin_pad=self.corr_pad, tc=tc)
+        w["convc2"] = ops.pack_conv(enc.convc2.weight, enc.convc2.bias, tc=tc)
+        stem1 = enc.convd1 if self.igev else enc.convf1
+        stem2 = enc.convd2 if self.igev else enc.convf2
+        w["stem1"] = ops.pack_conv(stem1.weight, stem1.bias, tc=False)           # 7x7, 1-2 input ch: CUDA cores
+        w["stem2"] = ops.pack_conv(stem2.weight, stem2.bias, tc=tc)
+        w["conv"] = ops.pack_conv(enc.conv.weight, enc.conv.bias, tc=tc)
+        self.gru_bias = []
+        for i, name in enumerate(b.gru_names):
+            g = getattr(b, name)
+            w[f"zr{i}"] = ops.pack_conv_cat([g.convz.weight, g.convr.weight], tc=tc)
+            w[f"q{i}"] = ops.pack_conv(g.convq.weight, None, tc=tc)
+            self.gru_bias.append(torch.cat([g.convz.bias, g.convr.bias, g.convq.bias]).detach().float().contiguous())
+        head = b.disp_head if self.igev else b.flow_head
+        w["head1"] = ops.pack_conv(head.conv1.weight, head.conv1.bias, tc=tc)
+        w["head2"] = ops.pack_conv(head.conv2.weight, head.conv2.bias, tc=tc)
+        if self.igev:
+            w["mask0"] = ops.pack_conv(b.mask_feat_4[0].weight, b.mask_feat_4[0].bias, tc=tc)
+        else:
+            w["mask0"] = ops.pack_conv(b.mask[0].weight, b.mask[0].bias, tc=tc)
+            w["mask2"] = ops.pack_conv(b.mask[2].weight, b.mask[2].bias, tc=tc)
+        self.weights, self._wsig = w, sig
+
+    # ---- buffers -------------------------------------------------------------------------------
+    def _buf(self, B, H, W, Cc, f32=True, split=None):
+        split = (self.impl == "tc") if split is None else split
+        dev = self.device
+        d = {"C": Cc, "f32": None, "hi": None, "lo": None}
+        if f32:
+            d["f32"] = torch.zeros(B, H, W, Cc, device=dev, dtype=torch.float32)
+        if split:
+            d["hi"] = torch.zeros(B, H, W, Cc, device=dev, dtype=torch.bfloat16)
+            d["lo"] = torch.zeros(B, H, W, Cc, device=dev, dtype=torch.bfloat16)
+        return d
+
+    @staticmethod
+    def _slice(buf, c0=0, cnt=None, f32=True, split=True):
+        return TS(buf["f32"] if f32 else None, buf["hi"] if split else None, buf["lo"] if split else None, c0, cnt)
+
+    def allocate(self, B: int, h: int, w: int, device) -> None:
+        shape = (B, h, w, str(device))
+        if self.shape == shape:
+            return
+        self.device = device
+        self.B = B
+        self.hw = [(h, w)]
+        for _ in range(2):
+            ph, pw = self.hw[-1]
+            self.hw.append(((ph - 1) // 2 + 1, (pw - 1) // 2 + 1))
+        (h0, w0), (h1, w1), (h2, w2) = self.hw
+        simt = self.impl == "simt"
+        nflow = 1 if self.igev else 2
+        self.nflow = nflow
+        # in "tc" mode fp32 copies are only kept where an elementwise consumer needs them
+        self.X = [self._buf(B, h0, w0, 384), self._buf(B, h1, w1, 384), self._buf(B, h2, w2, 256)]
+        self.RH = [self._buf(B, *self.hw[i], 128, f32=simt) for i in range(3)]
+        self.Z = [self._buf(B, *self.hw[i], 128, split=False) for i in range(3)]
+        self.CTX = [self._buf(B, *self.hw[i], 384, split=False) for i in range(3)]
+        self.CORR = self._buf(B, h0, w0, self.corr_pad)
+        self.COR1 = self._buf(B, h0, w0, 64, f32=simt)
+        self.FLO1 = self._buf(B, h0, w0, 64, f32=simt)
+        self.CF = self._buf(B, h0, w0, 128, f32=simt)
+        self.FH = self._buf(B, h0, w0, 256, f32=simt)
+        self.FLOW = self._buf(B, h0, w0, nflow, split=False)     # flow (x,y) or disparity
+        self.DELTA = self._buf(B, h0, w0, nflow, split=False)
+        self.MH = self._buf(B, h0, w0, 256 if not self.igev else 32, f32=True)
+        if not self.igev:
+            factor = 2 ** self.block.args.n_downsample
+            self.MASK = self._buf(B, h0, w0, 9 * factor * factor, split=False)
+        self.coords_x = torch.zeros(B, h0, w0, device=device, dtype=torch.float32)
+        self.shape = shape
+
+    # ---- per-forward state ---------------------------------------------------------------------
+    def load_state(self, net_list: Sequence[torch.Tensor], inp_list: Sequence[Sequence[torch.Tensor]]) -> None:
+        """net_list[i] (B,128,h_i,w_i) NCHW hidden states, inp_list[i] = (cz,cr,cq) NCHW context
+        terms (reference raft_stereo.py:110-114).  Conv biases of the gates are folded into the
+        context term once here."""
+        split = self.impl == "tc"
+        for i in range(3):
+            ops.nchw_to_nhwc(net_list[i], self._slice(self.X[i], 0, 128, True, split))
+            ctx = inp_list[i]
+            ctx = ctx if torch.is_tensor(ctx) else torch.cat(list(ctx), dim=1)
+            ops.nchw_to_nhwc(ctx, self._slice(self.CTX[i], 0, 384, True, False), bias=self.gru_bias[i])
+        self.DELTA["f32"].zero_()
+
+    def hidden_states(self) -> List[torch.Tensor]:
+        return [ops.nhwc_to_nchw(self._slice(self.X[i], 0, 128, True, False), self.B, *self.hw[i], self.device)
+                for i in range(3)]
+
+    # ---- one GRU ---------------------------------------------------------------------------------
+    def _gru(self, i: int, x_cnt: int) -> None:
+        """ConvGRU at scale i on X[i] = [h | x]; reference core/update.py:23-32."""
+        B, (H, W), impl, split, simt = self.B, self.hw[i], self.impl, self.impl == "tc", self.impl == "simt"
+        X, RH, Z, CTX = self.X[i], self.RH[i], self.Z[i], self.CTX[i]
+        hx = self._slice(X, 0, 128 + x_cnt, simt, split)
+        h = self._slice(X, 0, 128, True, False)
+        z = self._slice(Z, 0, 128, True, False)
+        e = ops.make_epilogue(L.EPI_GRU_ZR, out=self._slice(RH, 0, 128, simt, split), ctx=CTX["f32"], ctx_c0=0, z=z, h=h)
+        ops.conv2d([hx], self.weights[f"zr{i}"], e, B, H, W, impl)
+        e = ops.make_epilogue(L.EPI_GRU_Q, out=self._slice(X, 0, 128, True, split), ctx=CTX["f32"], ctx_c0=256, z=z, h=h)
+        ops.conv2d([self._slice(RH, 0, 128, simt, split), self._slice(X, 128, x_cnt, simt, split)],
+                   self.weights[f"q{i}"], e, B, H, W, impl)
+
+    # ---- one update-block call (reference core/update.py:115-138) -------------------------------
+    def step(self, lookup, with_mask: bool = False) -> None:
+        """lookup(engine) must fill self.CORR (and FLOW / coords bookkeeping) for this iteration."""
+        B, impl, split, simt = self.B, self.impl, self.impl == "tc", self.impl == "simt"
+        (h0, w0), (h1, w1), (h2, w2) = self.hw
+        X0, X1, X2 = self.X
+        Wt = self.weights
+        S = self._slice
+        # coarse -> fine; every GRU sees the OLD finer state pooled and the NEW coarser state upsampled
+        ops.pool2x(S(X1, 0, 128, True, False), S(X2, 128, 128, simt, split), B, h1, w1)
+        self._gru(2, 128)
+        ops.pool2x(S(X0, 0, 128, True, False), S(X1, 128, 128, simt, split), B, h0, w0)
+        ops.interp(S(X2, 0, 128, True, False), S(X1, 256, 128, simt, split), B, h2, w2, h1, w1)
+        self._gru(1, 256)
+        # motion encoder (reference core/update.py:77-85)
+        lookup(self)
+        E = ops.make_epilogue
+        ops.conv2d([S(self.CORR, 0, self.corr_pad, simt, split)], Wt["convc1"],
+                   E(L.EPI_LINEAR, S(self.COR1, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["convc1"].bias), B, h0, w0, impl)
+        ops.conv2d([S(self.COR1, 0, 64, simt, split)], Wt["convc2"],
+                   E(L.EPI_LINEAR, S(self.CF, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["convc2"].bias), B, h0, w0, impl)
+        ops.conv2d([S(self.FLOW, 0, self.nflow, True, False)], Wt["stem1"],
+                   E(L.EPI_LINEAR, S(self.FLO1, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["stem1"].bias), B, h0, w0, "simt")
+        ops.conv2d([S(self.FLO1, 0, 64, simt, split)], Wt["stem2"],
+                   E(L.EPI_LINEAR, S(self.CF, 64, 64, simt, split), act=L.ACT_RELU, bias=Wt["stem2"].bias), B, h0, w0, impl)
+        ops.conv2d([S(self.CF, 0, 128, simt, split)], Wt["conv"],
+                   E(L.EPI_LINEAR, S(X0, 128, 128, simt, split), act=L.ACT_RELU, bias=Wt["conv"].bias,
+                     tail=self.FLOW["f32"]), B, h0, w0, impl)
+        ops.interp(S(X1, 0, 128, True, False), S(X0, 256, 128, simt, split), B, h1, w1, h0, w0)
+        self._gru(0, 256)
+        # flow / disparity head (reference core/update.py:13-14)
+        ops.conv2d([S(X0, 0, 128, simt, split)], Wt["head1"],
+                   E(L.EPI_LINEAR, S(self.FH, 0, 256, simt, split), act=L.ACT_RELU, bias=Wt["head1"].bias), B, h0, w0, impl)
+        ops.conv2d([S(self.FH, 0, 256, simt, split)], Wt["head2"],
+                   E(L.EPI_LINEAR, S(self.DELTA, 0, self.nflow, True, False), bias=Wt["head2"].bias), B, h0, w0, impl)
+        if with_mask:
+            self.mask_head()
+
+    def mask_head(self) -> None:
+        """reference core/update.py:110-113,137 (RAFT) / igev update.py:117-119,141 (IGEV)."""
+        B, impl, split, simt = self.B, self.impl, self.impl == "tc", self.impl == "simt"
+        h0, w0 = self.hw[0]
+        S, E, Wt = self._slice, ops.make_epilogue, self.weights
+        if self.igev:
+            ops.conv2d([S(self.X[0], 0, 128, simt, split)], Wt["mask0"],
+                       E(L.EPI_LINEAR, S(self.MH, 0, 32, True, False), act=L.ACT_RELU, bias=Wt["mask0"].bias), B, h0, w0, impl)
+        else:
+            ops.conv2d([S(self.X[0], 0, 128, simt, split)], Wt["mask0"],
+                       E(L.EPI_LINEAR, S(self.MH, 0, 256, True, split), act=L.ACT_RELU, bias=Wt["mask0"].bias), B, h0, w0, impl)
+            ops.conv2d([S(self.MH, 0, 256, simt, split)], Wt["mask2"],
+                       E(L.EPI_LINEAR, S(self.MASK, 0, self.MASK["C"], True, False), scale=0.25, bias=Wt["mask2"].bias),
+                       B, h0, w0, impl)

@@ -1,0 +1,186 @@
+/*
+ * dkt_stereo_b200.h -- C ABI of the B200-native stereo hot path (libdkt_stereo_b200.so).
+ *
+ * This is the drop-in boundary for the ONE path this repository accelerates: the
+ * correlation-volume build + indexed lookup and the ConvGRU disparity-update loop of
+ * RAFT-Stereo / IGEV-Stereo as shipped in jiaw-z/DKT-Stereo.  The reference has no native
+ * source of its own; the closest thing it has to an operator ABI is the optional, un-vendored
+ * `corr_sampler` extension (reference core/corr.py:17-29,49).  Each entry point below names the
+ * reference code it replaces (paths relative to the reference checkout).
+ *
+ * Conventions (all entry points):
+ *   - plain C: raw DEVICE pointers + sizes, no framework types.  The caller owns every
+ *     buffer (inputs, outputs, workspace); the library allocates nothing persistent and keeps
+ *     no global state, so calls are thread-safe per stream and CUDA-graph capturable.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised.
+ *   - return value: 0 = ok, < 0 = invalid argument (DKT_E_*), > 0 = a cudaError_t.
+ *   - "NHWC" buffers are (B, H, W, C) fp32 / bf16 with C contiguous.  Activations on the
+ *     tensor-core path are carried as a bf16 (hi, lo) pair with hi + lo ~= x to 16 mantissa
+ *     bits; products are accumulated in fp32 as hi*hi + lo*hi + hi*lo (3-term split), which is
+ *     what keeps the 32-iteration recurrence within 1e-3 px of the fp32 reference.
+ *   - bf16 values are passed as uint16_t.
+ */
+#ifndef DKT_STEREO_B200_H
+#define DKT_STEREO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DKT_ABI_VERSION 1
+
+/* negative return codes */
+#define DKT_E_INVALID     (-1)  /* null pointer / bad dimension */
+#define DKT_E_UNSUPPORTED (-2)  /* shape outside what the kernels were built for */
+#define DKT_E_ALIGNMENT   (-3)  /* pointer or channel count not aligned as required */
+#define DKT_E_DRIVER      (-4)  /* cuTensorMapEncodeTiled unavailable / failed */
+
+#define DKT_MAX_LEVELS 4
+#define DKT_MAX_SRCS   3
+
+/* activation codes */
+#define DKT_ACT_NONE    0
+#define DKT_ACT_RELU    1
+#define DKT_ACT_SIGMOID 2
+#define DKT_ACT_TANH    3
+
+/* epilogue kinds of dkt_conv2d_* */
+#define DKT_EPI_LINEAR 0  /* y = scale * act(acc + bias[n] + ctx[p][n])                          */
+#define DKT_EPI_GRU_ZR 1  /* n <  N/2: z = sigmoid(acc + ctx) -> z ; n >= N/2: r = sigmoid(..),
+                             (r*h) -> out           (reference core/update.py:27-28,29 first half) */
+#define DKT_EPI_GRU_Q  2  /* q = tanh(acc + ctx); h' = (1-z)*h + z*q -> out (h may alias out)
+                             (reference core/update.py:29-31)                                     */
+
+/* One NHWC activation tensor, optionally in several precisions.  Null members are skipped
+ * by writers; readers document which member they need. */
+typedef struct dkt_tensor {
+    float*    f32;      /* fp32 values                                   */
+    uint16_t* hi;       /* bf16 high part  (tensor-core path)            */
+    uint16_t* lo;       /* bf16 low part   (tensor-core path)            */
+    int32_t   C;        /* channels per pixel in the buffer (the stride) */
+    int32_t   c_begin;  /* first channel of the slice used               */
+    int32_t   c_count;  /* number of channels in the slice               */
+} dkt_tensor;
+
+/* Fused epilogue description for the conv kernels. */
+typedef struct dkt_epilogue {
+    int32_t      kind;      /* DKT_EPI_*                                                       */
+    int32_t      act;       /* DKT_ACT_* (LINEAR only)                                         */
+    float        scale;     /* output multiplier applied after the activation (LINEAR only)    */
+    const float* bias;      /* [N] or NULL                                                     */
+    const float* ctx;       /* per-pixel additive term, NHWC fp32, or NULL                     */
+    int32_t      ctx_C;     /* channel stride of ctx                                           */
+    int32_t      ctx_c0;    /* channel of ctx that lines up with output channel 0              */
+    dkt_tensor   out;       /* destination slice (LINEAR: N channels; GRU_ZR: r*h, N/2; GRU_Q: h', N) */
+    dkt_tensor   z;         /* GRU_ZR: written (f32 only, N/2 ch).  GRU_Q: read                */
+    dkt_tensor   h;         /* GRU_ZR / GRU_Q: hidden state read (f32)                         */
+    const float* tail;      /* LINEAR: optional NHWC fp32 source copied into channels          */
+    int32_t      tail_C;    /*   [N_valid, N_valid+tail_C) of `out` (motion features ++ flow,  */
+                            /*   reference core/update.py:85).                                 */
+} dkt_epilogue;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int         dkt_abi_version(void);
+const char* dkt_error_string(int code);
+/* 1 if the running device is sm_100 (tcgen05/TMA paths usable), 0 otherwise, <0 on error. */
+int         dkt_device_supported(int device);
+
+/* ---- K1: all-pairs 1-D correlation volume + W2 pyramid -----------------------------------
+ * Replaces CorrBlock1D.corr + the avg_pool2d pyramid (reference core/corr.py:111-125,148-156)
+ * and, with scale = 1, Combined_Geo_Encoding_Volume.corr + its init_corr pyramid (reference
+ * meta_arch/igev_stereo/geometry.py:14-29,61-69).
+ *   fmap1/fmap2 : fp32, element (b,d,y,x) at b*sb + d*sd + y*sh + x*sw (elements); any of
+ *                 NCHW or channels_last is expressible.
+ *   pyr[l]      : fp32 (B,H,W1,W2>>l) contiguous, l < levels <= DKT_MAX_LEVELS; level l is the
+ *                 pairwise average of level l-1 (an odd tail element is dropped).
+ *   scale       : multiplier applied to the dot product (1/sqrt(D) for RAFT-Stereo). */
+int dkt_corr1d_build_f32(const float* fmap1, const float* fmap2,
+                         int64_t sb, int64_t sd, int64_t sh, int64_t sw,
+                         float* const* pyr, int B, int D, int H, int W1, int W2,
+                         int levels, float scale, void* stream);
+
+/* Tensor-core (tcgen05, 3-term bf16 split, TMA-staged) variant of the above.  Inputs are the
+ * feature maps already split to NHWC bf16 (hi, lo) pairs, (B,H,W,D) with D % 64 == 0 -- use
+ * dkt_split_nchw_to_nhwc_bf16x2 to produce them from the extractor's fp32 output. */
+int dkt_corr1d_build_tc(const uint16_t* f1_hi, const uint16_t* f1_lo,
+                        const uint16_t* f2_hi, const uint16_t* f2_lo,
+                        float* const* pyr, int B, int D, int H, int W1, int W2,
+                        int levels, float scale, void* stream);
+
+/* ---- K2: indexed multi-level lookup, fused with the coordinate update ---------------------
+ * Replaces CorrBlock1D.__call__ + bilinear_sampler (reference core/corr.py:127-146,
+ * core/utils/utils.py:59-74) and the corr_sampler.forward plugin (core/corr.py:22), plus the
+ * loop bookkeeping `delta_flow[:,1]=0; coords1 += delta_flow; flow = coords1 - coords0`
+ * (reference meta_arch/raft_stereo/raft_stereo.py:154-155,164-167).
+ *   coords_x : (B,H,W) fp32 current x coordinate; updated in place when delta != NULL
+ *   delta    : NULL, or the NHWC (B,H,W,delta_C) output of the flow head; channel 0 is added
+ *   flow     : NULL, or NHWC (B,H,W,2) fp32: receives (coords_x - x, flow_y unchanged = kept)
+ *   out      : level-major taps, channel = l*(2r+1)+k, element (b,c,p) at b*ob + c*oc + p*op
+ *              (NCHW: ob=C*H*W, oc=H*W, op=1; NHWC with padding: ob=H*W*Cp, oc=1, op=Cp).
+ *   out_hi/lo: optional bf16 split of the same values with the same strides (may be NULL). */
+int dkt_corr1d_lookup(const float* const* pyr, int levels, int radius,
+                      float* coords_x, const float* delta, int delta_C, float* flow,
+                      float* out, uint16_t* out_hi, uint16_t* out_lo,
+                      int64_t ob, int64_t oc, int64_t op,
+                      int B, int H, int W1, int W2, void* stream);
+
+/* ---- IGEV: geometry-encoding-volume pyramid + combined lookup ------------------------------
+ * dkt_geo_pool: (B,C,D,H,W) fp32 -> level 0 (B,H,W,C,D) and level 1 (B,H,W,C,D/2)
+ *   (reference meta_arch/igev_stereo/geometry.py:17-26; levels == 2 as in configs/igev_stereo).
+ * dkt_geo_lookup: reference geometry.py:34-58 -> per level [C*(2r+1) geo taps, (2r+1) init taps]. */
+int dkt_geo_pool(const float* gev, float* geo0, float* geo1, int B, int C, int D, int H, int W, void* stream);
+int dkt_geo_lookup(const float* geo0, const float* geo1, const float* init0, const float* init1,
+                   const float* disp, int radius, int C, int D,
+                   float* out, uint16_t* out_hi, uint16_t* out_lo,
+                   int64_t ob, int64_t oc, int64_t op,
+                   int B, int H, int W, void* stream);
+
+/* ---- K3: convolutions of the update block with fused epilogues ------------------------------
+ * Replaces nn.Conv2d + bias + activation + the GRU gate algebra of reference core/update.py
+ * (FlowHead :6-14, ConvGRU :16-32, BasicMotionEncoder :64-85, mask head :110-113) and the IGEV
+ * twins in meta_arch/igev_stereo/update.py.
+ * Input  = channel-concatenation of `nsrc` NHWC slices (all B x H x W), stride 1, pad ksize/2.
+ * Weight = fp32 [ksize*ksize][Cin_total][N] (SIMT) or bf16 hi/lo [ksize*ksize][Npad][Cin_total]
+ *          (tensor core; K contiguous, Npad = N rounded up to 16).
+ *   dkt_conv2d_simt : exact fp32 CUDA-core implicit GEMM (any Cin / N); reads src.f32.
+ *   dkt_conv2d_tc   : tcgen05 implicit GEMM, TMA im2col-free tap loads with zero-filled halos,
+ *                     3-term bf16 split; reads src.hi/lo; needs c_begin, c_count % 64 == 0,
+ *                     ksize in {1,3}, N <= 256. */
+int dkt_conv2d_simt(const dkt_tensor* srcs, int nsrc, const float* weight, int ksize, int N,
+                    const dkt_epilogue* epi, int B, int H, int W, void* stream);
+int dkt_conv2d_tc(const dkt_tensor* srcs, int nsrc, const uint16_t* w_hi, const uint16_t* w_lo,
+                  int ksize, int N, const dkt_epilogue* epi, int B, int H, int W, void* stream);
+
+/* ---- a8: cross-scale plumbing of the multi-level GRU -----------------------------------------
+ * dkt_pool2x  : F.avg_pool2d(x,3,stride=2,padding=1), divisor 9 (reference core/update.py:87-88)
+ * dkt_interp  : F.interpolate(bilinear, align_corners=True) (reference core/update.py:93-95)
+ * Both read src.f32 (B,Hs,Ws) and write every non-null member of dst (B,Hd,Wd). */
+int dkt_pool2x(const dkt_tensor* src, const dkt_tensor* dst, int B, int Hs, int Ws, int Hd, int Wd, void* stream);
+int dkt_interp(const dkt_tensor* src, const dkt_tensor* dst, int B, int Hs, int Ws, int Hd, int Wd, void* stream);
+
+/* ---- K4: final upsampling ---------------------------------------------------------------------
+ * dkt_convex_upsample : RAFTStereo.upsample_flow (reference meta_arch/raft_stereo/raft_stereo.py:70-82)
+ *   flow  NHWC (B,H,W,flow_C) fp32, channel 0 is upsampled; mask NHWC (B,H,W,9*f*f) fp32;
+ *   out (B,1,f*H,f*W) fp32.
+ * dkt_context_upsample : IGEV context_upsample (reference meta_arch/igev_stereo/submodule.py:242-254)
+ *   disp (B,H,W) fp32, weights (B,9,4H,4W) fp32 NCHW -> out (B,4H,4W), out = out_scale * sum. */
+int dkt_convex_upsample(const float* flow, int flow_C, const float* mask, float* out,
+                        int B, int H, int W, int factor, void* stream);
+int dkt_context_upsample(const float* disp, const float* weights, float* out, float in_scale, float out_scale,
+                         int B, int H, int W, void* stream);
+
+/* ---- layout / precision plumbing ---------------------------------------------------------------
+ * dkt_nchw_to_nhwc : fp32 (B,C,H,W) -> every non-null member of dst (NHWC slice), y = x + bias[c].
+ * dkt_nhwc_to_nchw : NHWC slice (f32) -> fp32 (B,C,H,W).
+ * dkt_split_nchw_to_nhwc_bf16x2 : strided fp32 feature map -> NHWC bf16 (hi, lo) for dkt_corr1d_build_tc. */
+int dkt_nchw_to_nhwc(const float* src, const float* bias, const dkt_tensor* dst, int B, int C, int H, int W, void* stream);
+int dkt_nhwc_to_nchw(const dkt_tensor* src, float* dst, int B, int C, int H, int W, void* stream);
+int dkt_split_nchw_to_nhwc_bf16x2(const float* src, int64_t sb, int64_t sd, int64_t sh, int64_t sw,
+                                  uint16_t* hi, uint16_t* lo, int B, int D, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DKT_STEREO_B200_H */

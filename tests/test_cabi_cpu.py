@@ -1,0 +1,58 @@
+"""CPU: the C-ABI library builds for sm_100a, loads without a GPU / libcuda, and exports every
+symbol include/dkt_stereo_b200.h declares.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "dkt_stereo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dkt_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    from dkt_stereo_b200 import _lib
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    # the ctypes table covers the header one to one
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.dkt_abi_version() == 1
+    assert lib.dkt_error_string(-2).decode().startswith("shape or option")
+
+
+def test_struct_layout_matches_header():
+    from dkt_stereo_b200 import _lib
+    # dkt_tensor: 3 pointers + 3 int32 (+4 pad) ; dkt_epilogue as declared
+    assert ctypes.sizeof(_lib.DktTensor) == 40
+    assert _lib.DktEpilogue.out.offset == 40
+    assert ctypes.sizeof(_lib.DktEpilogue) == 40 + 3 * 40 + 16
+
+
+def test_argument_validation_without_gpu():
+    """Invalid arguments are rejected before any CUDA call (so this is safe on a CPU box)."""
+    from dkt_stereo_b200 import _lib
+    lib = _lib.load()
+    assert lib.dkt_corr1d_build_f32(None, None, 0, 0, 0, 0, None, 1, 1, 1, 1, 1, 1, 1.0, None) == -1
+    assert lib.dkt_convex_upsample(None, 2, None, None, 1, 1, 1, 4, None) == -1
+    assert lib.dkt_conv2d_tc(None, 1, None, None, 3, 64, None, 1, 8, 8, None) == -1
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "dkt_stereo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("oracle/make_golden.py", ""), f"{f} mentions the oracle"
+    for f in ("tools/evaluate_stereo.py",):
+        path = os.path.join(ROOT, f)
+        if os.path.exists(path):
+            assert "import oracle" not in open(path).read() and "from oracle" not in open(path).read()

@@ -1,0 +1,279 @@
+"""GPU parity tests: every kernel family is called through the C ABI (ctypes) and compared with
+(a) the golden vectors produced by the real reference and (b) the CPU oracle on seeded inputs.
+
+Tolerances (fp32 data, written next to each assert):
+  * fp32 CUDA-core kernels: 2e-5 abs (different summation order only)
+  * tensor-core kernels (3-term bf16 split, ~2^-16 relative per product): 1e-4 .. 1e-3 abs on
+    O(1..10) values, stated per test
+  * end to end: mean |disparity difference| <= 1e-3 px (the north-star gate)
+"""
+from argparse import Namespace
+
+import pytest
+import torch
+
+from helpers import load_golden, golden_shapes, stats, RAFT_CFG, IGEV_CFG
+
+pytestmark = pytest.mark.gpu
+
+IMPLS = ["simt", "tc"]
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+# ---------------------------------------------------------------------------------------------
+# K1 / K2
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_corr1d_build_golden(impl, tag):
+    from dkt_stereo_b200 import ops
+    g = load_golden(f"corr1d_{tag}")
+    f1, f2 = g["fmap1"].to(dev()), g["fmap2"].to(dev())
+    D = f1.shape[1]
+    pyr = ops.corr1d_build(f1, f2, 4, 1.0 / D ** 0.5, impl=impl)
+    tol = 2e-5 if impl == "simt" else 2e-4
+    for i in range(4):
+        ref = g[f"pyr{i}"]
+        assert pyr[i].shape == ref.shape
+        assert stats(pyr[i].cpu(), ref)[1] < tol, (impl, tag, i, stats(pyr[i].cpu(), ref))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_corr1d_build_channels_last_and_sizes(impl):
+    """Strided (channels_last) feature maps and the cfg-sized row width 240 with D=256."""
+    from dkt_stereo_b200 import ops
+    from oracle import hotpath as O
+    g = torch.Generator().manual_seed(5)
+    f1 = torch.randn(1, 256, 3, 240, generator=g)
+    f2 = torch.randn(1, 256, 3, 240, generator=g)
+    ref = O.corr1d_pyramid(f1, f2, 4)
+    a = f1.to(dev()).contiguous(memory_format=torch.channels_last)
+    b = f2.to(dev()).contiguous(memory_format=torch.channels_last)
+    pyr = ops.corr1d_build(a, b, 4, 1.0 / 16.0, impl=impl)
+    tol = 3e-5 if impl == "simt" else 5e-4
+    for i in range(4):
+        assert stats(pyr[i].cpu(), ref[i])[1] < tol, (impl, i, stats(pyr[i].cpu(), ref[i]))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_corr1d_lookup_golden(tag):
+    from dkt_stereo_b200.corr import B200CorrBlock1D, corr_sampler_forward
+    g = load_golden(f"corr1d_{tag}")
+    blk = B200CorrBlock1D(g["fmap1"].to(dev()), g["fmap2"].to(dev()), num_levels=4, radius=4, impl="simt")
+    out = blk(g["coords"].to(dev()))
+    assert out.shape == g["out"].shape
+    assert stats(out.cpu(), g["out"])[1] < 2e-5
+    # plug-in ABI of the reference's corr_sampler extension, one level at a time
+    lvl = 1
+    (o1,) = corr_sampler_forward(g[f"pyr{lvl}"].to(dev()), g["coords"][:, :1].to(dev()) / 2 ** lvl, 4)
+    assert stats(o1.cpu(), g["out"][:, 9 * lvl:9 * (lvl + 1)])[1] < 2e-5
+
+
+def test_lookup_fused_coordinate_update():
+    """delta add + flow bookkeeping fused in front of the gather (raft_stereo.py:154-155,164-167)."""
+    from dkt_stereo_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 2, 4, 40
+    cx = (torch.rand(B, H, W, generator=g) * W).to(dev())
+    delta = torch.randn(B, H, W, 2, generator=g).to(dev())
+    flow = torch.zeros(B, H, W, 2, device=dev())
+    flow[..., 1] = 7.0
+    cx0 = cx.clone()
+    ops.corr1d_lookup([], cx, 4, None, delta=delta, flow=flow)
+    xs = torch.arange(W, device=dev()).view(1, 1, W)
+    assert torch.equal(cx, cx0 + delta[..., 0])
+    assert torch.equal(flow[..., 0], cx - xs)
+    assert torch.all(flow[..., 1] == 7.0)
+
+
+def test_geo_golden():
+    from dkt_stereo_b200 import ops
+    g = load_golden("geo_a")
+    f1, f2, gev, disp = (g[k].to(dev()) for k in ("fmap1", "fmap2", "gev", "disp"))
+    init = ops.corr1d_build(f1, f2, 2, 1.0, impl="simt")
+    geo = ops.geo_pool(gev)
+    B, _, H, W = disp.shape
+    out = torch.empty(B, 162, H, W, device=dev())
+    ops.geo_lookup(geo, init, disp[:, 0].contiguous(), 4, out, out_layout="nchw")
+    assert stats(out.cpu(), g["out"])[1] < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# K3: single convs with each epilogue vs torch conv2d (fp32 reference of the same op)
+# ---------------------------------------------------------------------------------------------
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _slice_of(x_nhwc, impl, c0=0, cnt=None):
+    from dkt_stereo_b200 import ops
+    from dkt_stereo_b200._lib import tensor_slice
+    if impl == "tc":
+        hi, lo = ops.split_bf16(x_nhwc)
+        keep = (x_nhwc, hi.contiguous(), lo.contiguous())
+        return tensor_slice(None, keep[1], keep[2], c0, cnt), keep
+    return tensor_slice(x_nhwc, None, None, c0, cnt), (x_nhwc,)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("shape", [(1, 64, 64, 8, 16, 3), (2, 128, 126, 19, 37, 3), (1, 64, 144, 9, 20, 1),
+                                   (1, 256, 2, 11, 18, 3), (2, 384, 256, 17, 30, 3)])
+def test_conv_linear(impl, shape):
+    from dkt_stereo_b200 import ops, _lib as L
+    B, Cin, N, H, W, k = shape
+    g = torch.Generator().manual_seed(Cin + N)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    wt = torch.randn(N, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    bias = torch.randn(N, generator=g)
+    ref = torch.relu(torch.nn.functional.conv2d(x, wt, bias, padding=k // 2))
+    xs, keep = _slice_of(_nhwc(x).to(dev()), impl)
+    W_ = ops.pack_conv(wt.to(dev()), bias.to(dev()), tc=(impl == "tc"))
+    Cout = (N + 3) // 4 * 4 if N >= 4 else N
+    out = torch.zeros(B, H, W, Cout, device=dev())
+    e = ops.make_epilogue(L.EPI_LINEAR, L.tensor_slice(out, None, None, 0, N), act=L.ACT_RELU, bias=W_.bias)
+    ops.conv2d([xs], W_, e, B, H, W, impl)
+    torch.cuda.synchronize()
+    got = out[..., :N].permute(0, 3, 1, 2).cpu()
+    tol = 2e-5 if impl == "simt" else 2e-4
+    assert stats(got, ref)[1] < tol, (impl, shape, stats(got, ref))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_conv_two_sources_and_tail(impl):
+    """channel-concat of two slices (one of them a sub-range of a wider buffer) + flow tail."""
+    from dkt_stereo_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(9)
+    B, H, W = 1, 13, 21
+    a = torch.randn(B, 64, H, W, generator=g)
+    big = torch.randn(B, 192, H, W, generator=g)
+    flow = torch.randn(B, 2, H, W, generator=g)
+    wt = torch.randn(126, 128, 3, 3, generator=g) / 34.0
+    bias = torch.randn(126, generator=g)
+    ref = torch.relu(torch.nn.functional.conv2d(torch.cat([a, big[:, 64:128]], 1), wt, bias, padding=1))
+    ref = torch.cat([ref, flow], 1)
+    s0, k0 = _slice_of(_nhwc(a).to(dev()), impl)
+    s1, k1 = _slice_of(_nhwc(big).to(dev()), impl, 64, 64)
+    W_ = ops.pack_conv(wt.to(dev()), bias.to(dev()), tc=(impl == "tc"))
+    out = torch.zeros(B, H, W, 384, device=dev())
+    fl = _nhwc(flow).to(dev())
+    e = ops.make_epilogue(L.EPI_LINEAR, L.tensor_slice(out, None, None, 128, 128), act=L.ACT_RELU, bias=W_.bias, tail=fl)
+    ops.conv2d([s0, s1], W_, e, B, H, W, impl)
+    got = out[..., 128:256].permute(0, 3, 1, 2).cpu()
+    tol = 2e-5 if impl == "simt" else 2e-4
+    assert stats(got, ref)[1] < tol, stats(got, ref)
+    assert float(out[..., :128].abs().max()) == 0 and float(out[..., 256:].abs().max()) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# a6..a11: one full update-block step vs the reference's own output (golden)
+# ---------------------------------------------------------------------------------------------
+def _run_update(tag, igev, impl):
+    from dkt_stereo_b200.update import BasicMultiUpdateBlock, UpdateEngine
+    from dkt_stereo_b200.synthetic import synthetic_state_dict
+    from dkt_stereo_b200 import ops
+    g = load_golden(f"update_{tag}")
+    cfg = IGEV_CFG if igev else RAFT_CFG
+    blk = BasicMultiUpdateBlock(Namespace(**cfg), hidden_dims=cfg["hidden_dims"], igev=igev)
+    blk.load_state_dict(synthetic_state_dict(golden_shapes(g), seed=3), strict=True)
+    blk = blk.to(dev())
+    eng = UpdateEngine(blk, impl)
+    eng.pack_weights()
+    B, _, h, w = g["net0"].shape
+    eng.allocate(B, h, w, dev())
+    eng.load_state([g[f"net{i}"].to(dev()) for i in range(3)],
+                   [[g[f"c{n}{i}"].to(dev()) for n in "zrq"] for i in range(3)])
+    corr, flow = g["corr"].to(dev()), g["flow"].to(dev())
+
+    def lookup(e):
+        e.CORR["f32"][..., :corr.shape[1]] = corr.permute(0, 2, 3, 1)
+        if e.CORR["hi"] is not None:
+            hi, lo = ops.split_bf16(e.CORR["f32"])
+            e.CORR["hi"].copy_(hi)
+            e.CORR["lo"].copy_(lo)
+        e.FLOW["f32"].copy_(flow.permute(0, 2, 3, 1))
+
+    eng.step(lookup, with_mask=True)
+    torch.cuda.synchronize()
+    net = eng.hidden_states()
+    tol = 3e-5 if impl == "simt" else 3e-4
+    for i in range(3):
+        assert stats(net[i].cpu(), g[f"net_out{i}"])[1] < tol, (impl, i, stats(net[i].cpu(), g[f"net_out{i}"]))
+    delta = eng.DELTA["f32"].permute(0, 3, 1, 2).cpu()
+    assert stats(delta, g["delta"])[1] < tol * 3, stats(delta, g["delta"])
+    mask = (eng.MH if igev else eng.MASK)["f32"].permute(0, 3, 1, 2).cpu()
+    assert stats(mask, g["mask"])[1] < tol * 3, stats(mask, g["mask"])
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_update_block_raft(impl):
+    _run_update("raft", False, impl)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_update_block_igev(impl):
+    _run_update("igev", True, impl)
+
+
+# ---------------------------------------------------------------------------------------------
+# K4
+# ---------------------------------------------------------------------------------------------
+def test_upsamplers_golden():
+    from dkt_stereo_b200 import ops
+    g = load_golden("convex_upsample")
+    up = ops.convex_upsample(_nhwc(g["flow"]).to(dev()), _nhwc(g["mask"]).to(dev()), 4)
+    assert stats(up.cpu(), g["out"][:, :1])[1] < 2e-5
+    g = load_golden("context_upsample")
+    up = ops.context_upsample(g["disp"][:, 0].contiguous().to(dev()), g["weights"].to(dev()), in_scale=1.0)
+    assert stats(up[:, 0].cpu(), g["out"])[1] < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# a12: the whole forward(test_mode=True) vs the reference's disparity maps
+# ---------------------------------------------------------------------------------------------
+def _model(impl, g):
+    from dkt_stereo_b200.raft_stereo import RAFTStereo
+    from dkt_stereo_b200.synthetic import synthetic_state_dict
+    cfg = dict(RAFT_CFG, corr_implementation="b200" if impl == "tc" else "b200_fp32")
+    model = RAFTStereo(Namespace(mixed_precision=False, **cfg)).eval()
+    model.load_state_dict(synthetic_state_dict(golden_shapes(g), seed=0), strict=True)
+    return model.to(dev())
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("tag", ["raft_fwd_small", "raft_fwd_shift", "raft_fwd_cfg1"])
+def test_raft_forward_golden(impl, tag):
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    g = load_golden(tag)
+    B, H, W, iters = [int(v) for v in g["meta"]]
+    model = _model(impl, g)
+    im1, im2 = synthetic_pair(B, H, W, seed=1234, mode=str(g["mode"]))
+    lr, up = model(im1.to(dev()), im2.to(dev()), iters=iters, test_mode=True)
+    assert up.shape == (B, 1, H, W) and lr.shape == (B, 2, H // 4, W // 4)
+    mean, mx = stats(up.cpu(), g["flow_up"])
+    print(f"[parity] {tag} impl={impl}: mean-abs {mean:.3e} px, max-abs {mx:.3e} px")
+    assert mean <= 1e-3, (tag, impl, mean, mx)          # north-star gate
+    assert stats(lr.cpu(), g["flow_lr"])[0] <= 1e-3
+    # CUDA-graph replay (3rd call) must reproduce the eager result bit for bit
+    model(im1.to(dev()), im2.to(dev()), iters=iters, test_mode=True)
+    lr3, up3 = model(im1.to(dev()), im2.to(dev()), iters=iters, test_mode=True)
+    assert torch.equal(up3, up) and torch.equal(lr3, lr)
+
+
+def test_flow_init_and_batch_independence():
+    """flow_init is honoured and per-sample results do not depend on the batch they ride in."""
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    g = load_golden("raft_fwd_small")
+    model = _model("tc", g)
+    im1, im2 = synthetic_pair(3, 64, 96, seed=77)
+    im1, im2 = im1.to(dev()), im2.to(dev())
+    _, up = model(im1, im2, iters=3, test_mode=True)
+    _, up1 = model(im1[1:2], im2[1:2], iters=3, test_mode=True)
+    assert stats(up[1:2].cpu(), up1.cpu())[0] < 1e-4      # cuDNN may pick another algorithm per batch size
+    fi = torch.zeros(3, 2, 16, 24, device=dev())
+    fi[:, 0] = -2.5
+    lr, _ = model(im1, im2, iters=1, flow_init=fi, test_mode=True)
+    lr0, _ = model(im1, im2, iters=1, test_mode=True)
+    assert float((lr - lr0).abs().mean()) > 0.5

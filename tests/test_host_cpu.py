@@ -1,0 +1,76 @@
+"""CPU: host-side logic (checkpoint key compatibility, weight packing, padding, synthetic data)."""
+from argparse import Namespace
+
+import pytest
+import torch
+
+from helpers import load_golden, golden_shapes, RAFT_CFG, IGEV_CFG
+
+
+def test_raft_state_dict_keys_match_reference():
+    from dkt_stereo_b200.raft_stereo import RAFTStereo
+    g = load_golden("raft_fwd_small")
+    ref = golden_shapes(g)                       # keys + shapes of the reference model's state_dict
+    model = RAFTStereo(Namespace(mixed_precision=False, **RAFT_CFG))
+    mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert mine == ref
+    # DataParallel-style checkpoints ("module." prefix, evaluate_stereo.py:361-370) load too
+    wrapped = torch.nn.DataParallel(model)
+    assert sorted(wrapped.state_dict()) == sorted("module." + k for k in ref)
+
+
+def test_update_block_keys_match_reference():
+    from dkt_stereo_b200.update import BasicMultiUpdateBlock
+    for tag, cfg, igev in (("raft", RAFT_CFG, False), ("igev", IGEV_CFG, True)):
+        ref = golden_shapes(load_golden(f"update_{tag}"))
+        blk = BasicMultiUpdateBlock(Namespace(**cfg), hidden_dims=cfg["hidden_dims"], igev=igev)
+        assert {k: tuple(v.shape) for k, v in blk.state_dict().items()} == ref
+
+
+def test_training_mode_and_cpu_inputs_fail_loudly():
+    from dkt_stereo_b200.raft_stereo import RAFTStereo
+    from dkt_stereo_b200._lib import DktError
+    model = RAFTStereo(Namespace(mixed_precision=False, **RAFT_CFG)).eval()
+    x = torch.zeros(1, 3, 32, 64)
+    with pytest.raises(NotImplementedError):
+        model(x, x, iters=1, test_mode=False)
+    with pytest.raises(DktError):
+        model(x, x, iters=1, test_mode=True)       # no CPU fallback
+    with pytest.raises(NotImplementedError):
+        RAFTStereo(Namespace(mixed_precision=False, **dict(RAFT_CFG, corr_implementation="alt")))
+
+
+def test_pack_conv_layouts():
+    from dkt_stereo_b200 import ops
+    w = torch.randn(5, 7, 3, 3)
+    b = torch.randn(5)
+    p = ops.pack_conv(w, b, cin_pad=16, tc=True)
+    assert p.w_simt.shape == (9, 16, 5) and p.w_hi.shape == (9, 16, 16) and p.cin == 16 and p.n == 5
+    assert torch.equal(p.w_simt[4, :7, :], w[:, :, 1, 1].t())
+    assert float(p.w_simt[:, 7:, :].abs().max()) == 0
+    rec = p.w_hi.float() + p.w_lo.float()
+    assert torch.allclose(rec[4, :5, :7], w[:, :, 1, 1], rtol=2e-5, atol=1e-6)
+    assert float(rec[:, 5:, :].abs().max()) == 0
+    hi, lo = ops.split_bf16(torch.tensor([1.2345678, -3.1415927e-3, 1e4]))
+    err = (hi.float() + lo.float() - torch.tensor([1.2345678, -3.1415927e-3, 1e4])).abs()
+    assert torch.all(err <= torch.tensor([1.2345678, 3.1415927e-3, 1e4]) * 2.0 ** -16)
+
+
+def test_input_padder_roundtrip():
+    from dkt_stereo_b200.utils import InputPadder, coords_grid
+    x = torch.arange(2 * 3 * 37 * 50, dtype=torch.float32).view(2, 3, 37, 50)
+    p = InputPadder(x.shape, divis_by=32)
+    (y,) = p.pad(x)
+    assert y.shape[-2] % 32 == 0 and y.shape[-1] % 32 == 0
+    assert torch.equal(p.unpad(y), x)
+    c = coords_grid(1, 3, 4)
+    assert c[0, 0, 2, 3] == 3 and c[0, 1, 2, 3] == 2
+
+
+def test_synthetic_is_deterministic():
+    from dkt_stereo_b200.synthetic import synthetic_pair, synthetic_state_dict
+    a, b = synthetic_pair(1, 8, 16)
+    a2, b2 = synthetic_pair(1, 8, 16)
+    assert torch.equal(a, a2) and torch.equal(b, b2) and not torch.equal(a, b)
+    s1 = synthetic_state_dict({"x.weight": (4, 3, 3, 3), "y.norm3.weight": (4,), "y.downsample.1.weight": (4,)})
+    assert torch.equal(s1["y.norm3.weight"], s1["y.downsample.1.weight"])
