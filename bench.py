@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Headline benchmark: stereo pairs/sec of RAFT-Stereo forward(test_mode=True) at 544x960, 32 GRU
+iterations, batch 8 per GPU (BASELINE.json configs[1]), synthetic inputs, random-init weights.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                    # this engine
+    python bench.py --impl reference --steps 2 --warmup 1             # CPU baseline arm (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what every key means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from argparse import Namespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+RAFT_CFG = dict(model="RAFTStereo", loss_func="sequence_loss_raft", backbone_type="default",
+                corr_implementation="reg", shared_backbone=False, corr_levels=4, corr_radius=4,
+                n_downsample=2, context_norm="batch", slow_fast_gru=False, n_gru_layers=3,
+                hidden_dims=[128, 128, 128])
+
+METRIC = "stereo pairs/sec @ 544x960, 32 iters"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_burst=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"],
+                    source="MEASURED_PEAKS.json (of measured)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="B200_PROFILING.md fallback (of fallback)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+def host_info():
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    model = ln.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return dict(cores=os.cpu_count(), cpu=model)
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference path) -- the only place bench.py executes oracle/
+# ---------------------------------------------------------------------------------------------
+def cpu_pairs_per_sec(height, width, iters, batch, steps, warmup, threads):
+    from oracle import hotpath as O
+    from dkt_stereo_b200.raft_stereo import RAFTStereo
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = RAFTStereo(Namespace(mixed_precision=False, **RAFT_CFG)).eval()     # weights only
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    im1, im2 = synthetic_pair(batch, height, width, seed=1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.raft_forward(sd, im1, im2, iters, RAFT_CFG)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return batch * len(times) / total, 1e3 * total / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    hi = host_info()
+    threads = hi["cores"] or 1
+    H, W, iters = args.height, args.width, args.iters
+    value, ms = cpu_pairs_per_sec(H, W, iters, 1, args.steps, args.warmup, threads)
+    sample = f"1 pair per step (B=1) of the same {H}x{W}, {iters}-iter workload; {args.steps} timed steps"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"RAFT-Stereo {H}x{W}, {iters} iters, CPU fp32, B=1 per step", "host": hi},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    from dkt_stereo_b200 import _lib as L, ops, parallel
+    from dkt_stereo_b200.raft_stereo import RAFTStereo
+    from dkt_stereo_b200.synthetic import synthetic_pair
+
+    rank, local, world = parallel.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the engine)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+    H, W, iters, Bg = args.height, args.width, args.iters, args.batch
+    h, w = H // 4, W // 4
+
+    torch.manual_seed(0)
+    cfg = dict(RAFT_CFG, corr_implementation="b200" if args.kernels == "tc" else "b200_fp32")
+    model = RAFTStereo(Namespace(mixed_precision=False, extractor_tf32=args.extractor_tf32, **cfg)).eval().to(dev)
+    bcast_bytes = parallel.broadcast_weights(model, src=0)          # the one collective of the path
+
+    # every rank works on its own shard of the global batch (weak scaling: B per GPU fixed)
+    im1_h, im2_h = synthetic_pair(Bg, H, W, seed=1234 + rank)
+    im1_h, im2_h = im1_h.pin_memory(), im2_h.pin_memory()
+    im1_d, im2_d = im1_h.to(dev), im2_h.to(dev)
+
+    def step_device():
+        return model(im1_d, im2_d, iters=iters, test_mode=True)
+
+    def step_e2e():
+        a = im1_h.to(dev, non_blocking=True)
+        b = im2_h.to(dev, non_blocking=True)
+        _, up = model(a, b, iters=iters, test_mode=True)
+        return up.to("cpu", non_blocking=False)
+
+    # warm-up (also builds the CUDA graph on the 2nd call)
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+
+    # launches per step, counted on one eager (graph-less) pass
+    model.use_cuda_graph = False
+    n0 = L.LAUNCHES
+    step_device()
+    torch.cuda.synchronize()
+    launches_per_step = L.LAUNCHES - n0
+    # per-kernel breakdown of one step (CUDA events around every launch; eager, so slightly pessimistic)
+    with ops.LaunchProfiler() as prof:
+        step_device()
+    breakdown = prof.summary()
+    model.use_cuda_graph = True
+    step_device()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+
+    def timed(fn, steps):
+        parallel.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        return parallel.all_reduce_max(a.elapsed_time(b), dev)
+
+    ms_total = timed(step_device, args.steps)
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel: the gru08 z||r gate conv (3x3, 384 -> 256 at 1/4 res) ----
+    eng = model.engine
+    P = Bg * h * w
+    flops_zr = 2.0 * P * 256 * 9 * 384
+    reps = 20
+    evs = []
+    for _ in range(3):
+        eng._gru(0, 256)
+    torch.cuda.synchronize()
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        Sx = eng._slice
+        split, simt = eng.impl == "tc", eng.impl == "simt"
+        e = ops.make_epilogue(L.EPI_GRU_ZR, out=Sx(eng.RH[0], 0, 128, simt, split), ctx=eng.CTX[0]["f32"], ctx_c0=0,
+                              z=Sx(eng.Z[0], 0, 128, True, False), h=Sx(eng.X[0], 0, 128, True, False))
+        ops.conv2d([Sx(eng.X[0], 0, 384, simt, split)], eng.weights["zr0"], e, Bg, h, w, eng.impl)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    zr_ms = sum(a.elapsed_time(b) for a, b in evs) / reps
+    tflops = flops_zr / (zr_ms * 1e-3) / 1e12
+    roofline = {"kernel": "conv_tc_kernel (gru08 z||r gates, 3x3 384->256)", "bound": "tensor",
+                "achieved": tflops, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": tflops / peaks["bf16_burst"],
+                "traffic": None, "ms_per_launch": zr_ms, "flops_per_launch": flops_zr,
+                "note": "useful fp32-equivalent FLOPs; the 3-term bf16 split issues 3x this many MMA flops",
+                "peak_source": peaks["source"] + ", burst (kernel timed alone)"}
+
+    # ---- roofline of the correlation-volume build (K1), HBM bound ----
+    fm = torch.randn(Bg, 256, h, w, device=dev)
+    fm2 = torch.randn(Bg, 256, h, w, device=dev)
+    pyr = model._pyr
+    for _ in range(2):
+        ops.corr1d_build(fm, fm2, 4, 1.0 / 16, impl=eng.impl, pyr=pyr)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        ops.corr1d_build(fm, fm2, 4, 1.0 / 16, impl=eng.impl, pyr=pyr)
+    b.record()
+    torch.cuda.synchronize()
+    k1_ms = a.elapsed_time(b) / 5
+    k1_bytes = 2.0 * Bg * 256 * h * w * 4 + sum(P * (w >> l) * 4 for l in range(4))
+    # lookup (K2): bytes per iteration = P * [L*(2r+2)*4 + 4 + L*(2r+1)*4]
+    k2_bytes = P * (4 * 10 * 4 + 4 + 4 * 9 * 4)
+    k2 = breakdown.get("corr1d_lookup", (1, float("nan")))
+    k2_ms = k2[1] / max(k2[0], 1)
+    roofline_corr = {
+        "build": {"bound": "hbm", "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                  "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": k1_ms, "bytes": k1_bytes,
+                  "launches": "2x split + tcgen05 build"},
+        "lookup": {"bound": "hbm", "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                   "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": k2_ms, "bytes": k2_bytes},
+    }
+
+    if rank != 0:
+        return
+    # CPU baseline on rank 0 at N=1 only: one pair of the same workload through the oracle port
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        hi = host_info()
+        v, ms = cpu_pairs_per_sec(H, W, iters, 1, 1, 0, hi["cores"] or 1)
+        cpu = {"value": v, "unit": "pairs/s", "cores": hi["cores"], "kind": "port", "cpu": hi["cpu"],
+               "sample": f"1 pair (B=1) of the same {H}x{W}, {iters}-iter workload, 1 run, {ms / 1e3:.1f} s"}
+
+    ms_step = ms_total / args.steps
+    value = world * Bg * args.steps / (ms_total * 1e-3)
+    e2e_value = world * Bg * args.steps / (ms_e2e * 1e-3)
+    top = sorted(breakdown.items(), key=lambda kv: -kv[1][1])[:12]
+    total_prof = sum(t for _, t in breakdown.values())
+    out = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16x3" if args.kernels == "tc" else "f32", "data": "synthetic",
+        "config": {"workload": f"RAFT-Stereo {H}x{W}, {iters} iters, batch {Bg} per GPU (BASELINE configs[1])",
+                   "global_batch": world * Bg, "parallelism": f"dp{world} (batch shards, no steady-state collective)",
+                   "kernels": args.kernels, "extractor": "PyTorch cuDNN fp32" + (" (TF32 allowed)" if args.extractor_tf32 else ""),
+                   "cache": "working set per step (470 MB volume + 1.3 GB activations) >> 126 MB L2; no flush needed",
+                   "weight_broadcast_bytes": bcast_bytes},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": 2 * im1_h.numel() * 4, "d2h_bytes_per_step": Bg * H * W * 4},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": roofline, "roofline_corr": roofline_corr, "cpu_baseline": cpu, "clocks": clocks,
+        "breakdown_ms_per_step": {k: round(v[1], 3) for k, v in top},
+        "breakdown_total_ms": round(total_prof, 3),
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--kernels", default="tc", choices=["tc", "simt"])
+    ap.add_argument("--height", type=int, default=544)
+    ap.add_argument("--width", type=int, default=960)
+    ap.add_argument("--iters", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
+    ap.add_argument("--extractor-tf32", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -93,7 +93,12 @@ def load() -> C.CDLL:
     return lib
 
 
+LAUNCHES = 0   # kernels launched through the C ABI by this process (every ok check() is one launch)
+
+
 def check(rc: int, what: str = "") -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         msg = load().dkt_error_string(rc).decode()
         raise DktError(f"{what or 'dkt call'} failed with code {rc}: {msg}")

@@ -53,7 +53,7 @@ def corr1d_build(fmap1: torch.Tensor, fmap2: torch.Tensor, levels: int, scale: f
         pyr = alloc_pyramid(B, H, W1, W2, levels, fmap1.device)
     ptrs = L.pointer_array(pyr)
     sb, sd, sh, sw = fmap1.stride()
-    if impl == "tc" and D % 64 == 0 and W2 % 16 == 0 and W2 <= 256:
+    if impl == "tc" and D % 8 == 0 and W2 <= 256:
         hi1 = torch.empty(B, H, W1, D, device=fmap1.device, dtype=torch.bfloat16)
         lo1, hi2, lo2 = torch.empty_like(hi1), torch.empty(B, H, W2, D, device=fmap1.device, dtype=torch.bfloat16), None
         lo2 = torch.empty_like(hi2)
@@ -248,3 +248,63 @@ def nhwc_to_nchw(src: DktTensor, B: int, H: int, W: int, device) -> torch.Tensor
     L.check(L.load().dkt_nhwc_to_nchw(C.byref(src), out.data_ptr(), B, src.c_count, H, W, L.stream_ptr()),
             "nhwc_to_nchw")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# optional per-launch CUDA-event profiler (used by bench.py for the per-kernel breakdown)
+# ---------------------------------------------------------------------------------------------
+class LaunchProfiler:
+    """with LaunchProfiler() as p: ... ; p.summary() -> {name: (count, total_ms)} after a sync."""
+
+    active: Optional["LaunchProfiler"] = None
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        LaunchProfiler.active = self
+        return self
+
+    def __exit__(self, *exc):
+        LaunchProfiler.active = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.records:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + a.elapsed_time(b))
+        return out
+
+
+def _profiled(namer):
+    def deco(fn):
+        def wrapper(*args, **kwargs):
+            prof = LaunchProfiler.active
+            if prof is None:
+                return fn(*args, **kwargs)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = fn(*args, **kwargs)
+            b.record()
+            prof.records.append((namer(*args, **kwargs), a, b))
+            return r
+        wrapper.__name__ = fn.__name__
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+    return deco
+
+
+def _conv_name(srcs, w, epi, B, H, W, impl="tc"):
+    kind = {0: "lin", 1: "gru_zr", 2: "gru_q"}[epi.kind]
+    return f"conv{w.ksize}x{w.ksize}_{w.cin}to{w.n}_{H}x{W}_{kind}_{impl}"
+
+
+conv2d = _profiled(_conv_name)(conv2d)
+corr1d_build = _profiled(lambda *a, **k: f"corr1d_build_{k.get('impl', a[4] if len(a) > 4 else 'tc')}")(corr1d_build)
+corr1d_lookup = _profiled(lambda pyr, *a, **k: "corr1d_lookup" if len(pyr) else "coords_update")(corr1d_lookup)
+pool2x = _profiled(lambda *a, **k: "pool2x")(pool2x)
+interp = _profiled(lambda *a, **k: "interp")(interp)
+convex_upsample = _profiled(lambda *a, **k: "convex_upsample")(convex_upsample)
+nchw_to_nhwc = _profiled(lambda *a, **k: "nchw_to_nhwc")(nchw_to_nhwc)
+geo_lookup = _profiled(lambda *a, **k: "geo_lookup")(geo_lookup)
