@@ -193,6 +193,16 @@ def run_b200(args):
         step_device()
     torch.cuda.synchronize()
 
+    if args.ncu_step:
+        # profiler window = exactly one step (ncu --profile-from-start off); nothing is timed or printed
+        model.use_cuda_graph = False          # same kernels, launched eagerly so ncu sees each one
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+
     # launches per step, counted on one eager (graph-less) pass
     model.use_cuda_graph = False
     n0 = L.LAUNCHES
@@ -330,6 +340,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
     ap.add_argument("--extractor-tf32", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="warm up, then run ONE step inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
