@@ -12,9 +12,21 @@
 // Precision: activations and weights are bf16 (hi, lo) pairs; each K step issues
 // hi*hi + lo*hi + hi*lo into the same fp32 TMEM accumulator (3-term split, ~16 mantissa bits).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> fused bias/context/activation/GRU algebra ->
-// NHWC global stores in fp32 and/or split bf16).
+// conv_tc_kernel<BK> (v2, default) is PERSISTENT: grid = min(tiles, #SMs), each CTA walks tiles
+// blockIdx.x, +gridDim.x, ...  Three pipelines run concurrently inside a CTA:
+//   warp 0      TMA producer      smem ring of (A hi, A lo, W hi, W lo) stages, full/empty mbarriers
+//   warp 1      MMA issuer        two TMEM accumulator stages (2 x Npad columns), tmem_full/empty
+//   warps 2..9  epilogue          tile i is drained while the MMAs of tile i+1 run
+// The epilogue is coalesced: a warp owns 32 pixels (its TMEM lane quarter); it pulls a 32-column
+// chunk with tcgen05.ld (thread = pixel), transposes it through a swizzled 4 KB smem buffer and
+// continues with lanes = 8 x 16-byte channel groups of 4 pixels, so every global access of the
+// fused epilogue (context term, h, z, fp32 / bf16 hi / bf16 lo stores) is a full 128-byte line.
+// The two warps that share a lane quarter take alternate column chunks.
+// BK = K block in channels: 64 (SWIZZLE_128B rows) for N <= 128, 32 (SWIZZLE_64B) for N = 256 so
+// that four stages fit next to the epilogue buffers.
+//
+// conv_tc_v1_kernel is the first (one tile per CTA, serial epilogue) version, kept selectable
+// with DKT_CONV_TC=v1 for A/B measurements.
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -23,7 +35,7 @@ namespace dkt {
 using namespace tc;
 
 constexpr int TC_TILE_W = 16, TC_TILE_H = 8, TC_BLOCK_K = 64;
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_STAGES = 8;
 constexpr uint32_t TC_A_BYTES = 128 * 128;          // 128 pixels x 64 bf16
 constexpr int TC_THREADS = 192;
 
@@ -36,7 +48,9 @@ struct TcConvParams {
     int ksize, pad, taps;
     int N, Npad;
     int H, W, tiles_x, tiles_y;
+    int num_tiles;
     int stages;
+    uint32_t acc_cols;              // v2: TMEM columns per accumulator stage
     uint32_t tmem_cols;
     dkt_epilogue epi;
 };
@@ -84,7 +98,7 @@ __device__ __forceinline__ void tc_epilogue1(const dkt_epilogue& e, int64_t p, i
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
+conv_tc_v1_kernel(const __grid_constant__ TcConvParams prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -211,6 +225,202 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, prm.tmem_cols);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// v2: persistent, double-buffered accumulators, coalesced epilogue
+// ---------------------------------------------------------------------------------------------
+constexpr int TC2_THREADS = 320;
+constexpr int TC2_EPI_WARPS = 8;
+constexpr uint32_t TC2_EPI_BYTES = TC2_EPI_WARPS * 32 * 128;     // one 32 px x 32 ch fp32 tile per warp
+
+template <int BK>
+__device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr) {
+    constexpr uint32_t ROW = BK * 2;                 // bytes per row (64 or 128) == swizzle span
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * ROW) >> 4) << 32;           // stride between 8-row atoms
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(BK == 64 ? 2 : 4) << 61;         // SWIZZLE_128B : SWIZZLE_64B
+    return d;
+}
+
+template <int BK>
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
+    constexpr uint32_t ROW = BK * 2;
+    constexpr uint32_t A_BYTES = 128 * ROW;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    const uint32_t b_bytes = (uint32_t)prm.Npad * ROW;
+    const uint32_t stage_bytes = 2u * A_BYTES + 2u * b_bytes;
+    uint8_t* epi_smem = smem + (size_t)prm.stages * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + TC2_EPI_BYTES);
+    uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + TC_MAX_STAGES;     // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int kb_total = 0;
+    for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
+    const int ksteps = prm.taps * kb_total;                  // per tile
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < prm.nsrc; ++s) { tma_prefetch_desc(&prm.act[s][0]); tma_prefetch_desc(&prm.act[s][1]); }
+        tma_prefetch_desc(&prm.wgt[0]);
+        tma_prefetch_desc(&prm.wgt[1]);
+        for (int s = 0; s < prm.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], TC2_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * prm.acc_cols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles_per_img = prm.tiles_x * prm.tiles_y;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+                const int b = tile / tiles_per_img;
+                const int r = tile - b * tiles_per_img;
+                const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
+                for (int tap = 0; tap < prm.taps; ++tap) {
+                    const int ky = tap / prm.ksize, kx = tap - ky * prm.ksize;
+                    const int xs = x0 + kx - prm.pad, ys = y0 + ky - prm.pad;
+                    int kofs = 0;
+                    for (int s = 0; s < prm.nsrc; ++s) {
+                        for (int kb = 0; kb < prm.kblocks[s]; ++kb) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1u);
+                            uint8_t* st = smem + (size_t)stage * stage_bytes;
+                            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+                            const int c = prm.c_begin[s] + kb * BK;
+                            tma_load_4d(st, &prm.act[s][0], &full_bar[stage], c, xs, ys, b);
+                            tma_load_4d(st + A_BYTES, &prm.act[s][1], &full_bar[stage], c, xs, ys, b);
+                            tma_load_2d(st + 2 * A_BYTES, &prm.wgt[0], &full_bar[stage], kofs + kb * BK, tap * prm.Npad);
+                            tma_load_2d(st + 2 * A_BYTES + b_bytes, &prm.wgt[1], &full_bar[stage], kofs + kb * BK, tap * prm.Npad);
+                            if (++stage == prm.stages) { stage = 0; phase ^= 1u; }
+                        }
+                        kofs += prm.kblocks[s] * BK;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = idesc_bf16_m128((uint32_t)prm.Npad);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t t = 0;
+            for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
+                const uint32_t as = t & 1u, aphase = (t >> 1) & 1u;
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);          // epilogue drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + as * prm.acc_cols;
+                for (int it = 0; it < ksteps; ++it) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t a_lo = a_hi + A_BYTES;
+                    const uint32_t w_hi = a_hi + 2 * A_BYTES;
+                    const uint32_t w_lo = w_hi + b_bytes;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t dah = smem_desc_kmajor<BK>(a_hi + k * 32), dal = smem_desc_kmajor<BK>(a_lo + k * 32);
+                        const uint64_t dwh = smem_desc_kmajor<BK>(w_hi + k * 32), dwl = smem_desc_kmajor<BK>(w_lo + k * 32);
+                        umma_bf16(tmem_d, dah, dwh, idesc, (it | k) != 0);
+                        umma_bf16(tmem_d, dal, dwh, idesc, 1u);
+                        umma_bf16(tmem_d, dah, dwl, idesc, 1u);
+                    }
+                    umma_commit(&empty_bar[stage]);                   // smem slot reusable once these MMAs retire
+                    if (++stage == prm.stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tmem_full_bar[as]);                      // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4; two warps per quarter =====
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        float* ebuf = reinterpret_cast<float*>(epi_smem + (size_t)ew * 4096);
+        const dkt_epilogue& e = prm.epi;
+        const int N = prm.N;
+        const int sub = lane >> 3;           // pixel within a group of 4
+        const int jg = lane & 7;             // 16-byte channel group within the 32-column chunk
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
+            const int b = tile / tiles_per_img;
+            const int r = tile - b * tiles_per_img;
+            const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
+            const uint32_t as = t & 1u, aphase = (t >> 1) & 1u;
+            mbar_wait(&tmem_full_bar[as], aphase);
+            tcgen05_fence_after();
+            const uint32_t tbase = tmem_base + as * prm.acc_cols + ((uint32_t)(q * 32) << 16);
+            for (int c0 = half * 32; c0 < prm.Npad; c0 += 64) {
+                float v[32];
+                const int ncols = (prm.Npad - c0 >= 32) ? 32 : 16;
+                __syncwarp();                       // tcgen05.ld is .sync.aligned; also: previous chunk's reads done
+                if (ncols == 32) {
+                    tmem_ld32(tbase + c0, v);
+                } else {
+                    tmem_ld16(tbase + c0, v);
+#pragma unroll
+                    for (int j = 16; j < 32; ++j) v[j] = 0.f;
+                }
+                tmem_ld_wait();
+                // thread = pixel `lane`: row of 8 x 16 B, chunk j stored at j ^ (lane & 7)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(ebuf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                const int n = c0 + 4 * jg;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = i * 4 + sub;                        // pixel of this warp's quarter
+                    const float4 a = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
+                    const int m = q * 32 + row;
+                    const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
+                    if (y < prm.H && x < prm.W && n < N) {
+                        const int64_t p = ((int64_t)b * prm.H + y) * prm.W + x;
+                        if (n + 3 < N) {
+                            tc_epilogue4(e, N, p, n, a);
+                        } else {
+                            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) if (n + u < N) tc_epilogue1(e, p, n + u, av[u]);
+                        }
+                    }
+                }
+            }
+            if (e.tail && half == 0) {
+                const int m = q * 32 + lane;
+                const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
+                if (y < prm.H && x < prm.W) {
+                    const int64_t p = ((int64_t)b * prm.H + y) * prm.W + x;
+                    for (int u = 0; u < e.tail_C; ++u) store_all(e.out, p, N + u, __ldg(e.tail + p * e.tail_C + u));
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * prm.acc_cols);
 }
 
 }  // namespace dkt
