@@ -22,13 +22,14 @@
 // continues with lanes = 8 x 16-byte channel groups of 4 pixels, so every global access of the
 // fused epilogue (context term, h, z, fp32 / bf16 hi / bf16 lo stores) is a full 128-byte line.
 // The two warps that share a lane quarter take alternate column chunks.
-// BK = K block in channels: 64 (SWIZZLE_128B rows) for N <= 128, 32 (SWIZZLE_64B) for N = 256 so
-// that four stages fit next to the epilogue buffers.
+// BK = K block in channels: 64 (SWIZZLE_128B rows, default) or 32 (SWIZZLE_64B rows, twice the
+// stages at N = 256; measured 2 % slower, kept selectable with DKT_CONV_BK=32).
 //
 // conv_tc_v1_kernel is the first (one tile per CTA, serial epilogue) version, kept selectable
 // with DKT_CONV_TC=v1 for A/B measurements.
 #include "common.cuh"
 #include "tc.cuh"
+#include <stdlib.h>
 
 namespace dkt {
 
@@ -450,6 +451,24 @@ extern "C" int dkt_conv2d_tc(const dkt_tensor* srcs, int nsrc, const uint16_t* w
     if (e.bias && !aligned16(e.bias)) return DKT_E_ALIGNMENT;
     if (!aligned16(e.out.f32) || !aligned16(e.out.hi) || !aligned16(e.out.lo)) return DKT_E_ALIGNMENT;
 
+    // kernel generation / K block: v2 (persistent) unless DKT_CONV_TC=v1; BK = 64 unless DKT_CONV_BK=32
+    static const int s_version = [] { const char* v = getenv("DKT_CONV_TC"); return (v && v[0] == 'v' && v[1] == '1') ? 1 : 2; }();
+    static const int s_bk_env = [] { const char* v = getenv("DKT_CONV_BK"); return v ? atoi(v) : 0; }();
+    static const int s_sms = [] {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = kNumSMs;
+        }
+        return n;
+    }();
+    const int Npad = (N + 15) / 16 * 16;
+    int BK = 64;
+    if (s_version == 2) {
+        // measured on B200 (gru08 z||r, N = 256): 2 stages x BK 64 = 0.957 ms, 4 stages x BK 32 = 0.980 ms
+        if (s_bk_env == 32) BK = 32;
+    }
+
     TcConvParams prm{};
     prm.nsrc = nsrc;
     int cin_total = 0;
@@ -459,50 +478,69 @@ extern "C" int dkt_conv2d_tc(const dkt_tensor* srcs, int nsrc, const uint16_t* w
         if ((t.c_begin % 64) || (t.c_count % 64) || (t.C % 8) || !aligned16(t.hi) || !aligned16(t.lo))
             return DKT_E_ALIGNMENT;
         prm.c_begin[s] = t.c_begin;
-        prm.kblocks[s] = t.c_count / 64;
+        prm.kblocks[s] = t.c_count / BK;
         cin_total += t.c_count;
         const uint64_t dims[4] = {(uint64_t)t.C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
         const uint64_t strides[4] = {1, (uint64_t)t.C, (uint64_t)t.C * W, (uint64_t)t.C * W * H};
-        const uint32_t box[4] = {64, TC_TILE_W, TC_TILE_H, 1};
-        if (!make_tmap_bf16(&prm.act[s][0], t.hi, 4, dims, strides, box)) return DKT_E_DRIVER;
-        if (!make_tmap_bf16(&prm.act[s][1], t.lo, 4, dims, strides, box)) return DKT_E_DRIVER;
+        const uint32_t box[4] = {(uint32_t)BK, TC_TILE_W, TC_TILE_H, 1};
+        if (!make_tmap_bf16(&prm.act[s][0], t.hi, 4, dims, strides, box, BK * 2)) return DKT_E_DRIVER;
+        if (!make_tmap_bf16(&prm.act[s][1], t.lo, 4, dims, strides, box, BK * 2)) return DKT_E_DRIVER;
     }
     prm.ksize = ksize;
     prm.pad = ksize / 2;
     prm.taps = ksize * ksize;
     prm.N = N;
-    prm.Npad = (N + 15) / 16 * 16;
+    prm.Npad = Npad;
     {
         const uint64_t dims[2] = {(uint64_t)cin_total, (uint64_t)prm.taps * prm.Npad};
         const uint64_t strides[2] = {1, (uint64_t)cin_total};
-        const uint32_t box[2] = {64, (uint32_t)prm.Npad};
+        const uint32_t box[2] = {(uint32_t)BK, (uint32_t)prm.Npad};
         if (!aligned16(w_hi) || !aligned16(w_lo)) return DKT_E_ALIGNMENT;
-        if (!make_tmap_bf16(&prm.wgt[0], w_hi, 2, dims, strides, box)) return DKT_E_DRIVER;
-        if (!make_tmap_bf16(&prm.wgt[1], w_lo, 2, dims, strides, box)) return DKT_E_DRIVER;
+        if (!make_tmap_bf16(&prm.wgt[0], w_hi, 2, dims, strides, box, BK * 2)) return DKT_E_DRIVER;
+        if (!make_tmap_bf16(&prm.wgt[1], w_lo, 2, dims, strides, box, BK * 2)) return DKT_E_DRIVER;
     }
     prm.H = H;
     prm.W = W;
     prm.tiles_x = ceil_div(W, TC_TILE_W);
     prm.tiles_y = ceil_div(H, TC_TILE_H);
-    const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * (uint32_t)prm.Npad * 128u;
-    int stages = (int)((200u * 1024u) / stage_bytes);
-    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-    if (stages < 2) return DKT_E_UNSUPPORTED;
-    prm.stages = stages;
+    const int64_t tiles = (int64_t)prm.tiles_x * prm.tiles_y * B;
+    if (tiles > 0x7fffffff) return DKT_E_UNSUPPORTED;
+    prm.num_tiles = (int)tiles;
     uint32_t cols = 32;
     while (cols < (uint32_t)prm.Npad) cols <<= 1;
     prm.tmem_cols = cols;
+    prm.acc_cols = cols;
     prm.epi = e;
+    const uint32_t stage_bytes = 2u * 128u * (uint32_t)BK * 2u + 2u * (uint32_t)prm.Npad * (uint32_t)BK * 2u;
 
-    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align*/ + 128 /*barriers*/;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t ce = cudaFuncSetAttribute(conv_tc_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce != cudaSuccess) return (int)ce;
         attr_set = true;
     }
-    const int64_t tiles = (int64_t)prm.tiles_x * prm.tiles_y * B;
-    if (tiles > 0x7fffffff) return DKT_E_UNSUPPORTED;
-    conv_tc_kernel<<<(unsigned)tiles, TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
+    if (s_version == 1) {
+        int stages = (int)((200u * 1024u) / stage_bytes);
+        if (stages > 4) stages = 4;
+        if (stages < 2) return DKT_E_UNSUPPORTED;
+        prm.stages = stages;
+        const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+        conv_tc_v1_kernel<<<(unsigned)tiles, TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
+        DKT_RETURN_LAST();
+    }
+    // v2: the ring takes what the epilogue buffers and barriers leave of the 227 KB
+    const uint32_t budget = 227u * 1024u - 1024u /*align*/ - TC2_EPI_BYTES - 256u /*barriers*/;
+    int stages = (int)(budget / stage_bytes);
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 2) return DKT_E_UNSUPPORTED;
+    prm.stages = stages;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + TC2_EPI_BYTES + 1024 + 256;
+    const unsigned grid = (unsigned)(tiles < s_sms ? tiles : s_sms);
+    if (BK == 32)
+        conv_tc_kernel<32><<<grid, TC2_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
+    else
+        conv_tc_kernel<64><<<grid, TC2_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
     DKT_RETURN_LAST();
 }

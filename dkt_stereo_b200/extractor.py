@@ -119,8 +119,12 @@ class BasicEncoder(_Trunk):
 class MultiBasicEncoder(_Trunk):
     """cnet: per-scale (hidden, context) heads at 1/4, 1/8, 1/16 for n_downsample=2."""
 
-    def __init__(self, output_dim=((128, 128, 128),), norm_fn: str = "batch", dropout: float = 0.0, downsample: int = 3):
+    def __init__(self, output_dim=((128, 128, 128),), norm_fn: str = "batch", dropout: float = 0.0, downsample: int = 3,
+                 head_names=("outputs08", "outputs16", "outputs32")):
+        """``head_names``: RAFT-Stereo calls the three head lists outputs08/16/32
+        (core/extractor.py:234-258), IGEV-Stereo outputs04/08/16 (igev_stereo/extractor.py:239-256)."""
         super().__init__(norm_fn, downsample)
+        self.head_names = tuple(head_names)
         self.layer4 = self._stage(128, 128, 2)
         self.layer5 = self._stage(128, 128, 2)
 
@@ -131,9 +135,9 @@ class MultiBasicEncoder(_Trunk):
                 out.append(nn.Sequential(ResidualBlock(128, 128, norm_fn, 1), conv) if with_block else conv)
             return nn.ModuleList(out)
 
-        self.outputs08 = heads(2, True)
-        self.outputs16 = heads(1, True)
-        self.outputs32 = heads(0, False)
+        setattr(self, self.head_names[0], heads(2, True))
+        setattr(self, self.head_names[1], heads(1, True))
+        setattr(self, self.head_names[2], heads(0, False))
         self.dropout = nn.Dropout2d(p=dropout) if dropout > 0 else None
         _init_encoder(self)
 
@@ -143,13 +147,14 @@ class MultiBasicEncoder(_Trunk):
         if dual_inp:
             v = x
             x = x[: x.shape[0] // 2]
-        scales = [[f(x) for f in self.outputs08]]
+        h0, h1, h2 = (getattr(self, n) for n in self.head_names)
+        scales = [[f(x) for f in h0]]
         if num_layers >= 2:
             y = self.layer4(x)
-            scales.append([f(y) for f in self.outputs16])
+            scales.append([f(y) for f in h1])
         if num_layers >= 3:
             z = self.layer5(y)
-            scales.append([f(z) for f in self.outputs32])
+            scales.append([f(z) for f in h2])
         if dual_inp:
             scales.append(v)
         return tuple(scales)
