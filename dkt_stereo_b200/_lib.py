@@ -47,7 +47,9 @@ SIGNATURES = {
     "dkt_corr1d_build_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "dkt_corr1d_lookup": [_P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _I64, _I64, _I64, _I, _I, _I, _I, _P],
     "dkt_geo_pool": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "dkt_geo_lookup": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _I64, _I64, _I64, _I, _I, _I, _P],
+    "dkt_corr1d_lookup_enc": [_P, _I, _I, _P, _P, _I, _P, _P, _P, _TP, _I, _I, _I, _I, _P],
+    "dkt_geo_lookup": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I64, _I64, _I64, _I, _I, _I, _P],
+    "dkt_geo_lookup_enc": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _TP, _I, _I, _I, _P],
     "dkt_conv2d_simt": [_TP, _I, _P, _I, _I, _EP, _I, _I, _I, _P],
     "dkt_conv2d_tc": [_TP, _I, _P, _P, _I, _I, _EP, _I, _I, _I, _P],
     "dkt_pool2x": [_TP, _TP, _I, _I, _I, _I, _I, _P],

@@ -45,3 +45,28 @@ def corr_sampler_forward(volume: torch.Tensor, coords: torch.Tensor, radius: int
     out = torch.empty(B, 2 * radius + 1, H, W1, device=volume.device, dtype=torch.float32)
     ops.corr1d_lookup([volume.contiguous().float()], coords[:, 0].contiguous().float(), radius, out, out_layout="nchw")
     return (out,)
+
+
+class Combined_Geo_Encoding_Volume:
+    """Drop-in for reference meta_arch/igev_stereo/geometry.py:6-69: same constructor
+    ``(init_fmap1, init_fmap2, geo_volume, num_levels=2, radius=4)`` and call
+    ``(disp (B,1,h,w), coords (B,h,w,1)) -> (B, 2*9*(2r+1), h, w)`` fp32.  ``coords`` is accepted for
+    signature compatibility; the kernel derives the pixel x coordinate itself (the reference always
+    passes ``arange(w)``, igev_stereo.py:195)."""
+
+    def __init__(self, init_fmap1: torch.Tensor, init_fmap2: torch.Tensor, geo_volume: torch.Tensor,
+                 num_levels: int = 2, radius: int = 4, impl: str = "tc"):
+        L.require_device(init_fmap1)
+        if num_levels != 2:
+            raise NotImplementedError("the B200 geometry lookup serves the shipped 2-level configuration")
+        self.num_levels, self.radius = num_levels, radius
+        self.init_corr_pyramid = ops.corr1d_build(init_fmap1.float(), init_fmap2.float(), num_levels, 1.0, impl=impl)
+        self.geo_volume_pyramid = list(ops.geo_pool(geo_volume.float()))
+
+    def __call__(self, disp: torch.Tensor, coords: torch.Tensor | None = None) -> torch.Tensor:
+        B, _, H, W = disp.shape
+        Cg = self.geo_volume_pyramid[0].shape[3]
+        out = torch.empty(B, self.num_levels * (Cg + 1) * (2 * self.radius + 1), H, W, device=disp.device, dtype=torch.float32)
+        d = disp[:, 0].contiguous().float().clone()
+        ops.geo_lookup(self.geo_volume_pyramid, self.init_corr_pyramid, d, self.radius, out, out_layout="nchw")
+        return out

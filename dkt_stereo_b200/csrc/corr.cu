@@ -118,7 +118,15 @@ corr1d_build_simt_kernel(const float* __restrict__ f1, const float* __restrict__
 // ---------------------------------------------------------------------------------------------
 // K2: per pixel, per level: 2r+2 adjacent volume entries -> 2r+1 linearly interpolated taps
 // (all taps of a level share one fractional weight because the tap offsets are integers).
-// One thread per pixel; the (optional) coordinate update is fused in front.
+//
+// A CTA owns LK_PIX = 32 consecutive pixels.  Phase 1 (one thread per (pixel, row-sample))
+// gathers the taps into a shared tile [32][C]; phase 2 either streams the tile out with
+// fully coalesced 16-byte stores (fp32 + optional bf16 hi/lo, NHWC fast path; any strides on the
+// generic path) or -- ENC = true -- applies the motion encoder's 1x1 convolution + bias + ReLU
+// (reference core/update.py:79 `convc1`) in exact fp32 straight from the tile, so the 36 / 162
+// channel lookup result never travels to HBM.  The coordinate bookkeeping of the loop body
+// (`coords1 += delta_flow`, `flow = coords1 - coords0`, IGEV `disp += delta_disp`) is fused in
+// front: the CTA reads its 32 coordinates once, updates them in shared memory and writes back.
 // ---------------------------------------------------------------------------------------------
 template <int R>
 __device__ __forceinline__ void sample_row(const float* __restrict__ row, int W, float x, float* taps) {
@@ -140,41 +148,190 @@ struct ConstPyrPtrs {
     int          w[DKT_MAX_LEVELS];
 };
 
-template <int R>
-__global__ void __launch_bounds__(128)
-corr1d_lookup_kernel(ConstPyrPtrs pyr, int levels, float* __restrict__ coords_x,
-                     const float* __restrict__ delta, int delta_C, float* __restrict__ flow,
-                     float* __restrict__ out, uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo,
-                     int64_t ob, int64_t oc, int64_t op, int64_t P, int HW, int W1) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    float cx = coords_x[p];
-    if (delta) {
-        cx += delta[p * delta_C];
-        coords_x[p] = cx;
-    }
-    if (flow) flow[p * 2] = cx - (float)(p % W1);
-    if (!out) return;
-    const int64_t b = p / HW;
-    const int64_t pix = p - b * HW;
-    const int64_t obase = b * ob + pix * op;
-    float inv = 1.f;
-    for (int l = 0; l < levels; ++l) {
-        float taps[2 * R + 1];
-        sample_row<R>(pyr.p[l] + p * pyr.w[l], pyr.w[l], cx * inv, taps);
-        inv *= 0.5f;
+constexpr int LK_PIX = 32;
+constexpr int LK_ENC_N = 64;          // output channels of convc1
+
+struct LookupOut {
+    float* f32; uint16_t* hi; uint16_t* lo;     // plain output (ENC = false)
+    int64_t ob, oc, op;
+    int fast;                                    // NHWC, oc == 1, ob == HW * op, op % 4 == 0
+    const float* enc_w;                          // ENC: [C][64] fp32 (k-major), bias [64]
+    const float* enc_b;
+    dkt_tensor enc_out;                          // ENC: 64-channel NHWC slice
+};
+
+// phase 2, plain: tile (row stride TS) -> global
+__device__ __forceinline__ void lookup_store_tile(const float* tile, int TS, int C, const LookupOut& o,
+                                                  int64_t p0, int npix, int HW) {
+    if (o.fast) {
+        const int C4 = (int)o.op >> 2;           // 16-byte groups per pixel row (incl. zero padding)
+        for (int i = threadIdx.x; i < npix * C4; i += blockDim.x) {
+            const int px = i / C4, c = (i - px * C4) << 2;
+            float v[4];
 #pragma unroll
-        for (int k = 0; k < 2 * R + 1; ++k) {
-            int64_t o = obase + (int64_t)(l * (2 * R + 1) + k) * oc;
-            out[o] = taps[k];
-            if (out_hi) {
-                uint16_t h, lo_;
-                split_bf16(taps[k], h, lo_);
-                out_hi[o] = h;
-                if (out_lo) out_lo[o] = lo_;
+            for (int u = 0; u < 4; ++u) v[u] = (c + u < C) ? tile[px * TS + c + u] : 0.f;
+            const int64_t off = (p0 + px) * o.op + c;
+            *reinterpret_cast<float4*>(o.f32 + off) = make_float4(v[0], v[1], v[2], v[3]);
+            if (o.hi) {
+                uint32_t h0, l0, h1, l1;
+                split_bf16x2(v[0], v[1], h0, l0);
+                split_bf16x2(v[2], v[3], h1, l1);
+                *reinterpret_cast<uint2*>(o.hi + off) = make_uint2(h0, h1);
+                if (o.lo) *reinterpret_cast<uint2*>(o.lo + off) = make_uint2(l0, l1);
+            }
+        }
+    } else {
+        // generic strides (e.g. NCHW for the drop-in CorrBlock1D): pixel fastest for coalescing
+        for (int i = threadIdx.x; i < npix * C; i += blockDim.x) {
+            const int c = i / npix, px = i - c * npix;
+            const int64_t p = p0 + px;
+            const int64_t b = p / HW;
+            const int64_t off = b * o.ob + (p - b * HW) * o.op + (int64_t)c * o.oc;
+            const float v = tile[px * TS + c];
+            o.f32[off] = v;
+            if (o.hi) {
+                uint16_t h, l;
+                split_bf16(v, h, l);
+                o.hi[off] = h;
+                if (o.lo) o.lo[off] = l;
             }
         }
     }
+}
+
+// phase 2, ENC: out[px][n] = relu(b[n] + sum_k tile[px][k] * w[k][n]), n < 64.
+// thread -> 4 consecutive channels (cg = tid & 15) of PPT pixels (pg = tid >> 4).
+template <int PPT>
+__device__ __forceinline__ void lookup_encode_tile(const float* tile, int TS, int C, const float* ws,
+                                                   const LookupOut& o, int64_t p0, int npix) {
+    const int cg = threadIdx.x & 15, pg = threadIdx.x >> 4;
+    float acc[PPT][4];
+    const float4 bias = *reinterpret_cast<const float4*>(o.enc_b + cg * 4);
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) { acc[i][0] = bias.x; acc[i][1] = bias.y; acc[i][2] = bias.z; acc[i][3] = bias.w; }
+    const float* trow = tile + pg * PPT * TS;
+    for (int k = 0; k < C; ++k) {
+        const float4 w = *reinterpret_cast<const float4*>(ws + k * LK_ENC_N + cg * 4);
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const float a = trow[i * TS + k];
+            acc[i][0] = fmaf(a, w.x, acc[i][0]);
+            acc[i][1] = fmaf(a, w.y, acc[i][1]);
+            acc[i][2] = fmaf(a, w.z, acc[i][2]);
+            acc[i][3] = fmaf(a, w.w, acc[i][3]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int px = pg * PPT + i;
+        if (px < npix)
+            store_all4(o.enc_out, p0 + px, cg * 4,
+                       make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f), fmaxf(acc[i][3], 0.f)));
+    }
+}
+
+// RAFT-Stereo: 128 threads = 32 pixels x 4 levels.
+template <int R, bool ENC>
+__global__ void __launch_bounds__(128)
+corr1d_lookup_kernel(ConstPyrPtrs pyr, int levels, float* __restrict__ coords_x,
+                     const float* __restrict__ delta, int delta_C, float* __restrict__ flow,
+                     LookupOut o, int64_t P, int HW, int W1) {
+    constexpr int T = 2 * R + 1;
+    constexpr int TS = DKT_MAX_LEVELS * T + 1;                 // odd row stride: conflict-free column walks
+    __shared__ float s_x[LK_PIX];
+    __shared__ __align__(16) float tile[LK_PIX * TS];
+    __shared__ __align__(16) float ws[ENC ? DKT_MAX_LEVELS * T * LK_ENC_N : 4];
+    const int64_t p0 = (int64_t)blockIdx.x * LK_PIX;
+    const int npix = (int)((P - p0) < LK_PIX ? (P - p0) : LK_PIX);
+    const int C = levels * T;
+    if (ENC) {
+        for (int i = threadIdx.x; i < C * LK_ENC_N / 4; i += blockDim.x)
+            reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(o.enc_w) + i);
+    }
+    if (threadIdx.x < npix) {
+        const int64_t p = p0 + threadIdx.x;
+        float cx = coords_x[p];
+        if (delta) {
+            cx += delta[p * delta_C];
+            coords_x[p] = cx;
+        }
+        if (flow) flow[p * 2] = cx - (float)(p % W1);
+        s_x[threadIdx.x] = cx;
+    }
+    if (levels == 0) return;
+    __syncthreads();
+    {
+        const int px = threadIdx.x >> 2, l = threadIdx.x & 3;
+        if (px < npix && l < levels) {
+            float taps[T];
+            sample_row<R>(pyr.p[l] + (p0 + px) * pyr.w[l], pyr.w[l], s_x[px] * (1.f / (float)(1 << l)), taps);
+#pragma unroll
+            for (int k = 0; k < T; ++k) tile[px * TS + l * T + k] = taps[k];
+        }
+    }
+    __syncthreads();
+    if (ENC) lookup_encode_tile<4>(tile, TS, C, ws, o, p0, npix);
+    else lookup_store_tile(tile, TS, C, o, p0, npix, HW);
+}
+
+// IGEV: per pixel 2 levels x (Cg geometry channels + 1 init-corr row) row samples; the channel
+// order of the reference is level-major: [geo(Cg*T), init(T)] per level (geometry.py:36-57).
+// 256 threads walk the 32 * 2 * (Cg+1) row samples of the CTA's pixels.
+struct GeoPtrs {
+    const float* geo[2];
+    const float* init[2];
+};
+
+template <int R, bool ENC>
+__global__ void __launch_bounds__(256)
+geo_lookup_kernel(GeoPtrs g, float* __restrict__ disp, const float* __restrict__ delta, int delta_C,
+                  int Cg, int D, int W, LookupOut o, int64_t P, int HW) {
+    constexpr int T = 2 * R + 1;
+    extern __shared__ __align__(16) float gsm[];
+    const int G = 2 * (Cg + 1);
+    const int C = G * T;
+    const int TS = C | 1;
+    float* s_d = gsm;                         // [32]
+    float* tile = gsm + LK_PIX;               // [32][TS]
+    float* ws = tile + ((LK_PIX * TS + 3) & ~3);   // ENC: [C][64]
+    const int64_t p0 = (int64_t)blockIdx.x * LK_PIX;
+    const int npix = (int)((P - p0) < LK_PIX ? (P - p0) : LK_PIX);
+    if (ENC) {
+        for (int i = threadIdx.x; i < C * LK_ENC_N / 4; i += blockDim.x)
+            reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(o.enc_w) + i);
+    }
+    if (threadIdx.x < npix) {
+        const int64_t p = p0 + threadIdx.x;
+        float d = disp[p];
+        if (delta) {
+            d += delta[p * delta_C];
+            disp[p] = d;
+        }
+        s_d[threadIdx.x] = d;
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < npix * G; it += blockDim.x) {
+        const int px = it / G, gi = it - px * G;
+        const int l = gi / (Cg + 1), j = gi - l * (Cg + 1);
+        const int64_t p = p0 + px;
+        const float d = s_d[px];
+        const float inv = l ? 0.5f : 1.f;
+        float taps[T];
+        if (j < Cg) {
+            const int Dl = l ? D / 2 : D;
+            sample_row<R>(g.geo[l] + (p * Cg + j) * Dl, Dl, d * inv, taps);
+        } else {
+            const int Wl = l ? W / 2 : W;
+            const float x = (float)(p % W);
+            sample_row<R>(g.init[l] + p * Wl, Wl, x * inv - d * inv, taps);
+        }
+        float* dst = tile + px * TS + gi * T;
+#pragma unroll
+        for (int k = 0; k < T; ++k) dst[k] = taps[k];
+    }
+    __syncthreads();
+    if (ENC) lookup_encode_tile<2>(tile, TS, C, ws, o, p0, npix);
+    else lookup_store_tile(tile, TS, C, o, p0, npix, HW);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -210,50 +367,6 @@ geo_pool_kernel(const float* __restrict__ gev, float* __restrict__ geo0, float* 
     }
 }
 
-// One thread per (pixel, group); group g in [0, 2*(C+1)): level = g / (C+1), j = g % (C+1):
-// j < C -> geometry channel j sampled at disp/2^l ; j == C -> init-corr sampled at (x - disp)/2^l.
-template <int R>
-__global__ void __launch_bounds__(128)
-geo_lookup_kernel(const float* __restrict__ geo0, const float* __restrict__ geo1,
-                  const float* __restrict__ init0, const float* __restrict__ init1,
-                  const float* __restrict__ disp, int C, int D, int W,
-                  float* __restrict__ out, uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo,
-                  int64_t ob, int64_t oc, int64_t op, int64_t P, int HW) {
-    const int G = 2 * (C + 1);
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P * G) return;
-    const int64_t p = t / G;
-    const int g = (int)(t - p * G);
-    const int l = g / (C + 1), j = g % (C + 1);
-    const float d = disp[p];
-    const float inv = l ? 0.5f : 1.f;
-    float taps[2 * R + 1];
-    if (j < C) {
-        const int Dl = l ? D / 2 : D;
-        const float* row = (l ? geo1 : geo0) + (p * C + j) * Dl;
-        sample_row<R>(row, Dl, d * inv, taps);
-    } else {
-        const int Wl = l ? W / 2 : W;
-        const float* row = (l ? init1 : init0) + p * Wl;
-        const float x = (float)(p % W);
-        sample_row<R>(row, Wl, x * inv - d * inv, taps);
-    }
-    const int64_t b = p / HW;
-    const int64_t obase = b * ob + (p - b * HW) * op;
-    const int cbase = l * (C + 1) * (2 * R + 1) + j * (2 * R + 1);
-#pragma unroll
-    for (int k = 0; k < 2 * R + 1; ++k) {
-        int64_t o = obase + (int64_t)(cbase + k) * oc;
-        out[o] = taps[k];
-        if (out_hi) {
-            uint16_t h, lo_;
-            split_bf16(taps[k], h, lo_);
-            out_hi[o] = h;
-            if (out_lo) out_lo[o] = lo_;
-        }
-    }
-}
-
 }  // namespace dkt
 
 using namespace dkt;
@@ -280,30 +393,73 @@ extern "C" int dkt_corr1d_build_f32(const float* fmap1, const float* fmap2,
     DKT_RETURN_LAST();
 }
 
-extern "C" int dkt_corr1d_lookup(const float* const* pyr, int levels, int radius,
-                                 float* coords_x, const float* delta, int delta_C, float* flow,
-                                 float* out, uint16_t* out_hi, uint16_t* out_lo,
-                                 int64_t ob, int64_t oc, int64_t op,
-                                 int B, int H, int W1, int W2, void* stream) {
+static int fill_plain_out(LookupOut& o, float* out, uint16_t* out_hi, uint16_t* out_lo,
+                          int64_t ob, int64_t oc, int64_t op, int HW) {
+    o = LookupOut{};
+    o.f32 = out; o.hi = out_hi; o.lo = out_lo;
+    o.ob = ob; o.oc = oc; o.op = op;
+    const bool al = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out_hi) & 7) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(out_lo) & 7) == 0);
+    o.fast = (oc == 1 && op % 4 == 0 && ob == (int64_t)HW * op && al) ? 1 : 0;
+    return 0;
+}
+
+static int fill_enc_out(LookupOut& o, const float* enc_w, const float* enc_b, const dkt_tensor* enc_out) {
+    o = LookupOut{};
+    if (!enc_w || !enc_b || !enc_out) return DKT_E_INVALID;
+    if (!(enc_out->f32 || enc_out->hi) || enc_out->c_count != LK_ENC_N) return DKT_E_INVALID;
+    if ((enc_out->C % 4) || (enc_out->c_begin % 4)) return DKT_E_ALIGNMENT;
+    if ((reinterpret_cast<uintptr_t>(enc_w) & 15) || (reinterpret_cast<uintptr_t>(enc_b) & 15)) return DKT_E_ALIGNMENT;
+    o.enc_w = enc_w; o.enc_b = enc_b; o.enc_out = *enc_out;
+    return 0;
+}
+
+static int corr1d_lookup_launch(const float* const* pyr, int levels, int radius, float* coords_x,
+                                const float* delta, int delta_C, float* flow, const LookupOut& o, bool enc, bool want_out,
+                                int B, int H, int W1, int W2, void* stream) {
     DKT_CHECK_ARG(coords_x);
     DKT_CHECK_ARG(B > 0 && H > 0 && W1 > 0);
     if (levels < 0 || levels > DKT_MAX_LEVELS) return DKT_E_UNSUPPORTED;
     ConstPyrPtrs pp;
     int w = W2;
     for (int l = 0; l < DKT_MAX_LEVELS; ++l) {
-        pp.p[l] = (out && l < levels) ? pyr[l] : nullptr;
+        pp.p[l] = (want_out && l < levels) ? pyr[l] : nullptr;
         pp.w[l] = w;
-        if (out && l < levels) { DKT_CHECK_ARG(pyr && pyr[l] != nullptr && w > 0); }
+        if (want_out && l < levels) { DKT_CHECK_ARG(pyr && pyr[l] != nullptr && w > 0); }
         w /= 2;
     }
-    if (out && radius != 4) return DKT_E_UNSUPPORTED;   // configs/*/base.json: corr_radius = 4
+    if (want_out && radius != 4) return DKT_E_UNSUPPORTED;   // configs/*/base.json: corr_radius = 4
     if (delta) DKT_CHECK_ARG(delta_C > 0);
     const int64_t P = (int64_t)B * H * W1;
-    const int threads = 128;
-    const int64_t blocks = ceil_div64(P, threads);
-    corr1d_lookup_kernel<4><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        pp, levels, coords_x, delta, delta_C, flow, out, out_hi, out_lo, ob, oc, op, P, H * W1, W1);
+    const unsigned blocks = (unsigned)ceil_div64(P, LK_PIX);
+    const int lv = want_out ? levels : 0;
+    if (enc)
+        corr1d_lookup_kernel<4, true><<<blocks, 128, 0, (cudaStream_t)stream>>>(pp, lv, coords_x, delta, delta_C, flow, o, P, H * W1, W1);
+    else
+        corr1d_lookup_kernel<4, false><<<blocks, 128, 0, (cudaStream_t)stream>>>(pp, lv, coords_x, delta, delta_C, flow, o, P, H * W1, W1);
     DKT_RETURN_LAST();
+}
+
+extern "C" int dkt_corr1d_lookup(const float* const* pyr, int levels, int radius,
+                                 float* coords_x, const float* delta, int delta_C, float* flow,
+                                 float* out, uint16_t* out_hi, uint16_t* out_lo,
+                                 int64_t ob, int64_t oc, int64_t op,
+                                 int B, int H, int W1, int W2, void* stream) {
+    LookupOut o;
+    fill_plain_out(o, out, out_hi, out_lo, ob, oc, op, H * W1);
+    return corr1d_lookup_launch(pyr, levels, radius, coords_x, delta, delta_C, flow, o, false, out != nullptr,
+                                B, H, W1, W2, stream);
+}
+
+extern "C" int dkt_corr1d_lookup_enc(const float* const* pyr, int levels, int radius,
+                                     float* coords_x, const float* delta, int delta_C, float* flow,
+                                     const float* enc_w, const float* enc_b, const dkt_tensor* enc_out,
+                                     int B, int H, int W1, int W2, void* stream) {
+    LookupOut o;
+    int rc = fill_enc_out(o, enc_w, enc_b, enc_out);
+    if (rc) return rc;
+    DKT_CHECK_ARG(levels >= 1);
+    return corr1d_lookup_launch(pyr, levels, radius, coords_x, delta, delta_C, flow, o, true, true, B, H, W1, W2, stream);
 }
 
 extern "C" int dkt_geo_pool(const float* gev, float* geo0, float* geo1, int B, int C, int D, int H, int W,
@@ -324,17 +480,52 @@ extern "C" int dkt_geo_pool(const float* gev, float* geo0, float* geo1, int B, i
     DKT_RETURN_LAST();
 }
 
+static int geo_lookup_launch(const float* geo0, const float* geo1, const float* init0, const float* init1,
+                             float* disp, const float* delta, int delta_C, int radius, int C, int D,
+                             const LookupOut& o, bool enc, int B, int H, int W, void* stream) {
+    DKT_CHECK_ARG(geo0 && geo1 && init0 && init1 && disp);
+    DKT_CHECK_ARG(B > 0 && H > 0 && W > 1 && C > 0 && D > 1);
+    if (radius != 4) return DKT_E_UNSUPPORTED;
+    if (delta) DKT_CHECK_ARG(delta_C > 0);
+    const int64_t P = (int64_t)B * H * W;
+    const int Cout = 2 * (C + 1) * 9;
+    const int TS = Cout | 1;
+    size_t smem = (size_t)(LK_PIX + ((LK_PIX * TS + 3) & ~3)) * 4;
+    if (enc) smem += (size_t)Cout * LK_ENC_N * 4;
+    if (smem > 200 * 1024) return DKT_E_UNSUPPORTED;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t ce = cudaFuncSetAttribute(geo_lookup_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(geo_lookup_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ce != cudaSuccess) return (int)ce;
+        attr_set = true;
+    }
+    GeoPtrs g{{geo0, geo1}, {init0, init1}};
+    const unsigned blocks = (unsigned)ceil_div64(P, LK_PIX);
+    if (enc)
+        geo_lookup_kernel<4, true><<<blocks, 256, smem, (cudaStream_t)stream>>>(g, disp, delta, delta_C, C, D, W, o, P, H * W);
+    else
+        geo_lookup_kernel<4, false><<<blocks, 256, smem, (cudaStream_t)stream>>>(g, disp, delta, delta_C, C, D, W, o, P, H * W);
+    DKT_RETURN_LAST();
+}
+
 extern "C" int dkt_geo_lookup(const float* geo0, const float* geo1, const float* init0, const float* init1,
-                              const float* disp, int radius, int C, int D,
+                              float* disp, const float* delta, int delta_C, int radius, int C, int D,
                               float* out, uint16_t* out_hi, uint16_t* out_lo,
                               int64_t ob, int64_t oc, int64_t op,
                               int B, int H, int W, void* stream) {
-    DKT_CHECK_ARG(geo0 && geo1 && init0 && init1 && disp && out);
-    DKT_CHECK_ARG(B > 0 && H > 0 && W > 1 && C > 0 && D > 1);
-    if (radius != 4) return DKT_E_UNSUPPORTED;
-    const int64_t P = (int64_t)B * H * W;
-    const int64_t T = P * 2 * (C + 1);
-    geo_lookup_kernel<4><<<(unsigned)ceil_div64(T, 128), 128, 0, (cudaStream_t)stream>>>(
-        geo0, geo1, init0, init1, disp, C, D, W, out, out_hi, out_lo, ob, oc, op, P, H * W);
-    DKT_RETURN_LAST();
+    DKT_CHECK_ARG(out);
+    LookupOut o;
+    fill_plain_out(o, out, out_hi, out_lo, ob, oc, op, H * W);
+    return geo_lookup_launch(geo0, geo1, init0, init1, disp, delta, delta_C, radius, C, D, o, false, B, H, W, stream);
+}
+
+extern "C" int dkt_geo_lookup_enc(const float* geo0, const float* geo1, const float* init0, const float* init1,
+                                  float* disp, const float* delta, int delta_C, int radius, int C, int D,
+                                  const float* enc_w, const float* enc_b, const dkt_tensor* enc_out,
+                                  int B, int H, int W, void* stream) {
+    LookupOut o;
+    int rc = fill_enc_out(o, enc_w, enc_b, enc_out);
+    if (rc) return rc;
+    return geo_lookup_launch(geo0, geo1, init0, init1, disp, delta, delta_C, radius, C, D, o, true, B, H, W, stream);
 }

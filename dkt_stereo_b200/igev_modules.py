@@ -1,0 +1,227 @@
+"""PyTorch-side modules of IGEV-Stereo that run BEFORE the hot loop (feature pyramid, group-wise
+correlation volume, 3-D hourglass regularisation, soft-argmin initial disparity) and the small
+up-sampling convs after it.  They stay on cuDNN (SURVEY section 8f rank 2 is the "next" row that
+moves them); only their *products* -- matching features, geometry encoding volume, initial
+disparity, context terms -- enter the B200 kernels.
+
+Parameter names reproduce the reference so that IGEV / DKT-IGEV checkpoints load with
+``strict=True``:
+
+* ``ConvNormAct``  <- ``BasicConv`` / ``BasicConv_IN`` (meta_arch/igev_stereo/submodule.py:10-36, 80-106):
+  attributes ``conv`` + ``bn`` or ``IN``; LeakyReLU(0.01).
+* ``UpFuse``       <- ``Conv2x`` / ``Conv2x_IN`` (submodule.py:39-78, 109-148): ``conv1``, ``conv2``.
+* ``FeatureAtt``   <- submodule.py:227-240: ``feat_att.{0,1}``.
+* ``Hourglass``    <- ``hourglass`` (meta_arch/igev_stereo/igev_stereo.py:22-89).
+* ``Feature``      <- meta_arch/igev_stereo/extractor.py:327-361.  The reference builds it from
+  ``timm.create_model('mobilenetv2_100')`` (timm 0.5.4, not available offline); the MobileNetV2
+  below is written out with timm's attribute names (``conv_stem``, ``bn1``, ``conv_pw``,
+  ``conv_dw``, ``conv_pwl``, ``bn1..3``) so the state-dict keys match.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+# ---------------------------------------------------------------------------------------------
+# conv + norm + LeakyReLU in 2-D / 3-D, conv or transposed conv
+# ---------------------------------------------------------------------------------------------
+class ConvNormAct(nn.Module):
+    def __init__(self, cin: int, cout: int, norm: str = "bn", use_norm: bool = True, act: bool = True,
+                 deconv: bool = False, is_3d: bool = False, **conv_kw):
+        super().__init__()
+        assert norm in ("bn", "in")
+        conv_cls = {(False, False): nn.Conv2d, (False, True): nn.ConvTranspose2d,
+                    (True, False): nn.Conv3d, (True, True): nn.ConvTranspose3d}[(is_3d, deconv)]
+        self.conv = conv_cls(cin, cout, bias=False, **conv_kw)
+        if norm == "bn":
+            self.bn = (nn.BatchNorm3d if is_3d else nn.BatchNorm2d)(cout)
+        else:
+            self.IN = (nn.InstanceNorm3d if is_3d else nn.InstanceNorm2d)(cout)
+        self._norm_name = "bn" if norm == "bn" else "IN"
+        self.use_norm = use_norm
+        self.act = act
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.use_norm:
+            x = getattr(self, self._norm_name)(x)
+        return F.leaky_relu(x, 0.01) if self.act else x
+
+
+class UpFuse(nn.Module):
+    """Strided (de)conv to the skip tensor's resolution, concatenate with it, 3x3 conv."""
+
+    def __init__(self, cin: int, cout: int, deconv: bool = False, norm: str = "bn", keep_concat: bool = True):
+        super().__init__()
+        k = 4 if deconv else 3
+        self.conv1 = ConvNormAct(cin, cout, norm, deconv=deconv, kernel_size=k, stride=2, padding=1)
+        self.conv2 = ConvNormAct(cout * 2, cout * (2 if keep_concat else 1), norm, kernel_size=3, stride=1, padding=1)
+
+    def forward(self, x, skip):
+        x = self.conv1(x)
+        if x.shape != skip.shape:
+            x = F.interpolate(x, size=skip.shape[-2:], mode="nearest")
+        return self.conv2(torch.cat((x, skip), 1))
+
+
+class FeatureAtt(nn.Module):
+    """Channel attention of a cost volume from a 2-D feature map: cv * sigmoid(conv(feat))."""
+
+    def __init__(self, cv_chan: int, feat_chan: int):
+        super().__init__()
+        self.feat_att = nn.Sequential(ConvNormAct(feat_chan, feat_chan // 2, kernel_size=1, stride=1, padding=0),
+                                      nn.Conv2d(feat_chan // 2, cv_chan, 1))
+
+    def forward(self, cv, feat):
+        return torch.sigmoid(self.feat_att(feat).unsqueeze(2)) * cv
+
+
+class Hourglass(nn.Module):
+    def __init__(self, c: int):
+        super().__init__()
+
+        def down(cin, cout):
+            return nn.Sequential(ConvNormAct(cin, cout, is_3d=True, kernel_size=3, padding=1, stride=2, dilation=1),
+                                 ConvNormAct(cout, cout, is_3d=True, kernel_size=3, padding=1, stride=1, dilation=1))
+
+        def up(cin, cout, **kw):
+            return ConvNormAct(cin, cout, deconv=True, is_3d=True, kernel_size=(4, 4, 4), padding=(1, 1, 1),
+                               stride=(2, 2, 2), **kw)
+
+        def agg(cin, cout):
+            return nn.Sequential(ConvNormAct(cin, cout, is_3d=True, kernel_size=1, padding=0, stride=1),
+                                 ConvNormAct(cout, cout, is_3d=True, kernel_size=3, padding=1, stride=1),
+                                 ConvNormAct(cout, cout, is_3d=True, kernel_size=3, padding=1, stride=1))
+
+        self.conv1, self.conv2, self.conv3 = down(c, 2 * c), down(2 * c, 4 * c), down(4 * c, 6 * c)
+        self.conv3_up, self.conv2_up = up(6 * c, 4 * c), up(4 * c, 2 * c)
+        self.conv1_up = up(2 * c, 8, use_norm=False, act=False)
+        self.agg_0, self.agg_1 = agg(8 * c, 4 * c), agg(4 * c, 2 * c)
+        self.feature_att_8 = FeatureAtt(2 * c, 64)
+        self.feature_att_16 = FeatureAtt(4 * c, 192)
+        self.feature_att_32 = FeatureAtt(6 * c, 160)
+        self.feature_att_up_16 = FeatureAtt(4 * c, 192)
+        self.feature_att_up_8 = FeatureAtt(2 * c, 64)
+
+    def forward(self, x, feats: Sequence[torch.Tensor]):
+        c1 = self.feature_att_8(self.conv1(x), feats[1])
+        c2 = self.feature_att_16(self.conv2(c1), feats[2])
+        c3 = self.feature_att_32(self.conv3(c2), feats[3])
+        c2 = self.feature_att_up_16(self.agg_0(torch.cat((self.conv3_up(c3), c2), 1)), feats[2])
+        c1 = self.feature_att_up_8(self.agg_1(torch.cat((self.conv2_up(c2), c1), 1)), feats[1])
+        return self.conv1_up(c1)
+
+
+# ---------------------------------------------------------------------------------------------
+# MobileNetV2-1.0 feature pyramid with timm's module / parameter names
+# ---------------------------------------------------------------------------------------------
+class _DSConv(nn.Module):
+    """timm DepthwiseSeparableConv: 3x3 depthwise + BN + ReLU6, 1x1 project + BN."""
+
+    def __init__(self, cin: int, cout: int, stride: int):
+        super().__init__()
+        self.conv_dw = nn.Conv2d(cin, cin, 3, stride, 1, groups=cin, bias=False)
+        self.bn1 = nn.BatchNorm2d(cin)
+        self.act1 = nn.ReLU6(inplace=True)
+        self.conv_pw = nn.Conv2d(cin, cout, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.skip = stride == 1 and cin == cout
+
+    def forward(self, x):
+        y = self.bn2(self.conv_pw(self.act1(self.bn1(self.conv_dw(x)))))
+        return x + y if self.skip else y
+
+
+class _InvertedResidual(nn.Module):
+    """timm InvertedResidual: 1x1 expand, 3x3 depthwise, 1x1 linear projection."""
+
+    def __init__(self, cin: int, cout: int, stride: int, expand: int = 6):
+        super().__init__()
+        mid = cin * expand
+        self.conv_pw = nn.Conv2d(cin, mid, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(mid)
+        self.act1 = nn.ReLU6(inplace=True)
+        self.conv_dw = nn.Conv2d(mid, mid, 3, stride, 1, groups=mid, bias=False)
+        self.bn2 = nn.BatchNorm2d(mid)
+        self.act2 = nn.ReLU6(inplace=True)
+        self.conv_pwl = nn.Conv2d(mid, cout, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(cout)
+        self.skip = stride == 1 and cin == cout
+
+    def forward(self, x):
+        y = self.act1(self.bn1(self.conv_pw(x)))
+        y = self.act2(self.bn2(self.conv_dw(y)))
+        y = self.bn3(self.conv_pwl(y))
+        return x + y if self.skip else y
+
+
+# (repeats, out channels, first stride) of MobileNetV2-1.0 stages 1..5 (stage 0 is the DS conv, stage 6 unused)
+_MBV2_STAGES = ((2, 24, 2), (3, 32, 2), (4, 64, 2), (3, 96, 1), (3, 160, 2))
+
+
+def _mbv2_stage(cin: int, reps: int, cout: int, stride: int) -> nn.Sequential:
+    return nn.Sequential(*[_InvertedResidual(cin if i == 0 else cout, cout, stride if i == 0 else 1) for i in range(reps)])
+
+
+class Feature(nn.Module):
+    """1/4, 1/8, 1/16, 1/32 features: MobileNetV2 encoder + U-Net style decoder with instance norm."""
+
+    def __init__(self):
+        super().__init__()
+        chans = [16, 24, 32, 96, 160]
+        self.conv_stem = nn.Conv2d(3, 32, 3, 2, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(32)
+        self.act1 = nn.ReLU6(inplace=True)
+        stages = [nn.Sequential(_DSConv(32, 16, 1))]
+        cin = 16
+        for reps, cout, stride in _MBV2_STAGES:
+            stages.append(_mbv2_stage(cin, reps, cout, stride))
+            cin = cout
+        # the reference regroups timm's stage list as blocks[0:1], [1:2], [2:3], [3:5], [5:6]
+        self.block0 = nn.Sequential(stages[0])
+        self.block1 = nn.Sequential(stages[1])
+        self.block2 = nn.Sequential(stages[2])
+        self.block3 = nn.Sequential(stages[3], stages[4])
+        self.block4 = nn.Sequential(stages[5])
+        self.deconv32_16 = UpFuse(chans[4], chans[3], deconv=True, norm="in")
+        self.deconv16_8 = UpFuse(chans[3] * 2, chans[2], deconv=True, norm="in")
+        self.deconv8_4 = UpFuse(chans[2] * 2, chans[1], deconv=True, norm="in")
+        self.conv4 = ConvNormAct(chans[1] * 2, chans[1] * 2, "in", kernel_size=3, stride=1, padding=1)
+
+    def forward(self, x) -> List[torch.Tensor]:
+        x2 = self.block0(self.act1(self.bn1(self.conv_stem(x))))
+        x4 = self.block1(x2)
+        x8 = self.block2(x4)
+        x16 = self.block3(x8)
+        x32 = self.block4(x16)
+        x16 = self.deconv32_16(x32, x16)
+        x8 = self.deconv16_8(x16, x8)
+        x4 = self.conv4(self.deconv8_4(x8, x4))
+        return [x4, x8, x16, x32]
+
+
+# ---------------------------------------------------------------------------------------------
+# volume helpers
+# ---------------------------------------------------------------------------------------------
+def build_gwc_volume(ref: torch.Tensor, tgt: torch.Tensor, maxdisp: int, groups: int) -> torch.Tensor:
+    """Group-wise correlation volume (B, groups, maxdisp, H, W): for disparity d, the mean over each
+    channel group of ref[..., x] * tgt[..., x - d], zero where x < d (reference submodule.py:152-170).
+    One fused expression per disparity on views (no Python-side masking)."""
+    B, C, H, W = ref.shape
+    cpg = C // groups
+    vol = ref.new_zeros(B, groups, maxdisp, H, W)
+    r = ref.view(B, groups, cpg, H, W)
+    t = tgt.view(B, groups, cpg, H, W)
+    for d in range(min(maxdisp, W)):
+        vol[:, :, d, :, d:] = (r[..., d:] * t[..., : W - d]).mean(dim=2)
+    return vol
+
+
+def disparity_regression(prob: torch.Tensor, maxdisp: int) -> torch.Tensor:
+    """Soft-argmin: sum_d d * p(d) (reference submodule.py:220-224)."""
+    d = torch.arange(maxdisp, dtype=prob.dtype, device=prob.device).view(1, maxdisp, 1, 1)
+    return (prob * d).sum(1, keepdim=True)

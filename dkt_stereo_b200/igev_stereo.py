@@ -1,0 +1,184 @@
+"""IGEV-Stereo with the hot path (Combined Geometry Encoding Volume, lookup, GRU loop, learned
+upsampling) on B200 kernels.
+
+Drop-in for reference meta_arch/igev_stereo/igev_stereo.py: same constructor (``IGEVStereo(args)``),
+``forward(image1, image2, iters, flow_init, test_mode)`` and state-dict keys.  Only the inference
+contract (``test_mode=True`` -> ``(None, disp_up)``, disp_up = -disparity, reference :215-220) is
+served.
+
+What runs where:
+  PyTorch (cuDNN)  : MobileNetV2 feature pyramid, stems, GWC volume, 3-D hourglass, soft-argmin
+                     init disparity, cnet, context convs, the two small convs of ``upsample_disp``
+                     (reference igev_stereo.py:154-189, 143-144)  -- SURVEY 8f "next" rows
+  libdkt kernels   : all-pairs init-corr pyramid (K1, scale 1), geometry-volume pyramid
+                     (dkt_geo_pool), per-iteration combined lookup + `disp += delta` + convc1
+                     (dkt_geo_lookup_enc), motion encoder + 3 ConvGRUs + disp head (K3),
+                     mask_feat_4 head, context_upsample (K4)   (reference igev_stereo.py:192-216)
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import ops
+from .extractor import MultiBasicEncoder
+from .igev_modules import ConvNormAct, Feature, FeatureAtt, Hourglass, UpFuse, build_gwc_volume, disparity_regression
+from .raft_stereo import _fp32_math
+from .update import BasicMultiUpdateBlock, UpdateEngine
+
+
+class IGEVStereo(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        hd = args.hidden_dims
+        self.impl = os.environ.get("DKT_IMPL") or {"b200_fp32": "simt", "b200_simt": "simt"}.get(
+            getattr(args, "corr_implementation", "b200"), "tc")
+        self.cnet = MultiBasicEncoder(output_dim=[hd, hd], norm_fn="batch", downsample=args.n_downsample,
+                                      head_names=("outputs04", "outputs08", "outputs16"))
+        self.update_block = BasicMultiUpdateBlock(args, hidden_dims=hd, igev=True)
+        self.context_zqr_convs = nn.ModuleList([nn.Conv2d(hd[i], hd[i] * 3, 3, padding=1) for i in range(args.n_gru_layers)])
+        self.feature = Feature()
+
+        def stem(cin, cout):
+            return nn.Sequential(ConvNormAct(cin, cout, "in", kernel_size=3, stride=2, padding=1),
+                                 nn.Conv2d(cout, cout, 3, 1, 1, bias=False), nn.InstanceNorm2d(cout), nn.ReLU())
+
+        self.stem_2 = stem(3, 32)
+        self.stem_4 = stem(32, 48)
+        self.spx = nn.Sequential(nn.ConvTranspose2d(2 * 32, 9, kernel_size=4, stride=2, padding=1))
+        self.spx_2 = UpFuse(24, 32, deconv=True, norm="in")
+        self.spx_4 = nn.Sequential(ConvNormAct(96, 24, "in", kernel_size=3, stride=1, padding=1),
+                                   nn.Conv2d(24, 24, 3, 1, 1, bias=False), nn.InstanceNorm2d(24), nn.ReLU())
+        self.spx_2_gru = UpFuse(32, 32, deconv=True, norm="bn")
+        self.spx_gru = nn.Sequential(nn.ConvTranspose2d(2 * 32, 9, kernel_size=4, stride=2, padding=1))
+        self.conv = ConvNormAct(96, 96, "in", kernel_size=3, padding=1, stride=1)
+        self.desc = nn.Conv2d(96, 96, kernel_size=1, padding=0, stride=1)
+        self.corr_stem = ConvNormAct(8, 8, is_3d=True, kernel_size=3, stride=1, padding=1)
+        self.corr_feature_att = FeatureAtt(8, 96)
+        self.cost_agg = Hourglass(8)
+        self.classifier = nn.Conv3d(8, 1, 3, 1, 1, bias=False)
+
+        self.engine = UpdateEngine(self.update_block, self.impl)
+        self.use_cuda_graph = os.environ.get("DKT_CUDA_GRAPH", "1") == "1"
+        self.extractor_fp32 = not getattr(args, "extractor_tf32", False)
+        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._seen = set()
+        self._vol = None
+        self._vol_key = None
+
+    def freeze_bn(self):
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+
+    # ---- pre-loop (PyTorch): reference igev_stereo.py:154-189 -------------------------------------
+    def prepare(self, image1: torch.Tensor, image2: torch.Tensor):
+        """-> match_left, match_right (B,96,h,w), geo_encoding_volume (B,8,D,h,w), init_disp (B,1,h,w),
+        net_list, ctx_list (cz|cr|cq concatenated per scale), stem_2x (B,32,H/2,W/2)."""
+        args = self.args
+        image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
+        image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
+        with _fp32_math(self.extractor_fp32), torch.autocast("cuda", enabled=bool(getattr(args, "mixed_precision", False))):
+            fl, fr = self.feature(image1), self.feature(image2)
+            stem_2x = self.stem_2(image1)
+            stem_4x = self.stem_4(stem_2x)
+            stem_4y = self.stem_4(self.stem_2(image2))
+            fl[0] = torch.cat((fl[0], stem_4x), 1)
+            fr[0] = torch.cat((fr[0], stem_4y), 1)
+            match_left = self.desc(self.conv(fl[0]))
+            match_right = self.desc(self.conv(fr[0]))
+            D = args.max_disp // 4
+            vol = self.corr_stem(build_gwc_volume(match_left, match_right, D, 8))
+            vol = self.corr_feature_att(vol, fl[0])
+            gev = self.cost_agg(vol, fl)
+            prob = F.softmax(self.classifier(gev).squeeze(1), dim=1)
+            init_disp = disparity_regression(prob, D)
+            cnet_list = self.cnet(image1, num_layers=args.n_gru_layers)
+            net_list = [torch.tanh(x[0]) for x in cnet_list]
+            ctx_list = [conv(torch.relu(x[1])) for x, conv in zip(cnet_list, self.context_zqr_convs)]
+        return (match_left.float(), match_right.float(), gev.float(), init_disp.float(),
+                [n.float() for n in net_list], [c.float() for c in ctx_list], stem_2x.float())
+
+    # ---- hot path (B200 kernels): reference igev_stereo.py:192-216 --------------------------------
+    def _lookup(self, eng: UpdateEngine) -> None:
+        geo, init = self._vol
+        r = self.args.corr_radius
+        disp = eng.FLOW["f32"].view(eng.B, *eng.hw[0])            # (B,h,w,1) -> (B,h,w)
+        if eng.fused_enc:
+            ops.geo_lookup_enc(geo, init, disp, r, eng.weights["convc1"], eng.cor1_slice(), delta=eng.DELTA["f32"])
+        else:
+            ops.geo_lookup(geo, init, disp, r, eng.CORR["f32"], "nhwc", out_hi=eng.CORR["hi"], out_lo=eng.CORR["lo"],
+                           delta=eng.DELTA["f32"])
+
+    def _run_loop(self, iters: int) -> None:
+        for _ in range(iters):
+            self.engine.step(self._lookup, with_mask=False)
+
+    def upsample_disp(self, disp: torch.Tensor, mask_feat_4: torch.Tensor, stem_2x: torch.Tensor) -> torch.Tensor:
+        """reference igev_stereo.py:140-148.  disp (B,h,w) fp32, mask_feat_4 (B,32,h,w), stem_2x (B,32,2h,2w)
+        -> (B,1,4h,4w) = -context_upsample(4 * disp, softmax(spx_gru(spx_2_gru(...))))."""
+        with _fp32_math(self.extractor_fp32):
+            spx = F.softmax(self.spx_gru(self.spx_2_gru(mask_feat_4, stem_2x)), 1)
+        return ops.context_upsample(disp, spx, in_scale=4.0, out_scale=-1.0)      # reference :216 negates
+
+    def hot_path(self, match_left, match_right, gev, init_disp, net_list, ctx_list, stem_2x, iters: int) -> torch.Tensor:
+        """-> disp_up (B,1,H,W), already negated like the reference's return value."""
+        args, eng = self.args, self.engine
+        L.require_device(match_left)
+        assert args.corr_levels == 2, "IGEV configs use a 2-level geometry pyramid (configs/igev_stereo/base.json)"
+        B, D, h, w = match_left.shape
+        dev = match_left.device
+        eng.pack_weights()
+        eng.allocate(B, h, w, dev)
+        key = (B, D, h, w, tuple(gev.shape), str(dev))
+        if self._vol_key != key:
+            self._graphs.clear()
+            self._seen.clear()
+            self._vol_key = key
+            self._init_pyr = ops.alloc_pyramid(B, h, w, w, 2, dev)
+            Cg, Dg = gev.shape[1], gev.shape[2]
+            self._geo_pyr = (torch.empty(B, h, w, Cg, Dg, device=dev), torch.empty(B, h, w, Cg, Dg // 2, device=dev))
+        # volumes: init-corr pyramid = K1 with scale 1 (geometry.py:14,61-69), GEV pyramid (geometry.py:17-26);
+        # the buffers persist per shape because the captured loop graph holds their addresses
+        init = ops.corr1d_build(match_left, match_right, 2, 1.0, impl=self.impl, pyr=self._init_pyr)
+        geo = ops.geo_pool(gev, out=self._geo_pyr)
+        self._vol = (geo, init)
+        eng.load_state(net_list, ctx_list)
+        eng.FLOW["f32"].copy_(init_disp.permute(0, 2, 3, 1))
+        gkey = (iters,)
+        if self.use_cuda_graph and gkey in self._graphs:
+            self._graphs[gkey].replay()
+        elif self.use_cuda_graph and gkey in self._seen:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_loop(iters)
+            self._graphs[gkey] = g
+            g.replay()
+        else:
+            self._run_loop(iters)
+            self._seen.add(gkey)
+        # disp += delta of the last iteration (igev_stereo.py:210); mask features of the last state (:208)
+        disp = eng.FLOW["f32"].view(B, h, w)
+        ops.corr1d_lookup([], disp, args.corr_radius, None, delta=eng.DELTA["f32"])
+        eng.mask_head()
+        mask_feat_4 = eng.MH["f32"].permute(0, 3, 1, 2)
+        return self.upsample_disp(disp, mask_feat_4, stem_2x)
+
+    def forward(self, image1, image2, iters=12, flow_init=None, test_mode=False):
+        """Estimate disparity between a stereo pair; returns (None, -disparity) like the reference."""
+        if not test_mode:
+            raise NotImplementedError(
+                "the B200 engine serves inference (test_mode=True); train with the reference graph and "
+                "load the resulting checkpoint here")
+        if not image1.is_cuda:
+            raise L.DktError("IGEVStereo (B200 engine) needs CUDA inputs; there is no CPU fallback")
+        with torch.no_grad():
+            pre = self.prepare(image1, image2)
+            return None, self.hot_path(*pre, iters)

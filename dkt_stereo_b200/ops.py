@@ -100,21 +100,42 @@ def corr1d_lookup(pyr: Sequence[torch.Tensor], coords_x: torch.Tensor, radius: i
                                   B, H, W1, W2, L.stream_ptr()), "corr1d_lookup")
 
 
-def geo_pool(gev: torch.Tensor):
-    """(B,C,D,H,W) -> (B,H,W,C,D), (B,H,W,C,D//2)"""
+def geo_pool(gev: torch.Tensor, out: Optional[Sequence[torch.Tensor]] = None):
+    """(B,C,D,H,W) -> (B,H,W,C,D), (B,H,W,C,D//2); ``out`` reuses existing level buffers."""
     lib = L.load()
     L.require_device(gev)
     gev = gev.contiguous().float()
     B, Cc, D, H, W = gev.shape
-    g0 = torch.empty(B, H, W, Cc, D, device=gev.device, dtype=torch.float32)
-    g1 = torch.empty(B, H, W, Cc, D // 2, device=gev.device, dtype=torch.float32)
+    if out is not None:
+        g0, g1 = out
+        assert g0.shape == (B, H, W, Cc, D) and g1.shape == (B, H, W, Cc, D // 2)
+    else:
+        g0 = torch.empty(B, H, W, Cc, D, device=gev.device, dtype=torch.float32)
+        g1 = torch.empty(B, H, W, Cc, D // 2, device=gev.device, dtype=torch.float32)
     L.check(lib.dkt_geo_pool(gev.data_ptr(), g0.data_ptr(), g1.data_ptr(), B, Cc, D, H, W, L.stream_ptr()), "geo_pool")
     return g0, g1
 
 
+def corr1d_lookup_enc(pyr: Sequence[torch.Tensor], coords_x: torch.Tensor, radius: int, w: "ConvWeights",
+                      enc_out: DktTensor, delta: Optional[torch.Tensor] = None,
+                      flow: Optional[torch.Tensor] = None) -> None:
+    """Lookup fused with the motion encoder's 1x1 ``convc1`` + ReLU (exact fp32); ``w`` is the packed
+    convc1 (``w_simt`` [1][Cin_pad][64], bias [64]); ``enc_out`` a 64-channel NHWC slice."""
+    lib = L.load()
+    L.require_device(coords_x)
+    B, H, W1 = coords_x.shape
+    assert w.ksize == 1 and w.n == 64 and w.bias is not None
+    L.check(lib.dkt_corr1d_lookup_enc(L.pointer_array(pyr), len(pyr), radius, coords_x.data_ptr(),
+                                      L.ptr(delta), delta.shape[-1] if delta is not None else 0, L.ptr(flow),
+                                      w.w_simt.data_ptr(), w.bias.data_ptr(), C.byref(enc_out),
+                                      B, H, W1, pyr[0].shape[-1], L.stream_ptr()), "corr1d_lookup_enc")
+
+
 def geo_lookup(geo: Sequence[torch.Tensor], init: Sequence[torch.Tensor], disp: torch.Tensor, radius: int,
                out: torch.Tensor, out_layout: str = "nhwc",
-               out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None) -> None:
+               out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None,
+               delta: Optional[torch.Tensor] = None) -> None:
+    """disp (B,H,W) fp32, updated in place by delta[...,0] (NHWC) when given."""
     lib = L.load()
     B, H, W, Cc, D = geo[0].shape
     if out_layout == "nhwc":
@@ -123,8 +144,20 @@ def geo_lookup(geo: Sequence[torch.Tensor], init: Sequence[torch.Tensor], disp: 
     else:
         ob, oc, op = out.shape[1] * H * W, H * W, 1
     L.check(lib.dkt_geo_lookup(geo[0].data_ptr(), geo[1].data_ptr(), init[0].data_ptr(), init[1].data_ptr(),
-                               disp.data_ptr(), radius, Cc, D, out.data_ptr(), L.ptr(out_hi), L.ptr(out_lo),
+                               disp.data_ptr(), L.ptr(delta), delta.shape[-1] if delta is not None else 0,
+                               radius, Cc, D, out.data_ptr(), L.ptr(out_hi), L.ptr(out_lo),
                                ob, oc, op, B, H, W, L.stream_ptr()), "geo_lookup")
+
+
+def geo_lookup_enc(geo: Sequence[torch.Tensor], init: Sequence[torch.Tensor], disp: torch.Tensor, radius: int,
+                   w: "ConvWeights", enc_out: DktTensor, delta: Optional[torch.Tensor] = None) -> None:
+    lib = L.load()
+    B, H, W, Cc, D = geo[0].shape
+    assert w.ksize == 1 and w.n == 64 and w.bias is not None
+    L.check(lib.dkt_geo_lookup_enc(geo[0].data_ptr(), geo[1].data_ptr(), init[0].data_ptr(), init[1].data_ptr(),
+                                   disp.data_ptr(), L.ptr(delta), delta.shape[-1] if delta is not None else 0,
+                                   radius, Cc, D, w.w_simt.data_ptr(), w.bias.data_ptr(), C.byref(enc_out),
+                                   B, H, W, L.stream_ptr()), "geo_lookup_enc")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -308,3 +341,5 @@ interp = _profiled(lambda *a, **k: "interp")(interp)
 convex_upsample = _profiled(lambda *a, **k: "convex_upsample")(convex_upsample)
 nchw_to_nhwc = _profiled(lambda *a, **k: "nchw_to_nhwc")(nchw_to_nhwc)
 geo_lookup = _profiled(lambda *a, **k: "geo_lookup")(geo_lookup)
+corr1d_lookup_enc = _profiled(lambda *a, **k: "corr1d_lookup_enc")(corr1d_lookup_enc)
+geo_lookup_enc = _profiled(lambda *a, **k: "geo_lookup_enc")(geo_lookup_enc)

@@ -107,6 +107,10 @@ class RAFTStereo(nn.Module):
 
     # ---- L2: hot path (B200 kernels) ----------------------------------------------------------------
     def _lookup(self, eng: UpdateEngine) -> None:
+        if eng.fused_enc:
+            ops.corr1d_lookup_enc(self._pyr, eng.coords_x, self.args.corr_radius, eng.weights["convc1"],
+                                  eng.cor1_slice(), delta=eng.DELTA["f32"], flow=eng.FLOW["f32"])
+            return
         ops.corr1d_lookup(self._pyr, eng.coords_x, self.args.corr_radius, eng.CORR["f32"], "nhwc",
                           out_hi=eng.CORR["hi"], out_lo=eng.CORR["lo"], delta=eng.DELTA["f32"], flow=eng.FLOW["f32"])
 

@@ -15,6 +15,7 @@ directly into channel slices of the per-scale buffers
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -101,6 +102,9 @@ class UpdateEngine:
         self.block = block
         self.impl = impl
         self.igev = block.igev
+        # lookup kernels apply convc1 (1x1 + ReLU) on chip and write COR1 directly; set False to run the
+        # unfused pair (lookup -> CORR buffer -> convc1 conv) for A/B measurements
+        self.fused_enc = os.environ.get("DKT_FUSED_ENC", "1") == "1"
         self.weights: Optional[Dict[str, ops.ConvWeights]] = None
         self._wsig = None
         self.shape = None
@@ -152,6 +156,10 @@ class UpdateEngine:
             d["hi"] = torch.zeros(B, H, W, Cc, device=dev, dtype=torch.bfloat16)
             d["lo"] = torch.zeros(B, H, W, Cc, device=dev, dtype=torch.bfloat16)
         return d
+
+    def cor1_slice(self):
+        simt, split = self.impl == "simt", self.impl == "tc"
+        return self._slice(self.COR1, 0, 64, simt, split)
 
     @staticmethod
     def _slice(buf, c0=0, cnt=None, f32=True, split=True):
@@ -223,7 +231,8 @@ class UpdateEngine:
 
     # ---- one update-block call (reference core/update.py:115-138) -------------------------------
     def step(self, lookup, with_mask: bool = False) -> None:
-        """lookup(engine) must fill self.CORR (and FLOW / coords bookkeeping) for this iteration."""
+        """lookup(engine) does the coords / disparity bookkeeping of this iteration and fills self.COR1
+        (fused_enc: lookup + convc1 in one kernel) or self.CORR (unfused)."""
         B, impl, split, simt = self.B, self.impl, self.impl == "tc", self.impl == "simt"
         (h0, w0), (h1, w1), (h2, w2) = self.hw
         X0, X1, X2 = self.X
@@ -238,8 +247,9 @@ class UpdateEngine:
         # motion encoder (reference core/update.py:77-85)
         lookup(self)
         E = ops.make_epilogue
-        ops.conv2d([S(self.CORR, 0, self.corr_pad, simt, split)], Wt["convc1"],
-                   E(L.EPI_LINEAR, S(self.COR1, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["convc1"].bias), B, h0, w0, impl)
+        if not self.fused_enc:
+            ops.conv2d([S(self.CORR, 0, self.corr_pad, simt, split)], Wt["convc1"],
+                       E(L.EPI_LINEAR, S(self.COR1, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["convc1"].bias), B, h0, w0, impl)
         ops.conv2d([S(self.COR1, 0, 64, simt, split)], Wt["convc2"],
                    E(L.EPI_LINEAR, S(self.CF, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["convc2"].bias), B, h0, w0, impl)
         ops.conv2d([S(self.FLOW, 0, self.nflow, True, False)], Wt["stem1"],

@@ -118,24 +118,41 @@ int dkt_corr1d_build_tc(const uint16_t* f1_hi, const uint16_t* f1_lo,
  *   delta    : NULL, or the NHWC (B,H,W,delta_C) output of the flow head; channel 0 is added
  *   flow     : NULL, or NHWC (B,H,W,2) fp32: receives (coords_x - x, flow_y unchanged = kept)
  *   out      : level-major taps, channel = l*(2r+1)+k, element (b,c,p) at b*ob + c*oc + p*op
- *              (NCHW: ob=C*H*W, oc=H*W, op=1; NHWC with padding: ob=H*W*Cp, oc=1, op=Cp).
- *   out_hi/lo: optional bf16 split of the same values with the same strides (may be NULL). */
+ *              (NCHW: ob=C*H*W, oc=H*W, op=1; NHWC with padding: ob=H*W*Cp, oc=1, op=Cp; the
+ *              NHWC form takes the coalesced path and also zero-fills channels [C, Cp)).
+ *              out == NULL: only the coordinate / flow bookkeeping runs.
+ *   out_hi/lo: optional bf16 split of the same values with the same strides (may be NULL).
+ * dkt_corr1d_lookup_enc additionally applies the motion encoder's first layer to the taps while
+ * they are still on chip: enc_out[p][n] = relu(enc_b[n] + sum_c taps[p][c] * enc_w[c][n]), n < 64
+ * (reference core/update.py:72,79 `convc1`, exact fp32), enc_w fp32 [C][64]; enc_out is a
+ * 64-channel NHWC slice (every non-null precision is written).  The taps never reach HBM. */
 int dkt_corr1d_lookup(const float* const* pyr, int levels, int radius,
                       float* coords_x, const float* delta, int delta_C, float* flow,
                       float* out, uint16_t* out_hi, uint16_t* out_lo,
                       int64_t ob, int64_t oc, int64_t op,
                       int B, int H, int W1, int W2, void* stream);
+int dkt_corr1d_lookup_enc(const float* const* pyr, int levels, int radius,
+                          float* coords_x, const float* delta, int delta_C, float* flow,
+                          const float* enc_w, const float* enc_b, const dkt_tensor* enc_out,
+                          int B, int H, int W1, int W2, void* stream);
 
 /* ---- IGEV: geometry-encoding-volume pyramid + combined lookup ------------------------------
  * dkt_geo_pool: (B,C,D,H,W) fp32 -> level 0 (B,H,W,C,D) and level 1 (B,H,W,C,D/2)
  *   (reference meta_arch/igev_stereo/geometry.py:17-26; levels == 2 as in configs/igev_stereo).
- * dkt_geo_lookup: reference geometry.py:34-58 -> per level [C*(2r+1) geo taps, (2r+1) init taps]. */
+ * dkt_geo_lookup: reference geometry.py:34-58 -> per level [C*(2r+1) geo taps, (2r+1) init taps];
+ *   disp (B,H,W) fp32 is updated in place by delta[...,0] first when delta != NULL
+ *   (`disp = disp + delta_disp`, reference meta_arch/igev_stereo/igev_stereo.py:210).
+ * dkt_geo_lookup_enc: same + the IGEV motion encoder's convc1 (igev update.py:76,85), see above. */
 int dkt_geo_pool(const float* gev, float* geo0, float* geo1, int B, int C, int D, int H, int W, void* stream);
 int dkt_geo_lookup(const float* geo0, const float* geo1, const float* init0, const float* init1,
-                   const float* disp, int radius, int C, int D,
+                   float* disp, const float* delta, int delta_C, int radius, int C, int D,
                    float* out, uint16_t* out_hi, uint16_t* out_lo,
                    int64_t ob, int64_t oc, int64_t op,
                    int B, int H, int W, void* stream);
+int dkt_geo_lookup_enc(const float* geo0, const float* geo1, const float* init0, const float* init1,
+                       float* disp, const float* delta, int delta_C, int radius, int C, int D,
+                       const float* enc_w, const float* enc_b, const dkt_tensor* enc_out,
+                       int B, int H, int W, void* stream);
 
 /* ---- K3: convolutions of the update block with fused epilogues ------------------------------
  * Replaces nn.Conv2d + bias + activation + the GRU gate algebra of reference core/update.py

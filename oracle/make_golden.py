@@ -161,6 +161,67 @@ def golden_raft_forward(m, height=64, width=96, iters=4, tag="raft_fwd_small", b
          key_shapes=np.array([json.dumps(list(sd[k].shape)) for k in sorted(sd.keys())]))
 
 
+def _timm_stub():
+    """timm 0.5.4 is absent offline; torchvision's MobileNetV2 is architecture-identical and
+    supplies the attributes the reference slices (conv_stem, bn1, act1, blocks[0:7])."""
+    import torchvision
+
+    def create_model(name, pretrained=False, features_only=True):
+        assert name == "mobilenetv2_100"
+        f = torchvision.models.mobilenet_v2(weights=None).features
+        net = types.SimpleNamespace()
+        net.conv_stem, net.bn1, net.act1 = f[0][0], f[0][1], f[0][2]
+        groups = [f[1:2], f[2:4], f[4:7], f[7:11], f[11:14], f[14:17], f[17:18]]
+        net.blocks = [torch.nn.Sequential(*g) for g in groups]
+        return net
+
+    sys.modules["timm"].create_model = create_model
+
+
+def golden_igev_forward(m, height=64, width=96, iters=4, tag="igev_fwd_small", batch=1):
+    """Full reference IGEVStereo.forward(test_mode=True) (timm stubbed by torchvision).  Stores the
+    products of the pre-loop (the hot path's inputs, captured with hooks while the REAL forward runs)
+    and the final disparity, so the engine's IGEV hot path is pinned against the reference's loop."""
+    from dkt_stereo_b200.synthetic import synthetic_state_dict, shapes_of, synthetic_pair
+    _timm_stub()
+    igev = importlib.import_module("meta_arch.igev_stereo.igev_stereo")
+    cfg = igev_cfg()
+    torch.manual_seed(0)
+    model = igev.IGEVStereo(_ns(cfg)).eval()
+    sd = synthetic_state_dict(shapes_of(model.state_dict()), seed=0)
+    model.load_state_dict(sd, strict=True)
+    cap = {}
+
+    class Recorder(igev.Combined_Geo_Encoding_Volume):
+        def __init__(self, f1, f2, gev, **kw):
+            cap.update(match_left=f1.clone(), match_right=f2.clone(), gev=gev.clone())
+            super().__init__(f1, f2, gev, **kw)
+
+    def pre_hook(mod, args, kwargs):
+        if "net0" not in cap:
+            net, inp, _, disp = args[:4]
+            for i in range(3):
+                cap[f"net{i}"] = net[i].clone()
+                cap[f"ctx{i}"] = torch.cat(list(inp[i]), 1).clone()
+            cap["init_disp"] = disp.clone()
+
+    orig_up = model.upsample_disp
+
+    def up(disp, mask_feat_4, stem_2x):
+        cap.update(stem_2x=stem_2x.clone(), final_disp=disp.clone(), mask_feat_4=mask_feat_4.clone())
+        return orig_up(disp, mask_feat_4, stem_2x)
+
+    igev.Combined_Geo_Encoding_Volume = Recorder
+    model.update_block.register_forward_pre_hook(pre_hook, with_kwargs=True)
+    model.upsample_disp = up
+    im1, im2 = synthetic_pair(batch, height, width, seed=1234, mode="noise")
+    with torch.no_grad():
+        _, disp_up = model(im1, im2, iters=iters, test_mode=True)
+    hot_keys = sorted(k for k in sd if k.startswith(("update_block.", "spx_2_gru.", "spx_gru.")))
+    save(tag, disp_up=disp_up, meta=np.array([batch, height, width, iters]), keys=np.array(hot_keys),
+         key_shapes=np.array([json.dumps(list(sd[k].shape)) for k in hot_keys]), **cap)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -174,6 +235,8 @@ def main():
         "raft_small": lambda: golden_raft_forward(m),
         "raft_shift": lambda: golden_raft_forward(m, 64, 96, 6, "raft_fwd_shift", 1, "shift"),
         "raft_cfg1": lambda: golden_raft_forward(m, 256, 512, 12, "raft_fwd_cfg1", 1, "noise"),
+        "igev_small": lambda: golden_igev_forward(m),
+        "igev_mid": lambda: golden_igev_forward(m, 96, 160, 8, "igev_fwd_mid", 1),
     }
     for k, fn in jobs.items():
         if not args.only or k in args.only.split(","):

@@ -103,6 +103,75 @@ def test_geo_golden():
     assert stats(out.cpu(), g["out"])[0] < 5e-6
 
 
+def test_corr1d_lookup_nhwc_fast_path_and_enc():
+    """NHWC (padded, coalesced) output incl. bf16 hi/lo, ragged pixel count (not a multiple of 32), and
+    the lookup fused with convc1 + ReLU (core/update.py:72,79) against the oracle."""
+    from dkt_stereo_b200 import ops, _lib as L
+    from oracle import hotpath as O
+    g = torch.Generator().manual_seed(11)
+    B, D, H, W = 2, 32, 5, 43                         # P = 430: last CTA has 14 pixels
+    f1, f2 = torch.randn(B, D, H, W, generator=g), torch.randn(B, D, H, W, generator=g)
+    pyr_ref = O.corr1d_pyramid(f1, f2, 4)
+    cx = torch.arange(W).view(1, 1, W).float() + (torch.rand(B, H, W, generator=g) * (W + 16) - W / 2 - 8)
+    delta = torch.randn(B, H, W, 2, generator=g)
+    ref = O.corr1d_lookup(pyr_ref, cx + delta[..., 0], 4)              # (B,36,H,W)
+    pyr = ops.corr1d_build(f1.to(dev()), f2.to(dev()), 4, 1.0 / D ** 0.5, impl="simt")
+    cxd = cx.to(dev()).contiguous()
+    out = torch.full((B, H, W, 64), 7.0, device=dev())
+    hi = torch.zeros(B, H, W, 64, device=dev(), dtype=torch.bfloat16)
+    lo = torch.zeros_like(hi)
+    flow = torch.zeros(B, H, W, 2, device=dev())
+    ops.corr1d_lookup(pyr, cxd, 4, out, "nhwc", out_hi=hi, out_lo=lo, delta=delta.to(dev()), flow=flow)
+    assert torch.equal(cxd.cpu(), cx + delta[..., 0])
+    assert stats(out[..., :36].permute(0, 3, 1, 2).cpu(), ref)[1] < 2e-5
+    assert torch.all(out[..., 36:] == 0)                               # padding channels are zero-filled
+    assert stats((hi.float() + lo.float())[..., :36].cpu(), out[..., :36].cpu())[1] < 2e-4   # 16-bit split
+    # fused encoder
+    wt = torch.randn(64, 36, 1, 1, generator=g) / 6.0
+    bias = torch.randn(64, generator=g)
+    enc_ref = torch.relu(torch.nn.functional.conv2d(ref, wt, bias))
+    Wc = ops.pack_conv(wt.to(dev()), bias.to(dev()), cin_pad=64, tc=False)
+    enc = torch.zeros(B, H, W, 64, device=dev())
+    ehi = torch.zeros(B, H, W, 64, device=dev(), dtype=torch.bfloat16)
+    elo = torch.zeros_like(ehi)
+    cxd2 = cx.to(dev()).contiguous()
+    ops.corr1d_lookup_enc(pyr, cxd2, 4, Wc, L.tensor_slice(enc, ehi, elo, 0, 64), delta=delta.to(dev()), flow=flow)
+    assert stats(enc.permute(0, 3, 1, 2).cpu(), enc_ref)[1] < 5e-5
+    assert stats((ehi.float() + elo.float()).cpu(), enc.cpu())[1] < 2e-4
+
+
+def test_geo_lookup_update_nhwc_and_enc():
+    """IGEV lookup with the fused `disp += delta` (igev_stereo.py:210), NHWC padded output and the
+    fused 162 -> 64 convc1 (igev update.py:76,85)."""
+    from dkt_stereo_b200 import ops, _lib as L
+    from oracle import hotpath as O
+    g = load_golden("geo_a")
+    f1, f2, gev, disp = (g[k] for k in ("fmap1", "fmap2", "gev", "disp"))
+    gen = torch.Generator().manual_seed(5)
+    B, _, H, W = disp.shape
+    delta = torch.randn(B, H, W, 1, generator=gen)
+    geo_ref, init_ref = O.geo_pyramids(f1, f2, gev, 2)
+    ref = O.geo_lookup(geo_ref, init_ref, disp + delta.permute(0, 3, 1, 2), 4)       # (B,162,H,W)
+    init = ops.corr1d_build(f1.to(dev()), f2.to(dev()), 2, 1.0, impl="simt")
+    geo = ops.geo_pool(gev.to(dev()))
+    d = disp[:, 0].contiguous().to(dev())
+    out = torch.full((B, H, W, 192), 3.0, device=dev())
+    hi = torch.zeros(B, H, W, 192, device=dev(), dtype=torch.bfloat16)
+    lo = torch.zeros_like(hi)
+    ops.geo_lookup(geo, init, d, 4, out, "nhwc", out_hi=hi, out_lo=lo, delta=delta.to(dev()))
+    assert torch.equal(d.cpu(), disp[:, 0] + delta[..., 0])
+    assert stats(out[..., :162].permute(0, 3, 1, 2).cpu(), ref)[1] < 1e-4
+    assert torch.all(out[..., 162:] == 0)
+    wt = torch.randn(64, 162, 1, 1, generator=gen) / 12.0
+    bias = torch.randn(64, generator=gen)
+    enc_ref = torch.relu(torch.nn.functional.conv2d(ref, wt, bias))
+    Wc = ops.pack_conv(wt.to(dev()), bias.to(dev()), cin_pad=192, tc=False)
+    enc = torch.zeros(B, H, W, 64, device=dev())
+    d2 = disp[:, 0].contiguous().to(dev())
+    ops.geo_lookup_enc(geo, init, d2, 4, Wc, L.tensor_slice(enc, None, None, 0, 64), delta=delta.to(dev()))
+    assert stats(enc.permute(0, 3, 1, 2).cpu(), enc_ref)[1] < 2e-4
+
+
 # ---------------------------------------------------------------------------------------------
 # K3: single convs with each epilogue vs torch conv2d (fp32 reference of the same op)
 # ---------------------------------------------------------------------------------------------
@@ -279,3 +348,32 @@ def test_flow_init_and_batch_independence():
     lr, _ = model(im1, im2, iters=1, flow_init=fi, test_mode=True)
     lr0, _ = model(im1, im2, iters=1, test_mode=True)
     assert float((lr - lr0).abs().mean()) > 0.5
+
+
+# ---------------------------------------------------------------------------------------------
+# IGEV-Stereo hot path end to end: pre-loop products + final disparity of the REAL reference forward
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("tag", ["igev_fwd_small", "igev_fwd_mid"])
+def test_igev_hot_path_golden(tag, impl, monkeypatch):
+    from dkt_stereo_b200.igev_stereo import IGEVStereo
+    from dkt_stereo_b200.synthetic import synthetic_state_dict
+    monkeypatch.setenv("DKT_IMPL", impl)
+    g = load_golden(tag)
+    B, H, W, iters = [int(v) for v in g["meta"]]
+    model = IGEVStereo(Namespace(mixed_precision=False, **IGEV_CFG)).eval()
+    sd = synthetic_state_dict(golden_shapes(g), seed=0)           # update_block.*, spx_2_gru.*, spx_gru.*
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected
+    assert not [k for k in missing if k.startswith(("update_block.", "spx_2_gru.", "spx_gru."))]
+    model = model.to(dev())
+    d = lambda k: g[k].to(dev())
+    for rep in range(3):                                           # eager, graph capture, graph replay
+        with torch.no_grad():
+            up = model.hot_path(d("match_left"), d("match_right"), d("gev"), d("init_disp"),
+                                [d(f"net{i}") for i in range(3)], [d(f"ctx{i}") for i in range(3)], d("stem_2x"), iters)
+        torch.cuda.synchronize()
+        mean, mx = stats(up.cpu(), g["disp_up"])
+        print(f"[parity] {tag} impl={impl} rep={rep}: mean-abs {mean:.3e} px, max-abs {mx:.3e} px")
+        assert up.shape == (B, 1, H, W)
+        assert mean <= 1e-3, (tag, impl, rep, mean, mx)       # the north-star gate

@@ -74,3 +74,14 @@ def test_synthetic_is_deterministic():
     assert torch.equal(a, a2) and torch.equal(b, b2) and not torch.equal(a, b)
     s1 = synthetic_state_dict({"x.weight": (4, 3, 3, 3), "y.norm3.weight": (4,), "y.downsample.1.weight": (4,)})
     assert torch.equal(s1["y.norm3.weight"], s1["y.downsample.1.weight"])
+
+
+def test_registry_and_igev_hot_path_keys():
+    import dkt_stereo_b200 as pkg
+    assert "RAFTStereo" in pkg.__models__ and "IGEVStereo" in pkg.__models__
+    model = pkg.__models__["IGEVStereo"](Namespace(mixed_precision=False, **IGEV_CFG))
+    mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    ref = golden_shapes(load_golden("igev_fwd_small"))     # reference keys of update_block.*, spx_2_gru.*, spx_gru.*
+    assert ref and all(mine.get(k) == v for k, v in ref.items())
+    with pytest.raises(KeyError):
+        pkg.__models__["PCVNet"]

@@ -67,3 +67,20 @@ def test_raft_forward_small_and_shift():
         mean, mx = stats(up, g["flow_up"])
         assert mean < 1e-4, (tag, mean, mx)
         assert stats(lr, g["flow_lr"])[0] < 1e-4
+
+
+def test_igev_loop_against_reference_forward():
+    """The oracle's IGEV hot loop, fed with the pre-loop products the REAL reference forward produced
+    (captured by hooks in oracle/make_golden.py), reproduces the reference's final disparity."""
+    for tag in ("igev_fwd_small", "igev_fwd_mid"):
+        g = load_golden(tag)
+        B, H, W, iters = [int(v) for v in g["meta"]]
+        sd = synthetic_state_dict(golden_shapes(g), seed=0)
+        net = [g[f"net{i}"] for i in range(3)]
+        inp = [list(g[f"ctx{i}"].split(128, dim=1)) for i in range(3)]
+        with torch.no_grad():
+            up = O.igev_loop(sd, g["match_left"], g["match_right"], g["gev"], g["init_disp"], net, inp,
+                             g["stem_2x"], iters, IGEV_CFG)
+        assert up.shape == g["disp_up"].shape == (B, 1, H, W)
+        mean, mx = stats(up, g["disp_up"])
+        assert mean < 1e-4, (tag, mean, mx)
