@@ -27,7 +27,8 @@ class DktEpilogue(C.Structure):
     _fields_ = [("kind", C.c_int32), ("act", C.c_int32), ("scale", C.c_float),
                 ("bias", C.c_void_p), ("ctx", C.c_void_p), ("ctx_C", C.c_int32), ("ctx_c0", C.c_int32),
                 ("out", DktTensor), ("z", DktTensor), ("h", DktTensor),
-                ("tail", C.c_void_p), ("tail_C", C.c_int32)]
+                ("tail", C.c_void_p), ("tail_C", C.c_int32),
+                ("res", C.c_void_p), ("res_C", C.c_int32), ("res_c0", C.c_int32)]
 
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
@@ -52,12 +53,17 @@ SIGNATURES = {
     "dkt_geo_lookup_enc": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _TP, _I, _I, _I, _P],
     "dkt_conv2d_simt": [_TP, _I, _P, _I, _I, _EP, _I, _I, _I, _P],
     "dkt_conv2d_tc": [_TP, _I, _P, _P, _I, _I, _EP, _I, _I, _I, _P],
+    "dkt_conv2d_tc_ex": [_TP, _I, _P, _P, _I, _I, _I, _I, _EP, _I, _I, _I, _I, _I, _P],
     "dkt_pool2x": [_TP, _TP, _I, _I, _I, _I, _I, _P],
     "dkt_interp": [_TP, _TP, _I, _I, _I, _I, _I, _P],
     "dkt_convex_upsample": [_P, _I, _P, _P, _I, _I, _I, _I, _P],
     "dkt_context_upsample": [_P, _P, _P, _F, _F, _I, _I, _I, _P],
     "dkt_nchw_to_nhwc": [_P, _P, _TP, _I, _I, _I, _I, _P],
     "dkt_nhwc_to_nchw": [_TP, _P, _I, _I, _I, _I, _P],
+    "dkt_stem_rows_bf16x2": [_P, _F, _F, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "dkt_instnorm_workspace_floats": [_I, _I],
+    "dkt_instnorm_stats": [_TP, _P, _P, _F, _I, _I, _I, _P],
+    "dkt_instnorm_apply": [_TP, _P, _TP, _TP, _I, _I, _I, _I, _P],
     "dkt_split_nchw_to_nhwc_bf16x2": [_P, _I64, _I64, _I64, _I64, _P, _P, _I, _I, _I, _I, _P],
 }
 

@@ -25,8 +25,10 @@
 // BK = K block in channels: 64 (SWIZZLE_128B rows, default) or 32 (SWIZZLE_64B rows, twice the
 // stages at N = 256; measured 2 % slower, kept selectable with DKT_CONV_BK=32).
 //
-// conv_tc_v1_kernel is the first (one tile per CTA, serial epilogue) version, kept selectable
-// with DKT_CONV_TC=v1 for A/B measurements.
+// Strided convolutions (the encoders' stride-2 layers) use the same kernel: the TMA tensor map is
+// built with elementStrides = stride on the W/H dimensions, so the box {BK, 16*s, 8*s, 1} starting
+// at (s*x0 + kx - pad, s*y0 + ky - pad) delivers exactly the 8x16 input samples of tap (ky,kx).
+// Filters are kh x kw with independent padding (3x3, 1x1, and the 7x1 form of the 7x7 stem).
 #include "common.cuh"
 #include "tc.cuh"
 #include <stdlib.h>
@@ -35,10 +37,8 @@ namespace dkt {
 
 using namespace tc;
 
-constexpr int TC_TILE_W = 16, TC_TILE_H = 8, TC_BLOCK_K = 64;
+constexpr int TC_TILE_W = 16, TC_TILE_H = 8;
 constexpr int TC_MAX_STAGES = 8;
-constexpr uint32_t TC_A_BYTES = 128 * 128;          // 128 pixels x 64 bf16
-constexpr int TC_THREADS = 192;
 
 struct TcConvParams {
     CUtensorMap act[DKT_MAX_SRCS][2];   // [source][hi/lo], 4-D (C, W, H, B)
@@ -46,7 +46,7 @@ struct TcConvParams {
     int nsrc;
     int c_begin[DKT_MAX_SRCS];
     int kblocks[DKT_MAX_SRCS];
-    int ksize, pad, taps;
+    int kh, kw, pad_y, pad_x, stride, taps;
     int N, Npad;
     int H, W, tiles_x, tiles_y;
     int num_tiles;
@@ -65,6 +65,10 @@ __device__ __forceinline__ void tc_epilogue4(const dkt_epilogue& e, int N, int64
         if (e.ctx) { float4 c = ld4(e.ctx + p * e.ctx_C + e.ctx_c0 + n); a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; }
         a.x = apply_act(a.x, e.act) * e.scale; a.y = apply_act(a.y, e.act) * e.scale;
         a.z = apply_act(a.z, e.act) * e.scale; a.w = apply_act(a.w, e.act) * e.scale;
+        if (e.res) {       // residual block tail: relu(x + y)
+            float4 r = ld4(e.res + p * e.res_C + e.res_c0 + n);
+            a.x = fmaxf(a.x + r.x, 0.f); a.y = fmaxf(a.y + r.y, 0.f); a.z = fmaxf(a.z + r.z, 0.f); a.w = fmaxf(a.w + r.w, 0.f);
+        }
         store_all4(e.out, p, n, a);
     } else if (e.kind == DKT_EPI_GRU_ZR) {
         const int Nh = N >> 1;
@@ -95,139 +99,10 @@ __device__ __forceinline__ void tc_epilogue4(const dkt_epilogue& e, int N, int64
 __device__ __forceinline__ void tc_epilogue1(const dkt_epilogue& e, int64_t p, int n, float a) {
     if (e.bias) a += e.bias[n];
     if (e.ctx) a += e.ctx[p * e.ctx_C + e.ctx_c0 + n];
-    store_all(e.out, p, n, apply_act(a, e.act) * e.scale);
+    a = apply_act(a, e.act) * e.scale;
+    if (e.res) a = fmaxf(a + e.res[p * e.res_C + e.res_c0 + n], 0.f);
+    store_all(e.out, p, n, a);
 }
-
-__global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_v1_kernel(const __grid_constant__ TcConvParams prm) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-
-    const uint32_t b_bytes = (uint32_t)prm.Npad * 128u;
-    const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)prm.stages * stage_bytes);
-    uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
-    uint64_t* tmem_full_bar = empty_bar + TC_MAX_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    const int tx_t = tile % prm.tiles_x;
-    const int ty_t = (tile / prm.tiles_x) % prm.tiles_y;
-    const int b = tile / (prm.tiles_x * prm.tiles_y);
-    const int x0 = tx_t * TC_TILE_W, y0 = ty_t * TC_TILE_H;
-
-    int kb_total = 0;
-    for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
-    const int iters = prm.taps * kb_total;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < prm.nsrc; ++s) { tma_prefetch_desc(&prm.act[s][0]); tma_prefetch_desc(&prm.act[s][1]); }
-        tma_prefetch_desc(&prm.wgt[0]);
-        tma_prefetch_desc(&prm.wgt[1]);
-        for (int s = 0; s < prm.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, prm.tmem_cols);
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer =====
-            int it = 0;
-            for (int tap = 0; tap < prm.taps; ++tap) {
-                const int ky = tap / prm.ksize, kx = tap - ky * prm.ksize;
-                const int xs = x0 + kx - prm.pad, ys = y0 + ky - prm.pad;
-                int kofs = 0;
-                for (int s = 0; s < prm.nsrc; ++s) {
-                    for (int kb = 0; kb < prm.kblocks[s]; ++kb, ++it) {
-                        const int stage = it % prm.stages;
-                        const uint32_t phase = (uint32_t)(it / prm.stages) & 1u;
-                        mbar_wait(&empty_bar[stage], phase ^ 1u);
-                        uint8_t* st = smem + (size_t)stage * stage_bytes;
-                        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-                        const int c = prm.c_begin[s] + kb * TC_BLOCK_K;
-                        tma_load_4d(st, &prm.act[s][0], &full_bar[stage], c, xs, ys, b);
-                        tma_load_4d(st + TC_A_BYTES, &prm.act[s][1], &full_bar[stage], c, xs, ys, b);
-                        tma_load_2d(st + 2 * TC_A_BYTES, &prm.wgt[0], &full_bar[stage], kofs + kb * TC_BLOCK_K, tap * prm.Npad);
-                        tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &prm.wgt[1], &full_bar[stage], kofs + kb * TC_BLOCK_K, tap * prm.Npad);
-                    }
-                    kofs += prm.kblocks[s] * TC_BLOCK_K;
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t idesc = idesc_bf16_m128((uint32_t)prm.Npad);
-            for (int it = 0; it < iters; ++it) {
-                const int stage = it % prm.stages;
-                const uint32_t phase = (uint32_t)(it / prm.stages) & 1u;
-                mbar_wait(&full_bar[stage], phase);
-                tcgen05_fence_after();
-                const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint32_t a_lo = a_hi + TC_A_BYTES;
-                const uint32_t w_hi = a_hi + 2 * TC_A_BYTES;
-                const uint32_t w_lo = w_hi + b_bytes;
-#pragma unroll
-                for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
-                    const uint64_t dah = smem_desc_sw128(a_hi + k * 32), dal = smem_desc_sw128(a_lo + k * 32);
-                    const uint64_t dwh = smem_desc_sw128(w_hi + k * 32), dwl = smem_desc_sw128(w_lo + k * 32);
-                    umma_bf16(tmem_base, dah, dwh, idesc, (it | k) != 0);
-                    umma_bf16(tmem_base, dal, dwh, idesc, 1u);
-                    umma_bf16(tmem_base, dah, dwl, idesc, 1u);
-                }
-                umma_commit(&empty_bar[stage]);       // smem slot reusable once these MMAs retire
-            }
-            umma_commit(tmem_full_bar);               // accumulator complete
-        }
-    } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
-        const int q = warp & 3;
-        const int m = q * 32 + lane;
-        const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
-        const bool valid = (y < prm.H) && (x < prm.W);
-        const int64_t p = ((int64_t)b * prm.H + y) * prm.W + x;
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
-        const dkt_epilogue& e = prm.epi;
-        const int N = prm.N;
-        for (int c0 = 0; c0 < prm.Npad; c0 += 32) {
-            float v[32];
-            const int ncols = (prm.Npad - c0 >= 32) ? 32 : 16;
-            __syncwarp();                       // tcgen05.ld is .sync.aligned: reconverge first
-            if (ncols == 32) tmem_ld32(tbase + c0, v); else tmem_ld16(tbase + c0, v);
-            tmem_ld_wait();
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (j < ncols) {
-                        const int n = c0 + j;
-                        if (n + 3 < N) {
-                            tc_epilogue4(e, N, p, n, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) if (n + t < N) tc_epilogue1(e, p, n + t, v[j + t]);
-                        }
-                    }
-                }
-            }
-        }
-        if (valid && e.tail) {
-            for (int t = 0; t < e.tail_C; ++t) store_all(e.out, p, N + t, __ldg(e.tail + p * e.tail_C + t));
-        }
-    }
-
-    tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, prm.tmem_cols);
-}
-
 
 // ---------------------------------------------------------------------------------------------
 // v2: persistent, double-buffered accumulators, coalesced epilogue
@@ -296,8 +171,8 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
                 const int r = tile - b * tiles_per_img;
                 const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
                 for (int tap = 0; tap < prm.taps; ++tap) {
-                    const int ky = tap / prm.ksize, kx = tap - ky * prm.ksize;
-                    const int xs = x0 + kx - prm.pad, ys = y0 + ky - prm.pad;
+                    const int ky = tap / prm.kw, kx = tap - ky * prm.kw;
+                    const int xs = x0 * prm.stride + kx - prm.pad_x, ys = y0 * prm.stride + ky - prm.pad_y;
                     int kofs = 0;
                     for (int s = 0; s < prm.nsrc; ++s) {
                         for (int kb = 0; kb < prm.kblocks[s]; ++kb) {
@@ -430,13 +305,18 @@ using namespace dkt;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-extern "C" int dkt_conv2d_tc(const dkt_tensor* srcs, int nsrc, const uint16_t* w_hi, const uint16_t* w_lo,
-                             int ksize, int N, const dkt_epilogue* epi, int B, int H, int W, void* stream) {
+extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t* w_hi, const uint16_t* w_lo,
+                                int kh, int kw, int stride, int N, const dkt_epilogue* epi,
+                                int B, int Hin, int Win, int H, int W, void* stream) {
     DKT_CHECK_ARG(srcs && w_hi && w_lo && epi);
     DKT_CHECK_ARG(nsrc >= 1 && nsrc <= DKT_MAX_SRCS);
-    DKT_CHECK_ARG(B > 0 && H > 0 && W > 0 && N > 0);
-    if (ksize != 1 && ksize != 3) return DKT_E_UNSUPPORTED;
+    DKT_CHECK_ARG(B > 0 && H > 0 && W > 0 && Hin > 0 && Win > 0 && N > 0);
+    if (kh < 1 || kw < 1 || kh > 7 || kw > 7 || !(kh & 1) || !(kw & 1)) return DKT_E_UNSUPPORTED;
+    if (stride != 1 && stride != 2) return DKT_E_UNSUPPORTED;
     if (N > 256) return DKT_E_UNSUPPORTED;
+    const int pad_y = kh / 2, pad_x = kw / 2;
+    // output extent of a padded strided conv (PyTorch: floor((in + 2p - k) / s) + 1)
+    if (H != (Hin + 2 * pad_y - kh) / stride + 1 || W != (Win + 2 * pad_x - kw) / stride + 1) return DKT_E_INVALID;
     // epilogue sanity (vector accesses need 4-channel granularity)
     const dkt_epilogue& e = *epi;
     if (e.kind == DKT_EPI_LINEAR) {
@@ -448,11 +328,11 @@ extern "C" int dkt_conv2d_tc(const dkt_tensor* srcs, int nsrc, const uint16_t* w
     }
     if (N >= 4 && ((e.out.C % 4) || (e.out.c_begin % 4))) return DKT_E_ALIGNMENT;
     if (e.ctx && ((e.ctx_C % 4) || (e.ctx_c0 % 4) || !aligned16(e.ctx))) return DKT_E_ALIGNMENT;
+    if (e.res && ((e.res_C % 4) || (e.res_c0 % 4) || !aligned16(e.res))) return DKT_E_ALIGNMENT;
     if (e.bias && !aligned16(e.bias)) return DKT_E_ALIGNMENT;
     if (!aligned16(e.out.f32) || !aligned16(e.out.hi) || !aligned16(e.out.lo)) return DKT_E_ALIGNMENT;
 
-    // kernel generation / K block: v2 (persistent) unless DKT_CONV_TC=v1; BK = 64 unless DKT_CONV_BK=32
-    static const int s_version = [] { const char* v = getenv("DKT_CONV_TC"); return (v && v[0] == 'v' && v[1] == '1') ? 1 : 2; }();
+    // K block: 64 channels (SWIZZLE_128B) unless DKT_CONV_BK=32
     static const int s_bk_env = [] { const char* v = getenv("DKT_CONV_BK"); return v ? atoi(v) : 0; }();
     static const int s_sms = [] {
         int dev = 0, n = 0;
@@ -463,11 +343,8 @@ extern "C" int dkt_conv2d_tc(const dkt_tensor* srcs, int nsrc, const uint16_t* w
         return n;
     }();
     const int Npad = (N + 15) / 16 * 16;
-    int BK = 64;
-    if (s_version == 2) {
-        // measured on B200 (gru08 z||r, N = 256): 2 stages x BK 64 = 0.957 ms, 4 stages x BK 32 = 0.980 ms
-        if (s_bk_env == 32) BK = 32;
-    }
+    // measured on B200 (gru08 z||r, N = 256): 2 stages x BK 64 = 0.957 ms, 4 stages x BK 32 = 0.980 ms
+    const int BK = (s_bk_env == 32) ? 32 : 64;
 
     TcConvParams prm{};
     prm.nsrc = nsrc;
@@ -480,15 +357,15 @@ extern "C" int dkt_conv2d_tc(const dkt_tensor* srcs, int nsrc, const uint16_t* w
         prm.c_begin[s] = t.c_begin;
         prm.kblocks[s] = t.c_count / BK;
         cin_total += t.c_count;
-        const uint64_t dims[4] = {(uint64_t)t.C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-        const uint64_t strides[4] = {1, (uint64_t)t.C, (uint64_t)t.C * W, (uint64_t)t.C * W * H};
-        const uint32_t box[4] = {(uint32_t)BK, TC_TILE_W, TC_TILE_H, 1};
-        if (!make_tmap_bf16(&prm.act[s][0], t.hi, 4, dims, strides, box, BK * 2)) return DKT_E_DRIVER;
-        if (!make_tmap_bf16(&prm.act[s][1], t.lo, 4, dims, strides, box, BK * 2)) return DKT_E_DRIVER;
+        const uint64_t dims[4] = {(uint64_t)t.C, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
+        const uint64_t strides[4] = {1, (uint64_t)t.C, (uint64_t)t.C * Win, (uint64_t)t.C * Win * Hin};
+        const uint32_t box[4] = {(uint32_t)BK, (uint32_t)(TC_TILE_W * stride), (uint32_t)(TC_TILE_H * stride), 1};
+        const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+        if (!make_tmap_bf16(&prm.act[s][0], t.hi, 4, dims, strides, box, BK * 2, estr)) return DKT_E_DRIVER;
+        if (!make_tmap_bf16(&prm.act[s][1], t.lo, 4, dims, strides, box, BK * 2, estr)) return DKT_E_DRIVER;
     }
-    prm.ksize = ksize;
-    prm.pad = ksize / 2;
-    prm.taps = ksize * ksize;
+    prm.kh = kh; prm.kw = kw; prm.pad_y = pad_y; prm.pad_x = pad_x; prm.stride = stride;
+    prm.taps = kh * kw;
     prm.N = N;
     prm.Npad = Npad;
     {
@@ -515,22 +392,12 @@ extern "C" int dkt_conv2d_tc(const dkt_tensor* srcs, int nsrc, const uint16_t* w
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(conv_tc_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce != cudaSuccess) return (int)ce;
         attr_set = true;
     }
-    if (s_version == 1) {
-        int stages = (int)((200u * 1024u) / stage_bytes);
-        if (stages > 4) stages = 4;
-        if (stages < 2) return DKT_E_UNSUPPORTED;
-        prm.stages = stages;
-        const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
-        conv_tc_v1_kernel<<<(unsigned)tiles, TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
-        DKT_RETURN_LAST();
-    }
-    // v2: the ring takes what the epilogue buffers and barriers leave of the 227 KB
+    // the ring takes what the epilogue buffers and barriers leave of the 227 KB
     const uint32_t budget = 227u * 1024u - 1024u /*align*/ - TC2_EPI_BYTES - 256u /*barriers*/;
     int stages = (int)(budget / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -543,4 +410,10 @@ extern "C" int dkt_conv2d_tc(const dkt_tensor* srcs, int nsrc, const uint16_t* w
     else
         conv_tc_kernel<64><<<grid, TC2_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
     DKT_RETURN_LAST();
+}
+
+extern "C" int dkt_conv2d_tc(const dkt_tensor* srcs, int nsrc, const uint16_t* w_hi, const uint16_t* w_lo,
+                             int ksize, int N, const dkt_epilogue* epi, int B, int H, int W, void* stream) {
+    if (ksize != 1 && ksize != 3) return DKT_E_UNSUPPORTED;
+    return dkt_conv2d_tc_ex(srcs, nsrc, w_hi, w_lo, ksize, ksize, 1, N, epi, B, H, W, H, W, stream);
 }

@@ -37,12 +37,13 @@ inline EncodeTiledFn encode_fn() {
 // dims/strides in elements (strides[0] implied 1); box in elements.
 // swizzle_bytes: 128 (inner box = 64 elements) or 64 (inner box = 32 elements).
 inline bool make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                           const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes = 128) {
+                           const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes = 128,
+                           const uint32_t* elem_strides = nullptr) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t gdim[4], gstr[3];
     cuuint32_t bx[4], es[4];
-    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
     for (int i = 1; i < rank; ++i) gstr[i - 1] = strides_elems[i] * 2;
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE,

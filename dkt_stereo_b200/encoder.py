@@ -1,0 +1,256 @@
+"""Feature / context encoders of RAFT-Stereo executed on the B200 kernels.
+
+The PyTorch modules in ``extractor.py`` stay the *parameter containers* (reference state-dict keys,
+reference core/extractor.py:122-300); ``EncoderEngine`` runs their arithmetic with the same
+tensor-core convolution kernel as the GRU loop (3-term bf16 split, fp32 accumulate), NHWC end to end:
+
+* stem            image normalisation + x-im2col (``dkt_stem_rows_bf16x2``), then the 7x7 conv as a 7x1 conv
+* residual stages ``dkt_conv2d_tc_ex`` (3x3 / strided 3x3 / strided 1x1 shortcut)
+    - fnet (InstanceNorm): conv -> raw fp32 -> ``dkt_instnorm_stats`` -> ``dkt_instnorm_apply``
+      (normalise + ReLU + residual in one pass, writes fp32 + bf16 hi/lo)
+    - cnet (BatchNorm, eval): the norm is folded into weight/bias at pack time; ReLU and the
+      residual ``relu(x + y)`` run in the conv epilogue
+* outputs         fnet's 1x1 conv writes the matching features directly as NHWC bf16 (hi, lo) -- the
+                  operand layout of the correlation build, so no split / transpose pass exists; cnet's
+                  heads write tanh(hidden) straight into the GRU state buffers and the context convs
+                  (``context_zqr_convs`` + folded GRU gate biases, reference raft_stereo.py:110-114)
+                  straight into the per-scale context buffers of ``UpdateEngine``.
+
+96-channel stages run with their channels zero-padded to 128 (K blocks are 64 wide); the padded
+channels stay exactly zero through conv, norm and residual.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from ._lib import tensor_slice as TS
+from .extractor import BasicEncoder, MultiBasicEncoder, ResidualBlock
+from .update import UpdateEngine
+
+
+def _pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+class _Act:
+    """An NHWC activation (B,H,W,C) held as fp32 and/or bf16 (hi, lo)."""
+
+    def __init__(self, B, H, W, Cc, device, f32=True, split=True):
+        self.B, self.H, self.W, self.C = B, H, W, Cc
+        self.f32 = torch.zeros(B, H, W, Cc, device=device) if f32 else None
+        self.hi = torch.zeros(B, H, W, Cc, device=device, dtype=torch.bfloat16) if split else None
+        self.lo = torch.zeros(B, H, W, Cc, device=device, dtype=torch.bfloat16) if split else None
+
+    def view(self, B: int) -> "_Act":
+        """The first B images (cnet reuses fnet's larger scratch buffers)."""
+        v = object.__new__(_Act)
+        v.B, v.H, v.W, v.C = B, self.H, self.W, self.C
+        v.f32 = self.f32[:B] if self.f32 is not None else None
+        v.hi = self.hi[:B] if self.hi is not None else None
+        v.lo = self.lo[:B] if self.lo is not None else None
+        return v
+
+    def s(self, f32=True, split=True, c0=0, cnt=None):
+        return TS(self.f32 if f32 else None, self.hi if split else None, self.lo if split else None, c0, cnt)
+
+
+class EncoderEngine:
+    def __init__(self, fnet: BasicEncoder, cnet: MultiBasicEncoder, zqr_convs: nn.ModuleList, update: UpdateEngine):
+        assert fnet.norm_fn == "instance" and cnet.norm_fn == "batch", "engine serves configs/raft_stereo/base.json"
+        self.fnet, self.cnet, self.zqr, self.update = fnet, cnet, zqr_convs, update
+        self.w: Optional[Dict[str, ops.ConvWeights]] = None
+        self._sig = None
+        self.shape = None
+
+    # ---- weights -------------------------------------------------------------------------------
+    def _signature(self):
+        mods = list(self.fnet.parameters()) + list(self.cnet.parameters()) + list(self.cnet.buffers()) + \
+            list(self.zqr.parameters()) + list(self.update.block.parameters())
+        return tuple((p.data_ptr(), p._version) for p in mods)
+
+    @staticmethod
+    def _bn(norm: nn.Module):
+        return (norm.weight, norm.bias, norm.running_mean, norm.running_var) if isinstance(norm, nn.BatchNorm2d) else None
+
+    def _pack_block(self, w, key: str, blk: ResidualBlock):
+        cin, cout = blk.conv1.in_channels, blk.conv1.out_channels
+        stride = blk.conv1.stride[0]
+        w[key + ".conv1"] = ops.pack_conv_general(blk.conv1.weight, blk.conv1.bias, stride=stride, cin_pad=_pad64(cin),
+                                                  n_pad=_pad64(cout), bn=self._bn(blk.norm1))
+        w[key + ".conv2"] = ops.pack_conv_general(blk.conv2.weight, blk.conv2.bias, cin_pad=_pad64(cout),
+                                                  n_pad=_pad64(cout), bn=self._bn(blk.norm2))
+        if blk.downsample is not None:
+            ds = blk.downsample[0]
+            w[key + ".ds"] = ops.pack_conv_general(ds.weight, ds.bias, stride=stride, cin_pad=_pad64(cin),
+                                                   n_pad=_pad64(cout), bn=self._bn(blk.norm3))
+
+    def pack_weights(self) -> None:
+        sig = self._signature()
+        if self.w is not None and sig == self._sig:
+            return
+        self.update.pack_weights()
+        w: Dict[str, ops.ConvWeights] = {}
+        for tag, net in (("f", self.fnet), ("c", self.cnet)):
+            c1 = net.conv1
+            assert c1.kernel_size == (7, 7) and c1.stride == (1, 1) and c1.in_channels == 3, "n_downsample <= 2 stem"
+            # 7x7x3 -> 7x1 over the x-im2col channels kx*3 + c (dkt_stem_rows_bf16x2)
+            w7 = c1.weight.detach().permute(0, 3, 1, 2).reshape(c1.out_channels, 21, 7, 1)
+            w[tag + ".conv1"] = ops.pack_conv_general(w7, c1.bias, cin_pad=64, bn=self._bn(net.norm1))
+            for lname in ("layer1", "layer2", "layer3") + (("layer4", "layer5") if tag == "c" else ()):
+                for i, blk in enumerate(getattr(net, lname)):
+                    self._pack_block(w, f"{tag}.{lname}.{i}", blk)
+        w["f.conv2"] = ops.pack_conv_general(self.fnet.conv2.weight, self.fnet.conv2.bias)
+        heads = [getattr(self.cnet, n) for n in self.cnet.head_names]
+        for i, hl in enumerate(heads):
+            for j, head in enumerate(hl):
+                if isinstance(head, nn.Sequential):
+                    self._pack_block(w, f"c.head{i}.{j}.block", head[0])
+                    conv = head[1]
+                else:
+                    conv = head
+                w[f"c.head{i}.{j}.conv"] = ops.pack_conv_general(conv.weight, conv.bias)
+            z = self.zqr[i]
+            bias = z.bias.detach() + self.update.gru_bias[i].to(z.bias.device)      # fold the GRU gate biases
+            w[f"c.zqr{i}.zr"] = ops.pack_conv_general(z.weight[:256], bias[:256])
+            w[f"c.zqr{i}.q"] = ops.pack_conv_general(z.weight[256:], bias[256:])
+        self.w, self._sig = w, sig
+
+    # ---- buffers -------------------------------------------------------------------------------
+    def allocate(self, B: int, H: int, W: int, device) -> None:
+        shape = (B, H, W, str(device))
+        if self.shape == shape:
+            return
+        self.device, self.B, self.H, self.W = device, B, H, W
+        nd = self.fnet.downsample
+        assert nd == 2, "engine serves n_downsample = 2 (configs/raft_stereo/base.json)"
+        dims = [(H, W)]
+        for _ in range(4):
+            h, w_ = dims[-1]
+            dims.append(((h - 1) // 2 + 1, (w_ - 1) // 2 + 1))
+        self.dims = dims                                   # full, 1/2, 1/4, 1/8, 1/16
+        B2 = 2 * B
+        chans = [64, 128, 128, 128, 128]
+        nimg = [B2, B2, B2, B, B]
+        self.lvl = []
+        for (h, w_), c, n in zip(dims, chans, nimg):
+            self.lvl.append(dict(A=_Act(n, h, w_, c, device), Bb=_Act(n, h, w_, c, device),
+                                 Y=_Act(n, h, w_, c, device, f32=False), RAW=_Act(n, h, w_, c, device, split=False),
+                                 RAWD=_Act(n, h, w_, c, device, split=False)))
+        self.STEM = _Act(B2, H, W, 64, device, f32=False)
+        self.FMAP = _Act(B2, dims[2][0], dims[2][1], 256, device, f32=False)
+        self.HEAD = [_Act(B, *dims[2 + i], 128, device) for i in range(3)]          # head residual-block output
+        self.HY = [_Act(B, *dims[2 + i], 128, device, f32=False) for i in range(3)]
+        self.CIN = [_Act(B, *dims[2 + i], 128, device, f32=False) for i in range(3)]  # relu(context head)
+        self.stats = torch.zeros(B2, 128, 2, device=device)
+        self.stats2 = torch.zeros(B2, 128, 2, device=device)
+        self.ws = ops.instnorm_workspace(B2, 128, device)
+        self.shape = shape
+
+    # ---- building blocks -------------------------------------------------------------------------
+    def _conv(self, key: str, src: _Act, out_slice, Hin: int, Win: int, act=L.ACT_NONE, res=None) -> Tuple[int, int]:
+        w = self.w[key]
+        e = ops.make_epilogue(L.EPI_LINEAR, out_slice, act=act, bias=w.bias, res=res)
+        return ops.conv2d_ex([src.s(f32=False)], w, e, src.B, Hin, Win)
+
+    def _in_norm(self, raw: _Act, out_slice, stats, relu=True, res=None):
+        ops.instnorm_stats(raw.s(split=False), self.ws, stats, raw.B, raw.H, raw.W)
+        ops.instnorm_apply(raw.s(split=False), stats, out_slice, raw.B, raw.H, raw.W, relu=relu, res=res)
+
+    def _block(self, key: str, x: _Act, out: _Act, scratch: dict, inst: bool) -> None:
+        """ResidualBlock (reference core/extractor.py:6-60): x -> out (possibly at half resolution)."""
+        n = x.B
+        Y, RAW, RAWD = scratch["Y"].view(n), scratch["RAW"].view(n), scratch["RAWD"].view(n)
+        has_ds = (key + ".ds") in self.w
+        if inst:
+            self._conv(key + ".conv1", x, RAW.s(split=False), x.H, x.W)
+            self._in_norm(RAW, Y.s(f32=False), self.stats, relu=True)
+            if has_ds:
+                self._conv(key + ".ds", x, RAWD.s(split=False), x.H, x.W)
+                self._in_norm(RAWD, RAWD.s(split=False), self.stats2, relu=False)
+                res = RAWD.s(split=False)
+            else:
+                res = x.s(split=False)
+            self._conv(key + ".conv2", Y, RAW.s(split=False), Y.H, Y.W)
+            self._in_norm(RAW, out.s(), self.stats, relu=True, res=res)
+        else:
+            self._conv(key + ".conv1", x, Y.s(f32=False), x.H, x.W, act=L.ACT_RELU)
+            if has_ds:
+                self._conv(key + ".ds", x, RAWD.s(split=False), x.H, x.W)
+                res = (RAWD.f32, 0)
+            else:
+                res = (x.f32, 0)
+            self._conv(key + ".conv2", Y, out.s(), Y.H, Y.W, act=L.ACT_RELU, res=res)
+
+    def _trunk(self, tag: str, net, n: int) -> _Act:
+        """conv1 + norm + relu, layer1..3 (reference core/extractor.py:173-190 / 274-281) on the first n
+        images of the stem buffer -> 128-channel activation at 1/4 resolution."""
+        inst = net.norm_fn == "instance"
+        l0 = self.lvl[0]
+        x = l0["A"].view(n)
+        stem = self.STEM.view(n)
+        if inst:
+            raw = l0["RAW"].view(n)
+            self._conv(tag + ".conv1", stem, raw.s(split=False), self.H, self.W)
+            self._in_norm(raw, x.s(), self.stats, relu=True)
+        else:
+            self._conv(tag + ".conv1", stem, x.s(), self.H, self.W, act=L.ACT_RELU)
+        cur, cur_lvl = x, 0
+        for lname, lvl in (("layer1", 0), ("layer2", 1), ("layer3", 2)):
+            for i in range(2):
+                scratch = self.lvl[lvl]
+                cand = scratch["A"].view(n)
+                out = scratch["Bb"].view(n) if cand.f32.data_ptr() == cur.f32.data_ptr() else cand
+                self._block(f"{tag}.{lname}.{i}", cur, out, scratch, inst)
+                cur = out
+        return cur
+
+    # ---- forward -----------------------------------------------------------------------------------
+    def run(self, image1: torch.Tensor, image2: torch.Tensor) -> None:
+        """image (B,3,H,W) fp32 in [0,255].  Fills self.FMAP (bf16 hi/lo, images [0,B) = left, [B,2B) = right),
+        and the update engine's hidden-state slices X[i][:, :128] and context buffers CTX[i]."""
+        B, _, H, W = image1.shape
+        L.require_device(image1)
+        self.pack_weights()
+        self.allocate(B, H, W, image1.device)
+        eng = self.update
+        eng.allocate(B, self.dims[2][0], self.dims[2][1], image1.device)
+        im1 = image1.contiguous().float()
+        im2 = image2.contiguous().float()
+        # ---- fnet on [left; right] (reference raft_stereo.py:102) ----
+        ops.stem_rows(im1, self.STEM.hi[:B], self.STEM.lo[:B])
+        ops.stem_rows(im2, self.STEM.hi[B:], self.STEM.lo[B:])
+        x = self._trunk("f", self.fnet, 2 * B)
+        self._conv("f.conv2", x, self.FMAP.s(f32=False), x.H, x.W)
+        # ---- cnet on left (reference raft_stereo.py:101); the stem rows of the left images are still there ----
+        x = self._trunk("c", self.cnet, B)
+        feats = [x]
+        for li, lname in ((3, "layer4"), (4, "layer5")):
+            cur = feats[-1]
+            for i in range(2):
+                scratch = self.lvl[li]
+                cand = scratch["A"].view(B)
+                out = scratch["Bb"].view(B) if cand.f32.data_ptr() == cur.f32.data_ptr() else cand
+                self._block(f"c.{lname}.{i}", cur, out, scratch, False)
+                cur = out
+            feats.append(cur)
+        for i in range(3):
+            f = feats[i]
+            scratch = dict(Y=self.HY[i], RAW=self.lvl[2 + i]["RAW"], RAWD=self.lvl[2 + i]["RAWD"])
+            for j in range(2):
+                src = f
+                if (f"c.head{i}.{j}.block.conv1") in self.w:
+                    self._block(f"c.head{i}.{j}.block", f, self.HEAD[i], scratch, False)
+                    src = self.HEAD[i]
+                if j == 0:      # hidden state: tanh -> GRU state buffer (fp32 + hi/lo)
+                    split = eng.impl == "tc"
+                    self._conv(f"c.head{i}.0.conv", src, eng._slice(eng.X[i], 0, 128, True, split), src.H, src.W, act=L.ACT_TANH)
+                else:           # context: relu -> zqr conv (+ folded gate biases) -> CTX
+                    self._conv(f"c.head{i}.1.conv", src, self.CIN[i].s(f32=False), src.H, src.W, act=L.ACT_RELU)
+                    ctx = eng.CTX[i]
+                    self._conv(f"c.zqr{i}.zr", self.CIN[i], TS(ctx["f32"], None, None, 0, 256), src.H, src.W)
+                    self._conv(f"c.zqr{i}.q", self.CIN[i], TS(ctx["f32"], None, None, 256, 128), src.H, src.W)

@@ -150,6 +150,7 @@ class IGEVStereo(nn.Module):
         geo = ops.geo_pool(gev, out=self._geo_pyr)
         self._vol = (geo, init)
         eng.load_state(net_list, ctx_list)
+        eng.DELTA["f32"].zero_()
         eng.FLOW["f32"].copy_(init_disp.permute(0, 2, 3, 1))
         gkey = (iters,)
         if self.use_cuda_graph and gkey in self._graphs:

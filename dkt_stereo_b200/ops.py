@@ -70,6 +70,19 @@ def corr1d_build(fmap1: torch.Tensor, fmap2: torch.Tensor, levels: int, scale: f
     return pyr
 
 
+def corr1d_build_split(hi1: torch.Tensor, lo1: torch.Tensor, hi2: torch.Tensor, lo2: torch.Tensor,
+                       levels: int, scale: float, pyr: List[torch.Tensor]) -> List[torch.Tensor]:
+    """K1 straight from NHWC (B,H,W,D) bf16 (hi, lo) feature maps (what the encoder engine writes)."""
+    lib = L.load()
+    B, H, W1, D = hi1.shape
+    W2 = hi2.shape[2]
+    for t in (hi1, lo1, hi2, lo2):
+        assert t.is_contiguous() and t.dtype == torch.bfloat16
+    L.check(lib.dkt_corr1d_build_tc(hi1.data_ptr(), lo1.data_ptr(), hi2.data_ptr(), lo2.data_ptr(), L.pointer_array(pyr),
+                                    B, D, H, W1, W2, levels, float(scale), L.stream_ptr()), "corr1d_build_tc")
+    return pyr
+
+
 # ---------------------------------------------------------------------------------------------
 # K2
 # ---------------------------------------------------------------------------------------------
@@ -166,13 +179,15 @@ def geo_lookup_enc(geo: Sequence[torch.Tensor], init: Sequence[torch.Tensor], di
 @dataclass
 class ConvWeights:
     """A conv layer repacked for the engine (done once per checkpoint load)."""
-    ksize: int
+    ksize: int               # kh (== kw for the square filters of the update block)
     cin: int                 # padded input channels the kernel iterates over
     n: int                   # real output channels
     w_simt: torch.Tensor     # fp32 [taps][cin][n]
     w_hi: Optional[torch.Tensor]   # bf16 [taps][npad][cin]
     w_lo: Optional[torch.Tensor]
     bias: Optional[torch.Tensor]   # fp32 [n] (None when folded into a context term)
+    kw: Optional[int] = None       # filter width when it differs from ksize (7x1 stem)
+    stride: int = 1
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], cin_pad: Optional[int] = None,
@@ -207,7 +222,7 @@ def pack_conv_cat(weights: Sequence[torch.Tensor], tc: bool = True) -> ConvWeigh
 def make_epilogue(kind: int, out: DktTensor, act: int = L.ACT_NONE, scale: float = 1.0,
                   bias: Optional[torch.Tensor] = None, ctx: Optional[torch.Tensor] = None, ctx_c0: int = 0,
                   z: Optional[DktTensor] = None, h: Optional[DktTensor] = None,
-                  tail: Optional[torch.Tensor] = None) -> DktEpilogue:
+                  tail: Optional[torch.Tensor] = None, res: Optional[tuple] = None) -> DktEpilogue:
     e = DktEpilogue()
     e.kind, e.act, e.scale = kind, act, scale
     e.bias = L.ptr(bias)
@@ -219,7 +234,78 @@ def make_epilogue(kind: int, out: DktTensor, act: int = L.ACT_NONE, scale: float
     e.h = h if h is not None else null_tensor()
     e.tail = L.ptr(tail)
     e.tail_C = tail.shape[-1] if tail is not None else 0
+    if res is not None:          # (tensor NHWC fp32, first channel)
+        e.res, e.res_C, e.res_c0 = L.ptr(res[0]), res[0].shape[-1], res[1]
     return e
+
+
+def pack_conv_general(weight: torch.Tensor, bias: Optional[torch.Tensor], *, stride: int = 1,
+                      cin_pad: Optional[int] = None, n_pad: Optional[int] = None,
+                      bn: Optional[Sequence[torch.Tensor]] = None, bn_eps: float = 1e-5) -> ConvWeights:
+    """Encoder conv (N, Cin, kh, kw) -> tensor-core layout [kh*kw][Npad][Cin_pad] bf16 hi/lo.
+    ``bn`` = (gamma, beta, running_mean, running_var) folds an eval-mode BatchNorm that follows the conv
+    into weight and bias; ``cin_pad`` / ``n_pad`` zero-pad channels (96-channel stages run as 128)."""
+    w = weight.detach().double()
+    N, Cin, kh, kw = w.shape
+    b = bias.detach().double() if bias is not None else torch.zeros(N, dtype=torch.float64, device=w.device)
+    if bn is not None:
+        gamma, beta, mean, var = (t.detach().double() for t in bn)
+        s = gamma / torch.sqrt(var + bn_eps)
+        w = w * s.view(-1, 1, 1, 1)
+        b = (b - mean) * s + beta
+    if cin_pad is not None and cin_pad > Cin:
+        w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, cin_pad - Cin))
+        Cin = cin_pad
+    if n_pad is not None and n_pad > N:
+        w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, n_pad - N))
+        b = torch.nn.functional.pad(b, (0, n_pad - N))
+        N = n_pad
+    w = w.float()
+    npad = (N + 15) // 16 * 16
+    w_tnk = w.permute(2, 3, 0, 1).reshape(kh * kw, N, Cin)
+    if npad != N:
+        w_tnk = torch.nn.functional.pad(w_tnk, (0, 0, 0, npad - N))
+    w_hi, w_lo = split_bf16(w_tnk.contiguous())
+    return ConvWeights(kh, Cin, N, None, w_hi.contiguous(), w_lo.contiguous(), b.float().contiguous(), kw=kw, stride=stride)
+
+
+def conv2d_ex(srcs: Sequence[DktTensor], w: ConvWeights, epi: DktEpilogue, B: int, Hin: int, Win: int) -> tuple:
+    """Tensor-core conv with kh x kw filter and stride; returns the output extent (H, W)."""
+    lib = L.load()
+    kh, kw, s = w.ksize, (w.kw or w.ksize), w.stride
+    H = (Hin + 2 * (kh // 2) - kh) // s + 1
+    W = (Win + 2 * (kw // 2) - kw) // s + 1
+    n = len(srcs)
+    arr = (DktTensor * n)(*srcs)
+    assert sum(t.c_count for t in srcs) == w.cin, (sum(t.c_count for t in srcs), w.cin)
+    L.check(lib.dkt_conv2d_tc_ex(arr, n, w.w_hi.data_ptr(), w.w_lo.data_ptr(), kh, kw, s, w.n, C.byref(epi),
+                                 B, Hin, Win, H, W, L.stream_ptr()), "conv2d_tc_ex")
+    return H, W
+
+
+def stem_rows(img: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, kw: int = 7,
+              scale: float = 2.0 / 255.0, shift: float = -1.0) -> None:
+    """img (B,Cin,H,W) fp32 in [0,255] -> hi/lo (B,H,W,Cpad) bf16, channel kx*Cin + c (see the header)."""
+    B, Cin, H, W = img.shape
+    assert img.is_contiguous() and img.dtype == torch.float32 and hi.shape == (B, H, W, hi.shape[-1])
+    L.check(L.load().dkt_stem_rows_bf16x2(img.data_ptr(), scale, shift, hi.data_ptr(), lo.data_ptr(),
+                                          B, Cin, H, W, kw, hi.shape[-1], L.stream_ptr()), "stem_rows")
+
+
+def instnorm_workspace(B: int, Cc: int, device) -> torch.Tensor:
+    return torch.empty(L.load().dkt_instnorm_workspace_floats(B, Cc), device=device, dtype=torch.float32)
+
+
+def instnorm_stats(x: DktTensor, workspace: torch.Tensor, stats: torch.Tensor, B: int, H: int, W: int,
+                   eps: float = 1e-5) -> None:
+    L.check(L.load().dkt_instnorm_stats(C.byref(x), workspace.data_ptr(), stats.data_ptr(), eps, B, H, W,
+                                        L.stream_ptr()), "instnorm_stats")
+
+
+def instnorm_apply(x: DktTensor, stats: torch.Tensor, out: DktTensor, B: int, H: int, W: int,
+                   relu: bool = True, res: Optional[DktTensor] = None) -> None:
+    L.check(L.load().dkt_instnorm_apply(C.byref(x), stats.data_ptr(), C.byref(res) if res is not None else None,
+                                        C.byref(out), int(relu), B, H, W, L.stream_ptr()), "instnorm_apply")
 
 
 def conv2d(srcs: Sequence[DktTensor], w: ConvWeights, epi: DktEpilogue, B: int, H: int, W: int,
@@ -334,7 +420,12 @@ def _conv_name(srcs, w, epi, B, H, W, impl="tc"):
 
 
 conv2d = _profiled(_conv_name)(conv2d)
+conv2d_ex = _profiled(lambda srcs, w, epi, B, Hin, Win: f"enc_conv{w.ksize}x{w.kw or w.ksize}s{w.stride}_{w.cin}to{w.n}_{Hin}x{Win}")(conv2d_ex)
+stem_rows = _profiled(lambda *a, **k: "stem_rows")(stem_rows)
+instnorm_stats = _profiled(lambda *a, **k: "instnorm_stats")(instnorm_stats)
+instnorm_apply = _profiled(lambda *a, **k: "instnorm_apply")(instnorm_apply)
 corr1d_build = _profiled(lambda *a, **k: f"corr1d_build_{k.get('impl', a[4] if len(a) > 4 else 'tc')}")(corr1d_build)
+corr1d_build_split = _profiled(lambda *a, **k: "corr1d_build_tc")(corr1d_build_split)
 corr1d_lookup = _profiled(lambda pyr, *a, **k: "corr1d_lookup" if len(pyr) else "coords_update")(corr1d_lookup)
 pool2x = _profiled(lambda *a, **k: "pool2x")(pool2x)
 interp = _profiled(lambda *a, **k: "interp")(interp)

@@ -7,10 +7,13 @@ iters, flow_init, test_mode)`` and the same ``state_dict`` keys, so DKT checkpoi
 graph (autograd through the loop) is outside this engine's scope and raises.
 
 What runs where:
-  PyTorch (cuDNN)  : cnet / fnet / context_zqr_convs       (reference raft_stereo.py:91-114)
   libdkt kernels   : correlation pyramid (K1), per-iteration lookup + coordinate update (K2),
                      motion encoder + 3 ConvGRUs + flow head (K3), mask head + convex
                      upsampling (K4)                          (reference raft_stereo.py:118-183)
+                     and -- default on the tensor-core path -- cnet / fnet / context_zqr_convs on the
+                     same conv kernel (``encoder.EncoderEngine``, reference raft_stereo.py:91-114)
+  PyTorch (cuDNN)  : the encoders when ``DKT_NATIVE_ENCODER=0``, ``corr_implementation="b200_fp32"``,
+                     mixed precision, or a configuration the encoder engine does not serve
 The GRU loop is captured into a CUDA graph per (shape, iters) and replayed.
 """
 from __future__ import annotations
@@ -72,6 +75,11 @@ class RAFTStereo(nn.Module):
         else:
             self.fnet = BasicEncoder(output_dim=256, norm_fn="instance", downsample=args.n_downsample)
         self.engine = UpdateEngine(self.update_block, self.impl)
+        self.encoder = None
+        if (os.environ.get("DKT_NATIVE_ENCODER", "1") == "1" and self.impl == "tc" and not getattr(args, "shared_backbone", False)
+                and args.context_norm == "batch" and args.n_downsample == 2 and not getattr(args, "mixed_precision", False)):
+            from .encoder import EncoderEngine
+            self.encoder = EncoderEngine(self.fnet, self.cnet, self.context_zqr_convs, self.engine)
         self.use_cuda_graph = os.environ.get("DKT_CUDA_GRAPH", "1") == "1"
         self.extractor_fp32 = not getattr(args, "extractor_tf32", False)
         self.channels_last = os.environ.get("DKT_CHANNELS_LAST", "0") == "1"
@@ -120,24 +128,31 @@ class RAFTStereo(nn.Module):
 
     def hot_path(self, fmap1, fmap2, net_list, ctx_list, iters: int, flow_init: Optional[torch.Tensor] = None
                  ) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Volume build -> ``iters`` update iterations -> convex upsampling.
-        Returns (flow_lowres (B,2,h,w), flow_up (B,1,H,W)) as reference raft_stereo.py:182-183."""
+        """Volume build -> ``iters`` update iterations -> convex upsampling, from the PyTorch encoders'
+        NCHW products.  Returns (flow_lowres (B,2,h,w), flow_up (B,1,H,W)) as reference raft_stereo.py:182-183."""
         args, eng = self.args, self.engine
         L.require_device(fmap1)
         B, D, h, w = fmap1.shape
-        dev = fmap1.device
         eng.pack_weights()
-        eng.allocate(B, h, w, dev)
-        key = (B, D, h, w, args.corr_levels, str(dev))
+        eng.allocate(B, h, w, fmap1.device)
+        self._ensure_volume(B, D, h, w, fmap1.device)
+        ops.corr1d_build(fmap1, fmap2, args.corr_levels, 1.0 / (D ** 0.5), impl=self.impl, pyr=self._pyr)      # K1
+        eng.load_state(net_list, ctx_list)
+        return self._loop_and_upsample(B, h, w, iters, flow_init)
+
+    def _ensure_volume(self, B, D, h, w, dev) -> None:
+        key = (B, D, h, w, self.args.corr_levels, str(dev))
         if self._pyr_key != key:
-            self._pyr = ops.alloc_pyramid(B, h, w, w, args.corr_levels, dev)
+            self._pyr = ops.alloc_pyramid(B, h, w, w, self.args.corr_levels, dev)
             self._pyr_key = key
             self._graphs.clear()
             self._seen.clear()
-        # K1
-        ops.corr1d_build(fmap1, fmap2, args.corr_levels, 1.0 / (D ** 0.5), impl=self.impl, pyr=self._pyr)
+
+    def _loop_and_upsample(self, B, h, w, iters, flow_init):
+        args, eng = self.args, self.engine
+        dev = eng.device
         # loop state: coords0 = pixel grid; coords1 = coords0 (+ flow_init); flow = coords1 - coords0
-        eng.load_state(net_list, ctx_list)
+        eng.DELTA["f32"].zero_()
         xs = torch.arange(w, device=dev, dtype=torch.float32).view(1, 1, w).expand(B, h, w)
         eng.FLOW["f32"].zero_()
         if flow_init is not None:
@@ -165,6 +180,19 @@ class RAFTStereo(nn.Module):
         flow_lr = eng.FLOW["f32"].permute(0, 3, 1, 2).contiguous()
         return flow_lr, flow_up
 
+    def forward_native(self, image1, image2, iters: int, flow_init=None):
+        """Whole forward on libdkt kernels: encoders (EncoderEngine) -> K1 from the bf16 (hi, lo) feature maps
+        the encoder wrote -> loop -> upsampling.  No NCHW <-> NHWC conversion and no fp32 -> bf16 split pass."""
+        args, enc, eng = self.args, self.encoder, self.engine
+        B = image1.shape[0]
+        enc.run(image1, image2)
+        h, w = enc.dims[2]
+        D = enc.FMAP.C
+        self._ensure_volume(B, D, h, w, image1.device)
+        f = enc.FMAP
+        ops.corr1d_build_split(f.hi[:B], f.lo[:B], f.hi[B:], f.lo[B:], args.corr_levels, 1.0 / (D ** 0.5), self._pyr)
+        return self._loop_and_upsample(B, h, w, iters, flow_init)
+
     def forward(self, image1, image2, iters=12, flow_init=None, test_mode=False):
         """Estimate disparity (returned as negative flow, like the reference) between a stereo pair."""
         if not test_mode:
@@ -174,5 +202,7 @@ class RAFTStereo(nn.Module):
         if not image1.is_cuda:
             raise L.DktError("RAFTStereo (B200 engine) needs CUDA inputs; there is no CPU fallback")
         with torch.no_grad():
+            if self.encoder is not None:
+                return self.forward_native(image1, image2, iters, flow_init)
             fmap1, fmap2, net_list, ctx_list = self.extract(image1, image2)
             return self.hot_path(fmap1, fmap2, net_list, ctx_list, iters, flow_init)

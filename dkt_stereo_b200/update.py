@@ -209,7 +209,6 @@ class UpdateEngine:
             ctx = inp_list[i]
             ctx = ctx if torch.is_tensor(ctx) else torch.cat(list(ctx), dim=1)
             ops.nchw_to_nhwc(ctx, self._slice(self.CTX[i], 0, 384, True, False), bias=self.gru_bias[i])
-        self.DELTA["f32"].zero_()
 
     def hidden_states(self) -> List[torch.Tensor]:
         return [ops.nhwc_to_nchw(self._slice(self.X[i], 0, 128, True, False), self.B, *self.hw[i], self.device)

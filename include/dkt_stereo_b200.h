@@ -79,6 +79,9 @@ typedef struct dkt_epilogue {
     const float* tail;      /* LINEAR: optional NHWC fp32 source copied into channels          */
     int32_t      tail_C;    /*   [N_valid, N_valid+tail_C) of `out` (motion features ++ flow,  */
                             /*   reference core/update.py:85).                                 */
+    const float* res;       /* LINEAR (tensor-core path): optional NHWC fp32 residual; the     */
+    int32_t      res_C;     /*   result becomes relu(y + res[p][res_c0 + n]) -- the tail of a  */
+    int32_t      res_c0;    /*   ResidualBlock (reference core/extractor.py:56-60).            */
 } dkt_epilogue;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -169,6 +172,12 @@ int dkt_conv2d_simt(const dkt_tensor* srcs, int nsrc, const float* weight, int k
                     const dkt_epilogue* epi, int B, int H, int W, void* stream);
 int dkt_conv2d_tc(const dkt_tensor* srcs, int nsrc, const uint16_t* w_hi, const uint16_t* w_lo,
                   int ksize, int N, const dkt_epilogue* epi, int B, int H, int W, void* stream);
+/* General form used by the encoders (reference core/extractor.py): kh x kw filter (odd, <= 7, padding
+ * k/2), stride 1 or 2; sources are (B,Hin,Win,C), outputs (B,H,W,.) with H = (Hin + 2*(kh/2) - kh)/stride + 1.
+ * Weight layout as above with taps = kh*kw, tap = ky*kw + kx. */
+int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t* w_hi, const uint16_t* w_lo,
+                     int kh, int kw, int stride, int N, const dkt_epilogue* epi,
+                     int B, int Hin, int Win, int H, int W, void* stream);
 
 /* ---- a8: cross-scale plumbing of the multi-level GRU -----------------------------------------
  * dkt_pool2x  : F.avg_pool2d(x,3,stride=2,padding=1), divisor 9 (reference core/update.py:87-88)
@@ -196,6 +205,23 @@ int dkt_nchw_to_nhwc(const float* src, const float* bias, const dkt_tensor* dst,
 int dkt_nhwc_to_nchw(const dkt_tensor* src, float* dst, int B, int C, int H, int W, void* stream);
 int dkt_split_nchw_to_nhwc_bf16x2(const float* src, int64_t sb, int64_t sd, int64_t sh, int64_t sw,
                                   uint16_t* hi, uint16_t* lo, int B, int D, int H, int W, void* stream);
+
+/* ---- encoder side (reference core/extractor.py:122-300 on the same kernels) ----
+ * dkt_stem_rows_bf16x2 : image (B,Cin,H,W) fp32 -> NHWC (B,H,W,Cpad) bf16 (hi,lo) with channel kx*Cin + c =
+ *   scale*img[b,c,y,x+kx-kw/2] + shift (0 outside the image; channels >= kw*Cin are 0).  With scale = 2/255,
+ *   shift = -1 this is the input normalisation of raft_stereo.py:91-92 fused with an x-im2col, after which the
+ *   7x7 stem conv (core/extractor.py:140) is a dkt_conv2d_tc_ex with kh = 7, kw = 1 over Cpad channels.
+ * dkt_instnorm_stats   : nn.InstanceNorm2d statistics (biased variance) of an NHWC fp32 slice ->
+ *   stats (B,C,2) = (mean, 1/sqrt(var+eps)); workspace >= dkt_instnorm_workspace_floats(B,C) floats.
+ * dkt_instnorm_apply   : out = (x - mean)*rstd, then ReLU if relu != 0, then relu(res + out) if res != NULL
+ *   (the ResidualBlock tail, core/extractor.py:56-60); writes every non-null precision of `out`. */
+int dkt_stem_rows_bf16x2(const float* img, float scale, float shift, uint16_t* hi, uint16_t* lo,
+                         int B, int Cin, int H, int W, int kw, int Cpad, void* stream);
+int dkt_instnorm_workspace_floats(int B, int C);
+int dkt_instnorm_stats(const dkt_tensor* x, float* workspace, float* stats, float eps,
+                       int B, int H, int W, void* stream);
+int dkt_instnorm_apply(const dkt_tensor* x, const float* stats, const dkt_tensor* res, const dkt_tensor* out,
+                       int relu, int B, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

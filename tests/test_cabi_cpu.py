@@ -28,12 +28,26 @@ def test_library_builds_and_exports_header_symbols():
     assert lib.dkt_error_string(-2).decode().startswith("shape or option")
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof / offsetof of the two ABI structs as gcc lays them out from the header == the ctypes mirror."""
+    import subprocess
     from dkt_stereo_b200 import _lib
-    # dkt_tensor: 3 pointers + 3 int32 (+4 pad) ; dkt_epilogue as declared
-    assert ctypes.sizeof(_lib.DktTensor) == 40
-    assert _lib.DktEpilogue.out.offset == 40
-    assert ctypes.sizeof(_lib.DktEpilogue) == 40 + 3 * 40 + 16
+    fields_t = [n for n, _ in _lib.DktTensor._fields_]
+    fields_e = [n for n, _ in _lib.DktEpilogue._fields_]
+    src = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/dkt_stereo_b200.h"', 'int main(void){',
+             'printf("%zu %zu\\n", sizeof(dkt_tensor), sizeof(dkt_epilogue));']
+    lines += [f'printf("%zu\\n", offsetof(dkt_tensor, {f}));' for f in fields_t]
+    lines += [f'printf("%zu\\n", offsetof(dkt_epilogue, {f}));' for f in fields_e]
+    lines += ['return 0;}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    vals = [int(v) for v in out]
+    assert vals[0] == ctypes.sizeof(_lib.DktTensor) and vals[1] == ctypes.sizeof(_lib.DktEpilogue)
+    mine = [getattr(_lib.DktTensor, f).offset for f in fields_t] + [getattr(_lib.DktEpilogue, f).offset for f in fields_e]
+    assert vals[2:] == mine
 
 
 def test_argument_validation_without_gpu():

@@ -266,6 +266,7 @@ def _run_update(tag, igev, impl):
             e.CORR["lo"].copy_(lo)
         e.FLOW["f32"].copy_(flow.permute(0, 2, 3, 1))
 
+    eng.fused_enc = False          # this test injects the correlation features itself (no lookup kernel)
     eng.step(lookup, with_mask=True)
     torch.cuda.synchronize()
     net = eng.hidden_states()
@@ -307,13 +308,17 @@ def test_upsamplers_golden():
 def _model(impl, g):
     from dkt_stereo_b200.raft_stereo import RAFTStereo
     from dkt_stereo_b200.synthetic import synthetic_state_dict
-    cfg = dict(RAFT_CFG, corr_implementation="b200" if impl == "tc" else "b200_fp32")
+    cfg = dict(RAFT_CFG, corr_implementation="b200_fp32" if impl == "simt" else "b200")
     model = RAFTStereo(Namespace(mixed_precision=False, **cfg)).eval()
     model.load_state_dict(synthetic_state_dict(golden_shapes(g), seed=0), strict=True)
+    if impl == "tc_torchenc":          # tensor-core hot path fed by the PyTorch (cuDNN fp32) encoders
+        model.encoder = None
+    else:
+        assert (model.encoder is not None) == (impl == "tc")
     return model.to(dev())
 
 
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl", ["simt", "tc", "tc_torchenc"])
 @pytest.mark.parametrize("tag", ["raft_fwd_small", "raft_fwd_shift", "raft_fwd_cfg1"])
 def test_raft_forward_golden(impl, tag):
     from dkt_stereo_b200.synthetic import synthetic_pair
@@ -377,3 +382,114 @@ def test_igev_hot_path_golden(tag, impl, monkeypatch):
         print(f"[parity] {tag} impl={impl} rep={rep}: mean-abs {mean:.3e} px, max-abs {mx:.3e} px")
         assert up.shape == (B, 1, H, W)
         assert mean <= 1e-3, (tag, impl, rep, mean, mx)       # the north-star gate
+
+
+# ---------------------------------------------------------------------------------------------
+# encoder side: strided / 7x1 convs, residual epilogue, instance norm, whole encoders
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 64, 96, 19, 37, 3, 2), (1, 128, 128, 16, 32, 1, 2), (2, 64, 64, 18, 33, 3, 1),
+                                   (1, 128, 256, 9, 21, 1, 1)])
+def test_conv_ex_strided_and_residual(shape):
+    """dkt_conv2d_tc_ex: 3x3 / 1x1, stride 1 / 2 (TMA element strides), bias + ReLU + residual tail."""
+    from dkt_stereo_b200 import ops, _lib as L
+    B, Cin, N, H, W, k, stride = shape
+    g = torch.Generator().manual_seed(Cin * 7 + N + stride)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    wt = torch.randn(N, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    bias = torch.randn(N, generator=g)
+    y = torch.relu(torch.nn.functional.conv2d(x, wt, bias, stride=stride, padding=k // 2))
+    Ho, Wo = y.shape[-2:]
+    res = torch.randn(B, N, Ho, Wo, generator=g)
+    ref = torch.relu(y + res)
+    xs, keep = _slice_of(_nhwc(x).to(dev()), "tc")
+    npad = (N + 63) // 64 * 64
+    Wc = ops.pack_conv_general(wt.to(dev()), bias.to(dev()), stride=stride, n_pad=npad)
+    out = torch.zeros(B, Ho, Wo, npad, device=dev())
+    hi = torch.zeros(B, Ho, Wo, npad, device=dev(), dtype=torch.bfloat16)
+    lo = torch.zeros_like(hi)
+    resd = torch.zeros(B, Ho, Wo, npad, device=dev())
+    resd[..., :N] = _nhwc(res).to(dev())
+    e = ops.make_epilogue(L.EPI_LINEAR, L.tensor_slice(out, hi, lo, 0, npad), act=L.ACT_RELU, bias=Wc.bias, res=(resd, 0))
+    assert ops.conv2d_ex([xs], Wc, e, B, H, W) == (Ho, Wo)
+    torch.cuda.synchronize()
+    got = out[..., :N].permute(0, 3, 1, 2).cpu()
+    assert stats(got, ref)[1] < 3e-4, stats(got, ref)
+    assert torch.all(out[..., N:] == 0)                          # padded output channels stay exactly zero
+    assert stats((hi.float() + lo.float()).cpu(), out.cpu())[1] < 3e-4
+
+
+def test_stem_rows_7x7():
+    """Image normalisation + x-im2col + 7x1 tensor-core conv == conv2d(2*(img/255)-1, 7x7, pad 3)
+    (reference raft_stereo.py:91-92, core/extractor.py:140)."""
+    from dkt_stereo_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(21)
+    B, H, W = 2, 21, 70
+    img = torch.rand(B, 3, H, W, generator=g) * 255
+    wt = torch.randn(64, 3, 7, 7, generator=g) / 12.0
+    bias = torch.randn(64, generator=g)
+    ref = torch.nn.functional.conv2d(2 * (img / 255.0) - 1.0, wt, bias, padding=3)
+    hi = torch.zeros(B, H, W, 64, device=dev(), dtype=torch.bfloat16)
+    lo = torch.zeros_like(hi)
+    ops.stem_rows(img.to(dev()), hi, lo)
+    w7 = wt.permute(0, 3, 1, 2).reshape(64, 21, 7, 1)
+    Wc = ops.pack_conv_general(w7.to(dev()), bias.to(dev()), cin_pad=64)
+    out = torch.zeros(B, H, W, 64, device=dev())
+    e = ops.make_epilogue(L.EPI_LINEAR, L.tensor_slice(out, None, None, 0, 64), bias=Wc.bias)
+    ops.conv2d_ex([L.tensor_slice(None, hi, lo, 0, 64)], Wc, e, B, H, W)
+    torch.cuda.synchronize()
+    assert stats(out.permute(0, 3, 1, 2).cpu(), ref)[1] < 2e-4
+
+
+def test_instnorm():
+    from dkt_stereo_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(8)
+    B, Cc, H, W = 3, 128, 37, 29
+    x = torch.randn(B, Cc, H, W, generator=g) * 3 + 1.5
+    x[:, 100:] = 0                                             # zero-padded channels must stay zero
+    res = torch.randn(B, Cc, H, W, generator=g)
+    y = torch.relu(torch.nn.functional.instance_norm(x))
+    ref = torch.relu(res + y)
+    xd, rd = _nhwc(x).to(dev()), _nhwc(res).to(dev())
+    st = torch.zeros(B, Cc, 2, device=dev())
+    ws = ops.instnorm_workspace(B, Cc, dev())
+    out = torch.zeros(B, H, W, Cc, device=dev())
+    hi = torch.zeros(B, H, W, Cc, device=dev(), dtype=torch.bfloat16)
+    lo = torch.zeros_like(hi)
+    ops.instnorm_stats(L.tensor_slice(xd, None, None, 0, Cc), ws, st, B, H, W)
+    ops.instnorm_apply(L.tensor_slice(xd, None, None, 0, Cc), st, L.tensor_slice(out, hi, lo, 0, Cc), B, H, W,
+                       relu=True, res=L.tensor_slice(rd, None, None, 0, Cc))
+    torch.cuda.synchronize()
+    assert stats(out.permute(0, 3, 1, 2).cpu(), ref)[1] < 2e-5
+    assert stats(st[:, :100, 0].cpu(), x[:, :100].mean(dim=(2, 3)))[1] < 1e-5
+    plain = torch.zeros(B, H, W, Cc, device=dev())
+    ops.instnorm_apply(L.tensor_slice(xd, None, None, 0, Cc), st, L.tensor_slice(plain, None, None, 0, Cc), B, H, W, relu=False)
+    assert torch.all(plain[..., 100:] == 0)
+    assert stats(plain.permute(0, 3, 1, 2).cpu(), torch.nn.functional.instance_norm(x))[1] < 2e-5
+
+
+def test_encoder_engine_vs_pytorch_extractor():
+    """fnet / cnet / context convs on libdkt kernels vs the same modules on cuDNN fp32."""
+    from dkt_stereo_b200.raft_stereo import RAFTStereo
+    from dkt_stereo_b200.synthetic import synthetic_state_dict, synthetic_pair, shapes_of
+    model = RAFTStereo(Namespace(mixed_precision=False, **dict(RAFT_CFG, corr_implementation="b200"))).eval()
+    model.load_state_dict(synthetic_state_dict(shapes_of(model.state_dict()), seed=0), strict=True)
+    model = model.to(dev())
+    assert model.encoder is not None
+    im1, im2 = synthetic_pair(2, 96, 160, seed=77)
+    im1, im2 = im1.to(dev()), im2.to(dev())
+    with torch.no_grad():
+        fmap1, fmap2, net_list, ctx_list = model.extract(im1, im2)
+        model.encoder.run(im1, im2)
+    torch.cuda.synchronize()
+    enc, eng = model.encoder, model.engine
+    f = (enc.FMAP.hi.float() + enc.FMAP.lo.float()).permute(0, 3, 1, 2)
+    ref = torch.cat([fmap1, fmap2], 0)
+    m, mx = stats(f.cpu(), ref.cpu())
+    print(f"[encoder] fmap: mean-abs {m:.3e} max-abs {mx:.3e} (|ref| mean {float(ref.abs().mean()):.3f})")
+    assert mx < 2e-3 and m < 1e-4
+    for i in range(3):
+        h = eng.X[i]["f32"][..., :128].permute(0, 3, 1, 2)
+        assert stats(h.cpu(), net_list[i].cpu())[1] < 1e-3, (i, stats(h.cpu(), net_list[i].cpu()))
+        c = eng.CTX[i]["f32"].permute(0, 3, 1, 2)
+        cref = ctx_list[i] + eng.gru_bias[i].view(1, -1, 1, 1)
+        assert stats(c.cpu(), cref.cpu())[1] < 2e-3, (i, stats(c.cpu(), cref.cpu()))
