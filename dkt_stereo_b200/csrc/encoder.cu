@@ -22,7 +22,7 @@ namespace dkt {
 constexpr int SR_PIX = 64;
 
 __global__ void __launch_bounds__(256)
-stem_rows_kernel(const float* __restrict__ img, float scale, float shift,
+stem_rows_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64_t sy, int64_t sx, float scale, float shift,
                  uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
                  int Cin, int H, int W, int kw, int Cpad) {
     extern __shared__ float s_img[];                 // [Cin][SR_PIX + kw - 1]
@@ -34,7 +34,7 @@ stem_rows_kernel(const float* __restrict__ img, float scale, float shift,
         const int c = i / span, j = i - c * span;
         const int x = x0 + j - halo;
         float v = 0.f;
-        if (x >= 0 && x < W) v = fmaf(__ldg(img + (((int64_t)b * Cin + c) * H + y) * W + x), scale, shift);
+        if (x >= 0 && x < W) v = fmaf(img[b * sb + c * sc + y * sy + x * sx], scale, shift);
         s_img[i] = v;
     }
     __syncthreads();
@@ -139,11 +139,52 @@ instnorm_apply_kernel(const float* __restrict__ x, int xC, int xc0, const float*
     store_all4(out, p, c, y);
 }
 
+// ---------------------------------------------------------------------------------------------
+// tap sum: the second half of a 3x3 convolution with one output channel computed as
+// (a) a 1x1 tensor-core conv to the 9 per-tap responses T[p][t] = sum_c w[t][c] x[p][c] and
+// (b) out[p] = bias + sum_t T[p + (ky-1, kx-1)][t] (zero outside the image == zero padding).
+// Used for the flow / disparity head's last conv (reference core/update.py:10,14: 256 -> 2, of which
+// only channel 0 is ever used because raft_stereo.py:164 zeroes the y component), whose N = 2 would
+// otherwise drag the 256-channel input through nine shifted tensor-core tiles.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tapsum_kernel(const float* __restrict__ T, int TC, float bias, float* __restrict__ out, int out_C,
+              int64_t P, int H, int W) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int x = (int)(p % W);
+    const int y = (int)((p / W) % H);
+    float acc = bias;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xx = x + kx - 1;
+            if (xx < 0 || xx >= W) continue;
+            acc += __ldg(T + (p + (int64_t)(ky - 1) * W + (kx - 1)) * TC + ky * 3 + kx);
+        }
+    }
+    out[p * out_C] = acc;
+}
+
 }  // namespace dkt
 
 using namespace dkt;
 
-extern "C" int dkt_stem_rows_bf16x2(const float* img, float scale, float shift, uint16_t* hi, uint16_t* lo,
+extern "C" int dkt_tapsum3x3(const float* taps, int taps_C, float bias, float* out, int out_C,
+                             int B, int H, int W, void* stream) {
+    DKT_CHECK_ARG(taps && out);
+    DKT_CHECK_ARG(B > 0 && H > 0 && W > 0 && taps_C >= 9 && out_C >= 1);
+    const int64_t P = (int64_t)B * H * W;
+    tapsum_kernel<<<(unsigned)ceil_div64(P, 256), 256, 0, (cudaStream_t)stream>>>(taps, taps_C, bias, out, out_C, P, H, W);
+    DKT_RETURN_LAST();
+}
+
+
+extern "C" int dkt_stem_rows_bf16x2(const float* img, int64_t sb, int64_t sc, int64_t sy, int64_t sx,
+                                    float scale, float shift, uint16_t* hi, uint16_t* lo,
                                     int B, int Cin, int H, int W, int kw, int Cpad, void* stream) {
     DKT_CHECK_ARG(img && hi && lo);
     DKT_CHECK_ARG(B > 0 && Cin > 0 && H > 0 && W > 0 && kw > 0 && (kw & 1));
@@ -154,14 +195,14 @@ extern "C" int dkt_stem_rows_bf16x2(const float* img, float scale, float shift, 
     if (grid.y > 65535) {
         // gridDim.y limit: one image (or row band) at a time
         for (int b = 0; b < B; ++b) {
-            int rc = dkt_stem_rows_bf16x2(img + (int64_t)b * Cin * H * W, scale, shift, hi + (int64_t)b * H * W * Cpad,
+            int rc = dkt_stem_rows_bf16x2(img + (int64_t)b * sb, sb, sc, sy, sx, scale, shift, hi + (int64_t)b * H * W * Cpad,
                                           lo + (int64_t)b * H * W * Cpad, 1, Cin, H, W, kw, Cpad, stream);
             if (rc) return rc;
         }
         return 0;
     }
     const size_t smem = (size_t)Cin * (SR_PIX + kw - 1) * sizeof(float);
-    stem_rows_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(img, scale, shift, hi, lo, Cin, H, W, kw, Cpad);
+    stem_rows_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(img, sb, sc, sy, sx, scale, shift, hi, lo, Cin, H, W, kw, Cpad);
     DKT_RETURN_LAST();
 }
 

@@ -284,12 +284,25 @@ def conv2d_ex(srcs: Sequence[DktTensor], w: ConvWeights, epi: DktEpilogue, B: in
 
 
 def stem_rows(img: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, kw: int = 7,
-              scale: float = 2.0 / 255.0, shift: float = -1.0) -> None:
-    """img (B,Cin,H,W) fp32 in [0,255] -> hi/lo (B,H,W,Cpad) bf16, channel kx*Cin + c (see the header)."""
-    B, Cin, H, W = img.shape
-    assert img.is_contiguous() and img.dtype == torch.float32 and hi.shape == (B, H, W, hi.shape[-1])
-    L.check(L.load().dkt_stem_rows_bf16x2(img.data_ptr(), scale, shift, hi.data_ptr(), lo.data_ptr(),
+              scale: float = 2.0 / 255.0, shift: float = -1.0, layout: str = "nchw") -> None:
+    """img fp32, (B,Cin,H,W) or NHWC (B,H,W,Cin) -> hi/lo (B,H,W,Cpad) bf16, channel kx*Cin + c (see the header)."""
+    assert img.is_contiguous() and img.dtype == torch.float32
+    if layout == "nchw":
+        B, Cin, H, W = img.shape
+        sb, sc, sy, sx = Cin * H * W, H * W, W, 1
+    else:
+        B, H, W, Cin = img.shape
+        sb, sc, sy, sx = H * W * Cin, 1, W * Cin, Cin
+    assert hi.shape == (B, H, W, hi.shape[-1])
+    L.check(L.load().dkt_stem_rows_bf16x2(img.data_ptr(), sb, sc, sy, sx, scale, shift, hi.data_ptr(), lo.data_ptr(),
                                           B, Cin, H, W, kw, hi.shape[-1], L.stream_ptr()), "stem_rows")
+
+
+def tapsum3x3(taps: torch.Tensor, bias: float, out: torch.Tensor) -> None:
+    """taps NHWC (B,H,W,>=9) fp32 -> out[..., 0] (NHWC, any channel count) = bias + 3x3 spatial tap sum."""
+    B, H, W, TCc = taps.shape
+    L.check(L.load().dkt_tapsum3x3(taps.data_ptr(), TCc, float(bias), out.data_ptr(), out.shape[-1], B, H, W,
+                                   L.stream_ptr()), "tapsum3x3")
 
 
 def instnorm_workspace(B: int, Cc: int, device) -> torch.Tensor:
@@ -422,6 +435,7 @@ def _conv_name(srcs, w, epi, B, H, W, impl="tc"):
 conv2d = _profiled(_conv_name)(conv2d)
 conv2d_ex = _profiled(lambda srcs, w, epi, B, Hin, Win: f"enc_conv{w.ksize}x{w.kw or w.ksize}s{w.stride}_{w.cin}to{w.n}_{Hin}x{Win}")(conv2d_ex)
 stem_rows = _profiled(lambda *a, **k: "stem_rows")(stem_rows)
+tapsum3x3 = _profiled(lambda *a, **k: "tapsum3x3")(tapsum3x3)
 instnorm_stats = _profiled(lambda *a, **k: "instnorm_stats")(instnorm_stats)
 instnorm_apply = _profiled(lambda *a, **k: "instnorm_apply")(instnorm_apply)
 corr1d_build = _profiled(lambda *a, **k: f"corr1d_build_{k.get('impl', a[4] if len(a) > 4 else 'tc')}")(corr1d_build)

@@ -105,6 +105,8 @@ class UpdateEngine:
         # lookup kernels apply convc1 (1x1 + ReLU) on chip and write COR1 directly; set False to run the
         # unfused pair (lookup -> CORR buffer -> convc1 conv) for A/B measurements
         self.fused_enc = os.environ.get("DKT_FUSED_ENC", "1") == "1"
+        # 7x7 flow stem and the head's last conv in their tensor-core forms (tc only); 0 = generic kernels
+        self.fast_small_convs = os.environ.get("DKT_FAST_SMALL_CONVS", "1") == "1"
         self.weights: Optional[Dict[str, ops.ConvWeights]] = None
         self._wsig = None
         self.shape = None
@@ -138,6 +140,17 @@ class UpdateEngine:
         head = b.disp_head if self.igev else b.flow_head
         w["head1"] = ops.pack_conv(head.conv1.weight, head.conv1.bias, tc=tc)
         w["head2"] = ops.pack_conv(head.conv2.weight, head.conv2.bias, tc=tc)
+        if tc:
+            # tensor-core forms of the two awkward convs (see DESIGN.md "Iteration schedule"):
+            #  * the 7x7 flow stem as x-im2col rows + a 7x1 conv over 64 channels
+            #  * the head's 3x3 conv to ONE used channel as a 1x1 conv to 9 tap responses + a spatial tap sum
+            nfl = stem1.in_channels
+            w7 = stem1.weight.detach().permute(0, 3, 1, 2).reshape(stem1.out_channels, 7 * nfl, 7, 1)
+            w["stem1t"] = ops.pack_conv_general(w7, stem1.bias, cin_pad=64)
+            c2 = head.conv2
+            w9 = c2.weight.detach()[0].permute(1, 2, 0).reshape(9, c2.in_channels, 1, 1)
+            w["head2t"] = ops.pack_conv(w9, None, tc=True)
+            self.head2_bias0 = float(c2.bias.detach()[0])
         if self.igev:
             w["mask0"] = ops.pack_conv(b.mask_feat_4[0].weight, b.mask_feat_4[0].bias, tc=tc)
         else:
@@ -195,6 +208,9 @@ class UpdateEngine:
         if not self.igev:
             factor = 2 ** self.block.args.n_downsample
             self.MASK = self._buf(B, h0, w0, 9 * factor * factor, split=False)
+        if self.impl == "tc":
+            self.FROWS = self._buf(B, h0, w0, 64, f32=False)        # x-im2col of the flow field (7 taps x nflow)
+            self.TAPS = self._buf(B, h0, w0, 16, split=False)       # 9 tap responses of the head's last conv
         self.coords_x = torch.zeros(B, h0, w0, device=device, dtype=torch.float32)
         self.shape = shape
 
@@ -251,8 +267,13 @@ class UpdateEngine:
                        E(L.EPI_LINEAR, S(self.COR1, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["convc1"].bias), B, h0, w0, impl)
         ops.conv2d([S(self.COR1, 0, 64, simt, split)], Wt["convc2"],
                    E(L.EPI_LINEAR, S(self.CF, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["convc2"].bias), B, h0, w0, impl)
-        ops.conv2d([S(self.FLOW, 0, self.nflow, True, False)], Wt["stem1"],
-                   E(L.EPI_LINEAR, S(self.FLO1, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["stem1"].bias), B, h0, w0, "simt")
+        if split and self.fast_small_convs:
+            ops.stem_rows(self.FLOW["f32"], self.FROWS["hi"], self.FROWS["lo"], kw=7, scale=1.0, shift=0.0, layout="nhwc")
+            ops.conv2d_ex([S(self.FROWS, 0, 64, False, True)], Wt["stem1t"],
+                          E(L.EPI_LINEAR, S(self.FLO1, 0, 64, False, True), act=L.ACT_RELU, bias=Wt["stem1t"].bias), B, h0, w0)
+        else:
+            ops.conv2d([S(self.FLOW, 0, self.nflow, True, False)], Wt["stem1"],
+                       E(L.EPI_LINEAR, S(self.FLO1, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["stem1"].bias), B, h0, w0, "simt")
         ops.conv2d([S(self.FLO1, 0, 64, simt, split)], Wt["stem2"],
                    E(L.EPI_LINEAR, S(self.CF, 64, 64, simt, split), act=L.ACT_RELU, bias=Wt["stem2"].bias), B, h0, w0, impl)
         ops.conv2d([S(self.CF, 0, 128, simt, split)], Wt["conv"],
@@ -263,8 +284,13 @@ class UpdateEngine:
         # flow / disparity head (reference core/update.py:13-14)
         ops.conv2d([S(X0, 0, 128, simt, split)], Wt["head1"],
                    E(L.EPI_LINEAR, S(self.FH, 0, 256, simt, split), act=L.ACT_RELU, bias=Wt["head1"].bias), B, h0, w0, impl)
-        ops.conv2d([S(self.FH, 0, 256, simt, split)], Wt["head2"],
-                   E(L.EPI_LINEAR, S(self.DELTA, 0, self.nflow, True, False), bias=Wt["head2"].bias), B, h0, w0, impl)
+        if split and self.fast_small_convs:
+            ops.conv2d([S(self.FH, 0, 256, False, True)], Wt["head2t"],
+                       E(L.EPI_LINEAR, S(self.TAPS, 0, 9, True, False)), B, h0, w0, "tc")
+            ops.tapsum3x3(self.TAPS["f32"], self.head2_bias0, self.DELTA["f32"])
+        else:
+            ops.conv2d([S(self.FH, 0, 256, simt, split)], Wt["head2"],
+                       E(L.EPI_LINEAR, S(self.DELTA, 0, self.nflow, True, False), bias=Wt["head2"].bias), B, h0, w0, impl)
         if with_mask:
             self.mask_head()
 

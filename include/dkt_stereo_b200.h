@@ -207,16 +207,25 @@ int dkt_split_nchw_to_nhwc_bf16x2(const float* src, int64_t sb, int64_t sd, int6
                                   uint16_t* hi, uint16_t* lo, int B, int D, int H, int W, void* stream);
 
 /* ---- encoder side (reference core/extractor.py:122-300 on the same kernels) ----
- * dkt_stem_rows_bf16x2 : image (B,Cin,H,W) fp32 -> NHWC (B,H,W,Cpad) bf16 (hi,lo) with channel kx*Cin + c =
+ * dkt_stem_rows_bf16x2 : image fp32 (element (b,c,y,x) at b*sb + c*sc + y*sy + x*sx) -> NHWC (B,H,W,Cpad)
+ *   bf16 (hi,lo) with channel kx*Cin + c =
  *   scale*img[b,c,y,x+kx-kw/2] + shift (0 outside the image; channels >= kw*Cin are 0).  With scale = 2/255,
  *   shift = -1 this is the input normalisation of raft_stereo.py:91-92 fused with an x-im2col, after which the
  *   7x7 stem conv (core/extractor.py:140) is a dkt_conv2d_tc_ex with kh = 7, kw = 1 over Cpad channels.
+ *   The motion encoder's 7x7 flow stem (core/update.py:73,81) uses the same pair on the NHWC flow field.
  * dkt_instnorm_stats   : nn.InstanceNorm2d statistics (biased variance) of an NHWC fp32 slice ->
  *   stats (B,C,2) = (mean, 1/sqrt(var+eps)); workspace >= dkt_instnorm_workspace_floats(B,C) floats.
  * dkt_instnorm_apply   : out = (x - mean)*rstd, then ReLU if relu != 0, then relu(res + out) if res != NULL
  *   (the ResidualBlock tail, core/extractor.py:56-60); writes every non-null precision of `out`. */
-int dkt_stem_rows_bf16x2(const float* img, float scale, float shift, uint16_t* hi, uint16_t* lo,
+int dkt_stem_rows_bf16x2(const float* img, int64_t sb, int64_t sc, int64_t sy, int64_t sx,
+                         float scale, float shift, uint16_t* hi, uint16_t* lo,
                          int B, int Cin, int H, int W, int kw, int Cpad, void* stream);
+/* dkt_tapsum3x3 : out[p*out_C] = bias + sum_{ky,kx} taps[(p + (ky-1)*W + (kx-1))*taps_C + ky*3+kx] with zero
+ *   outside the image: the spatial half of a one-output-channel 3x3 conv whose channel half (a 1x1 conv to
+ *   9 tap responses) ran on dkt_conv2d_tc.  Used for FlowHead.conv2 / DispHead.conv2 (reference
+ *   core/update.py:10,14; only output channel 0 is consumed, raft_stereo.py:164). */
+int dkt_tapsum3x3(const float* taps, int taps_C, float bias, float* out, int out_C,
+                  int B, int H, int W, void* stream);
 int dkt_instnorm_workspace_floats(int B, int C);
 int dkt_instnorm_stats(const dkt_tensor* x, float* workspace, float* stats, float eps,
                        int B, int H, int W, void* stream);

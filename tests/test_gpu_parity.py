@@ -274,7 +274,10 @@ def _run_update(tag, igev, impl):
     for i in range(3):
         assert stats(net[i].cpu(), g[f"net_out{i}"])[1] < tol, (impl, i, stats(net[i].cpu(), g[f"net_out{i}"]))
     delta = eng.DELTA["f32"].permute(0, 3, 1, 2).cpu()
-    assert stats(delta, g["delta"])[1] < tol * 3, stats(delta, g["delta"])
+    # the tensor-core schedule only produces the consumed channel 0 (the reference zeroes delta_flow[:,1],
+    # raft_stereo.py:164); the generic kernels (simt, or DKT_FAST_SMALL_CONVS=0) produce every channel
+    nd = 1 if (impl == "tc" and eng.fast_small_convs) else delta.shape[1]
+    assert stats(delta[:, :nd], g["delta"][:, :nd])[1] < tol * 3, stats(delta[:, :nd], g["delta"][:, :nd])
     mask = (eng.MH if igev else eng.MASK)["f32"].permute(0, 3, 1, 2).cpu()
     assert stats(mask, g["mask"])[1] < tol * 3, stats(mask, g["mask"])
 
@@ -282,6 +285,12 @@ def _run_update(tag, igev, impl):
 @pytest.mark.parametrize("impl", IMPLS)
 def test_update_block_raft(impl):
     _run_update("raft", False, impl)
+
+
+def test_update_block_generic_small_convs(monkeypatch):
+    """Same step with the 7x7 stem / head conv2 on the generic kernels (all delta channels checked)."""
+    monkeypatch.setenv("DKT_FAST_SMALL_CONVS", "0")
+    _run_update("raft", False, "tc")
 
 
 @pytest.mark.parametrize("impl", IMPLS)
