@@ -51,7 +51,10 @@ struct TcConvParams {
     int H, W, tiles_x, tiles_y;
     int num_tiles;
     int stages;
-    uint32_t acc_cols;              // v2: TMEM columns per accumulator stage
+    uint32_t acc_cols;              // TMEM columns per accumulator stage
+    // patch kernel: one A stage = a (TILE_H + ygroup - 1)-row halo patch serving `ygroup` vertical taps
+    int ygroup, a_stages, w_stages;
+    uint32_t a_part_bytes;          // bytes of one precision (hi or lo) of an A stage
     uint32_t tmem_cols;
     dkt_epilogue epi;
 };
@@ -121,6 +124,79 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr) {
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)(BK == 64 ? 2 : 4) << 61;         // SWIZZLE_128B : SWIZZLE_64B
     return d;
+}
+
+// epilogue warps 2..9 of both persistent kernels (see the header comment of this file)
+__device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, uint32_t tmem_base,
+                                                       uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
+                                                       uint8_t* epi_smem, int warp, int lane, int tiles_per_img) {
+    // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4; two warps per quarter =====
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        float* ebuf = reinterpret_cast<float*>(epi_smem + (size_t)ew * 4096);
+        const dkt_epilogue& e = prm.epi;
+        const int N = prm.N;
+        const int sub = lane >> 3;           // pixel within a group of 4
+        const int jg = lane & 7;             // 16-byte channel group within the 32-column chunk
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
+            const int b = tile / tiles_per_img;
+            const int r = tile - b * tiles_per_img;
+            const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
+            const uint32_t as = t & 1u, aphase = (t >> 1) & 1u;
+            mbar_wait(&tmem_full_bar[as], aphase);
+            tcgen05_fence_after();
+            const uint32_t tbase = tmem_base + as * prm.acc_cols + ((uint32_t)(q * 32) << 16);
+            for (int c0 = half * 32; c0 < prm.Npad; c0 += 64) {
+                float v[32];
+                const int ncols = (prm.Npad - c0 >= 32) ? 32 : 16;
+                __syncwarp();                       // tcgen05.ld is .sync.aligned; also: previous chunk's reads done
+                if (ncols == 32) {
+                    tmem_ld32(tbase + c0, v);
+                } else {
+                    tmem_ld16(tbase + c0, v);
+#pragma unroll
+                    for (int j = 16; j < 32; ++j) v[j] = 0.f;
+                }
+                tmem_ld_wait();
+                // thread = pixel `lane`: row of 8 x 16 B, chunk j stored at j ^ (lane & 7)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(ebuf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                const int n = c0 + 4 * jg;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = i * 4 + sub;                        // pixel of this warp's quarter
+                    const float4 a = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
+                    const int m = q * 32 + row;
+                    const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
+                    if (y < prm.H && x < prm.W && n < N) {
+                        const int64_t p = ((int64_t)b * prm.H + y) * prm.W + x;
+                        if (n + 3 < N) {
+                            tc_epilogue4(e, N, p, n, a);
+                        } else {
+                            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) if (n + u < N) tc_epilogue1(e, p, n + u, av[u]);
+                        }
+                    }
+                }
+            }
+            if (e.tail && half == 0) {
+                const int m = q * 32 + lane;
+                const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
+                if (y < prm.H && x < prm.W) {
+                    const int64_t p = ((int64_t)b * prm.H + y) * prm.W + x;
+                    for (int u = 0; u < e.tail_C; ++u) store_all(e.out, p, N + u, __ldg(e.tail + p * e.tail_C + u));
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        }
 }
 
 template <int BK>
@@ -225,73 +301,159 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
             }
         }
     } else {
-        // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4; two warps per quarter =====
-        const int ew = warp - 2;
-        const int q = warp & 3;
-        const int half = ew >> 2;
-        float* ebuf = reinterpret_cast<float*>(epi_smem + (size_t)ew * 4096);
-        const dkt_epilogue& e = prm.epi;
-        const int N = prm.N;
-        const int sub = lane >> 3;           // pixel within a group of 4
-        const int jg = lane & 7;             // 16-byte channel group within the 32-column chunk
-        uint32_t t = 0;
-        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
-            const int b = tile / tiles_per_img;
-            const int r = tile - b * tiles_per_img;
-            const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
-            const uint32_t as = t & 1u, aphase = (t >> 1) & 1u;
-            mbar_wait(&tmem_full_bar[as], aphase);
-            tcgen05_fence_after();
-            const uint32_t tbase = tmem_base + as * prm.acc_cols + ((uint32_t)(q * 32) << 16);
-            for (int c0 = half * 32; c0 < prm.Npad; c0 += 64) {
-                float v[32];
-                const int ncols = (prm.Npad - c0 >= 32) ? 32 : 16;
-                __syncwarp();                       // tcgen05.ld is .sync.aligned; also: previous chunk's reads done
-                if (ncols == 32) {
-                    tmem_ld32(tbase + c0, v);
-                } else {
-                    tmem_ld16(tbase + c0, v);
-#pragma unroll
-                    for (int j = 16; j < 32; ++j) v[j] = 0.f;
-                }
-                tmem_ld_wait();
-                // thread = pixel `lane`: row of 8 x 16 B, chunk j stored at j ^ (lane & 7)
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(ebuf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                __syncwarp();
-                const int n = c0 + 4 * jg;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = i * 4 + sub;                        // pixel of this warp's quarter
-                    const float4 a = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
-                    const int m = q * 32 + row;
-                    const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
-                    if (y < prm.H && x < prm.W && n < N) {
-                        const int64_t p = ((int64_t)b * prm.H + y) * prm.W + x;
-                        if (n + 3 < N) {
-                            tc_epilogue4(e, N, p, n, a);
-                        } else {
-                            const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) if (n + u < N) tc_epilogue1(e, p, n + u, av[u]);
+        conv_tc_epilogue_warps(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img);
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * prm.acc_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// v3 ("row patch"): same roles and epilogue as conv_tc_kernel, but the A operand of the `ygroup`
+// vertical taps (ky) of a filter column kx comes from ONE TMA box of TILE_H + ygroup - 1 rows:
+// with the 8 x 16 pixel tile, M row m = (my, mx) sits at byte (my*16 + mx) * 128 of the box, so tap ky
+// is the same box read from byte offset ky * 2048 -- a 1024-byte-aligned start address, i.e. a
+// standard SWIZZLE_128B K-major descriptor (no re-staging, no im2col).  A 3x3 conv thus pulls 3
+// patches of 10 rows per 64-channel block instead of 9 tiles of 8 rows (2.4x less activation traffic
+// from L2, which is what bounds these kernels: see DESIGN.md "K3 roofline"); the 7x1 stem pulls 1
+// patch of 14 rows instead of 7 tiles.  Weights stream through their own ring in K blocks of WK
+// channels (32 when N > 128 so that three stages fit).  Strided convs use ygroup = 1 (plain tiles).
+// ---------------------------------------------------------------------------------------------
+constexpr int TCP_MAX_A = 4, TCP_MAX_W = 8;
+
+template <int WK>
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
+    constexpr uint32_t WROW = WK * 2;
+    constexpr int WSPLIT = 64 / WK;                   // W steps per 64-channel A block
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    const uint32_t a_part = prm.a_part_bytes, a_stage_bytes = 2u * prm.a_part_bytes;
+    const uint32_t b_bytes = (uint32_t)prm.Npad * WROW, w_stage_bytes = 2u * b_bytes;
+    uint8_t* a_ring = smem;
+    uint8_t* w_ring = a_ring + (size_t)prm.a_stages * a_stage_bytes;
+    uint8_t* epi_smem = w_ring + (size_t)prm.w_stages * w_stage_bytes;
+    uint64_t* afull = reinterpret_cast<uint64_t*>(epi_smem + TC2_EPI_BYTES);
+    uint64_t* aempty = afull + TCP_MAX_A;
+    uint64_t* wfull = aempty + TCP_MAX_A;
+    uint64_t* wempty = wfull + TCP_MAX_W;
+    uint64_t* tmem_full_bar = wempty + TCP_MAX_W;            // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ygroups = prm.kh / prm.ygroup;                 // A steps per (kb, kx)
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < prm.nsrc; ++s) { tma_prefetch_desc(&prm.act[s][0]); tma_prefetch_desc(&prm.act[s][1]); }
+        tma_prefetch_desc(&prm.wgt[0]);
+        tma_prefetch_desc(&prm.wgt[1]);
+        for (int s = 0; s < prm.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < prm.w_stages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], TC2_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * prm.acc_cols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles_per_img = prm.tiles_x * prm.tiles_y;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer: A patches and W tiles in the order the MMA warp consumes them =====
+            int as = 0, ws = 0;
+            uint32_t aph = 0, wph = 0;
+            for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+                const int b = tile / tiles_per_img;
+                const int r = tile - b * tiles_per_img;
+                const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
+                int kofs = 0;
+                for (int s = 0; s < prm.nsrc; ++s) {
+                    for (int kb = 0; kb < prm.kblocks[s]; ++kb) {
+                        const int c = prm.c_begin[s] + kb * 64;
+                        for (int kx = 0; kx < prm.kw; ++kx) {
+                            const int xs = x0 * prm.stride + kx - prm.pad_x;
+                            for (int yg = 0; yg < ygroups; ++yg) {
+                                const int ys = y0 * prm.stride + yg * prm.ygroup - prm.pad_y;
+                                mbar_wait(&aempty[as], aph ^ 1u);
+                                uint8_t* ast = a_ring + (size_t)as * a_stage_bytes;
+                                mbar_arrive_expect_tx(&afull[as], a_stage_bytes);
+                                tma_load_4d(ast, &prm.act[s][0], &afull[as], c, xs, ys, b);
+                                tma_load_4d(ast + a_part, &prm.act[s][1], &afull[as], c, xs, ys, b);
+                                if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
+                                for (int kyi = 0; kyi < prm.ygroup; ++kyi) {
+                                    const int tap = (yg * prm.ygroup + kyi) * prm.kw + kx;
+                                    for (int wh = 0; wh < WSPLIT; ++wh) {
+                                        mbar_wait(&wempty[ws], wph ^ 1u);
+                                        uint8_t* wst = w_ring + (size_t)ws * w_stage_bytes;
+                                        mbar_arrive_expect_tx(&wfull[ws], w_stage_bytes);
+                                        const int kc = kofs + kb * 64 + wh * WK;
+                                        tma_load_2d(wst, &prm.wgt[0], &wfull[ws], kc, tap * prm.Npad);
+                                        tma_load_2d(wst + b_bytes, &prm.wgt[1], &wfull[ws], kc, tap * prm.Npad);
+                                        if (++ws == prm.w_stages) { ws = 0; wph ^= 1u; }
+                                    }
+                                }
+                            }
                         }
                     }
+                    kofs += prm.kblocks[s] * 64;
                 }
             }
-            if (e.tail && half == 0) {
-                const int m = q * 32 + lane;
-                const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
-                if (y < prm.H && x < prm.W) {
-                    const int64_t p = ((int64_t)b * prm.H + y) * prm.W + x;
-                    for (int u = 0; u < e.tail_C; ++u) store_all(e.out, p, N + u, __ldg(e.tail + p * e.tail_C + u));
-                }
-            }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
         }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = idesc_bf16_m128((uint32_t)prm.Npad);
+            int as = 0, ws = 0;
+            uint32_t aph = 0, wph = 0, t = 0;
+            int kb_total = 0;
+            for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
+            const int a_steps = kb_total * prm.kw * ygroups;
+            for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
+                const uint32_t acs = t & 1u, aphase = (t >> 1) & 1u;
+                mbar_wait(&tmem_empty_bar[acs], aphase ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acs * prm.acc_cols;
+                uint32_t accumulate = 0;
+                for (int ai = 0; ai < a_steps; ++ai) {
+                    mbar_wait(&afull[as], aph);
+                    tcgen05_fence_after();
+                    const uint32_t a_hi0 = smem_u32(a_ring + (size_t)as * a_stage_bytes);
+                    for (int kyi = 0; kyi < prm.ygroup; ++kyi) {
+                        const uint32_t a_hi = a_hi0 + (uint32_t)kyi * (TC_TILE_W * 128u);
+                        const uint32_t a_lo = a_hi + a_part;
+#pragma unroll
+                        for (int wh = 0; wh < WSPLIT; ++wh) {
+                            mbar_wait(&wfull[ws], wph);
+                            tcgen05_fence_after();
+                            const uint32_t w_hi = smem_u32(w_ring + (size_t)ws * w_stage_bytes);
+                            const uint32_t w_lo = w_hi + b_bytes;
+#pragma unroll
+                            for (int k = 0; k < WK / 16; ++k) {
+                                const uint32_t ak = (uint32_t)(wh * WK * 2 + k * 32);
+                                const uint64_t dah = smem_desc_kmajor<64>(a_hi + ak), dal = smem_desc_kmajor<64>(a_lo + ak);
+                                const uint64_t dwh = smem_desc_kmajor<WK>(w_hi + k * 32), dwl = smem_desc_kmajor<WK>(w_lo + k * 32);
+                                umma_bf16(tmem_d, dah, dwh, idesc, accumulate);
+                                umma_bf16(tmem_d, dal, dwh, idesc, 1u);
+                                umma_bf16(tmem_d, dah, dwl, idesc, 1u);
+                                accumulate = 1u;
+                            }
+                            umma_commit(&wempty[ws]);
+                            if (++ws == prm.w_stages) { ws = 0; wph ^= 1u; }
+                        }
+                    }
+                    umma_commit(&aempty[as]);                 // patch reusable once every tap's MMAs retire
+                    if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
+                }
+                umma_commit(&tmem_full_bar[acs]);
+            }
+        }
+    } else {
+        conv_tc_epilogue_warps(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img);
     }
 
     tcgen05_fence_before();
@@ -332,8 +494,10 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     if (e.bias && !aligned16(e.bias)) return DKT_E_ALIGNMENT;
     if (!aligned16(e.out.f32) || !aligned16(e.out.hi) || !aligned16(e.out.lo)) return DKT_E_ALIGNMENT;
 
-    // K block: 64 channels (SWIZZLE_128B) unless DKT_CONV_BK=32
+    // kernel choice: the row-patch kernel (default) or the per-tap kernel (DKT_CONV_PATCH=0; K block 64 unless
+    // DKT_CONV_BK=32)
     static const int s_bk_env = [] { const char* v = getenv("DKT_CONV_BK"); return v ? atoi(v) : 0; }();
+    static const int s_patch = [] { const char* v = getenv("DKT_CONV_PATCH"); return (v && v[0] == '0') ? 0 : 1; }();
     static const int s_sms = [] {
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
@@ -343,8 +507,32 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         return n;
     }();
     const int Npad = (N + 15) / 16 * 16;
-    // measured on B200 (gru08 z||r, N = 256): 2 stages x BK 64 = 0.957 ms, 4 stages x BK 32 = 0.980 ms
-    const int BK = (s_bk_env == 32) ? 32 : 64;
+    const uint32_t budget = 227u * 1024u - 1024u /*align*/ - TC2_EPI_BYTES - 256u /*barriers*/;
+
+    // ring geometry of the row-patch kernel
+    const int ygroup = (stride == 1) ? kh : 1;
+    const int rows_loaded = (stride == 1) ? TC_TILE_H + ygroup - 1 : TC_TILE_H;
+    const uint32_t a_part_bytes = (uint32_t)rows_loaded * TC_TILE_W * 128u;
+    const int WK = (Npad > 128) ? 32 : 64;
+    const uint32_t w_stage_bytes = 2u * (uint32_t)Npad * (uint32_t)WK * 2u;
+    int a_stages = 2, w_stages = 0;
+    bool use_patch = s_patch != 0;
+    if (use_patch) {
+        if (2u * a_part_bytes * a_stages >= budget) use_patch = false;
+        else {
+            w_stages = (int)((budget - 2u * a_part_bytes * a_stages) / w_stage_bytes);
+            if (w_stages > TCP_MAX_W) w_stages = TCP_MAX_W;
+            if (w_stages < 2) use_patch = false;
+            else if (w_stages >= 5 && 2u * a_part_bytes * 3 + 4u * w_stage_bytes <= budget) {
+                a_stages = 3;
+                w_stages = (int)((budget - 2u * a_part_bytes * 3) / w_stage_bytes);
+                if (w_stages > TCP_MAX_W) w_stages = TCP_MAX_W;
+            }
+        }
+    }
+    // measured on B200 (gru08 z||r, N = 256, per-tap kernel): 2 stages x BK 64 = 0.957 ms, 4 stages x BK 32 = 0.980 ms
+    const int BK = use_patch ? 64 : ((s_bk_env == 32) ? 32 : 64);
+    const int WBK = use_patch ? WK : BK;          // K extent of a weight box
 
     TcConvParams prm{};
     prm.nsrc = nsrc;
@@ -359,7 +547,8 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         cin_total += t.c_count;
         const uint64_t dims[4] = {(uint64_t)t.C, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
         const uint64_t strides[4] = {1, (uint64_t)t.C, (uint64_t)t.C * Win, (uint64_t)t.C * Win * Hin};
-        const uint32_t box[4] = {(uint32_t)BK, (uint32_t)(TC_TILE_W * stride), (uint32_t)(TC_TILE_H * stride), 1};
+        const uint32_t box_rows = use_patch ? (uint32_t)(stride == 1 ? rows_loaded : TC_TILE_H * stride) : (uint32_t)(TC_TILE_H * stride);
+        const uint32_t box[4] = {(uint32_t)BK, (uint32_t)(TC_TILE_W * stride), box_rows, 1};
         const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
         if (!make_tmap_bf16(&prm.act[s][0], t.hi, 4, dims, strides, box, BK * 2, estr)) return DKT_E_DRIVER;
         if (!make_tmap_bf16(&prm.act[s][1], t.lo, 4, dims, strides, box, BK * 2, estr)) return DKT_E_DRIVER;
@@ -371,10 +560,10 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     {
         const uint64_t dims[2] = {(uint64_t)cin_total, (uint64_t)prm.taps * prm.Npad};
         const uint64_t strides[2] = {1, (uint64_t)cin_total};
-        const uint32_t box[2] = {(uint32_t)BK, (uint32_t)prm.Npad};
+        const uint32_t box[2] = {(uint32_t)WBK, (uint32_t)prm.Npad};
         if (!aligned16(w_hi) || !aligned16(w_lo)) return DKT_E_ALIGNMENT;
-        if (!make_tmap_bf16(&prm.wgt[0], w_hi, 2, dims, strides, box, BK * 2)) return DKT_E_DRIVER;
-        if (!make_tmap_bf16(&prm.wgt[1], w_lo, 2, dims, strides, box, BK * 2)) return DKT_E_DRIVER;
+        if (!make_tmap_bf16(&prm.wgt[0], w_hi, 2, dims, strides, box, WBK * 2)) return DKT_E_DRIVER;
+        if (!make_tmap_bf16(&prm.wgt[1], w_lo, 2, dims, strides, box, WBK * 2)) return DKT_E_DRIVER;
     }
     prm.H = H;
     prm.W = W;
@@ -388,23 +577,36 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     prm.tmem_cols = cols;
     prm.acc_cols = cols;
     prm.epi = e;
-    const uint32_t stage_bytes = 2u * 128u * (uint32_t)BK * 2u + 2u * (uint32_t)prm.Npad * (uint32_t)BK * 2u;
 
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_patch_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_patch_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce != cudaSuccess) return (int)ce;
         attr_set = true;
     }
-    // the ring takes what the epilogue buffers and barriers leave of the 227 KB
-    const uint32_t budget = 227u * 1024u - 1024u /*align*/ - TC2_EPI_BYTES - 256u /*barriers*/;
+    const unsigned grid = (unsigned)(tiles < s_sms ? tiles : s_sms);
+    if (use_patch) {
+        prm.ygroup = ygroup;
+        prm.a_stages = a_stages;
+        prm.w_stages = w_stages;
+        prm.a_part_bytes = a_part_bytes;
+        const size_t smem_bytes = (size_t)a_stages * 2 * a_part_bytes + (size_t)w_stages * w_stage_bytes + TC2_EPI_BYTES + 1024 + 256;
+        if (WK == 32)
+            conv_tc_patch_kernel<32><<<grid, TC2_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
+        else
+            conv_tc_patch_kernel<64><<<grid, TC2_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
+        DKT_RETURN_LAST();
+    }
+    // per-tap kernel: the ring takes what the epilogue buffers and barriers leave of the 227 KB
+    const uint32_t stage_bytes = 2u * 128u * (uint32_t)BK * 2u + 2u * (uint32_t)prm.Npad * (uint32_t)BK * 2u;
     int stages = (int)(budget / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) return DKT_E_UNSUPPORTED;
     prm.stages = stages;
     const size_t smem_bytes = (size_t)stages * stage_bytes + TC2_EPI_BYTES + 1024 + 256;
-    const unsigned grid = (unsigned)(tiles < s_sms ? tiles : s_sms);
     if (BK == 32)
         conv_tc_kernel<32><<<grid, TC2_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
     else
