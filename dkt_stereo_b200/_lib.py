@@ -28,11 +28,13 @@ class DktEpilogue(C.Structure):
                 ("bias", C.c_void_p), ("ctx", C.c_void_p), ("ctx_C", C.c_int32), ("ctx_c0", C.c_int32),
                 ("out", DktTensor), ("z", DktTensor), ("h", DktTensor),
                 ("tail", C.c_void_p), ("tail_C", C.c_int32),
-                ("res", C.c_void_p), ("res_C", C.c_int32), ("res_c0", C.c_int32)]
+                ("res", C.c_void_p), ("res_C", C.c_int32), ("res_c0", C.c_int32),
+                ("proj", C.c_void_p)]
 
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
-EPI_LINEAR, EPI_GRU_ZR, EPI_GRU_Q = 0, 1, 2
+EPI_LINEAR, EPI_GRU_ZR, EPI_GRU_Q, EPI_PROJ = 0, 1, 2, 3
+PROJ_LD = 12
 MAX_LEVELS = 4
 
 _I, _I64, _F, _P = C.c_int, C.c_int64, C.c_float, C.c_void_p

@@ -24,13 +24,12 @@ __device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) 
     lo = __bfloat16_as_ushort(l);
 }
 
-// pack two consecutive channels
+// pack two consecutive channels (one packed F2FP conversion per pair instead of two F2F)
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    uint16_t ah, al, bh, bl;
-    split_bf16(a, ah, al);
-    split_bf16(b, bh, bl);
-    hi = (uint32_t)ah | ((uint32_t)bh << 16);
-    lo = (uint32_t)al | ((uint32_t)bl << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // .x = a (low half), .y = b
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __low2float(h), b - __high2float(h));
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // ---- activations.  expf / tanhf (not the __ intrinsics): the recurrence is sensitive ----

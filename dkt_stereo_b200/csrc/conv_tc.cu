@@ -12,7 +12,7 @@
 // Precision: activations and weights are bf16 (hi, lo) pairs; each K step issues
 // hi*hi + lo*hi + hi*lo into the same fp32 TMEM accumulator (3-term split, ~16 mantissa bits).
 //
-// conv_tc_kernel<BK> (v2, default) is PERSISTENT: grid = min(tiles, #SMs), each CTA walks tiles
+// conv_tc_kernel<BK, KIND, ACT> (v2) is PERSISTENT: grid = min(tiles, #SMs), each CTA walks tiles
 // blockIdx.x, +gridDim.x, ...  Three pipelines run concurrently inside a CTA:
 //   warp 0      TMA producer      smem ring of (A hi, A lo, W hi, W lo) stages, full/empty mbarriers
 //   warp 1      MMA issuer        two TMEM accumulator stages (2 x Npad columns), tmem_full/empty
@@ -22,8 +22,8 @@
 // continues with lanes = 8 x 16-byte channel groups of 4 pixels, so every global access of the
 // fused epilogue (context term, h, z, fp32 / bf16 hi / bf16 lo stores) is a full 128-byte line.
 // The two warps that share a lane quarter take alternate column chunks.
-// BK = K block in channels: 64 (SWIZZLE_128B rows, default) or 32 (SWIZZLE_64B rows, twice the
-// stages at N = 256; measured 2 % slower, kept selectable with DKT_CONV_BK=32).
+// BK = K block in channels = 64 (SWIZZLE_128B rows).  Every kernel is instantiated per epilogue kind and
+// activation (KIND, ACT): the epilogue loop is straight-line code for exactly one fused tail.
 //
 // Strided convolutions (the encoders' stride-2 layers) use the same kernel: the TMA tensor map is
 // built with elementStrides = stride on the W/H dimensions, so the box {BK, 16*s, 8*s, 1} starting
@@ -61,48 +61,21 @@ struct TcConvParams {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// one group of 4 consecutive output channels of one pixel
-__device__ __forceinline__ void tc_epilogue4(const dkt_epilogue& e, int N, int64_t p, int n, float4 a) {
-    if (e.kind == DKT_EPI_LINEAR) {
-        if (e.bias) { float4 b = ld4(e.bias + n); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
-        if (e.ctx) { float4 c = ld4(e.ctx + p * e.ctx_C + e.ctx_c0 + n); a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; }
-        a.x = apply_act(a.x, e.act) * e.scale; a.y = apply_act(a.y, e.act) * e.scale;
-        a.z = apply_act(a.z, e.act) * e.scale; a.w = apply_act(a.w, e.act) * e.scale;
-        if (e.res) {       // residual block tail: relu(x + y)
-            float4 r = ld4(e.res + p * e.res_C + e.res_c0 + n);
-            a.x = fmaxf(a.x + r.x, 0.f); a.y = fmaxf(a.y + r.y, 0.f); a.z = fmaxf(a.z + r.z, 0.f); a.w = fmaxf(a.w + r.w, 0.f);
-        }
-        store_all4(e.out, p, n, a);
-    } else if (e.kind == DKT_EPI_GRU_ZR) {
-        const int Nh = N >> 1;
-        float4 c = ld4(e.ctx + p * e.ctx_C + e.ctx_c0 + n);
-        float4 s = make_float4(sigmoidf_acc(a.x + c.x), sigmoidf_acc(a.y + c.y),
-                               sigmoidf_acc(a.z + c.z), sigmoidf_acc(a.w + c.w));
-        if (n < Nh) {
-            *reinterpret_cast<float4*>(e.z.f32 + p * e.z.C + e.z.c_begin + n) = s;
-        } else {
-            const int ch = n - Nh;
-            float4 h = ld4(e.h.f32 + p * e.h.C + e.h.c_begin + ch);
-            store_all4(e.out, p, ch, make_float4(s.x * h.x, s.y * h.y, s.z * h.z, s.w * h.w));
-        }
-    } else {
-        float4 c = ld4(e.ctx + p * e.ctx_C + e.ctx_c0 + n);
-        float4 z = ld4(e.z.f32 + p * e.z.C + e.z.c_begin + n);
-        float4 h = ld4(e.h.f32 + p * e.h.C + e.h.c_begin + n);
-        float4 o;
-        o.x = (1.f - z.x) * h.x + z.x * tanhf(a.x + c.x);
-        o.y = (1.f - z.y) * h.y + z.y * tanhf(a.y + c.y);
-        o.z = (1.f - z.z) * h.z + z.z * tanhf(a.z + c.z);
-        o.w = (1.f - z.w) * h.w + z.w * tanhf(a.w + c.w);
-        store_all4(e.out, p, n, o);
-    }
+// compile-time activation (the runtime switch of apply_act gets if-converted into ~50 issued instructions per value)
+template <int ACT>
+__device__ __forceinline__ float act_ct(float x) {
+    if constexpr (ACT == DKT_ACT_RELU) return fmaxf(x, 0.0f);
+    else if constexpr (ACT == DKT_ACT_SIGMOID) return sigmoidf_acc(x);
+    else if constexpr (ACT == DKT_ACT_TANH) return tanhf(x);
+    else return x;
 }
 
-// scalar tail of a partially valid 4-group (only LINEAR convs have N % 4 != 0)
-__device__ __forceinline__ void tc_epilogue1(const dkt_epilogue& e, int64_t p, int n, float a) {
+// scalar path of a partially valid 4-group of a LINEAR conv whose N is not a multiple of 4 (rare shapes only)
+template <int ACT>
+__device__ __noinline__ void tc_epilogue1(const dkt_epilogue& e, int64_t p, int n, float a) {
     if (e.bias) a += e.bias[n];
     if (e.ctx) a += e.ctx[p * e.ctx_C + e.ctx_c0 + n];
-    a = apply_act(a, e.act) * e.scale;
+    a = act_ct<ACT>(a) * e.scale;
     if (e.res) a = fmaxf(a + e.res[p * e.res_C + e.res_c0 + n], 0.f);
     store_all(e.out, p, n, a);
 }
@@ -126,80 +99,259 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr) {
     return d;
 }
 
-// epilogue warps 2..9 of both persistent kernels (see the header comment of this file)
+// Epilogue warps 2..9 of both persistent kernels (see the header comment of this file), specialised at compile
+// time on the epilogue kind and activation: the instruction count of this loop, not the tensor pipe, bounded every
+// conv while it was generic (ncu r01f: ~8000 issued warp instructions per 32 x 32 chunk; now a few hundred).
+// TMEM lane quarter = warp % 4; the two warps of a quarter take alternate 32-column chunks.  Per chunk a warp
+// pulls 32 columns with tcgen05.ld (thread = pixel), transposes through a swizzled 4 KB smem buffer and continues
+// with lanes = 8 x 16-byte channel groups of 4 pixels, so every global access is a full 128-byte line.
+template <int KIND, int ACT>
 __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, uint32_t tmem_base,
                                                        uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
                                                        uint8_t* epi_smem, int warp, int lane, int tiles_per_img) {
-    // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4; two warps per quarter =====
-        const int ew = warp - 2;
-        const int q = warp & 3;
-        const int half = ew >> 2;
-        float* ebuf = reinterpret_cast<float*>(epi_smem + (size_t)ew * 4096);
-        const dkt_epilogue& e = prm.epi;
-        const int N = prm.N;
-        const int sub = lane >> 3;           // pixel within a group of 4
-        const int jg = lane & 7;             // 16-byte channel group within the 32-column chunk
-        uint32_t t = 0;
-        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
-            const int b = tile / tiles_per_img;
-            const int r = tile - b * tiles_per_img;
-            const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
-            const uint32_t as = t & 1u, aphase = (t >> 1) & 1u;
-            mbar_wait(&tmem_full_bar[as], aphase);
-            tcgen05_fence_after();
-            const uint32_t tbase = tmem_base + as * prm.acc_cols + ((uint32_t)(q * 32) << 16);
-            for (int c0 = half * 32; c0 < prm.Npad; c0 += 64) {
-                float v[32];
-                const int ncols = (prm.Npad - c0 >= 32) ? 32 : 16;
-                __syncwarp();                       // tcgen05.ld is .sync.aligned; also: previous chunk's reads done
-                if (ncols == 32) {
-                    tmem_ld32(tbase + c0, v);
-                } else {
-                    tmem_ld16(tbase + c0, v);
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    float* ebuf = reinterpret_cast<float*>(epi_smem + (size_t)ew * 4096);
+    const dkt_epilogue& e = prm.epi;
+    const int N = prm.N, H = prm.H, W = prm.W;
+    const int sub = lane >> 3;           // pixel within a group of 4
+    const int jg = lane & 7;             // 16-byte channel group within the 32-column chunk
+    // loop-invariant epilogue parameters
+    const float* const bias = e.bias;
+    const float* const ctx = e.ctx;
+    const float* const res = (KIND == DKT_EPI_LINEAR) ? e.res : nullptr;
+    const float* const tail = (KIND == DKT_EPI_LINEAR) ? e.tail : nullptr;
+    const int tail_C = e.tail_C;
+    const float scale = e.scale;
+    float* const o_f32 = e.out.f32;
+    uint16_t* const o_hi = e.out.hi;
+    uint16_t* const o_lo = e.out.lo;
+    const int oC = e.out.C, oc0 = e.out.c_begin;
+    const int Nh = N >> 1;
+    // a tail (e.g. the flow field appended to the motion features) that completes the last 4-group of an
+    // N % 4 != 0 conv is merged into that group's vector store; otherwise it is copied after the chunk loop
+    const bool tail_merged = tail && (N & 3) && (((N + tail_C) & 3) == 0) && tail_C < 4;
+    const int Nvec = tail_merged ? N + tail_C : N;
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
+        const int b = tile / tiles_per_img;
+        const int r = tile - b * tiles_per_img;
+        const int ty = r / prm.tiles_x;
+        const int y0 = ty * TC_TILE_H, x0 = (r - ty * prm.tiles_x) * TC_TILE_W;
+        const uint32_t as = t & 1u, aphase = (t >> 1) & 1u;
+        // this lane's 8 pixels: row = i*4 + sub of the warp's quarter -> (y, x) = (y0 + 2q + (i>>2), x0 + (i&3)*4 + sub)
+        const int64_t p00 = ((int64_t)b * H + y0 + 2 * q) * W + x0 + sub;
+        const bool yok0 = (y0 + 2 * q) < H, yok1 = (y0 + 2 * q + 1) < H;
+        mbar_wait(&tmem_full_bar[as], aphase);
+        tcgen05_fence_after();
+        const uint32_t tbase = tmem_base + as * prm.acc_cols + ((uint32_t)(q * 32) << 16);
+        for (int c0 = half * 32; c0 < prm.Npad; c0 += 64) {
+            float v[32];
+            const int ncols = (prm.Npad - c0 >= 32) ? 32 : 16;
+            __syncwarp();                       // tcgen05.ld is .sync.aligned; also: previous chunk's reads done
+            if (ncols == 32) {
+                tmem_ld32(tbase + c0, v);
+            } else {
+                tmem_ld16(tbase + c0, v);
 #pragma unroll
-                    for (int j = 16; j < 32; ++j) v[j] = 0.f;
-                }
-                tmem_ld_wait();
-                // thread = pixel `lane`: row of 8 x 16 B, chunk j stored at j ^ (lane & 7)
+                for (int j = 16; j < 32; ++j) v[j] = 0.f;
+            }
+            tmem_ld_wait();
+            // thread = pixel `lane`: row of 8 x 16 B, chunk j stored at j ^ (lane & 7)
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(ebuf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                __syncwarp();
-                const int n = c0 + 4 * jg;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = i * 4 + sub;                        // pixel of this warp's quarter
-                    const float4 a = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
-                    const int m = q * 32 + row;
-                    const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
-                    if (y < prm.H && x < prm.W && n < N) {
-                        const int64_t p = ((int64_t)b * prm.H + y) * prm.W + x;
-                        if (n + 3 < N) {
-                            tc_epilogue4(e, N, p, n, a);
-                        } else {
-                            const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) if (n + u < N) tc_epilogue1(e, p, n + u, av[u]);
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(ebuf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            const int n = c0 + 4 * jg;
+            if (n >= Nvec) continue;            // padded columns (lane-divergent only in the last chunk)
+            const bool vec = (n + 3 < Nvec);
+            if (KIND != DKT_EPI_LINEAR || vec) {
+                // ---------------- vector path: 4 channels x 8 pixels per lane ----------------
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                int ntail = 0;                   // components of this group that come from the tail
+                if (KIND == DKT_EPI_LINEAR) {
+                    if (n + 3 < N) {
+                        if (bias) bv = ld4(bias + n);
+                    } else {                     // the merged-tail group
+                        ntail = n + 4 - N;
+                        if (bias) {
+                            bv.x = bias[n];
+                            if (n + 1 < N) bv.y = bias[n + 1];
+                            if (n + 2 < N) bv.z = bias[n + 2];
                         }
                     }
                 }
-            }
-            if (e.tail && half == 0) {
-                const int m = q * 32 + lane;
-                const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
-                if (y < prm.H && x < prm.W) {
-                    const int64_t p = ((int64_t)b * prm.H + y) * prm.W + x;
-                    for (int u = 0; u < e.tail_C; ++u) store_all(e.out, p, N + u, __ldg(e.tail + p * e.tail_C + u));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = i * 4 + sub;
+                    const int xo = (i & 3) * 4;
+                    if (!((i < 4 ? yok0 : yok1) && (x0 + xo + sub) < W)) continue;
+                    const int64_t p = p00 + xo + (i < 4 ? 0 : W);
+                    float4 a = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
+                    if (KIND == DKT_EPI_LINEAR) {
+                        a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
+                        if (ctx) { const float4 c = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n); a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; }
+                        a.x = act_ct<ACT>(a.x) * scale; a.y = act_ct<ACT>(a.y) * scale;
+                        a.z = act_ct<ACT>(a.z) * scale; a.w = act_ct<ACT>(a.w) * scale;
+                        if (res) {               // residual block tail: relu(x + y)
+                            const float4 rr = ld4(res + p * e.res_C + e.res_c0 + n);
+                            a.x = fmaxf(a.x + rr.x, 0.f); a.y = fmaxf(a.y + rr.y, 0.f);
+                            a.z = fmaxf(a.z + rr.z, 0.f); a.w = fmaxf(a.w + rr.w, 0.f);
+                        }
+                        if (ntail) {             // 1..3 trailing components are copied from the tail tensor
+                            const float* tp = tail + p * tail_C;
+                            if (ntail == 1) a.w = tp[0];
+                            else if (ntail == 2) { a.z = tp[0]; a.w = tp[1]; }
+                            else { a.y = tp[0]; a.z = tp[1]; a.w = tp[2]; }
+                        }
+                    } else if (KIND == DKT_EPI_GRU_ZR) {
+                        const float4 c = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n);
+                        a.x = sigmoidf_acc(a.x + c.x); a.y = sigmoidf_acc(a.y + c.y);
+                        a.z = sigmoidf_acc(a.z + c.z); a.w = sigmoidf_acc(a.w + c.w);
+                        if (n < Nh) {
+                            *reinterpret_cast<float4*>(e.z.f32 + p * e.z.C + e.z.c_begin + n) = a;
+                            continue;
+                        }
+                        const float4 h = ld4(e.h.f32 + p * e.h.C + e.h.c_begin + (n - Nh));
+                        a.x *= h.x; a.y *= h.y; a.z *= h.z; a.w *= h.w;
+                    } else {                     // GRU_Q
+                        const float4 c = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n);
+                        const float4 z = ld4(e.z.f32 + p * e.z.C + e.z.c_begin + n);
+                        const float4 h = ld4(e.h.f32 + p * e.h.C + e.h.c_begin + n);
+                        a.x = (1.f - z.x) * h.x + z.x * tanhf(a.x + c.x);
+                        a.y = (1.f - z.y) * h.y + z.y * tanhf(a.y + c.y);
+                        a.z = (1.f - z.z) * h.z + z.z * tanhf(a.z + c.z);
+                        a.w = (1.f - z.w) * h.w + z.w * tanhf(a.w + c.w);
+                    }
+                    const int64_t off = p * oC + oc0 + (KIND == DKT_EPI_GRU_ZR ? n - Nh : n);
+                    if (o_f32) *reinterpret_cast<float4*>(o_f32 + off) = a;
+                    if (o_hi) {
+                        uint32_t h0, l0, h1, l1;
+                        split_bf16x2(a.x, a.y, h0, l0);
+                        split_bf16x2(a.z, a.w, h1, l1);
+                        *reinterpret_cast<uint2*>(o_hi + off) = make_uint2(h0, h1);
+                        if (o_lo) *reinterpret_cast<uint2*>(o_lo + off) = make_uint2(l0, l1);
+                    }
+                }
+            } else {
+                // ---------------- scalar path: partially valid last group of a LINEAR conv ----------------
+                for (int i = 0; i < 8; ++i) {
+                    const int row = i * 4 + sub;
+                    const int xo = (i & 3) * 4;
+                    if (!((i < 4 ? yok0 : yok1) && (x0 + xo + sub) < W)) continue;
+                    const int64_t p = p00 + xo + (i < 4 ? 0 : W);
+                    const float4 a = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
+                    const float av[4] = {a.x, a.y, a.z, a.w};
+                    for (int u = 0; u < 4; ++u) if (n + u < N) tc_epilogue1<ACT>(e, p, n + u, av[u]);
                 }
             }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
         }
+        if (tail && !tail_merged && half == 0) {
+            const int m = q * 32 + lane;
+            const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
+            if (y < H && x < W) {
+                const int64_t p = ((int64_t)b * H + y) * W + x;
+                for (int u = 0; u < tail_C; ++u) store_all(e.out, p, N + u, __ldg(tail + p * tail_C + u));
+            }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+    }
 }
 
-template <int BK>
+// PROJ epilogue (DKT_EPI_PROJ): y = act(acc + bias) stays on chip; each pixel's N values are contracted with a
+// small fp32 matrix proj[N][12] (the 9 per-tap channel responses of the one-output 3x3 conv that follows) and only
+// those 12 floats per pixel are stored.  Layout: thread = pixel (its TMEM lane), the two warps of a lane quarter
+// take alternate 32-column chunks and meet through shared memory (double-buffered by tile parity) on a
+// 64-thread named barrier.
+constexpr int PROJ_T = 9;
+template <int ACT>
+__device__ __forceinline__ void conv_tc_epilogue_proj(const TcConvParams& prm, uint32_t tmem_base,
+                                                      uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
+                                                      uint8_t* epi_smem, int warp, int lane, int tiles_per_img) {
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    float* s_w = reinterpret_cast<float*>(epi_smem);            // [256][12]
+    float* s_b = s_w + 256 * DKT_PROJ_LD;                        // [256]
+    float* s_x = s_b + 256;                                      // [2][128][12]
+    const dkt_epilogue& e = prm.epi;
+    const int N = prm.N;
+    const float scale = e.scale;
+    const int et = (int)threadIdx.x - 64;
+    for (int i = et; i < 256 * DKT_PROJ_LD; i += TC2_EPI_WARPS * 32) s_w[i] = (i < N * DKT_PROJ_LD) ? __ldg(e.proj + i) : 0.f;
+    for (int i = et; i < 256; i += TC2_EPI_WARPS * 32) s_b[i] = (i < N && e.bias) ? __ldg(e.bias + i) : 0.f;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
+        const int b = tile / tiles_per_img;
+        const int r = tile - b * tiles_per_img;
+        const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
+        const uint32_t as = t & 1u, aphase = (t >> 1) & 1u;
+        mbar_wait(&tmem_full_bar[as], aphase);
+        tcgen05_fence_after();
+        const uint32_t tbase = tmem_base + as * prm.acc_cols + ((uint32_t)(q * 32) << 16);
+        float acc[PROJ_T];
+#pragma unroll
+        for (int u = 0; u < PROJ_T; ++u) acc[u] = 0.f;
+        for (int c0 = half * 32; c0 < prm.Npad; c0 += 64) {
+            float v[32];
+            const int ncols = (prm.Npad - c0 >= 32) ? 32 : 16;
+            __syncwarp();
+            if (ncols == 32) {
+                tmem_ld32(tbase + c0, v);
+            } else {
+                tmem_ld16(tbase + c0, v);
+#pragma unroll
+                for (int j = 16; j < 32; ++j) v[j] = 0.f;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = c0 + j;                               // < 256: rows >= N of s_w are zero
+                const float y = act_ct<ACT>(v[j] + s_b[n]) * scale;
+                const float4 w0 = *reinterpret_cast<const float4*>(s_w + n * DKT_PROJ_LD);
+                const float4 w1 = *reinterpret_cast<const float4*>(s_w + n * DKT_PROJ_LD + 4);
+                const float w2 = s_w[n * DKT_PROJ_LD + 8];
+                acc[0] = fmaf(y, w0.x, acc[0]); acc[1] = fmaf(y, w0.y, acc[1]);
+                acc[2] = fmaf(y, w0.z, acc[2]); acc[3] = fmaf(y, w0.w, acc[3]);
+                acc[4] = fmaf(y, w1.x, acc[4]); acc[5] = fmaf(y, w1.y, acc[5]);
+                acc[6] = fmaf(y, w1.z, acc[6]); acc[7] = fmaf(y, w1.w, acc[7]);
+                acc[8] = fmaf(y, w2, acc[8]);
+            }
+        }
+        // accumulator drained: hand it back to the MMA warp before the (slow) exchange + store
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        float* xb = s_x + ((t & 1u) * 128 + q * 32 + lane) * DKT_PROJ_LD;
+        if (half == 1) {
+            *reinterpret_cast<float4*>(xb) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(xb + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            xb[8] = acc[8];
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        if (half == 0) {
+            const float4 o0 = *reinterpret_cast<const float4*>(xb);
+            const float4 o1 = *reinterpret_cast<const float4*>(xb + 4);
+            const float o2 = xb[8];
+            const int m = q * 32 + lane;
+            const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
+            if (y < prm.H && x < prm.W) {
+                const int64_t p = ((int64_t)b * prm.H + y) * prm.W + x;
+                float* dst = e.out.f32 + p * e.out.C + e.out.c_begin;
+                *reinterpret_cast<float4*>(dst) = make_float4(acc[0] + o0.x, acc[1] + o0.y, acc[2] + o0.z, acc[3] + o0.w);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4] + o1.x, acc[5] + o1.y, acc[6] + o1.z, acc[7] + o1.w);
+                *reinterpret_cast<float4*>(dst + 8) = make_float4(acc[8] + o2, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+}
+
+template <int BK, int KIND, int ACT>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
     constexpr uint32_t ROW = BK * 2;
@@ -301,7 +453,10 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
             }
         }
     } else {
-        conv_tc_epilogue_warps(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img);
+        if constexpr (KIND == DKT_EPI_PROJ)
+            conv_tc_epilogue_proj<ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img);
+        else
+            conv_tc_epilogue_warps<KIND, ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img);
     }
 
     tcgen05_fence_before();
@@ -322,7 +477,7 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
 // ---------------------------------------------------------------------------------------------
 constexpr int TCP_MAX_A = 4, TCP_MAX_W = 8;
 
-template <int WK>
+template <int WK, int KIND, int ACT>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
     constexpr uint32_t WROW = WK * 2;
@@ -453,7 +608,10 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
             }
         }
     } else {
-        conv_tc_epilogue_warps(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img);
+        if constexpr (KIND == DKT_EPI_PROJ)
+            conv_tc_epilogue_proj<ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img);
+        else
+            conv_tc_epilogue_warps<KIND, ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img);
     }
 
     tcgen05_fence_before();
@@ -466,6 +624,45 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
 using namespace dkt;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---- launch: one instantiation per (kernel family, epilogue kind, activation) ----
+enum ConvFamily { FAM_PATCH32, FAM_PATCH64, FAM_TAP64 };
+
+template <int KIND, int ACT>
+static int launch_conv_ka(ConvFamily fam, const TcConvParams& prm, unsigned grid, size_t smem_bytes, cudaStream_t st) {
+    static bool attr_set = false;                    // per instantiation
+    if (!attr_set) {
+        cudaError_t ce = cudaFuncSetAttribute(conv_tc_patch_kernel<32, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_patch_kernel<64, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<64, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce != cudaSuccess) return (int)ce;
+        attr_set = true;
+    }
+    switch (fam) {
+        case FAM_PATCH32: conv_tc_patch_kernel<32, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
+        case FAM_PATCH64: conv_tc_patch_kernel<64, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
+        default:          conv_tc_kernel<64, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
+    }
+    DKT_RETURN_LAST();
+}
+
+static int launch_conv(ConvFamily fam, const TcConvParams& prm, unsigned grid, size_t smem_bytes, cudaStream_t st) {
+    const int kind = prm.epi.kind, act = prm.epi.act;
+    if (kind == DKT_EPI_GRU_ZR) return launch_conv_ka<DKT_EPI_GRU_ZR, DKT_ACT_NONE>(fam, prm, grid, smem_bytes, st);
+    if (kind == DKT_EPI_GRU_Q) return launch_conv_ka<DKT_EPI_GRU_Q, DKT_ACT_NONE>(fam, prm, grid, smem_bytes, st);
+    if (kind == DKT_EPI_PROJ) {
+        if (act == DKT_ACT_RELU) return launch_conv_ka<DKT_EPI_PROJ, DKT_ACT_RELU>(fam, prm, grid, smem_bytes, st);
+        if (act == DKT_ACT_NONE) return launch_conv_ka<DKT_EPI_PROJ, DKT_ACT_NONE>(fam, prm, grid, smem_bytes, st);
+        return DKT_E_UNSUPPORTED;
+    }
+    switch (act) {
+        case DKT_ACT_NONE:    return launch_conv_ka<DKT_EPI_LINEAR, DKT_ACT_NONE>(fam, prm, grid, smem_bytes, st);
+        case DKT_ACT_RELU:    return launch_conv_ka<DKT_EPI_LINEAR, DKT_ACT_RELU>(fam, prm, grid, smem_bytes, st);
+        case DKT_ACT_SIGMOID: return launch_conv_ka<DKT_EPI_LINEAR, DKT_ACT_SIGMOID>(fam, prm, grid, smem_bytes, st);
+        case DKT_ACT_TANH:    return launch_conv_ka<DKT_EPI_LINEAR, DKT_ACT_TANH>(fam, prm, grid, smem_bytes, st);
+        default:              return DKT_E_INVALID;
+    }
+}
 
 extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t* w_hi, const uint16_t* w_lo,
                                 int kh, int kw, int stride, int N, const dkt_epilogue* epi,
@@ -483,6 +680,12 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     const dkt_epilogue& e = *epi;
     if (e.kind == DKT_EPI_LINEAR) {
         DKT_CHECK_ARG(e.out.f32 || e.out.hi);
+    } else if (e.kind == DKT_EPI_PROJ) {
+        DKT_CHECK_ARG(e.proj && e.out.f32 && e.out.c_count >= DKT_PROJ_LD);
+        if ((e.out.C % 4) || (e.out.c_begin % 4) || !aligned16(e.proj)) return DKT_E_ALIGNMENT;
+        if (e.ctx || e.res || e.tail) return DKT_E_UNSUPPORTED;
+    } else if (e.kind != DKT_EPI_GRU_ZR && e.kind != DKT_EPI_GRU_Q) {
+        return DKT_E_INVALID;
     } else {
         DKT_CHECK_ARG(e.ctx && e.z.f32 && e.h.f32 && (e.out.f32 || e.out.hi));
         if (N % 8) return DKT_E_ALIGNMENT;
@@ -494,9 +697,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     if (e.bias && !aligned16(e.bias)) return DKT_E_ALIGNMENT;
     if (!aligned16(e.out.f32) || !aligned16(e.out.hi) || !aligned16(e.out.lo)) return DKT_E_ALIGNMENT;
 
-    // kernel choice: the row-patch kernel (default) or the per-tap kernel (DKT_CONV_PATCH=0; K block 64 unless
-    // DKT_CONV_BK=32)
-    static const int s_bk_env = [] { const char* v = getenv("DKT_CONV_BK"); return v ? atoi(v) : 0; }();
+    // kernel choice: the row-patch kernel (default) or the per-tap kernel (strided convs, or DKT_CONV_PATCH=0)
     static const int s_patch = [] { const char* v = getenv("DKT_CONV_PATCH"); return (v && v[0] == '0') ? 0 : 1; }();
     static const int s_sms = [] {
         int dev = 0, n = 0;
@@ -530,8 +731,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
             }
         }
     }
-    // measured on B200 (gru08 z||r, N = 256, per-tap kernel): 2 stages x BK 64 = 0.957 ms, 4 stages x BK 32 = 0.980 ms
-    const int BK = use_patch ? 64 : ((s_bk_env == 32) ? 32 : 64);
+    const int BK = 64;
     const int WBK = use_patch ? WK : BK;          // K extent of a weight box
 
     TcConvParams prm{};
@@ -578,15 +778,6 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     prm.acc_cols = cols;
     prm.epi = e;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_patch_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_patch_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce != cudaSuccess) return (int)ce;
-        attr_set = true;
-    }
     const unsigned grid = (unsigned)(tiles < s_sms ? tiles : s_sms);
     if (use_patch) {
         prm.ygroup = ygroup;
@@ -594,11 +785,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         prm.w_stages = w_stages;
         prm.a_part_bytes = a_part_bytes;
         const size_t smem_bytes = (size_t)a_stages * 2 * a_part_bytes + (size_t)w_stages * w_stage_bytes + TC2_EPI_BYTES + 1024 + 256;
-        if (WK == 32)
-            conv_tc_patch_kernel<32><<<grid, TC2_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
-        else
-            conv_tc_patch_kernel<64><<<grid, TC2_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
-        DKT_RETURN_LAST();
+        return launch_conv(WK == 32 ? FAM_PATCH32 : FAM_PATCH64, prm, grid, smem_bytes, (cudaStream_t)stream);
     }
     // per-tap kernel: the ring takes what the epilogue buffers and barriers leave of the 227 KB
     const uint32_t stage_bytes = 2u * 128u * (uint32_t)BK * 2u + 2u * (uint32_t)prm.Npad * (uint32_t)BK * 2u;
@@ -607,11 +794,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     if (stages < 2) return DKT_E_UNSUPPORTED;
     prm.stages = stages;
     const size_t smem_bytes = (size_t)stages * stage_bytes + TC2_EPI_BYTES + 1024 + 256;
-    if (BK == 32)
-        conv_tc_kernel<32><<<grid, TC2_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
-    else
-        conv_tc_kernel<64><<<grid, TC2_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
-    DKT_RETURN_LAST();
+    return launch_conv(FAM_TAP64, prm, grid, smem_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int dkt_conv2d_tc(const dkt_tensor* srcs, int nsrc, const uint16_t* w_hi, const uint16_t* w_lo,

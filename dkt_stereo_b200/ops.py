@@ -222,7 +222,8 @@ def pack_conv_cat(weights: Sequence[torch.Tensor], tc: bool = True) -> ConvWeigh
 def make_epilogue(kind: int, out: DktTensor, act: int = L.ACT_NONE, scale: float = 1.0,
                   bias: Optional[torch.Tensor] = None, ctx: Optional[torch.Tensor] = None, ctx_c0: int = 0,
                   z: Optional[DktTensor] = None, h: Optional[DktTensor] = None,
-                  tail: Optional[torch.Tensor] = None, res: Optional[tuple] = None) -> DktEpilogue:
+                  tail: Optional[torch.Tensor] = None, res: Optional[tuple] = None,
+                  proj: Optional[torch.Tensor] = None) -> DktEpilogue:
     e = DktEpilogue()
     e.kind, e.act, e.scale = kind, act, scale
     e.bias = L.ptr(bias)
@@ -236,7 +237,20 @@ def make_epilogue(kind: int, out: DktTensor, act: int = L.ACT_NONE, scale: float
     e.tail_C = tail.shape[-1] if tail is not None else 0
     if res is not None:          # (tensor NHWC fp32, first channel)
         e.res, e.res_C, e.res_c0 = L.ptr(res[0]), res[0].shape[-1], res[1]
+    if proj is not None:         # fp32 [N][PROJ_LD], see pack_proj3x3
+        assert proj.dtype == torch.float32 and proj.is_contiguous() and proj.shape[-1] == L.PROJ_LD
+        e.proj = proj.data_ptr()
     return e
+
+
+def pack_proj3x3(weight: torch.Tensor, out_channel: int = 0) -> torch.Tensor:
+    """conv weight (Nout, Cin, 3, 3) -> fp32 [Cin][PROJ_LD] with [c][ky*3+kx] = weight[out_channel, c, ky, kx]:
+    the channel half of a one-output-channel 3x3 conv, applied by the DKT_EPI_PROJ epilogue of the conv that
+    produces its input; the spatial half is ``tapsum3x3``."""
+    w = weight.detach().float()[out_channel]                     # (Cin, 3, 3)
+    out = torch.zeros(w.shape[0], L.PROJ_LD, device=w.device, dtype=torch.float32)
+    out[:, :9] = w.reshape(w.shape[0], 9)
+    return out.contiguous()
 
 
 def pack_conv_general(weight: torch.Tensor, bias: Optional[torch.Tensor], *, stride: int = 1,
@@ -428,7 +442,7 @@ def _profiled(namer):
 
 
 def _conv_name(srcs, w, epi, B, H, W, impl="tc"):
-    kind = {0: "lin", 1: "gru_zr", 2: "gru_q"}[epi.kind]
+    kind = {0: "lin", 1: "gru_zr", 2: "gru_q", 3: "proj"}[epi.kind]
     return f"conv{w.ksize}x{w.ksize}_{w.cin}to{w.n}_{H}x{W}_{kind}_{impl}"
 
 

@@ -107,6 +107,9 @@ class UpdateEngine:
         self.fused_enc = os.environ.get("DKT_FUSED_ENC", "1") == "1"
         # 7x7 flow stem and the head's last conv in their tensor-core forms (tc only); 0 = generic kernels
         self.fast_small_convs = os.environ.get("DKT_FAST_SMALL_CONVS", "1") == "1"
+        # head conv1 + ReLU + the channel half of conv2 in ONE kernel (DKT_EPI_PROJ): the 256-channel hidden map of
+        # the flow / disparity head never reaches HBM; 0 = conv1 -> FH -> 1x1 tap conv
+        self.fused_head = os.environ.get("DKT_FUSED_HEAD", "1") == "1"
         self.weights: Optional[Dict[str, ops.ConvWeights]] = None
         self._wsig = None
         self.shape = None
@@ -150,6 +153,7 @@ class UpdateEngine:
             c2 = head.conv2
             w9 = c2.weight.detach()[0].permute(1, 2, 0).reshape(9, c2.in_channels, 1, 1)
             w["head2t"] = ops.pack_conv(w9, None, tc=True)
+            self.head2_proj = ops.pack_proj3x3(c2.weight, 0)
             self.head2_bias0 = float(c2.bias.detach()[0])
         if self.igev:
             w["mask0"] = ops.pack_conv(b.mask_feat_4[0].weight, b.mask_feat_4[0].bias, tc=tc)
@@ -282,6 +286,14 @@ class UpdateEngine:
         ops.interp(S(X1, 0, 128, True, False), S(X0, 256, 128, simt, split), B, h1, w1, h0, w0)
         self._gru(0, 256)
         # flow / disparity head (reference core/update.py:13-14)
+        if split and self.fast_small_convs and self.fused_head:
+            ops.conv2d([S(X0, 0, 128, False, True)], Wt["head1"],
+                       E(L.EPI_PROJ, S(self.TAPS, 0, 16, True, False), act=L.ACT_RELU, bias=Wt["head1"].bias,
+                         proj=self.head2_proj), B, h0, w0, "tc")
+            ops.tapsum3x3(self.TAPS["f32"], self.head2_bias0, self.DELTA["f32"])
+            if with_mask:
+                self.mask_head()
+            return
         ops.conv2d([S(X0, 0, 128, simt, split)], Wt["head1"],
                    E(L.EPI_LINEAR, S(self.FH, 0, 256, simt, split), act=L.ACT_RELU, bias=Wt["head1"].bias), B, h0, w0, impl)
         if split and self.fast_small_convs:

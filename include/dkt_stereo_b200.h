@@ -52,6 +52,12 @@ extern "C" {
                              (r*h) -> out           (reference core/update.py:27-28,29 first half) */
 #define DKT_EPI_GRU_Q  2  /* q = tanh(acc + ctx); h' = (1-z)*h + z*q -> out (h may alias out)
                              (reference core/update.py:29-31)                                     */
+#define DKT_EPI_PROJ   3  /* tensor-core path only: y = act(acc + bias[n]) never reaches HBM; instead
+                             out.f32[p][t] = sum_n y[n] * proj[n][t], t < DKT_PROJ_LD -- the channel half of
+                             the conv that FOLLOWS this one, applied while the tile is still in TMEM
+                             (FlowHead / DispHead: conv1+ReLU, then the 9 per-tap responses of conv2's
+                             used output channel; reference core/update.py:9-14)                  */
+#define DKT_PROJ_LD 12    /* row length of dkt_epilogue.proj (floats; 16-byte aligned rows)        */
 
 /* One NHWC activation tensor, optionally in several precisions.  Null members are skipped
  * by writers; readers document which member they need. */
@@ -82,6 +88,7 @@ typedef struct dkt_epilogue {
     const float* res;       /* LINEAR (tensor-core path): optional NHWC fp32 residual; the     */
     int32_t      res_C;     /*   result becomes relu(y + res[p][res_c0 + n]) -- the tail of a  */
     int32_t      res_c0;    /*   ResidualBlock (reference core/extractor.py:56-60).            */
+    const float* proj;      /* PROJ: fp32 [N][DKT_PROJ_LD] projection matrix (unused columns 0)    */
 } dkt_epilogue;
 
 /* ---- library ---------------------------------------------------------------------------- */

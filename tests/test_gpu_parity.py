@@ -502,3 +502,30 @@ def test_encoder_engine_vs_pytorch_extractor():
         c = eng.CTX[i]["f32"].permute(0, 3, 1, 2)
         cref = ctx_list[i] + eng.gru_bias[i].view(1, -1, 1, 1)
         assert stats(c.cpu(), cref.cpu())[1] < 2e-3, (i, stats(c.cpu(), cref.cpu()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 128, 256, 19, 37), (2, 64, 96, 8, 16), (1, 128, 250, 24, 48)])
+def test_conv_proj_epilogue(shape):
+    """DKT_EPI_PROJ: conv1 + ReLU + the channel half of a one-output 3x3 conv2 in one kernel, then tapsum3x3
+    == F.conv2d(relu(F.conv2d(x, w1, b1)), w2, b2)[:, 0] (FlowHead, reference core/update.py:13-14)."""
+    from dkt_stereo_b200 import ops, _lib as L
+    B, Cin, N, H, W = shape
+    g = torch.Generator().manual_seed(N + H)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w1 = torch.randn(N, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    b1 = torch.randn(N, generator=g)
+    w2 = torch.randn(2, N, 3, 3, generator=g) / (N * 9) ** 0.5
+    b2 = torch.randn(2, generator=g)
+    ref = torch.nn.functional.conv2d(torch.relu(torch.nn.functional.conv2d(x, w1, b1, padding=1)), w2, b2, padding=1)[:, 0]
+    xs, keep = _slice_of(_nhwc(x).to(dev()), "tc")
+    W1 = ops.pack_conv(w1.to(dev()), b1.to(dev()), tc=True)
+    proj = ops.pack_proj3x3(w2.to(dev()), 0)
+    taps = torch.full((B, H, W, 16), float("nan"), device=dev())
+    e = ops.make_epilogue(L.EPI_PROJ, L.tensor_slice(taps, None, None, 0, 16), act=L.ACT_RELU, bias=W1.bias, proj=proj)
+    ops.conv2d([xs], W1, e, B, H, W, "tc")
+    out = torch.zeros(B, H, W, 2, device=dev())
+    ops.tapsum3x3(taps, float(b2[0]), out)
+    torch.cuda.synchronize()
+    assert not torch.isnan(taps[..., :12]).any()
+    assert stats(out[..., 0].cpu(), ref)[1] < 3e-4, stats(out[..., 0].cpu(), ref)
