@@ -56,7 +56,15 @@ struct TcConvParams {
     int ygroup, a_stages, w_stages;
     uint32_t a_part_bytes;          // bytes of one precision (hi or lo) of an A stage
     uint32_t tmem_cols;
+    int w_resident;                 // pair kernel: the whole filter stays in the W ring (loaded once per CTA)
     dkt_epilogue epi;
+};
+
+// how the epilogue warps of a CTA walk their share of the tiles
+struct TileWalk {
+    int first, step, items;     // work items first, first + step, ... < items
+    int mul, off;               // tile = item * mul + off (pair kernel: 2 * item + cluster rank; may be >= num_tiles)
+    uint32_t empty_remote;      // shared::cluster address of the LEADER's tmem_empty_bar[0]; 0 = arrive locally
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -99,6 +107,12 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr) {
     return d;
 }
 
+// The role loops of warps 0 (TMA) and 1 (MMA) are executed by the WHOLE warp with one elected lane issuing:
+// warp-uniform control flow lets ptxas keep descriptors, coordinates and barrier addresses in uniform registers.
+// (Inside `if (lane == 0)` every UTCHMMA / UTMALDG was wrapped in an ELECT + 5x R2UR.BROADCAST retry loop, which
+// bounded the issue rate -- and with it the tensor pipe -- of every conv with N <= 128: ncu r01h.)
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // Epilogue warps 2..9 of both persistent kernels (see the header comment of this file), specialised at compile
 // time on the epilogue kind and activation: the instruction count of this loop, not the tensor pipe, bounded every
 // conv while it was generic (ncu r01f: ~8000 issued warp instructions per 32 x 32 chunk; now a few hundred).
@@ -108,7 +122,8 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr) {
 template <int KIND, int ACT>
 __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, uint32_t tmem_base,
                                                        uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
-                                                       uint8_t* epi_smem, int warp, int lane, int tiles_per_img) {
+                                                       uint8_t* epi_smem, int warp, int lane, int tiles_per_img,
+                                                       const TileWalk tw) {
     const int ew = warp - 2;
     const int q = warp & 3;
     const int half = ew >> 2;
@@ -134,7 +149,9 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
     const bool tail_merged = tail && (N & 3) && (((N + tail_C) & 3) == 0) && tail_C < 4;
     const int Nvec = tail_merged ? N + tail_C : N;
     uint32_t t = 0;
-    for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
+    for (int item = tw.first; item < tw.items; item += tw.step, ++t) {
+        const int tile = item * tw.mul + tw.off;
+        const bool live = tile < prm.num_tiles;          // the odd tile count's filler of a CTA pair is drained, not stored
         const int b = tile / tiles_per_img;
         const int r = tile - b * tiles_per_img;
         const int ty = r / prm.tiles_x;
@@ -146,7 +163,7 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
         mbar_wait(&tmem_full_bar[as], aphase);
         tcgen05_fence_after();
         const uint32_t tbase = tmem_base + as * prm.acc_cols + ((uint32_t)(q * 32) << 16);
-        for (int c0 = half * 32; c0 < prm.Npad; c0 += 64) {
+        for (int c0 = half * 32; live && c0 < prm.Npad; c0 += 64) {
             float v[32];
             const int ncols = (prm.Npad - c0 >= 32) ? 32 : 16;
             __syncwarp();                       // tcgen05.ld is .sync.aligned; also: previous chunk's reads done
@@ -248,7 +265,7 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                 }
             }
         }
-        if (tail && !tail_merged && half == 0) {
+        if (live && tail && !tail_merged && half == 0) {
             const int m = q * 32 + lane;
             const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
             if (y < H && x < W) {
@@ -258,7 +275,10 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        if (lane == 0) {
+            if (tw.empty_remote) mbar_arrive_cluster(tw.empty_remote + as * 8u);
+            else mbar_arrive(&tmem_empty_bar[as]);
+        }
     }
 }
 
@@ -271,7 +291,8 @@ constexpr int PROJ_T = 9;
 template <int ACT>
 __device__ __forceinline__ void conv_tc_epilogue_proj(const TcConvParams& prm, uint32_t tmem_base,
                                                       uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
-                                                      uint8_t* epi_smem, int warp, int lane, int tiles_per_img) {
+                                                      uint8_t* epi_smem, int warp, int lane, int tiles_per_img,
+                                                      const TileWalk tw) {
     const int ew = warp - 2;
     const int q = warp & 3;
     const int half = ew >> 2;
@@ -286,7 +307,9 @@ __device__ __forceinline__ void conv_tc_epilogue_proj(const TcConvParams& prm, u
     for (int i = et; i < 256; i += TC2_EPI_WARPS * 32) s_b[i] = (i < N && e.bias) ? __ldg(e.bias + i) : 0.f;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     uint32_t t = 0;
-    for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
+    for (int item = tw.first; item < tw.items; item += tw.step, ++t) {
+        const int tile = item * tw.mul + tw.off;
+        const bool live = tile < prm.num_tiles;
         const int b = tile / tiles_per_img;
         const int r = tile - b * tiles_per_img;
         const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
@@ -297,7 +320,7 @@ __device__ __forceinline__ void conv_tc_epilogue_proj(const TcConvParams& prm, u
         float acc[PROJ_T];
 #pragma unroll
         for (int u = 0; u < PROJ_T; ++u) acc[u] = 0.f;
-        for (int c0 = half * 32; c0 < prm.Npad; c0 += 64) {
+        for (int c0 = half * 32; live && c0 < prm.Npad; c0 += 64) {
             float v[32];
             const int ncols = (prm.Npad - c0 >= 32) ? 32 : 16;
             __syncwarp();
@@ -326,7 +349,11 @@ __device__ __forceinline__ void conv_tc_epilogue_proj(const TcConvParams& prm, u
         // accumulator drained: hand it back to the MMA warp before the (slow) exchange + store
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        if (lane == 0) {
+            if (tw.empty_remote) mbar_arrive_cluster(tw.empty_remote + as * 8u);
+            else mbar_arrive(&tmem_empty_bar[as]);
+        }
+        if (!live) continue;                          // uniform over the CTA: both warps of a quarter skip the exchange
         float* xb = s_x + ((t & 1u) * 128 + q * 32 + lane) * DKT_PROJ_LD;
         if (half == 1) {
             *reinterpret_cast<float4*>(xb) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -368,7 +395,7 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
 
     int kb_total = 0;
     for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
@@ -390,21 +417,21 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
     const int tiles_per_img = prm.tiles_x * prm.tiles_y;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer =====
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
-                const int b = tile / tiles_per_img;
-                const int r = tile - b * tiles_per_img;
-                const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
-                for (int tap = 0; tap < prm.taps; ++tap) {
-                    const int ky = tap / prm.kw, kx = tap - ky * prm.kw;
-                    const int xs = x0 * prm.stride + kx - prm.pad_x, ys = y0 * prm.stride + ky - prm.pad_y;
-                    int kofs = 0;
-                    for (int s = 0; s < prm.nsrc; ++s) {
-                        for (int kb = 0; kb < prm.kblocks[s]; ++kb) {
-                            mbar_wait(&empty_bar[stage], phase ^ 1u);
+        // ===== TMA producer =====
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+            const int b = tile / tiles_per_img;
+            const int r = tile - b * tiles_per_img;
+            const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
+            for (int tap = 0; tap < prm.taps; ++tap) {
+                const int ky = tap / prm.kw, kx = tap - ky * prm.kw;
+                const int xs = x0 * prm.stride + kx - prm.pad_x, ys = y0 * prm.stride + ky - prm.pad_y;
+                int kofs = 0;
+                for (int s = 0; s < prm.nsrc; ++s) {
+                    for (int kb = 0; kb < prm.kblocks[s]; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        if (elect_one()) {
                             uint8_t* st = smem + (size_t)stage * stage_bytes;
                             mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                             const int c = prm.c_begin[s] + kb * BK;
@@ -412,51 +439,49 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
                             tma_load_4d(st + A_BYTES, &prm.act[s][1], &full_bar[stage], c, xs, ys, b);
                             tma_load_2d(st + 2 * A_BYTES, &prm.wgt[0], &full_bar[stage], kofs + kb * BK, tap * prm.Npad);
                             tma_load_2d(st + 2 * A_BYTES + b_bytes, &prm.wgt[1], &full_bar[stage], kofs + kb * BK, tap * prm.Npad);
-                            if (++stage == prm.stages) { stage = 0; phase ^= 1u; }
                         }
-                        kofs += prm.kblocks[s] * BK;
+                        if (++stage == prm.stages) { stage = 0; phase ^= 1u; }
                     }
+                    kofs += prm.kblocks[s] * BK;
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t idesc = idesc_bf16_m128((uint32_t)prm.Npad);
-            int stage = 0;
-            uint32_t phase = 0;
-            uint32_t t = 0;
-            for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
-                const uint32_t as = t & 1u, aphase = (t >> 1) & 1u;
-                mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);          // epilogue drained this accumulator
+        // ===== MMA issuer =====
+        const uint32_t idesc = idesc_bf16_m128((uint32_t)prm.Npad);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
+            const uint32_t as = t & 1u, aphase = (t >> 1) & 1u;
+            mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);          // epilogue drained this accumulator
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + as * prm.acc_cols;
+            for (int it = 0; it < ksteps; ++it) {
+                mbar_wait(&full_bar[stage], phase);
                 tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + as * prm.acc_cols;
-                for (int it = 0; it < ksteps; ++it) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tcgen05_fence_after();
+                if (elect_one()) {
                     const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t a_lo = a_hi + A_BYTES;
-                    const uint32_t w_hi = a_hi + 2 * A_BYTES;
-                    const uint32_t w_lo = w_hi + b_bytes;
+                    const uint64_t dah = smem_desc_kmajor<BK>(a_hi), dal = smem_desc_kmajor<BK>(a_hi + A_BYTES);
+                    const uint64_t dwh = smem_desc_kmajor<BK>(a_hi + 2 * A_BYTES), dwl = smem_desc_kmajor<BK>(a_hi + 2 * A_BYTES + b_bytes);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t dah = smem_desc_kmajor<BK>(a_hi + k * 32), dal = smem_desc_kmajor<BK>(a_lo + k * 32);
-                        const uint64_t dwh = smem_desc_kmajor<BK>(w_hi + k * 32), dwl = smem_desc_kmajor<BK>(w_lo + k * 32);
-                        umma_bf16(tmem_d, dah, dwh, idesc, (it | k) != 0);
-                        umma_bf16(tmem_d, dal, dwh, idesc, 1u);
-                        umma_bf16(tmem_d, dah, dwl, idesc, 1u);
+                    for (int k = 0; k < BK / 16; ++k) {           // +32 bytes per K16 step = +2 in the address field
+                        umma_bf16(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, (it | k) != 0);
+                        umma_bf16(tmem_d, dal + 2 * k, dwh + 2 * k, idesc, 1u);
+                        umma_bf16(tmem_d, dah + 2 * k, dwl + 2 * k, idesc, 1u);
                     }
-                    umma_commit(&empty_bar[stage]);                   // smem slot reusable once these MMAs retire
-                    if (++stage == prm.stages) { stage = 0; phase ^= 1u; }
+                    umma_commit(&empty_bar[stage]);               // smem slot reusable once these MMAs retire
                 }
-                umma_commit(&tmem_full_bar[as]);                      // accumulator complete
+                if (++stage == prm.stages) { stage = 0; phase ^= 1u; }
             }
+            if (elect_one()) umma_commit(&tmem_full_bar[as]);     // accumulator complete
         }
     } else {
+        const TileWalk tw{(int)blockIdx.x, (int)gridDim.x, prm.num_tiles, 1, 0, 0u};
         if constexpr (KIND == DKT_EPI_PROJ)
-            conv_tc_epilogue_proj<ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img);
+            conv_tc_epilogue_proj<ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
         else
-            conv_tc_epilogue_warps<KIND, ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img);
+            conv_tc_epilogue_warps<KIND, ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
     }
 
     tcgen05_fence_before();
@@ -475,7 +500,7 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
 // patch of 14 rows instead of 7 tiles.  Weights stream through their own ring in K blocks of WK
 // channels (32 when N > 128 so that three stages fit).  Strided convs use ygroup = 1 (plain tiles).
 // ---------------------------------------------------------------------------------------------
-constexpr int TCP_MAX_A = 4, TCP_MAX_W = 8;
+constexpr int TCP_MAX_A = 4, TCP_MAX_W = 9;
 
 template <int WK, int KIND, int ACT>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
@@ -498,7 +523,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int ygroups = prm.kh / prm.ygroup;                 // A steps per (kb, kx)
 
     if (warp == 0 && lane == 0) {
@@ -518,59 +543,230 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
     const int tiles_per_img = prm.tiles_x * prm.tiles_y;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer: A patches and W tiles in the order the MMA warp consumes them =====
-            int as = 0, ws = 0;
-            uint32_t aph = 0, wph = 0;
-            for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
-                const int b = tile / tiles_per_img;
-                const int r = tile - b * tiles_per_img;
-                const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
-                int kofs = 0;
-                for (int s = 0; s < prm.nsrc; ++s) {
-                    for (int kb = 0; kb < prm.kblocks[s]; ++kb) {
-                        const int c = prm.c_begin[s] + kb * 64;
-                        for (int kx = 0; kx < prm.kw; ++kx) {
-                            const int xs = x0 * prm.stride + kx - prm.pad_x;
-                            for (int yg = 0; yg < ygroups; ++yg) {
-                                const int ys = y0 * prm.stride + yg * prm.ygroup - prm.pad_y;
-                                mbar_wait(&aempty[as], aph ^ 1u);
+        // ===== TMA producer: A patches and W tiles in the order the MMA warp consumes them =====
+        int as = 0, ws = 0;
+        uint32_t aph = 0, wph = 0;
+        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+            const int b = tile / tiles_per_img;
+            const int r = tile - b * tiles_per_img;
+            const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
+            int kofs = 0;
+            for (int s = 0; s < prm.nsrc; ++s) {
+                for (int kb = 0; kb < prm.kblocks[s]; ++kb) {
+                    const int c = prm.c_begin[s] + kb * 64;
+                    for (int kx = 0; kx < prm.kw; ++kx) {
+                        const int xs = x0 * prm.stride + kx - prm.pad_x;
+                        for (int yg = 0; yg < ygroups; ++yg) {
+                            const int ys = y0 * prm.stride + yg * prm.ygroup - prm.pad_y;
+                            mbar_wait(&aempty[as], aph ^ 1u);
+                            if (elect_one()) {
                                 uint8_t* ast = a_ring + (size_t)as * a_stage_bytes;
                                 mbar_arrive_expect_tx(&afull[as], a_stage_bytes);
                                 tma_load_4d(ast, &prm.act[s][0], &afull[as], c, xs, ys, b);
                                 tma_load_4d(ast + a_part, &prm.act[s][1], &afull[as], c, xs, ys, b);
-                                if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
-                                for (int kyi = 0; kyi < prm.ygroup; ++kyi) {
-                                    const int tap = (yg * prm.ygroup + kyi) * prm.kw + kx;
-                                    for (int wh = 0; wh < WSPLIT; ++wh) {
-                                        mbar_wait(&wempty[ws], wph ^ 1u);
+                            }
+                            if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
+                            for (int kyi = 0; kyi < prm.ygroup; ++kyi) {
+                                const int tap = (yg * prm.ygroup + kyi) * prm.kw + kx;
+                                for (int wh = 0; wh < WSPLIT; ++wh) {
+                                    mbar_wait(&wempty[ws], wph ^ 1u);
+                                    if (elect_one()) {
                                         uint8_t* wst = w_ring + (size_t)ws * w_stage_bytes;
                                         mbar_arrive_expect_tx(&wfull[ws], w_stage_bytes);
                                         const int kc = kofs + kb * 64 + wh * WK;
                                         tma_load_2d(wst, &prm.wgt[0], &wfull[ws], kc, tap * prm.Npad);
                                         tma_load_2d(wst + b_bytes, &prm.wgt[1], &wfull[ws], kc, tap * prm.Npad);
-                                        if (++ws == prm.w_stages) { ws = 0; wph ^= 1u; }
                                     }
+                                    if (++ws == prm.w_stages) { ws = 0; wph ^= 1u; }
                                 }
                             }
                         }
                     }
-                    kofs += prm.kblocks[s] * 64;
                 }
+                kofs += prm.kblocks[s] * 64;
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t idesc = idesc_bf16_m128((uint32_t)prm.Npad);
+        // ===== MMA issuer =====
+        const uint32_t idesc = idesc_bf16_m128((uint32_t)prm.Npad);
+        int as = 0, ws = 0;
+        uint32_t aph = 0, wph = 0, t = 0;
+        int kb_total = 0;
+        for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
+        const int a_steps = kb_total * prm.kw * ygroups;
+        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
+            const uint32_t acs = t & 1u, aphase = (t >> 1) & 1u;
+            mbar_wait(&tmem_empty_bar[acs], aphase ^ 1u);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + acs * prm.acc_cols;
+            uint32_t accumulate = 0;
+            for (int ai = 0; ai < a_steps; ++ai) {
+                mbar_wait(&afull[as], aph);
+                tcgen05_fence_after();
+                const uint32_t a_hi0 = smem_u32(a_ring + (size_t)as * a_stage_bytes);
+                for (int kyi = 0; kyi < prm.ygroup; ++kyi) {
+                    const uint32_t a_hi = a_hi0 + (uint32_t)kyi * (TC_TILE_W * 128u);
+#pragma unroll
+                    for (int wh = 0; wh < WSPLIT; ++wh) {
+                        mbar_wait(&wfull[ws], wph);
+                        tcgen05_fence_after();
+                        if (elect_one()) {
+                            const uint32_t w_hi = smem_u32(w_ring + (size_t)ws * w_stage_bytes);
+                            const uint64_t dah = smem_desc_kmajor<64>(a_hi + wh * WK * 2), dal = smem_desc_kmajor<64>(a_hi + a_part + wh * WK * 2);
+                            const uint64_t dwh = smem_desc_kmajor<WK>(w_hi), dwl = smem_desc_kmajor<WK>(w_hi + b_bytes);
+#pragma unroll
+                            for (int k = 0; k < WK / 16; ++k) {   // +32 bytes per K16 step = +2 in the address field
+                                umma_bf16(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, accumulate);
+                                umma_bf16(tmem_d, dal + 2 * k, dwh + 2 * k, idesc, 1u);
+                                umma_bf16(tmem_d, dah + 2 * k, dwl + 2 * k, idesc, 1u);
+                                accumulate = 1u;
+                            }
+                            umma_commit(&wempty[ws]);
+                        }
+                        accumulate = 1u;
+                        if (++ws == prm.w_stages) { ws = 0; wph ^= 1u; }
+                    }
+                }
+                if (elect_one()) umma_commit(&aempty[as]);         // patch reusable once every tap's MMAs retire
+                if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
+            }
+            if (elect_one()) umma_commit(&tmem_full_bar[acs]);
+        }
+    } else {
+        const TileWalk tw{(int)blockIdx.x, (int)gridDim.x, prm.num_tiles, 1, 0, 0u};
+        if constexpr (KIND == DKT_EPI_PROJ)
+            conv_tc_epilogue_proj<ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+        else
+            conv_tc_epilogue_warps<KIND, ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * prm.acc_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// v4 ("CTA pair"): the row-patch kernel on tcgen05 cta_group::2.  Two CTAs of a cluster (one TPC) work on two
+// tiles at once as ONE M = 256 MMA: each CTA stages the halo patches of its own 128-pixel tile and only HALF of
+// every weight block (rows [rank * Npad/2, (rank+1) * Npad/2) of the N x 64 tile); the tensor core of the pair
+// reads A from both CTAs and the two B halves from both CTAs.  Why: after the epilogue was specialised every
+// conv of the step sat at 8.5 - 10.5 TB/s of L2 -> SM traffic (ncu r01g, l1tex__m_xbar2l1tex_read_bytes), the
+// cap of the L2 fabric, and the weight stream was most of it (3.5 MB of 4.3 MB per tile for the gru08 gates).
+// Halving the weight bytes per SM also doubles the K depth a weight stage holds; filters whose half fits
+// (3x3 / 7x1 at 64 -> 64) stay resident in the ring for the whole launch (`w_resident`).
+//   barriers   afull / wfull / tmem_empty live in the LEADER (cluster rank 0): both producers' TMA bytes are
+//              counted there (the leader arms 2x the stage bytes), the follower's epilogue warps arrive remotely;
+//              aempty / wempty / tmem_full exist in both CTAs and are signalled by multicast tcgen05.commit.
+//   roles      warp 0 = TMA producer (both CTAs), warp 1 = MMA issuer (leader only; allocates TMEM in both),
+//              warps 2..9 = epilogue of the CTA's own tile (TMEM lanes 0..127 of each CTA = its 128 pixels).
+// ---------------------------------------------------------------------------------------------
+template <int KIND, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
+conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    const int Nh = prm.Npad >> 1;                                   // weight rows staged by this CTA
+    const uint32_t a_part = prm.a_part_bytes, a_stage_bytes = 2u * prm.a_part_bytes;
+    const uint32_t b_bytes = (uint32_t)Nh * 128u, w_stage_bytes = 2u * b_bytes;     // K block of 64 channels
+    uint8_t* a_ring = smem;
+    uint8_t* w_ring = a_ring + (size_t)prm.a_stages * a_stage_bytes;
+    uint8_t* epi_smem = w_ring + (size_t)prm.w_stages * w_stage_bytes;
+    uint64_t* afull = reinterpret_cast<uint64_t*>(epi_smem + TC2_EPI_BYTES);
+    uint64_t* aempty = afull + TCP_MAX_A;
+    uint64_t* wfull = aempty + TCP_MAX_A;
+    uint64_t* wempty = wfull + TCP_MAX_W;
+    uint64_t* tmem_full_bar = wempty + TCP_MAX_W;            // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int ygroups = prm.kh / prm.ygroup;                 // A steps per (kb, kx)
+    const int pairs = (int)gridDim.x >> 1, pair_id = (int)blockIdx.x >> 1;
+    const int items = (prm.num_tiles + 1) >> 1;              // work item = two consecutive tiles
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < prm.nsrc; ++s) { tma_prefetch_desc(&prm.act[s][0]); tma_prefetch_desc(&prm.act[s][1]); }
+        tma_prefetch_desc(&prm.wgt[0]);
+        tma_prefetch_desc(&prm.wgt[1]);
+        for (int s = 0; s < prm.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < prm.w_stages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 2 * TC2_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot, 2 * prm.acc_cols);
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                      // both CTAs' barriers and TMEM exist before any remote access
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles_per_img = prm.tiles_x * prm.tiles_y;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own A patches, own half of the W blocks; bytes counted on the leader =====
+        const uint32_t afull_l = mapa_u32(smem_u32(afull), 0), wfull_l = mapa_u32(smem_u32(wfull), 0);
+        const int wrow0 = (int)rank * Nh;
+        int as = 0, ws = 0;
+        uint32_t aph = 0, wph = 0;
+        bool first = true;
+        for (int item = pair_id; item < items; item += pairs) {
+            int tile = 2 * item + (int)rank;
+            if (tile >= prm.num_tiles) tile = prm.num_tiles - 1;      // filler: valid loads, results dropped
+            const int b = tile / tiles_per_img;
+            const int r = tile - b * tiles_per_img;
+            const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
+            int kofs = 0;
+            for (int s = 0; s < prm.nsrc; ++s) {
+                for (int kb = 0; kb < prm.kblocks[s]; ++kb) {
+                    const int c = prm.c_begin[s] + kb * 64;
+                    for (int kx = 0; kx < prm.kw; ++kx) {
+                        const int xs = x0 + kx - prm.pad_x;
+                        for (int yg = 0; yg < ygroups; ++yg) {
+                            const int ys = y0 + yg * prm.ygroup - prm.pad_y;
+                            mbar_wait(&aempty[as], aph ^ 1u);
+                            if (elect_one()) {
+                                uint8_t* ast = a_ring + (size_t)as * a_stage_bytes;
+                                if (leader) mbar_arrive_expect_tx(&afull[as], 2u * a_stage_bytes);
+                                tma_load_4d_pair(ast, &prm.act[s][0], afull_l + as * 8u, c, xs, ys, b);
+                                tma_load_4d_pair(ast + a_part, &prm.act[s][1], afull_l + as * 8u, c, xs, ys, b);
+                            }
+                            if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
+                            for (int kyi = 0; kyi < prm.ygroup; ++kyi) {
+                                if (!prm.w_resident || first) {
+                                    const int tap = (yg * prm.ygroup + kyi) * prm.kw + kx;
+                                    mbar_wait(&wempty[ws], wph ^ 1u);
+                                    if (elect_one()) {
+                                        uint8_t* wst = w_ring + (size_t)ws * w_stage_bytes;
+                                        if (leader) mbar_arrive_expect_tx(&wfull[ws], 2u * w_stage_bytes);
+                                        const int kc = kofs + kb * 64;
+                                        tma_load_2d_pair(wst, &prm.wgt[0], wfull_l + ws * 8u, kc, tap * prm.Npad + wrow0);
+                                        tma_load_2d_pair(wst + b_bytes, &prm.wgt[1], wfull_l + ws * 8u, kc, tap * prm.Npad + wrow0);
+                                    }
+                                }
+                                if (++ws == prm.w_stages) { ws = 0; wph ^= 1u; }
+                            }
+                        }
+                    }
+                }
+                kofs += prm.kblocks[s] * 64;
+            }
+            first = false;
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            // ===== MMA issuer (leader): M = 256 over both CTAs' tiles =====
+            const uint32_t idesc = idesc_bf16_m256((uint32_t)prm.Npad);
             int as = 0, ws = 0;
             uint32_t aph = 0, wph = 0, t = 0;
             int kb_total = 0;
             for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
             const int a_steps = kb_total * prm.kw * ygroups;
-            for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
+            bool first = true;
+            for (int item = pair_id; item < items; item += pairs, ++t) {
                 const uint32_t acs = t & 1u, aphase = (t >> 1) & 1u;
-                mbar_wait(&tmem_empty_bar[acs], aphase ^ 1u);
+                mbar_wait(&tmem_empty_bar[acs], aphase ^ 1u);     // both CTAs' epilogues drained this accumulator
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acs * prm.acc_cols;
                 uint32_t accumulate = 0;
@@ -580,43 +776,46 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
                     const uint32_t a_hi0 = smem_u32(a_ring + (size_t)as * a_stage_bytes);
                     for (int kyi = 0; kyi < prm.ygroup; ++kyi) {
                         const uint32_t a_hi = a_hi0 + (uint32_t)kyi * (TC_TILE_W * 128u);
-                        const uint32_t a_lo = a_hi + a_part;
-#pragma unroll
-                        for (int wh = 0; wh < WSPLIT; ++wh) {
+                        if (!prm.w_resident || first) {
                             mbar_wait(&wfull[ws], wph);
                             tcgen05_fence_after();
+                        }
+                        if (elect_one()) {
                             const uint32_t w_hi = smem_u32(w_ring + (size_t)ws * w_stage_bytes);
-                            const uint32_t w_lo = w_hi + b_bytes;
+                            const uint64_t dah = smem_desc_kmajor<64>(a_hi), dal = smem_desc_kmajor<64>(a_hi + a_part);
+                            const uint64_t dwh = smem_desc_kmajor<64>(w_hi), dwl = smem_desc_kmajor<64>(w_hi + b_bytes);
 #pragma unroll
-                            for (int k = 0; k < WK / 16; ++k) {
-                                const uint32_t ak = (uint32_t)(wh * WK * 2 + k * 32);
-                                const uint64_t dah = smem_desc_kmajor<64>(a_hi + ak), dal = smem_desc_kmajor<64>(a_lo + ak);
-                                const uint64_t dwh = smem_desc_kmajor<WK>(w_hi + k * 32), dwl = smem_desc_kmajor<WK>(w_lo + k * 32);
-                                umma_bf16(tmem_d, dah, dwh, idesc, accumulate);
-                                umma_bf16(tmem_d, dal, dwh, idesc, 1u);
-                                umma_bf16(tmem_d, dah, dwl, idesc, 1u);
+                            for (int k = 0; k < 4; ++k) {         // +32 bytes per K16 step = +2 in the address field
+                                umma_bf16_pair(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, accumulate);
+                                umma_bf16_pair(tmem_d, dal + 2 * k, dwh + 2 * k, idesc, 1u);
+                                umma_bf16_pair(tmem_d, dah + 2 * k, dwl + 2 * k, idesc, 1u);
                                 accumulate = 1u;
                             }
-                            umma_commit(&wempty[ws]);
-                            if (++ws == prm.w_stages) { ws = 0; wph ^= 1u; }
+                            if (!prm.w_resident) umma_commit_pair(&wempty[ws]);
                         }
+                        accumulate = 1u;
+                        if (++ws == prm.w_stages) { ws = 0; wph ^= 1u; }
                     }
-                    umma_commit(&aempty[as]);                 // patch reusable once every tap's MMAs retire
+                    if (elect_one()) umma_commit_pair(&aempty[as]);   // both CTAs' patches reusable once every tap's MMAs retire
                     if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
                 }
-                umma_commit(&tmem_full_bar[acs]);
+                if (elect_one()) umma_commit_pair(&tmem_full_bar[acs]);
+                first = false;
             }
         }
     } else {
+        const TileWalk tw{pair_id, pairs, items, 2, (int)rank, leader ? 0u : mapa_u32(smem_u32(tmem_empty_bar), 0)};
         if constexpr (KIND == DKT_EPI_PROJ)
-            conv_tc_epilogue_proj<ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img);
+            conv_tc_epilogue_proj<ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
         else
-            conv_tc_epilogue_warps<KIND, ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img);
+            conv_tc_epilogue_warps<KIND, ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
     }
 
+    // neither CTA may leave (or free TMEM) while its peer can still reach its shared memory / barriers
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * prm.acc_cols);
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_pair(tmem_base, 2 * prm.acc_cols);
 }
 
 }  // namespace dkt
@@ -626,7 +825,7 @@ using namespace dkt;
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ---- launch: one instantiation per (kernel family, epilogue kind, activation) ----
-enum ConvFamily { FAM_PATCH32, FAM_PATCH64, FAM_TAP64 };
+enum ConvFamily { FAM_PATCH32, FAM_PATCH64, FAM_TAP64, FAM_PAIR };
 
 template <int KIND, int ACT>
 static int launch_conv_ka(ConvFamily fam, const TcConvParams& prm, unsigned grid, size_t smem_bytes, cudaStream_t st) {
@@ -635,12 +834,14 @@ static int launch_conv_ka(ConvFamily fam, const TcConvParams& prm, unsigned grid
         cudaError_t ce = cudaFuncSetAttribute(conv_tc_patch_kernel<32, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_patch_kernel<64, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<64, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_pair_kernel<KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce != cudaSuccess) return (int)ce;
         attr_set = true;
     }
     switch (fam) {
         case FAM_PATCH32: conv_tc_patch_kernel<32, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
         case FAM_PATCH64: conv_tc_patch_kernel<64, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
+        case FAM_PAIR:    conv_tc_pair_kernel<KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;   // grid even (cluster of 2)
         default:          conv_tc_kernel<64, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
     }
     DKT_RETURN_LAST();
@@ -699,6 +900,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
 
     // kernel choice: the row-patch kernel (default) or the per-tap kernel (strided convs, or DKT_CONV_PATCH=0)
     static const int s_patch = [] { const char* v = getenv("DKT_CONV_PATCH"); return (v && v[0] == '0') ? 0 : 1; }();
+    static const int s_pair = [] { const char* v = getenv("DKT_CONV_PAIR"); return (v && v[0] == '0') ? 0 : 1; }();
     static const int s_sms = [] {
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
@@ -714,25 +916,54 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     const int ygroup = (stride == 1) ? kh : 1;
     const int rows_loaded = (stride == 1) ? TC_TILE_H + ygroup - 1 : TC_TILE_H;
     const uint32_t a_part_bytes = (uint32_t)rows_loaded * TC_TILE_W * 128u;
+    int cin_sum = 0;
+    for (int s = 0; s < nsrc; ++s) cin_sum += srcs[s].c_count;
+    const int64_t tiles64 = (int64_t)ceil_div(W, TC_TILE_W) * ceil_div(H, TC_TILE_H) * B;
+
+    // CTA-pair kernel (default for stride 1): each CTA stages half of a 64-channel weight block
+    bool use_pair = s_pair != 0 && s_patch != 0 && stride == 1 && tiles64 >= 2 && (cin_sum % 64) == 0;
+    int p_a_stages = 2, p_w_stages = 0, p_resident = 0;
+    const uint32_t p_w_stage_bytes = 2u * (uint32_t)(Npad / 2) * 128u;
+    if (use_pair) {
+        const int w_steps = (cin_sum / 64) * kh * kw;              // weight blocks per tile
+        if (2u * a_part_bytes * 2 >= budget) use_pair = false;
+        else if (w_steps <= TCP_MAX_W && 2u * a_part_bytes * 2 + (uint32_t)w_steps * p_w_stage_bytes <= budget) {
+            p_resident = 1;                                        // whole filter half stays in the ring
+            p_w_stages = w_steps;
+            p_a_stages = (int)((budget - (uint32_t)w_steps * p_w_stage_bytes) / (2u * a_part_bytes));
+            if (p_a_stages > TCP_MAX_A) p_a_stages = TCP_MAX_A;
+        } else {
+            p_w_stages = (int)((budget - 2u * a_part_bytes * 2) / p_w_stage_bytes);
+            if (p_w_stages > 8) p_w_stages = 8;
+            if (p_w_stages < 2) use_pair = false;
+            else if (p_w_stages >= 7 && 2u * a_part_bytes * 3 + 4u * p_w_stage_bytes <= budget) {
+                p_a_stages = 3;                                    // small N: a third patch stage is worth more
+                p_w_stages = (int)((budget - 2u * a_part_bytes * 3) / p_w_stage_bytes);
+                if (p_w_stages > 8) p_w_stages = 8;
+            }
+        }
+    }
+
     const int WK = (Npad > 128) ? 32 : 64;
     const uint32_t w_stage_bytes = 2u * (uint32_t)Npad * (uint32_t)WK * 2u;
     int a_stages = 2, w_stages = 0;
     bool use_patch = s_patch != 0;
-    if (use_patch) {
+    if (use_patch && !use_pair) {
         if (2u * a_part_bytes * a_stages >= budget) use_patch = false;
         else {
             w_stages = (int)((budget - 2u * a_part_bytes * a_stages) / w_stage_bytes);
-            if (w_stages > TCP_MAX_W) w_stages = TCP_MAX_W;
+            if (w_stages > 8) w_stages = 8;
             if (w_stages < 2) use_patch = false;
             else if (w_stages >= 5 && 2u * a_part_bytes * 3 + 4u * w_stage_bytes <= budget) {
                 a_stages = 3;
                 w_stages = (int)((budget - 2u * a_part_bytes * 3) / w_stage_bytes);
-                if (w_stages > TCP_MAX_W) w_stages = TCP_MAX_W;
+                if (w_stages > 8) w_stages = 8;
             }
         }
     }
     const int BK = 64;
-    const int WBK = use_patch ? WK : BK;          // K extent of a weight box
+    const int WBK = use_pair ? 64 : (use_patch ? WK : BK);   // K extent of a weight box
+    const int wbox_rows = use_pair ? Npad / 2 : Npad;         // N extent of a weight box
 
     TcConvParams prm{};
     prm.nsrc = nsrc;
@@ -760,7 +991,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     {
         const uint64_t dims[2] = {(uint64_t)cin_total, (uint64_t)prm.taps * prm.Npad};
         const uint64_t strides[2] = {1, (uint64_t)cin_total};
-        const uint32_t box[2] = {(uint32_t)WBK, (uint32_t)prm.Npad};
+        const uint32_t box[2] = {(uint32_t)WBK, (uint32_t)wbox_rows};
         if (!aligned16(w_hi) || !aligned16(w_lo)) return DKT_E_ALIGNMENT;
         if (!make_tmap_bf16(&prm.wgt[0], w_hi, 2, dims, strides, box, WBK * 2)) return DKT_E_DRIVER;
         if (!make_tmap_bf16(&prm.wgt[1], w_lo, 2, dims, strides, box, WBK * 2)) return DKT_E_DRIVER;
@@ -778,6 +1009,17 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     prm.acc_cols = cols;
     prm.epi = e;
 
+    if (use_pair) {
+        prm.ygroup = ygroup;
+        prm.a_stages = p_a_stages;
+        prm.w_stages = p_w_stages;
+        prm.w_resident = p_resident;
+        prm.a_part_bytes = a_part_bytes;
+        const int items = (int)((tiles + 1) / 2);
+        const int pairs = items < s_sms / 2 ? items : s_sms / 2;
+        const size_t smem_bytes = (size_t)p_a_stages * 2 * a_part_bytes + (size_t)p_w_stages * p_w_stage_bytes + TC2_EPI_BYTES + 1024 + 256;
+        return launch_conv(FAM_PAIR, prm, 2u * (unsigned)pairs, smem_bytes, (cudaStream_t)stream);
+    }
     const unsigned grid = (unsigned)(tiles < s_sms ? tiles : s_sms);
     if (use_patch) {
         prm.ygroup = ygroup;

@@ -191,7 +191,10 @@ def _slice_of(x_nhwc, impl, c0=0, cnt=None):
 
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("shape", [(1, 64, 64, 8, 16, 3), (2, 128, 126, 19, 37, 3), (1, 64, 144, 9, 20, 1),
-                                   (1, 256, 2, 11, 18, 3), (2, 384, 256, 17, 30, 3)])
+                                   (1, 256, 2, 11, 18, 3), (2, 384, 256, 17, 30, 3),
+                                   # odd tile counts (the CTA-pair kernel's filler tile), resident / streamed filters
+                                   (1, 64, 64, 24, 16, 3), (3, 64, 32, 8, 16, 3), (1, 128, 256, 24, 16, 3),
+                                   (1, 192, 128, 17, 33, 3)])
 def test_conv_linear(impl, shape):
     from dkt_stereo_b200 import ops, _lib as L
     B, Cin, N, H, W, k = shape
@@ -529,3 +532,39 @@ def test_conv_proj_epilogue(shape):
     torch.cuda.synchronize()
     assert not torch.isnan(taps[..., :12]).any()
     assert stats(out[..., 0].cpu(), ref)[1] < 3e-4, stats(out[..., 0].cpu(), ref)
+
+
+def test_conv_pair_matches_single_cta():
+    """The CTA-pair (cta_group::2) kernel and the single-CTA row-patch kernel are the same arithmetic in the same
+    order per output: results must agree bit for bit (DKT_CONV_PAIR is read once per process, so this test drives
+    the choice through a subprocess)."""
+    import subprocess, sys, os
+    code = r"""
+import torch, sys
+sys.path.insert(0, %r)
+from dkt_stereo_b200 import ops, _lib as L
+torch.manual_seed(3)
+dev = torch.device('cuda:0')
+outs = []
+for (B, Cin, N, H, W) in [(2, 384, 256, 17, 30), (1, 64, 64, 24, 16), (1, 128, 126, 40, 56)]:
+    x = torch.randn(B, H, W, Cin, device=dev)
+    hi, lo = ops.split_bf16(x)
+    wt = torch.randn(N, Cin, 3, 3, device=dev) / (Cin * 9) ** 0.5
+    bias = torch.randn(N, device=dev)
+    Wp = ops.pack_conv(wt, bias, tc=True)
+    out = torch.zeros(B, H, W, (N + 3) // 4 * 4, device=dev)
+    e = ops.make_epilogue(L.EPI_LINEAR, L.tensor_slice(out, None, None, 0, N), act=L.ACT_RELU, bias=Wp.bias)
+    ops.conv2d([L.tensor_slice(None, hi.contiguous(), lo.contiguous())], Wp, e, B, H, W, 'tc')
+    torch.cuda.synchronize()
+    outs.append(out.cpu())
+torch.save(outs, sys.argv[1])
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    res = {}
+    for mode in ("0", "1"):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            env = dict(os.environ, DKT_CONV_PAIR=mode)
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
+            res[mode] = torch.load(f.name)
+    for a, b in zip(res["0"], res["1"]):
+        assert torch.equal(a, b), float((a - b).abs().max())
