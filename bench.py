@@ -32,6 +32,20 @@ RAFT_CFG = dict(model="RAFTStereo", loss_func="sequence_loss_raft", backbone_typ
                 hidden_dims=[128, 128, 128])
 
 METRIC = "stereo pairs/sec @ 544x960, 32 iters"
+IGEV_CFG = dict(model="IGEVStereo", loss_func="sequence_loss_raft", corr_levels=2, corr_radius=4,
+                n_downsample=2, context_norm="batch", slow_fast_gru=False, n_gru_layers=3,
+                hidden_dims=[128, 128, 128], max_disp=192)
+
+
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
+    written by tools/extract_traffic.py); None when that capture is missing."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(kernel_key)
+    except (OSError, ValueError):
+        return None
 
 
 def load_peaks():
@@ -182,11 +196,13 @@ def run_b200(args):
     def step_device():
         return model(im1_d, im2_d, iters=iters, test_mode=True)
 
+    # end to end through the public host API: every step uploads ITS pair of pinned host batches (overlapped with
+    # the previous step's compute by HostPipeline) and reads its disparity maps back into pinned host memory
+    from dkt_stereo_b200.pipeline import HostPipeline
+    pipe = HostPipeline(model, iters=iters)
+
     def step_e2e():
-        a = im1_h.to(dev, non_blocking=True)
-        b = im2_h.to(dev, non_blocking=True)
-        _, up = model(a, b, iters=iters, test_mode=True)
-        return up.to("cpu", non_blocking=False)
+        return pipe.step((im1_h, im2_h))
 
     # warm-up (also builds the CUDA graph on the 2nd call)
     for _ in range(max(args.warmup, 3)):
@@ -235,6 +251,8 @@ def run_b200(args):
         return parallel.all_reduce_max(a.elapsed_time(b), dev)
 
     ms_total = timed(step_device, args.steps)
+    pipe.prefetch(im1_h, im2_h)             # the first batch's upload is the only one outside the timed region ...
+    step_e2e()                              # ... and this untimed step consumes it, so K timed steps = K uploads + K reads
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -260,10 +278,14 @@ def run_b200(args):
     torch.cuda.synchronize()
     zr_ms = sum(a.elapsed_time(b) for a, b in evs) / reps
     tflops = flops_zr / (zr_ms * 1e-3) / 1e12
-    roofline = {"kernel": "conv_tc_kernel (gru08 z||r gates, 3x3 384->256)", "bound": "tensor",
+    tr = ncu_traffic("gru08_zr") if (H, W, Bg) == (544, 960, 8) else None
+    roofline = {"kernel": "conv_tc_pair_kernel<GRU_ZR> (gru08 z||r gates, 3x3 384->256, tcgen05 cta_group::2)", "bound": "tensor",
                 "achieved": tflops, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": tflops / peaks["bf16_burst"],
-                "traffic": None, "ms_per_launch": zr_ms, "flops_per_launch": flops_zr,
-                "note": "useful fp32-equivalent FLOPs; the 3-term bf16 split issues 3x this many MMA flops",
+                "traffic": tr["dram_bytes"] if tr else None, "traffic_source": tr["source"] if tr else None,
+                "issued_frac": 3.0 * tflops / peaks["bf16_burst"],
+                "ms_per_launch": zr_ms, "flops_per_launch": flops_zr,
+                "note": "achieved = useful fp32-equivalent FLOPs; the 3-term bf16 split issues 3x this many MMA flops "
+                        "(issued_frac = tensor-pipe work actually done / peak)",
                 "peak_source": peaks["source"] + ", burst (kernel timed alone)"}
 
     # ---- roofline of the correlation-volume build (K1), HBM bound ----
@@ -359,6 +381,113 @@ def run_b200(args):
     print(json.dumps(out), flush=True)
 
 
+def run_b200_igev(args):
+    """Secondary line (BASELINE configs[2]): IGEV-Stereo forward(test_mode=True), pre-loop modules in PyTorch
+    (SURVEY 8f rank 2), Combined_Geo_Encoding_Volume + GRU loop + upsampling on the library's kernels."""
+    from dkt_stereo_b200 import _lib as L, ops, parallel
+    from dkt_stereo_b200.igev_stereo import IGEVStereo
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    rank, local, world = parallel.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the engine)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+    H, W, iters, Bg = args.height, args.width, args.iters, args.batch
+    h, w = H // 4, W // 4
+    torch.manual_seed(0)
+    model = IGEVStereo(Namespace(mixed_precision=False, corr_implementation="b200", **IGEV_CFG)).eval().to(dev)
+    parallel.broadcast_weights(model, src=0)
+    im1_h, im2_h = synthetic_pair(Bg, H, W, seed=1234 + rank)
+    im1_h, im2_h = im1_h.pin_memory(), im2_h.pin_memory()
+    im1_d, im2_d = im1_h.to(dev), im2_h.to(dev)
+
+    def step_device():
+        return model(im1_d, im2_d, iters=iters, test_mode=True)
+
+    def step_e2e():
+        _, up = model(im1_h.to(dev, non_blocking=True), im2_h.to(dev, non_blocking=True), iters=iters, test_mode=True)
+        return up.to("cpu")
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    model.use_cuda_graph = False             # count the library's launches on one eager pass
+    n0 = L.LAUNCHES
+    step_device()
+    torch.cuda.synchronize()
+    launches_per_step = L.LAUNCHES - n0
+    model.use_cuda_graph = True
+
+    def timed(fn, steps):
+        parallel.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        return parallel.all_reduce_max(a.elapsed_time(b), dev)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms_total = timed(step_device, args.steps)
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    # split: pre-loop (PyTorch) vs hot path (kernels)
+    with torch.no_grad():
+        pre = model.prepare(im1_d, im2_d)
+        torch.cuda.synchronize()
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        pre = model.prepare(im1_d, im2_d)
+        b.record()
+        model.hot_path(*pre, iters)
+        c.record()
+        torch.cuda.synchronize()
+        pre_ms, hot_ms = a.elapsed_time(b), b.elapsed_time(c)
+    # combined lookup (a5) alone on the volumes of the last step; algorithmic bytes of SURVEY 8d
+    eng = model.engine
+    P = Bg * h * w
+    geo, init = model._vol
+    lk_bytes = P * (2 * 9 * 10 * 4 + 4 + 2 * 64 * 2)            # reads + disparity, writes 64 ch bf16 hi/lo (fused convc1)
+    disp = eng.FLOW["f32"].view(Bg, h, w).clone()
+    for _ in range(3):
+        ops.geo_lookup_enc(geo, init, disp, 4, eng.weights["convc1"], eng.cor1_slice())
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        ops.geo_lookup_enc(geo, init, disp, 4, eng.weights["convc1"], eng.cor1_slice())
+    b.record()
+    torch.cuda.synchronize()
+    lk_ms = a.elapsed_time(b) / 20
+    if rank != 0:
+        return
+    out = {
+        "metric": METRIC + " (IGEV-Stereo)", "value": world * Bg * args.steps / (ms_total * 1e-3), "unit": "pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3", "data": "synthetic",
+        "config": {"workload": f"IGEV-Stereo {H}x{W}, {iters} iters, batch {Bg} per GPU (BASELINE configs[2])",
+                   "global_batch": world * Bg, "parallelism": f"dp{world} (batch shards, no steady-state collective)",
+                   "pre_loop": "PyTorch cuDNN fp32 (MobileNetV2 pyramid, GWC volume, 3-D hourglass): next row of SURVEY 8f",
+                   "cache": "volumes (init-corr 376 MB + GEV 602 MB) >> 126 MB L2; no flush needed"},
+        "e2e": {"value": world * Bg * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": 2 * im1_h.numel() * 4, "d2h_bytes_per_step": Bg * H * W * 4},
+        "gpu_launches": launches_per_step * args.steps,
+        "split_ms": {"pre_loop_pytorch": pre_ms, "hot_path_kernels": hot_ms},
+        "roofline": {"kernel": "geo_lookup_kernel<4, ENC> (Combined_Geo_Encoding_Volume lookup + convc1)", "bound": "hbm",
+                     "achieved": lk_bytes / (lk_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": lk_bytes / (lk_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": lk_ms,
+                     "bytes_per_launch": lk_bytes, "peak_source": peaks["source"]},
+        "cpu_baseline": None, "clocks": clocks,
+    }
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -366,6 +495,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--kernels", default="tc", choices=["tc", "simt"])
+    ap.add_argument("--model", default="raft", choices=["raft", "igev"],
+                    help="raft = the headline workload (BASELINE configs[1]); igev = secondary line (configs[2])")
     ap.add_argument("--height", type=int, default=544)
     ap.add_argument("--width", type=int, default=960)
     ap.add_argument("--iters", type=int, default=32)
@@ -377,6 +508,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.model == "igev":
+        run_b200_igev(args)
     else:
         run_b200(args)
 

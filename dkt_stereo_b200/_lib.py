@@ -29,7 +29,8 @@ class DktEpilogue(C.Structure):
                 ("out", DktTensor), ("z", DktTensor), ("h", DktTensor),
                 ("tail", C.c_void_p), ("tail_C", C.c_int32),
                 ("res", C.c_void_p), ("res_C", C.c_int32), ("res_c0", C.c_int32),
-                ("proj", C.c_void_p)]
+                ("proj", C.c_void_p), ("res_hi", C.c_void_p), ("res_lo", C.c_void_p),
+                ("stats_partial", C.c_void_p)]
 
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
@@ -67,6 +68,8 @@ SIGNATURES = {
     "dkt_instnorm_workspace_floats": [_I, _I],
     "dkt_instnorm_stats": [_TP, _P, _P, _F, _I, _I, _I, _P],
     "dkt_instnorm_apply": [_TP, _P, _TP, _TP, _I, _I, _I, _I, _P],
+    "dkt_instnorm_tiles_workspace_floats": [_I, _I],
+    "dkt_instnorm_finalize_tiles": [_P, _P, _P, _F, _I, _I, _I, _I, _P],
     "dkt_split_nchw_to_nhwc_bf16x2": [_P, _I64, _I64, _I64, _I64, _P, _P, _I, _I, _I, _I, _P],
 }
 

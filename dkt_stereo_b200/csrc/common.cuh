@@ -32,6 +32,18 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// 4 consecutive channels of a bf16 (hi, lo) pair -> fp32 (hi + lo); read-only (non-coherent) path
+__device__ __forceinline__ float4 load_split4(const uint16_t* hi, const uint16_t* lo, int64_t off) {
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(hi + off));
+    const uint2 l = __ldg(reinterpret_cast<const uint2*>(lo + off));
+    float4 r;
+    r.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+    r.y = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+    r.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+    r.w = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+    return r;
+}
+
 // ---- activations.  expf / tanhf (not the __ intrinsics): the recurrence is sensitive ----
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 

@@ -39,6 +39,8 @@ using namespace tc;
 
 constexpr int TC_TILE_W = 16, TC_TILE_H = 8;
 constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_MAX_ACC = 8;           // accumulator stages (tmem_full / tmem_empty barrier pairs)
+constexpr uint32_t TC_BAR_BYTES = 512;  // barrier block at the end of the dynamic shared memory
 
 struct TcConvParams {
     CUtensorMap act[DKT_MAX_SRCS][2];   // [source][hi/lo], 4-D (C, W, H, B)
@@ -52,6 +54,7 @@ struct TcConvParams {
     int num_tiles;
     int stages;
     uint32_t acc_cols;              // TMEM columns per accumulator stage
+    uint32_t acc_stages;            // accumulator stages in TMEM: 2 (N > 128), 4 (N <= 128), 8 (N <= 64)
     // patch kernel: one A stage = a (TILE_H + ygroup - 1)-row halo patch serving `ygroup` vertical taps
     int ygroup, a_stages, w_stages;
     uint32_t a_part_bytes;          // bytes of one precision (hi or lo) of an A stage
@@ -67,7 +70,11 @@ struct TileWalk {
     uint32_t empty_remote;      // shared::cluster address of the LEADER's tmem_empty_bar[0]; 0 = arrive locally
 };
 
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// Epilogue operands (context term, gates, hidden state, residual) go through the read-only path: every element is
+// read by the one thread that later stores to it (h' may overwrite h in place), never by another, so a
+// non-coherent line can only ever be stale in elements nobody reads again.  What it buys: the loads no longer alias
+// the stores as far as the compiler knows, so all of a chunk's loads are in flight before the first store.
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // compile-time activation (the runtime switch of apply_act gets if-converted into ~50 issued instructions per value)
 template <int ACT>
@@ -85,6 +92,10 @@ __device__ __noinline__ void tc_epilogue1(const dkt_epilogue& e, int64_t p, int 
     if (e.ctx) a += e.ctx[p * e.ctx_C + e.ctx_c0 + n];
     a = act_ct<ACT>(a) * e.scale;
     if (e.res) a = fmaxf(a + e.res[p * e.res_C + e.res_c0 + n], 0.f);
+    else if (e.res_hi) {
+        const int64_t off = p * e.res_C + e.res_c0 + n;
+        a = fmaxf(a + __uint_as_float((uint32_t)e.res_hi[off] << 16) + __uint_as_float((uint32_t)e.res_lo[off] << 16), 0.f);
+    }
     store_all(e.out, p, n, a);
 }
 
@@ -93,7 +104,8 @@ __device__ __noinline__ void tc_epilogue1(const dkt_epilogue& e, int64_t p, int 
 // ---------------------------------------------------------------------------------------------
 constexpr int TC2_THREADS = 320;
 constexpr int TC2_EPI_WARPS = 8;
-constexpr uint32_t TC2_EPI_BYTES = TC2_EPI_WARPS * 32 * 128;     // one 32 px x 32 ch fp32 tile per warp
+constexpr uint32_t TC2_EPI_TILE_BYTES = TC2_EPI_WARPS * 32 * 128;   // one 32 px x 32 ch fp32 tile per warp
+constexpr uint32_t TC2_EPI_BYTES = TC2_EPI_TILE_BYTES + 1024;        // + the conv bias (256 floats, zero beyond N)
 
 template <int BK>
 __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr) {
@@ -136,6 +148,8 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
     const float* const bias = e.bias;
     const float* const ctx = e.ctx;
     const float* const res = (KIND == DKT_EPI_LINEAR) ? e.res : nullptr;
+    const uint16_t* const res_hi = (KIND == DKT_EPI_LINEAR && !e.res) ? e.res_hi : nullptr;
+    const uint16_t* const res_lo = e.res_lo;
     const float* const tail = (KIND == DKT_EPI_LINEAR) ? e.tail : nullptr;
     const int tail_C = e.tail_C;
     const float scale = e.scale;
@@ -148,7 +162,18 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
     // N % 4 != 0 conv is merged into that group's vector store; otherwise it is copied after the chunk loop
     const bool tail_merged = tail && (N & 3) && (((N + tail_C) & 3) == 0) && tail_C < 4;
     const int Nvec = tail_merged ? N + tail_C : N;
-    uint32_t t = 0;
+    // per-tile channel statistics of the stored values (InstanceNorm fused into the producing conv; LINEAR only)
+    float* const stats_out = (KIND == DKT_EPI_LINEAR) ? e.stats_partial : nullptr;
+    // the bias lives in shared memory: a global load here would sit in the latency chain of every chunk
+    float* const s_bias = reinterpret_cast<float*>(epi_smem + TC2_EPI_TILE_BYTES);
+    if (KIND == DKT_EPI_LINEAR) {
+        for (int i = (int)threadIdx.x - 64; i < 256; i += TC2_EPI_WARPS * 32) s_bias[i] = (i < N && bias) ? __ldg(bias + i) : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    // accumulator stages: the MMA warp may run acc_stages - 1 tiles ahead of this drain, which hides the
+    // commit -> wake-up and arrive -> wake-up latencies of the hand-off (they bounded the N <= 128 convs at 2 stages)
+    const uint32_t nacc = prm.acc_stages;
+    uint32_t t = 0, as = 0, aphase = 0;
     for (int item = tw.first; item < tw.items; item += tw.step, ++t) {
         const int tile = item * tw.mul + tw.off;
         const bool live = tile < prm.num_tiles;          // the odd tile count's filler of a CTA pair is drained, not stored
@@ -156,7 +181,6 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
         const int r = tile - b * tiles_per_img;
         const int ty = r / prm.tiles_x;
         const int y0 = ty * TC_TILE_H, x0 = (r - ty * prm.tiles_x) * TC_TILE_W;
-        const uint32_t as = t & 1u, aphase = (t >> 1) & 1u;
         // this lane's 8 pixels: row = i*4 + sub of the warp's quarter -> (y, x) = (y0 + 2q + (i>>2), x0 + (i&3)*4 + sub)
         const int64_t p00 = ((int64_t)b * H + y0 + 2 * q) * W + x0 + sub;
         const bool yok0 = (y0 + 2 * q) < H, yok1 = (y0 + 2 * q + 1) < H;
@@ -182,74 +206,102 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                     make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             __syncwarp();
             const int n = c0 + 4 * jg;
-            if (n >= Nvec) continue;            // padded columns (lane-divergent only in the last chunk)
+            float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = make_float4(0.f, 0.f, 0.f, 0.f);
             const bool vec = (n + 3 < Nvec);
-            if (KIND != DKT_EPI_LINEAR || vec) {
+            if (n >= Nvec) {
+                // padded columns (lane-divergent only in the last chunk): nothing to store
+            } else if (KIND != DKT_EPI_LINEAR || vec) {
                 // ---------------- vector path: 4 channels x 8 pixels per lane ----------------
                 float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                 int ntail = 0;                   // components of this group that come from the tail
                 if (KIND == DKT_EPI_LINEAR) {
-                    if (n + 3 < N) {
-                        if (bias) bv = ld4(bias + n);
-                    } else {                     // the merged-tail group
-                        ntail = n + 4 - N;
-                        if (bias) {
-                            bv.x = bias[n];
-                            if (n + 1 < N) bv.y = bias[n + 1];
-                            if (n + 2 < N) bv.z = bias[n + 2];
-                        }
-                    }
+                    bv = *reinterpret_cast<const float4*>(s_bias + n);      // zero beyond N
+                    if (n + 3 >= N) ntail = n + 4 - N;                     // the merged-tail group
                 }
+                // two batches of 4 pixels (tile rows 2q and 2q + 1): all global loads of a batch are issued before
+                // its math and stores, so their latencies overlap (stores may alias the loads as far as the compiler
+                // knows, which used to serialise one load round trip per pixel)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = i * 4 + sub;
-                    const int xo = (i & 3) * 4;
-                    if (!((i < 4 ? yok0 : yok1) && (x0 + xo + sub) < W)) continue;
-                    const int64_t p = p00 + xo + (i < 4 ? 0 : W);
-                    float4 a = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
-                    if (KIND == DKT_EPI_LINEAR) {
-                        a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
-                        if (ctx) { const float4 c = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n); a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; }
-                        a.x = act_ct<ACT>(a.x) * scale; a.y = act_ct<ACT>(a.y) * scale;
-                        a.z = act_ct<ACT>(a.z) * scale; a.w = act_ct<ACT>(a.w) * scale;
-                        if (res) {               // residual block tail: relu(x + y)
-                            const float4 rr = ld4(res + p * e.res_C + e.res_c0 + n);
-                            a.x = fmaxf(a.x + rr.x, 0.f); a.y = fmaxf(a.y + rr.y, 0.f);
-                            a.z = fmaxf(a.z + rr.z, 0.f); a.w = fmaxf(a.w + rr.w, 0.f);
+                for (int hb = 0; hb < 2; ++hb) {
+                    const bool yok = hb ? yok1 : yok0;
+                    const int64_t pb = p00 + (hb ? W : 0);
+                    float4 av[4], cv[4], zv[4], hv[4];
+                    float tv[4][3];
+                    bool ok[4];
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const int row = hb * 16 + i4 * 4 + sub;
+                        ok[i4] = yok && (x0 + i4 * 4 + sub) < W;
+                        if (!ok[i4]) continue;
+                        const int64_t p = pb + i4 * 4;
+                        av[i4] = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
+                        if (KIND == DKT_EPI_LINEAR) {
+                            if (ctx) cv[i4] = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n);
+                            if (res) hv[i4] = ld4(res + p * e.res_C + e.res_c0 + n);
+                            else if (res_hi) hv[i4] = load_split4(res_hi, res_lo, p * e.res_C + e.res_c0 + n);
+                            if (ntail) {
+                                const float* tp = tail + p * tail_C;
+                                tv[i4][0] = tp[0];
+                                if (ntail > 1) tv[i4][1] = tp[1];
+                                if (ntail > 2) tv[i4][2] = tp[2];
+                            }
+                        } else if (KIND == DKT_EPI_GRU_ZR) {
+                            cv[i4] = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n);
+                            if (n >= Nh) hv[i4] = ld4(e.h.f32 + p * e.h.C + e.h.c_begin + (n - Nh));
+                        } else {
+                            cv[i4] = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n);
+                            zv[i4] = ld4(e.z.f32 + p * e.z.C + e.z.c_begin + n);
+                            hv[i4] = ld4(e.h.f32 + p * e.h.C + e.h.c_begin + n);
                         }
-                        if (ntail) {             // 1..3 trailing components are copied from the tail tensor
-                            const float* tp = tail + p * tail_C;
-                            if (ntail == 1) a.w = tp[0];
-                            else if (ntail == 2) { a.z = tp[0]; a.w = tp[1]; }
-                            else { a.y = tp[0]; a.z = tp[1]; a.w = tp[2]; }
-                        }
-                    } else if (KIND == DKT_EPI_GRU_ZR) {
-                        const float4 c = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n);
-                        a.x = sigmoidf_acc(a.x + c.x); a.y = sigmoidf_acc(a.y + c.y);
-                        a.z = sigmoidf_acc(a.z + c.z); a.w = sigmoidf_acc(a.w + c.w);
-                        if (n < Nh) {
-                            *reinterpret_cast<float4*>(e.z.f32 + p * e.z.C + e.z.c_begin + n) = a;
-                            continue;
-                        }
-                        const float4 h = ld4(e.h.f32 + p * e.h.C + e.h.c_begin + (n - Nh));
-                        a.x *= h.x; a.y *= h.y; a.z *= h.z; a.w *= h.w;
-                    } else {                     // GRU_Q
-                        const float4 c = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n);
-                        const float4 z = ld4(e.z.f32 + p * e.z.C + e.z.c_begin + n);
-                        const float4 h = ld4(e.h.f32 + p * e.h.C + e.h.c_begin + n);
-                        a.x = (1.f - z.x) * h.x + z.x * tanhf(a.x + c.x);
-                        a.y = (1.f - z.y) * h.y + z.y * tanhf(a.y + c.y);
-                        a.z = (1.f - z.z) * h.z + z.z * tanhf(a.z + c.z);
-                        a.w = (1.f - z.w) * h.w + z.w * tanhf(a.w + c.w);
                     }
-                    const int64_t off = p * oC + oc0 + (KIND == DKT_EPI_GRU_ZR ? n - Nh : n);
-                    if (o_f32) *reinterpret_cast<float4*>(o_f32 + off) = a;
-                    if (o_hi) {
-                        uint32_t h0, l0, h1, l1;
-                        split_bf16x2(a.x, a.y, h0, l0);
-                        split_bf16x2(a.z, a.w, h1, l1);
-                        *reinterpret_cast<uint2*>(o_hi + off) = make_uint2(h0, h1);
-                        if (o_lo) *reinterpret_cast<uint2*>(o_lo + off) = make_uint2(l0, l1);
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        if (!ok[i4]) continue;
+                        const int64_t p = pb + i4 * 4;
+                        float4 a = av[i4];
+                        if (KIND == DKT_EPI_LINEAR) {
+                            a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
+                            if (ctx) { a.x += cv[i4].x; a.y += cv[i4].y; a.z += cv[i4].z; a.w += cv[i4].w; }
+                            a.x = act_ct<ACT>(a.x) * scale; a.y = act_ct<ACT>(a.y) * scale;
+                            a.z = act_ct<ACT>(a.z) * scale; a.w = act_ct<ACT>(a.w) * scale;
+                            if (res || res_hi) {     // residual block tail: relu(x + y)
+                                a.x = fmaxf(a.x + hv[i4].x, 0.f); a.y = fmaxf(a.y + hv[i4].y, 0.f);
+                                a.z = fmaxf(a.z + hv[i4].z, 0.f); a.w = fmaxf(a.w + hv[i4].w, 0.f);
+                            }
+                            if (ntail) {             // 1..3 trailing components are copied from the tail tensor
+                                if (ntail == 1) a.w = tv[i4][0];
+                                else if (ntail == 2) { a.z = tv[i4][0]; a.w = tv[i4][1]; }
+                                else { a.y = tv[i4][0]; a.z = tv[i4][1]; a.w = tv[i4][2]; }
+                            }
+                        } else if (KIND == DKT_EPI_GRU_ZR) {
+                            a.x = sigmoidf_acc(a.x + cv[i4].x); a.y = sigmoidf_acc(a.y + cv[i4].y);
+                            a.z = sigmoidf_acc(a.z + cv[i4].z); a.w = sigmoidf_acc(a.w + cv[i4].w);
+                            if (n < Nh) {
+                                *reinterpret_cast<float4*>(e.z.f32 + p * e.z.C + e.z.c_begin + n) = a;
+                                continue;
+                            }
+                            a.x *= hv[i4].x; a.y *= hv[i4].y; a.z *= hv[i4].z; a.w *= hv[i4].w;
+                        } else {                     // GRU_Q
+                            const float4 z = zv[i4], h = hv[i4];
+                            a.x = (1.f - z.x) * h.x + z.x * tanhf(a.x + cv[i4].x);
+                            a.y = (1.f - z.y) * h.y + z.y * tanhf(a.y + cv[i4].y);
+                            a.z = (1.f - z.z) * h.z + z.z * tanhf(a.z + cv[i4].z);
+                            a.w = (1.f - z.w) * h.w + z.w * tanhf(a.w + cv[i4].w);
+                        }
+                        if (KIND == DKT_EPI_LINEAR && stats_out) {
+                            ssum.x += a.x; ssum.y += a.y; ssum.z += a.z; ssum.w += a.w;
+                            ssq.x = fmaf(a.x, a.x, ssq.x); ssq.y = fmaf(a.y, a.y, ssq.y);
+                            ssq.z = fmaf(a.z, a.z, ssq.z); ssq.w = fmaf(a.w, a.w, ssq.w);
+                        }
+                        const int64_t off = p * oC + oc0 + (KIND == DKT_EPI_GRU_ZR ? n - Nh : n);
+                        if (o_f32) *reinterpret_cast<float4*>(o_f32 + off) = a;
+                        if (o_hi) {
+                            uint32_t h0, l0, h1, l1;
+                            split_bf16x2(a.x, a.y, h0, l0);
+                            split_bf16x2(a.z, a.w, h1, l1);
+                            *reinterpret_cast<uint2*>(o_hi + off) = make_uint2(h0, h1);
+                            if (o_lo) *reinterpret_cast<uint2*>(o_lo + off) = make_uint2(l0, l1);
+                        }
                     }
                 }
             } else {
@@ -262,6 +314,22 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                     const float4 a = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
                     const float av[4] = {a.x, a.y, a.z, a.w};
                     for (int u = 0; u < 4; ++u) if (n + u < N) tc_epilogue1<ACT>(e, p, n + u, av[u]);
+                }
+            }
+            if (KIND == DKT_EPI_LINEAR && stats_out) {
+                // fixed-order reduction (deterministic): 8 pixels per lane above, then the warp's 4 pixel groups by
+                // shuffles; the warp's 32-pixel sums go straight to HBM ([tile][quarter][sum, sumsq][N]) -- no cross-warp
+                // exchange in the epilogue; quarters and tiles are added up by dkt_instnorm_finalize_tiles
+                float r[8] = {ssum.x, ssum.y, ssum.z, ssum.w, ssq.x, ssq.y, ssq.z, ssq.w};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    r[u] += __shfl_xor_sync(0xffffffffu, r[u], 8);
+                    r[u] += __shfl_xor_sync(0xffffffffu, r[u], 16);
+                }
+                if (sub == 0 && n < N) {
+                    float* sp = stats_out + (((int64_t)tile * 4 + q) * 2) * N + n;
+                    *reinterpret_cast<float4*>(sp) = make_float4(r[0], r[1], r[2], r[3]);
+                    *reinterpret_cast<float4*>(sp + N) = make_float4(r[4], r[5], r[6], r[7]);
                 }
             }
         }
@@ -279,6 +347,7 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
             if (tw.empty_remote) mbar_arrive_cluster(tw.empty_remote + as * 8u);
             else mbar_arrive(&tmem_empty_bar[as]);
         }
+        if (++as == nacc) { as = 0; aphase ^= 1u; }
     }
 }
 
@@ -306,14 +375,14 @@ __device__ __forceinline__ void conv_tc_epilogue_proj(const TcConvParams& prm, u
     for (int i = et; i < 256 * DKT_PROJ_LD; i += TC2_EPI_WARPS * 32) s_w[i] = (i < N * DKT_PROJ_LD) ? __ldg(e.proj + i) : 0.f;
     for (int i = et; i < 256; i += TC2_EPI_WARPS * 32) s_b[i] = (i < N && e.bias) ? __ldg(e.bias + i) : 0.f;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    uint32_t t = 0;
+    const uint32_t nacc = prm.acc_stages;
+    uint32_t t = 0, as = 0, aphase = 0;
     for (int item = tw.first; item < tw.items; item += tw.step, ++t) {
         const int tile = item * tw.mul + tw.off;
         const bool live = tile < prm.num_tiles;
         const int b = tile / tiles_per_img;
         const int r = tile - b * tiles_per_img;
         const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
-        const uint32_t as = t & 1u, aphase = (t >> 1) & 1u;
         mbar_wait(&tmem_full_bar[as], aphase);
         tcgen05_fence_after();
         const uint32_t tbase = tmem_base + as * prm.acc_cols + ((uint32_t)(q * 32) << 16);
@@ -353,6 +422,7 @@ __device__ __forceinline__ void conv_tc_epilogue_proj(const TcConvParams& prm, u
             if (tw.empty_remote) mbar_arrive_cluster(tw.empty_remote + as * 8u);
             else mbar_arrive(&tmem_empty_bar[as]);
         }
+        if (++as == nacc) { as = 0; aphase ^= 1u; }
         if (!live) continue;                          // uniform over the CTA: both warps of a quarter skip the exchange
         float* xb = s_x + ((t & 1u) * 128 + q * 32 + lane) * DKT_PROJ_LD;
         if (half == 1) {
@@ -391,9 +461,9 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
     uint8_t* epi_smem = smem + (size_t)prm.stages * stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + TC2_EPI_BYTES);
     uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
-    uint64_t* tmem_full_bar = empty_bar + TC_MAX_STAGES;     // [2]
-    uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* tmem_full_bar = empty_bar + TC_MAX_STAGES;     // [TC_MAX_ACC]
+    uint64_t* tmem_empty_bar = tmem_full_bar + TC_MAX_ACC;   // [TC_MAX_ACC]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + TC_MAX_ACC);
 
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
 
@@ -406,10 +476,10 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
         tma_prefetch_desc(&prm.wgt[0]);
         tma_prefetch_desc(&prm.wgt[1]);
         for (int s = 0; s < prm.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], TC2_EPI_WARPS); }
+        for (int s = 0; s < (int)prm.acc_stages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], TC2_EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * prm.acc_cols);
+    if (warp == 1) tmem_alloc(tmem_slot, prm.tmem_cols);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -451,9 +521,8 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
         const uint32_t idesc = idesc_bf16_m128((uint32_t)prm.Npad);
         int stage = 0;
         uint32_t phase = 0;
-        uint32_t t = 0;
-        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
-            const uint32_t as = t & 1u, aphase = (t >> 1) & 1u;
+        uint32_t as = 0, aphase = 0;
+        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
             mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);          // epilogue drained this accumulator
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + as * prm.acc_cols;
@@ -475,6 +544,7 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
                 if (++stage == prm.stages) { stage = 0; phase ^= 1u; }
             }
             if (elect_one()) umma_commit(&tmem_full_bar[as]);     // accumulator complete
+            if (++as == prm.acc_stages) { as = 0; aphase ^= 1u; }
         }
     } else {
         const TileWalk tw{(int)blockIdx.x, (int)gridDim.x, prm.num_tiles, 1, 0, 0u};
@@ -486,7 +556,7 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
 
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * prm.acc_cols);
+    if (warp == 1) tmem_dealloc(tmem_base, prm.tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -519,9 +589,9 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
     uint64_t* aempty = afull + TCP_MAX_A;
     uint64_t* wfull = aempty + TCP_MAX_A;
     uint64_t* wempty = wfull + TCP_MAX_W;
-    uint64_t* tmem_full_bar = wempty + TCP_MAX_W;            // [2]
-    uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* tmem_full_bar = wempty + TCP_MAX_W;            // [TC_MAX_ACC]
+    uint64_t* tmem_empty_bar = tmem_full_bar + TC_MAX_ACC;   // [TC_MAX_ACC]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + TC_MAX_ACC);
 
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int ygroups = prm.kh / prm.ygroup;                 // A steps per (kb, kx)
@@ -532,10 +602,10 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
         tma_prefetch_desc(&prm.wgt[1]);
         for (int s = 0; s < prm.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < prm.w_stages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], TC2_EPI_WARPS); }
+        for (int s = 0; s < (int)prm.acc_stages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], TC2_EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * prm.acc_cols);
+    if (warp == 1) tmem_alloc(tmem_slot, prm.tmem_cols);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -590,12 +660,11 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
         // ===== MMA issuer =====
         const uint32_t idesc = idesc_bf16_m128((uint32_t)prm.Npad);
         int as = 0, ws = 0;
-        uint32_t aph = 0, wph = 0, t = 0;
+        uint32_t aph = 0, wph = 0, acs = 0, aphase = 0;
         int kb_total = 0;
         for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
         const int a_steps = kb_total * prm.kw * ygroups;
-        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
-            const uint32_t acs = t & 1u, aphase = (t >> 1) & 1u;
+        for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
             mbar_wait(&tmem_empty_bar[acs], aphase ^ 1u);
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + acs * prm.acc_cols;
@@ -631,6 +700,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
                 if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
             }
             if (elect_one()) umma_commit(&tmem_full_bar[acs]);
+            if (++acs == prm.acc_stages) { acs = 0; aphase ^= 1u; }
         }
     } else {
         const TileWalk tw{(int)blockIdx.x, (int)gridDim.x, prm.num_tiles, 1, 0, 0u};
@@ -642,7 +712,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
 
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * prm.acc_cols);
+    if (warp == 1) tmem_dealloc(tmem_base, prm.tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -652,7 +722,8 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
 // reads A from both CTAs and the two B halves from both CTAs.  Why: after the epilogue was specialised every
 // conv of the step sat at 8.5 - 10.5 TB/s of L2 -> SM traffic (ncu r01g, l1tex__m_xbar2l1tex_read_bytes), the
 // cap of the L2 fabric, and the weight stream was most of it (3.5 MB of 4.3 MB per tile for the gru08 gates).
-// Halving the weight bytes per SM also doubles the K depth a weight stage holds; filters whose half fits
+// KB = channels per K block: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows; the 7x7 stems, whose x-im2col
+// rows carry 21 / 14 real channels).  Halving the weight bytes per SM also doubles the K depth a weight stage holds; filters whose half fits
 // (3x3 / 7x1 at 64 -> 64) stay resident in the ring for the whole launch (`w_resident`).
 //   barriers   afull / wfull / tmem_empty live in the LEADER (cluster rank 0): both producers' TMA bytes are
 //              counted there (the leader arms 2x the stage bytes), the follower's epilogue warps arrive remotely;
@@ -660,7 +731,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
 //   roles      warp 0 = TMA producer (both CTAs), warp 1 = MMA issuer (leader only; allocates TMEM in both),
 //              warps 2..9 = epilogue of the CTA's own tile (TMEM lanes 0..127 of each CTA = its 128 pixels).
 // ---------------------------------------------------------------------------------------------
-template <int KIND, int ACT>
+template <int KIND, int ACT, int KB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
     extern __shared__ uint8_t smem_raw[];
@@ -668,7 +739,8 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
 
     const int Nh = prm.Npad >> 1;                                   // weight rows staged by this CTA
     const uint32_t a_part = prm.a_part_bytes, a_stage_bytes = 2u * prm.a_part_bytes;
-    const uint32_t b_bytes = (uint32_t)Nh * 128u, w_stage_bytes = 2u * b_bytes;     // K block of 64 channels
+    constexpr uint32_t KROW = KB * 2;                               // bytes of one K block row (128 or 64) == swizzle span
+    const uint32_t b_bytes = (uint32_t)Nh * KROW, w_stage_bytes = 2u * b_bytes;    // K block of KB channels
     uint8_t* a_ring = smem;
     uint8_t* w_ring = a_ring + (size_t)prm.a_stages * a_stage_bytes;
     uint8_t* epi_smem = w_ring + (size_t)prm.w_stages * w_stage_bytes;
@@ -676,9 +748,9 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
     uint64_t* aempty = afull + TCP_MAX_A;
     uint64_t* wfull = aempty + TCP_MAX_A;
     uint64_t* wempty = wfull + TCP_MAX_W;
-    uint64_t* tmem_full_bar = wempty + TCP_MAX_W;            // [2]
-    uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* tmem_full_bar = wempty + TCP_MAX_W;            // [TC_MAX_ACC]
+    uint64_t* tmem_empty_bar = tmem_full_bar + TC_MAX_ACC;   // [TC_MAX_ACC]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + TC_MAX_ACC);
 
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -693,10 +765,10 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
         tma_prefetch_desc(&prm.wgt[1]);
         for (int s = 0; s < prm.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < prm.w_stages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 2 * TC2_EPI_WARPS); }
+        for (int s = 0; s < (int)prm.acc_stages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 2 * TC2_EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc_pair(tmem_slot, 2 * prm.acc_cols);
+    if (warp == 1) tmem_alloc_pair(tmem_slot, prm.tmem_cols);
     tcgen05_fence_before();
     __syncthreads();
     cluster_sync_all();                                      // both CTAs' barriers and TMEM exist before any remote access
@@ -720,7 +792,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
             int kofs = 0;
             for (int s = 0; s < prm.nsrc; ++s) {
                 for (int kb = 0; kb < prm.kblocks[s]; ++kb) {
-                    const int c = prm.c_begin[s] + kb * 64;
+                    const int c = prm.c_begin[s] + kb * KB;
                     for (int kx = 0; kx < prm.kw; ++kx) {
                         const int xs = x0 + kx - prm.pad_x;
                         for (int yg = 0; yg < ygroups; ++yg) {
@@ -740,7 +812,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                                     if (elect_one()) {
                                         uint8_t* wst = w_ring + (size_t)ws * w_stage_bytes;
                                         if (leader) mbar_arrive_expect_tx(&wfull[ws], 2u * w_stage_bytes);
-                                        const int kc = kofs + kb * 64;
+                                        const int kc = kofs + kb * KB;
                                         tma_load_2d_pair(wst, &prm.wgt[0], wfull_l + ws * 8u, kc, tap * prm.Npad + wrow0);
                                         tma_load_2d_pair(wst + b_bytes, &prm.wgt[1], wfull_l + ws * 8u, kc, tap * prm.Npad + wrow0);
                                     }
@@ -750,7 +822,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                         }
                     }
                 }
-                kofs += prm.kblocks[s] * 64;
+                kofs += prm.kblocks[s] * KB;
             }
             first = false;
         }
@@ -759,13 +831,12 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
             // ===== MMA issuer (leader): M = 256 over both CTAs' tiles =====
             const uint32_t idesc = idesc_bf16_m256((uint32_t)prm.Npad);
             int as = 0, ws = 0;
-            uint32_t aph = 0, wph = 0, t = 0;
+            uint32_t aph = 0, wph = 0, acs = 0, aphase = 0;
             int kb_total = 0;
             for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
             const int a_steps = kb_total * prm.kw * ygroups;
             bool first = true;
-            for (int item = pair_id; item < items; item += pairs, ++t) {
-                const uint32_t acs = t & 1u, aphase = (t >> 1) & 1u;
+            for (int item = pair_id; item < items; item += pairs) {
                 mbar_wait(&tmem_empty_bar[acs], aphase ^ 1u);     // both CTAs' epilogues drained this accumulator
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acs * prm.acc_cols;
@@ -775,17 +846,17 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                     tcgen05_fence_after();
                     const uint32_t a_hi0 = smem_u32(a_ring + (size_t)as * a_stage_bytes);
                     for (int kyi = 0; kyi < prm.ygroup; ++kyi) {
-                        const uint32_t a_hi = a_hi0 + (uint32_t)kyi * (TC_TILE_W * 128u);
+                        const uint32_t a_hi = a_hi0 + (uint32_t)kyi * (TC_TILE_W * KROW);
                         if (!prm.w_resident || first) {
                             mbar_wait(&wfull[ws], wph);
                             tcgen05_fence_after();
                         }
                         if (elect_one()) {
                             const uint32_t w_hi = smem_u32(w_ring + (size_t)ws * w_stage_bytes);
-                            const uint64_t dah = smem_desc_kmajor<64>(a_hi), dal = smem_desc_kmajor<64>(a_hi + a_part);
-                            const uint64_t dwh = smem_desc_kmajor<64>(w_hi), dwl = smem_desc_kmajor<64>(w_hi + b_bytes);
+                            const uint64_t dah = smem_desc_kmajor<KB>(a_hi), dal = smem_desc_kmajor<KB>(a_hi + a_part);
+                            const uint64_t dwh = smem_desc_kmajor<KB>(w_hi), dwl = smem_desc_kmajor<KB>(w_hi + b_bytes);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {         // +32 bytes per K16 step = +2 in the address field
+                            for (int k = 0; k < KB / 16; ++k) {   // +32 bytes per K16 step = +2 in the address field
                                 umma_bf16_pair(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, accumulate);
                                 umma_bf16_pair(tmem_d, dal + 2 * k, dwh + 2 * k, idesc, 1u);
                                 umma_bf16_pair(tmem_d, dah + 2 * k, dwl + 2 * k, idesc, 1u);
@@ -800,6 +871,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                     if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
                 }
                 if (elect_one()) umma_commit_pair(&tmem_full_bar[acs]);
+                if (++acs == prm.acc_stages) { acs = 0; aphase ^= 1u; }
                 first = false;
             }
         }
@@ -815,7 +887,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
     tcgen05_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 1) tmem_dealloc_pair(tmem_base, 2 * prm.acc_cols);
+    if (warp == 1) tmem_dealloc_pair(tmem_base, prm.tmem_cols);
 }
 
 }  // namespace dkt
@@ -825,7 +897,7 @@ using namespace dkt;
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ---- launch: one instantiation per (kernel family, epilogue kind, activation) ----
-enum ConvFamily { FAM_PATCH32, FAM_PATCH64, FAM_TAP64, FAM_PAIR };
+enum ConvFamily { FAM_PATCH32, FAM_PATCH64, FAM_TAP64, FAM_PAIR, FAM_PAIR_K32 };
 
 template <int KIND, int ACT>
 static int launch_conv_ka(ConvFamily fam, const TcConvParams& prm, unsigned grid, size_t smem_bytes, cudaStream_t st) {
@@ -834,14 +906,24 @@ static int launch_conv_ka(ConvFamily fam, const TcConvParams& prm, unsigned grid
         cudaError_t ce = cudaFuncSetAttribute(conv_tc_patch_kernel<32, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_patch_kernel<64, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<64, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_pair_kernel<KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_pair_kernel<KIND, ACT, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (KIND == DKT_EPI_LINEAR && (ACT == DKT_ACT_NONE || ACT == DKT_ACT_RELU) && ce == cudaSuccess)
+            ce = cudaFuncSetAttribute(conv_tc_pair_kernel<KIND, ACT, (KIND == DKT_EPI_LINEAR && (ACT == DKT_ACT_NONE || ACT == DKT_ACT_RELU)) ? 32 : 64>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce != cudaSuccess) return (int)ce;
         attr_set = true;
     }
     switch (fam) {
         case FAM_PATCH32: conv_tc_patch_kernel<32, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
         case FAM_PATCH64: conv_tc_patch_kernel<64, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
-        case FAM_PAIR:    conv_tc_pair_kernel<KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;   // grid even (cluster of 2)
+        case FAM_PAIR:    conv_tc_pair_kernel<KIND, ACT, 64><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;   // grid even (cluster of 2)
+        case FAM_PAIR_K32:                           // 32-channel K blocks: instantiated for the stems' epilogues only
+            if constexpr (KIND == DKT_EPI_LINEAR && (ACT == DKT_ACT_NONE || ACT == DKT_ACT_RELU)) {
+                conv_tc_pair_kernel<KIND, ACT, 32><<<grid, TC2_THREADS, smem_bytes, st>>>(prm);
+                break;
+            } else {
+                return DKT_E_UNSUPPORTED;
+            }
         default:          conv_tc_kernel<64, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
     }
     DKT_RETURN_LAST();
@@ -881,6 +963,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     const dkt_epilogue& e = *epi;
     if (e.kind == DKT_EPI_LINEAR) {
         DKT_CHECK_ARG(e.out.f32 || e.out.hi);
+        if (e.stats_partial && ((N % 32) || e.tail)) return DKT_E_UNSUPPORTED;
     } else if (e.kind == DKT_EPI_PROJ) {
         DKT_CHECK_ARG(e.proj && e.out.f32 && e.out.c_count >= DKT_PROJ_LD);
         if ((e.out.C % 4) || (e.out.c_begin % 4) || !aligned16(e.proj)) return DKT_E_ALIGNMENT;
@@ -895,6 +978,11 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     if (N >= 4 && ((e.out.C % 4) || (e.out.c_begin % 4))) return DKT_E_ALIGNMENT;
     if (e.ctx && ((e.ctx_C % 4) || (e.ctx_c0 % 4) || !aligned16(e.ctx))) return DKT_E_ALIGNMENT;
     if (e.res && ((e.res_C % 4) || (e.res_c0 % 4) || !aligned16(e.res))) return DKT_E_ALIGNMENT;
+    if (!e.res && e.res_hi) {
+        DKT_CHECK_ARG(e.res_lo != nullptr);
+        if ((e.res_C % 4) || (e.res_c0 % 4) || (reinterpret_cast<uintptr_t>(e.res_hi) & 7) || (reinterpret_cast<uintptr_t>(e.res_lo) & 7))
+            return DKT_E_ALIGNMENT;
+    }
     if (e.bias && !aligned16(e.bias)) return DKT_E_ALIGNMENT;
     if (!aligned16(e.out.f32) || !aligned16(e.out.hi) || !aligned16(e.out.lo)) return DKT_E_ALIGNMENT;
 
@@ -910,22 +998,25 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         return n;
     }();
     const int Npad = (N + 15) / 16 * 16;
-    const uint32_t budget = 227u * 1024u - 1024u /*align*/ - TC2_EPI_BYTES - 256u /*barriers*/;
+    const uint32_t budget = 227u * 1024u - 1024u /*align*/ - TC2_EPI_BYTES - TC_BAR_BYTES;
 
     // ring geometry of the row-patch kernel
     const int ygroup = (stride == 1) ? kh : 1;
     const int rows_loaded = (stride == 1) ? TC_TILE_H + ygroup - 1 : TC_TILE_H;
-    const uint32_t a_part_bytes = (uint32_t)rows_loaded * TC_TILE_W * 128u;
     int cin_sum = 0;
     for (int s = 0; s < nsrc; ++s) cin_sum += srcs[s].c_count;
     const int64_t tiles64 = (int64_t)ceil_div(W, TC_TILE_W) * ceil_div(H, TC_TILE_H) * B;
+    // K blocks of 32 channels (64-byte rows): a single 32-channel source, i.e. the x-im2col rows of a 7x7 stem
+    const bool k32 = nsrc == 1 && srcs[0].c_count == 32 && (srcs[0].c_begin % 32) == 0;
+    const int KBLK = k32 ? 32 : 64;
+    const uint32_t a_part_bytes = (uint32_t)rows_loaded * TC_TILE_W * (uint32_t)KBLK * 2u;
 
-    // CTA-pair kernel (default for stride 1): each CTA stages half of a 64-channel weight block
-    bool use_pair = s_pair != 0 && s_patch != 0 && stride == 1 && tiles64 >= 2 && (cin_sum % 64) == 0;
+    // CTA-pair kernel (default for stride 1): each CTA stages half of a KBLK-channel weight block
+    bool use_pair = s_pair != 0 && s_patch != 0 && stride == 1 && tiles64 >= 2 && (cin_sum % KBLK) == 0;
     int p_a_stages = 2, p_w_stages = 0, p_resident = 0;
-    const uint32_t p_w_stage_bytes = 2u * (uint32_t)(Npad / 2) * 128u;
+    const uint32_t p_w_stage_bytes = 2u * (uint32_t)(Npad / 2) * (uint32_t)KBLK * 2u;
     if (use_pair) {
-        const int w_steps = (cin_sum / 64) * kh * kw;              // weight blocks per tile
+        const int w_steps = (cin_sum / KBLK) * kh * kw;            // weight blocks per tile
         if (2u * a_part_bytes * 2 >= budget) use_pair = false;
         else if (w_steps <= TCP_MAX_W && 2u * a_part_bytes * 2 + (uint32_t)w_steps * p_w_stage_bytes <= budget) {
             p_resident = 1;                                        // whole filter half stays in the ring
@@ -961,8 +1052,9 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
             }
         }
     }
-    const int BK = 64;
-    const int WBK = use_pair ? 64 : (use_patch ? WK : BK);   // K extent of a weight box
+    if (k32 && !use_pair) return DKT_E_UNSUPPORTED;           // 32-channel K blocks exist in the pair kernel only
+    const int BK = KBLK;
+    const int WBK = use_pair ? KBLK : (use_patch ? WK : BK);  // K extent of a weight box
     const int wbox_rows = use_pair ? Npad / 2 : Npad;         // N extent of a weight box
 
     TcConvParams prm{};
@@ -971,7 +1063,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     for (int s = 0; s < nsrc; ++s) {
         const dkt_tensor& t = srcs[s];
         DKT_CHECK_ARG(t.hi && t.lo && t.c_count > 0 && t.c_begin >= 0 && t.c_begin + t.c_count <= t.C);
-        if ((t.c_begin % 64) || (t.c_count % 64) || (t.C % 8) || !aligned16(t.hi) || !aligned16(t.lo))
+        if ((t.c_begin % BK) || (t.c_count % BK) || (t.C % 8) || !aligned16(t.hi) || !aligned16(t.lo))
             return DKT_E_ALIGNMENT;
         prm.c_begin[s] = t.c_begin;
         prm.kblocks[s] = t.c_count / BK;
@@ -1005,8 +1097,13 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     prm.num_tiles = (int)tiles;
     uint32_t cols = 32;
     while (cols < (uint32_t)prm.Npad) cols <<= 1;
-    prm.tmem_cols = cols;
     prm.acc_cols = cols;
+    prm.acc_stages = 512u / cols > (uint32_t)TC_MAX_ACC ? (uint32_t)TC_MAX_ACC : 512u / cols;
+    {
+        static const int s_acc_env = [] { const char* v = getenv("DKT_CONV_ACC_STAGES"); return v ? atoi(v) : 0; }();
+        if (s_acc_env >= 2 && (uint32_t)s_acc_env < prm.acc_stages) prm.acc_stages = (uint32_t)s_acc_env;   // A/B knob (2 = old)
+    }
+    prm.tmem_cols = prm.acc_stages * cols;            // a power of two >= 32 by construction
     prm.epi = e;
 
     if (use_pair) {
@@ -1017,8 +1114,8 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         prm.a_part_bytes = a_part_bytes;
         const int items = (int)((tiles + 1) / 2);
         const int pairs = items < s_sms / 2 ? items : s_sms / 2;
-        const size_t smem_bytes = (size_t)p_a_stages * 2 * a_part_bytes + (size_t)p_w_stages * p_w_stage_bytes + TC2_EPI_BYTES + 1024 + 256;
-        return launch_conv(FAM_PAIR, prm, 2u * (unsigned)pairs, smem_bytes, (cudaStream_t)stream);
+        const size_t smem_bytes = (size_t)p_a_stages * 2 * a_part_bytes + (size_t)p_w_stages * p_w_stage_bytes + TC2_EPI_BYTES + 1024 + TC_BAR_BYTES;
+        return launch_conv(k32 ? FAM_PAIR_K32 : FAM_PAIR, prm, 2u * (unsigned)pairs, smem_bytes, (cudaStream_t)stream);
     }
     const unsigned grid = (unsigned)(tiles < s_sms ? tiles : s_sms);
     if (use_patch) {
@@ -1026,7 +1123,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         prm.a_stages = a_stages;
         prm.w_stages = w_stages;
         prm.a_part_bytes = a_part_bytes;
-        const size_t smem_bytes = (size_t)a_stages * 2 * a_part_bytes + (size_t)w_stages * w_stage_bytes + TC2_EPI_BYTES + 1024 + 256;
+        const size_t smem_bytes = (size_t)a_stages * 2 * a_part_bytes + (size_t)w_stages * w_stage_bytes + TC2_EPI_BYTES + 1024 + TC_BAR_BYTES;
         return launch_conv(WK == 32 ? FAM_PATCH32 : FAM_PATCH64, prm, grid, smem_bytes, (cudaStream_t)stream);
     }
     // per-tap kernel: the ring takes what the epilogue buffers and barriers leave of the 227 KB
@@ -1035,7 +1132,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) return DKT_E_UNSUPPORTED;
     prm.stages = stages;
-    const size_t smem_bytes = (size_t)stages * stage_bytes + TC2_EPI_BYTES + 1024 + 256;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + TC2_EPI_BYTES + 1024 + TC_BAR_BYTES;
     return launch_conv(FAM_TAP64, prm, grid, smem_bytes, (cudaStream_t)stream);
 }
 

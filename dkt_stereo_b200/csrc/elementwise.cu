@@ -6,18 +6,17 @@
 namespace dkt {
 
 // ---- pool2x: 3x3 / stride 2 / pad 1 average, divisor 9 (count_include_pad) -----------------
+// grid: x = ceil(Wd * C4 / 256), y = B * Hd (one output row per blockIdx.y): no 64-bit div/mod per thread
 __global__ void __launch_bounds__(256)
 pool2x_kernel(const float* __restrict__ src, int sC, int sc0, dkt_tensor dst, int C4,
-              int Hs, int Ws, int Hd, int Wd, int64_t total) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int q = (int)(t % C4);
-    int64_t p = t / C4;
-    const int xo = (int)(p % Wd);
-    int64_t r = p / Wd;
-    const int yo = (int)(r % Hd);
-    const int64_t b = r / Hd;
+              int Hs, int Ws, int Hd, int Wd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Wd * C4) return;
+    const int xo = i / C4, q = i - xo * C4;
+    const int row = blockIdx.y;                   // b * Hd + yo
+    const int b = row / Hd, yo = row - b * Hd;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* base = src + (int64_t)b * Hs * Ws * sC + sc0 + q * 4;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
         const int y = 2 * yo + dy;
@@ -26,33 +25,30 @@ pool2x_kernel(const float* __restrict__ src, int sC, int sc0, dkt_tensor dst, in
         for (int dx = -1; dx <= 1; ++dx) {
             const int x = 2 * xo + dx;
             if (x < 0 || x >= Ws) continue;
-            float4 v = __ldg(reinterpret_cast<const float4*>(src + ((b * Hs + y) * (int64_t)Ws + x) * sC + sc0 + q * 4));
+            float4 v = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y * Ws + x) * sC));
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
     }
     // ATen divides the window sum by 9; keep a true division for bit-level agreement
     s.x /= 9.f; s.y /= 9.f; s.z /= 9.f; s.w /= 9.f;
-    store_all4(dst, p, q * 4, s);
+    store_all4(dst, (int64_t)row * Wd + xo, q * 4, s);
 }
 
 // ---- bilinear resize, align_corners=True ------------------------------------------------------
 __global__ void __launch_bounds__(256)
 interp_kernel(const float* __restrict__ src, int sC, int sc0, dkt_tensor dst, int C4,
-              int Hs, int Ws, int Hd, int Wd, float sy, float sx, int64_t total) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int q = (int)(t % C4);
-    int64_t p = t / C4;
-    const int xo = (int)(p % Wd);
-    int64_t r = p / Wd;
-    const int yo = (int)(r % Hd);
-    const int64_t b = r / Hd;
+              int Hs, int Ws, int Hd, int Wd, float sy, float sx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Wd * C4) return;
+    const int xo = i / C4, q = i - xo * C4;
+    const int row = blockIdx.y;                   // b * Hd + yo
+    const int b = row / Hd, yo = row - b * Hd;
     const float fy = sy * yo, fx = sx * xo;
     const int y0 = (int)fy, x0 = (int)fx;
     const int y1 = y0 + (y0 < Hs - 1), x1 = x0 + (x0 < Ws - 1);
     const float ly = fy - y0, lx = fx - x0;
     const float hy = 1.f - ly, hx = 1.f - lx;
-    const float* base = src + b * Hs * (int64_t)Ws * sC + sc0 + q * 4;
+    const float* base = src + (int64_t)b * Hs * Ws * sC + sc0 + q * 4;
     float4 v00 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y0 * Ws + x0) * sC));
     float4 v01 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y0 * Ws + x1) * sC));
     float4 v10 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y1 * Ws + x0) * sC));
@@ -62,7 +58,7 @@ interp_kernel(const float* __restrict__ src, int sC, int sc0, dkt_tensor dst, in
     o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
     o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
     o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
-    store_all4(dst, p, q * 4, o);
+    store_all4(dst, (int64_t)row * Wd + xo, q * 4, o);
 }
 
 // ---- K4 RAFT: convex combination upsampling ---------------------------------------------------
@@ -206,9 +202,9 @@ extern "C" int dkt_pool2x(const dkt_tensor* src, const dkt_tensor* dst, int B, i
     DKT_CHECK_ARG(src->c_count == dst->c_count);
     DKT_CHECK_ARG(Hd == (Hs - 1) / 2 + 1 && Wd == (Ws - 1) / 2 + 1);
     const int C4 = src->c_count / 4;
-    const int64_t total = (int64_t)B * Hd * Wd * C4;
-    pool2x_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        src->f32, src->C, src->c_begin, *dst, C4, Hs, Ws, Hd, Wd, total);
+    if ((int64_t)B * Hd > 65535 || (int64_t)Wd * C4 > 0x7fffffff) return DKT_E_UNSUPPORTED;
+    pool2x_kernel<<<dim3((unsigned)ceil_div(Wd * C4, 256), (unsigned)(B * Hd)), 256, 0, (cudaStream_t)stream>>>(
+        src->f32, src->C, src->c_begin, *dst, C4, Hs, Ws, Hd, Wd);
     DKT_RETURN_LAST();
 }
 
@@ -220,11 +216,11 @@ extern "C" int dkt_interp(const dkt_tensor* src, const dkt_tensor* dst, int B, i
     DKT_CHECK_ARG(B > 0 && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0);
     DKT_CHECK_ARG(src->c_count == dst->c_count);
     const int C4 = src->c_count / 4;
-    const int64_t total = (int64_t)B * Hd * Wd * C4;
+    if ((int64_t)B * Hd > 65535 || (int64_t)Wd * C4 > 0x7fffffff) return DKT_E_UNSUPPORTED;
     const float sy = Hd > 1 ? (float)(Hs - 1) / (float)(Hd - 1) : 0.f;
     const float sx = Wd > 1 ? (float)(Ws - 1) / (float)(Wd - 1) : 0.f;
-    interp_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        src->f32, src->C, src->c_begin, *dst, C4, Hs, Ws, Hd, Wd, sy, sx, total);
+    interp_kernel<<<dim3((unsigned)ceil_div(Wd * C4, 256), (unsigned)(B * Hd)), 256, 0, (cudaStream_t)stream>>>(
+        src->f32, src->C, src->c_begin, *dst, C4, Hs, Ws, Hd, Wd, sy, sx);
     DKT_RETURN_LAST();
 }
 

@@ -117,23 +117,75 @@ __global__ void instnorm_finalize_kernel(const float* __restrict__ partial, floa
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// statistics from per-tile partial sums (written by the conv epilogue, dkt_epilogue.stats_partial):
+// stage 1: grid (segments, B): segment sums over a contiguous range of the image's tiles, fp64;
+// stage 2: grid B: the segments in order -> mean / rstd.  Every order is fixed: bit-reproducible and
+// independent of the batch size and of the image's position in the batch.
+// ---------------------------------------------------------------------------------------------
+constexpr int IN_SEGS = 32;
+
+__global__ void __launch_bounds__(256)
+instnorm_tiles_stage1_kernel(const float* __restrict__ partial, double* __restrict__ seg, int tiles_per_img, int C2) {
+    // C2 = 2*C values per tile; thread -> (slice, value): slices walk the segment's tiles interleaved
+    extern __shared__ double s_acc[];                // [slices][C2]
+    const int b = blockIdx.y, sgm = blockIdx.x;
+    const int per = (tiles_per_img + IN_SEGS - 1) / IN_SEGS;
+    const int t0 = sgm * per, t1 = min(tiles_per_img, t0 + per);
+    const int slices = blockDim.x / C2;
+    const int v = threadIdx.x % C2, sl = threadIdx.x / C2;
+    if (sl < slices) {
+        double acc = 0.0;
+        const float* base = partial + ((int64_t)b * tiles_per_img) * C2 + v;
+        for (int t = t0 + sl; t < t1; t += slices) acc += (double)__ldg(base + (int64_t)t * C2);
+        s_acc[sl * C2 + v] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < C2) {
+        double acc = 0.0;
+        for (int k = 0; k < slices; ++k) acc += s_acc[k * C2 + threadIdx.x];
+        seg[((int64_t)b * IN_SEGS + sgm) * C2 + threadIdx.x] = acc;
+    }
+}
+
+__global__ void instnorm_tiles_stage2_kernel(const double* __restrict__ seg, float* __restrict__ stats,
+                                             int HW, int C, float eps) {
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double s = 0.0, q = 0.0;
+        for (int k = 0; k < IN_SEGS; ++k) {
+            s += seg[((int64_t)b * IN_SEGS + k) * 2 * C + c];
+            q += seg[((int64_t)b * IN_SEGS + k) * 2 * C + C + c];
+        }
+        const double mean = s / HW;
+        double var = q / HW - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stats[((int64_t)b * C + c) * 2 + 0] = (float)mean;
+        stats[((int64_t)b * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+}
+
+// grid: x = ceil(HW * C/4 / 256), y = B: 32-bit index math only, the image's stats address is block-uniform
 __global__ void __launch_bounds__(256)
 instnorm_apply_kernel(const float* __restrict__ x, int xC, int xc0, const float* __restrict__ stats,
-                      const float* __restrict__ res, int res_C, int res_c0, dkt_tensor out,
-                      int relu, int64_t P, int HW, int C) {
+                      const float* __restrict__ res, const uint16_t* __restrict__ res_hi,
+                      const uint16_t* __restrict__ res_lo, int res_C, int res_c0, dkt_tensor out,
+                      int relu, int HW, int C) {
     const int groups = C >> 2;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P * groups) return;
-    const int64_t p = i / groups;
-    const int c = (int)(i - p * groups) << 2;
-    const int b = (int)(p / HW);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HW * groups) return;
+    const int pl = i / groups;
+    const int c = (i - pl * groups) << 2;
+    const int b = blockIdx.y;
+    const int64_t p = (int64_t)b * HW + pl;
     const float4 v = *reinterpret_cast<const float4*>(x + p * xC + xc0 + c);
     const float4 st0 = __ldg(reinterpret_cast<const float4*>(stats + ((int64_t)b * C + c) * 2));       // m0 r0 m1 r1
     const float4 st1 = __ldg(reinterpret_cast<const float4*>(stats + ((int64_t)b * C + c) * 2 + 4));   // m2 r2 m3 r3
     float4 y = make_float4((v.x - st0.x) * st0.y, (v.y - st0.z) * st0.w, (v.z - st1.x) * st1.y, (v.w - st1.z) * st1.w);
     if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-    if (res) {
-        const float4 r = *reinterpret_cast<const float4*>(res + p * res_C + res_c0 + c);
+    if (res || res_hi) {
+        const float4 r = res ? *reinterpret_cast<const float4*>(res + p * res_C + res_c0 + c)
+                             : load_split4(res_hi, res_lo, p * res_C + res_c0 + c);
         y.x = fmaxf(y.x + r.x, 0.f); y.y = fmaxf(y.y + r.y, 0.f); y.z = fmaxf(y.z + r.z, 0.f); y.w = fmaxf(y.w + r.w, 0.f);
     }
     store_all4(out, p, c, y);
@@ -229,6 +281,25 @@ extern "C" int dkt_instnorm_stats(const dkt_tensor* x, float* workspace, float* 
     DKT_RETURN_LAST();
 }
 
+extern "C" int dkt_instnorm_tiles_workspace_floats(int B, int C) {
+    return B * 32 * 2 * C * 2;       // IN_SEGS segments of 2*C doubles per image
+}
+
+extern "C" int dkt_instnorm_finalize_tiles(const float* partial, float* workspace, float* stats, float eps,
+                                           int B, int C, int H, int W, void* stream) {
+    DKT_CHECK_ARG(partial && workspace && stats);
+    DKT_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0);
+    if (2 * C > 256 || (reinterpret_cast<uintptr_t>(workspace) & 7)) return DKT_E_UNSUPPORTED;
+    const int tiles_per_img = ceil_div(W, 16) * ceil_div(H, 8) * 4;      // entries: one per (tile, 2-row quarter)
+    const int C2 = 2 * C;
+    const int slices = 256 / C2;
+    double* seg = reinterpret_cast<double*>(workspace);
+    instnorm_tiles_stage1_kernel<<<dim3(IN_SEGS, B), 256, (size_t)slices * C2 * sizeof(double), (cudaStream_t)stream>>>(
+        partial, seg, tiles_per_img, C2);
+    instnorm_tiles_stage2_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(seg, stats, H * W, C, eps);
+    DKT_RETURN_LAST();
+}
+
 extern "C" int dkt_instnorm_apply(const dkt_tensor* x, const float* stats, const dkt_tensor* res, const dkt_tensor* out,
                                   int relu, int B, int H, int W, void* stream) {
     DKT_CHECK_ARG(x && x->f32 && stats && out && (out->f32 || out->hi));
@@ -236,13 +307,13 @@ extern "C" int dkt_instnorm_apply(const dkt_tensor* x, const float* stats, const
     DKT_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && out->c_count == C);
     if ((C % 4) || (x->C % 4) || (x->c_begin % 4) || (out->C % 4) || (out->c_begin % 4)) return DKT_E_ALIGNMENT;
     if (res) {
-        DKT_CHECK_ARG(res->f32 && res->c_count == C);
+        DKT_CHECK_ARG((res->f32 || (res->hi && res->lo)) && res->c_count == C);
         if ((res->C % 4) || (res->c_begin % 4)) return DKT_E_ALIGNMENT;
     }
-    const int64_t P = (int64_t)B * H * W;
-    const int64_t n = P * (C / 4);
-    instnorm_apply_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        x->f32, x->C, x->c_begin, stats, res ? res->f32 : nullptr, res ? res->C : 0, res ? res->c_begin : 0, *out,
-        relu, P, H * W, C);
+    const int64_t n = (int64_t)H * W * (C / 4);
+    if (n > 0x7fffffff || B > 65535) return DKT_E_UNSUPPORTED;
+    instnorm_apply_kernel<<<dim3((unsigned)ceil_div64(n, 256), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
+        x->f32, x->C, x->c_begin, stats, res ? res->f32 : nullptr, res ? res->hi : nullptr, res ? res->lo : nullptr,
+        res ? res->C : 0, res ? res->c_begin : 0, *out, relu, H * W, C);
     DKT_RETURN_LAST();
 }

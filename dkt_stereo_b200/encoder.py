@@ -21,6 +21,7 @@ channels stay exactly zero through conv, norm and residual.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -89,10 +90,11 @@ class EncoderEngine:
             w[key + ".ds"] = ops.pack_conv_general(ds.weight, ds.bias, stride=stride, cin_pad=_pad64(cin),
                                                    n_pad=_pad64(cout), bn=self._bn(blk.norm3))
 
-    def pack_weights(self) -> None:
+    def pack_weights(self) -> bool:
+        """Repack when a parameter changed; returns True if it did (captured CUDA graphs are stale then)."""
         sig = self._signature()
         if self.w is not None and sig == self._sig:
-            return
+            return False
         self.update.pack_weights()
         w: Dict[str, ops.ConvWeights] = {}
         for tag, net in (("f", self.fnet), ("c", self.cnet)):
@@ -100,7 +102,7 @@ class EncoderEngine:
             assert c1.kernel_size == (7, 7) and c1.stride == (1, 1) and c1.in_channels == 3, "n_downsample <= 2 stem"
             # 7x7x3 -> 7x1 over the x-im2col channels kx*3 + c (dkt_stem_rows_bf16x2)
             w7 = c1.weight.detach().permute(0, 3, 1, 2).reshape(c1.out_channels, 21, 7, 1)
-            w[tag + ".conv1"] = ops.pack_conv_general(w7, c1.bias, cin_pad=64, bn=self._bn(net.norm1))
+            w[tag + ".conv1"] = ops.pack_conv_general(w7, c1.bias, cin_pad=32, bn=self._bn(net.norm1))
             for lname in ("layer1", "layer2", "layer3") + (("layer4", "layer5") if tag == "c" else ()):
                 for i, blk in enumerate(getattr(net, lname)):
                     self._pack_block(w, f"{tag}.{lname}.{i}", blk)
@@ -119,6 +121,7 @@ class EncoderEngine:
             w[f"c.zqr{i}.zr"] = ops.pack_conv_general(z.weight[:256], bias[:256])
             w[f"c.zqr{i}.q"] = ops.pack_conv_general(z.weight[256:], bias[256:])
         self.w, self._sig = w, sig
+        return True
 
     # ---- buffers -------------------------------------------------------------------------------
     def allocate(self, B: int, H: int, W: int, device) -> None:
@@ -136,29 +139,59 @@ class EncoderEngine:
         B2 = 2 * B
         chans = [64, 128, 128, 128, 128]
         nimg = [B2, B2, B2, B, B]
+        # block inputs / outputs live as bf16 (hi, lo) only: the residual x of relu(x + y) is read back as hi + lo
+        # (16 mantissa bits, the precision every conv already consumes), so no fp32 copy of them is written or read.
+        # DKT_SPLIT_RES=0 keeps fp32 copies and fp32 residuals.
+        self.split_res = os.environ.get("DKT_SPLIT_RES", "1") == "1"
+        kf = not self.split_res
         self.lvl = []
         for (h, w_), c, n in zip(dims, chans, nimg):
-            self.lvl.append(dict(A=_Act(n, h, w_, c, device), Bb=_Act(n, h, w_, c, device),
+            self.lvl.append(dict(A=_Act(n, h, w_, c, device, f32=kf), Bb=_Act(n, h, w_, c, device, f32=kf),
                                  Y=_Act(n, h, w_, c, device, f32=False), RAW=_Act(n, h, w_, c, device, split=False),
                                  RAWD=_Act(n, h, w_, c, device, split=False)))
-        self.STEM = _Act(B2, H, W, 64, device, f32=False)
+        self.STEM = _Act(B2, H, W, 32, device, f32=False)     # 7 x 3 = 21 x-im2col channels in a 32-channel K block
         self.FMAP = _Act(B2, dims[2][0], dims[2][1], 256, device, f32=False)
-        self.HEAD = [_Act(B, *dims[2 + i], 128, device) for i in range(3)]          # head residual-block output
+        self.HEAD = [_Act(B, *dims[2 + i], 128, device, f32=kf) for i in range(3)]   # head residual-block output
         self.HY = [_Act(B, *dims[2 + i], 128, device, f32=False) for i in range(3)]
         self.CIN = [_Act(B, *dims[2 + i], 128, device, f32=False) for i in range(3)]  # relu(context head)
         self.stats = torch.zeros(B2, 128, 2, device=device)
         self.stats2 = torch.zeros(B2, 128, 2, device=device)
         self.ws = ops.instnorm_workspace(B2, 128, device)
+        # InstanceNorm statistics come out of the producing conv's epilogue as per-tile sums (DKT_FUSED_STATS=0:
+        # separate statistics pass over the raw conv output)
+        self.fused_stats = os.environ.get("DKT_FUSED_STATS", "1") == "1"
+        self.tile_part = torch.zeros(B2 * max(ops.conv_tiles(h, w_) * 2 * c for (h, w_), c in zip(dims, chans)),
+                                     device=device)
+        self.tile_ws = ops.instnorm_tiles_workspace(B2, 128, device)
         self.shape = shape
 
     # ---- building blocks -------------------------------------------------------------------------
-    def _conv(self, key: str, src: _Act, out_slice, Hin: int, Win: int, act=L.ACT_NONE, res=None) -> Tuple[int, int]:
+    def _o(self, a: _Act):
+        """destination slice of a block input / output activation"""
+        return a.s(f32=not self.split_res)
+
+    def _res_t(self, x: _Act):
+        """residual operand of instnorm_apply (dkt_tensor)"""
+        return x.s(f32=False) if self.split_res else x.s(split=False)
+
+    def _res_e(self, x: _Act):
+        """residual operand of a conv epilogue"""
+        return ((x.hi, x.lo), 0) if self.split_res else (x.f32, 0)
+
+    def _conv(self, key: str, src: _Act, out_slice, Hin: int, Win: int, act=L.ACT_NONE, res=None,
+              stats: bool = False) -> Tuple[int, int]:
+        """``stats``: the output feeds an InstanceNorm -- the epilogue also writes its per-tile channel sums."""
         w = self.w[key]
-        e = ops.make_epilogue(L.EPI_LINEAR, out_slice, act=act, bias=w.bias, res=res)
+        part = self.tile_part if (stats and self.fused_stats) else None
+        e = ops.make_epilogue(L.EPI_LINEAR, out_slice, act=act, bias=w.bias, res=res, stats_partial=part)
         return ops.conv2d_ex([src.s(f32=False)], w, e, src.B, Hin, Win)
 
     def _in_norm(self, raw: _Act, out_slice, stats, relu=True, res=None):
-        ops.instnorm_stats(raw.s(split=False), self.ws, stats, raw.B, raw.H, raw.W)
+        """InstanceNorm2d (+ReLU, + residual) of a raw conv output produced by ``_conv(..., stats=True)``."""
+        if self.fused_stats:
+            ops.instnorm_finalize_tiles(self.tile_part, self.tile_ws, stats, raw.B, raw.C, raw.H, raw.W)
+        else:
+            ops.instnorm_stats(raw.s(split=False), self.ws, stats, raw.B, raw.H, raw.W)
         ops.instnorm_apply(raw.s(split=False), stats, out_slice, raw.B, raw.H, raw.W, relu=relu, res=res)
 
     def _block(self, key: str, x: _Act, out: _Act, scratch: dict, inst: bool) -> None:
@@ -167,24 +200,24 @@ class EncoderEngine:
         Y, RAW, RAWD = scratch["Y"].view(n), scratch["RAW"].view(n), scratch["RAWD"].view(n)
         has_ds = (key + ".ds") in self.w
         if inst:
-            self._conv(key + ".conv1", x, RAW.s(split=False), x.H, x.W)
+            self._conv(key + ".conv1", x, RAW.s(split=False), x.H, x.W, stats=True)
             self._in_norm(RAW, Y.s(f32=False), self.stats, relu=True)
             if has_ds:
-                self._conv(key + ".ds", x, RAWD.s(split=False), x.H, x.W)
+                self._conv(key + ".ds", x, RAWD.s(split=False), x.H, x.W, stats=True)
                 self._in_norm(RAWD, RAWD.s(split=False), self.stats2, relu=False)
                 res = RAWD.s(split=False)
             else:
-                res = x.s(split=False)
-            self._conv(key + ".conv2", Y, RAW.s(split=False), Y.H, Y.W)
-            self._in_norm(RAW, out.s(), self.stats, relu=True, res=res)
+                res = self._res_t(x)
+            self._conv(key + ".conv2", Y, RAW.s(split=False), Y.H, Y.W, stats=True)
+            self._in_norm(RAW, self._o(out), self.stats, relu=True, res=res)
         else:
             self._conv(key + ".conv1", x, Y.s(f32=False), x.H, x.W, act=L.ACT_RELU)
             if has_ds:
                 self._conv(key + ".ds", x, RAWD.s(split=False), x.H, x.W)
                 res = (RAWD.f32, 0)
             else:
-                res = (x.f32, 0)
-            self._conv(key + ".conv2", Y, out.s(), Y.H, Y.W, act=L.ACT_RELU, res=res)
+                res = self._res_e(x)
+            self._conv(key + ".conv2", Y, self._o(out), Y.H, Y.W, act=L.ACT_RELU, res=res)
 
     def _trunk(self, tag: str, net, n: int) -> _Act:
         """conv1 + norm + relu, layer1..3 (reference core/extractor.py:173-190 / 274-281) on the first n
@@ -195,16 +228,16 @@ class EncoderEngine:
         stem = self.STEM.view(n)
         if inst:
             raw = l0["RAW"].view(n)
-            self._conv(tag + ".conv1", stem, raw.s(split=False), self.H, self.W)
-            self._in_norm(raw, x.s(), self.stats, relu=True)
+            self._conv(tag + ".conv1", stem, raw.s(split=False), self.H, self.W, stats=True)
+            self._in_norm(raw, self._o(x), self.stats, relu=True)
         else:
-            self._conv(tag + ".conv1", stem, x.s(), self.H, self.W, act=L.ACT_RELU)
+            self._conv(tag + ".conv1", stem, self._o(x), self.H, self.W, act=L.ACT_RELU)
         cur, cur_lvl = x, 0
         for lname, lvl in (("layer1", 0), ("layer2", 1), ("layer3", 2)):
             for i in range(2):
                 scratch = self.lvl[lvl]
                 cand = scratch["A"].view(n)
-                out = scratch["Bb"].view(n) if cand.f32.data_ptr() == cur.f32.data_ptr() else cand
+                out = scratch["Bb"].view(n) if cand.hi.data_ptr() == cur.hi.data_ptr() else cand
                 self._block(f"{tag}.{lname}.{i}", cur, out, scratch, inst)
                 cur = out
         return cur
@@ -234,7 +267,7 @@ class EncoderEngine:
             for i in range(2):
                 scratch = self.lvl[li]
                 cand = scratch["A"].view(B)
-                out = scratch["Bb"].view(B) if cand.f32.data_ptr() == cur.f32.data_ptr() else cand
+                out = scratch["Bb"].view(B) if cand.hi.data_ptr() == cur.hi.data_ptr() else cand
                 self._block(f"c.{lname}.{i}", cur, out, scratch, False)
                 cur = out
             feats.append(cur)

@@ -134,7 +134,9 @@ class IGEVStereo(nn.Module):
         assert args.corr_levels == 2, "IGEV configs use a 2-level geometry pyramid (configs/igev_stereo/base.json)"
         B, D, h, w = match_left.shape
         dev = match_left.device
-        eng.pack_weights()
+        if eng.pack_weights():                    # weights changed: the captured loop graph points into the old packs
+            self._graphs.clear()
+            self._seen.clear()
         eng.allocate(B, h, w, dev)
         key = (B, D, h, w, tuple(gev.shape), str(dev))
         if self._vol_key != key:

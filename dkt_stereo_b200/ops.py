@@ -223,7 +223,7 @@ def make_epilogue(kind: int, out: DktTensor, act: int = L.ACT_NONE, scale: float
                   bias: Optional[torch.Tensor] = None, ctx: Optional[torch.Tensor] = None, ctx_c0: int = 0,
                   z: Optional[DktTensor] = None, h: Optional[DktTensor] = None,
                   tail: Optional[torch.Tensor] = None, res: Optional[tuple] = None,
-                  proj: Optional[torch.Tensor] = None) -> DktEpilogue:
+                  proj: Optional[torch.Tensor] = None, stats_partial: Optional[torch.Tensor] = None) -> DktEpilogue:
     e = DktEpilogue()
     e.kind, e.act, e.scale = kind, act, scale
     e.bias = L.ptr(bias)
@@ -235,11 +235,16 @@ def make_epilogue(kind: int, out: DktTensor, act: int = L.ACT_NONE, scale: float
     e.h = h if h is not None else null_tensor()
     e.tail = L.ptr(tail)
     e.tail_C = tail.shape[-1] if tail is not None else 0
-    if res is not None:          # (tensor NHWC fp32, first channel)
-        e.res, e.res_C, e.res_c0 = L.ptr(res[0]), res[0].shape[-1], res[1]
+    if res is not None:          # (tensor NHWC fp32, first channel) or ((hi, lo) NHWC bf16, first channel)
+        if isinstance(res[0], tuple):
+            e.res_hi, e.res_lo, e.res_C, e.res_c0 = L.ptr(res[0][0]), L.ptr(res[0][1]), res[0][0].shape[-1], res[1]
+        else:
+            e.res, e.res_C, e.res_c0 = L.ptr(res[0]), res[0].shape[-1], res[1]
     if proj is not None:         # fp32 [N][PROJ_LD], see pack_proj3x3
         assert proj.dtype == torch.float32 and proj.is_contiguous() and proj.shape[-1] == L.PROJ_LD
         e.proj = proj.data_ptr()
+    if stats_partial is not None:    # fp32 [tiles][2][N]: per-tile sums written next to the conv output
+        e.stats_partial = stats_partial.data_ptr()
     return e
 
 
@@ -327,6 +332,22 @@ def instnorm_stats(x: DktTensor, workspace: torch.Tensor, stats: torch.Tensor, B
                    eps: float = 1e-5) -> None:
     L.check(L.load().dkt_instnorm_stats(C.byref(x), workspace.data_ptr(), stats.data_ptr(), eps, B, H, W,
                                         L.stream_ptr()), "instnorm_stats")
+
+
+def instnorm_tiles_workspace(B: int, Cc: int, device) -> torch.Tensor:
+    return torch.empty(L.load().dkt_instnorm_tiles_workspace_floats(B, Cc), device=device, dtype=torch.float32)
+
+
+def conv_tiles(H: int, W: int) -> int:
+    """Entries of dkt_epilogue.stats_partial per image: 8 x 16 output tiles of the tensor-core conv x 4 quarters."""
+    return ((H + 7) // 8) * ((W + 15) // 16) * 4
+
+
+def instnorm_finalize_tiles(partial: torch.Tensor, workspace: torch.Tensor, stats: torch.Tensor, B: int, Cc: int,
+                            H: int, W: int, eps: float = 1e-5) -> None:
+    """per-tile sums (conv epilogue, ``stats_partial``) -> stats (B,C,2) = (mean, rstd)."""
+    L.check(L.load().dkt_instnorm_finalize_tiles(partial.data_ptr(), workspace.data_ptr(), stats.data_ptr(), eps,
+                                                 B, Cc, H, W, L.stream_ptr()), "instnorm_finalize_tiles")
 
 
 def instnorm_apply(x: DktTensor, stats: torch.Tensor, out: DktTensor, B: int, H: int, W: int,
@@ -452,6 +473,7 @@ stem_rows = _profiled(lambda *a, **k: "stem_rows")(stem_rows)
 tapsum3x3 = _profiled(lambda *a, **k: "tapsum3x3")(tapsum3x3)
 instnorm_stats = _profiled(lambda *a, **k: "instnorm_stats")(instnorm_stats)
 instnorm_apply = _profiled(lambda *a, **k: "instnorm_apply")(instnorm_apply)
+instnorm_finalize_tiles = _profiled(lambda *a, **k: "instnorm_finalize_tiles")(instnorm_finalize_tiles)
 corr1d_build = _profiled(lambda *a, **k: f"corr1d_build_{k.get('impl', a[4] if len(a) > 4 else 'tc')}")(corr1d_build)
 corr1d_build_split = _profiled(lambda *a, **k: "corr1d_build_tc")(corr1d_build_split)
 corr1d_lookup = _profiled(lambda pyr, *a, **k: "corr1d_lookup" if len(pyr) else "coords_update")(corr1d_lookup)

@@ -85,6 +85,12 @@ class RAFTStereo(nn.Module):
         self.channels_last = os.environ.get("DKT_CHANNELS_LAST", "0") == "1"
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self._seen = set()
+        # whole-forward CUDA graphs of the native path (encoders + volume + loop + upsampling), per input shape:
+        # one replay per call instead of ~700 launches through Python (DKT_FULL_GRAPH=0: only the loop is a graph)
+        self.full_graph = os.environ.get("DKT_FULL_GRAPH", "1") == "1"
+        self._full: Dict[tuple, tuple] = {}
+        self._full_seen = set()
+        self._capturing = False
         self._pyr = None
         self._pyr_key = None
 
@@ -133,7 +139,9 @@ class RAFTStereo(nn.Module):
         args, eng = self.args, self.engine
         L.require_device(fmap1)
         B, D, h, w = fmap1.shape
-        eng.pack_weights()
+        if eng.pack_weights():                    # weights changed: the captured loop graph points into the old packs
+            self._graphs.clear()
+            self._seen.clear()
         eng.allocate(B, h, w, fmap1.device)
         self._ensure_volume(B, D, h, w, fmap1.device)
         ops.corr1d_build(fmap1, fmap2, args.corr_levels, 1.0 / (D ** 0.5), impl=self.impl, pyr=self._pyr)      # K1
@@ -161,7 +169,9 @@ class RAFTStereo(nn.Module):
         else:
             eng.coords_x.copy_(xs)
         gkey = (iters,)
-        if self.use_cuda_graph and gkey in self._graphs:
+        if self._capturing:                      # inside the whole-forward capture: the loop joins that graph
+            self._run_loop(iters)
+        elif self.use_cuda_graph and gkey in self._graphs:
             self._graphs[gkey].replay()
         elif self.use_cuda_graph and gkey in self._seen:
             torch.cuda.synchronize()
@@ -180,10 +190,8 @@ class RAFTStereo(nn.Module):
         flow_lr = eng.FLOW["f32"].permute(0, 3, 1, 2).contiguous()
         return flow_lr, flow_up
 
-    def forward_native(self, image1, image2, iters: int, flow_init=None):
-        """Whole forward on libdkt kernels: encoders (EncoderEngine) -> K1 from the bf16 (hi, lo) feature maps
-        the encoder wrote -> loop -> upsampling.  No NCHW <-> NHWC conversion and no fp32 -> bf16 split pass."""
-        args, enc, eng = self.args, self.encoder, self.engine
+    def _forward_native_eager(self, image1, image2, iters: int, flow_init=None):
+        args, enc = self.args, self.encoder
         B = image1.shape[0]
         enc.run(image1, image2)
         h, w = enc.dims[2]
@@ -192,6 +200,43 @@ class RAFTStereo(nn.Module):
         f = enc.FMAP
         ops.corr1d_build_split(f.hi[:B], f.lo[:B], f.hi[B:], f.lo[B:], args.corr_levels, 1.0 / (D ** 0.5), self._pyr)
         return self._loop_and_upsample(B, h, w, iters, flow_init)
+
+    def forward_native(self, image1, image2, iters: int, flow_init=None):
+        """Whole forward on libdkt kernels: encoders (EncoderEngine) -> K1 from the bf16 (hi, lo) feature maps
+        the encoder wrote -> loop -> upsampling.  No NCHW <-> NHWC conversion and no fp32 -> bf16 split pass.
+        From the third call with the same input shape the whole thing is ONE CUDA-graph replay: the images are
+        copied into static device buffers, the results are returned as fresh tensors."""
+        if self.encoder.pack_weights():          # weights changed: captured graphs point into the old packs
+            self._graphs.clear()
+            self._seen.clear()
+            self._full.clear()
+            self._full_seen.clear()
+        if not (self.use_cuda_graph and self.full_graph and flow_init is None):
+            return self._forward_native_eager(image1, image2, iters, flow_init)
+        key = (tuple(image1.shape), str(image1.device), iters)
+        ent = self._full.get(key)
+        if ent is None:
+            if key not in self._full_seen:       # first call: allocates buffers, packs weights, warms up
+                self._full_seen.add(key)
+                return self._forward_native_eager(image1, image2, iters, None)
+            in1 = torch.empty(image1.shape, device=image1.device, dtype=torch.float32)
+            in2 = torch.empty_like(in1)
+            in1.copy_(image1)
+            in2.copy_(image2)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            self._capturing = True
+            try:
+                with torch.cuda.graph(g):
+                    lr, up = self._forward_native_eager(in1, in2, iters, None)
+            finally:
+                self._capturing = False
+            ent = self._full[key] = (g, in1, in2, lr, up)
+        g, in1, in2, lr, up = ent
+        in1.copy_(image1, non_blocking=True)     # device or pinned-host source; same stream as the replay
+        in2.copy_(image2, non_blocking=True)
+        g.replay()
+        return lr.clone(), up.clone()
 
     def forward(self, image1, image2, iters=12, flow_init=None, test_mode=False):
         """Estimate disparity (returned as negative flow, like the reference) between a stereo pair."""

@@ -118,10 +118,11 @@ class UpdateEngine:
     def _signature(self):
         return tuple((p.data_ptr(), p._version) for p in self.block.parameters())
 
-    def pack_weights(self) -> None:
+    def pack_weights(self) -> bool:
+        """Repack when a parameter changed; returns True if it did (captured CUDA graphs are stale then)."""
         sig = self._signature()
         if self.weights is not None and sig == self._wsig:
-            return
+            return False
         b, tc = self.block, self.impl == "tc"
         enc = b.encoder
         w: Dict[str, ops.ConvWeights] = {}
@@ -149,7 +150,7 @@ class UpdateEngine:
             #  * the head's 3x3 conv to ONE used channel as a 1x1 conv to 9 tap responses + a spatial tap sum
             nfl = stem1.in_channels
             w7 = stem1.weight.detach().permute(0, 3, 1, 2).reshape(stem1.out_channels, 7 * nfl, 7, 1)
-            w["stem1t"] = ops.pack_conv_general(w7, stem1.bias, cin_pad=64)
+            w["stem1t"] = ops.pack_conv_general(w7, stem1.bias, cin_pad=32)
             c2 = head.conv2
             w9 = c2.weight.detach()[0].permute(1, 2, 0).reshape(9, c2.in_channels, 1, 1)
             w["head2t"] = ops.pack_conv(w9, None, tc=True)
@@ -161,6 +162,7 @@ class UpdateEngine:
             w["mask0"] = ops.pack_conv(b.mask[0].weight, b.mask[0].bias, tc=tc)
             w["mask2"] = ops.pack_conv(b.mask[2].weight, b.mask[2].bias, tc=tc)
         self.weights, self._wsig = w, sig
+        return True
 
     # ---- buffers -------------------------------------------------------------------------------
     def _buf(self, B, H, W, Cc, f32=True, split=None):
@@ -213,7 +215,7 @@ class UpdateEngine:
             factor = 2 ** self.block.args.n_downsample
             self.MASK = self._buf(B, h0, w0, 9 * factor * factor, split=False)
         if self.impl == "tc":
-            self.FROWS = self._buf(B, h0, w0, 64, f32=False)        # x-im2col of the flow field (7 taps x nflow)
+            self.FROWS = self._buf(B, h0, w0, 32, f32=False)        # x-im2col of the flow field (7 taps x nflow <= 14 ch)
             self.TAPS = self._buf(B, h0, w0, 16, split=False)       # 9 tap responses of the head's last conv
         self.coords_x = torch.zeros(B, h0, w0, device=device, dtype=torch.float32)
         self.shape = shape
@@ -273,7 +275,7 @@ class UpdateEngine:
                    E(L.EPI_LINEAR, S(self.CF, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["convc2"].bias), B, h0, w0, impl)
         if split and self.fast_small_convs:
             ops.stem_rows(self.FLOW["f32"], self.FROWS["hi"], self.FROWS["lo"], kw=7, scale=1.0, shift=0.0, layout="nhwc")
-            ops.conv2d_ex([S(self.FROWS, 0, 64, False, True)], Wt["stem1t"],
+            ops.conv2d_ex([S(self.FROWS, 0, 32, False, True)], Wt["stem1t"],
                           E(L.EPI_LINEAR, S(self.FLO1, 0, 64, False, True), act=L.ACT_RELU, bias=Wt["stem1t"].bias), B, h0, w0)
         else:
             ops.conv2d([S(self.FLOW, 0, self.nflow, True, False)], Wt["stem1"],

@@ -89,6 +89,16 @@ typedef struct dkt_epilogue {
     int32_t      res_C;     /*   result becomes relu(y + res[p][res_c0 + n]) -- the tail of a  */
     int32_t      res_c0;    /*   ResidualBlock (reference core/extractor.py:56-60).            */
     const float* proj;      /* PROJ: fp32 [N][DKT_PROJ_LD] projection matrix (unused columns 0)    */
+    const uint16_t* res_hi; /* LINEAR (tensor-core path): the residual as a bf16 (hi, lo) pair, used when    */
+    const uint16_t* res_lo; /*   res == NULL (same res_C / res_c0): residual = hi + lo, so the block input  */
+                            /*   needs no separate fp32 copy in HBM.                                        */
+    float*       stats_partial; /* LINEAR (tensor-core path, N % 32 == 0): when non-NULL the kernel also  */
+                            /*   writes, per 8 x 16 output tile t (t = (b*tiles_y + ty)*tiles_x + tx) and  */
+                            /*   per 2-row quarter q of the tile, [t][q][0][n] = sum and [t][q][1][n] =    */
+                            /*   sum of squares of the stored values over the quarter's valid pixels       */
+                            /*   (fixed summation order): the statistics pass of nn.InstanceNorm2d fused   */
+                            /*   into the conv that feeds it, finished by dkt_instnorm_finalize_tiles      */
+                            /*   (reference core/extractor.py:16-33).  Size: tiles * 8 * N floats.         */
 } dkt_epilogue;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -223,7 +233,8 @@ int dkt_split_nchw_to_nhwc_bf16x2(const float* src, int64_t sb, int64_t sd, int6
  * dkt_instnorm_stats   : nn.InstanceNorm2d statistics (biased variance) of an NHWC fp32 slice ->
  *   stats (B,C,2) = (mean, 1/sqrt(var+eps)); workspace >= dkt_instnorm_workspace_floats(B,C) floats.
  * dkt_instnorm_apply   : out = (x - mean)*rstd, then ReLU if relu != 0, then relu(res + out) if res != NULL
- *   (the ResidualBlock tail, core/extractor.py:56-60); writes every non-null precision of `out`. */
+ *   (the ResidualBlock tail, core/extractor.py:56-60; res is read as fp32 if res->f32 != NULL, else as hi + lo);
+ *   writes every non-null precision of `out`. */
 int dkt_stem_rows_bf16x2(const float* img, int64_t sb, int64_t sc, int64_t sy, int64_t sx,
                          float scale, float shift, uint16_t* hi, uint16_t* lo,
                          int B, int Cin, int H, int W, int kw, int Cpad, void* stream);
@@ -238,6 +249,13 @@ int dkt_instnorm_stats(const dkt_tensor* x, float* workspace, float* stats, floa
                        int B, int H, int W, void* stream);
 int dkt_instnorm_apply(const dkt_tensor* x, const float* stats, const dkt_tensor* res, const dkt_tensor* out,
                        int relu, int B, int H, int W, void* stream);
+/* dkt_instnorm_finalize_tiles : per-tile partial sums written by a conv with dkt_epilogue.stats_partial
+ *   (B * tiles_per_img tiles of 8 x 16 pixels, [tile][4][2][C]) -> stats (B,C,2) = (mean, 1/sqrt(var+eps)) over the H*W
+ *   pixels of each image; tiles are reduced in a fixed order, in double.  workspace >=
+ *   dkt_instnorm_tiles_workspace_floats(B, C) floats. */
+int dkt_instnorm_tiles_workspace_floats(int B, int C);
+int dkt_instnorm_finalize_tiles(const float* partial, float* workspace, float* stats, float eps,
+                                int B, int C, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

@@ -568,3 +568,99 @@ torch.save(outs, sys.argv[1])
             res[mode] = torch.load(f.name)
     for a, b in zip(res["0"], res["1"]):
         assert torch.equal(a, b), float((a - b).abs().max())
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 19, 37, 1), (3, 64, 128, 40, 50, 2), (1, 128, 128, 8, 16, 1)])
+def test_conv_fused_instnorm_stats(shape):
+    """dkt_epilogue.stats_partial + dkt_instnorm_finalize_tiles == mean / rstd of the conv output
+    (nn.InstanceNorm2d statistics, reference core/extractor.py:16-33), ragged tiles and strided convs included."""
+    from dkt_stereo_b200 import ops, _lib as L
+    B, Cin, N, H, W, stride = shape
+    g = torch.Generator().manual_seed(N + H)
+    x = torch.randn(B, Cin, H, W, generator=g) * 2 + 0.5
+    wt = torch.randn(N, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    bias = torch.randn(N, generator=g)
+    ref = torch.nn.functional.conv2d(x, wt, bias, padding=1, stride=stride)
+    Ho, Wo = ref.shape[2:]
+    xs, keep = _slice_of(_nhwc(x).to(dev()), "tc")
+    Wp = ops.pack_conv_general(wt.to(dev()), bias.to(dev()), stride=stride)
+    out = torch.zeros(B, Ho, Wo, N, device=dev())
+    part = torch.full((B * ops.conv_tiles(Ho, Wo) * 2 * N,), float("nan"), device=dev())
+    e = ops.make_epilogue(L.EPI_LINEAR, L.tensor_slice(out, None, None, 0, N), bias=Wp.bias, stats_partial=part)
+    ops.conv2d_ex([xs], Wp, e, B, H, W)
+    stats = torch.zeros(B, N, 2, device=dev())
+    ops.instnorm_finalize_tiles(part, ops.instnorm_tiles_workspace(B, N, dev()), stats, B, N, Ho, Wo)
+    torch.cuda.synchronize()
+    got = out.permute(0, 3, 1, 2).double().cpu()
+    mean = got.mean(dim=(2, 3))
+    rstd = 1.0 / torch.sqrt(got.var(dim=(2, 3), unbiased=False) + 1e-5)
+    assert not torch.isnan(part).any()
+    assert float((stats[..., 0].cpu().double() - mean).abs().max()) < 1e-5
+    assert float(((stats[..., 1].cpu().double() - rstd) / rstd).abs().max()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE sizes (544 x 960, configs[1]): size-independent properties, no oracle needed
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties():
+    """At the benchmark resolution: (1) the volume pyramid is self-consistent (level l+1 = pairwise mean of level l,
+    level 0 = scaled dot products of the feature maps); (2) looking the volume up at integer coordinates returns
+    the volume's own entries; (3) a sample's disparity map does not depend on the batch it rides in (bit exact:
+    every kernel reduces in a fixed, batch-independent order) and a repeated forward is bit-identical."""
+    from dkt_stereo_b200 import ops
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    g = load_golden("raft_fwd_small")
+    model = _model("tc", g)
+    H, W = 544, 960
+    im1, im2 = synthetic_pair(2, H, W, seed=5)
+    im1, im2 = im1.to(dev()), im2.to(dev())
+    lr, up = model(im1, im2, iters=4, test_mode=True)
+    assert up.shape == (2, 1, H, W) and torch.isfinite(up).all()
+    pyr = [p.clone() for p in model._pyr]
+    # (1) pyramid consistency
+    for l in range(3):
+        w2 = pyr[l + 1].shape[-1]
+        ref = 0.5 * (pyr[l][..., 0:2 * w2:2] + pyr[l][..., 1:2 * w2:2])
+        assert float((pyr[l + 1] - ref).abs().max()) < 1e-5
+    f = model.encoder.FMAP
+    f1 = (f.hi[:2].float() + f.lo[:2].float())[0, 7]               # image 0, row 7: (W1, D)
+    f2 = (f.hi[2:].float() + f.lo[2:].float())[0, 7]
+    ref = (f1.double() @ f2.double().T / 16.0).float()
+    assert float((pyr[0][0, 7] - ref).abs().max()) < 2e-4
+    # (2) identity lookup: coords = pixel x -> tap k of level 0 is volume[.., x, x + k - 4]
+    B, h, w = 2, H // 4, W // 4
+    cx = torch.arange(w, device=dev(), dtype=torch.float32).view(1, 1, w).expand(B, h, w).contiguous()
+    out = torch.zeros(B, h, w, 36, device=dev())
+    ops.corr1d_lookup(pyr, cx, 4, out, "nhwc")
+    xs = torch.arange(w, device=dev())
+    for k in (0, 4, 8):
+        j = xs + k - 4
+        ok = (j >= 0) & (j < w)
+        ref = pyr[0][:, :, xs[ok], j[ok]]
+        assert torch.equal(out[:, :, ok, k], ref)
+    # (3) batch independence + determinism, bit exact
+    lr_b, up_b = model(im1, im2, iters=4, test_mode=True)
+    assert torch.equal(up_b, up) and torch.equal(lr_b, lr)
+    _, up0 = model(im1[:1], im2[:1], iters=4, test_mode=True)
+    assert torch.equal(up0, up[:1]), float((up0 - up[:1]).abs().max())
+    _, up1 = model(im1[1:], im2[1:], iters=4, test_mode=True)
+    assert torch.equal(up1, up[1:]), float((up1 - up[1:]).abs().max())
+
+
+def test_host_pipeline_matches_direct_calls():
+    """HostPipeline (pinned upload overlapped with compute, pinned read-back) returns exactly what direct forward
+    calls return, batch after batch, including across the eager -> capture -> replay transitions of the CUDA graph."""
+    from dkt_stereo_b200.pipeline import HostPipeline
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    g = load_golden("raft_fwd_small")
+    model = _model("tc", g)
+    batches = [tuple(t.pin_memory() for t in synthetic_pair(2, 64, 96, seed=100 + i)) for i in range(5)]
+    want = []
+    for a, b in batches:
+        _, up = model(a.to(dev()), b.to(dev()), iters=3, test_mode=True)
+        want.append(up.cpu())
+    pipe = HostPipeline(model, iters=3)
+    pipe.prefetch(*batches[0])
+    for i in range(5):
+        got = pipe.step(batches[i + 1] if i + 1 < 5 else None).clone()
+        assert torch.equal(got, want[i]), (i, float((got - want[i]).abs().max()))
