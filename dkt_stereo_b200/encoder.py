@@ -61,8 +61,10 @@ class _Act:
 
 
 class EncoderEngine:
-    def __init__(self, fnet: BasicEncoder, cnet: MultiBasicEncoder, zqr_convs: nn.ModuleList, update: UpdateEngine):
-        assert fnet.norm_fn == "instance" and cnet.norm_fn == "batch", "engine serves configs/raft_stereo/base.json"
+    def __init__(self, fnet: Optional[BasicEncoder], cnet: MultiBasicEncoder, zqr_convs: nn.ModuleList, update: UpdateEngine):
+        """``fnet=None``: context encoder only (IGEV-Stereo, whose matching features come from its own pyramid)."""
+        assert (fnet is None or fnet.norm_fn == "instance") and cnet.norm_fn == "batch", \
+            "engine serves configs/raft_stereo/base.json and configs/igev_stereo/base.json"
         self.fnet, self.cnet, self.zqr, self.update = fnet, cnet, zqr_convs, update
         self.w: Optional[Dict[str, ops.ConvWeights]] = None
         self._sig = None
@@ -70,8 +72,8 @@ class EncoderEngine:
 
     # ---- weights -------------------------------------------------------------------------------
     def _signature(self):
-        mods = list(self.fnet.parameters()) + list(self.cnet.parameters()) + list(self.cnet.buffers()) + \
-            list(self.zqr.parameters()) + list(self.update.block.parameters())
+        mods = (list(self.fnet.parameters()) if self.fnet is not None else []) + list(self.cnet.parameters()) + \
+            list(self.cnet.buffers()) + list(self.zqr.parameters()) + list(self.update.block.parameters())
         return tuple((p.data_ptr(), p._version) for p in mods)
 
     @staticmethod
@@ -98,6 +100,8 @@ class EncoderEngine:
         self.update.pack_weights()
         w: Dict[str, ops.ConvWeights] = {}
         for tag, net in (("f", self.fnet), ("c", self.cnet)):
+            if net is None:
+                continue
             c1 = net.conv1
             assert c1.kernel_size == (7, 7) and c1.stride == (1, 1) and c1.in_channels == 3, "n_downsample <= 2 stem"
             # 7x7x3 -> 7x1 over the x-im2col channels kx*3 + c (dkt_stem_rows_bf16x2)
@@ -106,7 +110,8 @@ class EncoderEngine:
             for lname in ("layer1", "layer2", "layer3") + (("layer4", "layer5") if tag == "c" else ()):
                 for i, blk in enumerate(getattr(net, lname)):
                     self._pack_block(w, f"{tag}.{lname}.{i}", blk)
-        w["f.conv2"] = ops.pack_conv_general(self.fnet.conv2.weight, self.fnet.conv2.bias)
+        if self.fnet is not None:
+            w["f.conv2"] = ops.pack_conv_general(self.fnet.conv2.weight, self.fnet.conv2.bias)
         heads = [getattr(self.cnet, n) for n in self.cnet.head_names]
         for i, hl in enumerate(heads):
             for j, head in enumerate(hl):
@@ -129,14 +134,14 @@ class EncoderEngine:
         if self.shape == shape:
             return
         self.device, self.B, self.H, self.W = device, B, H, W
-        nd = self.fnet.downsample
-        assert nd == 2, "engine serves n_downsample = 2 (configs/raft_stereo/base.json)"
+        nd = self.cnet.downsample
+        assert nd == 2, "engine serves n_downsample = 2 (configs/*/base.json)"
         dims = [(H, W)]
         for _ in range(4):
             h, w_ = dims[-1]
             dims.append(((h - 1) // 2 + 1, (w_ - 1) // 2 + 1))
         self.dims = dims                                   # full, 1/2, 1/4, 1/8, 1/16
-        B2 = 2 * B
+        B2 = 2 * B if self.fnet is not None else B
         chans = [64, 128, 128, 128, 128]
         nimg = [B2, B2, B2, B, B]
         # block inputs / outputs live as bf16 (hi, lo) only: the residual x of relu(x + y) is read back as hi + lo
@@ -150,7 +155,7 @@ class EncoderEngine:
                                  Y=_Act(n, h, w_, c, device, f32=False), RAW=_Act(n, h, w_, c, device, split=False),
                                  RAWD=_Act(n, h, w_, c, device, split=False)))
         self.STEM = _Act(B2, H, W, 32, device, f32=False)     # 7 x 3 = 21 x-im2col channels in a 32-channel K block
-        self.FMAP = _Act(B2, dims[2][0], dims[2][1], 256, device, f32=False)
+        self.FMAP = _Act(B2, dims[2][0], dims[2][1], 256, device, f32=False) if self.fnet is not None else None
         self.HEAD = [_Act(B, *dims[2 + i], 128, device, f32=kf) for i in range(3)]   # head residual-block output
         self.HY = [_Act(B, *dims[2 + i], 128, device, f32=False) for i in range(3)]
         self.CIN = [_Act(B, *dims[2 + i], 128, device, f32=False) for i in range(3)]  # relu(context head)
@@ -243,9 +248,9 @@ class EncoderEngine:
         return cur
 
     # ---- forward -----------------------------------------------------------------------------------
-    def run(self, image1: torch.Tensor, image2: torch.Tensor) -> None:
-        """image (B,3,H,W) fp32 in [0,255].  Fills self.FMAP (bf16 hi/lo, images [0,B) = left, [B,2B) = right),
-        and the update engine's hidden-state slices X[i][:, :128] and context buffers CTX[i]."""
+    def run(self, image1: torch.Tensor, image2: Optional[torch.Tensor] = None) -> None:
+        """image (B,3,H,W) fp32 in [0,255].  Fills self.FMAP (bf16 hi/lo, images [0,B) = left, [B,2B) = right; only
+        with an fnet), and the update engine's hidden-state slices X[i][:, :128] and context buffers CTX[i]."""
         B, _, H, W = image1.shape
         L.require_device(image1)
         self.pack_weights()
@@ -253,12 +258,13 @@ class EncoderEngine:
         eng = self.update
         eng.allocate(B, self.dims[2][0], self.dims[2][1], image1.device)
         im1 = image1.contiguous().float()
-        im2 = image2.contiguous().float()
-        # ---- fnet on [left; right] (reference raft_stereo.py:102) ----
         ops.stem_rows(im1, self.STEM.hi[:B], self.STEM.lo[:B])
-        ops.stem_rows(im2, self.STEM.hi[B:], self.STEM.lo[B:])
-        x = self._trunk("f", self.fnet, 2 * B)
-        self._conv("f.conv2", x, self.FMAP.s(f32=False), x.H, x.W)
+        if self.fnet is not None:
+            # ---- fnet on [left; right] (reference raft_stereo.py:102) ----
+            im2 = image2.contiguous().float()
+            ops.stem_rows(im2, self.STEM.hi[B:], self.STEM.lo[B:])
+            x = self._trunk("f", self.fnet, 2 * B)
+            self._conv("f.conv2", x, self.FMAP.s(f32=False), x.H, x.W)
         # ---- cnet on left (reference raft_stereo.py:101); the stem rows of the left images are still there ----
         x = self._trunk("c", self.cnet, B)
         feats = [x]

@@ -65,6 +65,13 @@ class IGEVStereo(nn.Module):
         self.classifier = nn.Conv3d(8, 1, 3, 1, 1, bias=False)
 
         self.engine = UpdateEngine(self.update_block, self.impl)
+        # context encoder + context convs on the library's tensor-core conv kernel (same EncoderEngine as RAFT-Stereo's
+        # cnet; 152 of the 235 ms the PyTorch pre-loop took at cfg3 were this fp32 cuDNN encoder)
+        self.encoder = None
+        if (os.environ.get("DKT_NATIVE_ENCODER", "1") == "1" and self.impl == "tc" and args.n_downsample == 2
+                and not getattr(args, "mixed_precision", False)):
+            from .encoder import EncoderEngine
+            self.encoder = EncoderEngine(None, self.cnet, self.context_zqr_convs, self.engine)
         self.use_cuda_graph = os.environ.get("DKT_CUDA_GRAPH", "1") == "1"
         self.extractor_fp32 = not getattr(args, "extractor_tf32", False)
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
@@ -99,11 +106,13 @@ class IGEVStereo(nn.Module):
             gev = self.cost_agg(vol, fl)
             prob = F.softmax(self.classifier(gev).squeeze(1), dim=1)
             init_disp = disparity_regression(prob, D)
-            cnet_list = self.cnet(image1, num_layers=args.n_gru_layers)
-            net_list = [torch.tanh(x[0]) for x in cnet_list]
-            ctx_list = [conv(torch.relu(x[1])) for x, conv in zip(cnet_list, self.context_zqr_convs)]
-        return (match_left.float(), match_right.float(), gev.float(), init_disp.float(),
-                [n.float() for n in net_list], [c.float() for c in ctx_list], stem_2x.float())
+            if self.encoder is not None and image1.is_cuda:
+                net_list = ctx_list = None       # written straight into the update engine's buffers by forward()
+            else:
+                cnet_list = self.cnet(image1, num_layers=args.n_gru_layers)
+                net_list = [torch.tanh(x[0]).float() for x in cnet_list]
+                ctx_list = [conv(torch.relu(x[1])).float() for x, conv in zip(cnet_list, self.context_zqr_convs)]
+        return (match_left.float(), match_right.float(), gev.float(), init_disp.float(), net_list, ctx_list, stem_2x.float())
 
     # ---- hot path (B200 kernels): reference igev_stereo.py:192-216 --------------------------------
     def _lookup(self, eng: UpdateEngine) -> None:
@@ -151,7 +160,8 @@ class IGEVStereo(nn.Module):
         init = ops.corr1d_build(match_left, match_right, 2, 1.0, impl=self.impl, pyr=self._init_pyr)
         geo = ops.geo_pool(gev, out=self._geo_pyr)
         self._vol = (geo, init)
-        eng.load_state(net_list, ctx_list)
+        if net_list is not None:
+            eng.load_state(net_list, ctx_list)   # else: EncoderEngine.run already filled X[i][:, :128] and CTX[i]
         eng.DELTA["f32"].zero_()
         eng.FLOW["f32"].copy_(init_disp.permute(0, 2, 3, 1))
         gkey = (iters,)
@@ -184,4 +194,9 @@ class IGEVStereo(nn.Module):
             raise L.DktError("IGEVStereo (B200 engine) needs CUDA inputs; there is no CPU fallback")
         with torch.no_grad():
             pre = self.prepare(image1, image2)
+            if self.encoder is not None:
+                if self.encoder.pack_weights():
+                    self._graphs.clear()
+                    self._seen.clear()
+                self.encoder.run(image1)         # cnet + context convs -> hidden states / context terms (NHWC, in place)
             return None, self.hot_path(*pre, iters)

@@ -90,6 +90,10 @@ class BasicMultiUpdateBlock(nn.Module):
 # ---------------------------------------------------------------------------------------------
 # engine
 # ---------------------------------------------------------------------------------------------
+def LaunchProfilerActive():
+    return ops.LaunchProfiler.active
+
+
 def _pad64(c: int) -> int:
     return (c + 63) // 64 * 64
 
@@ -110,6 +114,8 @@ class UpdateEngine:
         # head conv1 + ReLU + the channel half of conv2 in ONE kernel (DKT_EPI_PROJ): the 256-channel hidden map of
         # the flow / disparity head never reaches HBM; 0 = conv1 -> FH -> 1x1 tap conv
         self.fused_head = os.environ.get("DKT_FUSED_HEAD", "1") == "1"
+        self.two_streams = os.environ.get("DKT_TWO_STREAMS", "1") == "1"
+        self.side_stream = None
         self.weights: Optional[Dict[str, ops.ConvWeights]] = None
         self._wsig = None
         self.shape = None
@@ -250,6 +256,19 @@ class UpdateEngine:
         ops.conv2d([self._slice(RH, 0, 128, simt, split), self._slice(X, 128, x_cnt, simt, split)],
                    self.weights[f"q{i}"], e, B, H, W, impl)
 
+    def _coarse_grus(self) -> None:
+        """gru32 then gru16 (reference core/update.py:118-128): coarse -> fine; every GRU sees the OLD finer state
+        pooled and the NEW coarser state upsampled."""
+        B, split, simt = self.B, self.impl == "tc", self.impl == "simt"
+        (h0, w0), (h1, w1), (h2, w2) = self.hw
+        X0, X1, X2 = self.X
+        S = self._slice
+        ops.pool2x(S(X1, 0, 128, True, False), S(X2, 128, 128, simt, split), B, h1, w1)
+        self._gru(2, 128)
+        ops.pool2x(S(X0, 0, 128, True, False), S(X1, 128, 128, simt, split), B, h0, w0)
+        ops.interp(S(X2, 0, 128, True, False), S(X1, 256, 128, simt, split), B, h2, w2, h1, w1)
+        self._gru(1, 256)
+
     # ---- one update-block call (reference core/update.py:115-138) -------------------------------
     def step(self, lookup, with_mask: bool = False) -> None:
         """lookup(engine) does the coords / disparity bookkeeping of this iteration and fills self.COR1
@@ -259,15 +278,26 @@ class UpdateEngine:
         X0, X1, X2 = self.X
         Wt = self.weights
         S = self._slice
-        # coarse -> fine; every GRU sees the OLD finer state pooled and the NEW coarser state upsampled
-        ops.pool2x(S(X1, 0, 128, True, False), S(X2, 128, 128, simt, split), B, h1, w1)
-        self._gru(2, 128)
-        ops.pool2x(S(X0, 0, 128, True, False), S(X1, 128, 128, simt, split), B, h0, w0)
-        ops.interp(S(X2, 0, 128, True, False), S(X1, 256, 128, simt, split), B, h2, w2, h1, w1)
-        self._gru(1, 256)
+        E = ops.make_epilogue
+        # The two coarse GRUs and the motion encoder are independent until gru08: they run on two streams (fork /
+        # join with events, also inside a CUDA-graph capture) so that the tail of one branch's persistent kernels
+        # (1/8 and 1/16 resolution fill 3.4 and 0.9 waves of CTA pairs) overlaps the other branch's work.
+        fork = self.two_streams and LaunchProfilerActive() is None
+        main = torch.cuda.current_stream()
+        if fork:
+            if self.side_stream is None or self.side_stream.device != self.device:
+                self.side_stream = torch.cuda.Stream(device=self.device)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.side_stream.wait_event(ev)
+            with torch.cuda.stream(self.side_stream):
+                self._coarse_grus()
+                ev2 = torch.cuda.Event()
+                ev2.record(self.side_stream)
+        else:
+            self._coarse_grus()
         # motion encoder (reference core/update.py:77-85)
         lookup(self)
-        E = ops.make_epilogue
         if not self.fused_enc:
             ops.conv2d([S(self.CORR, 0, self.corr_pad, simt, split)], Wt["convc1"],
                        E(L.EPI_LINEAR, S(self.COR1, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["convc1"].bias), B, h0, w0, impl)
@@ -285,6 +315,8 @@ class UpdateEngine:
         ops.conv2d([S(self.CF, 0, 128, simt, split)], Wt["conv"],
                    E(L.EPI_LINEAR, S(X0, 128, 128, simt, split), act=L.ACT_RELU, bias=Wt["conv"].bias,
                      tail=self.FLOW["f32"]), B, h0, w0, impl)
+        if fork:
+            main.wait_event(ev2)
         ops.interp(S(X1, 0, 128, True, False), S(X0, 256, 128, simt, split), B, h1, w1, h0, w0)
         self._gru(0, 256)
         # flow / disparity head (reference core/update.py:13-14)
