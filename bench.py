@@ -512,6 +512,9 @@ def main():
         run_b200_igev(args)
     else:
         run_b200(args)
+    if args.impl != "reference":
+        from dkt_stereo_b200 import parallel
+        parallel.shutdown()
 
 
 if __name__ == "__main__":

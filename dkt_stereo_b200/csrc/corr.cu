@@ -143,6 +143,19 @@ __device__ __forceinline__ void sample_row(const float* __restrict__ row, int W,
     for (int k = 0; k < 2 * R + 1; ++k) taps[k] = (1.f - a) * v[k] + a * v[k + 1];
 }
 
+// the same in two halves, so that a thread can have the loads of several row samples in flight before it consumes any
+template <int R>
+__device__ __forceinline__ void sample_row_load(const float* __restrict__ row, int W, float x, float* v, float& a) {
+    const float xf = floorf(x);
+    a = x - xf;
+    const int i0 = (int)xf - R;
+#pragma unroll
+    for (int k = 0; k < 2 * R + 2; ++k) {
+        int idx = i0 + k;
+        v[k] = (idx >= 0 && idx < W) ? __ldg(row + idx) : 0.f;
+    }
+}
+
 struct ConstPyrPtrs {
     const float* p[DKT_MAX_LEVELS];
     int          w[DKT_MAX_LEVELS];
@@ -199,79 +212,95 @@ __device__ __forceinline__ void lookup_store_tile(const float* tile, int TS, int
     }
 }
 
-// phase 2, ENC: out[px][n] = relu(b[n] + sum_k tile[px][k] * w[k][n]), n < 64.
-// thread -> 4 consecutive channels (cg = tid & 15) of PPT pixels (pg = tid >> 4).
-template <int PPT>
-__device__ __forceinline__ void lookup_encode_tile(const float* tile, int TS, int C, const float* ws,
+// phase 2, ENC: out[px][n] = relu(b[n] + sum_k tile[k][px] * w[k][n]), n < 64, for a chunk of LK_ENC_PIX = 64 pixels.
+// The tile is K-MAJOR ([k][TSP], pixels contiguous): a thread owns 4 pixels x 4 channels (pg = tid >> 4, cg = tid & 15;
+// 256 threads) and per k needs one 16-byte load of its 4 pixels (2 distinct addresses per warp: broadcast) and one
+// of its 4 weights -- 2 LDS per 16 FMA, against 3 per 8 with a pixel-major tile and 2 x 4 outputs per thread.
+constexpr int LK_ENC_PIX = 64;
+constexpr int LK_ENC_TSP = LK_ENC_PIX + 4;      // row stride of the k-major tile (16-byte aligned rows)
+
+__device__ __forceinline__ void lookup_encode_tile(const float* tile, int C, const float* ws,
                                                    const LookupOut& o, int64_t p0, int npix) {
     const int cg = threadIdx.x & 15, pg = threadIdx.x >> 4;
-    float acc[PPT][4];
+    float acc[4][4];
     const float4 bias = *reinterpret_cast<const float4*>(o.enc_b + cg * 4);
 #pragma unroll
-    for (int i = 0; i < PPT; ++i) { acc[i][0] = bias.x; acc[i][1] = bias.y; acc[i][2] = bias.z; acc[i][3] = bias.w; }
-    const float* trow = tile + pg * PPT * TS;
+    for (int i = 0; i < 4; ++i) { acc[i][0] = bias.x; acc[i][1] = bias.y; acc[i][2] = bias.z; acc[i][3] = bias.w; }
+    const float* tcol = tile + pg * 4;
+    const float* wcol = ws + cg * 4;
+#pragma unroll 2
     for (int k = 0; k < C; ++k) {
-        const float4 w = *reinterpret_cast<const float4*>(ws + k * LK_ENC_N + cg * 4);
+        const float4 a = *reinterpret_cast<const float4*>(tcol + k * LK_ENC_TSP);
+        const float4 w = *reinterpret_cast<const float4*>(wcol + k * LK_ENC_N);
+        const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-        for (int i = 0; i < PPT; ++i) {
-            const float a = trow[i * TS + k];
-            acc[i][0] = fmaf(a, w.x, acc[i][0]);
-            acc[i][1] = fmaf(a, w.y, acc[i][1]);
-            acc[i][2] = fmaf(a, w.z, acc[i][2]);
-            acc[i][3] = fmaf(a, w.w, acc[i][3]);
+        for (int i = 0; i < 4; ++i) {
+            acc[i][0] = fmaf(av[i], w.x, acc[i][0]);
+            acc[i][1] = fmaf(av[i], w.y, acc[i][1]);
+            acc[i][2] = fmaf(av[i], w.z, acc[i][2]);
+            acc[i][3] = fmaf(av[i], w.w, acc[i][3]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < PPT; ++i) {
-        const int px = pg * PPT + i;
+    for (int i = 0; i < 4; ++i) {
+        const int px = pg * 4 + i;
         if (px < npix)
             store_all4(o.enc_out, p0 + px, cg * 4,
                        make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f), fmaxf(acc[i][3], 0.f)));
     }
 }
 
-// RAFT-Stereo: 128 threads = 32 pixels x 4 levels.
+// RAFT-Stereo.  Plain: 128 threads = 32 pixels x 4 levels per chunk.  ENC: 256 threads = 64 pixels x 4 levels.
+// CTAs are persistent over chunks (grid = a few CTAs per SM): the encoder weights are staged once per CTA.
 template <int R, bool ENC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(ENC ? 256 : 128)
 corr1d_lookup_kernel(ConstPyrPtrs pyr, int levels, float* __restrict__ coords_x,
                      const float* __restrict__ delta, int delta_C, float* __restrict__ flow,
                      LookupOut o, int64_t P, int HW, int W1) {
     constexpr int T = 2 * R + 1;
-    constexpr int TS = DKT_MAX_LEVELS * T + 1;                 // odd row stride: conflict-free column walks
-    __shared__ float s_x[LK_PIX];
-    __shared__ __align__(16) float tile[LK_PIX * TS];
+    constexpr int PIX = ENC ? LK_ENC_PIX : LK_PIX;
+    constexpr int TS = DKT_MAX_LEVELS * T + 1;                 // plain: odd row stride, conflict-free column walks
+    __shared__ float s_x[PIX];
+    __shared__ __align__(16) float tile[ENC ? DKT_MAX_LEVELS * T * LK_ENC_TSP : LK_PIX * TS];
     __shared__ __align__(16) float ws[ENC ? DKT_MAX_LEVELS * T * LK_ENC_N : 4];
-    const int64_t p0 = (int64_t)blockIdx.x * LK_PIX;
-    const int npix = (int)((P - p0) < LK_PIX ? (P - p0) : LK_PIX);
     const int C = levels * T;
     if (ENC) {
         for (int i = threadIdx.x; i < C * LK_ENC_N / 4; i += blockDim.x)
             reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(o.enc_w) + i);
     }
-    if (threadIdx.x < npix) {
-        const int64_t p = p0 + threadIdx.x;
-        float cx = coords_x[p];
-        if (delta) {
-            cx += delta[p * delta_C];
-            coords_x[p] = cx;
+    const int64_t nchunks = (P + PIX - 1) / PIX;
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const int64_t p0 = chunk * PIX;
+        const int npix = (int)((P - p0) < PIX ? (P - p0) : PIX);
+        if ((int)threadIdx.x < npix) {
+            const int64_t p = p0 + threadIdx.x;
+            float cx = coords_x[p];
+            if (delta) {
+                cx += delta[p * delta_C];
+                coords_x[p] = cx;
+            }
+            if (flow) flow[p * 2] = cx - (float)(p % W1);
+            s_x[threadIdx.x] = cx;
         }
-        if (flow) flow[p * 2] = cx - (float)(p % W1);
-        s_x[threadIdx.x] = cx;
-    }
-    if (levels == 0) return;
-    __syncthreads();
-    {
-        const int px = threadIdx.x >> 2, l = threadIdx.x & 3;
-        if (px < npix && l < levels) {
-            float taps[T];
-            sample_row<R>(pyr.p[l] + (p0 + px) * pyr.w[l], pyr.w[l], s_x[px] * (1.f / (float)(1 << l)), taps);
+        if (levels == 0) continue;
+        __syncthreads();
+        {
+            const int px = threadIdx.x >> 2, l = threadIdx.x & 3;
+            if (px < npix && l < levels) {
+                float taps[T];
+                sample_row<R>(pyr.p[l] + (p0 + px) * pyr.w[l], pyr.w[l], s_x[px] * (1.f / (float)(1 << l)), taps);
 #pragma unroll
-            for (int k = 0; k < T; ++k) tile[px * TS + l * T + k] = taps[k];
+                for (int k = 0; k < T; ++k) {
+                    if (ENC) tile[(l * T + k) * LK_ENC_TSP + px] = taps[k];
+                    else tile[px * TS + l * T + k] = taps[k];
+                }
+            }
         }
+        __syncthreads();
+        if (ENC) lookup_encode_tile(tile, C, ws, o, p0, npix);
+        else lookup_store_tile(tile, TS, C, o, p0, npix, HW);
+        __syncthreads();                                       // tile and s_x are reused by the next chunk
     }
-    __syncthreads();
-    if (ENC) lookup_encode_tile<4>(tile, TS, C, ws, o, p0, npix);
-    else lookup_store_tile(tile, TS, C, o, p0, npix, HW);
 }
 
 // IGEV: per pixel 2 levels x (Cg geometry channels + 1 init-corr row) row samples; the channel
@@ -287,51 +316,76 @@ __global__ void __launch_bounds__(256)
 geo_lookup_kernel(GeoPtrs g, float* __restrict__ disp, const float* __restrict__ delta, int delta_C,
                   int Cg, int D, int W, LookupOut o, int64_t P, int HW) {
     constexpr int T = 2 * R + 1;
+    constexpr int PIX = ENC ? LK_ENC_PIX : LK_PIX;
     extern __shared__ __align__(16) float gsm[];
     const int G = 2 * (Cg + 1);
     const int C = G * T;
-    const int TS = C | 1;
-    float* s_d = gsm;                         // [32]
-    float* tile = gsm + LK_PIX;               // [32][TS]
-    float* ws = tile + ((LK_PIX * TS + 3) & ~3);   // ENC: [C][64]
-    const int64_t p0 = (int64_t)blockIdx.x * LK_PIX;
-    const int npix = (int)((P - p0) < LK_PIX ? (P - p0) : LK_PIX);
+    const int TS = C | 1;                     // plain: pixel-major rows
+    float* s_d = gsm;                         // [PIX]
+    float* tile = gsm + PIX;                  // plain [32][TS]; ENC k-major [C][LK_ENC_TSP]
+    float* ws = tile + (ENC ? C * LK_ENC_TSP : ((LK_PIX * TS + 3) & ~3));   // ENC: [C][64]
     if (ENC) {
         for (int i = threadIdx.x; i < C * LK_ENC_N / 4; i += blockDim.x)
             reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(o.enc_w) + i);
     }
-    if (threadIdx.x < npix) {
-        const int64_t p = p0 + threadIdx.x;
-        float d = disp[p];
-        if (delta) {
-            d += delta[p * delta_C];
-            disp[p] = d;
+    const int64_t nchunks = (P + PIX - 1) / PIX;
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const int64_t p0 = chunk * PIX;
+        const int npix = (int)((P - p0) < PIX ? (P - p0) : PIX);
+        if ((int)threadIdx.x < npix) {
+            const int64_t p = p0 + threadIdx.x;
+            float d = disp[p];
+            if (delta) {
+                d += delta[p * delta_C];
+                disp[p] = d;
+            }
+            s_d[threadIdx.x] = d;
         }
-        s_d[threadIdx.x] = d;
-    }
-    __syncthreads();
-    for (int it = threadIdx.x; it < npix * G; it += blockDim.x) {
-        const int px = it / G, gi = it - px * G;
-        const int l = gi / (Cg + 1), j = gi - l * (Cg + 1);
-        const int64_t p = p0 + px;
-        const float d = s_d[px];
-        const float inv = l ? 0.5f : 1.f;
-        float taps[T];
-        if (j < Cg) {
-            const int Dl = l ? D / 2 : D;
-            sample_row<R>(g.geo[l] + (p * Cg + j) * Dl, Dl, d * inv, taps);
-        } else {
-            const int Wl = l ? W / 2 : W;
-            const float x = (float)(p % W);
-            sample_row<R>(g.init[l] + p * Wl, Wl, x * inv - d * inv, taps);
-        }
-        float* dst = tile + px * TS + gi * T;
+        __syncthreads();
+        // the gather is latency bound: a thread issues the 10 loads of up to GU row samples before interpolating any
+        constexpr int GU = 3;
+        const float* const geo0 = g.geo[0];
+        const float* const geo1 = g.geo[1];
+        const float* const init0 = g.init[0];
+        const float* const init1 = g.init[1];
+        for (int it0 = threadIdx.x; it0 < npix * G; it0 += blockDim.x * GU) {
+            float v[GU][2 * R + 2], av[GU];
 #pragma unroll
-        for (int k = 0; k < T; ++k) dst[k] = taps[k];
+            for (int u = 0; u < GU; ++u) {
+                const int it = it0 + u * (int)blockDim.x;
+                if (it >= npix * G) continue;
+                const int px = it / G, gi = it - px * G;
+                const int l = gi / (Cg + 1), j = gi - l * (Cg + 1);
+                const int64_t p = p0 + px;
+                const float d = s_d[px];
+                const float inv = l ? 0.5f : 1.f;
+                if (j < Cg) {
+                    const int Dl = l ? D / 2 : D;
+                    sample_row_load<R>((l ? geo1 : geo0) + (p * Cg + j) * Dl, Dl, d * inv, v[u], av[u]);
+                } else {
+                    const int Wl = l ? W / 2 : W;
+                    const float x = (float)(p % W);
+                    sample_row_load<R>((l ? init1 : init0) + p * Wl, Wl, x * inv - d * inv, v[u], av[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < GU; ++u) {
+                const int it = it0 + u * (int)blockDim.x;
+                if (it >= npix * G) continue;
+                const int px = it / G, gi = it - px * G;
+#pragma unroll
+                for (int k = 0; k < T; ++k) {
+                    const float tap = (1.f - av[u]) * v[u][k] + av[u] * v[u][k + 1];
+                    if (ENC) tile[(gi * T + k) * LK_ENC_TSP + px] = tap;
+                    else tile[px * TS + gi * T + k] = tap;
+                }
+            }
+        }
+        __syncthreads();
+        if (ENC) lookup_encode_tile(tile, C, ws, o, p0, npix);
+        else lookup_store_tile(tile, TS, C, o, p0, npix, HW);
+        __syncthreads();                      // tile and s_d are reused by the next chunk
     }
-    __syncthreads();
-    if (ENC) lookup_encode_tile<2>(tile, TS, C, ws, o, p0, npix);
-    else lookup_store_tile(tile, TS, C, o, p0, npix, HW);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -431,12 +485,18 @@ static int corr1d_lookup_launch(const float* const* pyr, int levels, int radius,
     if (want_out && radius != 4) return DKT_E_UNSUPPORTED;   // configs/*/base.json: corr_radius = 4
     if (delta) DKT_CHECK_ARG(delta_C > 0);
     const int64_t P = (int64_t)B * H * W1;
-    const unsigned blocks = (unsigned)ceil_div64(P, LK_PIX);
     const int lv = want_out ? levels : 0;
-    if (enc)
-        corr1d_lookup_kernel<4, true><<<blocks, 128, 0, (cudaStream_t)stream>>>(pp, lv, coords_x, delta, delta_C, flow, o, P, H * W1, W1);
-    else
-        corr1d_lookup_kernel<4, false><<<blocks, 128, 0, (cudaStream_t)stream>>>(pp, lv, coords_x, delta, delta_C, flow, o, P, H * W1, W1);
+    // persistent over pixel chunks: at most 8 CTAs per SM's worth of CTAs, each walking chunks blockIdx.x, +gridDim.x, ..
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    if (enc) {
+        const int64_t chunks = ceil_div64(P, LK_ENC_PIX);
+        corr1d_lookup_kernel<4, true><<<(unsigned)(chunks < cap ? chunks : cap), 256, 0, (cudaStream_t)stream>>>(
+            pp, lv, coords_x, delta, delta_C, flow, o, P, H * W1, W1);
+    } else {
+        const int64_t chunks = ceil_div64(P, LK_PIX);
+        corr1d_lookup_kernel<4, false><<<(unsigned)(chunks < 4 * cap ? chunks : 4 * cap), 128, 0, (cudaStream_t)stream>>>(
+            pp, lv, coords_x, delta, delta_C, flow, o, P, H * W1, W1);
+    }
     DKT_RETURN_LAST();
 }
 
@@ -490,8 +550,8 @@ static int geo_lookup_launch(const float* geo0, const float* geo1, const float* 
     const int64_t P = (int64_t)B * H * W;
     const int Cout = 2 * (C + 1) * 9;
     const int TS = Cout | 1;
-    size_t smem = (size_t)(LK_PIX + ((LK_PIX * TS + 3) & ~3)) * 4;
-    if (enc) smem += (size_t)Cout * LK_ENC_N * 4;
+    size_t smem = enc ? (size_t)(LK_ENC_PIX + Cout * LK_ENC_TSP + Cout * LK_ENC_N) * 4
+                      : (size_t)(LK_PIX + ((LK_PIX * TS + 3) & ~3)) * 4;
     if (smem > 200 * 1024) return DKT_E_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {
@@ -501,11 +561,17 @@ static int geo_lookup_launch(const float* geo0, const float* geo1, const float* 
         attr_set = true;
     }
     GeoPtrs g{{geo0, geo1}, {init0, init1}};
-    const unsigned blocks = (unsigned)ceil_div64(P, LK_PIX);
-    if (enc)
-        geo_lookup_kernel<4, true><<<blocks, 256, smem, (cudaStream_t)stream>>>(g, disp, delta, delta_C, C, D, W, o, P, H * W);
-    else
-        geo_lookup_kernel<4, false><<<blocks, 256, smem, (cudaStream_t)stream>>>(g, disp, delta, delta_C, C, D, W, o, P, H * W);
+    if (enc) {
+        // persistent: as many CTAs as fit (shared memory bound), each walking 64-pixel chunks with the weights staged once
+        const int per_sm = (int)((227 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((227 * 1024) / (smem + 1024));
+        const int64_t chunks = ceil_div64(P, LK_ENC_PIX), cap = (int64_t)kNumSMs * per_sm;
+        geo_lookup_kernel<4, true><<<(unsigned)(chunks < cap ? chunks : cap), 256, smem, (cudaStream_t)stream>>>(
+            g, disp, delta, delta_C, C, D, W, o, P, H * W);
+    } else {
+        const int64_t chunks = ceil_div64(P, LK_PIX), cap = (int64_t)kNumSMs * 32;
+        geo_lookup_kernel<4, false><<<(unsigned)(chunks < cap ? chunks : cap), 256, smem, (cudaStream_t)stream>>>(
+            g, disp, delta, delta_C, C, D, W, o, P, H * W);
+    }
     DKT_RETURN_LAST();
 }
 

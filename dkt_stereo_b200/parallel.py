@@ -66,3 +66,9 @@ def all_reduce_max(value: float, device) -> float:
 def barrier() -> None:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+def shutdown() -> None:
+    """Tear the process group down (silences NCCL's leak warning at interpreter exit)."""
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
