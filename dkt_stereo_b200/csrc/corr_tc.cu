@@ -1,7 +1,7 @@
 // K1 / tensor-core variant: all-pairs 1-D correlation volume on tcgen05, pyramid pooled in the
 // epilogue.  Per image row (b,y) this is C[w1][w2] = scale * sum_d f1[w1][d] * f2[w2][d]:
 // both operands are K-major in the NHWC feature maps, so A = a 128-row w1 tile and B = the whole
-// w2 extent (<= 256) are fetched by 3-D TMA boxes {64 ch, rows, 1} straight into the canonical
+// w2 extent (in blocks of <= 256 columns) are fetched by 3-D TMA boxes {64 ch, rows, 1} straight into the canonical
 // 128-byte-swizzled UMMA layout.  Out-of-range rows / channels are zero-filled by the TMA unit.
 // 3-term bf16 split (hi*hi + lo*hi + hi*lo) with fp32 accumulation in TMEM.
 //
@@ -32,7 +32,7 @@ struct TcCorrParams {
     float* pyr[DKT_MAX_LEVELS];
     int pw[DKT_MAX_LEVELS];
     int levels;
-    int W1, W2, Npad, kblocks, m_tiles, num_tiles;
+    int W1, W2, Npad, kblocks, m_tiles, n_blocks, num_tiles;   // Npad = columns (w2) per tile; n_blocks tiles span W2
     int stages;
     uint32_t acc_cols;
     int vec;                // pw[0] % 8 == 0: every level's row start keeps its vector alignment
@@ -72,16 +72,18 @@ corr1d_build_tc_kernel(const __grid_constant__ TcCorrParams prm) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
-                const int row = tile / prm.m_tiles;          // b*H + y
-                const int m0 = (tile - row * prm.m_tiles) * 128;
+                const int nbk = tile % prm.n_blocks, rm = tile / prm.n_blocks;
+                const int row = rm / prm.m_tiles;            // b*H + y
+                const int m0 = (rm - row * prm.m_tiles) * 128;
+                const int n0 = nbk * prm.Npad;               // first w2 column of this tile
                 for (int kb = 0; kb < prm.kblocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     uint8_t* st = smem + (size_t)stage * stage_bytes;
                     mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                     tma_load_3d(st, &prm.f1[0], &full_bar[stage], kb * 64, m0, row);
                     tma_load_3d(st + CT_A_BYTES, &prm.f1[1], &full_bar[stage], kb * 64, m0, row);
-                    tma_load_3d(st + 2 * CT_A_BYTES, &prm.f2[0], &full_bar[stage], kb * 64, 0, row);
-                    tma_load_3d(st + 2 * CT_A_BYTES + b_bytes, &prm.f2[1], &full_bar[stage], kb * 64, 0, row);
+                    tma_load_3d(st + 2 * CT_A_BYTES, &prm.f2[0], &full_bar[stage], kb * 64, n0, row);
+                    tma_load_3d(st + 2 * CT_A_BYTES + b_bytes, &prm.f2[1], &full_bar[stage], kb * 64, n0, row);
                     if (++stage == prm.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -129,8 +131,10 @@ corr1d_build_tc_kernel(const __grid_constant__ TcCorrParams prm) {
         const int levels = prm.levels;
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, ++t) {
-            const int row = tile / prm.m_tiles;
-            const int m0 = (tile - row * prm.m_tiles) * 128;
+            const int nbk = tile % prm.n_blocks, rm = tile / prm.n_blocks;
+            const int row = rm / prm.m_tiles;
+            const int m0 = (rm - row * prm.m_tiles) * 128;
+            const int n0 = nbk * prm.Npad;
             const uint32_t as = t & 1u, aphase = (t >> 1) & 1u;
             mbar_wait(&tmem_full_bar[as], aphase);
             tcgen05_fence_after();
@@ -152,13 +156,14 @@ corr1d_build_tc_kernel(const __grid_constant__ TcCorrParams prm) {
                     *reinterpret_cast<float4*>(ebuf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
                         make_float4(v[4 * j] * prm.scale, v[4 * j + 1] * prm.scale, v[4 * j + 2] * prm.scale, v[4 * j + 3] * prm.scale);
                 __syncwarp();
-                const int c = c0 + 4 * jg;                              // first of this lane's 4 columns
+                const int c = n0 + c0 + 4 * jg;                         // first of this lane's 4 columns (w2)
+                const bool colok = c0 + 4 * jg < prm.Npad;              // false: zero-filled tail of a 16-column chunk (another tile's columns)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int r = i * 4 + sub;
                     const float4 a = *reinterpret_cast<const float4*>(ebuf + r * 32 + ((jg ^ (r & 7)) << 2));
                     const int w1 = m0 + q * 32 + r;
-                    const bool valid = w1 < prm.W1;
+                    const bool valid = w1 < prm.W1 && colok;
                     const int64_t prow = (int64_t)row * prm.W1 + w1;
                     // pooled values (same association as F.avg_pool2d chains: pairwise means)
                     const float l1a = (a.x + a.y) * 0.5f, l1b = (a.z + a.w) * 0.5f;
@@ -216,7 +221,7 @@ extern "C" int dkt_corr1d_build_tc(const uint16_t* f1_hi, const uint16_t* f1_lo,
     DKT_CHECK_ARG(f1_hi && f1_lo && f2_hi && f2_lo && pyr);
     DKT_CHECK_ARG(B > 0 && D > 0 && H > 0 && W1 > 0 && W2 > 0);
     if (levels < 1 || levels > DKT_MAX_LEVELS) return DKT_E_UNSUPPORTED;
-    if (W2 > 256) return DKT_E_UNSUPPORTED;          // one UMMA N extent; wider rows use the fp32 kernel
+    if (W2 > 4096) return DKT_E_UNSUPPORTED;
     if (D % 8) return DKT_E_ALIGNMENT;
     TcCorrParams prm{};
     int w = W2;
@@ -232,7 +237,10 @@ extern "C" int dkt_corr1d_build_tc(const uint16_t* f1_hi, const uint16_t* f1_lo,
     prm.levels = levels;
     prm.W1 = W1;
     prm.W2 = W2;
-    prm.Npad = (W2 + 15) / 16 * 16;
+    // one UMMA N extent is <= 256 columns: wider rows are cut into n_blocks equal column blocks (multiples of 16,
+    // so every block starts on a level-3 pooling boundary); columns past W2 are zero-filled by TMA and never stored
+    prm.n_blocks = ceil_div(W2, 256);
+    prm.Npad = (ceil_div(W2, prm.n_blocks) + 15) / 16 * 16;
     prm.kblocks = ceil_div(D, 64);
     prm.m_tiles = ceil_div(W1, 128);
     prm.scale = scale;
@@ -265,7 +273,7 @@ extern "C" int dkt_corr1d_build_tc(const uint16_t* f1_hi, const uint16_t* f1_lo,
         if (ce != cudaSuccess) return (int)ce;
         attr_set = true;
     }
-    const int64_t tiles = (int64_t)B * H * prm.m_tiles;
+    const int64_t tiles = (int64_t)B * H * prm.m_tiles * prm.n_blocks;
     if (tiles > 0x7fffffff) return DKT_E_UNSUPPORTED;
     prm.num_tiles = (int)tiles;
     static const int s_sms = [] {

@@ -53,7 +53,7 @@ def corr1d_build(fmap1: torch.Tensor, fmap2: torch.Tensor, levels: int, scale: f
         pyr = alloc_pyramid(B, H, W1, W2, levels, fmap1.device)
     ptrs = L.pointer_array(pyr)
     sb, sd, sh, sw = fmap1.stride()
-    if impl == "tc" and D % 8 == 0 and W2 <= 256:
+    if impl == "tc" and D % 8 == 0:
         hi1 = torch.empty(B, H, W1, D, device=fmap1.device, dtype=torch.bfloat16)
         lo1, hi2, lo2 = torch.empty_like(hi1), torch.empty(B, H, W2, D, device=fmap1.device, dtype=torch.bfloat16), None
         lo2 = torch.empty_like(hi2)
