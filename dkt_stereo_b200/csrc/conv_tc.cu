@@ -60,6 +60,7 @@ struct TcConvParams {
     uint32_t a_part_bytes;          // bytes of one precision (hi or lo) of an A stage
     uint32_t tmem_cols;
     int w_resident;                 // pair kernel: the whole filter stays in the W ring (loaded once per CTA)
+    uint32_t epi_sleep_ns;          // back-off of the epilogue warps' wait for an accumulator (0 = plain polling)
     dkt_epilogue epi;
 };
 
@@ -184,7 +185,7 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
         // this lane's 8 pixels: row = i*4 + sub of the warp's quarter -> (y, x) = (y0 + 2q + (i>>2), x0 + (i&3)*4 + sub)
         const int64_t p00 = ((int64_t)b * H + y0 + 2 * q) * W + x0 + sub;
         const bool yok0 = (y0 + 2 * q) < H, yok1 = (y0 + 2 * q + 1) < H;
-        mbar_wait(&tmem_full_bar[as], aphase);
+        mbar_wait_backoff(&tmem_full_bar[as], aphase, prm.epi_sleep_ns);
         tcgen05_fence_after();
         const uint32_t tbase = tmem_base + as * prm.acc_cols + ((uint32_t)(q * 32) << 16);
         for (int c0 = half * 32; live && c0 < prm.Npad; c0 += 64) {
@@ -383,7 +384,7 @@ __device__ __forceinline__ void conv_tc_epilogue_proj(const TcConvParams& prm, u
         const int b = tile / tiles_per_img;
         const int r = tile - b * tiles_per_img;
         const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
-        mbar_wait(&tmem_full_bar[as], aphase);
+        mbar_wait_backoff(&tmem_full_bar[as], aphase, prm.epi_sleep_ns);
         tcgen05_fence_after();
         const uint32_t tbase = tmem_base + as * prm.acc_cols + ((uint32_t)(q * 32) << 16);
         float acc[PROJ_T];
@@ -1104,6 +1105,10 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         if (s_acc_env >= 2 && (uint32_t)s_acc_env < prm.acc_stages) prm.acc_stages = (uint32_t)s_acc_env;   // A/B knob (2 = old)
     }
     prm.tmem_cols = prm.acc_stages * cols;            // a power of two >= 32 by construction
+    {
+        static const int s_sleep = [] { const char* v = getenv("DKT_EPI_SLEEP_NS"); return v ? atoi(v) : 0; }();
+        prm.epi_sleep_ns = (uint32_t)s_sleep;
+    }
     prm.epi = e;
 
     if (use_pair) {

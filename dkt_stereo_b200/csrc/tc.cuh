@@ -108,6 +108,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Same, for long waits of many threads (the eight epilogue warps waiting for an accumulator): back off with
+// nanosleep between polls so that the spinning warps do not compete for issue slots / power with the MMA warp.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        if (sleep_ns) __nanosleep(sleep_ns);
+        if (globaltimer_ns() - t0 > 4000000000ull) __trap();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // device: TMA tile loads (global -> shared, completion on an mbarrier)
 // ---------------------------------------------------------------------------------------------

@@ -235,6 +235,8 @@ def main():
         "raft_small": lambda: golden_raft_forward(m),
         "raft_shift": lambda: golden_raft_forward(m, 64, 96, 6, "raft_fwd_shift", 1, "shift"),
         "raft_cfg1": lambda: golden_raft_forward(m, 256, 512, 12, "raft_fwd_cfg1", 1, "noise"),
+        # the headline workload itself (BASELINE configs[1] resolution and iteration count), one pair
+        "raft_cfg2": lambda: golden_raft_forward(m, 544, 960, 32, "raft_fwd_cfg2", 1, "noise"),
         "igev_small": lambda: golden_igev_forward(m),
         "igev_mid": lambda: golden_igev_forward(m, 96, 160, 8, "igev_fwd_mid", 1),
     }

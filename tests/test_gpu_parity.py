@@ -364,8 +364,9 @@ def _model(impl, g):
 
 
 @pytest.mark.parametrize("impl", ["simt", "tc", "tc_torchenc"])
-@pytest.mark.parametrize("tag", ["raft_fwd_small", "raft_fwd_shift", "raft_fwd_cfg1"])
+@pytest.mark.parametrize("tag", ["raft_fwd_small", "raft_fwd_shift", "raft_fwd_cfg1", "raft_fwd_cfg2"])
 def test_raft_forward_golden(impl, tag):
+    """raft_fwd_cfg2 = the headline workload itself: 544 x 960, 32 iterations (one pair), the REAL reference's output."""
     from dkt_stereo_b200.synthetic import synthetic_pair
     g = load_golden(tag)
     B, H, W, iters = [int(v) for v in g["meta"]]

@@ -69,6 +69,19 @@ def test_raft_forward_small_and_shift():
         assert stats(lr, g["flow_lr"])[0] < 1e-4
 
 
+def test_raft_forward_headline_config():
+    """The oracle at the benchmark's own resolution and iteration count (544 x 960, 32 iterations, one pair) against
+    the real reference's disparity map (tests/golden/raft_fwd_cfg2.npz, oracle/make_golden.py --only raft_cfg2)."""
+    g = load_golden("raft_fwd_cfg2")
+    B, H, W, iters = [int(v) for v in g["meta"]]
+    assert (H, W, iters) == (544, 960, 32)
+    sd = synthetic_state_dict(golden_shapes(g), seed=0)
+    im1, im2 = synthetic_pair(B, H, W, seed=1234, mode=str(g["mode"]))
+    lr, up = O.raft_forward(sd, im1, im2, iters, RAFT_CFG)
+    mean, mx = stats(up, g["flow_up"])
+    assert mean < 1e-4, (mean, mx)
+
+
 def test_igev_loop_against_reference_forward():
     """The oracle's IGEV hot loop, fed with the pre-loop products the REAL reference forward produced
     (captured by hooks in oracle/make_golden.py), reproduces the reference's final disparity."""
