@@ -44,6 +44,10 @@ __device__ __forceinline__ float4 load_split4(const uint16_t* hi, const uint16_t
     return r;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ---- activations.  expf / tanhf (not the __ intrinsics): the recurrence is sensitive ----
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 

@@ -185,12 +185,43 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
         // this lane's 8 pixels: row = i*4 + sub of the warp's quarter -> (y, x) = (y0 + 2q + (i>>2), x0 + (i&3)*4 + sub)
         const int64_t p00 = ((int64_t)b * H + y0 + 2 * q) * W + x0 + sub;
         const bool yok0 = (y0 + 2 * q) < H, yok1 = (y0 + 2 * q + 1) < H;
+        // L2 prefetch of a chunk's epilogue operands (context / z / h / residual lines of this lane's 8 pixels).  Issued
+        // for the first chunk while the warp would only be waiting for the accumulator, and for chunk k+1 at the start of
+        // chunk k: the operand loads no longer sit with their DRAM latency in the per-tile chain (they were 2x on every
+        // residual conv with a single chunk per warp, ncu r01z).  One lane per pixel row covers the 128-byte line.
+        auto prefetch_chunk = [&](int c0p) {
+            if (jg != 0 || c0p >= prm.Npad) return;
+            const int np = c0p;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (!((i < 4 ? yok0 : yok1) && (x0 + (i & 3) * 4 + sub) < W)) continue;
+                const int64_t p = p00 + (i & 3) * 4 + (i < 4 ? 0 : W);
+                if (KIND == DKT_EPI_LINEAR) {
+                    if (ctx) prefetch_l2(ctx + p * e.ctx_C + e.ctx_c0 + np);
+                    if (res) prefetch_l2(res + p * e.res_C + e.res_c0 + np);
+                    else if (res_hi) {
+                        prefetch_l2(res_hi + p * e.res_C + e.res_c0 + np);
+                        prefetch_l2(res_lo + p * e.res_C + e.res_c0 + np);
+                    }
+                } else {
+                    prefetch_l2(ctx + p * e.ctx_C + e.ctx_c0 + np);
+                    if (KIND == DKT_EPI_GRU_Q) {
+                        prefetch_l2(e.z.f32 + p * e.z.C + e.z.c_begin + np);
+                        prefetch_l2(e.h.f32 + p * e.h.C + e.h.c_begin + np);
+                    } else if (np >= Nh) {
+                        prefetch_l2(e.h.f32 + p * e.h.C + e.h.c_begin + (np - Nh));
+                    }
+                }
+            }
+        };
+        if (live && (KIND != DKT_EPI_LINEAR || ctx || res || res_hi)) prefetch_chunk(half * 32);
         mbar_wait_backoff(&tmem_full_bar[as], aphase, prm.epi_sleep_ns);
         tcgen05_fence_after();
         const uint32_t tbase = tmem_base + as * prm.acc_cols + ((uint32_t)(q * 32) << 16);
         for (int c0 = half * 32; live && c0 < prm.Npad; c0 += 64) {
             float v[32];
             const int ncols = (prm.Npad - c0 >= 32) ? 32 : 16;
+            if (KIND != DKT_EPI_LINEAR || ctx || res || res_hi) prefetch_chunk(c0 + 64);
             __syncwarp();                       // tcgen05.ld is .sync.aligned; also: previous chunk's reads done
             if (ncols == 32) {
                 tmem_ld32(tbase + c0, v);

@@ -255,8 +255,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     return r;
 }
 
+// Relaxed on purpose: the only thing this arrive publishes is "my tcgen05.ld of the accumulator has completed", which
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync already order.  With .release.cluster the follower CTA's
+// epilogue warps waited (ERRBAR) for all their outstanding global stores of the tile to drain before every arrive,
+// which put a store round trip into the per-tile chain of every pair-kernel conv (ncu source view, profiles/r01y).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 // TMA tile loads of a CTA pair: data lands in the executing CTA, the completion bytes are counted on
