@@ -185,17 +185,18 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
         // this lane's 8 pixels: row = i*4 + sub of the warp's quarter -> (y, x) = (y0 + 2q + (i>>2), x0 + (i&3)*4 + sub)
         const int64_t p00 = ((int64_t)b * H + y0 + 2 * q) * W + x0 + sub;
         const bool yok0 = (y0 + 2 * q) < H, yok1 = (y0 + 2 * q + 1) < H;
-        // L2 prefetch of a chunk's epilogue operands (context / z / h / residual lines of this lane's 8 pixels).  Issued
-        // for the first chunk while the warp would only be waiting for the accumulator, and for chunk k+1 at the start of
-        // chunk k: the operand loads no longer sit with their DRAM latency in the per-tile chain (they were 2x on every
-        // residual conv with a single chunk per warp, ncu r01z).  One lane per pixel row covers the 128-byte line.
-        auto prefetch_chunk = [&](int c0p) {
+        // L2 prefetch of epilogue operands (context / z / h / residual lines of this lane's 8 pixels): the first chunk of
+        // the NEXT tile is requested now -- with several accumulator stages the MMA runs ahead, this warp never waits,
+        // and a prefetch issued at the top of the same tile has no lead time (ncu r02b: 30 % of the samples of a
+        // residual conv sat on the first use of the residual) -- and chunk k+1 of this tile at the start of chunk k.
+        // One lane per pixel row covers the 128-byte line.
+        auto prefetch_chunk = [&](int64_t pp00, int px0, bool pyok0, bool pyok1, int c0p) {
             if (jg != 0 || c0p >= prm.Npad) return;
             const int np = c0p;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (!((i < 4 ? yok0 : yok1) && (x0 + (i & 3) * 4 + sub) < W)) continue;
-                const int64_t p = p00 + (i & 3) * 4 + (i < 4 ? 0 : W);
+                if (!((i < 4 ? pyok0 : pyok1) && (px0 + (i & 3) * 4 + sub) < W)) continue;
+                const int64_t p = pp00 + (i & 3) * 4 + (i < 4 ? 0 : W);
                 if (KIND == DKT_EPI_LINEAR) {
                     if (ctx) prefetch_l2(ctx + p * e.ctx_C + e.ctx_c0 + np);
                     if (res) prefetch_l2(res + p * e.res_C + e.res_c0 + np);
@@ -214,14 +215,45 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                 }
             }
         };
-        if (live && (KIND != DKT_EPI_LINEAR || ctx || res || res_hi)) prefetch_chunk(half * 32);
+        const bool has_ops = KIND != DKT_EPI_LINEAR || ctx || res || res_hi;
+        if (has_ops) {
+            if (t == 0 && live) prefetch_chunk(p00, x0, yok0, yok1, half * 32);
+            const int ntile = (item + tw.step) * tw.mul + tw.off;
+            if (item + tw.step < tw.items && ntile < prm.num_tiles) {
+                const int nb = ntile / tiles_per_img;
+                const int nr = ntile - nb * tiles_per_img;
+                const int nty = nr / prm.tiles_x;
+                const int ny0 = nty * TC_TILE_H, nx0 = (nr - nty * prm.tiles_x) * TC_TILE_W;
+                prefetch_chunk(((int64_t)nb * H + ny0 + 2 * q) * W + nx0 + sub, nx0, (ny0 + 2 * q) < H, (ny0 + 2 * q + 1) < H, half * 32);
+            }
+        }
         mbar_wait_backoff(&tmem_full_bar[as], aphase, prm.epi_sleep_ns);
         tcgen05_fence_after();
         const uint32_t tbase = tmem_base + as * prm.acc_cols + ((uint32_t)(q * 32) << 16);
         for (int c0 = half * 32; live && c0 < prm.Npad; c0 += 64) {
             float v[32];
             const int ncols = (prm.Npad - c0 >= 32) ? 32 : 16;
-            if (KIND != DKT_EPI_LINEAR || ctx || res || res_hi) prefetch_chunk(c0 + 64);
+            if (has_ops) prefetch_chunk(p00, x0, yok0, yok1, c0 + 64);
+            // residual of this lane's 8 pixels, requested BEFORE the accumulator is pulled and transposed so that its
+            // latency hides behind that work; kept as raw bits (fp32 x4, or bf16 hi x4 | lo x4) until first use
+            uint4 rraw[8];
+            if (KIND == DKT_EPI_LINEAR && (res || res_hi)) {
+                const int nr_ = c0 + 4 * jg;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    rraw[i] = make_uint4(0u, 0u, 0u, 0u);
+                    if (nr_ + 3 < N && (i < 4 ? yok0 : yok1) && (x0 + (i & 3) * 4 + sub) < W) {
+                        const int64_t off = (p00 + (i & 3) * 4 + (i < 4 ? 0 : W)) * e.res_C + e.res_c0 + nr_;
+                        if (res) {
+                            rraw[i] = __ldg(reinterpret_cast<const uint4*>(res + off));
+                        } else {
+                            const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(res_hi + off));
+                            const uint2 l2 = __ldg(reinterpret_cast<const uint2*>(res_lo + off));
+                            rraw[i] = make_uint4(h2.x, h2.y, l2.x, l2.y);
+                        }
+                    }
+                }
+            }
             __syncwarp();                       // tcgen05.ld is .sync.aligned; also: previous chunk's reads done
             if (ncols == 32) {
                 tmem_ld32(tbase + c0, v);
@@ -269,8 +301,16 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                         av[i4] = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
                         if (KIND == DKT_EPI_LINEAR) {
                             if (ctx) cv[i4] = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n);
-                            if (res) hv[i4] = ld4(res + p * e.res_C + e.res_c0 + n);
-                            else if (res_hi) hv[i4] = load_split4(res_hi, res_lo, p * e.res_C + e.res_c0 + n);
+                            if (res) {
+                                const uint4 rr = rraw[hb * 4 + i4];
+                                hv[i4] = make_float4(__uint_as_float(rr.x), __uint_as_float(rr.y), __uint_as_float(rr.z), __uint_as_float(rr.w));
+                            } else if (res_hi) {
+                                const uint4 rr = rraw[hb * 4 + i4];
+                                hv[i4].x = __uint_as_float(rr.x << 16) + __uint_as_float(rr.z << 16);
+                                hv[i4].y = __uint_as_float(rr.x & 0xffff0000u) + __uint_as_float(rr.z & 0xffff0000u);
+                                hv[i4].z = __uint_as_float(rr.y << 16) + __uint_as_float(rr.w << 16);
+                                hv[i4].w = __uint_as_float(rr.y & 0xffff0000u) + __uint_as_float(rr.w & 0xffff0000u);
+                            }
                             if (ntail) {
                                 const float* tp = tail + p * tail_C;
                                 tv[i4][0] = tp[0];
