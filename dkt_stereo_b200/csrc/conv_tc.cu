@@ -32,6 +32,7 @@
 #include "common.cuh"
 #include "tc.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace dkt {
 
@@ -126,17 +127,32 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr) {
 // bounded the issue rate -- and with it the tensor pipe -- of every conv with N <= 128: ncu r01h.)
 __device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
-// Epilogue warps 2..9 of both persistent kernels (see the header comment of this file), specialised at compile
-// time on the epilogue kind and activation: the instruction count of this loop, not the tensor pipe, bounded every
-// conv while it was generic (ncu r01f: ~8000 issued warp instructions per 32 x 32 chunk; now a few hundred).
+// Epilogue warps 2..9 of the persistent kernels (see the header comment of this file).
 // TMEM lane quarter = warp % 4; the two warps of a quarter take alternate 32-column chunks.  Per chunk a warp
 // pulls 32 columns with tcgen05.ld (thread = pixel), transposes through a swizzled 4 KB smem buffer and continues
 // with lanes = 8 x 16-byte channel groups of 4 pixels, so every global access is a full 128-byte line.
-template <int KIND, int ACT>
+//
+// This loop, not the tensor pipe, bounds every conv whose MMA work per tile is small (N <= 64, or few K steps), and
+// what it is bound by is ISSUE SLOTS: ncu r02b counted 2028 executed warp instructions per 32 x 32 chunk of which
+// ~400 were the actual math / loads / stores and ~1300 integer address arithmetic, predicates and branches of the
+// run-time-generic code.  It is therefore specialised at compile time three ways:
+//   KIND, ACT   epilogue kind and activation
+//   FL          which optional operands / outputs exist (EPF_* bits); EPF_GENERIC keeps the run-time tests
+//   CHECK       per-pixel bounds tests only for tiles that cross the image border (chosen per tile, uniform)
+// and every pointer of a chunk is formed once (64-bit) with 32-bit element offsets per pixel.
+enum : int {
+    EPF_GENERIC = -1,
+    EPF_OUT_F32 = 1, EPF_OUT_SPLIT = 2, EPF_RES_F32 = 4, EPF_RES_SPLIT = 8, EPF_CTX = 16, EPF_STATS = 32, EPF_TAIL = 64,
+};
+
+template <int FL> __device__ __forceinline__ bool epf(int bit, bool runtime) { return FL < 0 ? runtime : (FL & bit) != 0; }
+
+template <int KIND, int ACT, int FL>
 __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, uint32_t tmem_base,
                                                        uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
                                                        uint8_t* epi_smem, int warp, int lane, int tiles_per_img,
                                                        const TileWalk tw) {
+    constexpr bool LIN = KIND == DKT_EPI_LINEAR;
     const int ew = warp - 2;
     const int q = warp & 3;
     const int half = ew >> 2;
@@ -145,13 +161,21 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
     const int N = prm.N, H = prm.H, W = prm.W;
     const int sub = lane >> 3;           // pixel within a group of 4
     const int jg = lane & 7;             // 16-byte channel group within the 32-column chunk
-    // loop-invariant epilogue parameters
-    const float* const bias = e.bias;
+    // ---- what exists (compile time unless FL is EPF_GENERIC) ----
+    const bool has_ctx = LIN ? epf<FL>(EPF_CTX, e.ctx != nullptr) : true;
+    const bool has_res = LIN && epf<FL>(EPF_RES_F32, e.res != nullptr);
+    const bool has_res2 = LIN && !has_res && epf<FL>(EPF_RES_SPLIT, e.res_hi != nullptr);
+    const bool has_tail = LIN && epf<FL>(EPF_TAIL, e.tail != nullptr);
+    const bool has_stats = LIN && epf<FL>(EPF_STATS, e.stats_partial != nullptr);
+    const bool out_f32 = epf<FL>(EPF_OUT_F32, e.out.f32 != nullptr);
+    const bool out_split = epf<FL>(EPF_OUT_SPLIT, e.out.hi != nullptr);
+    const bool out_lo = FL < 0 ? (e.out.lo != nullptr) : out_split;
+    // ---- loop-invariant parameters ----
     const float* const ctx = e.ctx;
-    const float* const res = (KIND == DKT_EPI_LINEAR) ? e.res : nullptr;
-    const uint16_t* const res_hi = (KIND == DKT_EPI_LINEAR && !e.res) ? e.res_hi : nullptr;
+    const float* const res = e.res;
+    const uint16_t* const res_hi = e.res_hi;
     const uint16_t* const res_lo = e.res_lo;
-    const float* const tail = (KIND == DKT_EPI_LINEAR) ? e.tail : nullptr;
+    const float* const tail = e.tail;
     const int tail_C = e.tail_C;
     const float scale = e.scale;
     float* const o_f32 = e.out.f32;
@@ -161,18 +185,17 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
     const int Nh = N >> 1;
     // a tail (e.g. the flow field appended to the motion features) that completes the last 4-group of an
     // N % 4 != 0 conv is merged into that group's vector store; otherwise it is copied after the chunk loop
-    const bool tail_merged = tail && (N & 3) && (((N + tail_C) & 3) == 0) && tail_C < 4;
+    const bool tail_merged = has_tail && (N & 3) && (((N + tail_C) & 3) == 0) && tail_C < 4;
     const int Nvec = tail_merged ? N + tail_C : N;
-    // per-tile channel statistics of the stored values (InstanceNorm fused into the producing conv; LINEAR only)
-    float* const stats_out = (KIND == DKT_EPI_LINEAR) ? e.stats_partial : nullptr;
+    float* const stats_out = e.stats_partial;
     // the bias lives in shared memory: a global load here would sit in the latency chain of every chunk
     float* const s_bias = reinterpret_cast<float*>(epi_smem + TC2_EPI_TILE_BYTES);
-    if (KIND == DKT_EPI_LINEAR) {
-        for (int i = (int)threadIdx.x - 64; i < 256; i += TC2_EPI_WARPS * 32) s_bias[i] = (i < N && bias) ? __ldg(bias + i) : 0.f;
+    if (LIN) {
+        for (int i = (int)threadIdx.x - 64; i < 256; i += TC2_EPI_WARPS * 32) s_bias[i] = (i < N && e.bias) ? __ldg(e.bias + i) : 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    // accumulator stages: the MMA warp may run acc_stages - 1 tiles ahead of this drain, which hides the
-    // commit -> wake-up and arrive -> wake-up latencies of the hand-off (they bounded the N <= 128 convs at 2 stages)
+    const bool has_ops = !LIN || has_ctx || has_res || has_res2;     // operands fetched from HBM per pixel
+    // accumulator stages: the MMA warp may run acc_stages - 1 tiles ahead of this drain
     const uint32_t nacc = prm.acc_stages;
     uint32_t t = 0, as = 0, aphase = 0;
     for (int item = tw.first; item < tw.items; item += tw.step, ++t) {
@@ -185,37 +208,34 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
         // this lane's 8 pixels: row = i*4 + sub of the warp's quarter -> (y, x) = (y0 + 2q + (i>>2), x0 + (i&3)*4 + sub)
         const int64_t p00 = ((int64_t)b * H + y0 + 2 * q) * W + x0 + sub;
         const bool yok0 = (y0 + 2 * q) < H, yok1 = (y0 + 2 * q + 1) < H;
-        // L2 prefetch of epilogue operands (context / z / h / residual lines of this lane's 8 pixels): the first chunk of
-        // the NEXT tile is requested now -- with several accumulator stages the MMA runs ahead, this warp never waits,
-        // and a prefetch issued at the top of the same tile has no lead time (ncu r02b: 30 % of the samples of a
-        // residual conv sat on the first use of the residual) -- and chunk k+1 of this tile at the start of chunk k.
-        // One lane per pixel row covers the 128-byte line.
+        const bool interior = (y0 + TC_TILE_H <= H) && (x0 + TC_TILE_W <= W);   // uniform: no per-pixel bounds tests needed
+        // L2 prefetch of the operand lines (context / z / h / residual) of a chunk; one lane per pixel row covers the
+        // 128-byte line.  The first chunk of the NEXT tile is requested now (the MMA runs ahead, so this warp does not
+        // wait and a same-tile prefetch has no lead time), chunk k+1 of this tile at the start of chunk k.
         auto prefetch_chunk = [&](int64_t pp00, int px0, bool pyok0, bool pyok1, int c0p) {
             if (jg != 0 || c0p >= prm.Npad) return;
-            const int np = c0p;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (!((i < 4 ? pyok0 : pyok1) && (px0 + (i & 3) * 4 + sub) < W)) continue;
                 const int64_t p = pp00 + (i & 3) * 4 + (i < 4 ? 0 : W);
-                if (KIND == DKT_EPI_LINEAR) {
-                    if (ctx) prefetch_l2(ctx + p * e.ctx_C + e.ctx_c0 + np);
-                    if (res) prefetch_l2(res + p * e.res_C + e.res_c0 + np);
-                    else if (res_hi) {
-                        prefetch_l2(res_hi + p * e.res_C + e.res_c0 + np);
-                        prefetch_l2(res_lo + p * e.res_C + e.res_c0 + np);
+                if (LIN) {
+                    if (has_ctx) prefetch_l2(ctx + p * e.ctx_C + e.ctx_c0 + c0p);
+                    if (has_res) prefetch_l2(res + p * e.res_C + e.res_c0 + c0p);
+                    if (has_res2) {
+                        prefetch_l2(res_hi + p * e.res_C + e.res_c0 + c0p);
+                        prefetch_l2(res_lo + p * e.res_C + e.res_c0 + c0p);
                     }
                 } else {
-                    prefetch_l2(ctx + p * e.ctx_C + e.ctx_c0 + np);
+                    prefetch_l2(ctx + p * e.ctx_C + e.ctx_c0 + c0p);
                     if (KIND == DKT_EPI_GRU_Q) {
-                        prefetch_l2(e.z.f32 + p * e.z.C + e.z.c_begin + np);
-                        prefetch_l2(e.h.f32 + p * e.h.C + e.h.c_begin + np);
-                    } else if (np >= Nh) {
-                        prefetch_l2(e.h.f32 + p * e.h.C + e.h.c_begin + (np - Nh));
+                        prefetch_l2(e.z.f32 + p * e.z.C + e.z.c_begin + c0p);
+                        prefetch_l2(e.h.f32 + p * e.h.C + e.h.c_begin + c0p);
+                    } else if (c0p >= Nh) {
+                        prefetch_l2(e.h.f32 + p * e.h.C + e.h.c_begin + (c0p - Nh));
                     }
                 }
             }
         };
-        const bool has_ops = KIND != DKT_EPI_LINEAR || ctx || res || res_hi;
         if (has_ops) {
             if (t == 0 && live) prefetch_chunk(p00, x0, yok0, yok1, half * 32);
             const int ntile = (item + tw.step) * tw.mul + tw.off;
@@ -233,18 +253,19 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
         for (int c0 = half * 32; live && c0 < prm.Npad; c0 += 64) {
             float v[32];
             const int ncols = (prm.Npad - c0 >= 32) ? 32 : 16;
+            const int n = c0 + 4 * jg;
             if (has_ops) prefetch_chunk(p00, x0, yok0, yok1, c0 + 64);
             // residual of this lane's 8 pixels, requested BEFORE the accumulator is pulled and transposed so that its
             // latency hides behind that work; kept as raw bits (fp32 x4, or bf16 hi x4 | lo x4) until first use
             uint4 rraw[8];
-            if (KIND == DKT_EPI_LINEAR && (res || res_hi)) {
-                const int nr_ = c0 + 4 * jg;
+            if (has_res || has_res2) {
+                const int64_t rbase = p00 * e.res_C + e.res_c0 + n;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     rraw[i] = make_uint4(0u, 0u, 0u, 0u);
-                    if (nr_ + 3 < N && (i < 4 ? yok0 : yok1) && (x0 + (i & 3) * 4 + sub) < W) {
-                        const int64_t off = (p00 + (i & 3) * 4 + (i < 4 ? 0 : W)) * e.res_C + e.res_c0 + nr_;
-                        if (res) {
+                    if (n + 3 < N && (interior || ((i < 4 ? yok0 : yok1) && (x0 + (i & 3) * 4 + sub) < W))) {
+                        const int64_t off = rbase + (int64_t)(((i & 3) * 4 + (i < 4 ? 0 : W)) * e.res_C);
+                        if (has_res) {
                             rraw[i] = __ldg(reinterpret_cast<const uint4*>(res + off));
                         } else {
                             const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(res_hi + off));
@@ -269,143 +290,168 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                 *reinterpret_cast<float4*>(ebuf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
                     make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             __syncwarp();
-            const int n = c0 + 4 * jg;
             float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = make_float4(0.f, 0.f, 0.f, 0.f);
             const bool vec = (n + 3 < Nvec);
             if (n >= Nvec) {
                 // padded columns (lane-divergent only in the last chunk): nothing to store
-            } else if (KIND != DKT_EPI_LINEAR || vec) {
+            } else if (!LIN || vec) {
                 // ---------------- vector path: 4 channels x 8 pixels per lane ----------------
                 float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                 int ntail = 0;                   // components of this group that come from the tail
-                if (KIND == DKT_EPI_LINEAR) {
+                if (LIN) {
                     bv = *reinterpret_cast<const float4*>(s_bias + n);      // zero beyond N
-                    if (n + 3 >= N) ntail = n + 4 - N;                     // the merged-tail group
+                    if (has_tail && n + 3 >= N) ntail = n + 4 - N;          // the merged-tail group
                 }
-                // two batches of 4 pixels (tile rows 2q and 2q + 1): all global loads of a batch are issued before
-                // its math and stores, so their latencies overlap (stores may alias the loads as far as the compiler
-                // knows, which used to serialise one load round trip per pixel)
+                // chunk-constant 64-bit bases; per pixel only a 32-bit element offset is added
+                // (LINEAR only: the GRU kinds hide their epilogue behind long MMA phases and are register-bound instead,
+                // so they form each address per pixel from the few values they keep live)
+                const int nout = (KIND == DKT_EPI_GRU_ZR) ? n - Nh : n;
+                const int64_t obase = p00 * oC + oc0 + nout;
+                float* const pf = o_f32 + obase;
+                uint16_t* const ph = o_hi + obase;
+                uint16_t* const pl = o_lo + obase;
+                const float* const pc = ctx + (p00 * e.ctx_C + e.ctx_c0 + n);
+                const float* const pt = tail + p00 * tail_C;
+                // two batches of 4 pixels (tile rows 2q and 2q + 1): all operand loads of a batch are issued before its
+                // math and stores, so their latencies overlap
+                auto pixels = [&](auto check_tag) {
+                    constexpr bool CHECK = decltype(check_tag)::value;
 #pragma unroll
-                for (int hb = 0; hb < 2; ++hb) {
-                    const bool yok = hb ? yok1 : yok0;
-                    const int64_t pb = p00 + (hb ? W : 0);
-                    float4 av[4], cv[4], zv[4], hv[4];
-                    float tv[4][3];
-                    bool ok[4];
+                    for (int hb = 0; hb < 2; ++hb) {
+                        float4 av[4], cv[4], zv[4], hv[4];
+                        float tv[4][3];
+                        bool ok[4];
 #pragma unroll
-                    for (int i4 = 0; i4 < 4; ++i4) {
-                        const int row = hb * 16 + i4 * 4 + sub;
-                        ok[i4] = yok && (x0 + i4 * 4 + sub) < W;
-                        if (!ok[i4]) continue;
-                        const int64_t p = pb + i4 * 4;
-                        av[i4] = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
-                        if (KIND == DKT_EPI_LINEAR) {
-                            if (ctx) cv[i4] = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n);
-                            if (res) {
-                                const uint4 rr = rraw[hb * 4 + i4];
-                                hv[i4] = make_float4(__uint_as_float(rr.x), __uint_as_float(rr.y), __uint_as_float(rr.z), __uint_as_float(rr.w));
-                            } else if (res_hi) {
-                                const uint4 rr = rraw[hb * 4 + i4];
-                                hv[i4].x = __uint_as_float(rr.x << 16) + __uint_as_float(rr.z << 16);
-                                hv[i4].y = __uint_as_float(rr.x & 0xffff0000u) + __uint_as_float(rr.z & 0xffff0000u);
-                                hv[i4].z = __uint_as_float(rr.y << 16) + __uint_as_float(rr.w << 16);
-                                hv[i4].w = __uint_as_float(rr.y & 0xffff0000u) + __uint_as_float(rr.w & 0xffff0000u);
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            const int row = hb * 16 + i4 * 4 + sub;
+                            ok[i4] = !CHECK || ((hb ? yok1 : yok0) && (x0 + i4 * 4 + sub) < W);
+                            if (!ok[i4]) continue;
+                            const int d = i4 * 4 + hb * W;                  // pixel delta from p00
+                            av[i4] = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
+                            if (LIN) {
+                                if (has_ctx) cv[i4] = ld4(pc + d * e.ctx_C);
+                                if (ntail) {
+                                    const float* tp = pt + d * tail_C;
+                                    tv[i4][0] = tp[0];
+                                    if (ntail > 1) tv[i4][1] = tp[1];
+                                    if (ntail > 2) tv[i4][2] = tp[2];
+                                }
+                            } else if (KIND == DKT_EPI_GRU_ZR) {
+                                const int64_t p = p00 + d;
+                                cv[i4] = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n);
+                                if (n >= Nh) hv[i4] = ld4(e.h.f32 + p * e.h.C + e.h.c_begin + (n - Nh));
+                            } else {
+                                const int64_t p = p00 + d;
+                                cv[i4] = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n);
+                                zv[i4] = ld4(e.z.f32 + p * e.z.C + e.z.c_begin + n);
+                                hv[i4] = ld4(e.h.f32 + p * e.h.C + e.h.c_begin + n);
                             }
-                            if (ntail) {
-                                const float* tp = tail + p * tail_C;
-                                tv[i4][0] = tp[0];
-                                if (ntail > 1) tv[i4][1] = tp[1];
-                                if (ntail > 2) tv[i4][2] = tp[2];
+                        }
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            if (!ok[i4]) continue;
+                            const int d = i4 * 4 + hb * W;
+                            float4 a = av[i4];
+                            if (LIN) {
+                                a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
+                                if (has_ctx) { a.x += cv[i4].x; a.y += cv[i4].y; a.z += cv[i4].z; a.w += cv[i4].w; }
+                                a.x = act_ct<ACT>(a.x) * scale; a.y = act_ct<ACT>(a.y) * scale;
+                                a.z = act_ct<ACT>(a.z) * scale; a.w = act_ct<ACT>(a.w) * scale;
+                                if (has_res || has_res2) {   // residual block tail: relu(x + y)
+                                    const uint4 rr = rraw[hb * 4 + i4];
+                                    float4 rv;
+                                    if (has_res) {
+                                        rv = make_float4(__uint_as_float(rr.x), __uint_as_float(rr.y), __uint_as_float(rr.z), __uint_as_float(rr.w));
+                                    } else {
+                                        rv.x = __uint_as_float(rr.x << 16) + __uint_as_float(rr.z << 16);
+                                        rv.y = __uint_as_float(rr.x & 0xffff0000u) + __uint_as_float(rr.z & 0xffff0000u);
+                                        rv.z = __uint_as_float(rr.y << 16) + __uint_as_float(rr.w << 16);
+                                        rv.w = __uint_as_float(rr.y & 0xffff0000u) + __uint_as_float(rr.w & 0xffff0000u);
+                                    }
+                                    a.x = fmaxf(a.x + rv.x, 0.f); a.y = fmaxf(a.y + rv.y, 0.f);
+                                    a.z = fmaxf(a.z + rv.z, 0.f); a.w = fmaxf(a.w + rv.w, 0.f);
+                                }
+                                if (ntail) {             // 1..3 trailing components are copied from the tail tensor
+                                    if (ntail == 1) a.w = tv[i4][0];
+                                    else if (ntail == 2) { a.z = tv[i4][0]; a.w = tv[i4][1]; }
+                                    else { a.y = tv[i4][0]; a.z = tv[i4][1]; a.w = tv[i4][2]; }
+                                }
+                            } else if (KIND == DKT_EPI_GRU_ZR) {
+                                a.x = sigmoidf_acc(a.x + cv[i4].x); a.y = sigmoidf_acc(a.y + cv[i4].y);
+                                a.z = sigmoidf_acc(a.z + cv[i4].z); a.w = sigmoidf_acc(a.w + cv[i4].w);
+                                if (n < Nh) {
+                                    *reinterpret_cast<float4*>(e.z.f32 + (p00 + d) * e.z.C + e.z.c_begin + n) = a;
+                                    continue;
+                                }
+                                a.x *= hv[i4].x; a.y *= hv[i4].y; a.z *= hv[i4].z; a.w *= hv[i4].w;
+                            } else {                     // GRU_Q
+                                const float4 z = zv[i4], h = hv[i4];
+                                a.x = (1.f - z.x) * h.x + z.x * tanhf(a.x + cv[i4].x);
+                                a.y = (1.f - z.y) * h.y + z.y * tanhf(a.y + cv[i4].y);
+                                a.z = (1.f - z.z) * h.z + z.z * tanhf(a.z + cv[i4].z);
+                                a.w = (1.f - z.w) * h.w + z.w * tanhf(a.w + cv[i4].w);
                             }
-                        } else if (KIND == DKT_EPI_GRU_ZR) {
-                            cv[i4] = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n);
-                            if (n >= Nh) hv[i4] = ld4(e.h.f32 + p * e.h.C + e.h.c_begin + (n - Nh));
-                        } else {
-                            cv[i4] = ld4(ctx + p * e.ctx_C + e.ctx_c0 + n);
-                            zv[i4] = ld4(e.z.f32 + p * e.z.C + e.z.c_begin + n);
-                            hv[i4] = ld4(e.h.f32 + p * e.h.C + e.h.c_begin + n);
+                            if (has_stats) {
+                                ssum.x += a.x; ssum.y += a.y; ssum.z += a.z; ssum.w += a.w;
+                                ssq.x = fmaf(a.x, a.x, ssq.x); ssq.y = fmaf(a.y, a.y, ssq.y);
+                                ssq.z = fmaf(a.z, a.z, ssq.z); ssq.w = fmaf(a.w, a.w, ssq.w);
+                            }
+                            if (LIN) {
+                                const int od = d * oC;
+                                if (out_f32) *reinterpret_cast<float4*>(pf + od) = a;
+                                if (out_split) {
+                                    uint32_t h0, l0, h1, l1;
+                                    split_bf16x2(a.x, a.y, h0, l0);
+                                    split_bf16x2(a.z, a.w, h1, l1);
+                                    *reinterpret_cast<uint2*>(ph + od) = make_uint2(h0, h1);
+                                    if (out_lo) *reinterpret_cast<uint2*>(pl + od) = make_uint2(l0, l1);
+                                }
+                            } else {
+                                const int64_t off = (p00 + d) * oC + oc0 + nout;
+                                if (out_f32) *reinterpret_cast<float4*>(o_f32 + off) = a;
+                                if (out_split) {
+                                    uint32_t h0, l0, h1, l1;
+                                    split_bf16x2(a.x, a.y, h0, l0);
+                                    split_bf16x2(a.z, a.w, h1, l1);
+                                    *reinterpret_cast<uint2*>(o_hi + off) = make_uint2(h0, h1);
+                                    if (out_lo) *reinterpret_cast<uint2*>(o_lo + off) = make_uint2(l0, l1);
+                                }
+                            }
                         }
                     }
-#pragma unroll
-                    for (int i4 = 0; i4 < 4; ++i4) {
-                        if (!ok[i4]) continue;
-                        const int64_t p = pb + i4 * 4;
-                        float4 a = av[i4];
-                        if (KIND == DKT_EPI_LINEAR) {
-                            a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
-                            if (ctx) { a.x += cv[i4].x; a.y += cv[i4].y; a.z += cv[i4].z; a.w += cv[i4].w; }
-                            a.x = act_ct<ACT>(a.x) * scale; a.y = act_ct<ACT>(a.y) * scale;
-                            a.z = act_ct<ACT>(a.z) * scale; a.w = act_ct<ACT>(a.w) * scale;
-                            if (res || res_hi) {     // residual block tail: relu(x + y)
-                                a.x = fmaxf(a.x + hv[i4].x, 0.f); a.y = fmaxf(a.y + hv[i4].y, 0.f);
-                                a.z = fmaxf(a.z + hv[i4].z, 0.f); a.w = fmaxf(a.w + hv[i4].w, 0.f);
-                            }
-                            if (ntail) {             // 1..3 trailing components are copied from the tail tensor
-                                if (ntail == 1) a.w = tv[i4][0];
-                                else if (ntail == 2) { a.z = tv[i4][0]; a.w = tv[i4][1]; }
-                                else { a.y = tv[i4][0]; a.z = tv[i4][1]; a.w = tv[i4][2]; }
-                            }
-                        } else if (KIND == DKT_EPI_GRU_ZR) {
-                            a.x = sigmoidf_acc(a.x + cv[i4].x); a.y = sigmoidf_acc(a.y + cv[i4].y);
-                            a.z = sigmoidf_acc(a.z + cv[i4].z); a.w = sigmoidf_acc(a.w + cv[i4].w);
-                            if (n < Nh) {
-                                *reinterpret_cast<float4*>(e.z.f32 + p * e.z.C + e.z.c_begin + n) = a;
-                                continue;
-                            }
-                            a.x *= hv[i4].x; a.y *= hv[i4].y; a.z *= hv[i4].z; a.w *= hv[i4].w;
-                        } else {                     // GRU_Q
-                            const float4 z = zv[i4], h = hv[i4];
-                            a.x = (1.f - z.x) * h.x + z.x * tanhf(a.x + cv[i4].x);
-                            a.y = (1.f - z.y) * h.y + z.y * tanhf(a.y + cv[i4].y);
-                            a.z = (1.f - z.z) * h.z + z.z * tanhf(a.z + cv[i4].z);
-                            a.w = (1.f - z.w) * h.w + z.w * tanhf(a.w + cv[i4].w);
-                        }
-                        if (KIND == DKT_EPI_LINEAR && stats_out) {
-                            ssum.x += a.x; ssum.y += a.y; ssum.z += a.z; ssum.w += a.w;
-                            ssq.x = fmaf(a.x, a.x, ssq.x); ssq.y = fmaf(a.y, a.y, ssq.y);
-                            ssq.z = fmaf(a.z, a.z, ssq.z); ssq.w = fmaf(a.w, a.w, ssq.w);
-                        }
-                        const int64_t off = p * oC + oc0 + (KIND == DKT_EPI_GRU_ZR ? n - Nh : n);
-                        if (o_f32) *reinterpret_cast<float4*>(o_f32 + off) = a;
-                        if (o_hi) {
-                            uint32_t h0, l0, h1, l1;
-                            split_bf16x2(a.x, a.y, h0, l0);
-                            split_bf16x2(a.z, a.w, h1, l1);
-                            *reinterpret_cast<uint2*>(o_hi + off) = make_uint2(h0, h1);
-                            if (o_lo) *reinterpret_cast<uint2*>(o_lo + off) = make_uint2(l0, l1);
-                        }
-                    }
-                }
+                };
+                if (LIN && interior) pixels(std::false_type{});
+                else pixels(std::true_type{});
             } else {
-                // ---------------- scalar path: partially valid last group of a LINEAR conv ----------------
+                // ---------------- scalar path: partially valid last group of a LINEAR conv (rare shapes) ----------------
                 for (int i = 0; i < 8; ++i) {
                     const int row = i * 4 + sub;
                     const int xo = (i & 3) * 4;
                     if (!((i < 4 ? yok0 : yok1) && (x0 + xo + sub) < W)) continue;
                     const int64_t p = p00 + xo + (i < 4 ? 0 : W);
                     const float4 a = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
-                    const float av[4] = {a.x, a.y, a.z, a.w};
-                    for (int u = 0; u < 4; ++u) if (n + u < N) tc_epilogue1<ACT>(e, p, n + u, av[u]);
+                    const float av1[4] = {a.x, a.y, a.z, a.w};
+                    for (int u = 0; u < 4; ++u) if (n + u < N) tc_epilogue1<ACT>(e, p, n + u, av1[u]);
                 }
             }
-            if (KIND == DKT_EPI_LINEAR && stats_out) {
+            if (has_stats) {
                 // fixed-order reduction (deterministic): 8 pixels per lane above, then the warp's 4 pixel groups by
                 // shuffles; the warp's 32-pixel sums go straight to HBM ([tile][quarter][sum, sumsq][N]) -- no cross-warp
                 // exchange in the epilogue; quarters and tiles are added up by dkt_instnorm_finalize_tiles
-                float r[8] = {ssum.x, ssum.y, ssum.z, ssum.w, ssq.x, ssq.y, ssq.z, ssq.w};
+                float rs[8] = {ssum.x, ssum.y, ssum.z, ssum.w, ssq.x, ssq.y, ssq.z, ssq.w};
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    r[u] += __shfl_xor_sync(0xffffffffu, r[u], 8);
-                    r[u] += __shfl_xor_sync(0xffffffffu, r[u], 16);
+                    rs[u] += __shfl_xor_sync(0xffffffffu, rs[u], 8);
+                    rs[u] += __shfl_xor_sync(0xffffffffu, rs[u], 16);
                 }
                 if (sub == 0 && n < N) {
                     float* sp = stats_out + (((int64_t)tile * 4 + q) * 2) * N + n;
-                    *reinterpret_cast<float4*>(sp) = make_float4(r[0], r[1], r[2], r[3]);
-                    *reinterpret_cast<float4*>(sp + N) = make_float4(r[4], r[5], r[6], r[7]);
+                    *reinterpret_cast<float4*>(sp) = make_float4(rs[0], rs[1], rs[2], rs[3]);
+                    *reinterpret_cast<float4*>(sp + N) = make_float4(rs[4], rs[5], rs[6], rs[7]);
                 }
             }
         }
-        if (live && tail && !tail_merged && half == 0) {
+        if (live && has_tail && !tail_merged && half == 0) {
             const int m = q * 32 + lane;
             const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
             if (y < H && x < W) {
@@ -623,7 +669,7 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
         if constexpr (KIND == DKT_EPI_PROJ)
             conv_tc_epilogue_proj<ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
         else
-            conv_tc_epilogue_warps<KIND, ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+            conv_tc_epilogue_warps<KIND, ACT, EPF_GENERIC>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
     }
 
     tcgen05_fence_before();
@@ -779,7 +825,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
         if constexpr (KIND == DKT_EPI_PROJ)
             conv_tc_epilogue_proj<ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
         else
-            conv_tc_epilogue_warps<KIND, ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+            conv_tc_epilogue_warps<KIND, ACT, EPF_GENERIC>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
     }
 
     tcgen05_fence_before();
@@ -803,7 +849,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
 //   roles      warp 0 = TMA producer (both CTAs), warp 1 = MMA issuer (leader only; allocates TMEM in both),
 //              warps 2..9 = epilogue of the CTA's own tile (TMEM lanes 0..127 of each CTA = its 128 pixels).
 // ---------------------------------------------------------------------------------------------
-template <int KIND, int ACT, int KB>
+template <int KIND, int ACT, int KB, int FL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
     extern __shared__ uint8_t smem_raw[];
@@ -952,7 +998,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
         if constexpr (KIND == DKT_EPI_PROJ)
             conv_tc_epilogue_proj<ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
         else
-            conv_tc_epilogue_warps<KIND, ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+            conv_tc_epilogue_warps<KIND, ACT, FL>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
     }
 
     // neither CTA may leave (or free TMEM) while its peer can still reach its shared memory / barriers
@@ -968,34 +1014,92 @@ using namespace dkt;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// ---- launch: one instantiation per (kernel family, epilogue kind, activation) ----
+// ---- launch: one instantiation per (kernel family, epilogue kind, activation[, K block, operand flags]) ----
 enum ConvFamily { FAM_PATCH32, FAM_PATCH64, FAM_TAP64, FAM_PAIR, FAM_PAIR_K32 };
+
+// which optional operands / outputs a LINEAR epilogue uses, as EPF_* bits (EPF_GENERIC if not expressible)
+static int epilogue_flags(const dkt_epilogue& e) {
+    if (e.kind == DKT_EPI_GRU_ZR || e.kind == DKT_EPI_GRU_Q) {       // only the output precisions vary
+        if (e.out.hi && !e.out.lo) return EPF_GENERIC;
+        return (e.out.f32 ? EPF_OUT_F32 : 0) | (e.out.hi ? EPF_OUT_SPLIT : 0);
+    }
+    if (e.kind != DKT_EPI_LINEAR) return EPF_GENERIC;
+    int fl = 0;
+    if (e.out.f32) fl |= EPF_OUT_F32;
+    if (e.out.hi) {
+        if (!e.out.lo) return EPF_GENERIC;
+        fl |= EPF_OUT_SPLIT;
+    }
+    if (e.res) fl |= EPF_RES_F32;
+    else if (e.res_hi) fl |= EPF_RES_SPLIT;
+    if (e.ctx) fl |= EPF_CTX;
+    if (e.stats_partial) fl |= EPF_STATS;
+    if (e.tail) fl |= EPF_TAIL;
+    return fl;
+}
+
+template <int KIND, int ACT, int KB, int FL>
+static int launch_pair(const TcConvParams& prm, unsigned grid, size_t smem_bytes, cudaStream_t st) {
+    static bool attr_set = false;                    // per instantiation
+    if (!attr_set) {
+        cudaError_t ce = cudaFuncSetAttribute(conv_tc_pair_kernel<KIND, ACT, KB, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce != cudaSuccess) return (int)ce;
+        attr_set = true;
+    }
+    conv_tc_pair_kernel<KIND, ACT, KB, FL><<<grid, TC2_THREADS, smem_bytes, st>>>(prm);   // grid even (cluster of 2)
+    DKT_RETURN_LAST();
+}
+
+// pair kernel: the hot LINEAR operand combinations of the two models get their own instantiation (see
+// conv_tc_epilogue_warps); everything else runs the run-time-generic epilogue
+template <int KIND, int ACT, int KB>
+static int launch_pair_fl(const TcConvParams& prm, unsigned grid, size_t smem_bytes, cudaStream_t st) {
+    if constexpr (KIND == DKT_EPI_LINEAR && ACT == DKT_ACT_RELU) {
+        const int fl = epilogue_flags(prm.epi);
+        if (fl == EPF_OUT_SPLIT) return launch_pair<KIND, ACT, KB, EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);
+        if constexpr (KB == 64) {
+            if (fl == (EPF_OUT_SPLIT | EPF_RES_SPLIT)) return launch_pair<KIND, ACT, KB, EPF_OUT_SPLIT | EPF_RES_SPLIT>(prm, grid, smem_bytes, st);
+            if (fl == (EPF_OUT_SPLIT | EPF_RES_F32)) return launch_pair<KIND, ACT, KB, EPF_OUT_SPLIT | EPF_RES_F32>(prm, grid, smem_bytes, st);
+            if (fl == (EPF_OUT_SPLIT | EPF_TAIL)) return launch_pair<KIND, ACT, KB, EPF_OUT_SPLIT | EPF_TAIL>(prm, grid, smem_bytes, st);
+        }
+    }
+    if constexpr (KIND == DKT_EPI_LINEAR && ACT == DKT_ACT_NONE) {
+        const int fl = epilogue_flags(prm.epi);
+        if (fl == (EPF_OUT_F32 | EPF_STATS)) return launch_pair<KIND, ACT, KB, EPF_OUT_F32 | EPF_STATS>(prm, grid, smem_bytes, st);
+        if constexpr (KB == 64) {
+            if (fl == EPF_OUT_F32) return launch_pair<KIND, ACT, KB, EPF_OUT_F32>(prm, grid, smem_bytes, st);
+        }
+    }
+    if constexpr (KIND == DKT_EPI_GRU_ZR && KB == 64) {            // tensor-core engine: r*h as bf16 (hi, lo) only
+        if (epilogue_flags(prm.epi) == EPF_OUT_SPLIT) return launch_pair<KIND, ACT, KB, EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);
+    }
+    if constexpr (KIND == DKT_EPI_GRU_Q && KB == 64) {             // h' as fp32 (for the next blend) + bf16 (hi, lo)
+        if (epilogue_flags(prm.epi) == (EPF_OUT_F32 | EPF_OUT_SPLIT))
+            return launch_pair<KIND, ACT, KB, EPF_OUT_F32 | EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);
+    }
+    return launch_pair<KIND, ACT, KB, EPF_GENERIC>(prm, grid, smem_bytes, st);
+}
 
 template <int KIND, int ACT>
 static int launch_conv_ka(ConvFamily fam, const TcConvParams& prm, unsigned grid, size_t smem_bytes, cudaStream_t st) {
+    if (fam == FAM_PAIR) return launch_pair_fl<KIND, ACT, 64>(prm, grid, smem_bytes, st);
+    if (fam == FAM_PAIR_K32) {                       // 32-channel K blocks: instantiated for the stems' epilogues only
+        if constexpr (KIND == DKT_EPI_LINEAR && (ACT == DKT_ACT_NONE || ACT == DKT_ACT_RELU))
+            return launch_pair_fl<KIND, ACT, 32>(prm, grid, smem_bytes, st);
+        else
+            return DKT_E_UNSUPPORTED;
+    }
     static bool attr_set = false;                    // per instantiation
     if (!attr_set) {
         cudaError_t ce = cudaFuncSetAttribute(conv_tc_patch_kernel<32, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_patch_kernel<64, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<64, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_pair_kernel<KIND, ACT, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (KIND == DKT_EPI_LINEAR && (ACT == DKT_ACT_NONE || ACT == DKT_ACT_RELU) && ce == cudaSuccess)
-            ce = cudaFuncSetAttribute(conv_tc_pair_kernel<KIND, ACT, (KIND == DKT_EPI_LINEAR && (ACT == DKT_ACT_NONE || ACT == DKT_ACT_RELU)) ? 32 : 64>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce != cudaSuccess) return (int)ce;
         attr_set = true;
     }
     switch (fam) {
         case FAM_PATCH32: conv_tc_patch_kernel<32, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
         case FAM_PATCH64: conv_tc_patch_kernel<64, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
-        case FAM_PAIR:    conv_tc_pair_kernel<KIND, ACT, 64><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;   // grid even (cluster of 2)
-        case FAM_PAIR_K32:                           // 32-channel K blocks: instantiated for the stems' epilogues only
-            if constexpr (KIND == DKT_EPI_LINEAR && (ACT == DKT_ACT_NONE || ACT == DKT_ACT_RELU)) {
-                conv_tc_pair_kernel<KIND, ACT, 32><<<grid, TC2_THREADS, smem_bytes, st>>>(prm);
-                break;
-            } else {
-                return DKT_E_UNSUPPORTED;
-            }
         default:          conv_tc_kernel<64, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
     }
     DKT_RETURN_LAST();
