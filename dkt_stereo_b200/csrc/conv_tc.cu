@@ -566,7 +566,7 @@ __device__ __forceinline__ void conv_tc_epilogue_proj(const TcConvParams& prm, u
     }
 }
 
-template <int BK, int KIND, int ACT>
+template <int BK, int KIND, int ACT, int FL>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
     constexpr uint32_t ROW = BK * 2;
@@ -669,7 +669,7 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
         if constexpr (KIND == DKT_EPI_PROJ)
             conv_tc_epilogue_proj<ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
         else
-            conv_tc_epilogue_warps<KIND, ACT, EPF_GENERIC>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+            conv_tc_epilogue_warps<KIND, ACT, FL>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
     }
 
     tcgen05_fence_before();
@@ -1080,9 +1080,36 @@ static int launch_pair_fl(const TcConvParams& prm, unsigned grid, size_t smem_by
     return launch_pair<KIND, ACT, KB, EPF_GENERIC>(prm, grid, smem_bytes, st);
 }
 
+template <int KIND, int ACT, int FL>
+static int launch_tap(const TcConvParams& prm, unsigned grid, size_t smem_bytes, cudaStream_t st) {
+    static bool attr_set = false;                    // per instantiation
+    if (!attr_set) {
+        cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel<64, KIND, ACT, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce != cudaSuccess) return (int)ce;
+        attr_set = true;
+    }
+    conv_tc_kernel<64, KIND, ACT, FL><<<grid, TC2_THREADS, smem_bytes, st>>>(prm);
+    DKT_RETURN_LAST();
+}
+
+// per-tap kernel (the encoders' stride-2 convs): same hot operand combinations as the pair kernel
+template <int KIND, int ACT>
+static int launch_tap_fl(const TcConvParams& prm, unsigned grid, size_t smem_bytes, cudaStream_t st) {
+    if constexpr (KIND == DKT_EPI_LINEAR && ACT == DKT_ACT_RELU) {
+        if (epilogue_flags(prm.epi) == EPF_OUT_SPLIT) return launch_tap<KIND, ACT, EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);
+    }
+    if constexpr (KIND == DKT_EPI_LINEAR && ACT == DKT_ACT_NONE) {
+        const int fl = epilogue_flags(prm.epi);
+        if (fl == (EPF_OUT_F32 | EPF_STATS)) return launch_tap<KIND, ACT, EPF_OUT_F32 | EPF_STATS>(prm, grid, smem_bytes, st);
+        if (fl == EPF_OUT_F32) return launch_tap<KIND, ACT, EPF_OUT_F32>(prm, grid, smem_bytes, st);
+    }
+    return launch_tap<KIND, ACT, EPF_GENERIC>(prm, grid, smem_bytes, st);
+}
+
 template <int KIND, int ACT>
 static int launch_conv_ka(ConvFamily fam, const TcConvParams& prm, unsigned grid, size_t smem_bytes, cudaStream_t st) {
     if (fam == FAM_PAIR) return launch_pair_fl<KIND, ACT, 64>(prm, grid, smem_bytes, st);
+    if (fam == FAM_TAP64) return launch_tap_fl<KIND, ACT>(prm, grid, smem_bytes, st);
     if (fam == FAM_PAIR_K32) {                       // 32-channel K blocks: instantiated for the stems' epilogues only
         if constexpr (KIND == DKT_EPI_LINEAR && (ACT == DKT_ACT_NONE || ACT == DKT_ACT_RELU))
             return launch_pair_fl<KIND, ACT, 32>(prm, grid, smem_bytes, st);
@@ -1093,14 +1120,12 @@ static int launch_conv_ka(ConvFamily fam, const TcConvParams& prm, unsigned grid
     if (!attr_set) {
         cudaError_t ce = cudaFuncSetAttribute(conv_tc_patch_kernel<32, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_patch_kernel<64, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_kernel<64, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce != cudaSuccess) return (int)ce;
         attr_set = true;
     }
     switch (fam) {
         case FAM_PATCH32: conv_tc_patch_kernel<32, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
-        case FAM_PATCH64: conv_tc_patch_kernel<64, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
-        default:          conv_tc_kernel<64, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
+        default:          conv_tc_patch_kernel<64, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
     }
     DKT_RETURN_LAST();
 }
