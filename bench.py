@@ -334,15 +334,20 @@ def run_b200(args):
 
     k2_ms = time_it(lambda: ops.corr1d_lookup(pyr, cx, 4, lk_out, "nhwc"))
     k2e_ms = time_it(lambda: ops.corr1d_lookup_enc(pyr, cx, 4, eng.weights["convc1"], eng.cor1_slice()))
+    cfg2 = (H, W, Bg) == (544, 960, 8)
+    tr_k1 = ncu_traffic("corr1d_build_tc") if cfg2 else None
+    tr_k2 = ncu_traffic("corr1d_lookup_enc") if cfg2 else None
     roofline_corr = {
         "build": {"bound": "hbm", "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                   "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": k1_ms, "bytes": k1_bytes,
-                  "launches": k1_launches},
+                  "traffic": tr_k1["dram_bytes"] if tr_k1 else None, "launches": k1_launches},
         "lookup": {"bound": "hbm", "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                    "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": k2_ms, "bytes": k2_bytes},
         "lookup_enc": {"bound": "hbm", "achieved": k2_enc_bytes / (k2e_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                        "unit": "GB/s", "frac": k2_enc_bytes / (k2e_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": k2e_ms,
-                       "bytes": k2_enc_bytes, "note": "lookup fused with convc1 (1x1, 36->64, ReLU): taps never reach HBM"},
+                       "bytes": k2_enc_bytes, "traffic": tr_k2["dram_bytes"] if tr_k2 else None,
+                       "note": "lookup fused with convc1 (1x1, 36->64, ReLU): taps never reach HBM; DRAM traffic is ~2x the "
+                               "algorithmic bytes because each 40-byte tap run touches 2-3 sectors of its own volume row"},
     }
 
     if rank != 0:
