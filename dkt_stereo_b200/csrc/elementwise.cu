@@ -35,30 +35,48 @@ pool2x_kernel(const float* __restrict__ src, int sC, int sc0, dkt_tensor dst, in
 }
 
 // ---- bilinear resize, align_corners=True ------------------------------------------------------
+// grid: x = ceil(Wd * C4 / 256), y = ceil(B * Hd / IR): a thread produces IR output rows of one (x, channel group)
+// column, loads first -- with one row per thread the kernel was bound by the block launch rate (32640 tiny blocks)
+constexpr int IR = 4;
 __global__ void __launch_bounds__(256)
 interp_kernel(const float* __restrict__ src, int sC, int sc0, dkt_tensor dst, int C4,
-              int Hs, int Ws, int Hd, int Wd, float sy, float sx) {
+              int Hs, int Ws, int Hd, int Wd, int rows_total, float sy, float sx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Wd * C4) return;
     const int xo = i / C4, q = i - xo * C4;
-    const int row = blockIdx.y;                   // b * Hd + yo
-    const int b = row / Hd, yo = row - b * Hd;
-    const float fy = sy * yo, fx = sx * xo;
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < Hs - 1), x1 = x0 + (x0 < Ws - 1);
-    const float ly = fy - y0, lx = fx - x0;
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    const float* base = src + (int64_t)b * Hs * Ws * sC + sc0 + q * 4;
-    float4 v00 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y0 * Ws + x0) * sC));
-    float4 v01 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y0 * Ws + x1) * sC));
-    float4 v10 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y1 * Ws + x0) * sC));
-    float4 v11 = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y1 * Ws + x1) * sC));
-    float4 o;
-    o.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
-    o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
-    o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
-    o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
-    store_all4(dst, (int64_t)row * Wd + xo, q * 4, o);
+    const float fx = sx * xo;
+    const int x0 = (int)fx;
+    const int x1 = x0 + (x0 < Ws - 1);
+    const float lx = fx - x0, hx = 1.f - lx;
+    float4 v00[IR], v01[IR], v10[IR], v11[IR];
+    float ly[IR];
+#pragma unroll
+    for (int r = 0; r < IR; ++r) {
+        const int row = blockIdx.y * IR + r;          // b * Hd + yo
+        if (row >= rows_total) continue;
+        const int b = row / Hd, yo = row - b * Hd;
+        const float fy = sy * yo;
+        const int y0 = (int)fy;
+        const int y1 = y0 + (y0 < Hs - 1);
+        ly[r] = fy - y0;
+        const float* base = src + (int64_t)b * Hs * Ws * sC + sc0 + q * 4;
+        v00[r] = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y0 * Ws + x0) * sC));
+        v01[r] = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y0 * Ws + x1) * sC));
+        v10[r] = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y1 * Ws + x0) * sC));
+        v11[r] = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)y1 * Ws + x1) * sC));
+    }
+#pragma unroll
+    for (int r = 0; r < IR; ++r) {
+        const int row = blockIdx.y * IR + r;
+        if (row >= rows_total) continue;
+        const float hy = 1.f - ly[r];
+        float4 o;
+        o.x = hy * (hx * v00[r].x + lx * v01[r].x) + ly[r] * (hx * v10[r].x + lx * v11[r].x);
+        o.y = hy * (hx * v00[r].y + lx * v01[r].y) + ly[r] * (hx * v10[r].y + lx * v11[r].y);
+        o.z = hy * (hx * v00[r].z + lx * v01[r].z) + ly[r] * (hx * v10[r].z + lx * v11[r].z);
+        o.w = hy * (hx * v00[r].w + lx * v01[r].w) + ly[r] * (hx * v10[r].w + lx * v11[r].w);
+        store_all4(dst, (int64_t)row * Wd + xo, q * 4, o);
+    }
 }
 
 // ---- K4 RAFT: convex combination upsampling ---------------------------------------------------
@@ -216,11 +234,11 @@ extern "C" int dkt_interp(const dkt_tensor* src, const dkt_tensor* dst, int B, i
     DKT_CHECK_ARG(B > 0 && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0);
     DKT_CHECK_ARG(src->c_count == dst->c_count);
     const int C4 = src->c_count / 4;
-    if ((int64_t)B * Hd > 65535 || (int64_t)Wd * C4 > 0x7fffffff) return DKT_E_UNSUPPORTED;
+    if ((int64_t)B * Hd > 65535 * IR || (int64_t)Wd * C4 > 0x7fffffff) return DKT_E_UNSUPPORTED;
     const float sy = Hd > 1 ? (float)(Hs - 1) / (float)(Hd - 1) : 0.f;
     const float sx = Wd > 1 ? (float)(Ws - 1) / (float)(Wd - 1) : 0.f;
-    interp_kernel<<<dim3((unsigned)ceil_div(Wd * C4, 256), (unsigned)(B * Hd)), 256, 0, (cudaStream_t)stream>>>(
-        src->f32, src->C, src->c_begin, *dst, C4, Hs, Ws, Hd, Wd, sy, sx);
+    interp_kernel<<<dim3((unsigned)ceil_div(Wd * C4, 256), (unsigned)ceil_div(B * Hd, IR)), 256, 0, (cudaStream_t)stream>>>(
+        src->f32, src->C, src->c_begin, *dst, C4, Hs, Ws, Hd, Wd, B * Hd, sy, sx);
     DKT_RETURN_LAST();
 }
 
