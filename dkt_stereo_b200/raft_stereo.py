@@ -91,6 +91,7 @@ class RAFTStereo(nn.Module):
         self._full: Dict[tuple, tuple] = {}
         self._full_seen = set()
         self._capturing = False
+        self._native_shape = None
         self._pyr = None
         self._pyr_key = None
 
@@ -206,7 +207,11 @@ class RAFTStereo(nn.Module):
         the encoder wrote -> loop -> upsampling.  No NCHW <-> NHWC conversion and no fp32 -> bf16 split pass.
         From the third call with the same input shape the whole thing is ONE CUDA-graph replay: the images are
         copied into static device buffers, the results are returned as fresh tensors."""
-        if self.encoder.pack_weights():          # weights changed: captured graphs point into the old packs
+        shape_key = (tuple(image1.shape), str(image1.device))
+        # captured graphs hold raw pointers: into the packed weights (stale after a parameter update) and into the
+        # engines' activation buffers (re-allocated when the input shape changes) -- drop them in both cases
+        if self.encoder.pack_weights() or shape_key != self._native_shape:
+            self._native_shape = shape_key
             self._graphs.clear()
             self._seen.clear()
             self._full.clear()

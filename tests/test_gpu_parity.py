@@ -721,3 +721,19 @@ def test_igev_context_encoder_on_engine(monkeypatch):
         mean, mx = stats(ua.cpu(), ub.cpu())
         print(f"[parity] igev cnet engine vs torch rep={rep}: mean-abs {mean:.3e} px, max-abs {mx:.3e} px")
         assert mean <= 1e-3, (rep, mean, mx)
+
+
+def test_shape_changes_invalidate_graphs():
+    """A -> B -> A input shapes: the engines re-allocate their buffers per shape, so CUDA graphs captured for an
+    earlier shape must not be replayed; every call must equal a fresh model's eager result."""
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    g = load_golden("raft_fwd_small")
+    model, fresh = _model("tc", g), _model("tc", g)
+    fresh.use_cuda_graph = False
+    shapes = [(1, 64, 96), (2, 96, 128), (1, 64, 96), (1, 64, 96), (1, 64, 96), (2, 96, 128), (2, 96, 128), (2, 96, 128)]
+    for k, (B, H, W) in enumerate(shapes):
+        im1, im2 = synthetic_pair(B, H, W, seed=40 + k)
+        im1, im2 = im1.to(dev()), im2.to(dev())
+        _, up = model(im1, im2, iters=3, test_mode=True)
+        _, ref = fresh(im1, im2, iters=3, test_mode=True)
+        assert torch.equal(up, ref), (k, float((up - ref).abs().max()))
