@@ -33,6 +33,7 @@ class DktEpilogue(C.Structure):
                 ("stats_partial", C.c_void_p)]
 
 
+ABI_VERSION = 2      # include/dkt_stereo_b200.h: DKT_ABI_VERSION
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
 EPI_LINEAR, EPI_GRU_ZR, EPI_GRU_Q, EPI_PROJ = 0, 1, 2, 3
 PROJ_LD = 12
@@ -101,7 +102,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here == ABI drift; let it surface
         fn.argtypes = argtypes
         fn.restype = C.c_char_p if name == "dkt_error_string" else C.c_int
-    if lib.dkt_abi_version() != 1:
+    if lib.dkt_abi_version() != ABI_VERSION:
         raise DktError("libdkt_stereo_b200.so ABI version mismatch")
     _lib = lib
     return lib

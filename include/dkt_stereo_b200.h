@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DKT_ABI_VERSION 1
+#define DKT_ABI_VERSION 2   /* 2: dkt_epilogue grew (proj, res_hi/res_lo, stats_partial) */
 
 /* negative return codes */
 #define DKT_E_INVALID     (-1)  /* null pointer / bad dimension */
@@ -183,8 +183,9 @@ int dkt_geo_lookup_enc(const float* geo0, const float* geo1, const float* init0,
  *          (tensor core; K contiguous, Npad = N rounded up to 16).
  *   dkt_conv2d_simt : exact fp32 CUDA-core implicit GEMM (any Cin / N); reads src.f32.
  *   dkt_conv2d_tc   : tcgen05 implicit GEMM, TMA im2col-free tap loads with zero-filled halos,
- *                     3-term bf16 split; reads src.hi/lo; needs c_begin, c_count % 64 == 0,
- *                     ksize in {1,3}, N <= 256. */
+ *                     3-term bf16 split; reads src.hi/lo; needs c_begin, c_count % 64 == 0 (or one
+ *                     32-channel source: the 7x7 stems' x-im2col rows), ksize in {1,3}, N <= 256.
+ *                     Stride-1 convs with >= 2 output tiles run as CTA pairs (tcgen05 cta_group::2). */
 int dkt_conv2d_simt(const dkt_tensor* srcs, int nsrc, const float* weight, int ksize, int N,
                     const dkt_epilogue* epi, int B, int H, int W, void* stream);
 int dkt_conv2d_tc(const dkt_tensor* srcs, int nsrc, const uint16_t* w_hi, const uint16_t* w_lo,

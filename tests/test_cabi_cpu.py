@@ -24,7 +24,7 @@ def test_library_builds_and_exports_header_symbols():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     # the ctypes table covers the header one to one
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.dkt_abi_version() == 1
+    assert lib.dkt_abi_version() == 2
     assert lib.dkt_error_string(-2).decode().startswith("shape or option")
 
 
