@@ -19,7 +19,7 @@ namespace dkt {
 // ---------------------------------------------------------------------------------------------
 // stem rows
 // ---------------------------------------------------------------------------------------------
-constexpr int SR_PIX = 64;
+constexpr int SR_PIX = 256;         // pixels of one image row per block (64 made 65 K tiny blocks per full-resolution launch)
 
 __global__ void __launch_bounds__(256)
 stem_rows_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64_t sy, int64_t sx, float scale, float shift,
@@ -123,7 +123,7 @@ __global__ void instnorm_finalize_kernel(const float* __restrict__ partial, floa
 // stage 2: grid B: the segments in order -> mean / rstd.  Every order is fixed: bit-reproducible and
 // independent of the batch size and of the image's position in the batch.
 // ---------------------------------------------------------------------------------------------
-constexpr int IN_SEGS = 32;
+constexpr int IN_SEGS = 128;       // segments per image: stage 1 is a chain of dependent loads per thread, keep it short
 
 __global__ void __launch_bounds__(256)
 instnorm_tiles_stage1_kernel(const float* __restrict__ partial, double* __restrict__ seg, int tiles_per_img, int C2) {
@@ -137,7 +137,13 @@ instnorm_tiles_stage1_kernel(const float* __restrict__ partial, double* __restri
     if (sl < slices) {
         double acc = 0.0;
         const float* base = partial + ((int64_t)b * tiles_per_img) * C2 + v;
-        for (int t = t0 + sl; t < t1; t += slices) acc += (double)__ldg(base + (int64_t)t * C2);
+        int t = t0 + sl;
+        for (; t + 3 * slices < t1; t += 4 * slices) {          // 4 independent loads in flight, summed in index order
+            const float a0 = __ldg(base + (int64_t)t * C2), a1 = __ldg(base + (int64_t)(t + slices) * C2);
+            const float a2 = __ldg(base + (int64_t)(t + 2 * slices) * C2), a3 = __ldg(base + (int64_t)(t + 3 * slices) * C2);
+            acc += (double)a0; acc += (double)a1; acc += (double)a2; acc += (double)a3;
+        }
+        for (; t < t1; t += slices) acc += (double)__ldg(base + (int64_t)t * C2);
         s_acc[sl * C2 + v] = acc;
     }
     __syncthreads();
@@ -282,7 +288,7 @@ extern "C" int dkt_instnorm_stats(const dkt_tensor* x, float* workspace, float* 
 }
 
 extern "C" int dkt_instnorm_tiles_workspace_floats(int B, int C) {
-    return B * 32 * 2 * C * 2;       // IN_SEGS segments of 2*C doubles per image
+    return B * IN_SEGS * 2 * C * 2;  // IN_SEGS segments of 2*C doubles per image
 }
 
 extern "C" int dkt_instnorm_finalize_tiles(const float* partial, float* workspace, float* stats, float eps,
