@@ -85,4 +85,18 @@ __device__ __forceinline__ void store_all4(const dkt_tensor& t, int64_t pixel, i
     }
 }
 
+// ---- K2: one row sample = 2r+2 adjacent volume entries around x (zero outside the row) + the fractional weight.
+// Split from the interpolation so that a thread can have the loads of several samples in flight before it consumes any.
+template <int R>
+__device__ __forceinline__ void sample_row_load(const float* __restrict__ row, int W, float x, float* v, float& a) {
+    const float xf = floorf(x);
+    a = x - xf;
+    const int i0 = (int)xf - R;
+#pragma unroll
+    for (int k = 0; k < 2 * R + 2; ++k) {
+        int idx = i0 + k;
+        v[k] = (idx >= 0 && idx < W) ? __ldg(row + idx) : 0.f;
+    }
+}
+
 }  // namespace dkt

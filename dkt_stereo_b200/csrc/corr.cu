@@ -143,19 +143,6 @@ __device__ __forceinline__ void sample_row(const float* __restrict__ row, int W,
     for (int k = 0; k < 2 * R + 1; ++k) taps[k] = (1.f - a) * v[k] + a * v[k + 1];
 }
 
-// the same in two halves, so that a thread can have the loads of several row samples in flight before it consumes any
-template <int R>
-__device__ __forceinline__ void sample_row_load(const float* __restrict__ row, int W, float x, float* v, float& a) {
-    const float xf = floorf(x);
-    a = x - xf;
-    const int i0 = (int)xf - R;
-#pragma unroll
-    for (int k = 0; k < 2 * R + 2; ++k) {
-        int idx = i0 + k;
-        v[k] = (idx >= 0 && idx < W) ? __ldg(row + idx) : 0.f;
-    }
-}
-
 struct ConstPyrPtrs {
     const float* p[DKT_MAX_LEVELS];
     int          w[DKT_MAX_LEVELS];
