@@ -1,5 +1,11 @@
-import sys, os, torch
-sys.path.insert(0, os.getcwd())
+"""Stand-alone timing of the RAFT-Stereo lookup at cfg2 (B8, 136x240, 4 levels): plain vs fused with convc1.
+Run on the GPU box: python tools/lookup_bench.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dkt_stereo_b200 import ops, _lib as L
 dev = torch.device("cuda:0")
 B, h, w = 8, 136, 240
@@ -18,9 +24,7 @@ def t(fn, reps=30):
     for _ in range(reps): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps * 1e3
-Wt = ops.pack_conv(wt, bias, cin_pad=64, tc=True)
 Wf = ops.pack_conv(wt, bias, cin_pad=64, tc=False)
-print("tc   : %.1f us" % t(lambda: ops.corr1d_lookup_enc(pyr, cx, 4, Wt, out)))
-print("fp32 : %.1f us" % t(lambda: ops.corr1d_lookup_enc(pyr, cx, 4, Wf, out)))
+print("fused lookup + convc1: %.1f us" % t(lambda: ops.corr1d_lookup_enc(pyr, cx, 4, Wf, out)))
 plain = torch.zeros(B, h, w, 36, device=dev)
-print("plain: %.1f us" % t(lambda: ops.corr1d_lookup(pyr, cx, 4, plain, "nhwc")))
+print("plain lookup (36 ch fp32): %.1f us" % t(lambda: ops.corr1d_lookup(pyr, cx, 4, plain, "nhwc")))
