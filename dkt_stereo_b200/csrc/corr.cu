@@ -209,23 +209,25 @@ constexpr int LK_ENC_TSP = LK_ENC_PIX + 4;      // row stride of the k-major til
 __device__ __forceinline__ void lookup_encode_tile(const float* tile, int C, const float* ws,
                                                    const LookupOut& o, int64_t p0, int npix) {
     const int cg = threadIdx.x & 15, pg = threadIdx.x >> 4;
-    float acc[4][4];
+    // packed fp32 FMAs (sm_100 FFMA2: two IEEE fmas per issue slot, bit-identical to fmaf): the contraction is bound by
+    // FMA issue, 36 x 64 (RAFT) / 162 x 64 (IGEV) per pixel
+    float2 acc[4][2];
     const float4 bias = *reinterpret_cast<const float4*>(o.enc_b + cg * 4);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { acc[i][0] = bias.x; acc[i][1] = bias.y; acc[i][2] = bias.z; acc[i][3] = bias.w; }
+    for (int i = 0; i < 4; ++i) { acc[i][0] = make_float2(bias.x, bias.y); acc[i][1] = make_float2(bias.z, bias.w); }
     const float* tcol = tile + pg * 4;
     const float* wcol = ws + cg * 4;
 #pragma unroll 2
     for (int k = 0; k < C; ++k) {
         const float4 a = *reinterpret_cast<const float4*>(tcol + k * LK_ENC_TSP);
         const float4 w = *reinterpret_cast<const float4*>(wcol + k * LK_ENC_N);
+        const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
         const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            acc[i][0] = fmaf(av[i], w.x, acc[i][0]);
-            acc[i][1] = fmaf(av[i], w.y, acc[i][1]);
-            acc[i][2] = fmaf(av[i], w.z, acc[i][2]);
-            acc[i][3] = fmaf(av[i], w.w, acc[i][3]);
+            const float2 a2 = make_float2(av[i], av[i]);
+            acc[i][0] = __ffma2_rn(a2, w01, acc[i][0]);
+            acc[i][1] = __ffma2_rn(a2, w23, acc[i][1]);
         }
     }
 #pragma unroll
@@ -233,7 +235,7 @@ __device__ __forceinline__ void lookup_encode_tile(const float* tile, int C, con
         const int px = pg * 4 + i;
         if (px < npix)
             store_all4(o.enc_out, p0 + px, cg * 4,
-                       make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f), fmaxf(acc[i][3], 0.f)));
+                       make_float4(fmaxf(acc[i][0].x, 0.f), fmaxf(acc[i][0].y, 0.f), fmaxf(acc[i][1].x, 0.f), fmaxf(acc[i][1].y, 0.f)));
     }
 }
 
