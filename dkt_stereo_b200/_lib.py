@@ -92,7 +92,10 @@ def load() -> C.CDLL:
         return _lib
     path = _build.LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    if os.path.exists(nvcc) and os.environ.get("DKT_NO_AUTOBUILD", "0") != "1":
+    override = os.environ.get("DKT_STEREO_LIB")      # A/B of two builds of the same ABI (tools/, never the default)
+    if override:
+        path = override
+    elif os.path.exists(nvcc) and os.environ.get("DKT_NO_AUTOBUILD", "0") != "1":
         path = _build.build()
     if not os.path.exists(path):
         raise DktError(f"{path} is missing and cannot be built (no nvcc): the B200 engine has no CPU or "

@@ -61,6 +61,8 @@ struct TcConvParams {
     uint32_t a_part_bytes;          // bytes of one precision (hi or lo) of an A stage
     uint32_t tmem_cols;
     int w_resident;                 // pair kernel: the whole filter stays in the W ring (loaded once per CTA)
+    uint32_t a_tx_bytes;            // pair kernel: bytes one CTA's TMA loads deliver per A stage (hi + lo boxes)
+    int patch_rows;                 // pair kernel, x-major patch: RY = TILE_H + kh - 1 (shared-memory row = x * RY + y)
     uint32_t epi_sleep_ns;          // back-off of the epilogue warps' wait for an accumulator (0 = plain polling)
     dkt_epilogue epi;
 };
@@ -125,6 +127,18 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr) {
 // warp-uniform control flow lets ptxas keep descriptors, coordinates and barrier addresses in uniform registers.
 // (Inside `if (lane == 0)` every UTCHMMA / UTMALDG was wrapped in an ELECT + 5x R2UR.BROADCAST retry loop, which
 // bounded the issue rate -- and with it the tensor pipe -- of every conv with N <= 128: ncu r01h.)
+// same with an explicit stride between 8-row atoms (x-major halo patch: RY rows instead of 8)
+template <int BK>
+__device__ __forceinline__ uint64_t smem_desc_kmajor_sbo(uint32_t addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(BK == 64 ? 2 : 4) << 61;
+    return d;
+}
+
 __device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
 // Epilogue warps 2..9 of the persistent kernels (see the header comment of this file).
@@ -147,7 +161,16 @@ enum : int {
 
 template <int FL> __device__ __forceinline__ bool epf(int bit, bool runtime) { return FL < 0 ? runtime : (FL & bit) != 0; }
 
-template <int KIND, int ACT, int FL>
+// XM ("x-major tile"): how an M row maps to a pixel of the 8 x 16 tile.  false: m = y * 16 + x (row-patch and per-tap
+// kernels).  true: m = x * 8 + y (pair kernel with the x-major halo patch, where all taps of a filter read ONE patch).
+// A warp's 32 M rows (one TMEM lane quarter q) are then a 2 x 16 / an 8 x 4 pixel group; lane (sub, jg) handles the
+// group's pixels r = i*4 + sub, i < 8.
+template <bool XM> __device__ __forceinline__ int epi_gy(int q) { return XM ? 0 : 2 * q; }
+template <bool XM> __device__ __forceinline__ int epi_gx(int q) { return XM ? 4 * q : 0; }
+template <bool XM> __device__ __forceinline__ int epi_dy(int i, int sub) { return XM ? ((i & 1) << 2) + sub : (i >> 2); }
+template <bool XM> __device__ __forceinline__ int epi_dx(int i, int sub) { return XM ? (i >> 1) : ((i & 3) << 2) + sub; }
+
+template <int KIND, int ACT, int FL, bool XM>
 __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, uint32_t tmem_base,
                                                        uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
                                                        uint8_t* epi_smem, int warp, int lane, int tiles_per_img,
@@ -205,19 +228,21 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
         const int r = tile - b * tiles_per_img;
         const int ty = r / prm.tiles_x;
         const int y0 = ty * TC_TILE_H, x0 = (r - ty * prm.tiles_x) * TC_TILE_W;
-        // this lane's 8 pixels: row = i*4 + sub of the warp's quarter -> (y, x) = (y0 + 2q + (i>>2), x0 + (i&3)*4 + sub)
-        const int64_t p00 = ((int64_t)b * H + y0 + 2 * q) * W + x0 + sub;
-        const bool yok0 = (y0 + 2 * q) < H, yok1 = (y0 + 2 * q + 1) < H;
+        // this warp's pixel group starts at (gy0, gx0); lane pixel i sits at (+epi_dy(i), +epi_dx(i))
+        const int gy0 = y0 + epi_gy<XM>(q), gx0 = x0 + epi_gx<XM>(q);
+        const int64_t p00 = ((int64_t)b * H + gy0) * W + gx0;
+        auto pix_ok = [&](int i) { return (gy0 + epi_dy<XM>(i, sub)) < H && (gx0 + epi_dx<XM>(i, sub)) < W; };
+        auto pix_d = [&](int i) { return epi_dy<XM>(i, sub) * W + epi_dx<XM>(i, sub); };    // pixel delta from p00
         const bool interior = (y0 + TC_TILE_H <= H) && (x0 + TC_TILE_W <= W);   // uniform: no per-pixel bounds tests needed
         // L2 prefetch of the operand lines (context / z / h / residual) of a chunk; one lane per pixel row covers the
         // 128-byte line.  The first chunk of the NEXT tile is requested now (the MMA runs ahead, so this warp does not
         // wait and a same-tile prefetch has no lead time), chunk k+1 of this tile at the start of chunk k.
-        auto prefetch_chunk = [&](int64_t pp00, int px0, bool pyok0, bool pyok1, int c0p) {
+        auto prefetch_chunk = [&](int64_t pp00, int pgy0, int pgx0, int c0p) {
             if (jg != 0 || c0p >= prm.Npad) return;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (!((i < 4 ? pyok0 : pyok1) && (px0 + (i & 3) * 4 + sub) < W)) continue;
-                const int64_t p = pp00 + (i & 3) * 4 + (i < 4 ? 0 : W);
+                if (!((pgy0 + epi_dy<XM>(i, sub)) < H && (pgx0 + epi_dx<XM>(i, sub)) < W)) continue;
+                const int64_t p = pp00 + epi_dy<XM>(i, sub) * W + epi_dx<XM>(i, sub);
                 if (LIN) {
                     if (has_ctx) prefetch_l2(ctx + p * e.ctx_C + e.ctx_c0 + c0p);
                     if (has_res) prefetch_l2(res + p * e.res_C + e.res_c0 + c0p);
@@ -237,14 +262,15 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
             }
         };
         if (has_ops) {
-            if (t == 0 && live) prefetch_chunk(p00, x0, yok0, yok1, half * 32);
+            if (t == 0 && live) prefetch_chunk(p00, gy0, gx0, half * 32);
             const int ntile = (item + tw.step) * tw.mul + tw.off;
             if (item + tw.step < tw.items && ntile < prm.num_tiles) {
                 const int nb = ntile / tiles_per_img;
                 const int nr = ntile - nb * tiles_per_img;
                 const int nty = nr / prm.tiles_x;
                 const int ny0 = nty * TC_TILE_H, nx0 = (nr - nty * prm.tiles_x) * TC_TILE_W;
-                prefetch_chunk(((int64_t)nb * H + ny0 + 2 * q) * W + nx0 + sub, nx0, (ny0 + 2 * q) < H, (ny0 + 2 * q + 1) < H, half * 32);
+                const int ngy0 = ny0 + epi_gy<XM>(q), ngx0 = nx0 + epi_gx<XM>(q);
+                prefetch_chunk(((int64_t)nb * H + ngy0) * W + ngx0, ngy0, ngx0, half * 32);
             }
         }
         mbar_wait_backoff(&tmem_full_bar[as], aphase, prm.epi_sleep_ns);
@@ -254,7 +280,7 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
             float v[32];
             const int ncols = (prm.Npad - c0 >= 32) ? 32 : 16;
             const int n = c0 + 4 * jg;
-            if (has_ops) prefetch_chunk(p00, x0, yok0, yok1, c0 + 64);
+            if (has_ops) prefetch_chunk(p00, gy0, gx0, c0 + 64);
             // residual of this lane's 8 pixels, requested BEFORE the accumulator is pulled and transposed so that its
             // latency hides behind that work; kept as raw bits (fp32 x4, or bf16 hi x4 | lo x4) until first use
             uint4 rraw[8];
@@ -263,8 +289,8 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     rraw[i] = make_uint4(0u, 0u, 0u, 0u);
-                    if (n + 3 < N && (interior || ((i < 4 ? yok0 : yok1) && (x0 + (i & 3) * 4 + sub) < W))) {
-                        const int64_t off = rbase + (int64_t)(((i & 3) * 4 + (i < 4 ? 0 : W)) * e.res_C);
+                    if (n + 3 < N && (interior || pix_ok(i))) {
+                        const int64_t off = rbase + (int64_t)(pix_d(i) * e.res_C);
                         if (has_res) {
                             rraw[i] = __ldg(reinterpret_cast<const uint4*>(res + off));
                         } else {
@@ -312,8 +338,8 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                 uint16_t* const pl = o_lo + obase;
                 const float* const pc = ctx + (p00 * e.ctx_C + e.ctx_c0 + n);
                 const float* const pt = tail + p00 * tail_C;
-                // two batches of 4 pixels (tile rows 2q and 2q + 1): all operand loads of a batch are issued before its
-                // math and stores, so their latencies overlap
+                // two batches of 4 pixels: all operand loads of a batch are issued before its math and stores, so their
+                // latencies overlap
                 auto pixels = [&](auto check_tag) {
                     constexpr bool CHECK = decltype(check_tag)::value;
 #pragma unroll
@@ -324,9 +350,9 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
 #pragma unroll
                         for (int i4 = 0; i4 < 4; ++i4) {
                             const int row = hb * 16 + i4 * 4 + sub;
-                            ok[i4] = !CHECK || ((hb ? yok1 : yok0) && (x0 + i4 * 4 + sub) < W);
+                            ok[i4] = !CHECK || pix_ok(hb * 4 + i4);
                             if (!ok[i4]) continue;
-                            const int d = i4 * 4 + hb * W;                  // pixel delta from p00
+                            const int d = pix_d(hb * 4 + i4);
                             av[i4] = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
                             if (LIN) {
                                 if (has_ctx) cv[i4] = ld4(pc + d * e.ctx_C);
@@ -350,7 +376,7 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
 #pragma unroll
                         for (int i4 = 0; i4 < 4; ++i4) {
                             if (!ok[i4]) continue;
-                            const int d = i4 * 4 + hb * W;
+                            const int d = pix_d(hb * 4 + i4);
                             float4 a = av[i4];
                             if (LIN) {
                                 a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
@@ -426,9 +452,8 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                 // ---------------- scalar path: partially valid last group of a LINEAR conv (rare shapes) ----------------
                 for (int i = 0; i < 8; ++i) {
                     const int row = i * 4 + sub;
-                    const int xo = (i & 3) * 4;
-                    if (!((i < 4 ? yok0 : yok1) && (x0 + xo + sub) < W)) continue;
-                    const int64_t p = p00 + xo + (i < 4 ? 0 : W);
+                    if (!pix_ok(i)) continue;
+                    const int64_t p = p00 + pix_d(i);
                     const float4 a = *reinterpret_cast<const float4*>(ebuf + row * 32 + ((jg ^ (row & 7)) << 2));
                     const float av1[4] = {a.x, a.y, a.z, a.w};
                     for (int u = 0; u < 4; ++u) if (n + u < N) tc_epilogue1<ACT>(e, p, n + u, av1[u]);
@@ -453,7 +478,7 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
         }
         if (live && has_tail && !tail_merged && half == 0) {
             const int m = q * 32 + lane;
-            const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
+            const int y = y0 + (XM ? (m & 7) : m / TC_TILE_W), x = x0 + (XM ? (m >> 3) : m % TC_TILE_W);
             if (y < H && x < W) {
                 const int64_t p = ((int64_t)b * H + y) * W + x;
                 for (int u = 0; u < tail_C; ++u) store_all(e.out, p, N + u, __ldg(tail + p * tail_C + u));
@@ -475,7 +500,7 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
 // take alternate 32-column chunks and meet through shared memory (double-buffered by tile parity) on a
 // 64-thread named barrier.
 constexpr int PROJ_T = 9;
-template <int ACT>
+template <int ACT, bool XM>
 __device__ __forceinline__ void conv_tc_epilogue_proj(const TcConvParams& prm, uint32_t tmem_base,
                                                       uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
                                                       uint8_t* epi_smem, int warp, int lane, int tiles_per_img,
@@ -554,7 +579,7 @@ __device__ __forceinline__ void conv_tc_epilogue_proj(const TcConvParams& prm, u
             const float4 o1 = *reinterpret_cast<const float4*>(xb + 4);
             const float o2 = xb[8];
             const int m = q * 32 + lane;
-            const int y = y0 + m / TC_TILE_W, x = x0 + m % TC_TILE_W;
+            const int y = y0 + (XM ? (m & 7) : m / TC_TILE_W), x = x0 + (XM ? (m >> 3) : m % TC_TILE_W);
             if (y < prm.H && x < prm.W) {
                 const int64_t p = ((int64_t)b * prm.H + y) * prm.W + x;
                 float* dst = e.out.f32 + p * e.out.C + e.out.c_begin;
@@ -569,6 +594,7 @@ __device__ __forceinline__ void conv_tc_epilogue_proj(const TcConvParams& prm, u
 template <int BK, int KIND, int ACT, int FL>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
+    constexpr bool XMT = false;                      // M row = y * 16 + x
     constexpr uint32_t ROW = BK * 2;
     constexpr uint32_t A_BYTES = 128 * ROW;
     extern __shared__ uint8_t smem_raw[];
@@ -667,9 +693,9 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
     } else {
         const TileWalk tw{(int)blockIdx.x, (int)gridDim.x, prm.num_tiles, 1, 0, 0u};
         if constexpr (KIND == DKT_EPI_PROJ)
-            conv_tc_epilogue_proj<ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+            conv_tc_epilogue_proj<ACT, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
         else
-            conv_tc_epilogue_warps<KIND, ACT, FL>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+            conv_tc_epilogue_warps<KIND, ACT, FL, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
     }
 
     tcgen05_fence_before();
@@ -693,6 +719,7 @@ constexpr int TCP_MAX_A = 4, TCP_MAX_W = 9;
 template <int WK, int KIND, int ACT>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
+    constexpr bool XMT = false;                      // M row = y * 16 + x
     constexpr uint32_t WROW = WK * 2;
     constexpr int WSPLIT = 64 / WK;                   // W steps per 64-channel A block
     extern __shared__ uint8_t smem_raw[];
@@ -823,9 +850,9 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
     } else {
         const TileWalk tw{(int)blockIdx.x, (int)gridDim.x, prm.num_tiles, 1, 0, 0u};
         if constexpr (KIND == DKT_EPI_PROJ)
-            conv_tc_epilogue_proj<ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+            conv_tc_epilogue_proj<ACT, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
         else
-            conv_tc_epilogue_warps<KIND, ACT, EPF_GENERIC>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+            conv_tc_epilogue_warps<KIND, ACT, EPF_GENERIC, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
     }
 
     tcgen05_fence_before();
@@ -852,6 +879,13 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
 template <int KIND, int ACT, int KB, int FL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
+    // KB = 64: x-major halo patch -- ONE TMA box of (8 + kh - 1) x (16 + kw - 1) pixels per 64-channel block, fetched with
+    // the tensor dims ordered {C, y, x} so that shared-memory row = x * RY + y, serves every tap: with M row m = x * 8 + y
+    // tap (ky,kx) is that patch read from row kx * RY + ky with an atom stride of RY rows.  (tools/umma_stride_probe.cu:
+    // a SWIZZLE_128B K-major descriptor accepts any 128-byte-aligned start and atom stride with base_offset 0.)  A 3x3
+    // conv pulls 1 patch of 10 x 18 pixels per block instead of 3 patches of 10 x 16: 2.6x less activation traffic.
+    // KB = 32 (the 7x1 stems, kw = 1: one box already serves all taps): y-major row patch as in conv_tc_patch_kernel.
+    constexpr bool XMT = (KB == 64);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -873,7 +907,8 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    const int ygroups = prm.kh / prm.ygroup;                 // A steps per (kb, kx)
+    const int ygroups = XMT ? 1 : prm.kh / prm.ygroup;       // A steps per (kb, kx); x-major: one patch per K block, ygroup = taps
+    const int kx_n = XMT ? 1 : prm.kw;
     const int pairs = (int)gridDim.x >> 1, pair_id = (int)blockIdx.x >> 1;
     const int items = (prm.num_tiles + 1) >> 1;              // work item = two consecutive tiles
 
@@ -911,21 +946,26 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
             for (int s = 0; s < prm.nsrc; ++s) {
                 for (int kb = 0; kb < prm.kblocks[s]; ++kb) {
                     const int c = prm.c_begin[s] + kb * KB;
-                    for (int kx = 0; kx < prm.kw; ++kx) {
-                        const int xs = x0 + kx - prm.pad_x;
+                    for (int kx = 0; kx < kx_n; ++kx) {
+                        const int xs = XMT ? x0 - prm.pad_x : x0 + kx - prm.pad_x;
                         for (int yg = 0; yg < ygroups; ++yg) {
-                            const int ys = y0 + yg * prm.ygroup - prm.pad_y;
+                            const int ys = y0 + (XMT ? 0 : yg * prm.ygroup) - prm.pad_y;
                             mbar_wait(&aempty[as], aph ^ 1u);
                             if (elect_one()) {
                                 uint8_t* ast = a_ring + (size_t)as * a_stage_bytes;
-                                if (leader) mbar_arrive_expect_tx(&afull[as], 2u * a_stage_bytes);
-                                tma_load_4d_pair(ast, &prm.act[s][0], afull_l + as * 8u, c, xs, ys, b);
-                                tma_load_4d_pair(ast + a_part, &prm.act[s][1], afull_l + as * 8u, c, xs, ys, b);
+                                if (leader) mbar_arrive_expect_tx(&afull[as], 2u * prm.a_tx_bytes);
+                                if (XMT) {           // tensor dims ordered {C, y, x, b}
+                                    tma_load_4d_pair(ast, &prm.act[s][0], afull_l + as * 8u, c, ys, xs, b);
+                                    tma_load_4d_pair(ast + a_part, &prm.act[s][1], afull_l + as * 8u, c, ys, xs, b);
+                                } else {
+                                    tma_load_4d_pair(ast, &prm.act[s][0], afull_l + as * 8u, c, xs, ys, b);
+                                    tma_load_4d_pair(ast + a_part, &prm.act[s][1], afull_l + as * 8u, c, xs, ys, b);
+                                }
                             }
                             if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
                             for (int kyi = 0; kyi < prm.ygroup; ++kyi) {
                                 if (!prm.w_resident || first) {
-                                    const int tap = (yg * prm.ygroup + kyi) * prm.kw + kx;
+                                    const int tap = XMT ? kyi : (yg * prm.ygroup + kyi) * prm.kw + kx;
                                     mbar_wait(&wempty[ws], wph ^ 1u);
                                     if (elect_one()) {
                                         uint8_t* wst = w_ring + (size_t)ws * w_stage_bytes;
@@ -952,7 +992,8 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
             uint32_t aph = 0, wph = 0, acs = 0, aphase = 0;
             int kb_total = 0;
             for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
-            const int a_steps = kb_total * prm.kw * ygroups;
+            const int a_steps = kb_total * kx_n * ygroups;
+            const uint32_t sbo = XMT ? (uint32_t)prm.patch_rows * KROW : 8u * KROW;      // bytes between 8-row atoms of A
             bool first = true;
             for (int item = pair_id; item < items; item += pairs) {
                 mbar_wait(&tmem_empty_bar[acs], aphase ^ 1u);     // both CTAs' epilogues drained this accumulator
@@ -964,14 +1005,20 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                     tcgen05_fence_after();
                     const uint32_t a_hi0 = smem_u32(a_ring + (size_t)as * a_stage_bytes);
                     for (int kyi = 0; kyi < prm.ygroup; ++kyi) {
-                        const uint32_t a_hi = a_hi0 + (uint32_t)kyi * (TC_TILE_W * KROW);
+                        uint32_t a_hi;
+                        if (XMT) {                   // tap kyi = (ky, kx): the patch read from row kx * RY + ky
+                            const int ky = kyi / prm.kw, kx = kyi - ky * prm.kw;
+                            a_hi = a_hi0 + (uint32_t)(kx * prm.patch_rows + ky) * KROW;
+                        } else {
+                            a_hi = a_hi0 + (uint32_t)kyi * (TC_TILE_W * KROW);
+                        }
                         if (!prm.w_resident || first) {
                             mbar_wait(&wfull[ws], wph);
                             tcgen05_fence_after();
                         }
                         if (elect_one()) {
                             const uint32_t w_hi = smem_u32(w_ring + (size_t)ws * w_stage_bytes);
-                            const uint64_t dah = smem_desc_kmajor<KB>(a_hi), dal = smem_desc_kmajor<KB>(a_hi + a_part);
+                            const uint64_t dah = smem_desc_kmajor_sbo<KB>(a_hi, sbo), dal = smem_desc_kmajor_sbo<KB>(a_hi + a_part, sbo);
                             const uint64_t dwh = smem_desc_kmajor<KB>(w_hi), dwl = smem_desc_kmajor<KB>(w_hi + b_bytes);
 #pragma unroll
                             for (int k = 0; k < KB / 16; ++k) {   // +32 bytes per K16 step = +2 in the address field
@@ -996,9 +1043,9 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
     } else {
         const TileWalk tw{pair_id, pairs, items, 2, (int)rank, leader ? 0u : mapa_u32(smem_u32(tmem_empty_bar), 0)};
         if constexpr (KIND == DKT_EPI_PROJ)
-            conv_tc_epilogue_proj<ACT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+            conv_tc_epilogue_proj<ACT, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
         else
-            conv_tc_epilogue_warps<KIND, ACT, FL>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+            conv_tc_epilogue_warps<KIND, ACT, FL, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
     }
 
     // neither CTA may leave (or free TMEM) while its peer can still reach its shared memory / barriers
@@ -1214,23 +1261,31 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
 
     // CTA-pair kernel (default for stride 1): each CTA stages half of a KBLK-channel weight block
     bool use_pair = s_pair != 0 && s_patch != 0 && stride == 1 && tiles64 >= 2 && (cin_sum % KBLK) == 0;
+    // 64-channel K blocks of the pair kernel: ONE x-major halo patch (RY x RX pixels, shared-memory row = x * RY + y) per
+    // K block serves every tap (tools/umma_stride_probe.cu: the SW128 descriptor takes any 128-byte-aligned start and any
+    // atom stride); each precision's slot is rounded up to the 1024-byte swizzle period
+    const bool xm = !k32;
+    const int patch_ry = TC_TILE_H + kh - 1, patch_rx = TC_TILE_W + kw - 1;
+    const uint32_t xm_box_bytes = (uint32_t)patch_ry * (uint32_t)patch_rx * 128u;
+    if (xm && (patch_ry > 256 || patch_rx > 256)) use_pair = false;
+    const uint32_t pair_a_part_bytes = xm ? (xm_box_bytes + 1023u) & ~1023u : a_part_bytes;
     int p_a_stages = 2, p_w_stages = 0, p_resident = 0;
     const uint32_t p_w_stage_bytes = 2u * (uint32_t)(Npad / 2) * (uint32_t)KBLK * 2u;
     if (use_pair) {
         const int w_steps = (cin_sum / KBLK) * kh * kw;            // weight blocks per tile
-        if (2u * a_part_bytes * 2 >= budget) use_pair = false;
-        else if (w_steps <= TCP_MAX_W && 2u * a_part_bytes * 2 + (uint32_t)w_steps * p_w_stage_bytes <= budget) {
+        if (2u * pair_a_part_bytes * 2 >= budget) use_pair = false;
+        else if (w_steps <= TCP_MAX_W && 2u * pair_a_part_bytes * 2 + (uint32_t)w_steps * p_w_stage_bytes <= budget) {
             p_resident = 1;                                        // whole filter half stays in the ring
             p_w_stages = w_steps;
-            p_a_stages = (int)((budget - (uint32_t)w_steps * p_w_stage_bytes) / (2u * a_part_bytes));
+            p_a_stages = (int)((budget - (uint32_t)w_steps * p_w_stage_bytes) / (2u * pair_a_part_bytes));
             if (p_a_stages > TCP_MAX_A) p_a_stages = TCP_MAX_A;
         } else {
-            p_w_stages = (int)((budget - 2u * a_part_bytes * 2) / p_w_stage_bytes);
+            p_w_stages = (int)((budget - 2u * pair_a_part_bytes * 2) / p_w_stage_bytes);
             if (p_w_stages > 8) p_w_stages = 8;
             if (p_w_stages < 2) use_pair = false;
-            else if (p_w_stages >= 7 && 2u * a_part_bytes * 3 + 4u * p_w_stage_bytes <= budget) {
+            else if (p_w_stages >= 7 && 2u * pair_a_part_bytes * 3 + 4u * p_w_stage_bytes <= budget) {
                 p_a_stages = 3;                                    // small N: a third patch stage is worth more
-                p_w_stages = (int)((budget - 2u * a_part_bytes * 3) / p_w_stage_bytes);
+                p_w_stages = (int)((budget - 2u * pair_a_part_bytes * 3) / p_w_stage_bytes);
                 if (p_w_stages > 8) p_w_stages = 8;
             }
         }
@@ -1269,6 +1324,16 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         prm.c_begin[s] = t.c_begin;
         prm.kblocks[s] = t.c_count / BK;
         cin_total += t.c_count;
+        if (use_pair && xm) {
+            // x-major patch: the tensor is described as {C, y, x, b} so that the box lands with y fastest
+            const uint64_t dims[4] = {(uint64_t)t.C, (uint64_t)Hin, (uint64_t)Win, (uint64_t)B};
+            const uint64_t strides[4] = {1, (uint64_t)t.C * Win, (uint64_t)t.C, (uint64_t)t.C * Win * Hin};
+            const uint32_t box[4] = {(uint32_t)BK, (uint32_t)patch_ry, (uint32_t)patch_rx, 1};
+            const uint32_t estr[4] = {1, 1, 1, 1};
+            if (!make_tmap_bf16(&prm.act[s][0], t.hi, 4, dims, strides, box, BK * 2, estr)) return DKT_E_DRIVER;
+            if (!make_tmap_bf16(&prm.act[s][1], t.lo, 4, dims, strides, box, BK * 2, estr)) return DKT_E_DRIVER;
+            continue;
+        }
         const uint64_t dims[4] = {(uint64_t)t.C, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
         const uint64_t strides[4] = {1, (uint64_t)t.C, (uint64_t)t.C * Win, (uint64_t)t.C * Win * Hin};
         const uint32_t box_rows = use_patch ? (uint32_t)(stride == 1 ? rows_loaded : TC_TILE_H * stride) : (uint32_t)(TC_TILE_H * stride);
@@ -1312,11 +1377,14 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     prm.epi = e;
 
     if (use_pair) {
-        prm.ygroup = ygroup;
+        prm.ygroup = xm ? kh * kw : ygroup;
+        prm.patch_rows = patch_ry;
         prm.a_stages = p_a_stages;
         prm.w_stages = p_w_stages;
         prm.w_resident = p_resident;
-        prm.a_part_bytes = a_part_bytes;
+        prm.a_part_bytes = pair_a_part_bytes;
+        prm.a_tx_bytes = 2u * (xm ? xm_box_bytes : a_part_bytes);
+        const uint32_t a_part_bytes = pair_a_part_bytes;
         const int items = (int)((tiles + 1) / 2);
         // as few CTA pairs as finish in the same number of rounds (255 items: 64 pairs x 4 rounds, not 74 x 3.45): the
         // SMs left free run the other stream's kernels (the coarse GRUs and the motion encoder overlap, update.py)

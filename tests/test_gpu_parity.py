@@ -569,9 +569,10 @@ def test_conv_proj_epilogue(shape):
 
 
 def test_conv_pair_matches_single_cta():
-    """The CTA-pair (cta_group::2) kernel and the single-CTA row-patch kernel are the same arithmetic in the same
-    order per output: results must agree bit for bit (DKT_CONV_PAIR is read once per process, so this test drives
-    the choice through a subprocess)."""
+    """The CTA-pair (cta_group::2) kernel with its x-major halo patch and the single-CTA row-patch kernel compute the
+    same products; only the order in which the taps enter the fp32 accumulator differs, so the results agree to
+    fp32 round-off (tolerance 2e-5 on O(1) outputs).  DKT_CONV_PAIR is read once per process, so this test drives
+    the choice through a subprocess."""
     import subprocess, sys, os
     code = r"""
 import torch, sys
@@ -601,7 +602,7 @@ torch.save(outs, sys.argv[1])
             subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300)
             res[mode] = torch.load(f.name)
     for a, b in zip(res["0"], res["1"]):
-        assert torch.equal(a, b), float((a - b).abs().max())
+        assert float((a - b).abs().max()) <= 2e-5, float((a - b).abs().max())
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 64, 19, 37, 1), (3, 64, 128, 40, 50, 2), (1, 128, 128, 8, 16, 1)])
