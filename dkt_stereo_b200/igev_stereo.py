@@ -7,10 +7,11 @@ contract (``test_mode=True`` -> ``(None, disp_up)``, disp_up = -disparity, refer
 served.
 
 What runs where:
-  PyTorch (cuDNN)  : MobileNetV2 feature pyramid, stems, GWC volume, 3-D hourglass, soft-argmin
-                     init disparity, cnet, context convs, the two small convs of ``upsample_disp``
-                     (reference igev_stereo.py:154-189, 143-144)  -- SURVEY 8f "next" rows
-  libdkt kernels   : all-pairs init-corr pyramid (K1, scale 1), geometry-volume pyramid
+  PyTorch (cuDNN)  : MobileNetV2 feature pyramid, stems, 3-D hourglass, the two small convs of
+                     ``upsample_disp`` (reference igev_stereo.py:154-189, 143-144)  -- SURVEY 8f "next" rows
+  libdkt kernels   : cnet + context convs (EncoderEngine), GWC volume, corr_stem (3-D conv + BN + LeakyReLU +
+                     feature attention), classifier + soft-argmin init disparity (igev_preloop.cu),
+                     all-pairs init-corr pyramid (K1, scale 1), geometry-volume pyramid
                      (dkt_geo_pool), per-iteration combined lookup + `disp += delta` + convc1
                      (dkt_geo_lookup_enc), motion encoder + 3 ConvGRUs + disp head (K3),
                      mask_feat_4 head, context_upsample (K4)   (reference igev_stereo.py:192-216)
@@ -72,6 +73,8 @@ class IGEVStereo(nn.Module):
                 and not getattr(args, "mixed_precision", False)):
             from .encoder import EncoderEngine
             self.encoder = EncoderEngine(None, self.cnet, self.context_zqr_convs, self.engine)
+        # volume stage of the pre-loop on libdkt kernels (GWC volume, corr_stem, classifier, soft-argmin)
+        self.native_volume = os.environ.get("DKT_NATIVE_VOLUME", "1") == "1" and not getattr(args, "mixed_precision", False)
         self.use_cuda_graph = os.environ.get("DKT_CUDA_GRAPH", "1") == "1"
         self.extractor_fp32 = not getattr(args, "extractor_tf32", False)
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
@@ -101,11 +104,27 @@ class IGEVStereo(nn.Module):
             match_left = self.desc(self.conv(fl[0]))
             match_right = self.desc(self.conv(fr[0]))
             D = args.max_disp // 4
-            vol = self.corr_stem(build_gwc_volume(match_left, match_right, D, 8))
-            vol = self.corr_feature_att(vol, fl[0])
+            native_vol = (self.native_volume and image1.is_cuda and match_left.dtype == torch.float32
+                          and not self.corr_stem.bn.training)
+            if native_vol:
+                # libdkt (igev_preloop.cu): GWC volume; corr_stem's 3-D conv with its eval-mode BatchNorm folded, LeakyReLU
+                # and the feature-attention product in the epilogue (reference igev_stereo.py:169-171)
+                bn = self.corr_stem.bn
+                scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                shift = bn.bias - bn.running_mean * scale
+                att = self.corr_feature_att.feat_att(fl[0]).float()
+                vol = ops.conv3d_c8(ops.gwc_volume(match_left, match_right, D, 8), self.corr_stem.conv.weight,
+                                    scale, shift, 0.01, att)
+            else:
+                vol = self.corr_stem(build_gwc_volume(match_left, match_right, D, 8))
+                vol = self.corr_feature_att(vol, fl[0])
             gev = self.cost_agg(vol, fl)
-            prob = F.softmax(self.classifier(gev).squeeze(1), dim=1)
-            init_disp = disparity_regression(prob, D)
+            if native_vol and gev.dtype == torch.float32:
+                # classifier conv + softmax + disparity regression (reference igev_stereo.py:175-176)
+                init_disp = ops.softargmin(ops.conv3d_c8(gev, self.classifier.weight).squeeze(1))
+            else:
+                prob = F.softmax(self.classifier(gev).squeeze(1), dim=1)
+                init_disp = disparity_regression(prob, D)
             if self.encoder is not None and image1.is_cuda:
                 net_list = ctx_list = None       # written straight into the update engine's buffers by forward()
             else:

@@ -129,6 +129,59 @@ def geo_pool(gev: torch.Tensor, out: Optional[Sequence[torch.Tensor]] = None):
     return g0, g1
 
 
+def gwc_volume(left: torch.Tensor, right: torch.Tensor, maxdisp: int, groups: int,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Group-wise correlation volume (B,groups,maxdisp,H,W) of two (B,C,H,W) fp32 feature maps
+    (reference meta_arch/igev_stereo/submodule.py:152-170)."""
+    lib = L.load()
+    L.require_device(left)
+    assert left.shape == right.shape and left.dtype == torch.float32 and right.dtype == torch.float32
+    left, right = left.contiguous(), right.contiguous()
+    B, C, H, W = left.shape
+    if out is None:
+        out = torch.empty(B, groups, maxdisp, H, W, device=left.device, dtype=torch.float32)
+    assert out.shape == (B, groups, maxdisp, H, W) and out.is_contiguous()
+    L.check(lib.dkt_gwc_volume(left.data_ptr(), right.data_ptr(), out.data_ptr(), B, C, groups, maxdisp, H, W,
+                               L.stream_ptr()), "gwc_volume")
+    return out
+
+
+def conv3d_c8(x: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Tensor] = None,
+              shift: Optional[torch.Tensor] = None, slope: float = 1.0, att: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3x3 Conv3d, 8 -> 8 or 1 channels, padding 1, no bias, then ``leaky(acc * scale + shift, slope) *
+    sigmoid(att)``: x (B,8,D,H,W), weight (CO,8,3,3,3), scale/shift (CO,), att (B,CO,H,W) logits
+    (reference BasicConv / FeatureAtt / classifier, meta_arch/igev_stereo/submodule.py:10-36,227-240)."""
+    lib = L.load()
+    L.require_device(x)
+    B, Cin, D, H, W = x.shape
+    CO = weight.shape[0]
+    assert Cin == 8 and tuple(weight.shape) == (CO, 8, 3, 3, 3) and x.dtype == torch.float32
+    x, weight = x.contiguous(), weight.contiguous().float()
+    if out is None:
+        out = torch.empty(B, CO, D, H, W, device=x.device, dtype=torch.float32)
+    assert out.shape == (B, CO, D, H, W) and out.is_contiguous()
+    keep = [t.contiguous().float() if t is not None else None for t in (scale, shift, att)]
+    if keep[2] is not None:
+        assert keep[2].shape == (B, CO, H, W)
+    ptr = [t.data_ptr() if t is not None else None for t in keep]
+    L.check(lib.dkt_conv3d_c8(x.data_ptr(), weight.data_ptr(), ptr[0], ptr[1], ptr[2], float(slope), out.data_ptr(),
+                              B, CO, D, H, W, L.stream_ptr()), "conv3d_c8")
+    return out
+
+
+def softargmin(logits: torch.Tensor) -> torch.Tensor:
+    """(B,D,H,W) fp32 -> (B,1,H,W) = sum_d d * softmax_d (reference submodule.py:220-224 after F.softmax)."""
+    lib = L.load()
+    L.require_device(logits)
+    assert logits.dtype == torch.float32
+    logits = logits.contiguous()
+    B, D, H, W = logits.shape
+    out = torch.empty(B, 1, H, W, device=logits.device, dtype=torch.float32)
+    L.check(lib.dkt_softargmin(logits.data_ptr(), out.data_ptr(), B, D, H, W, L.stream_ptr()), "softargmin")
+    return out
+
+
 def corr1d_lookup_enc(pyr: Sequence[torch.Tensor], coords_x: torch.Tensor, radius: int, w: "ConvWeights",
                       enc_out: DktTensor, delta: Optional[torch.Tensor] = None,
                       flow: Optional[torch.Tensor] = None) -> None:

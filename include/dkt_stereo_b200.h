@@ -174,6 +174,25 @@ int dkt_geo_lookup_enc(const float* geo0, const float* geo1, const float* init0,
                        const float* enc_w, const float* enc_b, const dkt_tensor* enc_out,
                        int B, int H, int W, void* stream);
 
+/* ---- IGEV pre-loop volume kernels, exact fp32 ------------------------------
+ * dkt_gwc_volume: group-wise correlation volume, replaces build_gwc_volume + groupwise_correlation
+ *   (reference meta_arch/igev_stereo/submodule.py:152-170; call site igev_stereo.py:169):
+ *   left, right (B,C,H,W) -> vol (B,groups,D,H,W), vol[b,g,d,y,x] = mean over the group's C/groups channels of
+ *   left[b,c,y,x] * right[b,c,y,x-d], 0 where x < d.  C/groups <= 16.
+ * dkt_conv3d_c8: 3x3x3 Conv3d (8 input channels, CO = 8 or 1 outputs, stride 1, padding 1, no bias) with the epilogue
+ *   v = acc * scale[co] + shift[co]; v = v > 0 ? v : slope * v; v *= sigmoid(att[b,co,y,x])  (scale/shift/att may be
+ *   NULL; slope = 1 for no activation).  in (B,8,D,H,W), weight [CO][8][3][3][3] (PyTorch layout), att (B,CO,H,W),
+ *   out (B,CO,D,H,W), in != out.  Replaces corr_stem = BasicConv(8,8,is_3d) with its eval-mode BatchNorm3d folded to
+ *   scale/shift + LeakyReLU(0.01) (submodule.py:10-36) followed by FeatureAtt's broadcast product (submodule.py:227-240;
+ *   igev_stereo.py:130-131,170-171), and `classifier` = nn.Conv3d(8,1,3,1,1,bias=False) (igev_stereo.py:133,175).
+ * dkt_softargmin: logits (B,D,H,W) -> disp (B,1,H,W) = sum_d d * softmax_d(logits): F.softmax(dim=1) followed by
+ *   disparity_regression (submodule.py:220-224; igev_stereo.py:175-176). */
+int dkt_gwc_volume(const float* left, const float* right, float* vol, int B, int C, int groups, int D, int H, int W,
+                   void* stream);
+int dkt_conv3d_c8(const float* in, const float* weight, const float* scale, const float* shift, const float* att,
+                  float slope, float* out, int B, int CO, int D, int H, int W, void* stream);
+int dkt_softargmin(const float* logits, float* disp, int B, int D, int H, int W, void* stream);
+
 /* ---- K3: convolutions of the update block with fused epilogues ------------------------------
  * Replaces nn.Conv2d + bias + activation + the GRU gate algebra of reference core/update.py
  * (FlowHead :6-14, ConvGRU :16-32, BasicMotionEncoder :64-85, mask head :110-113) and the IGEV

@@ -377,3 +377,44 @@ def igev_loop(sd: SD, match_left: Tensor, match_right: Tensor, geo_volume: Tenso
                                              with_mask=(it == iters - 1))
         disp = disp + delta
     return -igev_upsample_disp(sd, disp, mask_feat, stem_2x)
+
+
+# ----------------------------------------------------------------------------
+# IGEV pre-loop volume stage
+# ----------------------------------------------------------------------------
+def gwc_volume(left: Tensor, right: Tensor, maxdisp: int, groups: int) -> Tensor:
+    """Group-wise correlation volume (B,groups,maxdisp,H,W): reference
+    meta_arch/igev_stereo/submodule.py:152-170 (build_gwc_volume + groupwise_correlation)."""
+    B, C, H, W = left.shape
+    cpg = C // groups
+    vol = left.new_zeros(B, groups, maxdisp, H, W)
+    for d in range(maxdisp):
+        if d >= W:
+            break
+        prod = left[:, :, :, d:] * right[:, :, :, : W - d]
+        vol[:, :, d, :, d:] = prod.view(B, groups, cpg, H, W - d).mean(dim=2)
+    return vol
+
+
+def conv3d_bn_leaky_att(x: Tensor, weight: Tensor, bn: Optional[Dict[str, Tensor]], slope: float,
+                        att_logits: Optional[Tensor]) -> Tensor:
+    """BasicConv(is_3d, eval-mode BatchNorm3d, LeakyReLU(0.01)) followed by FeatureAtt's product: reference
+    meta_arch/igev_stereo/submodule.py:10-36 and :227-240 (call sites igev_stereo.py:170-171).
+    ``bn`` = dict(weight, bias, running_mean, running_var, eps) or None; ``att_logits`` (B,C,H,W) or None."""
+    y = F.conv3d(x, weight, None, stride=1, padding=1)
+    if bn is not None:
+        y = F.batch_norm(y, bn["running_mean"], bn["running_var"], bn["weight"], bn["bias"], False, 0.0, float(bn["eps"]))
+    if slope != 1.0:
+        y = F.leaky_relu(y, slope)
+    if att_logits is not None:
+        y = torch.sigmoid(att_logits.unsqueeze(2)) * y
+    return y
+
+
+def softargmin(logits: Tensor) -> Tensor:
+    """F.softmax over the disparity axis + disparity_regression: reference igev_stereo.py:175-176 and
+    submodule.py:220-224.  logits (B,D,H,W) -> (B,1,H,W)."""
+    prob = F.softmax(logits, dim=1)
+    D = logits.shape[1]
+    values = torch.arange(0, D, dtype=logits.dtype).view(1, D, 1, 1)
+    return torch.sum(prob * values, 1, keepdim=True)

@@ -222,6 +222,35 @@ def golden_igev_forward(m, height=64, width=96, iters=4, tag="igev_fwd_small", b
          key_shapes=np.array([json.dumps(list(sd[k].shape)) for k in hot_keys]), **cap)
 
 
+def golden_igev_volume(m, B=1, C=96, H=9, W=37, D=20, tag="igev_volume"):
+    """The volume stage of the IGEV pre-loop through the REAL reference modules: build_gwc_volume,
+    corr_stem (BasicConv 3-D, eval-mode BatchNorm with non-trivial running statistics), FeatureAtt, the classifier
+    convolution, softmax + disparity_regression (reference igev_stereo.py:169-176)."""
+    sub = m["igev_sub"]
+    g = torch.Generator().manual_seed(77)
+    left = torch.randn(B, C, H, W, generator=g)
+    right = torch.randn(B, C, H, W, generator=g)
+    feat = torch.randn(B, C, H, W, generator=g)
+    stem = sub.BasicConv(8, 8, is_3d=True, kernel_size=3, stride=1, padding=1).eval()
+    fatt = sub.FeatureAtt(8, C).eval()
+    classifier = torch.nn.Conv3d(8, 1, 3, 1, 1, bias=False)
+    with torch.no_grad():
+        for mod in (stem, fatt, classifier):
+            for prm in mod.parameters():
+                prm.copy_(torch.randn(prm.shape, generator=g) * 0.3)
+        for bn in (stem.bn, fatt.feat_att[0].bn):
+            bn.running_mean.copy_(torch.randn(bn.running_mean.shape, generator=g) * 0.2)
+            bn.running_var.copy_(torch.rand(bn.running_var.shape, generator=g) + 0.5)
+        gwc = sub.build_gwc_volume(left, right, D, 8)
+        att_logits = fatt.feat_att(feat)
+        vol = fatt(stem(gwc), feat)
+        logits = classifier(vol).squeeze(1)
+        disp = sub.disparity_regression(torch.nn.functional.softmax(logits, dim=1), D)
+    save(tag, left=left, right=right, gwc=gwc, stem_w=stem.conv.weight, bn_weight=stem.bn.weight, bn_bias=stem.bn.bias,
+         bn_mean=stem.bn.running_mean, bn_var=stem.bn.running_var, bn_eps=np.array(stem.bn.eps), att_logits=att_logits,
+         vol=vol, cls_w=classifier.weight, logits=logits, disp=disp, meta=np.array([B, C, H, W, D]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -239,6 +268,7 @@ def main():
         "raft_cfg2": lambda: golden_raft_forward(m, 544, 960, 32, "raft_fwd_cfg2", 1, "noise"),
         "igev_small": lambda: golden_igev_forward(m),
         "igev_mid": lambda: golden_igev_forward(m, 96, 160, 8, "igev_fwd_mid", 1),
+        "igev_volume": lambda: golden_igev_volume(m),
     }
     for k, fn in jobs.items():
         if not args.only or k in args.only.split(","):

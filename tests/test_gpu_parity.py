@@ -738,3 +738,116 @@ def test_shape_changes_invalidate_graphs():
         _, up = model(im1, im2, iters=3, test_mode=True)
         _, ref = fresh(im1, im2, iters=3, test_mode=True)
         assert torch.equal(up, ref), (k, float((up - ref).abs().max()))
+
+
+# ---------------------------------------------------------------------------------------------
+# IGEV pre-loop volume stage: exact-fp32 kernels, tolerance = fp32 round-off of a different
+# summation order (2e-5 abs on O(1..10) values; the soft-argmin's disparities are O(D): 1e-4)
+# ---------------------------------------------------------------------------------------------
+def _bn_fold(g):
+    scale = g["bn_weight"] / torch.sqrt(g["bn_var"] + float(g["bn_eps"]))
+    return scale, g["bn_bias"] - g["bn_mean"] * scale
+
+
+def test_igev_volume_stage_golden():
+    """dkt_gwc_volume / dkt_conv3d_c8 / dkt_softargmin against the real reference's modules (igev_volume.npz)."""
+    from dkt_stereo_b200 import ops
+    g = load_golden("igev_volume")
+    B, C, H, W, D = [int(v) for v in g["meta"]]
+    d = dev()
+    gwc = ops.gwc_volume(g["left"].to(d), g["right"].to(d), D, 8)
+    assert stats(gwc.cpu(), g["gwc"])[1] < 2e-6, stats(gwc.cpu(), g["gwc"])
+    scale, shift = _bn_fold(g)
+    vol = ops.conv3d_c8(g["gwc"].to(d), g["stem_w"].to(d), scale.to(d), shift.to(d), 0.01, g["att_logits"].to(d))
+    assert stats(vol.cpu(), g["vol"])[1] < 2e-5, stats(vol.cpu(), g["vol"])
+    logits = ops.conv3d_c8(g["vol"].to(d), g["cls_w"].to(d))
+    assert logits.shape == (B, 1, D, H, W)
+    assert stats(logits.cpu().squeeze(1), g["logits"])[1] < 2e-5
+    disp = ops.softargmin(g["logits"].to(d))
+    assert stats(disp.cpu(), g["disp"])[1] < 1e-4
+    # chained, as IGEVStereo.prepare runs them
+    disp2 = ops.softargmin(ops.conv3d_c8(vol, g["cls_w"].to(d)).squeeze(1))
+    assert stats(disp2.cpu(), g["disp"])[1] < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(2, 96, 5, 150, 48), (1, 32, 3, 64, 7), (1, 96, 2, 33, 48)])
+def test_gwc_volume_vs_oracle(shape):
+    """Several x tiles, W < D (disparities that never see a valid pixel stay 0), ragged widths."""
+    from dkt_stereo_b200 import ops
+    from oracle import hotpath as O
+    B, C, H, W, D = shape
+    g = torch.Generator().manual_seed(W + D)
+    left, right = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
+    ref = O.gwc_volume(left, right, D, 8)
+    got = torch.full((B, 8, D, H, W), float("nan"), device=dev())
+    ops.gwc_volume(left.to(dev()), right.to(dev()), D, 8, out=got)
+    assert not torch.isnan(got).any()
+    assert stats(got.cpu(), ref)[1] < 2e-6, stats(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 48, 11, 70), (1, 8, 5, 4, 32), (1, 1, 48, 9, 45), (2, 1, 17, 6, 33)])
+def test_conv3d_c8_vs_oracle(shape):
+    """Ragged tiles in d / y / x, both channel variants, every epilogue term on and off."""
+    from dkt_stereo_b200 import ops
+    from oracle import hotpath as O
+    B, CO, D, H, W = shape
+    g = torch.Generator().manual_seed(D * 7 + W)
+    x = torch.randn(B, 8, D, H, W, generator=g)
+    w = torch.randn(CO, 8, 3, 3, 3, generator=g) * 0.2
+    bn = dict(weight=torch.randn(CO, generator=g), bias=torch.randn(CO, generator=g), running_mean=torch.randn(CO, generator=g) * 0.1,
+              running_var=torch.rand(CO, generator=g) + 0.5, eps=1e-5)
+    att = torch.randn(B, CO, H, W, generator=g)
+    scale = bn["weight"] / torch.sqrt(bn["running_var"] + bn["eps"])
+    shift = bn["bias"] - bn["running_mean"] * scale
+    d = dev()
+    for use_bn, slope, use_att in ((True, 0.01, True), (False, 1.0, False), (True, 1.0, False)):
+        ref = O.conv3d_bn_leaky_att(x, w, bn if use_bn else None, slope, att if use_att else None)
+        got = torch.full((B, CO, D, H, W), float("nan"), device=d)
+        ops.conv3d_c8(x.to(d), w.to(d), scale.to(d) if use_bn else None, shift.to(d) if use_bn else None, slope,
+                      att.to(d) if use_att else None, out=got)
+        assert not torch.isnan(got).any()
+        assert stats(got.cpu(), ref)[1] < 3e-5, (use_bn, slope, use_att, stats(got.cpu(), ref))
+
+
+def test_softargmin_vs_oracle():
+    from dkt_stereo_b200 import ops
+    from oracle import hotpath as O
+    g = torch.Generator().manual_seed(9)
+    logits = torch.randn(3, 48, 7, 61, generator=g) * 4
+    ref = O.softargmin(logits)
+    got = ops.softargmin(logits.to(dev()))
+    assert got.shape == ref.shape
+    assert stats(got.cpu(), ref)[1] < 1e-4
+
+
+def test_igev_native_volume_stage_end_to_end(monkeypatch):
+    """IGEVStereo with the volume stage on libdkt kernels vs the same model with that stage in PyTorch fp32
+    (DKT_NATIVE_VOLUME=0): geometry volume and initial disparity agree to fp32 round-off, the final disparity within the
+    end-to-end gate (1e-3 px mean-abs)."""
+    from dkt_stereo_b200.igev_stereo import IGEVStereo
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    torch.manual_seed(12)
+    monkeypatch.setenv("DKT_NATIVE_VOLUME", "1")
+    a = IGEVStereo(Namespace(mixed_precision=False, **IGEV_CFG)).eval().to(dev())
+    monkeypatch.setenv("DKT_NATIVE_VOLUME", "0")
+    b = IGEVStereo(Namespace(mixed_precision=False, **IGEV_CFG)).eval().to(dev())
+    assert a.native_volume and not b.native_volume
+    with torch.no_grad():                      # non-trivial BatchNorm statistics in the folded layer
+        a.corr_stem.bn.running_mean.normal_(0, 0.2)
+        a.corr_stem.bn.running_var.uniform_(0.5, 1.5)
+        a.corr_stem.bn.weight.normal_(1, 0.2)
+        a.corr_stem.bn.bias.normal_(0, 0.2)
+    b.load_state_dict(a.state_dict(), strict=True)
+    im1, im2 = synthetic_pair(2, 128, 224, seed=22, mode="shift")
+    im1, im2 = im1.to(dev()), im2.to(dev())
+    with torch.no_grad():
+        pa, pb = a.prepare(im1, im2), b.prepare(im1, im2)
+    for name, i in (("gev", 2), ("init_disp", 3)):
+        mean, mx = stats(pa[i].cpu(), pb[i].cpu())
+        print(f"[parity] igev native volume stage {name}: mean-abs {mean:.3e}, max-abs {mx:.3e}")
+        assert mx < 5e-4, (name, mean, mx)
+    _, ua = a(im1, im2, iters=6, test_mode=True)
+    _, ub = b(im1, im2, iters=6, test_mode=True)
+    mean, mx = stats(ua.cpu(), ub.cpu())
+    print(f"[parity] igev native volume stage, final disparity: mean-abs {mean:.3e} px, max-abs {mx:.3e} px")
+    assert mean <= 1e-3, (mean, mx)

@@ -97,3 +97,21 @@ def test_igev_loop_against_reference_forward():
         assert up.shape == g["disp_up"].shape == (B, 1, H, W)
         mean, mx = stats(up, g["disp_up"])
         assert mean < 1e-4, (tag, mean, mx)
+
+
+def test_igev_volume_stage():
+    """GWC volume, 3-D corr_stem + BatchNorm + LeakyReLU + feature attention, classifier, soft-argmin against the real
+    reference's modules (tests/golden/igev_volume.npz, oracle/make_golden.py --only igev_volume)."""
+    g = load_golden("igev_volume")
+    B, C, H, W, D = [int(v) for v in g["meta"]]
+    gwc = O.gwc_volume(g["left"], g["right"], D, 8)
+    assert gwc.shape == g["gwc"].shape == (B, 8, D, H, W)
+    assert stats(gwc, g["gwc"])[1] < 2e-6
+    bn = dict(weight=g["bn_weight"], bias=g["bn_bias"], running_mean=g["bn_mean"], running_var=g["bn_var"], eps=float(g["bn_eps"]))
+    vol = O.conv3d_bn_leaky_att(g["gwc"], g["stem_w"], bn, 0.01, g["att_logits"])
+    assert stats(vol, g["vol"])[1] < 2e-5
+    logits = O.conv3d_bn_leaky_att(g["vol"], g["cls_w"], None, 1.0, None).squeeze(1)
+    assert stats(logits, g["logits"])[1] < 2e-5
+    disp = O.softargmin(g["logits"])
+    assert disp.shape == g["disp"].shape == (B, 1, H, W)
+    assert stats(disp, g["disp"])[1] < 2e-5

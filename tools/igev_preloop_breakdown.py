@@ -12,6 +12,8 @@ from dkt_stereo_b200.igev_modules import build_gwc_volume, disparity_regression
 from dkt_stereo_b200.raft_stereo import _fp32_math
 from dkt_stereo_b200.synthetic import synthetic_pair
 
+from dkt_stereo_b200 import ops
+NATIVE = os.environ.get("DKT_NATIVE_VOLUME", "1") == "1"
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 m = IGEVStereo(Namespace(mixed_precision=False, corr_implementation="b200", **IGEV_CFG)).eval().to(dev)
@@ -30,11 +32,22 @@ def run():
         fl[0] = torch.cat((fl[0], s4), 1); fr[0] = torch.cat((fr[0], s4y), 1)
         ml = m.desc(m.conv(fl[0])); mr = m.desc(m.conv(fr[0])); mark("conv+desc")
         D = a.max_disp // 4
-        g = build_gwc_volume(ml, mr, D, 8); mark("build_gwc_volume")
-        vol = m.corr_stem(g); mark("corr_stem (3D conv)")
-        vol = m.corr_feature_att(vol, fl[0]); mark("feature_att")
+        if NATIVE:
+            g = ops.gwc_volume(ml, mr, D, 8); mark("dkt_gwc_volume")
+            bn = m.corr_stem.bn
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps); shift = bn.bias - bn.running_mean * scale
+            att = m.corr_feature_att.feat_att(fl[0]); mark("feature_att logits (2-D convs)")
+            vol = ops.conv3d_c8(g, m.corr_stem.conv.weight, scale, shift, 0.01, att); mark("dkt_conv3d_c8 corr_stem+BN+leaky+att")
+        else:
+            g = build_gwc_volume(ml, mr, D, 8); mark("build_gwc_volume")
+            vol = m.corr_stem(g); mark("corr_stem (3D conv)")
+            vol = m.corr_feature_att(vol, fl[0]); mark("feature_att")
         gev = m.cost_agg(vol, fl); mark("hourglass (3D)")
-        prob = F.softmax(m.classifier(gev).squeeze(1), dim=1); d0 = disparity_regression(prob, D); mark("classifier+regress")
+        if NATIVE:
+            lg = ops.conv3d_c8(gev, m.classifier.weight); mark("dkt_conv3d_c8 classifier")
+            d0 = ops.softargmin(lg.squeeze(1)); mark("dkt_softargmin")
+        else:
+            prob = F.softmax(m.classifier(gev).squeeze(1), dim=1); d0 = disparity_regression(prob, D); mark("classifier+regress")
         cl = m.cnet(i1, num_layers=a.n_gru_layers); mark("cnet")
         nl = [torch.tanh(x[0]) for x in cl]; cx = [c(torch.relu(x[1])) for x, c in zip(cl, m.context_zqr_convs)]; mark("ctx convs")
 for _ in range(3):
