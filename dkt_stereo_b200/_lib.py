@@ -54,6 +54,9 @@ SIGNATURES = {
     "dkt_geo_pool": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dkt_gwc_volume": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dkt_conv3d_c8": [_P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _P],
+    "dkt_conv3d_k3": [_P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dkt_deconv3d_k4s2": [_P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _P],
+    "dkt_conv3d_k1": [_P, _I, _P, _I, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _P],
     "dkt_softargmin": [_P, _P, _I, _I, _I, _I, _P],
     "dkt_corr1d_lookup_enc": [_P, _I, _I, _P, _P, _I, _P, _P, _P, _TP, _I, _I, _I, _I, _P],
     "dkt_geo_lookup": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I64, _I64, _I64, _I, _I, _I, _P],

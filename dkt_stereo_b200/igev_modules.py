@@ -107,6 +107,45 @@ class Hourglass(nn.Module):
         self.feature_att_up_16 = FeatureAtt(4 * c, 192)
         self.feature_att_up_8 = FeatureAtt(2 * c, 64)
 
+    def forward_native(self, x, feats: Sequence[torch.Tensor]):
+        """The same graph on libdkt's exact-fp32 3-D convolution kernels (csrc/igev_preloop.cu): every BasicConv is one
+        launch with its eval-mode BatchNorm folded, LeakyReLU and the following FeatureAtt product in the epilogue; the
+        two torch.cat are read in place by the 1x1x1 kernel.  Reference igev_stereo.py:66-89."""
+        from . import ops
+
+        def fold(m: ConvNormAct):
+            if not m.use_norm:
+                return None, None, (0.01 if m.act else 1.0)
+            bn = m.bn
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            return scale, bn.bias - bn.running_mean * scale, (0.01 if m.act else 1.0)
+
+        def k3(m, v, stride=1, att=None):
+            sc, sh, sl = fold(m)
+            return ops.conv3d_k3(v, m.conv.weight, sc, sh, sl, att, stride)
+
+        def up(m, v):
+            sc, sh, sl = fold(m)
+            return ops.deconv3d_k4s2(v, m.conv.weight, sc, sh, sl)
+
+        def k1(m, a, b):
+            sc, sh, sl = fold(m)
+            return ops.conv3d_k1(a, b, m.conv.weight, sc, sh, sl)
+
+        att = lambda fa, f: fa.feat_att(f).float()
+        c1 = k3(self.conv1[1], k3(self.conv1[0], x, 2), att=att(self.feature_att_8, feats[1]))
+        c2 = k3(self.conv2[1], k3(self.conv2[0], c1, 2), att=att(self.feature_att_16, feats[2]))
+        c3 = k3(self.conv3[1], k3(self.conv3[0], c2, 2), att=att(self.feature_att_32, feats[3]))
+        a = k3(self.agg_0[1], k1(self.agg_0[0], up(self.conv3_up, c3), c2))
+        c2 = k3(self.agg_0[2], a, att=att(self.feature_att_up_16, feats[2]))
+        a = k3(self.agg_1[1], k1(self.agg_1[0], up(self.conv2_up, c2), c1))
+        c1 = k3(self.agg_1[2], a, att=att(self.feature_att_up_8, feats[1]))
+        return up(self.conv1_up, c1)
+
+    def native_ok(self, x: torch.Tensor) -> bool:
+        """Even sizes down the three stride-2 levels (the deconvolutions then return exactly the skip shapes)."""
+        return x.is_cuda and x.dtype == torch.float32 and not self.training and all(v % 8 == 0 for v in x.shape[2:])
+
     def forward(self, x, feats: Sequence[torch.Tensor]):
         c1 = self.feature_att_8(self.conv1(x), feats[1])
         c2 = self.feature_att_16(self.conv2(c1), feats[2])

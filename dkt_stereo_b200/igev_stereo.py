@@ -7,10 +7,10 @@ contract (``test_mode=True`` -> ``(None, disp_up)``, disp_up = -disparity, refer
 served.
 
 What runs where:
-  PyTorch (cuDNN)  : MobileNetV2 feature pyramid, stems, 3-D hourglass, the two small convs of
-                     ``upsample_disp`` (reference igev_stereo.py:154-189, 143-144)  -- SURVEY 8f "next" rows
+  PyTorch (cuDNN)  : MobileNetV2 feature pyramid, stems, the 2-D attention convs of FeatureAtt, the two small convs
+                     of ``upsample_disp`` (reference igev_stereo.py:154-168, 143-144)  -- SURVEY 8f "next" rows
   libdkt kernels   : cnet + context convs (EncoderEngine), GWC volume, corr_stem (3-D conv + BN + LeakyReLU +
-                     feature attention), classifier + soft-argmin init disparity (igev_preloop.cu),
+                     feature attention), the 3-D hourglass, classifier + soft-argmin init disparity (igev_preloop.cu),
                      all-pairs init-corr pyramid (K1, scale 1), geometry-volume pyramid
                      (dkt_geo_pool), per-iteration combined lookup + `disp += delta` + convc1
                      (dkt_geo_lookup_enc), motion encoder + 3 ConvGRUs + disp head (K3),
@@ -118,7 +118,10 @@ class IGEVStereo(nn.Module):
             else:
                 vol = self.corr_stem(build_gwc_volume(match_left, match_right, D, 8))
                 vol = self.corr_feature_att(vol, fl[0])
-            gev = self.cost_agg(vol, fl)
+            if native_vol and self.cost_agg.native_ok(vol):
+                gev = self.cost_agg.forward_native(vol, fl)          # 3-D hourglass, reference igev_stereo.py:22-89,172
+            else:
+                gev = self.cost_agg(vol, fl)
             if native_vol and gev.dtype == torch.float32:
                 # classifier conv + softmax + disparity regression (reference igev_stereo.py:175-176)
                 init_disp = ops.softargmin(ops.conv3d_c8(gev, self.classifier.weight).squeeze(1))

@@ -170,6 +170,72 @@ def conv3d_c8(x: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Tenso
     return out
 
 
+def _opt_ptrs(*ts):
+    keep = [t.contiguous().float() if t is not None else None for t in ts]
+    return keep, [t.data_ptr() if t is not None else None for t in keep]
+
+
+def conv3d_k3(x: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Tensor] = None,
+              shift: Optional[torch.Tensor] = None, slope: float = 1.0, att: Optional[torch.Tensor] = None,
+              stride: int = 1) -> torch.Tensor:
+    """3x3x3 Conv3d (padding 1, stride 1 | 2, no bias) + ``leaky(acc * scale + shift, slope) * sigmoid(att)``:
+    x (B,CI,D,H,W) fp32, weight (CO,CI,3,3,3), att (B,CO,Ho,Wo) logits (reference BasicConv / FeatureAtt,
+    meta_arch/igev_stereo/submodule.py:10-36,227-240)."""
+    lib = L.load()
+    L.require_device(x)
+    B, CI, D, H, W = x.shape
+    CO = weight.shape[0]
+    assert tuple(weight.shape) == (CO, CI, 3, 3, 3) and x.dtype == torch.float32
+    x, weight = x.contiguous(), weight.contiguous().float()
+    Do, Ho, Wo = ((v - 1) // stride + 1 for v in (D, H, W))
+    out = torch.empty(B, CO, Do, Ho, Wo, device=x.device, dtype=torch.float32)
+    keep, ptr = _opt_ptrs(scale, shift, att)
+    if keep[2] is not None:
+        assert keep[2].shape == (B, CO, Ho, Wo)
+    L.check(lib.dkt_conv3d_k3(x.data_ptr(), weight.data_ptr(), ptr[0], ptr[1], ptr[2], float(slope), out.data_ptr(),
+                              B, CI, CO, D, H, W, stride, L.stream_ptr()), "conv3d_k3")
+    return out
+
+
+def deconv3d_k4s2(x: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Tensor] = None,
+                  shift: Optional[torch.Tensor] = None, slope: float = 1.0) -> torch.Tensor:
+    """ConvTranspose3d(kernel 4, stride 2, padding 1, no bias) + ``leaky(acc * scale + shift, slope)``:
+    x (B,CI,D,H,W), weight (CI,CO,4,4,4) -> (B,CO,2D,2H,2W) (reference hourglass conv*_up, igev_stereo.py:42-49)."""
+    lib = L.load()
+    L.require_device(x)
+    B, CI, D, H, W = x.shape
+    CO = weight.shape[1]
+    assert tuple(weight.shape) == (CI, CO, 4, 4, 4) and x.dtype == torch.float32
+    x, weight = x.contiguous(), weight.contiguous().float()
+    out = torch.empty(B, CO, 2 * D, 2 * H, 2 * W, device=x.device, dtype=torch.float32)
+    keep, ptr = _opt_ptrs(scale, shift)
+    L.check(lib.dkt_deconv3d_k4s2(x.data_ptr(), weight.data_ptr(), ptr[0], ptr[1], float(slope), out.data_ptr(),
+                                  B, CI, CO, D, H, W, L.stream_ptr()), "deconv3d_k4s2")
+    return out
+
+
+def conv3d_k1(x0: torch.Tensor, x1: Optional[torch.Tensor], weight: torch.Tensor, scale: Optional[torch.Tensor] = None,
+              shift: Optional[torch.Tensor] = None, slope: float = 1.0, att: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """1x1x1 Conv3d over cat(x0, x1) (x1 may be None) with the epilogue of ``conv3d_k3``: weight (CO, C0+C1[,1,1,1])."""
+    lib = L.load()
+    L.require_device(x0)
+    B, C0, D, H, W = x0.shape
+    C1 = 0 if x1 is None else x1.shape[1]
+    CO = weight.shape[0]
+    weight = weight.reshape(CO, -1).contiguous().float()
+    assert weight.shape[1] == C0 + C1 and x0.dtype == torch.float32
+    x0 = x0.contiguous()
+    if x1 is not None:
+        assert x1.shape == (B, C1, D, H, W) and x1.dtype == torch.float32
+        x1 = x1.contiguous()
+    out = torch.empty(B, CO, D, H, W, device=x0.device, dtype=torch.float32)
+    keep, ptr = _opt_ptrs(scale, shift, att)
+    L.check(lib.dkt_conv3d_k1(x0.data_ptr(), C0, x1.data_ptr() if x1 is not None else None, C1, weight.data_ptr(),
+                              ptr[0], ptr[1], ptr[2], float(slope), out.data_ptr(), B, CO, D, H, W, L.stream_ptr()),
+            "conv3d_k1")
+    return out
+
+
 def softargmin(logits: torch.Tensor) -> torch.Tensor:
     """(B,D,H,W) fp32 -> (B,1,H,W) = sum_d d * softmax_d (reference submodule.py:220-224 after F.softmax)."""
     lib = L.load()

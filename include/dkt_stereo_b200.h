@@ -179,18 +179,33 @@ int dkt_geo_lookup_enc(const float* geo0, const float* geo1, const float* init0,
  *   (reference meta_arch/igev_stereo/submodule.py:152-170; call site igev_stereo.py:169):
  *   left, right (B,C,H,W) -> vol (B,groups,D,H,W), vol[b,g,d,y,x] = mean over the group's C/groups channels of
  *   left[b,c,y,x] * right[b,c,y,x-d], 0 where x < d.  C/groups <= 16.
- * dkt_conv3d_c8: 3x3x3 Conv3d (8 input channels, CO = 8 or 1 outputs, stride 1, padding 1, no bias) with the epilogue
+ * dkt_conv3d_k3: 3x3x3 Conv3d (padding 1, stride 1 or 2, no bias) with the epilogue
  *   v = acc * scale[co] + shift[co]; v = v > 0 ? v : slope * v; v *= sigmoid(att[b,co,y,x])  (scale/shift/att may be
- *   NULL; slope = 1 for no activation).  in (B,8,D,H,W), weight [CO][8][3][3][3] (PyTorch layout), att (B,CO,H,W),
- *   out (B,CO,D,H,W), in != out.  Replaces corr_stem = BasicConv(8,8,is_3d) with its eval-mode BatchNorm3d folded to
- *   scale/shift + LeakyReLU(0.01) (submodule.py:10-36) followed by FeatureAtt's broadcast product (submodule.py:227-240;
- *   igev_stereo.py:130-131,170-171), and `classifier` = nn.Conv3d(8,1,3,1,1,bias=False) (igev_stereo.py:133,175).
+ *   NULL; slope = 1 for no activation).  in (B,CI,D,H,W), weight [CO][CI][3][3][3] (PyTorch layout), out
+ *   (B,CO,Do,Ho,Wo) with Xo = (X-1)/stride + 1, att (B,CO,Ho,Wo), in != out; CI even.  Replaces BasicConv(is_3d) with
+ *   its eval-mode BatchNorm3d folded to scale/shift + LeakyReLU(0.01) (submodule.py:10-36) followed by FeatureAtt's
+ *   broadcast product (submodule.py:227-240): corr_stem + corr_feature_att (igev_stereo.py:130-131,170-171), the
+ *   3x3x3 layers of `hourglass` (igev_stereo.py:22-89) and `classifier` = nn.Conv3d(8,1,3,1,1) (igev_stereo.py:133,175).
+ * dkt_conv3d_c8: dkt_conv3d_k3 with CI = 8, stride 1, CO = 8 or 1.
+ * dkt_deconv3d_k4s2: ConvTranspose3d(kernel 4, stride 2, padding 1, no bias) + scale/shift + leaky: in (B,CI,D,H,W),
+ *   weight [CI][CO][4][4][4], out (B,CO,2D,2H,2W); CI % 4 == 0.  hourglass conv3_up / conv2_up / conv1_up
+ *   (igev_stereo.py:42-49).
+ * dkt_conv3d_k1: 1x1x1 Conv3d over the channel concatenation [in0 (C0) | in1 (C1)] (in1 may be NULL with C1 = 0),
+ *   weight [CO][C0+C1], same epilogue as dkt_conv3d_k3: torch.cat + the first layer of hourglass agg_0 / agg_1
+ *   (igev_stereo.py:51-58,76-77,81-82); C0 + C1 <= 128.
  * dkt_softargmin: logits (B,D,H,W) -> disp (B,1,H,W) = sum_d d * softmax_d(logits): F.softmax(dim=1) followed by
  *   disparity_regression (submodule.py:220-224; igev_stereo.py:175-176). */
 int dkt_gwc_volume(const float* left, const float* right, float* vol, int B, int C, int groups, int D, int H, int W,
                    void* stream);
+int dkt_conv3d_k3(const float* in, const float* weight, const float* scale, const float* shift, const float* att,
+                  float slope, float* out, int B, int CI, int CO, int D, int H, int W, int stride, void* stream);
 int dkt_conv3d_c8(const float* in, const float* weight, const float* scale, const float* shift, const float* att,
                   float slope, float* out, int B, int CO, int D, int H, int W, void* stream);
+int dkt_deconv3d_k4s2(const float* in, const float* weight, const float* scale, const float* shift, float slope,
+                      float* out, int B, int CI, int CO, int D, int H, int W, void* stream);
+int dkt_conv3d_k1(const float* in0, int C0, const float* in1, int C1, const float* weight, const float* scale,
+                  const float* shift, const float* att, float slope, float* out, int B, int CO, int D, int H, int W,
+                  void* stream);
 int dkt_softargmin(const float* logits, float* disp, int B, int D, int H, int W, void* stream);
 
 /* ---- K3: convolutions of the update block with fused epilogues ------------------------------

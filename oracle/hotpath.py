@@ -418,3 +418,44 @@ def softargmin(logits: Tensor) -> Tensor:
     D = logits.shape[1]
     values = torch.arange(0, D, dtype=logits.dtype).view(1, D, 1, 1)
     return torch.sum(prob * values, 1, keepdim=True)
+
+
+def _basic_conv3d(sd: SD, pre: str, x: Tensor, stride: int = 1, padding: int = 1, deconv: bool = False,
+                  bn: bool = True, relu: bool = True) -> Tensor:
+    """BasicConv(is_3d=True) in eval mode: conv | deconv (no bias) -> BatchNorm3d(running stats) -> LeakyReLU(0.01)
+    (reference meta_arch/igev_stereo/submodule.py:10-36)."""
+    w = sd[pre + ".conv.weight"]
+    y = F.conv_transpose3d(x, w, None, stride=stride, padding=padding) if deconv else F.conv3d(x, w, None, stride=stride, padding=padding)
+    if bn:
+        y = F.batch_norm(y, sd[pre + ".bn.running_mean"], sd[pre + ".bn.running_var"], sd[pre + ".bn.weight"],
+                         sd[pre + ".bn.bias"], False, 0.0, 1e-5)
+    return F.leaky_relu(y, 0.01) if relu else y
+
+
+def _feature_att(sd: SD, pre: str, cv: Tensor, feat: Tensor) -> Tensor:
+    """FeatureAtt: cv * sigmoid(conv1x1(BasicConv1x1(feat))) broadcast over disparity (submodule.py:227-240)."""
+    y = F.conv2d(feat, sd[pre + ".feat_att.0.conv.weight"])
+    y = F.batch_norm(y, sd[pre + ".feat_att.0.bn.running_mean"], sd[pre + ".feat_att.0.bn.running_var"],
+                     sd[pre + ".feat_att.0.bn.weight"], sd[pre + ".feat_att.0.bn.bias"], False, 0.0, 1e-5)
+    y = F.conv2d(F.leaky_relu(y, 0.01), sd[pre + ".feat_att.1.weight"], sd[pre + ".feat_att.1.bias"])
+    return torch.sigmoid(y.unsqueeze(2)) * cv
+
+
+def hourglass(sd: SD, pre: str, x: Tensor, feats: Sequence[Tensor]) -> Tensor:
+    """The 3-D hourglass `cost_agg` (reference meta_arch/igev_stereo/igev_stereo.py:22-89): x (B,8,D,H,W),
+    feats[1..3] the 1/8, 1/16, 1/32 feature maps (64 / 192 / 160 channels)."""
+    def down(name, v):
+        return _basic_conv3d(sd, f"{pre}.{name}.1", _basic_conv3d(sd, f"{pre}.{name}.0", v, stride=2))
+
+    def agg(name, v):
+        v = _basic_conv3d(sd, f"{pre}.{name}.0", v, padding=0)
+        return _basic_conv3d(sd, f"{pre}.{name}.2", _basic_conv3d(sd, f"{pre}.{name}.1", v))
+
+    c1 = _feature_att(sd, pre + ".feature_att_8", down("conv1", x), feats[1])
+    c2 = _feature_att(sd, pre + ".feature_att_16", down("conv2", c1), feats[2])
+    c3 = _feature_att(sd, pre + ".feature_att_32", down("conv3", c2), feats[3])
+    u3 = _basic_conv3d(sd, pre + ".conv3_up", c3, stride=2, deconv=True)
+    c2 = _feature_att(sd, pre + ".feature_att_up_16", agg("agg_0", torch.cat((u3, c2), 1)), feats[2])
+    u2 = _basic_conv3d(sd, pre + ".conv2_up", c2, stride=2, deconv=True)
+    c1 = _feature_att(sd, pre + ".feature_att_up_8", agg("agg_1", torch.cat((u2, c1), 1)), feats[1])
+    return _basic_conv3d(sd, pre + ".conv1_up", c1, stride=2, deconv=True, bn=False, relu=False)

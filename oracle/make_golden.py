@@ -251,6 +251,33 @@ def golden_igev_volume(m, B=1, C=96, H=9, W=37, D=20, tag="igev_volume"):
          vol=vol, cls_w=classifier.weight, logits=logits, disp=disp, meta=np.array([B, C, H, W, D]))
 
 
+def golden_igev_hourglass(m, B=1, D=16, H=16, W=40, tag="igev_hourglass"):
+    """The REAL reference `hourglass(8)` (meta_arch/igev_stereo/igev_stereo.py:22-89) in eval mode with seeded random
+    parameters and non-trivial BatchNorm statistics on a small volume; stores inputs, the state dict and the output."""
+    _timm_stub()
+    igev = importlib.import_module("meta_arch.igev_stereo.igev_stereo")
+    g = torch.Generator().manual_seed(78)
+    hg = igev.hourglass(8).eval()
+    with torch.no_grad():
+        for name, prm in hg.named_parameters():
+            fan = prm[0].numel() if prm.dim() > 1 else 1
+            prm.copy_(torch.randn(prm.shape, generator=g) * (1.5 / fan ** 0.5 if prm.dim() > 1 else 0.3))
+            if name.endswith("bn.weight"):
+                prm.add_(1.0)
+        for name, buf in hg.named_buffers():
+            if name.endswith("running_mean"):
+                buf.copy_(torch.randn(buf.shape, generator=g) * 0.2)
+            elif name.endswith("running_var"):
+                buf.copy_(torch.rand(buf.shape, generator=g) + 0.5)
+        x = torch.randn(B, 8, D, H, W, generator=g)
+        feats = [torch.zeros(1), torch.randn(B, 64, H // 2, W // 2, generator=g), torch.randn(B, 192, H // 4, W // 4, generator=g),
+                 torch.randn(B, 160, H // 8, W // 8, generator=g)]
+        out = hg(x, feats)
+    sd = {k: v for k, v in hg.state_dict().items() if not k.endswith("num_batches_tracked")}
+    save(tag, x=x, feat1=feats[1], feat2=feats[2], feat3=feats[3], out=out, keys=np.array(sorted(sd)),
+         **{"sd__" + k.replace(".", "__"): sd[k] for k in sd})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -269,6 +296,7 @@ def main():
         "igev_small": lambda: golden_igev_forward(m),
         "igev_mid": lambda: golden_igev_forward(m, 96, 160, 8, "igev_fwd_mid", 1),
         "igev_volume": lambda: golden_igev_volume(m),
+        "igev_hourglass": lambda: golden_igev_hourglass(m),
     }
     for k, fn in jobs.items():
         if not args.only or k in args.only.split(","):

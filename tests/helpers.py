@@ -32,3 +32,8 @@ def golden_shapes(g):
 def stats(a, b):
     d = (a.double() - b.double()).abs()
     return float(d.mean()), float(d.max())
+
+
+def golden_state_dict(g, prefix="sd__"):
+    """state dict stored in a golden file as sd__<key with '.' -> '__'> arrays."""
+    return {k[len(prefix):].replace("__", "."): v for k, v in g.items() if k.startswith(prefix)}

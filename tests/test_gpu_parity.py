@@ -12,7 +12,7 @@ from argparse import Namespace
 import pytest
 import torch
 
-from helpers import load_golden, golden_shapes, stats, RAFT_CFG, IGEV_CFG
+from helpers import load_golden, golden_shapes, golden_state_dict, stats, RAFT_CFG, IGEV_CFG
 
 pytestmark = pytest.mark.gpu
 
@@ -851,3 +851,80 @@ def test_igev_native_volume_stage_end_to_end(monkeypatch):
     mean, mx = stats(ua.cpu(), ub.cpu())
     print(f"[parity] igev native volume stage, final disparity: mean-abs {mean:.3e} px, max-abs {mx:.3e} px")
     assert mean <= 1e-3, (mean, mx)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 9, 7, 45, 1), (1, 16, 32, 12, 10, 70, 2), (1, 32, 48, 6, 9, 33, 2),
+                                   (1, 8, 16, 11, 9, 37, 2), (1, 48, 48, 5, 6, 30, 1), (1, 6, 8, 4, 5, 20, 1)])
+def test_conv3d_k3_vs_torch(shape):
+    """Every channel blocking (16 / 8 per thread, partial channel blocks), both strides, ragged tiles; fp32 reference =
+    torch conv3d on CPU (the oracle's primitive)."""
+    from dkt_stereo_b200 import ops
+    from oracle import hotpath as O
+    B, CI, CO, D, H, W, stride = shape
+    g = torch.Generator().manual_seed(CI * CO + D)
+    x = torch.randn(B, CI, D, H, W, generator=g)
+    w = torch.randn(CO, CI, 3, 3, 3, generator=g) / (CI * 27) ** 0.5
+    scale, shift = torch.randn(CO, generator=g), torch.randn(CO, generator=g)
+    ref = torch.nn.functional.conv3d(x, w, None, stride=stride, padding=1)
+    att = torch.randn(B, CO, ref.shape[3], ref.shape[4], generator=g)
+    ref = torch.nn.functional.leaky_relu(ref * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1), 0.01) * torch.sigmoid(att.unsqueeze(2))
+    d = dev()
+    got = ops.conv3d_k3(x.to(d), w.to(d), scale.to(d), shift.to(d), 0.01, att.to(d), stride)
+    assert got.shape == ref.shape
+    assert stats(got.cpu(), ref)[1] < 3e-5, stats(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 8, 5, 6, 37), (1, 48, 32, 3, 9, 15), (1, 32, 16, 6, 4, 32), (1, 8, 6, 2, 3, 5)])
+def test_deconv3d_k4s2_vs_torch(shape):
+    from dkt_stereo_b200 import ops
+    B, CI, CO, D, H, W = shape
+    g = torch.Generator().manual_seed(CI + CO + W)
+    x = torch.randn(B, CI, D, H, W, generator=g)
+    w = torch.randn(CI, CO, 4, 4, 4, generator=g) / (CI * 8) ** 0.5
+    scale, shift = torch.randn(CO, generator=g), torch.randn(CO, generator=g)
+    ref = torch.nn.functional.conv_transpose3d(x, w, None, stride=2, padding=1)
+    d = dev()
+    got = ops.deconv3d_k4s2(x.to(d), w.to(d))
+    assert got.shape == ref.shape == (B, CO, 2 * D, 2 * H, 2 * W)
+    assert stats(got.cpu(), ref)[1] < 3e-5, stats(got.cpu(), ref)
+    ref2 = torch.nn.functional.leaky_relu(ref * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1), 0.01)
+    got2 = ops.deconv3d_k4s2(x.to(d), w.to(d), scale.to(d), shift.to(d), 0.01)
+    assert stats(got2.cpu(), ref2)[1] < 3e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 32, 5, 6, 37), (1, 16, 16, 16, 4, 9, 70), (1, 24, 0, 20, 3, 5, 11)])
+def test_conv3d_k1_concat_vs_torch(shape):
+    from dkt_stereo_b200 import ops
+    B, C0, C1, CO, D, H, W = shape
+    g = torch.Generator().manual_seed(C0 + CO)
+    a = torch.randn(B, C0, D, H, W, generator=g)
+    b = torch.randn(B, C1, D, H, W, generator=g) if C1 else None
+    w = torch.randn(CO, C0 + C1, 1, 1, 1, generator=g) / (C0 + C1) ** 0.5
+    scale, shift = torch.randn(CO, generator=g), torch.randn(CO, generator=g)
+    xin = torch.cat((a, b), 1) if C1 else a
+    ref = torch.nn.functional.leaky_relu(torch.nn.functional.conv3d(xin, w) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1), 0.01)
+    d = dev()
+    got = ops.conv3d_k1(a.to(d), b.to(d) if C1 else None, w.to(d), scale.to(d), shift.to(d), 0.01)
+    assert stats(got.cpu(), ref)[1] < 2e-5, stats(got.cpu(), ref)
+
+
+def test_igev_hourglass_golden():
+    """Hourglass.forward_native (libdkt 3-D kernels) against the REAL reference hourglass's output
+    (tests/golden/igev_hourglass.npz): same state dict, fp32 round-off only."""
+    from dkt_stereo_b200.igev_modules import Hourglass
+    g = load_golden("igev_hourglass")
+    hg = Hourglass(8).eval()
+    hg.load_state_dict(golden_state_dict(g), strict=True)
+    hg = hg.to(dev())
+    x = g["x"].to(dev())
+    feats = [None, g["feat1"].to(dev()), g["feat2"].to(dev()), g["feat3"].to(dev())]
+    assert hg.native_ok(x)
+    from dkt_stereo_b200.raft_stereo import _fp32_math
+    with torch.no_grad(), _fp32_math(True):    # the 2-D attention convs stay in PyTorch: no TF32, as in IGEVStereo.prepare
+        out = hg.forward_native(x, feats)
+        out_t = hg(x, feats)
+    scale = float(g["out"].abs().max()) + 1.0
+    mean, mx = stats(out.cpu(), g["out"])
+    print(f"[parity] igev hourglass native vs reference: mean-abs {mean:.3e}, max-abs {mx:.3e} (|out| max {scale - 1:.2f})")
+    assert mx < 3e-5 * scale, (mean, mx)
+    assert stats(out_t.cpu(), g["out"])[1] < 3e-5 * scale

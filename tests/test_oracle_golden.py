@@ -4,7 +4,7 @@ import torch
 
 from oracle import hotpath as O
 from dkt_stereo_b200.synthetic import synthetic_state_dict, synthetic_pair
-from helpers import load_golden, golden_shapes, stats, RAFT_CFG, IGEV_CFG
+from helpers import load_golden, golden_shapes, golden_state_dict, stats, RAFT_CFG, IGEV_CFG
 
 
 def test_corr1d_build_and_lookup():
@@ -115,3 +115,20 @@ def test_igev_volume_stage():
     disp = O.softargmin(g["logits"])
     assert disp.shape == g["disp"].shape == (B, 1, H, W)
     assert stats(disp, g["disp"])[1] < 2e-5
+
+
+def test_igev_hourglass():
+    """The oracle's 3-D hourglass against the real reference module's output (tests/golden/igev_hourglass.npz)."""
+    g = load_golden("igev_hourglass")
+    sd = {"hg." + k: v for k, v in golden_state_dict(g).items()}
+    out = O.hourglass(sd, "hg", g["x"], [None, g["feat1"], g["feat2"], g["feat3"]])
+    assert out.shape == g["out"].shape
+    tol = 2e-5 * (float(g["out"].abs().max()) + 1.0)
+    assert stats(out, g["out"])[1] < tol
+    # the engine's module carries the reference's parameter names (strict load) and computes the same function
+    from dkt_stereo_b200.igev_modules import Hourglass
+    hg = Hourglass(8).eval()
+    hg.load_state_dict(golden_state_dict(g), strict=True)
+    with torch.no_grad():
+        mine = hg(g["x"], [None, g["feat1"], g["feat2"], g["feat3"]])
+    assert stats(mine, g["out"])[1] < tol

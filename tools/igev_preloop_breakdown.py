@@ -42,7 +42,10 @@ def run():
             g = build_gwc_volume(ml, mr, D, 8); mark("build_gwc_volume")
             vol = m.corr_stem(g); mark("corr_stem (3D conv)")
             vol = m.corr_feature_att(vol, fl[0]); mark("feature_att")
-        gev = m.cost_agg(vol, fl); mark("hourglass (3D)")
+        if NATIVE and m.cost_agg.native_ok(vol):
+            gev = m.cost_agg.forward_native(vol, fl); mark("hourglass (3D, dkt kernels)")
+        else:
+            gev = m.cost_agg(vol, fl); mark("hourglass (3D)")
         if NATIVE:
             lg = ops.conv3d_c8(gev, m.classifier.weight); mark("dkt_conv3d_c8 classifier")
             d0 = ops.softargmin(lg.squeeze(1)); mark("dkt_softargmin")
