@@ -104,7 +104,8 @@ struct K3Cfg {
     static constexpr int WCH = 27 * CO_T;                                 // weights per input channel
     static constexpr int STAGE = CH * (TILE + WCH);
     static constexpr int NV = (DS - 1) * STRIDE + 3;                      // inputs along d per thread
-    static constexpr size_t SMEM = 2 * (size_t)STAGE * sizeof(float);
+    static constexpr bool TABLE = (STRIDE == 1);                          // per-element fill table (see prefetch)
+    static constexpr size_t SMEM = (2 * (size_t)STAGE + (TABLE ? TILE : 0)) * sizeof(float);
 };
 
 template <int CO_T, int DS, int STRIDE>
@@ -123,10 +124,37 @@ conv3d_k3_kernel(const float* __restrict__ in, const float* __restrict__ wgt, co
     const int64_t iplane = (int64_t)Hi * Wi, oplane = (int64_t)Ho * Wo;
     const int xl = tid % C3_XT, yl = (tid / C3_XT) % C3_YT, ds = tid / (C3_XT * C3_YT);
 
+    // fill table: element e of a channel's tile -> offset inside that channel's volume, -1 = padding.  The positions a
+    // thread copies are the same for every input channel, so the index arithmetic (57 instructions per cp.async in
+    // the first version, profiles/r03d) is done once per CTA instead of once per element and chunk.
+    int* tab = reinterpret_cast<int*>(c3_smem + 2 * Cfg::STAGE);
+    if (Cfg::TABLE) {
+        for (int e = tid; e < Cfg::TILE; e += C3_THREADS) {
+            const int dd = e / (Cfg::YIN * Cfg::XIN);
+            const int rem = e - dd * (Cfg::YIN * Cfg::XIN);
+            const int yy = rem / Cfg::XIN, xx = rem - yy * Cfg::XIN;
+            const int d = d0 - 1 + dd, y = y0 - 1 + yy, x = x0 - 1 + xx;
+            const bool ok = dd < Cfg::DIN && d >= 0 && d < Di && y >= 0 && y < Hi && x >= 0 && x < Wi;
+            tab[e] = ok ? (int)(d * iplane + (int64_t)y * Wi + x) : -1;
+        }
+        __syncthreads();
+    }
+
     auto prefetch = [&](int chunk, int buf) {
         float* sI = c3_smem + buf * Cfg::STAGE;
         float* sW = sI + Cfg::CH * Cfg::TILE;
         const int ci0 = chunk * Cfg::CH;
+        if (Cfg::TABLE) {
+            for (int cc = 0; cc < Cfg::CH; ++cc) {
+                const float* base = in + ((int64_t)b * CI + ci0 + cc) * Di * iplane;
+                float* dst = sI + cc * Cfg::TILE;
+#pragma unroll 4
+                for (int e = tid; e < Cfg::TILE; e += C3_THREADS) {
+                    const int off = tab[e];
+                    cp_async4(dst + e, base + max(off, 0), off >= 0);
+                }
+            }
+        } else
         for (int r = warp; r < Cfg::CH * Cfg::DIN * Cfg::YIN; r += C3_THREADS / 32) {
             const int cc = r / (Cfg::DIN * Cfg::YIN);
             const int rem = r - cc * (Cfg::DIN * Cfg::YIN);
@@ -234,13 +262,13 @@ constexpr int DC_MD = 2, DC_CO = 4, DC_CH = 4;
 constexpr int DC_MDT = DC_MD * C3_NSTRIP;
 constexpr int DC_XIN = C3_XT + 2, DC_YIN = C3_YT + 2, DC_DIN = DC_MDT + 2;
 constexpr int DC_TILE = DC_DIN * DC_YIN * DC_XIN, DC_WCH = 64 * DC_CO, DC_STAGE = DC_CH * (DC_TILE + DC_WCH);
-constexpr size_t DC_SMEM = 2 * (size_t)DC_STAGE * sizeof(float);
+constexpr size_t DC_SMEM = (2 * (size_t)DC_STAGE + DC_TILE) * sizeof(float);      // two stages + the fill table
 
 __global__ void __launch_bounds__(C3_THREADS, 2)
 deconv3d_k4s2_kernel(const float* __restrict__ in, const float* __restrict__ wgt, const Conv3dEpi epi,
                      float* __restrict__ out, int CI, int CO, int Di, int Hi, int Wi, int dtiles, int coblocks) {
     extern __shared__ __align__(16) float c3_smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     int z = blockIdx.z;
     const int cb = z % coblocks; z /= coblocks;
     const int dt = z % dtiles;
@@ -251,22 +279,28 @@ deconv3d_k4s2_kernel(const float* __restrict__ in, const float* __restrict__ wgt
     const int64_t oplane = (int64_t)Ho * Wo;
     const int xl = tid % C3_XT, yl = (tid / C3_XT) % C3_YT, ds = tid / (C3_XT * C3_YT);
 
+    int* tab = reinterpret_cast<int*>(c3_smem + 2 * DC_STAGE);       // fill table, as in conv3d_k3_kernel
+    for (int e = tid; e < DC_TILE; e += C3_THREADS) {
+        const int dd = e / (DC_YIN * DC_XIN);
+        const int rem = e - dd * (DC_YIN * DC_XIN);
+        const int yy = rem / DC_XIN, xx = rem - yy * DC_XIN;
+        const int d = d0 - 1 + dd, y = y0 - 1 + yy, x = x0 - 1 + xx;
+        const bool ok = d >= 0 && d < Di && y >= 0 && y < Hi && x >= 0 && x < Wi;
+        tab[e] = ok ? (int)(d * iplane + (int64_t)y * Wi + x) : -1;
+    }
+    __syncthreads();
+
     auto prefetch = [&](int chunk, int buf) {
         float* sI = c3_smem + buf * DC_STAGE;
         float* sW = sI + DC_CH * DC_TILE;
         const int ci0 = chunk * DC_CH;
-        for (int r = warp; r < DC_CH * DC_DIN * DC_YIN; r += C3_THREADS / 32) {
-            const int cc = r / (DC_DIN * DC_YIN);
-            const int rem = r - cc * (DC_DIN * DC_YIN);
-            const int dd = rem / DC_YIN, yy = rem - dd * DC_YIN;
-            const int d = d0 - 1 + dd, y = y0 - 1 + yy;
-            const bool rowok = d >= 0 && d < Di && y >= 0 && y < Hi;
-            const float* src = rowok ? in + (((int64_t)b * CI + ci0 + cc) * Di + d) * iplane + (int64_t)y * Wi : in;
-            float* dst = sI + cc * DC_TILE + (dd * DC_YIN + yy) * DC_XIN;
-            for (int xx = lane; xx < DC_XIN; xx += 32) {
-                const int x = x0 - 1 + xx;
-                const bool ok = rowok && x >= 0 && x < Wi;
-                cp_async4(dst + xx, ok ? src + x : in, ok);
+        for (int cc = 0; cc < DC_CH; ++cc) {
+            const float* base = in + ((int64_t)b * CI + ci0 + cc) * Di * iplane;
+            float* dst = sI + cc * DC_TILE;
+#pragma unroll 4
+            for (int e = tid; e < DC_TILE; e += C3_THREADS) {
+                const int off = tab[e];
+                cp_async4(dst + e, base + max(off, 0), off >= 0);
             }
         }
         for (int i = tid; i < DC_CH * DC_WCH; i += C3_THREADS) {
