@@ -8,3 +8,5 @@ timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference_arm.json 2> gpurun_out/${TAG}_bench_ref.err; echo "ref rc=$?"; cut -c1-400 gpurun_out/${TAG}_bench_reference_arm.json
 timeout 400 python bench.py --model igev --no-cpu-baseline > gpurun_out/${TAG}_bench_igev.json 2> gpurun_out/${TAG}_bench_igev.err; echo "igev rc=$?"; cut -c1-300 gpurun_out/${TAG}_bench_igev.json
 bash tools/profile_launches.sh ${TAG}; echo "launches rc=$?"
+NCONV=100 FULL_SKIP=65 FULL_COUNT=2 bash tools/profile_convs.sh ${TAG} > /dev/null 2>&1; echo "convs rc=$?"
+ls -la gpurun_out | head -30; du -sh gpurun_out
