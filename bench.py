@@ -483,7 +483,7 @@ def run_b200_igev(args):
         "e2e": {"value": world * Bg * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": 2 * im1_h.numel() * 4, "d2h_bytes_per_step": Bg * H * W * 4},
         "gpu_launches": launches_per_step * args.steps,
-        "split_ms": {"pre_loop_pytorch": pre_ms, "hot_path_kernels": hot_ms},
+        "split_ms": {"pre_loop (PyTorch MobileNetV2 / stems + libdkt volume stage + context encoder)": pre_ms, "hot_path_kernels": hot_ms},
         "roofline": {"kernel": "geo_lookup_kernel<4, ENC> (Combined_Geo_Encoding_Volume lookup + convc1)", "bound": "hbm",
                      "achieved": lk_bytes / (lk_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": lk_bytes / (lk_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": lk_ms,
