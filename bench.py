@@ -164,7 +164,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -383,7 +383,7 @@ def run_b200(args):
         "breakdown_ms_per_step": {k: round(v[1], 3) for k, v in top},
         "breakdown_total_ms": round(total_prof, 3),
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def run_b200_igev(args):
@@ -490,7 +490,26 @@ def run_b200_igev(args):
                      "bytes_per_launch": lk_bytes, "peak_source": peaks["source"]},
         "cpu_baseline": None, "clocks": clocks,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Keep the process's real stdout for the ONE JSON line and point fd 1 at stderr for everything else: libraries
+    write banners to stdout (NCCL prints its version line there when NCCL_DEBUG is set in the environment)."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(out: dict) -> None:
+    stream = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    stream.write(json.dumps(out) + "\n")
+    stream.flush()
 
 
 def main():
@@ -511,6 +530,7 @@ def main():
     ap.add_argument("--ncu-step", action="store_true",
                     help="warm up, then run ONE step inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     elif args.model == "igev":
