@@ -95,14 +95,19 @@ class IGEVStereo(nn.Module):
         image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
         image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
         with _fp32_math(self.extractor_fp32), torch.autocast("cuda", enabled=bool(getattr(args, "mixed_precision", False))):
-            fl, fr = self.feature(image1), self.feature(image2)
-            stem_2x = self.stem_2(image1)
-            stem_4x = self.stem_4(stem_2x)
-            stem_4y = self.stem_4(self.stem_2(image2))
-            fl[0] = torch.cat((fl[0], stem_4x), 1)
-            fr[0] = torch.cat((fr[0], stem_4y), 1)
-            match_left = self.desc(self.conv(fl[0]))
-            match_right = self.desc(self.conv(fr[0]))
+            # left and right images go through the feature side as ONE batch (reference igev_stereo.py:154-168 runs the two
+            # halves separately): BatchNorm is in eval mode and InstanceNorm is per sample, so the result is the same; the
+            # 1/16 and 1/32-resolution layers are launch-bound at batch 8 and half as many launches are issued
+            B = image1.shape[0]
+            both = torch.cat((image1, image2), 0)
+            feats = self.feature(both)
+            stem_2 = self.stem_2(both)
+            stem_4 = self.stem_4(stem_2)
+            stem_2x = stem_2[:B]
+            feats[0] = torch.cat((feats[0], stem_4), 1)
+            match = self.desc(self.conv(feats[0]))
+            match_left, match_right = match[:B], match[B:]
+            fl = [f[:B] for f in feats]
             D = args.max_disp // 4
             native_vol = (self.native_volume and image1.is_cuda and match_left.dtype == torch.float32
                           and not self.corr_stem.bn.training)
