@@ -1,11 +1,13 @@
-// IGEV-Stereo pre-loop volume kernels: the group-wise correlation volume, the 8-channel 3x3x3
-// 3-D convolutions on it (corr_stem + BatchNorm + LeakyReLU + feature attention; classifier) and the soft-argmin
-// initial disparity.  Reference: meta_arch/igev_stereo/submodule.py:152-170 (build_gwc_volume), :10-36 (BasicConv),
-// :227-240 (FeatureAtt), :220-224 (disparity_regression); call sites meta_arch/igev_stereo/igev_stereo.py:169-176.
+// IGEV-Stereo pre-loop volume kernels: the group-wise correlation volume, the 3-D convolutions on
+// it (corr_stem + BatchNorm + LeakyReLU + feature attention; the 3-D hourglass; classifier) and the soft-argmin initial
+// disparity.  Reference: meta_arch/igev_stereo/submodule.py:152-170 (build_gwc_volume), :10-36 (BasicConv), :227-240
+// (FeatureAtt), :220-224 (disparity_regression); meta_arch/igev_stereo/igev_stereo.py:22-89 (hourglass), call sites
+// igev_stereo.py:169-176.
 //
-// All three are exact-fp32 SIMT kernels: the volumes are 401 MB at cfg3, the arithmetic intensity of an 8 -> 8 channel
-// 3x3x3 stencil is 432 flop per voxel-channel pair read once, i.e. FP32-FMA bound (43 GFLOP, 0.8 ms at the FMA peak)
-// with channel counts far too small for a 128-wide MMA tile; the volume build and the soft-argmin are one HBM pass.
+// All of them are exact-fp32 SIMT kernels on NCDHW volumes (PyTorch modules produce the inputs and consume the outputs):
+// the volumes are 401 MB at cfg3, an 8 -> 8 channel 3x3x3 stencil is 432 flop per voxel and input channel read once,
+// i.e. FP32-FMA bound (43 GFLOP, 0.8 ms at the FMA peak), and channel counts of 8..48 are too small for a 128-wide MMA
+// tile; the volume build and the soft-argmin are one HBM pass.  ncu launch tables: profiles/r03e_igev_preloop_launches.txt.
 #include "common.cuh"
 
 namespace dkt {
