@@ -158,6 +158,7 @@ struct LookupOut {
     const float* enc_w;                          // ENC: [C][64] fp32 (k-major), bias [64]
     const float* enc_b;
     dkt_tensor enc_out;                          // ENC: 64-channel NHWC slice
+    int dbg;                                     // profiling only (DKT_LOOKUP_PHASE): bit 0 skips the gather, bit 1 the encode
 };
 
 // phase 2, plain: tile (row stride TS) -> global
@@ -273,7 +274,7 @@ corr1d_lookup_kernel(ConstPyrPtrs pyr, int levels, float* __restrict__ coords_x,
         }
         if (levels == 0) continue;
         __syncthreads();
-        {
+        if (!(ENC && (o.dbg & 1))) {
             const int px = threadIdx.x >> 2, l = threadIdx.x & 3;
             if (px < npix && l < levels) {
                 float taps[T];
@@ -286,7 +287,7 @@ corr1d_lookup_kernel(ConstPyrPtrs pyr, int levels, float* __restrict__ coords_x,
             }
         }
         __syncthreads();
-        if (ENC) lookup_encode_tile(tile, C, ws, o, p0, npix);
+        if (ENC) { if (!(o.dbg & 2)) lookup_encode_tile(tile, C, ws, o, p0, npix); }
         else lookup_store_tile(tile, TS, C, o, p0, npix, HW);
         __syncthreads();                                       // tile and s_x are reused by the next chunk
     }
@@ -337,7 +338,7 @@ geo_lookup_kernel(GeoPtrs g, float* __restrict__ disp, const float* __restrict__
         const float* const geo1 = g.geo[1];
         const float* const init0 = g.init[0];
         const float* const init1 = g.init[1];
-        for (int it0 = threadIdx.x; it0 < npix * G; it0 += blockDim.x * GU) {
+        for (int it0 = threadIdx.x; it0 < ((ENC && (o.dbg & 1)) ? 0 : npix * G); it0 += blockDim.x * GU) {
             float v[GU][2 * R + 2], av[GU];
 #pragma unroll
             for (int u = 0; u < GU; ++u) {
@@ -371,7 +372,7 @@ geo_lookup_kernel(GeoPtrs g, float* __restrict__ disp, const float* __restrict__
             }
         }
         __syncthreads();
-        if (ENC) lookup_encode_tile(tile, C, ws, o, p0, npix);
+        if (ENC) { if (!(o.dbg & 2)) lookup_encode_tile(tile, C, ws, o, p0, npix); }
         else lookup_store_tile(tile, TS, C, o, p0, npix, HW);
         __syncthreads();                      // tile and s_d are reused by the next chunk
     }
@@ -454,6 +455,8 @@ static int fill_enc_out(LookupOut& o, const float* enc_w, const float* enc_b, co
     if ((enc_out->C % 4) || (enc_out->c_begin % 4)) return DKT_E_ALIGNMENT;
     if ((reinterpret_cast<uintptr_t>(enc_w) & 15) || (reinterpret_cast<uintptr_t>(enc_b) & 15)) return DKT_E_ALIGNMENT;
     o.enc_w = enc_w; o.enc_b = enc_b; o.enc_out = *enc_out;
+    static const int s_dbg = [] { const char* v = getenv("DKT_LOOKUP_PHASE"); return v ? atoi(v) : 0; }();
+    o.dbg = s_dbg;
     return 0;
 }
 
