@@ -57,6 +57,19 @@ def test_argument_validation_without_gpu():
     assert lib.dkt_corr1d_build_f32(None, None, 0, 0, 0, 0, None, 1, 1, 1, 1, 1, 1, 1.0, None) == -1
     assert lib.dkt_convex_upsample(None, 2, None, None, 1, 1, 1, 4, None) == -1
     assert lib.dkt_conv2d_tc(None, 1, None, None, 3, 64, None, 1, 8, 8, None) == -1
+    # IGEV pre-loop volume kernels: null pointers / bad sizes -> DKT_E_INVALID, unsupported shapes -> DKT_E_UNSUPPORTED
+    assert lib.dkt_gwc_volume(None, None, None, 1, 96, 8, 48, 8, 8, None) == -1
+    assert lib.dkt_gwc_volume(1 << 12, 1 << 13, 1 << 14, 1, 96, 7, 48, 8, 8, None) == -1        # 96 % 7 != 0
+    assert lib.dkt_gwc_volume(1 << 12, 1 << 13, 1 << 14, 1, 256, 8, 48, 8, 8, None) == -2      # 32 channels per group
+    assert lib.dkt_conv3d_k3(None, None, None, None, None, 1.0, None, 1, 8, 8, 8, 8, 8, 1, None) == -1
+    assert lib.dkt_conv3d_k3(1 << 12, 1 << 13, None, None, None, 1.0, 1 << 14, 1, 8, 8, 8, 8, 8, 3, None) == -2   # stride 3
+    assert lib.dkt_conv3d_k3(1 << 12, 1 << 13, None, None, None, 1.0, 1 << 12, 1, 8, 8, 8, 8, 8, 1, None) == -1   # in == out
+    assert lib.dkt_conv3d_c8(1 << 12, 1 << 13, None, None, None, 1.0, 1 << 14, 1, 4, 8, 8, 8, None) == -2         # CO not 8 | 1
+    assert lib.dkt_deconv3d_k4s2(None, None, None, None, 1.0, None, 1, 16, 8, 4, 4, 4, None) == -1
+    assert lib.dkt_deconv3d_k4s2(1 << 12, 1 << 13, None, None, 1.0, 1 << 14, 1, 6, 8, 4, 4, 4, None) == -2        # CI % 4
+    assert lib.dkt_conv3d_k1(None, 16, None, 0, None, None, None, None, 1.0, None, 1, 16, 4, 4, 4, None) == -1
+    assert lib.dkt_conv3d_k1(1 << 12, 100, 1 << 13, 100, 1 << 14, None, None, None, 1.0, 1 << 15, 1, 16, 4, 4, 4, None) == -2
+    assert lib.dkt_softargmin(None, None, 1, 48, 8, 8, None) == -1
 
 
 def test_product_never_imports_oracle():
