@@ -12,51 +12,89 @@
 
 namespace dkt {
 
+// 4-byte cp.async with zero fill (src-size 0): the staging loops below keep every load of a tile in flight at once
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ------------------------------------------------------------------------------------------------------------------
 // Group-wise correlation volume.  vol[b,g,d,y,x] = mean_{c in group g} L[b,c,y,x] * R[b,c,y,x-d]  (0 where x < d).
-// One CTA = one image row segment of GW_X pixels, all groups and disparities.  L and the D-1 pixel wider R segment are
-// staged once in shared memory (every R value is used by up to D outputs); thread = (x, d mod GW_DQ).
+// One CTA = one image row segment of GW_X pixels, all groups and disparities.  L and the wider R segment are staged once
+// in shared memory.  Thread = 4 consecutive x times 4 consecutive d: out(d0+j, x+i) needs R[x+i-d0-j], seven consecutive
+// values that two aligned 16-byte loads deliver, so a channel costs 3 shared-memory loads for 16 FMAs (the first version,
+// one (x, d) per thread, paid one load per FMA and ran at 0.55 ms for a 0.1 ms HBM pass).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int GW_X = 64;
-constexpr int GW_DQ = 4;
-constexpr int GW_MAX_CPG = 16;
+constexpr int GW_MAX_DQ = 64;          // D <= 256
 
-__global__ void __launch_bounds__(GW_X * GW_DQ)
+__global__ void __launch_bounds__(1024)
 gwc_volume_kernel(const float* __restrict__ left, const float* __restrict__ right, float* __restrict__ vol,
-                  int C, int G, int D, int H, int W) {
-    extern __shared__ float gw_smem[];
-    const int RW = GW_X + D - 1;                   // right segment: x0 - (D-1) .. x0 + GW_X - 1
+                  int C, int G, int D, int H, int W, int OFF) {
+    extern __shared__ __align__(16) float gw_smem[];
+    const int RW = GW_X + OFF;                     // right segment: x0 - OFF .. x0 + GW_X - 1 (OFF = D rounded up to 4)
     float* sL = gw_smem;                           // [C][GW_X]
     float* sR = gw_smem + C * GW_X;                // [C][RW]
     const int x0 = blockIdx.x * GW_X, y = blockIdx.y, b = blockIdx.z;
     const int64_t plane = (int64_t)H * W;
     const float* Lb = left + (int64_t)b * C * plane + (int64_t)y * W;
     const float* Rb = right + (int64_t)b * C * plane + (int64_t)y * W;
+    // asynchronous zero-filling copies: with plain loads the ~90 dependent load -> store rounds per thread were the whole
+    // run time of this kernel (0.53 ms for a 0.1 ms HBM pass)
     for (int i = threadIdx.x; i < C * GW_X; i += blockDim.x) {
         const int c = i / GW_X, x = x0 + (i - c * GW_X);
-        sL[i] = (x < W) ? __ldg(Lb + c * plane + x) : 0.f;
+        const bool ok = x < W;
+        cp_async4(sL + i, ok ? Lb + c * plane + x : left, ok);
     }
     for (int i = threadIdx.x; i < C * RW; i += blockDim.x) {
-        const int c = i / RW, x = x0 - (D - 1) + (i - c * RW);
-        sR[i] = (x >= 0 && x < W) ? __ldg(Rb + c * plane + x) : 0.f;
+        const int c = i / RW, x = x0 - OFF + (i - c * RW);
+        const bool ok = x >= 0 && x < W;
+        cp_async4(sR + i, ok ? Rb + c * plane + x : right, ok);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
-    const int xl = threadIdx.x % GW_X, dq = threadIdx.x / GW_X;
-    const int x = x0 + xl;
-    if (x >= W) return;
+    const int xq = threadIdx.x & 15, dq = threadIdx.x >> 4;
+    const int x = x0 + 4 * xq, d0 = 4 * dq;
+    if (x >= W || d0 >= D) return;
     const int cpg = C / G;
     const float inv = 1.0f / (float)cpg;
+    const bool vec = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(vol) & 15) == 0);
     for (int g = 0; g < G; ++g) {
-        float lv[GW_MAX_CPG];
+        float acc[4][4];
 #pragma unroll
-        for (int k = 0; k < GW_MAX_CPG; ++k) lv[k] = (k < cpg) ? sL[(g * cpg + k) * GW_X + xl] : 0.f;
-        for (int d = dq; d < D; d += GW_DQ) {
-            const float* r = sR + (g * cpg) * RW + (xl + (D - 1) - d);
-            float acc = 0.f;
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int k = 0; k < GW_MAX_CPG; ++k)
-                if (k < cpg) acc = fmaf(lv[k], r[k * RW], acc);
-            vol[(((int64_t)b * G + g) * D + d) * plane + (int64_t)y * W + x] = acc * inv;
+            for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+        const float* lp = sL + (g * cpg) * GW_X + 4 * xq;
+        const float* rp = sR + (g * cpg) * RW + (4 * xq - d0 - 4 + OFF);      // 16-byte aligned: OFF, d0 multiples of 4
+        for (int k = 0; k < cpg; ++k) {
+            const float4 l4 = *reinterpret_cast<const float4*>(lp + k * GW_X);
+            const float4 ra = *reinterpret_cast<const float4*>(rp + k * RW);
+            const float4 rb = *reinterpret_cast<const float4*>(rp + k * RW + 4);
+            const float l[4] = {l4.x, l4.y, l4.z, l4.w};
+            const float r[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(l[i], r[4 + i - j], acc[j][i]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int d = d0 + j;
+            if (d >= D) break;
+            float* o = vol + (((int64_t)b * G + g) * D + d) * plane + (int64_t)y * W + x;
+            if (vec) {
+                *reinterpret_cast<float4*>(o) = make_float4(acc[j][0] * inv, acc[j][1] * inv, acc[j][2] * inv, acc[j][3] * inv);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (x + i < W) o[i] = acc[j][i] * inv;
+            }
         }
     }
 }
@@ -73,14 +111,6 @@ gwc_volume_kernel(const float* __restrict__ left, const float* __restrict__ righ
 // double buffered so the next chunk lands while this one is consumed.  Per (ci, dy, dx) a thread reads DS*STRIDE+3-STRIDE
 // inputs along d and 3 x CO_T broadcast weights for 3 x DS x CO_T FMAs (>= 10 FMAs per shared-memory instruction).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    const int n = valid ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct Conv3dEpi {
     const float* scale;
@@ -494,8 +524,9 @@ extern "C" int dkt_gwc_volume(const float* left, const float* right, float* vol,
                               int H, int W, void* stream) {
     DKT_CHECK_ARG(left && right && vol);
     DKT_CHECK_ARG(B > 0 && C > 0 && groups > 0 && D > 0 && H > 0 && W > 0 && (C % groups) == 0);
-    if (C / groups > GW_MAX_CPG || H > 65535 || B > 65535) return DKT_E_UNSUPPORTED;
-    const size_t smem = (size_t)C * (GW_X + GW_X + D - 1) * sizeof(float);
+    const int dq = ceil_div(D, 4), off = 4 * dq;
+    if (C / groups > 16 || dq > GW_MAX_DQ || H > 65535 || B > 65535) return DKT_E_UNSUPPORTED;
+    const size_t smem = (size_t)C * (GW_X + GW_X + off) * sizeof(float);
     if (smem > 200 * 1024) return DKT_E_UNSUPPORTED;
     static size_t s_attr = 0;
     if (smem > s_attr) {
@@ -504,7 +535,7 @@ extern "C" int dkt_gwc_volume(const float* left, const float* right, float* vol,
         s_attr = smem;
     }
     dim3 grid(ceil_div(W, GW_X), H, B);
-    gwc_volume_kernel<<<grid, GW_X * GW_DQ, smem, (cudaStream_t)stream>>>(left, right, vol, C, groups, D, H, W);
+    gwc_volume_kernel<<<grid, 16 * dq, smem, (cudaStream_t)stream>>>(left, right, vol, C, groups, D, H, W, off);
     DKT_RETURN_LAST();
 }
 
