@@ -461,6 +461,7 @@ conv3d_k1_kernel(const float* __restrict__ in0, int C0, const float* __restrict_
 #pragma unroll
     for (int co = 0; co < K1_CO; ++co) acc[co] = 0.f;
     const float* a = in0 + (int64_t)b * C0 * vol + i;
+#pragma unroll 8
     for (int ci = 0; ci < C0; ++ci) {
         const float v = __ldg(a + ci * vol);
         const float4* w = reinterpret_cast<const float4*>(sw + ci * K1_CO);
@@ -473,6 +474,7 @@ conv3d_k1_kernel(const float* __restrict__ in0, int C0, const float* __restrict_
     }
     if (C1 > 0) {
         const float* c = in1 + (int64_t)b * C1 * vol + i;
+#pragma unroll 8
         for (int ci = 0; ci < C1; ++ci) {
             const float v = __ldg(c + ci * vol);
             const float4* w = reinterpret_cast<const float4*>(sw + (C0 + ci) * K1_CO);
