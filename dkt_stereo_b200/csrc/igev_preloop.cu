@@ -7,7 +7,7 @@
 // All of them are exact-fp32 SIMT kernels on NCDHW volumes (PyTorch modules produce the inputs and consume the outputs):
 // the volumes are 401 MB at cfg3, an 8 -> 8 channel 3x3x3 stencil is 432 flop per voxel and input channel read once,
 // i.e. FP32-FMA bound (43 GFLOP, 0.8 ms at the FMA peak), and channel counts of 8..48 are too small for a 128-wide MMA
-// tile; the volume build and the soft-argmin are one HBM pass.  ncu launch tables: profiles/r03e_igev_preloop_launches.txt.
+// tile; the volume build and the soft-argmin are one HBM pass.  ncu launch tables: profiles/r03r_igev_preloop_launches.txt.
 #include "common.cuh"
 
 namespace dkt {
