@@ -928,3 +928,45 @@ def test_igev_hourglass_golden():
     print(f"[parity] igev hourglass native vs reference: mean-abs {mean:.3e}, max-abs {mx:.3e} (|out| max {scale - 1:.2f})")
     assert mx < 3e-5 * scale, (mean, mx)
     assert stats(out_t.cpu(), g["out"])[1] < 3e-5 * scale
+
+
+# ---------------------------------------------------------------------------------------------
+# a8: pool2x / interp between the GRU scales (reference core/update.py:87-95), called directly
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 128, 136, 240), (1, 128, 17, 31), (3, 64, 8, 9)])
+def test_pool2x_and_interp_vs_torch(shape):
+    """dkt_pool2x = F.avg_pool2d(x, 3, stride=2, padding=1) (count_include_pad: border windows divide by 9) and
+    dkt_interp = F.interpolate(bilinear, align_corners=True) to the finer grid; fp32 source, destination written in
+    all three precisions into a channel slice of a wider buffer (the way the update engine uses them).
+    Tolerances: fp32 output 2e-6 (same arithmetic, different order); hi + lo reconstructs fp32 to 2^-16 relative."""
+    import torch.nn.functional as F
+    from dkt_stereo_b200 import ops
+    from dkt_stereo_b200._lib import tensor_slice
+    B, Cc, H, W = shape
+    g = torch.Generator().manual_seed(H * W)
+    x = torch.randn(B, Cc, H, W, generator=g)
+    xs = _nhwc(x).to(dev())
+    src = tensor_slice(xs, None, None, 0, Cc)
+    # pool to the coarser grid, into channels [Cc, 2Cc) of a 3Cc-wide buffer
+    Hd, Wd = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    f32 = torch.full((B, Hd, Wd, 3 * Cc), 7.0, device=dev())
+    hi = torch.zeros(B, Hd, Wd, 3 * Cc, device=dev(), dtype=torch.bfloat16)
+    lo = torch.zeros_like(hi)
+    ops.pool2x(src, tensor_slice(f32, hi, lo, Cc, Cc), B, H, W)
+    ref = _nhwc(F.avg_pool2d(x, 3, stride=2, padding=1))
+    got = f32[..., Cc:2 * Cc].cpu()
+    assert stats(got, ref)[1] < 2e-6, stats(got, ref)
+    rec = (hi.float() + lo.float())[..., Cc:2 * Cc].cpu()
+    assert stats(rec, ref)[1] < 1e-4
+    assert bool((f32[..., :Cc] == 7.0).all()) and bool((f32[..., 2 * Cc:] == 7.0).all())      # neighbours untouched
+    # interpolate the pooled map back to (H, W)
+    coarse = f32[..., Cc:2 * Cc].contiguous()
+    up32 = torch.zeros(B, H, W, 2 * Cc, device=dev())
+    uph = torch.zeros(B, H, W, 2 * Cc, device=dev(), dtype=torch.bfloat16)
+    upl = torch.zeros_like(uph)
+    ops.interp(tensor_slice(coarse, None, None, 0, Cc), tensor_slice(up32, uph, upl, Cc, Cc), B, Hd, Wd, H, W)
+    ref_up = _nhwc(F.interpolate(coarse.permute(0, 3, 1, 2).cpu(), (H, W), mode="bilinear", align_corners=True))
+    got_up = up32[..., Cc:].cpu()
+    assert stats(got_up, ref_up)[1] < 5e-6, stats(got_up, ref_up)
+    assert stats((uph.float() + upl.float())[..., Cc:].cpu(), ref_up)[1] < 1e-4
+    assert bool((up32[..., :Cc] == 0).all())
