@@ -566,6 +566,7 @@ extern "C" int dkt_conv3d_k3(const float* in, const float* weight, const float* 
     DKT_CHECK_ARG(in && weight && out && in != out);
     DKT_CHECK_ARG(B > 0 && CI > 0 && CO > 0 && D > 0 && H > 0 && W > 0);
     if (stride != 1 && stride != 2) return DKT_E_UNSUPPORTED;
+    if ((int64_t)D * H * W > 0x7fffffff) return DKT_E_UNSUPPORTED;        // 32-bit offsets inside one channel volume (fill table)
     const int Do = (D - 1) / stride + 1, Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
     const Conv3dEpi epi{scale, shift, att, slope};
     cudaStream_t st = (cudaStream_t)stream;
@@ -590,6 +591,7 @@ extern "C" int dkt_deconv3d_k4s2(const float* in, const float* weight, const flo
     DKT_CHECK_ARG(in && weight && out && in != out);
     DKT_CHECK_ARG(B > 0 && CI > 0 && CO > 0 && D > 0 && H > 0 && W > 0);
     if (CI % DC_CH) return DKT_E_UNSUPPORTED;
+    if ((int64_t)D * H * W > 0x7fffffff / 8) return DKT_E_UNSUPPORTED;    // 32-bit offsets inside one channel volume (in and out)
     if (reinterpret_cast<uintptr_t>(out) & 7) return DKT_E_ALIGNMENT;
     static bool attr_set = false;
     if (!attr_set) {
