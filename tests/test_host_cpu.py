@@ -85,3 +85,25 @@ def test_registry_and_igev_hot_path_keys():
     assert ref and all(mine.get(k) == v for k, v in ref.items())
     with pytest.raises(KeyError):
         pkg.__models__["PCVNet"]
+
+
+def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): exactly one stdout line, JSON, with
+    the keys of the measurement contract; library chatter must not reach stdout.  Tiny shape so it runs in seconds."""
+    import json, subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--height", "64", "--width", "96", "--iters", "2"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
+        assert k in d, k
+    # non-zero ranks of a torchrun launch exit quietly without work
+    r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=120, cwd=root, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
