@@ -3,14 +3,49 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <atomic>
 #include "../../include/dkt_stereo_b200.h"
 
 #define DKT_CHECK_ARG(cond)  do { if (!(cond)) return DKT_E_INVALID; } while (0)
 #define DKT_RETURN_LAST()    do { cudaError_t e__ = cudaGetLastError(); return e__ == cudaSuccess ? 0 : (int)e__; } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: remember per (call site, device)
+// whether it has been raised.  One process may drive several GPUs (nn.DataParallel in the reference's evaluator) from
+// several host threads; the bit mask is atomic and setting the attribute twice is harmless.
+#define DKT_ENSURE_SMEM(bytes, ...)                                                                              \
+    do {                                                                                                         \
+        static std::atomic<uint64_t> done__{0};                                                                  \
+        int dev__ = 0;                                                                                           \
+        if (cudaGetDevice(&dev__) != cudaSuccess) { cudaGetLastError(); dev__ = 0; }                             \
+        const uint64_t bit__ = 1ull << (dev__ & 63);                                                             \
+        if (dev__ > 63 || !(done__.load(std::memory_order_acquire) & bit__)) {                                   \
+            cudaError_t ce__ = cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+            if (ce__ != cudaSuccess) return (int)ce__;                                                           \
+            done__.fetch_or(bit__, std::memory_order_release);                                                   \
+        }                                                                                                        \
+    } while (0)
+
 namespace dkt {
 
 constexpr int kNumSMs = 148;
+
+// SM count of the CURRENT device (cached per device ordinal; 148 if the query fails)
+inline int device_sms() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return kNumSMs; }
+    if (dev >= 0 && dev < 64) {
+        const int c = cache[dev].load(std::memory_order_relaxed);
+        if (c > 0) return c;
+    }
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = kNumSMs;
+    }
+    if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
+    return n;
+}
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

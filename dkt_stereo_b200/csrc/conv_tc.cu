@@ -1087,12 +1087,7 @@ static int epilogue_flags(const dkt_epilogue& e) {
 
 template <int KIND, int ACT, int KB, int FL>
 static int launch_pair(const TcConvParams& prm, unsigned grid, size_t smem_bytes, cudaStream_t st) {
-    static bool attr_set = false;                    // per instantiation
-    if (!attr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(conv_tc_pair_kernel<KIND, ACT, KB, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce != cudaSuccess) return (int)ce;
-        attr_set = true;
-    }
+    DKT_ENSURE_SMEM(227 * 1024, conv_tc_pair_kernel<KIND, ACT, KB, FL>);
     conv_tc_pair_kernel<KIND, ACT, KB, FL><<<grid, TC2_THREADS, smem_bytes, st>>>(prm);   // grid even (cluster of 2)
     DKT_RETURN_LAST();
 }
@@ -1129,12 +1124,7 @@ static int launch_pair_fl(const TcConvParams& prm, unsigned grid, size_t smem_by
 
 template <int KIND, int ACT, int FL>
 static int launch_tap(const TcConvParams& prm, unsigned grid, size_t smem_bytes, cudaStream_t st) {
-    static bool attr_set = false;                    // per instantiation
-    if (!attr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel<64, KIND, ACT, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce != cudaSuccess) return (int)ce;
-        attr_set = true;
-    }
+    DKT_ENSURE_SMEM(227 * 1024, conv_tc_kernel<64, KIND, ACT, FL>);
     conv_tc_kernel<64, KIND, ACT, FL><<<grid, TC2_THREADS, smem_bytes, st>>>(prm);
     DKT_RETURN_LAST();
 }
@@ -1163,13 +1153,8 @@ static int launch_conv_ka(ConvFamily fam, const TcConvParams& prm, unsigned grid
         else
             return DKT_E_UNSUPPORTED;
     }
-    static bool attr_set = false;                    // per instantiation
-    if (!attr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(conv_tc_patch_kernel<32, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_tc_patch_kernel<64, KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce != cudaSuccess) return (int)ce;
-        attr_set = true;
-    }
+    DKT_ENSURE_SMEM(227 * 1024, conv_tc_patch_kernel<32, KIND, ACT>);
+    DKT_ENSURE_SMEM(227 * 1024, conv_tc_patch_kernel<64, KIND, ACT>);
     switch (fam) {
         case FAM_PATCH32: conv_tc_patch_kernel<32, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
         default:          conv_tc_patch_kernel<64, KIND, ACT><<<grid, TC2_THREADS, smem_bytes, st>>>(prm); break;
@@ -1237,14 +1222,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     // kernel choice: the row-patch kernel (default) or the per-tap kernel (strided convs, or DKT_CONV_PATCH=0)
     static const int s_patch = [] { const char* v = getenv("DKT_CONV_PATCH"); return (v && v[0] == '0') ? 0 : 1; }();
     static const int s_pair = [] { const char* v = getenv("DKT_CONV_PAIR"); return (v && v[0] == '0') ? 0 : 1; }();
-    static const int s_sms = [] {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
-            cudaGetLastError();
-            n = kNumSMs;
-        }
-        return n;
-    }();
+    const int s_sms = device_sms();
     const int Npad = (N + 15) / 16 * 16;
     const uint32_t budget = 227u * 1024u - 1024u /*align*/ - TC2_EPI_BYTES - TC_BAR_BYTES;
 

@@ -479,7 +479,7 @@ static int corr1d_lookup_launch(const float* const* pyr, int levels, int radius,
     const int64_t P = (int64_t)B * H * W1;
     const int lv = want_out ? levels : 0;
     // persistent over pixel chunks: at most 8 CTAs per SM's worth of CTAs, each walking chunks blockIdx.x, +gridDim.x, ..
-    const int64_t cap = (int64_t)kNumSMs * 8;
+    const int64_t cap = (int64_t)device_sms() * 8;
     if (enc) {
         const int64_t chunks = ceil_div64(P, LK_ENC_PIX);
         corr1d_lookup_kernel<4, true><<<(unsigned)(chunks < cap ? chunks : cap), 256, 0, (cudaStream_t)stream>>>(
@@ -545,22 +545,17 @@ static int geo_lookup_launch(const float* geo0, const float* geo1, const float* 
     size_t smem = enc ? (size_t)(LK_ENC_PIX + Cout * LK_ENC_TSP + Cout * LK_ENC_N) * 4
                       : (size_t)(LK_PIX + ((LK_PIX * TS + 3) & ~3)) * 4;
     if (smem > 200 * 1024) return DKT_E_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(geo_lookup_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(geo_lookup_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (ce != cudaSuccess) return (int)ce;
-        attr_set = true;
-    }
+    DKT_ENSURE_SMEM(200 * 1024, geo_lookup_kernel<4, true>);
+    DKT_ENSURE_SMEM(200 * 1024, geo_lookup_kernel<4, false>);
     GeoPtrs g{{geo0, geo1}, {init0, init1}};
     if (enc) {
         // persistent: as many CTAs as fit (shared memory bound), each walking 64-pixel chunks with the weights staged once
         const int per_sm = (int)((227 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((227 * 1024) / (smem + 1024));
-        const int64_t chunks = ceil_div64(P, LK_ENC_PIX), cap = (int64_t)kNumSMs * per_sm;
+        const int64_t chunks = ceil_div64(P, LK_ENC_PIX), cap = (int64_t)device_sms() * per_sm;
         geo_lookup_kernel<4, true><<<(unsigned)(chunks < cap ? chunks : cap), 256, smem, (cudaStream_t)stream>>>(
             g, disp, delta, delta_C, C, D, W, o, P, H * W);
     } else {
-        const int64_t chunks = ceil_div64(P, LK_PIX), cap = (int64_t)kNumSMs * 32;
+        const int64_t chunks = ceil_div64(P, LK_PIX), cap = (int64_t)device_sms() * 32;
         geo_lookup_kernel<4, false><<<(unsigned)(chunks < cap ? chunks : cap), 256, smem, (cudaStream_t)stream>>>(
             g, disp, delta, delta_C, C, D, W, o, P, H * W);
     }

@@ -267,23 +267,11 @@ extern "C" int dkt_corr1d_build_tc(const uint16_t* f1_hi, const uint16_t* f1_lo,
     prm.acc_cols = cols;
     prm.vec = (W2 % 8 == 0) ? 1 : 0;
     const size_t smem_bytes = (size_t)stages * stage_bytes + CT_EPI_BYTES + 1024 + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(corr1d_build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce != cudaSuccess) return (int)ce;
-        attr_set = true;
-    }
+    DKT_ENSURE_SMEM(227 * 1024, corr1d_build_tc_kernel);
     const int64_t tiles = (int64_t)B * H * prm.m_tiles * prm.n_blocks;
     if (tiles > 0x7fffffff) return DKT_E_UNSUPPORTED;
     prm.num_tiles = (int)tiles;
-    static const int s_sms = [] {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
-            cudaGetLastError();
-            n = kNumSMs;
-        }
-        return n;
-    }();
+    const int s_sms = device_sms();
     const unsigned grid = (unsigned)(tiles < s_sms ? tiles : s_sms);
     corr1d_build_tc_kernel<<<grid, CT_THREADS, smem_bytes, (cudaStream_t)stream>>>(prm);
     DKT_RETURN_LAST();

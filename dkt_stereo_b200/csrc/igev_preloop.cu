@@ -546,12 +546,7 @@ static int launch_k3(const float* in, const float* weight, const Conv3dEpi& epi,
                      int Di, int Hi, int Wi, int Do, int Ho, int Wo, cudaStream_t stream) {
     using Cfg = K3Cfg<CO_T, DS, STRIDE>;
     if (CI % Cfg::CH) return DKT_E_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(conv3d_k3_kernel<CO_T, DS, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-        if (ce != cudaSuccess) return (int)ce;
-        attr_set = true;
-    }
+    DKT_ENSURE_SMEM((int)Cfg::SMEM, conv3d_k3_kernel<CO_T, DS, STRIDE>);
     const int dtiles = ceil_div(Do, Cfg::DT), coblocks = ceil_div(CO, CO_T);
     if ((int64_t)B * dtiles * coblocks > 65535 || ceil_div(Ho, C3_YT) > 65535) return DKT_E_UNSUPPORTED;
     dim3 grid(ceil_div(Wo, C3_XT), ceil_div(Ho, C3_YT), B * dtiles * coblocks);
@@ -593,12 +588,7 @@ extern "C" int dkt_deconv3d_k4s2(const float* in, const float* weight, const flo
     if (CI % DC_CH) return DKT_E_UNSUPPORTED;
     if ((int64_t)D * H * W > 0x7fffffff / 8) return DKT_E_UNSUPPORTED;    // 32-bit offsets inside one channel volume (in and out)
     if (reinterpret_cast<uintptr_t>(out) & 7) return DKT_E_ALIGNMENT;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t ce = cudaFuncSetAttribute(deconv3d_k4s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DC_SMEM);
-        if (ce != cudaSuccess) return (int)ce;
-        attr_set = true;
-    }
+    DKT_ENSURE_SMEM((int)DC_SMEM, deconv3d_k4s2_kernel);
     const int dtiles = ceil_div(D, DC_MDT), coblocks = ceil_div(CO, DC_CO);
     if ((int64_t)B * dtiles * coblocks > 65535 || ceil_div(H, C3_YT) > 65535) return DKT_E_UNSUPPORTED;
     const Conv3dEpi epi{scale, shift, nullptr, slope};

@@ -7,6 +7,7 @@ implementations that exist for the GEMM-shaped kernels: ``"tc"`` (tcgen05 tensor
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -309,10 +310,32 @@ class ConvWeights:
     stride: int = 1
 
 
+def _pack_on_host() -> bool:
+    """DKT_PACK_ON_HOST=1: repack weights with CPU arithmetic and upload the packed tensors (no GPU kernels at all
+    for a checkpoint load; the default packs on the parameters' own device, which is what a per-step EMA-teacher
+    update wants)."""
+    return os.environ.get("DKT_PACK_ON_HOST", "0") == "1"
+
+
+def _pack_src(*ts):
+    """-> (device the packs must end up on, detached sources on the device the packing arithmetic runs on)"""
+    dev = next(t for t in ts if t is not None).device
+    if _pack_on_host():
+        ts = tuple(t.detach().cpu() if t is not None else None for t in ts)
+    else:
+        ts = tuple(t.detach() if t is not None else None for t in ts)
+    return (dev,) + ts
+
+
+def _to(t: Optional[torch.Tensor], dev) -> Optional[torch.Tensor]:
+    return t if t is None or t.device == dev else t.to(dev)
+
+
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], cin_pad: Optional[int] = None,
               tc: bool = True, keep_bias: bool = True) -> ConvWeights:
     """weight (N, Cin, k, k) fp32 (PyTorch OIHW) -> engine layouts.  cin_pad zero-pads the
     reduction dimension (e.g. 36 correlation channels carried in a 64-channel buffer)."""
+    dev, weight, bias = _pack_src(weight, bias)
     N, Cin, k, _ = weight.shape
     w = weight.detach().float()
     if cin_pad is not None and cin_pad > Cin:
@@ -330,7 +353,7 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], cin_pad: Optio
         w_hi, w_lo = split_bf16(w_tnk)
         w_hi, w_lo = w_hi.contiguous(), w_lo.contiguous()
     b = bias.detach().float().contiguous() if (bias is not None and keep_bias) else None
-    return ConvWeights(k, Cin, N, w_tkn, w_hi, w_lo, b)
+    return ConvWeights(k, Cin, N, _to(w_tkn, dev), _to(w_hi, dev), _to(w_lo, dev), _to(b, dev))
 
 
 def pack_conv_cat(weights: Sequence[torch.Tensor], tc: bool = True) -> ConvWeights:
@@ -371,10 +394,11 @@ def pack_proj3x3(weight: torch.Tensor, out_channel: int = 0) -> torch.Tensor:
     """conv weight (Nout, Cin, 3, 3) -> fp32 [Cin][PROJ_LD] with [c][ky*3+kx] = weight[out_channel, c, ky, kx]:
     the channel half of a one-output-channel 3x3 conv, applied by the DKT_EPI_PROJ epilogue of the conv that
     produces its input; the spatial half is ``tapsum3x3``."""
+    dev, weight = _pack_src(weight)
     w = weight.detach().float()[out_channel]                     # (Cin, 3, 3)
     out = torch.zeros(w.shape[0], L.PROJ_LD, device=w.device, dtype=torch.float32)
     out[:, :9] = w.reshape(w.shape[0], 9)
-    return out.contiguous()
+    return _to(out.contiguous(), dev)
 
 
 def pack_conv_general(weight: torch.Tensor, bias: Optional[torch.Tensor], *, stride: int = 1,
@@ -383,11 +407,12 @@ def pack_conv_general(weight: torch.Tensor, bias: Optional[torch.Tensor], *, str
     """Encoder conv (N, Cin, kh, kw) -> tensor-core layout [kh*kw][Npad][Cin_pad] bf16 hi/lo.
     ``bn`` = (gamma, beta, running_mean, running_var) folds an eval-mode BatchNorm that follows the conv
     into weight and bias; ``cin_pad`` / ``n_pad`` zero-pad channels (96-channel stages run as 128)."""
+    dev, weight, bias = _pack_src(weight, bias)
     w = weight.detach().double()
     N, Cin, kh, kw = w.shape
     b = bias.detach().double() if bias is not None else torch.zeros(N, dtype=torch.float64, device=w.device)
     if bn is not None:
-        gamma, beta, mean, var = (t.detach().double() for t in bn)
+        gamma, beta, mean, var = (t.detach().double().to(w.device) for t in bn)
         s = gamma / torch.sqrt(var + bn_eps)
         w = w * s.view(-1, 1, 1, 1)
         b = (b - mean) * s + beta
@@ -404,7 +429,8 @@ def pack_conv_general(weight: torch.Tensor, bias: Optional[torch.Tensor], *, str
     if npad != N:
         w_tnk = torch.nn.functional.pad(w_tnk, (0, 0, 0, npad - N))
     w_hi, w_lo = split_bf16(w_tnk.contiguous())
-    return ConvWeights(kh, Cin, N, None, w_hi.contiguous(), w_lo.contiguous(), b.float().contiguous(), kw=kw, stride=stride)
+    return ConvWeights(kh, Cin, N, None, _to(w_hi.contiguous(), dev), _to(w_lo.contiguous(), dev),
+                       _to(b.float().contiguous(), dev), kw=kw, stride=stride)
 
 
 def conv2d_ex(srcs: Sequence[DktTensor], w: ConvWeights, epi: DktEpilogue, B: int, Hin: int, Win: int) -> tuple:

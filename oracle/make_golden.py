@@ -146,17 +146,20 @@ def golden_update(m):
     save("context_upsample", disp=disp, weights=wts, out=m["igev_sub"].context_upsample(disp, wts))
 
 
-def golden_raft_forward(m, height=64, width=96, iters=4, tag="raft_fwd_small", batch=1, mode="noise"):
-    """Full RAFTStereo.forward(test_mode=True) with name-seeded synthetic weights."""
+def golden_raft_forward(m, height=64, width=96, iters=4, tag="raft_fwd_small", batch=1, mode="noise",
+                        wseed=0, iseed=1234):
+    """Full RAFTStereo.forward(test_mode=True) with name-seeded synthetic weights (weight seed ``wseed``, image seed
+    ``iseed``; both are stored so the GPU test regenerates the same inputs without the reference)."""
     from dkt_stereo_b200.synthetic import synthetic_state_dict, shapes_of, synthetic_pair
     cfg = raft_cfg()
     model = m["raft"].RAFTStereo(_ns(cfg)).eval()
-    sd = synthetic_state_dict(shapes_of(model.state_dict()), seed=0)
+    sd = synthetic_state_dict(shapes_of(model.state_dict()), seed=wseed)
     model.load_state_dict(sd, strict=True)
-    im1, im2 = synthetic_pair(batch, height, width, seed=1234, mode=mode)
+    im1, im2 = synthetic_pair(batch, height, width, seed=iseed, mode=mode)
     with torch.no_grad():
         flow_lr, flow_up = model(im1, im2, iters=iters, test_mode=True)
     save(tag, flow_lr=flow_lr, flow_up=flow_up, meta=np.array([batch, height, width, iters]),
+         seeds=np.array([wseed, iseed]),
          mode=np.array(mode), keys=np.array(sorted(sd.keys())),
          key_shapes=np.array([json.dumps(list(sd[k].shape)) for k in sorted(sd.keys())]))
 
@@ -220,6 +223,26 @@ def golden_igev_forward(m, height=64, width=96, iters=4, tag="igev_fwd_small", b
     hot_keys = sorted(k for k in sd if k.startswith(("update_block.", "spx_2_gru.", "spx_gru.")))
     save(tag, disp_up=disp_up, meta=np.array([batch, height, width, iters]), keys=np.array(hot_keys),
          key_shapes=np.array([json.dumps(list(sd[k].shape)) for k in hot_keys]), **cap)
+
+
+def golden_igev_forward_full(m, height, width, iters, tag, batch=1, mode="noise", wseed=0, iseed=1234):
+    """The REAL reference ``IGEVStereo.forward(image1, image2, iters, test_mode=True)`` (igev_stereo.py:151-226; timm
+    stubbed by torchvision's MobileNetV2) at a BASELINE configuration: stores only ``disp_up`` plus the names / shapes of
+    the reference's state dict (torchvision MobileNetV2 naming) and the two seeds, so that the GPU test rebuilds the same
+    weights by name, maps them onto the drop-in's timm-named parameters and calls the PUBLIC forward()."""
+    from dkt_stereo_b200.synthetic import synthetic_state_dict, shapes_of, synthetic_pair
+    _timm_stub()
+    igev = importlib.import_module("meta_arch.igev_stereo.igev_stereo")
+    torch.manual_seed(0)
+    model = igev.IGEVStereo(_ns(igev_cfg())).eval()
+    sd = synthetic_state_dict(shapes_of(model.state_dict()), seed=wseed)
+    model.load_state_dict(sd, strict=True)
+    im1, im2 = synthetic_pair(batch, height, width, seed=iseed, mode=mode)
+    with torch.no_grad():
+        _, disp_up = model(im1, im2, iters=iters, test_mode=True)
+    keys = sorted(sd.keys())
+    save(tag, disp_up=disp_up, meta=np.array([batch, height, width, iters]), seeds=np.array([wseed, iseed]),
+         mode=np.array(mode), keys=np.array(keys), key_shapes=np.array([json.dumps(list(sd[k].shape)) for k in keys]))
 
 
 def golden_igev_volume(m, B=1, C=96, H=9, W=37, D=20, tag="igev_volume"):
@@ -293,6 +316,14 @@ def main():
         "raft_cfg1": lambda: golden_raft_forward(m, 256, 512, 12, "raft_fwd_cfg1", 1, "noise"),
         # the headline workload itself (BASELINE configs[1] resolution and iteration count), one pair
         "raft_cfg2": lambda: golden_raft_forward(m, 544, 960, 32, "raft_fwd_cfg2", 1, "noise"),
+        # a second (weights, images) sample of the headline workload
+        "raft_cfg2_s2": lambda: golden_raft_forward(m, 544, 960, 32, "raft_fwd_cfg2_s2", 1, "noise", wseed=1, iseed=4321),
+        # BASELINE configs[3] resolution (w/4 = 320 > one UMMA N extent), one pair
+        "raft_cfg4": lambda: golden_raft_forward(m, 736, 1280, 32, "raft_fwd_cfg4shape", 1, "noise"),
+        # BASELINE configs[2] / configs[4] through the reference's public IGEVStereo.forward()
+        "igev_cfg3": lambda: golden_igev_forward_full(m, 544, 960, 32, "igev_fwd_cfg3"),
+        "igev_cfg3_shift": lambda: golden_igev_forward_full(m, 544, 960, 32, "igev_fwd_cfg3_shift", mode="shift"),
+        "igev_cfg5": lambda: golden_igev_forward_full(m, 1024, 1536, 22, "igev_fwd_cfg5shape"),
         "igev_small": lambda: golden_igev_forward(m),
         "igev_mid": lambda: golden_igev_forward(m, 96, 160, 8, "igev_fwd_mid", 1),
         "igev_volume": lambda: golden_igev_volume(m),

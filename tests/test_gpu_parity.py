@@ -12,7 +12,7 @@ from argparse import Namespace
 import pytest
 import torch
 
-from helpers import load_golden, golden_shapes, golden_state_dict, stats, RAFT_CFG, IGEV_CFG
+from helpers import load_golden, golden_shapes, golden_state_dict, golden_seeds, stats, tv_to_timm, RAFT_CFG, IGEV_CFG
 
 pytestmark = pytest.mark.gpu
 
@@ -355,7 +355,7 @@ def _model(impl, g):
     from dkt_stereo_b200.synthetic import synthetic_state_dict
     cfg = dict(RAFT_CFG, corr_implementation="b200_fp32" if impl == "simt" else "b200")
     model = RAFTStereo(Namespace(mixed_precision=False, **cfg)).eval()
-    model.load_state_dict(synthetic_state_dict(golden_shapes(g), seed=0), strict=True)
+    model.load_state_dict(synthetic_state_dict(golden_shapes(g), seed=golden_seeds(g)[0]), strict=True)
     if impl == "tc_torchenc":          # tensor-core hot path fed by the PyTorch (cuDNN fp32) encoders
         model.encoder = None
     else:
@@ -382,6 +382,53 @@ def test_raft_forward_golden(impl, tag):
     model(im1.to(dev()), im2.to(dev()), iters=iters, test_mode=True)
     lr3, up3 = model(im1.to(dev()), im2.to(dev()), iters=iters, test_mode=True)
     assert torch.equal(up3, up) and torch.equal(lr3, lr)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("tag", ["raft_fwd_cfg2_s2", "raft_fwd_cfg4shape"])
+def test_raft_forward_golden_large(impl, tag):
+    """The REAL reference's ``flow_up`` at (a) a second (weights, images) sample of the headline workload and (b) the
+    BASELINE configs[3] resolution 736 x 1280 (w/4 = 320: K1 runs in column blocks), 32 iterations, through forward()."""
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    g = load_golden(tag)
+    B, H, W, iters = [int(v) for v in g["meta"]]
+    model = _model(impl, g)
+    im1, im2 = synthetic_pair(B, H, W, seed=golden_seeds(g)[1], mode=str(g["mode"]))
+    lr, up = model(im1.to(dev()), im2.to(dev()), iters=iters, test_mode=True)
+    mean, mx = stats(up.cpu(), g["flow_up"])
+    print(f"[parity] {tag} impl={impl}: mean-abs {mean:.3e} px, max-abs {mx:.3e} px")
+    assert up.shape == (B, 1, H, W) and mean <= 1e-3, (tag, impl, mean, mx)          # north-star gate
+
+
+def _igev_model_from_golden(g, impl, monkeypatch):
+    """The drop-in IGEVStereo with the weights the golden was made with: every tensor is re-drawn from its REFERENCE-side
+    name (torchvision MobileNetV2 naming of the generator's timm stub) and loaded under the timm name the drop-in (and
+    real DKT checkpoints) use, strict=True."""
+    from dkt_stereo_b200.igev_stereo import IGEVStereo
+    from dkt_stereo_b200.synthetic import synthetic_state_dict
+    monkeypatch.setenv("DKT_IMPL", impl)
+    model = IGEVStereo(Namespace(mixed_precision=False, **IGEV_CFG)).eval()
+    sd = synthetic_state_dict(golden_shapes(g), seed=golden_seeds(g)[0])
+    model.load_state_dict({tv_to_timm(k): v for k, v in sd.items()}, strict=True)
+    return model.to(dev())
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("tag", ["igev_fwd_cfg3", "igev_fwd_cfg3_shift", "igev_fwd_cfg5shape"])
+def test_igev_forward_golden(tag, impl, monkeypatch):
+    """Images in, ``disp_up`` out through the PUBLIC ``IGEVStereo.forward(test_mode=True)`` against the real reference's
+    forward (igev_stereo.py:151-226) at BASELINE configs[2] (544 x 960, 32 iterations; noise pair and a pair with a true
+    disparity ramp) and at the configs[4] resolution (1024 x 1536, 22 iterations)."""
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    g = load_golden(tag)
+    B, H, W, iters = [int(v) for v in g["meta"]]
+    model = _igev_model_from_golden(g, impl, monkeypatch)
+    im1, im2 = synthetic_pair(B, H, W, seed=golden_seeds(g)[1], mode=str(g["mode"]))
+    for rep in range(3):                                           # eager, graph capture, graph replay
+        _, up = model(im1.to(dev()), im2.to(dev()), iters=iters, test_mode=True)
+        mean, mx = stats(up.cpu(), g["disp_up"])
+        print(f"[parity] {tag} impl={impl} rep={rep}: mean-abs {mean:.3e} px, max-abs {mx:.3e} px")
+        assert up.shape == (B, 1, H, W) and mean <= 1e-3, (tag, impl, rep, mean, mx)   # north-star gate
 
 
 def test_flow_init_and_batch_independence():

@@ -2,14 +2,13 @@
 /root/reference does not exist): the drop-in models expose exactly the reference's state-dict keys
 and shapes, and the PyTorch-side IGEV pre-loop reproduces the reference's pre-loop products."""
 import os
-import re
 import sys
 from argparse import Namespace
 
 import pytest
 import torch
 
-from helpers import RAFT_CFG, IGEV_CFG, load_golden, stats
+from helpers import RAFT_CFG, IGEV_CFG, load_golden, stats, tv_to_timm
 
 REF = os.environ.get("DKT_REFERENCE", "/root/reference")
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
@@ -23,19 +22,6 @@ def _ref_modules():
     m = MG.import_reference()
     MG._timm_stub()
     return MG, m
-
-
-# torchvision MobileNetV2 parameter names (what the timm stub yields) -> timm 0.5.4 names
-_TV_DS = {"conv.0.0": "conv_dw", "conv.0.1": "bn1", "conv.1": "conv_pw", "conv.2": "bn2"}
-_TV_IR = {"conv.0.0": "conv_pw", "conv.0.1": "bn1", "conv.1.0": "conv_dw", "conv.1.1": "bn2", "conv.2": "conv_pwl", "conv.3": "bn3"}
-
-
-def tv_to_timm(key: str) -> str:
-    mt = re.match(r"(feature\.block(\d)\.\d+\.\d+\.)(conv\.\d(?:\.\d)?)\.(.*)", key)
-    if not mt:
-        return key
-    table = _TV_DS if mt.group(2) == "0" else _TV_IR
-    return mt.group(1) + table[mt.group(3)] + "." + mt.group(4)
 
 
 def test_raft_state_dict_matches_reference():
