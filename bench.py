@@ -110,6 +110,16 @@ class ClockSampler:
                     reasons=sorted(reasons))
 
 
+def precision_tag(eng) -> str:
+    """Arithmetic type of the tensor-core path: operands are 16-bit (hi, lo) splits of fp32 values, fp32 accumulate."""
+    from dkt_stereo_b200 import _lib as L
+    base = "f16" if L.split_dtype() == torch.float16 else "bf16"
+    if eng.gru2 or eng.menc2:
+        return f"{base}x3 (encoders, heads, volume) + {base}x2 (" + "+".join(
+            n for n, on in (("GRUs", eng.gru2), ("motion encoder", eng.menc2)) if on) + "), fp32 accumulate"
+    return f"{base}x3, fp32 accumulate"
+
+
 def host_info():
     model = "unknown"
     try:
@@ -270,9 +280,10 @@ def run_b200(args):
         a.record()
         Sx = eng._slice
         split, simt = eng.impl == "tc", eng.impl == "simt"
-        e = ops.make_epilogue(L.EPI_GRU_ZR, out=Sx(eng.RH[0], 0, 128, simt, split), ctx=eng.CTX[0]["f32"], ctx_c0=0,
+        glo = not eng.gru2                    # (hi, lo) activations = 3 MMAs per K step; hi only = 2
+        e = ops.make_epilogue(L.EPI_GRU_ZR, out=Sx(eng.RH[0], 0, 128, simt, split, glo), ctx=eng.CTX[0]["f32"], ctx_c0=0,
                               z=Sx(eng.Z[0], 0, 128, True, False), h=Sx(eng.X[0], 0, 128, True, False))
-        ops.conv2d([Sx(eng.X[0], 0, 384, simt, split)], eng.weights["zr0"], e, Bg, h, w, eng.impl)
+        ops.conv2d([Sx(eng.X[0], 0, 384, simt, split, glo)], eng.weights["zr0"], e, Bg, h, w, eng.impl)
         b.record()
         evs.append((a, b))
     torch.cuda.synchronize()
@@ -282,10 +293,11 @@ def run_b200(args):
     roofline = {"kernel": "conv_tc_pair_kernel<GRU_ZR> (gru08 z||r gates, 3x3 384->256, tcgen05 cta_group::2)", "bound": "tensor",
                 "achieved": tflops, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": tflops / peaks["bf16_burst"],
                 "traffic": tr["dram_bytes"] if tr else None, "traffic_source": tr["source"] if tr else None,
-                "issued_frac": 3.0 * tflops / peaks["bf16_burst"],
+                "mma_per_k_step": 2 if eng.gru2 else 3,
+                "issued_frac": (2.0 if eng.gru2 else 3.0) * tflops / peaks["bf16_burst"],
                 "ms_per_launch": zr_ms, "flops_per_launch": flops_zr,
-                "note": "achieved = useful fp32-equivalent FLOPs; the 3-term bf16 split issues 3x this many MMA flops "
-                        "(issued_frac = tensor-pipe work actually done / peak)",
+                "note": "achieved = useful fp32-equivalent FLOPs; the split-precision path issues mma_per_k_step x this many "
+                        "MMA flops (issued_frac = tensor-pipe work actually done / peak)",
                 "peak_source": peaks["source"] + ", burst (kernel timed alone)"}
 
     # ---- roofline of the correlation-volume build (K1), HBM bound ----
@@ -368,7 +380,7 @@ def run_b200(args):
     out = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16x3" if args.kernels == "tc" else "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": precision_tag(eng) if args.kernels == "tc" else "f32", "data": "synthetic",
         "config": {"workload": f"RAFT-Stereo {H}x{W}, {iters} iters, batch {Bg} per GPU (BASELINE configs[1])",
                    "global_batch": world * Bg, "parallelism": f"dp{world} (batch shards, no steady-state collective)",
                    "kernels": args.kernels,
@@ -475,7 +487,7 @@ def run_b200_igev(args):
     out = {
         "metric": METRIC + " (IGEV-Stereo)", "value": world * Bg * args.steps / (ms_total * 1e-3), "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision_tag(eng), "data": "synthetic",
         "config": {"workload": f"IGEV-Stereo {H}x{W}, {iters} iters, batch {Bg} per GPU (BASELINE configs[2])",
                    "global_batch": world * Bg, "parallelism": f"dp{world} (batch shards, no steady-state collective)",
                    "pre_loop": "PyTorch cuDNN fp32 (MobileNetV2 pyramid, GWC volume, 3-D hourglass): next row of SURVEY 8f",

@@ -33,7 +33,7 @@ class DktEpilogue(C.Structure):
                 ("stats_partial", C.c_void_p)]
 
 
-ABI_VERSION = 2      # include/dkt_stereo_b200.h: DKT_ABI_VERSION
+ABI_VERSION = 3      # include/dkt_stereo_b200.h: DKT_ABI_VERSION
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
 EPI_LINEAR, EPI_GRU_ZR, EPI_GRU_Q, EPI_PROJ = 0, 1, 2, 3
 PROJ_LD = 12
@@ -46,6 +46,7 @@ _EP = C.POINTER(DktEpilogue)
 # name -> argtypes; mirrors include/dkt_stereo_b200.h one to one (tests check the list)
 SIGNATURES = {
     "dkt_abi_version": [],
+    "dkt_split_format": [],
     "dkt_error_string": [_I],
     "dkt_device_supported": [_I],
     "dkt_corr1d_build_f32": [_P, _P, _I64, _I64, _I64, _I64, _P, _I, _I, _I, _I, _I, _I, _F, _P],
@@ -120,6 +121,17 @@ def load() -> C.CDLL:
 LAUNCHES = 0   # kernels launched through the C ABI by this process (every ok check() is one launch)
 
 
+_split_dtype = None
+
+
+def split_dtype() -> torch.dtype:
+    """torch dtype of the library's 16-bit (hi, lo) planes: float16 (default build) or bfloat16 (DKT_SPLIT_FP16=0)."""
+    global _split_dtype
+    if _split_dtype is None:
+        _split_dtype = torch.float16 if load().dkt_split_format() == 1 else torch.bfloat16
+    return _split_dtype
+
+
 def check(rc: int, what: str = "") -> None:
     global LAUNCHES
     LAUNCHES += 1
@@ -147,7 +159,8 @@ def tensor_slice(f32: Optional[torch.Tensor] = None, hi: Optional[torch.Tensor] 
     ref = f32 if f32 is not None else hi
     assert ref is not None and ref.is_contiguous()
     Cc = ref.shape[-1]
-    for t, dt in ((f32, torch.float32), (hi, torch.bfloat16), (lo, torch.bfloat16)):
+    sd = split_dtype() if (hi is not None or lo is not None) else None
+    for t, dt in ((f32, torch.float32), (hi, sd), (lo, sd)):
         if t is not None:
             assert t.dtype == dt and t.is_contiguous() and t.shape[-1] == Cc, (t.dtype, t.shape)
     return DktTensor(ptr(f32), ptr(hi), ptr(lo), Cc, c_begin, Cc - c_begin if c_count is None else c_count)

@@ -32,6 +32,35 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(tag: str, defines, verbose: bool = False) -> str:
+    """A second build of the same sources with extra -D flags, for A/B runs through DKT_STEREO_LIB (never loaded by
+    default): e.g. build_variant("bf16", ["-DDKT_SPLIT_FP16=0"]) -> lib/libdkt_stereo_b200_bf16.so."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out = os.path.join(LIB_DIR, f"libdkt_stereo_b200_{tag}.so")
+    obj_dir = os.path.join(HERE, "build", tag)
+    os.makedirs(obj_dir, exist_ok=True)
+    os.makedirs(LIB_DIR, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(defines)
+    procs, objs = [], []
+    for src in sources():
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        cmd = [nvcc, *flags, "-c", src, "-o", obj]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        o, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(o)
+        if p.returncode:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    r = subprocess.run([nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
+                        "-Xcompiler", "-fPIC", "-o", out, *objs], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("link failed")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
@@ -81,4 +110,7 @@ def _build_locked(verbose: bool) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--bf16" in sys.argv:
+        print(build_variant("bf16", ["-DDKT_SPLIT_FP16=0"], verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

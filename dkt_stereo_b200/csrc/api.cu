@@ -3,6 +3,8 @@
 
 extern "C" int dkt_abi_version(void) { return DKT_ABI_VERSION; }
 
+extern "C" int dkt_split_format(void) { return DKT_SPLIT_FP16 ? DKT_FMT_FP16 : DKT_FMT_BF16; }
+
 extern "C" const char* dkt_error_string(int code) {
     switch (code) {
         case 0:                 return "ok";

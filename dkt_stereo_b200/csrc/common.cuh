@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <atomic>
 #include "../../include/dkt_stereo_b200.h"
@@ -50,8 +51,43 @@ inline int device_sms() {
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// ---- bf16 (hi, lo) split: hi = rn(x), lo = rn(x - hi).  hi + lo carries 16 mantissa bits ----
-__device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) {
+// ---- 16-bit (hi, lo) operand split: hi = rn16(x), lo = rn16(x - hi) ----------------------------------------------
+// DKT_SPLIT_FP16 = 1 (default): IEEE half.  hi alone carries 11 significant bits -- enough, with (hi, lo) WEIGHTS, for
+// the convs that run 2 MMAs per K step (profiles/r2_precision_study_*.txt); hi + lo carries 22 bits (abs. floor
+// 2^-25 from half's subnormals), range +-65504 (the range the reference's own --mixed_precision autocast mode lives in).
+// DKT_SPLIT_FP16 = 0: bfloat16 as in round 1 (8 / 16 significant bits, fp32 range); every conv then needs 3 MMAs.
+#ifndef DKT_SPLIT_FP16
+#define DKT_SPLIT_FP16 1
+#endif
+
+#if DKT_SPLIT_FP16
+__device__ __forceinline__ void split16(float x, uint16_t& hi, uint16_t& lo) {
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn(x - __half2float(h));
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
+}
+
+// pack two consecutive channels (one packed F2FP conversion per pair instead of two F2F)
+__device__ __forceinline__ void split16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);                     // .x = a (low half), .y = b
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// hi word only (destinations that feed 2-MMA convs carry no lo plane)
+__device__ __forceinline__ uint32_t pack_hi16x2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// two packed 16-bit values (low, high half of w) -> fp32
+__device__ __forceinline__ float2 unpack16x2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+__device__ __forceinline__ float unpack16(uint16_t v) { return __half2float(__ushort_as_half(v)); }
+#else
+__device__ __forceinline__ void split16(float x, uint16_t& hi, uint16_t& lo) {
     __nv_bfloat16 h = __float2bfloat16_rn(x);
     float r = x - __bfloat162float(h);
     __nv_bfloat16 l = __float2bfloat16_rn(r);
@@ -59,24 +95,28 @@ __device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) 
     lo = __bfloat16_as_ushort(l);
 }
 
-// pack two consecutive channels (one packed F2FP conversion per pair instead of two F2F)
-__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+__device__ __forceinline__ void split16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // .x = a (low half), .y = b
     const __nv_bfloat162 l = __floats2bfloat162_rn(a - __low2float(h), b - __high2float(h));
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// 4 consecutive channels of a bf16 (hi, lo) pair -> fp32 (hi + lo); read-only (non-coherent) path
+__device__ __forceinline__ uint32_t pack_hi16x2(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__device__ __forceinline__ float2 unpack16x2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+__device__ __forceinline__ float unpack16(uint16_t v) { return __uint_as_float((uint32_t)v << 16); }
+#endif
+
+// 4 consecutive channels of a 16-bit (hi, lo) pair -> fp32 (hi + lo); read-only (non-coherent) path
 __device__ __forceinline__ float4 load_split4(const uint16_t* hi, const uint16_t* lo, int64_t off) {
     const uint2 h = __ldg(reinterpret_cast<const uint2*>(hi + off));
     const uint2 l = __ldg(reinterpret_cast<const uint2*>(lo + off));
-    float4 r;
-    r.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
-    r.y = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
-    r.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
-    r.w = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
-    return r;
+    const float2 h0 = unpack16x2(h.x), h1 = unpack16x2(h.y), l0 = unpack16x2(l.x), l1 = unpack16x2(l.y);
+    return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
@@ -101,7 +141,7 @@ __device__ __forceinline__ void store_all(const dkt_tensor& t, int64_t pixel, in
     if (t.f32) t.f32[off] = v;
     if (t.hi) {
         uint16_t h, l;
-        split_bf16(v, h, l);
+        split16(v, h, l);
         t.hi[off] = h;
         if (t.lo) t.lo[off] = l;
     }
@@ -112,11 +152,15 @@ __device__ __forceinline__ void store_all4(const dkt_tensor& t, int64_t pixel, i
     int64_t off = pixel * t.C + t.c_begin + c;
     if (t.f32) *reinterpret_cast<float4*>(t.f32 + off) = v;
     if (t.hi) {
-        uint32_t h0, l0, h1, l1;
-        split_bf16x2(v.x, v.y, h0, l0);
-        split_bf16x2(v.z, v.w, h1, l1);
-        *reinterpret_cast<uint2*>(t.hi + off) = make_uint2(h0, h1);
-        if (t.lo) *reinterpret_cast<uint2*>(t.lo + off) = make_uint2(l0, l1);
+        if (t.lo) {
+            uint32_t h0, l0, h1, l1;
+            split16x2(v.x, v.y, h0, l0);
+            split16x2(v.z, v.w, h1, l1);
+            *reinterpret_cast<uint2*>(t.hi + off) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(t.lo + off) = make_uint2(l0, l1);
+        } else {
+            *reinterpret_cast<uint2*>(t.hi + off) = make_uint2(pack_hi16x2(v.x, v.y), pack_hi16x2(v.z, v.w));
+        }
     }
 }
 

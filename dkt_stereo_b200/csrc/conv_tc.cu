@@ -60,6 +60,7 @@ struct TcConvParams {
     int ygroup, a_stages, w_stages;
     uint32_t a_part_bytes;          // bytes of one precision (hi or lo) of an A stage
     uint32_t tmem_cols;
+    int a_parts;                    // 2: activations are (hi, lo) pairs, 3 MMAs per K step; 1: hi only, 2 MMAs (x_hi * w_hi + x_hi * w_lo)
     int w_resident;                 // pair kernel: the whole filter stays in the W ring (loaded once per CTA)
     uint32_t a_tx_bytes;            // pair kernel: bytes one CTA's TMA loads deliver per A stage (hi + lo boxes)
     int patch_rows;                 // pair kernel, x-major patch: RY = TILE_H + kh - 1 (shared-memory row = x * RY + y)
@@ -98,7 +99,7 @@ __device__ __noinline__ void tc_epilogue1(const dkt_epilogue& e, int64_t p, int 
     if (e.res) a = fmaxf(a + e.res[p * e.res_C + e.res_c0 + n], 0.f);
     else if (e.res_hi) {
         const int64_t off = p * e.res_C + e.res_c0 + n;
-        a = fmaxf(a + __uint_as_float((uint32_t)e.res_hi[off] << 16) + __uint_as_float((uint32_t)e.res_lo[off] << 16), 0.f);
+        a = fmaxf(a + unpack16(e.res_hi[off]) + unpack16(e.res_lo[off]), 0.f);
     }
     store_all(e.out, p, n, a);
 }
@@ -157,6 +158,7 @@ __device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffff
 enum : int {
     EPF_GENERIC = -1,
     EPF_OUT_F32 = 1, EPF_OUT_SPLIT = 2, EPF_RES_F32 = 4, EPF_RES_SPLIT = 8, EPF_CTX = 16, EPF_STATS = 32, EPF_TAIL = 64,
+    EPF_OUT_HI = 128,        // 16-bit hi plane only (the destination feeds 2-MMA convs); EPF_OUT_SPLIT = hi and lo
 };
 
 template <int FL> __device__ __forceinline__ bool epf(int bit, bool runtime) { return FL < 0 ? runtime : (FL & bit) != 0; }
@@ -191,8 +193,8 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
     const bool has_tail = LIN && epf<FL>(EPF_TAIL, e.tail != nullptr);
     const bool has_stats = LIN && epf<FL>(EPF_STATS, e.stats_partial != nullptr);
     const bool out_f32 = epf<FL>(EPF_OUT_F32, e.out.f32 != nullptr);
-    const bool out_split = epf<FL>(EPF_OUT_SPLIT, e.out.hi != nullptr);
-    const bool out_lo = FL < 0 ? (e.out.lo != nullptr) : out_split;
+    const bool out_split = epf<FL>(EPF_OUT_SPLIT | EPF_OUT_HI, e.out.hi != nullptr);
+    const bool out_lo = epf<FL>(EPF_OUT_SPLIT, e.out.lo != nullptr);
     // ---- loop-invariant parameters ----
     const float* const ctx = e.ctx;
     const float* const res = e.res;
@@ -389,10 +391,8 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                                     if (has_res) {
                                         rv = make_float4(__uint_as_float(rr.x), __uint_as_float(rr.y), __uint_as_float(rr.z), __uint_as_float(rr.w));
                                     } else {
-                                        rv.x = __uint_as_float(rr.x << 16) + __uint_as_float(rr.z << 16);
-                                        rv.y = __uint_as_float(rr.x & 0xffff0000u) + __uint_as_float(rr.z & 0xffff0000u);
-                                        rv.z = __uint_as_float(rr.y << 16) + __uint_as_float(rr.w << 16);
-                                        rv.w = __uint_as_float(rr.y & 0xffff0000u) + __uint_as_float(rr.w & 0xffff0000u);
+                                        const float2 h0 = unpack16x2(rr.x), h1 = unpack16x2(rr.y), l0 = unpack16x2(rr.z), l1 = unpack16x2(rr.w);
+                                        rv = make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
                                     }
                                     a.x = fmaxf(a.x + rv.x, 0.f); a.y = fmaxf(a.y + rv.y, 0.f);
                                     a.z = fmaxf(a.z + rv.z, 0.f); a.w = fmaxf(a.w + rv.w, 0.f);
@@ -426,21 +426,29 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                                 const int od = d * oC;
                                 if (out_f32) *reinterpret_cast<float4*>(pf + od) = a;
                                 if (out_split) {
-                                    uint32_t h0, l0, h1, l1;
-                                    split_bf16x2(a.x, a.y, h0, l0);
-                                    split_bf16x2(a.z, a.w, h1, l1);
-                                    *reinterpret_cast<uint2*>(ph + od) = make_uint2(h0, h1);
-                                    if (out_lo) *reinterpret_cast<uint2*>(pl + od) = make_uint2(l0, l1);
+                                    if (out_lo) {
+                                        uint32_t h0, l0, h1, l1;
+                                        split16x2(a.x, a.y, h0, l0);
+                                        split16x2(a.z, a.w, h1, l1);
+                                        *reinterpret_cast<uint2*>(ph + od) = make_uint2(h0, h1);
+                                        *reinterpret_cast<uint2*>(pl + od) = make_uint2(l0, l1);
+                                    } else {
+                                        *reinterpret_cast<uint2*>(ph + od) = make_uint2(pack_hi16x2(a.x, a.y), pack_hi16x2(a.z, a.w));
+                                    }
                                 }
                             } else {
                                 const int64_t off = (p00 + d) * oC + oc0 + nout;
                                 if (out_f32) *reinterpret_cast<float4*>(o_f32 + off) = a;
                                 if (out_split) {
-                                    uint32_t h0, l0, h1, l1;
-                                    split_bf16x2(a.x, a.y, h0, l0);
-                                    split_bf16x2(a.z, a.w, h1, l1);
-                                    *reinterpret_cast<uint2*>(o_hi + off) = make_uint2(h0, h1);
-                                    if (out_lo) *reinterpret_cast<uint2*>(o_lo + off) = make_uint2(l0, l1);
+                                    if (out_lo) {
+                                        uint32_t h0, l0, h1, l1;
+                                        split16x2(a.x, a.y, h0, l0);
+                                        split16x2(a.z, a.w, h1, l1);
+                                        *reinterpret_cast<uint2*>(o_hi + off) = make_uint2(h0, h1);
+                                        *reinterpret_cast<uint2*>(o_lo + off) = make_uint2(l0, l1);
+                                    } else {
+                                        *reinterpret_cast<uint2*>(o_hi + off) = make_uint2(pack_hi16x2(a.x, a.y), pack_hi16x2(a.z, a.w));
+                                    }
                                 }
                             }
                         }
@@ -601,7 +609,8 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const uint32_t b_bytes = (uint32_t)prm.Npad * ROW;
-    const uint32_t stage_bytes = 2u * A_BYTES + 2u * b_bytes;
+    const uint32_t a_bytes = (uint32_t)prm.a_parts * A_BYTES;         // hi [+ lo]
+    const uint32_t stage_bytes = a_bytes + 2u * b_bytes;
     uint8_t* epi_smem = smem + (size_t)prm.stages * stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + TC2_EPI_BYTES);
     uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
@@ -650,9 +659,9 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
                             mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                             const int c = prm.c_begin[s] + kb * BK;
                             tma_load_4d(st, &prm.act[s][0], &full_bar[stage], c, xs, ys, b);
-                            tma_load_4d(st + A_BYTES, &prm.act[s][1], &full_bar[stage], c, xs, ys, b);
-                            tma_load_2d(st + 2 * A_BYTES, &prm.wgt[0], &full_bar[stage], kofs + kb * BK, tap * prm.Npad);
-                            tma_load_2d(st + 2 * A_BYTES + b_bytes, &prm.wgt[1], &full_bar[stage], kofs + kb * BK, tap * prm.Npad);
+                            if (prm.a_parts == 2) tma_load_4d(st + A_BYTES, &prm.act[s][1], &full_bar[stage], c, xs, ys, b);
+                            tma_load_2d(st + a_bytes, &prm.wgt[0], &full_bar[stage], kofs + kb * BK, tap * prm.Npad);
+                            tma_load_2d(st + a_bytes + b_bytes, &prm.wgt[1], &full_bar[stage], kofs + kb * BK, tap * prm.Npad);
                         }
                         if (++stage == prm.stages) { stage = 0; phase ^= 1u; }
                     }
@@ -676,11 +685,12 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
                 if (elect_one()) {
                     const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint64_t dah = smem_desc_kmajor<BK>(a_hi), dal = smem_desc_kmajor<BK>(a_hi + A_BYTES);
-                    const uint64_t dwh = smem_desc_kmajor<BK>(a_hi + 2 * A_BYTES), dwl = smem_desc_kmajor<BK>(a_hi + 2 * A_BYTES + b_bytes);
+                    const uint64_t dwh = smem_desc_kmajor<BK>(a_hi + a_bytes), dwl = smem_desc_kmajor<BK>(a_hi + a_bytes + b_bytes);
+                    const bool a_lo = prm.a_parts == 2;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {           // +32 bytes per K16 step = +2 in the address field
                         umma_bf16(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, (it | k) != 0);
-                        umma_bf16(tmem_d, dal + 2 * k, dwh + 2 * k, idesc, 1u);
+                        if (a_lo) umma_bf16(tmem_d, dal + 2 * k, dwh + 2 * k, idesc, 1u);
                         umma_bf16(tmem_d, dah + 2 * k, dwl + 2 * k, idesc, 1u);
                     }
                     umma_commit(&empty_bar[stage]);               // smem slot reusable once these MMAs retire
@@ -725,7 +735,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-    const uint32_t a_part = prm.a_part_bytes, a_stage_bytes = 2u * prm.a_part_bytes;
+    const uint32_t a_part = prm.a_part_bytes, a_stage_bytes = (uint32_t)prm.a_parts * prm.a_part_bytes;
     const uint32_t b_bytes = (uint32_t)prm.Npad * WROW, w_stage_bytes = 2u * b_bytes;
     uint8_t* a_ring = smem;
     uint8_t* w_ring = a_ring + (size_t)prm.a_stages * a_stage_bytes;
@@ -778,7 +788,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
                                 uint8_t* ast = a_ring + (size_t)as * a_stage_bytes;
                                 mbar_arrive_expect_tx(&afull[as], a_stage_bytes);
                                 tma_load_4d(ast, &prm.act[s][0], &afull[as], c, xs, ys, b);
-                                tma_load_4d(ast + a_part, &prm.act[s][1], &afull[as], c, xs, ys, b);
+                                if (prm.a_parts == 2) tma_load_4d(ast + a_part, &prm.act[s][1], &afull[as], c, xs, ys, b);
                             }
                             if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
                             for (int kyi = 0; kyi < prm.ygroup; ++kyi) {
@@ -831,7 +841,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
 #pragma unroll
                             for (int k = 0; k < WK / 16; ++k) {   // +32 bytes per K16 step = +2 in the address field
                                 umma_bf16(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, accumulate);
-                                umma_bf16(tmem_d, dal + 2 * k, dwh + 2 * k, idesc, 1u);
+                                if (prm.a_parts == 2) umma_bf16(tmem_d, dal + 2 * k, dwh + 2 * k, idesc, 1u);
                                 umma_bf16(tmem_d, dah + 2 * k, dwl + 2 * k, idesc, 1u);
                                 accumulate = 1u;
                             }
@@ -890,7 +900,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const int Nh = prm.Npad >> 1;                                   // weight rows staged by this CTA
-    const uint32_t a_part = prm.a_part_bytes, a_stage_bytes = 2u * prm.a_part_bytes;
+    const uint32_t a_part = prm.a_part_bytes, a_stage_bytes = (uint32_t)prm.a_parts * prm.a_part_bytes;
     constexpr uint32_t KROW = KB * 2;                               // bytes of one K block row (128 or 64) == swizzle span
     const uint32_t b_bytes = (uint32_t)Nh * KROW, w_stage_bytes = 2u * b_bytes;    // K block of KB channels
     uint8_t* a_ring = smem;
@@ -956,10 +966,10 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                                 if (leader) mbar_arrive_expect_tx(&afull[as], 2u * prm.a_tx_bytes);
                                 if (XMT) {           // tensor dims ordered {C, y, x, b}
                                     tma_load_4d_pair(ast, &prm.act[s][0], afull_l + as * 8u, c, ys, xs, b);
-                                    tma_load_4d_pair(ast + a_part, &prm.act[s][1], afull_l + as * 8u, c, ys, xs, b);
+                                    if (prm.a_parts == 2) tma_load_4d_pair(ast + a_part, &prm.act[s][1], afull_l + as * 8u, c, ys, xs, b);
                                 } else {
                                     tma_load_4d_pair(ast, &prm.act[s][0], afull_l + as * 8u, c, xs, ys, b);
-                                    tma_load_4d_pair(ast + a_part, &prm.act[s][1], afull_l + as * 8u, c, xs, ys, b);
+                                    if (prm.a_parts == 2) tma_load_4d_pair(ast + a_part, &prm.act[s][1], afull_l + as * 8u, c, xs, ys, b);
                                 }
                             }
                             if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
@@ -994,6 +1004,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
             for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
             const int a_steps = kb_total * kx_n * ygroups;
             const uint32_t sbo = XMT ? (uint32_t)prm.patch_rows * KROW : 8u * KROW;      // bytes between 8-row atoms of A
+            const bool a_lo = prm.a_parts == 2;
             bool first = true;
             for (int item = pair_id; item < items; item += pairs) {
                 mbar_wait(&tmem_empty_bar[acs], aphase ^ 1u);     // both CTAs' epilogues drained this accumulator
@@ -1023,7 +1034,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
 #pragma unroll
                             for (int k = 0; k < KB / 16; ++k) {   // +32 bytes per K16 step = +2 in the address field
                                 umma_bf16_pair(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, accumulate);
-                                umma_bf16_pair(tmem_d, dal + 2 * k, dwh + 2 * k, idesc, 1u);
+                                if (a_lo) umma_bf16_pair(tmem_d, dal + 2 * k, dwh + 2 * k, idesc, 1u);
                                 umma_bf16_pair(tmem_d, dah + 2 * k, dwl + 2 * k, idesc, 1u);
                                 accumulate = 1u;
                             }
@@ -1067,16 +1078,12 @@ enum ConvFamily { FAM_PATCH32, FAM_PATCH64, FAM_TAP64, FAM_PAIR, FAM_PAIR_K32 };
 // which optional operands / outputs a LINEAR epilogue uses, as EPF_* bits (EPF_GENERIC if not expressible)
 static int epilogue_flags(const dkt_epilogue& e) {
     if (e.kind == DKT_EPI_GRU_ZR || e.kind == DKT_EPI_GRU_Q) {       // only the output precisions vary
-        if (e.out.hi && !e.out.lo) return EPF_GENERIC;
-        return (e.out.f32 ? EPF_OUT_F32 : 0) | (e.out.hi ? EPF_OUT_SPLIT : 0);
+        return (e.out.f32 ? EPF_OUT_F32 : 0) | (e.out.hi ? (e.out.lo ? EPF_OUT_SPLIT : EPF_OUT_HI) : 0);
     }
     if (e.kind != DKT_EPI_LINEAR) return EPF_GENERIC;
     int fl = 0;
     if (e.out.f32) fl |= EPF_OUT_F32;
-    if (e.out.hi) {
-        if (!e.out.lo) return EPF_GENERIC;
-        fl |= EPF_OUT_SPLIT;
-    }
+    if (e.out.hi) fl |= e.out.lo ? EPF_OUT_SPLIT : EPF_OUT_HI;
     if (e.res) fl |= EPF_RES_F32;
     else if (e.res_hi) fl |= EPF_RES_SPLIT;
     if (e.ctx) fl |= EPF_CTX;
@@ -1099,7 +1106,9 @@ static int launch_pair_fl(const TcConvParams& prm, unsigned grid, size_t smem_by
     if constexpr (KIND == DKT_EPI_LINEAR && ACT == DKT_ACT_RELU) {
         const int fl = epilogue_flags(prm.epi);
         if (fl == EPF_OUT_SPLIT) return launch_pair<KIND, ACT, KB, EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);
+        if (fl == EPF_OUT_HI) return launch_pair<KIND, ACT, KB, EPF_OUT_HI>(prm, grid, smem_bytes, st);
         if constexpr (KB == 64) {
+            if (fl == (EPF_OUT_HI | EPF_TAIL)) return launch_pair<KIND, ACT, KB, EPF_OUT_HI | EPF_TAIL>(prm, grid, smem_bytes, st);
             if (fl == (EPF_OUT_SPLIT | EPF_RES_SPLIT)) return launch_pair<KIND, ACT, KB, EPF_OUT_SPLIT | EPF_RES_SPLIT>(prm, grid, smem_bytes, st);
             if (fl == (EPF_OUT_SPLIT | EPF_RES_F32)) return launch_pair<KIND, ACT, KB, EPF_OUT_SPLIT | EPF_RES_F32>(prm, grid, smem_bytes, st);
             if (fl == (EPF_OUT_SPLIT | EPF_TAIL)) return launch_pair<KIND, ACT, KB, EPF_OUT_SPLIT | EPF_TAIL>(prm, grid, smem_bytes, st);
@@ -1112,12 +1121,15 @@ static int launch_pair_fl(const TcConvParams& prm, unsigned grid, size_t smem_by
             if (fl == EPF_OUT_F32) return launch_pair<KIND, ACT, KB, EPF_OUT_F32>(prm, grid, smem_bytes, st);
         }
     }
-    if constexpr (KIND == DKT_EPI_GRU_ZR && KB == 64) {            // tensor-core engine: r*h as bf16 (hi, lo) only
+    if constexpr (KIND == DKT_EPI_GRU_ZR && KB == 64) {            // tensor-core engine: r*h as a 16-bit pair, or hi only
         if (epilogue_flags(prm.epi) == EPF_OUT_SPLIT) return launch_pair<KIND, ACT, KB, EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);
+        if (epilogue_flags(prm.epi) == EPF_OUT_HI) return launch_pair<KIND, ACT, KB, EPF_OUT_HI>(prm, grid, smem_bytes, st);
     }
-    if constexpr (KIND == DKT_EPI_GRU_Q && KB == 64) {             // h' as fp32 (for the next blend) + bf16 (hi, lo)
+    if constexpr (KIND == DKT_EPI_GRU_Q && KB == 64) {             // h' as fp32 (for the next blend) + 16-bit (hi, lo) / hi
         if (epilogue_flags(prm.epi) == (EPF_OUT_F32 | EPF_OUT_SPLIT))
             return launch_pair<KIND, ACT, KB, EPF_OUT_F32 | EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);
+        if (epilogue_flags(prm.epi) == (EPF_OUT_F32 | EPF_OUT_HI))
+            return launch_pair<KIND, ACT, KB, EPF_OUT_F32 | EPF_OUT_HI>(prm, grid, smem_bytes, st);
     }
     return launch_pair<KIND, ACT, KB, EPF_GENERIC>(prm, grid, smem_bytes, st);
 }
@@ -1224,6 +1236,11 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     static const int s_pair = [] { const char* v = getenv("DKT_CONV_PAIR"); return (v && v[0] == '0') ? 0 : 1; }();
     const int s_sms = device_sms();
     const int Npad = (N + 15) / 16 * 16;
+    // 2-MMA mode: the sources carry no lo plane (all of them, or none)
+    int n_lo = 0;
+    for (int s = 0; s < nsrc; ++s) n_lo += srcs[s].lo != nullptr;
+    if (n_lo != 0 && n_lo != nsrc) return DKT_E_INVALID;
+    const uint32_t AP = n_lo ? 2u : 1u;
     const uint32_t budget = 227u * 1024u - 1024u /*align*/ - TC2_EPI_BYTES - TC_BAR_BYTES;
 
     // ring geometry of the row-patch kernel
@@ -1251,19 +1268,19 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     const uint32_t p_w_stage_bytes = 2u * (uint32_t)(Npad / 2) * (uint32_t)KBLK * 2u;
     if (use_pair) {
         const int w_steps = (cin_sum / KBLK) * kh * kw;            // weight blocks per tile
-        if (2u * pair_a_part_bytes * 2 >= budget) use_pair = false;
-        else if (w_steps <= TCP_MAX_W && 2u * pair_a_part_bytes * 2 + (uint32_t)w_steps * p_w_stage_bytes <= budget) {
+        if (AP * pair_a_part_bytes * 2 >= budget) use_pair = false;
+        else if (w_steps <= TCP_MAX_W && AP * pair_a_part_bytes * 2 + (uint32_t)w_steps * p_w_stage_bytes <= budget) {
             p_resident = 1;                                        // whole filter half stays in the ring
             p_w_stages = w_steps;
-            p_a_stages = (int)((budget - (uint32_t)w_steps * p_w_stage_bytes) / (2u * pair_a_part_bytes));
+            p_a_stages = (int)((budget - (uint32_t)w_steps * p_w_stage_bytes) / (AP * pair_a_part_bytes));
             if (p_a_stages > TCP_MAX_A) p_a_stages = TCP_MAX_A;
         } else {
-            p_w_stages = (int)((budget - 2u * pair_a_part_bytes * 2) / p_w_stage_bytes);
+            p_w_stages = (int)((budget - AP * pair_a_part_bytes * 2) / p_w_stage_bytes);
             if (p_w_stages > 8) p_w_stages = 8;
             if (p_w_stages < 2) use_pair = false;
-            else if (p_w_stages >= 7 && 2u * pair_a_part_bytes * 3 + 4u * p_w_stage_bytes <= budget) {
+            else if (p_w_stages >= 7 && AP * pair_a_part_bytes * 3 + 4u * p_w_stage_bytes <= budget) {
                 p_a_stages = 3;                                    // small N: a third patch stage is worth more
-                p_w_stages = (int)((budget - 2u * pair_a_part_bytes * 3) / p_w_stage_bytes);
+                p_w_stages = (int)((budget - AP * pair_a_part_bytes * 3) / p_w_stage_bytes);
                 if (p_w_stages > 8) p_w_stages = 8;
             }
         }
@@ -1274,14 +1291,14 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     int a_stages = 2, w_stages = 0;
     bool use_patch = s_patch != 0;
     if (use_patch && !use_pair) {
-        if (2u * a_part_bytes * a_stages >= budget) use_patch = false;
+        if (AP * a_part_bytes * a_stages >= budget) use_patch = false;
         else {
-            w_stages = (int)((budget - 2u * a_part_bytes * a_stages) / w_stage_bytes);
+            w_stages = (int)((budget - AP * a_part_bytes * a_stages) / w_stage_bytes);
             if (w_stages > 8) w_stages = 8;
             if (w_stages < 2) use_patch = false;
-            else if (w_stages >= 5 && 2u * a_part_bytes * 3 + 4u * w_stage_bytes <= budget) {
+            else if (w_stages >= 5 && AP * a_part_bytes * 3 + 4u * w_stage_bytes <= budget) {
                 a_stages = 3;
-                w_stages = (int)((budget - 2u * a_part_bytes * 3) / w_stage_bytes);
+                w_stages = (int)((budget - AP * a_part_bytes * 3) / w_stage_bytes);
                 if (w_stages > 8) w_stages = 8;
             }
         }
@@ -1293,10 +1310,11 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
 
     TcConvParams prm{};
     prm.nsrc = nsrc;
+    prm.a_parts = (int)AP;
     int cin_total = 0;
     for (int s = 0; s < nsrc; ++s) {
         const dkt_tensor& t = srcs[s];
-        DKT_CHECK_ARG(t.hi && t.lo && t.c_count > 0 && t.c_begin >= 0 && t.c_begin + t.c_count <= t.C);
+        DKT_CHECK_ARG(t.hi && t.c_count > 0 && t.c_begin >= 0 && t.c_begin + t.c_count <= t.C);
         if ((t.c_begin % BK) || (t.c_count % BK) || (t.C % 8) || !aligned16(t.hi) || !aligned16(t.lo))
             return DKT_E_ALIGNMENT;
         prm.c_begin[s] = t.c_begin;
@@ -1309,7 +1327,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
             const uint32_t box[4] = {(uint32_t)BK, (uint32_t)patch_ry, (uint32_t)patch_rx, 1};
             const uint32_t estr[4] = {1, 1, 1, 1};
             if (!make_tmap_bf16(&prm.act[s][0], t.hi, 4, dims, strides, box, BK * 2, estr)) return DKT_E_DRIVER;
-            if (!make_tmap_bf16(&prm.act[s][1], t.lo, 4, dims, strides, box, BK * 2, estr)) return DKT_E_DRIVER;
+            if (!make_tmap_bf16(&prm.act[s][1], t.lo ? t.lo : t.hi, 4, dims, strides, box, BK * 2, estr)) return DKT_E_DRIVER;
             continue;
         }
         const uint64_t dims[4] = {(uint64_t)t.C, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
@@ -1318,7 +1336,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         const uint32_t box[4] = {(uint32_t)BK, (uint32_t)(TC_TILE_W * stride), box_rows, 1};
         const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
         if (!make_tmap_bf16(&prm.act[s][0], t.hi, 4, dims, strides, box, BK * 2, estr)) return DKT_E_DRIVER;
-        if (!make_tmap_bf16(&prm.act[s][1], t.lo, 4, dims, strides, box, BK * 2, estr)) return DKT_E_DRIVER;
+        if (!make_tmap_bf16(&prm.act[s][1], t.lo ? t.lo : t.hi, 4, dims, strides, box, BK * 2, estr)) return DKT_E_DRIVER;
     }
     prm.kh = kh; prm.kw = kw; prm.pad_y = pad_y; prm.pad_x = pad_x; prm.stride = stride;
     prm.taps = kh * kw;
@@ -1361,7 +1379,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         prm.w_stages = p_w_stages;
         prm.w_resident = p_resident;
         prm.a_part_bytes = pair_a_part_bytes;
-        prm.a_tx_bytes = 2u * (xm ? xm_box_bytes : a_part_bytes);
+        prm.a_tx_bytes = AP * (xm ? xm_box_bytes : a_part_bytes);
         const uint32_t a_part_bytes = pair_a_part_bytes;
         const int items = (int)((tiles + 1) / 2);
         // as few CTA pairs as finish in the same number of rounds (255 items: 64 pairs x 4 rounds, not 74 x 3.45): the
@@ -1369,7 +1387,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         const int max_pairs = s_sms / 2;
         const int rounds = (items + max_pairs - 1) / max_pairs;
         const int pairs = (items + rounds - 1) / rounds;
-        const size_t smem_bytes = (size_t)p_a_stages * 2 * a_part_bytes + (size_t)p_w_stages * p_w_stage_bytes + TC2_EPI_BYTES + 1024 + TC_BAR_BYTES;
+        const size_t smem_bytes = (size_t)p_a_stages * AP * a_part_bytes + (size_t)p_w_stages * p_w_stage_bytes + TC2_EPI_BYTES + 1024 + TC_BAR_BYTES;
         return launch_conv(k32 ? FAM_PAIR_K32 : FAM_PAIR, prm, 2u * (unsigned)pairs, smem_bytes, (cudaStream_t)stream);
     }
     const unsigned grid = (unsigned)(tiles < s_sms ? tiles : s_sms);
@@ -1378,11 +1396,11 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         prm.a_stages = a_stages;
         prm.w_stages = w_stages;
         prm.a_part_bytes = a_part_bytes;
-        const size_t smem_bytes = (size_t)a_stages * 2 * a_part_bytes + (size_t)w_stages * w_stage_bytes + TC2_EPI_BYTES + 1024 + TC_BAR_BYTES;
+        const size_t smem_bytes = (size_t)a_stages * AP * a_part_bytes + (size_t)w_stages * w_stage_bytes + TC2_EPI_BYTES + 1024 + TC_BAR_BYTES;
         return launch_conv(WK == 32 ? FAM_PATCH32 : FAM_PATCH64, prm, grid, smem_bytes, (cudaStream_t)stream);
     }
     // per-tap kernel: the ring takes what the epilogue buffers and barriers leave of the 227 KB
-    const uint32_t stage_bytes = 2u * 128u * (uint32_t)BK * 2u + 2u * (uint32_t)prm.Npad * (uint32_t)BK * 2u;
+    const uint32_t stage_bytes = AP * 128u * (uint32_t)BK * 2u + 2u * (uint32_t)prm.Npad * (uint32_t)BK * 2u;
     int stages = (int)(budget / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) return DKT_E_UNSUPPORTED;

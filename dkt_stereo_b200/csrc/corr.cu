@@ -175,8 +175,8 @@ __device__ __forceinline__ void lookup_store_tile(const float* tile, int TS, int
             *reinterpret_cast<float4*>(o.f32 + off) = make_float4(v[0], v[1], v[2], v[3]);
             if (o.hi) {
                 uint32_t h0, l0, h1, l1;
-                split_bf16x2(v[0], v[1], h0, l0);
-                split_bf16x2(v[2], v[3], h1, l1);
+                split16x2(v[0], v[1], h0, l0);
+                split16x2(v[2], v[3], h1, l1);
                 *reinterpret_cast<uint2*>(o.hi + off) = make_uint2(h0, h1);
                 if (o.lo) *reinterpret_cast<uint2*>(o.lo + off) = make_uint2(l0, l1);
             }
@@ -192,7 +192,7 @@ __device__ __forceinline__ void lookup_store_tile(const float* tile, int TS, int
             o.f32[off] = v;
             if (o.hi) {
                 uint16_t h, l;
-                split_bf16(v, h, l);
+                split16(v, h, l);
                 o.hi[off] = h;
                 if (o.lo) o.lo[off] = l;
             }

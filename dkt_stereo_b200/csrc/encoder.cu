@@ -55,8 +55,8 @@ stem_rows_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64_t 
             }
         }
         uint32_t h0, l0, h1, l1;
-        split_bf16x2(v[0], v[1], h0, l0);
-        split_bf16x2(v[2], v[3], h1, l1);
+        split16x2(v[0], v[1], h0, l0);
+        split16x2(v[2], v[3], h1, l1);
         const int64_t off = ((int64_t)row * W + x0 + px) * Cpad + g * 4;
         *reinterpret_cast<uint2*>(hi + off) = make_uint2(h0, h1);
         *reinterpret_cast<uint2*>(lo + off) = make_uint2(l0, l1);

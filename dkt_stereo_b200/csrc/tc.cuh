@@ -222,12 +222,18 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
     return d;
 }
 
-// instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128
+// operand format code of kind::f16 instruction descriptors: 0 = F16, 1 = BF16 (follows common.cuh's DKT_SPLIT_FP16)
+#ifndef DKT_SPLIT_FP16
+#define DKT_SPLIT_FP16 1
+#endif
+constexpr uint32_t kOperandFmt = DKT_SPLIT_FP16 ? 0u : 1u;
+
+// instruction descriptor: 16-bit x 16-bit -> fp32, both operands K-major, M = 128
 __host__ __device__ inline uint32_t idesc_bf16_m128(uint32_t n) {
     uint32_t d = 0;
     d |= 1u << 4;            // C format: F32
-    d |= 1u << 7;            // A format: BF16
-    d |= 1u << 10;           // B format: BF16
+    d |= kOperandFmt << 7;   // A format
+    d |= kOperandFmt << 10;  // B format
     d |= (n >> 3) << 17;     // N / 8
     d |= (128u >> 4) << 24;  // M / 16
     return d;
@@ -309,12 +315,12 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                  : "memory");
 }
 
-// instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 256 (CTA pair)
+// instruction descriptor: 16-bit x 16-bit -> fp32, both operands K-major, M = 256 (CTA pair)
 __host__ __device__ inline uint32_t idesc_bf16_m256(uint32_t n) {
     uint32_t d = 0;
     d |= 1u << 4;            // C format: F32
-    d |= 1u << 7;            // A format: BF16
-    d |= 1u << 10;           // B format: BF16
+    d |= kOperandFmt << 7;   // A format
+    d |= kOperandFmt << 10;  // B format
     d |= (n >> 3) << 17;     // N / 8
     d |= (256u >> 4) << 24;  // M / 16
     return d;

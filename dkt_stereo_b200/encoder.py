@@ -44,8 +44,8 @@ class _Act:
     def __init__(self, B, H, W, Cc, device, f32=True, split=True):
         self.B, self.H, self.W, self.C = B, H, W, Cc
         self.f32 = torch.zeros(B, H, W, Cc, device=device) if f32 else None
-        self.hi = torch.zeros(B, H, W, Cc, device=device, dtype=torch.bfloat16) if split else None
-        self.lo = torch.zeros(B, H, W, Cc, device=device, dtype=torch.bfloat16) if split else None
+        self.hi = torch.zeros(B, H, W, Cc, device=device, dtype=L.split_dtype()) if split else None
+        self.lo = torch.zeros(B, H, W, Cc, device=device, dtype=L.split_dtype()) if split else None
 
     def view(self, B: int) -> "_Act":
         """The first B images (cnet reuses fnet's larger scratch buffers)."""

@@ -17,11 +17,16 @@ from . import _lib as L
 from ._lib import DktEpilogue, DktTensor, tensor_slice, null_tensor
 
 
-def split_bf16(x: torch.Tensor):
-    """x (fp32) -> (hi, lo) bf16 with hi + lo ~= x to 16 mantissa bits (same rule as csrc/common.cuh)."""
-    hi = x.to(torch.bfloat16)
-    lo = (x - hi.float()).to(torch.bfloat16)
+def split16(x: torch.Tensor):
+    """x (fp32) -> (hi, lo) in the library's 16-bit format (``_lib.split_dtype()``: half by default) with
+    hi = rn16(x), lo = rn16(x - hi) -- the same rule as csrc/common.cuh."""
+    dt = L.split_dtype()
+    hi = x.to(dt)
+    lo = (x - hi.float()).to(dt)
     return hi, lo
+
+
+split_bf16 = split16          # round-1 name
 
 
 # ---------------------------------------------------------------------------------------------
@@ -55,8 +60,8 @@ def corr1d_build(fmap1: torch.Tensor, fmap2: torch.Tensor, levels: int, scale: f
     ptrs = L.pointer_array(pyr)
     sb, sd, sh, sw = fmap1.stride()
     if impl == "tc" and D % 8 == 0:
-        hi1 = torch.empty(B, H, W1, D, device=fmap1.device, dtype=torch.bfloat16)
-        lo1, hi2, lo2 = torch.empty_like(hi1), torch.empty(B, H, W2, D, device=fmap1.device, dtype=torch.bfloat16), None
+        hi1 = torch.empty(B, H, W1, D, device=fmap1.device, dtype=L.split_dtype())
+        lo1, hi2, lo2 = torch.empty_like(hi1), torch.empty(B, H, W2, D, device=fmap1.device, dtype=L.split_dtype()), None
         lo2 = torch.empty_like(hi2)
         s = L.stream_ptr()
         L.check(lib.dkt_split_nchw_to_nhwc_bf16x2(fmap1.data_ptr(), sb, sd, sh, sw, hi1.data_ptr(), lo1.data_ptr(),
@@ -78,7 +83,7 @@ def corr1d_build_split(hi1: torch.Tensor, lo1: torch.Tensor, hi2: torch.Tensor, 
     B, H, W1, D = hi1.shape
     W2 = hi2.shape[2]
     for t in (hi1, lo1, hi2, lo2):
-        assert t.is_contiguous() and t.dtype == torch.bfloat16
+        assert t.is_contiguous() and t.dtype == L.split_dtype()
     L.check(lib.dkt_corr1d_build_tc(hi1.data_ptr(), lo1.data_ptr(), hi2.data_ptr(), lo2.data_ptr(), L.pointer_array(pyr),
                                     B, D, H, W1, W2, levels, float(scale), L.stream_ptr()), "corr1d_build_tc")
     return pyr
@@ -350,7 +355,7 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], cin_pad: Optio
         if npad != N:
             w_tnk = torch.nn.functional.pad(w_tnk, (0, 0, 0, npad - N))
         w_tnk = w_tnk.contiguous()
-        w_hi, w_lo = split_bf16(w_tnk)
+        w_hi, w_lo = split16(w_tnk)
         w_hi, w_lo = w_hi.contiguous(), w_lo.contiguous()
     b = bias.detach().float().contiguous() if (bias is not None and keep_bias) else None
     return ConvWeights(k, Cin, N, _to(w_tkn, dev), _to(w_hi, dev), _to(w_lo, dev), _to(b, dev))
@@ -428,7 +433,7 @@ def pack_conv_general(weight: torch.Tensor, bias: Optional[torch.Tensor], *, str
     w_tnk = w.permute(2, 3, 0, 1).reshape(kh * kw, N, Cin)
     if npad != N:
         w_tnk = torch.nn.functional.pad(w_tnk, (0, 0, 0, npad - N))
-    w_hi, w_lo = split_bf16(w_tnk.contiguous())
+    w_hi, w_lo = split16(w_tnk.contiguous())
     return ConvWeights(kh, Cin, N, None, _to(w_hi.contiguous(), dev), _to(w_lo.contiguous(), dev),
                        _to(b.float().contiguous(), dev), kw=kw, stride=stride)
 

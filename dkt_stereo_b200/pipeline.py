@@ -30,8 +30,14 @@ class HostPipeline:
     def _slot(self, i: int, like: torch.Tensor, dev) -> Tuple[torch.Tensor, torch.Tensor]:
         s = self.slots[i]
         if s is None or s[0].shape != like.shape or s[0].device != dev:
-            s = self.slots[i] = (torch.empty(like.shape, device=dev, dtype=torch.float32),
-                                 torch.empty(like.shape, device=dev, dtype=torch.float32))
+            # the slot is first WRITTEN on the copy stream and READ on the compute stream: allocate it under the copy
+            # stream (so the caching allocator cannot hand out a block whose previous compute-stream user is still
+            # queued) and tell the allocator about the second stream
+            with torch.cuda.stream(self.copy_stream):
+                s = self.slots[i] = (torch.empty(like.shape, device=dev, dtype=torch.float32),
+                                     torch.empty(like.shape, device=dev, dtype=torch.float32))
+            for t in s:
+                t.record_stream(torch.cuda.current_stream(dev))
         return s
 
     def _upload(self, slot: int, batch) -> None:

@@ -115,6 +115,17 @@ class UpdateEngine:
         # the flow / disparity head never reaches HBM; 0 = conv1 -> FH -> 1x1 tap conv
         self.fused_head = os.environ.get("DKT_FUSED_HEAD", "1") == "1"
         self.two_streams = os.environ.get("DKT_TWO_STREAMS", "1") == "1"
+        # args.slow_fast_gru (reference raft_stereo.py:157-160, igev_stereo.py:201-204): per iteration one extra
+        # update of the coarsest GRU, then one of the two coarse GRUs, before the full update
+        self.slow_fast = bool(getattr(block.args, "slow_fast_gru", False))
+        # MMAs per K step of the GRU convs and of the motion encoder's 64/128-channel convs (tensor-core path): 3 = every
+        # operand a 16-bit (hi, lo) pair; 2 = activations as ONE half value (hi plane only) against (hi, lo) weights.
+        # The per-group error study on the headline workload (profiles/r2_precision_study_*)
+        # puts 2-MMA GRUs + motion encoder at +1.3e-4 px over the 3-MMA engine; encoders and heads keep 3 (they cost
+        # 3e-3 / 3e-4 px with 2).  bfloat16 builds (DKT_SPLIT_FP16=0) always run 3: one bf16 value has 8 bits.
+        half = impl == "tc" and L.split_dtype() == torch.float16
+        self.gru2 = half and os.environ.get("DKT_GRU_TERMS", "2") == "2"
+        self.menc2 = half and os.environ.get("DKT_MENC_TERMS", "2") == "2"
         self.side_stream = None
         self.weights: Optional[Dict[str, ops.ConvWeights]] = None
         self._wsig = None
@@ -178,17 +189,19 @@ class UpdateEngine:
         if f32:
             d["f32"] = torch.zeros(B, H, W, Cc, device=dev, dtype=torch.float32)
         if split:
-            d["hi"] = torch.zeros(B, H, W, Cc, device=dev, dtype=torch.bfloat16)
-            d["lo"] = torch.zeros(B, H, W, Cc, device=dev, dtype=torch.bfloat16)
+            d["hi"] = torch.zeros(B, H, W, Cc, device=dev, dtype=L.split_dtype())
+            d["lo"] = torch.zeros(B, H, W, Cc, device=dev, dtype=L.split_dtype())
         return d
 
     def cor1_slice(self):
         simt, split = self.impl == "simt", self.impl == "tc"
-        return self._slice(self.COR1, 0, 64, simt, split)
+        return self._slice(self.COR1, 0, 64, simt, split, lo=not self.menc2)
 
     @staticmethod
-    def _slice(buf, c0=0, cnt=None, f32=True, split=True):
-        return TS(buf["f32"] if f32 else None, buf["hi"] if split else None, buf["lo"] if split else None, c0, cnt)
+    def _slice(buf, c0=0, cnt=None, f32=True, split=True, lo=True):
+        """``lo=False``: the hi plane only -- as a conv SOURCE this selects the 2-MMA form, as a destination it skips
+        the lo store (the buffer keeps its lo plane allocated; nobody reads it)."""
+        return TS(buf["f32"] if f32 else None, buf["hi"] if split else None, buf["lo"] if (split and lo) else None, c0, cnt)
 
     def allocate(self, B: int, h: int, w: int, device) -> None:
         shape = (B, h, w, str(device))
@@ -247,14 +260,24 @@ class UpdateEngine:
         """ConvGRU at scale i on X[i] = [h | x]; reference core/update.py:23-32."""
         B, (H, W), impl, split, simt = self.B, self.hw[i], self.impl, self.impl == "tc", self.impl == "simt"
         X, RH, Z, CTX = self.X[i], self.RH[i], self.Z[i], self.CTX[i]
-        hx = self._slice(X, 0, 128 + x_cnt, simt, split)
+        lo = not self.gru2                   # the GRU convs read (hi, lo) pairs (3 MMAs) or hi planes (2 MMAs)
+        hx = self._slice(X, 0, 128 + x_cnt, simt, split, lo)
         h = self._slice(X, 0, 128, True, False)
         z = self._slice(Z, 0, 128, True, False)
-        e = ops.make_epilogue(L.EPI_GRU_ZR, out=self._slice(RH, 0, 128, simt, split), ctx=CTX["f32"], ctx_c0=0, z=z, h=h)
+        e = ops.make_epilogue(L.EPI_GRU_ZR, out=self._slice(RH, 0, 128, simt, split, lo), ctx=CTX["f32"], ctx_c0=0, z=z, h=h)
         ops.conv2d([hx], self.weights[f"zr{i}"], e, B, H, W, impl)
-        e = ops.make_epilogue(L.EPI_GRU_Q, out=self._slice(X, 0, 128, True, split), ctx=CTX["f32"], ctx_c0=256, z=z, h=h)
-        ops.conv2d([self._slice(RH, 0, 128, simt, split), self._slice(X, 128, x_cnt, simt, split)],
+        # h' of the finest scale also feeds the flow / mask heads, which always run 3 MMAs: it keeps its lo plane
+        e = ops.make_epilogue(L.EPI_GRU_Q, out=self._slice(X, 0, 128, True, split, lo or i == 0), ctx=CTX["f32"], ctx_c0=256, z=z, h=h)
+        ops.conv2d([self._slice(RH, 0, 128, simt, split, lo), self._slice(X, 128, x_cnt, simt, split, lo)],
                    self.weights[f"q{i}"], e, B, H, W, impl)
+
+    def _coarsest_gru(self) -> None:
+        """gru32 alone: update_block(iter32=True, iter16=False, iter08=False, update=False), reference core/update.py:117-118."""
+        B, split, simt = self.B, self.impl == "tc", self.impl == "simt"
+        h1, w1 = self.hw[1]
+        S = self._slice
+        ops.pool2x(S(self.X[1], 0, 128, True, False), S(self.X[2], 128, 128, simt, split, not self.gru2), B, h1, w1)
+        self._gru(2, 128)
 
     def _coarse_grus(self) -> None:
         """gru32 then gru16 (reference core/update.py:118-128): coarse -> fine; every GRU sees the OLD finer state
@@ -263,10 +286,9 @@ class UpdateEngine:
         (h0, w0), (h1, w1), (h2, w2) = self.hw
         X0, X1, X2 = self.X
         S = self._slice
-        ops.pool2x(S(X1, 0, 128, True, False), S(X2, 128, 128, simt, split), B, h1, w1)
-        self._gru(2, 128)
-        ops.pool2x(S(X0, 0, 128, True, False), S(X1, 128, 128, simt, split), B, h0, w0)
-        ops.interp(S(X2, 0, 128, True, False), S(X1, 256, 128, simt, split), B, h2, w2, h1, w1)
+        self._coarsest_gru()
+        ops.pool2x(S(X0, 0, 128, True, False), S(X1, 128, 128, simt, split, not self.gru2), B, h0, w0)
+        ops.interp(S(X2, 0, 128, True, False), S(X1, 256, 128, simt, split, not self.gru2), B, h2, w2, h1, w1)
         self._gru(1, 256)
 
     # ---- one update-block call (reference core/update.py:115-138) -------------------------------
@@ -284,6 +306,9 @@ class UpdateEngine:
         # (1/8 and 1/16 resolution fill 3.4 and 0.9 waves of CTA pairs) overlaps the other branch's work.
         fork = self.two_streams and LaunchProfilerActive() is None
         main = torch.cuda.current_stream()
+        if self.slow_fast:
+            self._coarsest_gru()
+            self._coarse_grus()
         if fork:
             if self.side_stream is None or self.side_stream.device != self.device:
                 self.side_stream = torch.cuda.Stream(device=self.device)
@@ -298,26 +323,28 @@ class UpdateEngine:
             self._coarse_grus()
         # motion encoder (reference core/update.py:77-85)
         lookup(self)
+        mlo, glo = not self.menc2, not self.gru2   # lo planes of the motion encoder's / the GRUs' activations in use?
         if not self.fused_enc:
             ops.conv2d([S(self.CORR, 0, self.corr_pad, simt, split)], Wt["convc1"],
-                       E(L.EPI_LINEAR, S(self.COR1, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["convc1"].bias), B, h0, w0, impl)
-        ops.conv2d([S(self.COR1, 0, 64, simt, split)], Wt["convc2"],
-                   E(L.EPI_LINEAR, S(self.CF, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["convc2"].bias), B, h0, w0, impl)
+                       E(L.EPI_LINEAR, S(self.COR1, 0, 64, simt, split, mlo), act=L.ACT_RELU, bias=Wt["convc1"].bias), B, h0, w0, impl)
+        ops.conv2d([S(self.COR1, 0, 64, simt, split, mlo)], Wt["convc2"],
+                   E(L.EPI_LINEAR, S(self.CF, 0, 64, simt, split, mlo), act=L.ACT_RELU, bias=Wt["convc2"].bias), B, h0, w0, impl)
         if split and self.fast_small_convs:
+            # the 7x7 stem sees the flow / disparity VALUES (hundreds of pixels at large widths): always a (hi, lo) pair
             ops.stem_rows(self.FLOW["f32"], self.FROWS["hi"], self.FROWS["lo"], kw=7, scale=1.0, shift=0.0, layout="nhwc")
             ops.conv2d_ex([S(self.FROWS, 0, 32, False, True)], Wt["stem1t"],
-                          E(L.EPI_LINEAR, S(self.FLO1, 0, 64, False, True), act=L.ACT_RELU, bias=Wt["stem1t"].bias), B, h0, w0)
+                          E(L.EPI_LINEAR, S(self.FLO1, 0, 64, False, True, mlo), act=L.ACT_RELU, bias=Wt["stem1t"].bias), B, h0, w0)
         else:
             ops.conv2d([S(self.FLOW, 0, self.nflow, True, False)], Wt["stem1"],
-                       E(L.EPI_LINEAR, S(self.FLO1, 0, 64, simt, split), act=L.ACT_RELU, bias=Wt["stem1"].bias), B, h0, w0, "simt")
-        ops.conv2d([S(self.FLO1, 0, 64, simt, split)], Wt["stem2"],
-                   E(L.EPI_LINEAR, S(self.CF, 64, 64, simt, split), act=L.ACT_RELU, bias=Wt["stem2"].bias), B, h0, w0, impl)
-        ops.conv2d([S(self.CF, 0, 128, simt, split)], Wt["conv"],
-                   E(L.EPI_LINEAR, S(X0, 128, 128, simt, split), act=L.ACT_RELU, bias=Wt["conv"].bias,
+                       E(L.EPI_LINEAR, S(self.FLO1, 0, 64, simt, split, mlo), act=L.ACT_RELU, bias=Wt["stem1"].bias), B, h0, w0, "simt")
+        ops.conv2d([S(self.FLO1, 0, 64, simt, split, mlo)], Wt["stem2"],
+                   E(L.EPI_LINEAR, S(self.CF, 64, 64, simt, split, mlo), act=L.ACT_RELU, bias=Wt["stem2"].bias), B, h0, w0, impl)
+        ops.conv2d([S(self.CF, 0, 128, simt, split, mlo)], Wt["conv"],
+                   E(L.EPI_LINEAR, S(X0, 128, 128, simt, split, glo), act=L.ACT_RELU, bias=Wt["conv"].bias,
                      tail=self.FLOW["f32"]), B, h0, w0, impl)
         if fork:
             main.wait_event(ev2)
-        ops.interp(S(X1, 0, 128, True, False), S(X0, 256, 128, simt, split), B, h1, w1, h0, w0)
+        ops.interp(S(X1, 0, 128, True, False), S(X0, 256, 128, simt, split, glo), B, h1, w1, h0, w0)
         self._gru(0, 256)
         # flow / disparity head (reference core/update.py:13-14)
         if split and self.fast_small_convs and self.fused_head:

@@ -14,11 +14,17 @@
  *     no global state, so calls are thread-safe per stream and CUDA-graph capturable.
  *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised.
  *   - return value: 0 = ok, < 0 = invalid argument (DKT_E_*), > 0 = a cudaError_t.
- *   - "NHWC" buffers are (B, H, W, C) fp32 / bf16 with C contiguous.  Activations on the
- *     tensor-core path are carried as a bf16 (hi, lo) pair with hi + lo ~= x to 16 mantissa
- *     bits; products are accumulated in fp32 as hi*hi + lo*hi + hi*lo (3-term split), which is
- *     what keeps the 32-iteration recurrence within 1e-3 px of the fp32 reference.
- *   - bf16 values are passed as uint16_t.
+ *   - "NHWC" buffers are (B, H, W, C) fp32 / 16-bit with C contiguous.  Activations and weights
+ *     on the tensor-core path are carried as a 16-bit (hi, lo) pair, hi = rn16(x), lo = rn16(x - hi),
+ *     in the format dkt_split_format() reports: IEEE half (default build; hi alone = 11 significant
+ *     bits, hi + lo = 22) or bfloat16 (-DDKT_SPLIT_FP16=0; 8 / 16 bits).  Products are accumulated
+ *     in fp32 as  hi*hi + lo*hi + hi*lo  (3 MMAs per K step; every tensor with both planes) or, for a
+ *     conv whose SOURCE tensors are passed with lo == NULL, as  hi*w_hi + hi*w_lo  (2 MMAs: half
+ *     activations against full-precision weights).  Which convs may run with 2 is a property of the
+ *     network, measured in profiles/r2_precision_study_*.txt; the engine in dkt_stereo_b200/update.py
+ *     makes that choice, this library only executes it.
+ *   - 16-bit values are passed as uint16_t ("bf16" in entry-point names is historical: it means
+ *     "the library's 16-bit split format").
  */
 #ifndef DKT_STEREO_B200_H
 #define DKT_STEREO_B200_H
@@ -29,7 +35,12 @@
 extern "C" {
 #endif
 
-#define DKT_ABI_VERSION 2   /* 2: dkt_epilogue grew (proj, res_hi/res_lo, stats_partial) */
+#define DKT_ABI_VERSION 3   /* 2: dkt_epilogue grew (proj, res_hi/res_lo, stats_partial)
+                               3: dkt_split_format(); conv sources / destinations may omit the lo plane */
+
+/* 16-bit operand formats (dkt_split_format) */
+#define DKT_FMT_BF16 0
+#define DKT_FMT_FP16 1
 
 /* negative return codes */
 #define DKT_E_INVALID     (-1)  /* null pointer / bad dimension */
@@ -63,8 +74,8 @@ extern "C" {
  * by writers; readers document which member they need. */
 typedef struct dkt_tensor {
     float*    f32;      /* fp32 values                                   */
-    uint16_t* hi;       /* bf16 high part  (tensor-core path)            */
-    uint16_t* lo;       /* bf16 low part   (tensor-core path)            */
+    uint16_t* hi;       /* 16-bit high part (tensor-core path)           */
+    uint16_t* lo;       /* 16-bit low part; NULL = hi-only tensor        */
     int32_t   C;        /* channels per pixel in the buffer (the stride) */
     int32_t   c_begin;  /* first channel of the slice used               */
     int32_t   c_count;  /* number of channels in the slice               */
@@ -104,6 +115,8 @@ typedef struct dkt_epilogue {
 /* ---- library ---------------------------------------------------------------------------- */
 int         dkt_abi_version(void);
 const char* dkt_error_string(int code);
+/* DKT_FMT_FP16 or DKT_FMT_BF16: the 16-bit format of every hi / lo plane this build reads and writes. */
+int         dkt_split_format(void);
 /* 1 if the running device is sm_100 (tcgen05/TMA paths usable), 0 otherwise, <0 on error. */
 int         dkt_device_supported(int device);
 

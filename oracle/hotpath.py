@@ -180,24 +180,29 @@ def interp_to(x: Tensor, dest: Tensor) -> Tensor:
     return F.interpolate(x, dest.shape[2:], mode="bilinear", align_corners=True)
 
 
-def update_block(sd: SD, pre: str, net: List[Tensor], inp, corr: Tensor, flow: Tensor,
-                 igev: bool = False, n_gru_layers: int = 3, with_mask: bool = True):
-    """core/update.py:115-138 / meta_arch/igev_stereo/update.py:121-142 with all three
-    GRUs active (slow_fast_gru=False).  Returns (net, mask, delta)."""
+def update_block(sd: SD, pre: str, net: List[Tensor], inp, corr: Optional[Tensor], flow: Optional[Tensor],
+                 igev: bool = False, n_gru_layers: int = 3, with_mask: bool = True,
+                 iter_fine: bool = True, iter_mid: bool = True, iter_coarse: bool = True, update: bool = True):
+    """core/update.py:115-138 / meta_arch/igev_stereo/update.py:121-142.  ``iter_*`` / ``update`` are the reference's
+    iter08/iter16/iter32 (iter04/08/16 for IGEV) and update flags, used by the slow_fast_gru schedule.
+    Returns (net, mask, delta), or net alone when ``update`` is False."""
     g_fine, g_mid, g_coarse = ("gru04", "gru08", "gru16") if igev else ("gru08", "gru16", "gru32")
     net = list(net)
-    if n_gru_layers == 3:
+    if n_gru_layers == 3 and iter_coarse:
         net[2] = conv_gru(sd, pre + g_coarse + ".", net[2], *inp[2], pool2x(net[1]))
-    if n_gru_layers >= 2:
+    if n_gru_layers >= 2 and iter_mid:
         if n_gru_layers > 2:
             net[1] = conv_gru(sd, pre + g_mid + ".", net[1], *inp[1], pool2x(net[0]), interp_to(net[2], net[1]))
         else:
             net[1] = conv_gru(sd, pre + g_mid + ".", net[1], *inp[1], pool2x(net[0]))
-    motion = motion_encoder(sd, pre + "encoder.", flow, corr, igev)
-    if n_gru_layers > 1:
-        net[0] = conv_gru(sd, pre + g_fine + ".", net[0], *inp[0], motion, interp_to(net[1], net[0]))
-    else:
-        net[0] = conv_gru(sd, pre + g_fine + ".", net[0], *inp[0], motion)
+    if iter_fine:
+        motion = motion_encoder(sd, pre + "encoder.", flow, corr, igev)
+        if n_gru_layers > 1:
+            net[0] = conv_gru(sd, pre + g_fine + ".", net[0], *inp[0], motion, interp_to(net[1], net[0]))
+        else:
+            net[0] = conv_gru(sd, pre + g_fine + ".", net[0], *inp[0], motion)
+    if not update:
+        return net
     head = "disp_head." if igev else "flow_head."
     delta = _conv(sd, pre + head + "conv2", F.relu(_conv(sd, pre + head + "conv1", net[0], padding=1)), padding=1)
     mask = None
@@ -305,6 +310,20 @@ def raft_prepare(sd: SD, image1: Tensor, image2: Tensor, cfg: dict):
     return fmap1.float(), fmap2.float(), net, inp
 
 
+def slow_fast_updates(sd: SD, net, inp, cfg: dict, igev: bool):
+    """The extra coarse-GRU updates of ``slow_fast_gru`` (raft_stereo.py:157-160, igev_stereo.py:201-204)."""
+    n = cfg.get("n_gru_layers", 3)
+    if not cfg.get("slow_fast_gru", False):
+        return net
+    if n == 3:
+        net = update_block(sd, "update_block.", net, inp, None, None, igev=igev, n_gru_layers=n,
+                           iter_fine=False, iter_mid=False, iter_coarse=True, update=False)
+    if n >= 2:
+        net = update_block(sd, "update_block.", net, inp, None, None, igev=igev, n_gru_layers=n,
+                           iter_fine=False, iter_mid=True, iter_coarse=(n == 3), update=False)
+    return net
+
+
 def raft_loop(sd: SD, fmap1: Tensor, fmap2: Tensor, net, inp, iters: int, cfg: dict,
               flow_init: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """meta_arch/raft_stereo/raft_stereo.py:118-183 with corr_implementation='reg', test_mode=True."""
@@ -320,6 +339,7 @@ def raft_loop(sd: SD, fmap1: Tensor, fmap2: Tensor, net, inp, iters: int, cfg: d
     for it in range(iters):
         corr = corr1d_lookup(pyr, coords1[:, 0], r)
         flow = coords1 - coords0
+        net = slow_fast_updates(sd, net, inp, cfg, igev=False)
         net, mask, delta = update_block(sd, "update_block.", net, inp, corr, flow,
                                         igev=False, n_gru_layers=cfg.get("n_gru_layers", 3),
                                         with_mask=(it == iters - 1))
@@ -372,6 +392,7 @@ def igev_loop(sd: SD, match_left: Tensor, match_right: Tensor, geo_volume: Tenso
     mask_feat = None
     for it in range(iters):
         feat = geo_lookup(geo_pyr, init_pyr, disp, r)
+        net = slow_fast_updates(sd, net, inp, cfg, igev=True)
         net, mask_feat, delta = update_block(sd, "update_block.", net, inp, feat, disp, igev=True,
                                              n_gru_layers=cfg.get("n_gru_layers", 3),
                                              with_mask=(it == iters - 1))

@@ -147,11 +147,11 @@ def golden_update(m):
 
 
 def golden_raft_forward(m, height=64, width=96, iters=4, tag="raft_fwd_small", batch=1, mode="noise",
-                        wseed=0, iseed=1234):
+                        wseed=0, iseed=1234, **cfg_over):
     """Full RAFTStereo.forward(test_mode=True) with name-seeded synthetic weights (weight seed ``wseed``, image seed
     ``iseed``; both are stored so the GPU test regenerates the same inputs without the reference)."""
     from dkt_stereo_b200.synthetic import synthetic_state_dict, shapes_of, synthetic_pair
-    cfg = raft_cfg()
+    cfg = dict(raft_cfg(), **cfg_over)
     model = m["raft"].RAFTStereo(_ns(cfg)).eval()
     sd = synthetic_state_dict(shapes_of(model.state_dict()), seed=wseed)
     model.load_state_dict(sd, strict=True)
@@ -181,14 +181,14 @@ def _timm_stub():
     sys.modules["timm"].create_model = create_model
 
 
-def golden_igev_forward(m, height=64, width=96, iters=4, tag="igev_fwd_small", batch=1):
+def golden_igev_forward(m, height=64, width=96, iters=4, tag="igev_fwd_small", batch=1, **cfg_over):
     """Full reference IGEVStereo.forward(test_mode=True) (timm stubbed by torchvision).  Stores the
     products of the pre-loop (the hot path's inputs, captured with hooks while the REAL forward runs)
     and the final disparity, so the engine's IGEV hot path is pinned against the reference's loop."""
     from dkt_stereo_b200.synthetic import synthetic_state_dict, shapes_of, synthetic_pair
     _timm_stub()
     igev = importlib.import_module("meta_arch.igev_stereo.igev_stereo")
-    cfg = igev_cfg()
+    cfg = dict(igev_cfg(), **cfg_over)
     torch.manual_seed(0)
     model = igev.IGEVStereo(_ns(cfg)).eval()
     sd = synthetic_state_dict(shapes_of(model.state_dict()), seed=0)
@@ -324,6 +324,9 @@ def main():
         "igev_cfg3": lambda: golden_igev_forward_full(m, 544, 960, 32, "igev_fwd_cfg3"),
         "igev_cfg3_shift": lambda: golden_igev_forward_full(m, 544, 960, 32, "igev_fwd_cfg3_shift", mode="shift"),
         "igev_cfg5": lambda: golden_igev_forward_full(m, 1024, 1536, 22, "igev_fwd_cfg5shape"),
+        # slow_fast_gru=True (raft_stereo.py:157-160 / igev_stereo.py:201-204): extra coarse-GRU updates per iteration
+        "raft_slowfast": lambda: golden_raft_forward(m, 64, 96, 4, "raft_fwd_slowfast", 1, "noise", slow_fast_gru=True),
+        "igev_slowfast": lambda: golden_igev_forward(m, 64, 96, 4, "igev_fwd_slowfast", 1, slow_fast_gru=True),
         "igev_small": lambda: golden_igev_forward(m),
         "igev_mid": lambda: golden_igev_forward(m, 96, 160, 8, "igev_fwd_mid", 1),
         "igev_volume": lambda: golden_igev_volume(m),

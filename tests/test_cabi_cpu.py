@@ -24,7 +24,8 @@ def test_library_builds_and_exports_header_symbols():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     # the ctypes table covers the header one to one
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.dkt_abi_version() == 2
+    assert lib.dkt_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.dkt_split_format() in (0, 1)
     assert lib.dkt_error_string(-2).decode().startswith("shape or option")
 
 

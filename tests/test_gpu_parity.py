@@ -23,6 +23,12 @@ def dev():
     return torch.device("cuda:0")
 
 
+def L16():
+    """torch dtype of the library's 16-bit (hi, lo) planes (half by default)."""
+    from dkt_stereo_b200 import _lib
+    return _lib.split_dtype()
+
+
 # ---------------------------------------------------------------------------------------------
 # K1 / K2
 # ---------------------------------------------------------------------------------------------
@@ -151,7 +157,7 @@ def test_corr1d_lookup_nhwc_fast_path_and_enc():
     pyr = ops.corr1d_build(f1.to(dev()), f2.to(dev()), 4, 1.0 / D ** 0.5, impl="simt")
     cxd = cx.to(dev()).contiguous()
     out = torch.full((B, H, W, 64), 7.0, device=dev())
-    hi = torch.zeros(B, H, W, 64, device=dev(), dtype=torch.bfloat16)
+    hi = torch.zeros(B, H, W, 64, device=dev(), dtype=L16())
     lo = torch.zeros_like(hi)
     flow = torch.zeros(B, H, W, 2, device=dev())
     ops.corr1d_lookup(pyr, cxd, 4, out, "nhwc", out_hi=hi, out_lo=lo, delta=delta.to(dev()), flow=flow)
@@ -165,7 +171,7 @@ def test_corr1d_lookup_nhwc_fast_path_and_enc():
     enc_ref = torch.relu(torch.nn.functional.conv2d(ref, wt, bias))
     Wc = ops.pack_conv(wt.to(dev()), bias.to(dev()), cin_pad=64, tc=False)
     enc = torch.zeros(B, H, W, 64, device=dev())
-    ehi = torch.zeros(B, H, W, 64, device=dev(), dtype=torch.bfloat16)
+    ehi = torch.zeros(B, H, W, 64, device=dev(), dtype=L16())
     elo = torch.zeros_like(ehi)
     cxd2 = cx.to(dev()).contiguous()
     ops.corr1d_lookup_enc(pyr, cxd2, 4, Wc, L.tensor_slice(enc, ehi, elo, 0, 64), delta=delta.to(dev()), flow=flow)
@@ -189,7 +195,7 @@ def test_geo_lookup_update_nhwc_and_enc():
     geo = ops.geo_pool(gev.to(dev()))
     d = disp[:, 0].contiguous().to(dev())
     out = torch.full((B, H, W, 192), 3.0, device=dev())
-    hi = torch.zeros(B, H, W, 192, device=dev(), dtype=torch.bfloat16)
+    hi = torch.zeros(B, H, W, 192, device=dev(), dtype=L16())
     lo = torch.zeros_like(hi)
     ops.geo_lookup(geo, init, d, 4, out, "nhwc", out_hi=hi, out_lo=lo, delta=delta.to(dev()))
     assert torch.equal(d.cpu(), disp[:, 0] + delta[..., 0])
@@ -277,8 +283,13 @@ def test_conv_two_sources_and_tail(impl):
 # ---------------------------------------------------------------------------------------------
 # a6..a11: one full update-block step vs the reference's own output (golden)
 # ---------------------------------------------------------------------------------------------
-def _run_update(tag, igev, impl):
+def _run_update(tag, igev, impl, terms=2, monkeypatch=None):
+    """terms: MMAs per K step of the GRU / motion-encoder convs on the tensor-core path (3 = (hi, lo) activations,
+    2 = one half value per activation, the default engine policy -- see UpdateEngine.gru2)."""
     from dkt_stereo_b200.update import BasicMultiUpdateBlock, UpdateEngine
+    if monkeypatch is not None:
+        monkeypatch.setenv("DKT_GRU_TERMS", str(terms))
+        monkeypatch.setenv("DKT_MENC_TERMS", str(terms))
     from dkt_stereo_b200.synthetic import synthetic_state_dict
     from dkt_stereo_b200 import ops
     g = load_golden(f"update_{tag}")
@@ -287,6 +298,7 @@ def _run_update(tag, igev, impl):
     blk.load_state_dict(synthetic_state_dict(golden_shapes(g), seed=3), strict=True)
     blk = blk.to(dev())
     eng = UpdateEngine(blk, impl)
+    assert impl != "tc" or monkeypatch is None or (eng.gru2, eng.menc2) == (terms == 2, terms == 2)
     eng.pack_weights()
     B, _, h, w = g["net0"].shape
     eng.allocate(B, h, w, dev())
@@ -306,7 +318,9 @@ def _run_update(tag, igev, impl):
     eng.step(lookup, with_mask=True)
     torch.cuda.synchronize()
     net = eng.hidden_states()
-    tol = 3e-5 if impl == "simt" else 3e-4
+    # one update step: fp32 kernels 3e-5; 3-MMA tensor-core path 3e-4; 2-MMA path 1.5e-3 max-abs on O(1) states (one
+    # half-precision value per activation = 2^-12 relative per operand; the end-to-end gate is what bounds its use)
+    tol = 3e-5 if impl == "simt" else (3e-4 if not eng.gru2 else 1.5e-3)
     for i in range(3):
         assert stats(net[i].cpu(), g[f"net_out{i}"])[1] < tol, (impl, i, stats(net[i].cpu(), g[f"net_out{i}"]))
     delta = eng.DELTA["f32"].permute(0, 3, 1, 2).cpu()
@@ -318,20 +332,55 @@ def _run_update(tag, igev, impl):
     assert stats(mask, g["mask"])[1] < tol * 3, stats(mask, g["mask"])
 
 
-@pytest.mark.parametrize("impl", IMPLS)
-def test_update_block_raft(impl):
-    _run_update("raft", False, impl)
+@pytest.mark.parametrize("impl,terms", [("simt", 3), ("tc", 3), ("tc", 2)])
+def test_update_block_raft(impl, terms, monkeypatch):
+    _run_update("raft", False, impl, terms, monkeypatch)
 
 
 def test_update_block_generic_small_convs(monkeypatch):
     """Same step with the 7x7 stem / head conv2 on the generic kernels (all delta channels checked)."""
     monkeypatch.setenv("DKT_FAST_SMALL_CONVS", "0")
-    _run_update("raft", False, "tc")
+    _run_update("raft", False, "tc", 3, monkeypatch)
 
 
-@pytest.mark.parametrize("impl", IMPLS)
-def test_update_block_igev(impl):
-    _run_update("igev", True, impl)
+@pytest.mark.parametrize("impl,terms", [("simt", 3), ("tc", 3), ("tc", 2)])
+def test_update_block_igev(impl, terms, monkeypatch):
+    _run_update("igev", True, impl, terms, monkeypatch)
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 64, 8, 16, 3), (2, 384, 256, 17, 30, 3), (1, 128, 126, 19, 37, 3), (3, 64, 32, 8, 16, 3)])
+def test_conv_two_mma_mode(shape):
+    """Sources WITHOUT a lo plane select the 2-MMA form x_hi * (w_hi + w_lo) and a destination without a lo plane gets
+    its hi plane only: the result must equal the fp32 conv of the half-ROUNDED activations (weights at full precision)
+    to 3-MMA accuracy, and the untouched lo plane must stay untouched."""
+    from dkt_stereo_b200 import ops, _lib as L
+    if L.split_dtype() != torch.float16:
+        pytest.skip("bfloat16 build: hi-only activations are not used")
+    B, Cin, N, H, W, k = shape
+    g = torch.Generator().manual_seed(Cin * 7 + N)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    wt = torch.randn(N, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    bias = torch.randn(N, generator=g)
+    xh = x.half().float()
+    ref = torch.relu(torch.nn.functional.conv2d(xh, wt, bias, padding=k // 2))
+    hi = _nhwc(x).to(dev()).half().contiguous()
+    W_ = ops.pack_conv(wt.to(dev()), bias.to(dev()), tc=True)
+    Cout = (N + 7) // 8 * 8
+    out = torch.zeros(B, H, W, Cout, device=dev())
+    ohi = torch.zeros(B, H, W, Cout, device=dev(), dtype=torch.float16)
+    olo = torch.full((B, H, W, Cout), 7.0, device=dev(), dtype=torch.float16)
+    e = ops.make_epilogue(L.EPI_LINEAR, L.tensor_slice(out, ohi, None, 0, N), act=L.ACT_RELU, bias=W_.bias)
+    ops.conv2d([L.tensor_slice(None, hi, None)], W_, e, B, H, W, "tc")
+    torch.cuda.synchronize()
+    got = out[..., :N].permute(0, 3, 1, 2).cpu()
+    assert stats(got, ref)[1] < 2e-4, (shape, stats(got, ref))
+    assert torch.equal(ohi[..., :N].cpu(), out[..., :N].half().cpu())         # hi = rn16(value)
+    assert float((olo - 7.0).abs().max()) == 0.0
+    # mixing sources with and without lo is refused
+    lo = torch.zeros_like(hi)
+    if Cin >= 128:
+        with pytest.raises(L.DktError):
+            ops.conv2d([L.tensor_slice(None, hi, lo, 0, 64), L.tensor_slice(None, hi, None, 64, Cin - 64)], W_, e, B, H, W, "tc")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -498,7 +547,7 @@ def test_conv_ex_strided_and_residual(shape):
     npad = (N + 63) // 64 * 64
     Wc = ops.pack_conv_general(wt.to(dev()), bias.to(dev()), stride=stride, n_pad=npad)
     out = torch.zeros(B, Ho, Wo, npad, device=dev())
-    hi = torch.zeros(B, Ho, Wo, npad, device=dev(), dtype=torch.bfloat16)
+    hi = torch.zeros(B, Ho, Wo, npad, device=dev(), dtype=L16())
     lo = torch.zeros_like(hi)
     resd = torch.zeros(B, Ho, Wo, npad, device=dev())
     resd[..., :N] = _nhwc(res).to(dev())
@@ -521,7 +570,7 @@ def test_stem_rows_7x7():
     wt = torch.randn(64, 3, 7, 7, generator=g) / 12.0
     bias = torch.randn(64, generator=g)
     ref = torch.nn.functional.conv2d(2 * (img / 255.0) - 1.0, wt, bias, padding=3)
-    hi = torch.zeros(B, H, W, 64, device=dev(), dtype=torch.bfloat16)
+    hi = torch.zeros(B, H, W, 64, device=dev(), dtype=L16())
     lo = torch.zeros_like(hi)
     ops.stem_rows(img.to(dev()), hi, lo)
     w7 = wt.permute(0, 3, 1, 2).reshape(64, 21, 7, 1)
@@ -546,7 +595,7 @@ def test_instnorm():
     st = torch.zeros(B, Cc, 2, device=dev())
     ws = ops.instnorm_workspace(B, Cc, dev())
     out = torch.zeros(B, H, W, Cc, device=dev())
-    hi = torch.zeros(B, H, W, Cc, device=dev(), dtype=torch.bfloat16)
+    hi = torch.zeros(B, H, W, Cc, device=dev(), dtype=L16())
     lo = torch.zeros_like(hi)
     ops.instnorm_stats(L.tensor_slice(xd, None, None, 0, Cc), ws, st, B, H, W)
     ops.instnorm_apply(L.tensor_slice(xd, None, None, 0, Cc), st, L.tensor_slice(out, hi, lo, 0, Cc), B, H, W,
@@ -997,7 +1046,7 @@ def test_pool2x_and_interp_vs_torch(shape):
     # pool to the coarser grid, into channels [Cc, 2Cc) of a 3Cc-wide buffer
     Hd, Wd = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     f32 = torch.full((B, Hd, Wd, 3 * Cc), 7.0, device=dev())
-    hi = torch.zeros(B, Hd, Wd, 3 * Cc, device=dev(), dtype=torch.bfloat16)
+    hi = torch.zeros(B, Hd, Wd, 3 * Cc, device=dev(), dtype=L16())
     lo = torch.zeros_like(hi)
     ops.pool2x(src, tensor_slice(f32, hi, lo, Cc, Cc), B, H, W)
     ref = _nhwc(F.avg_pool2d(x, 3, stride=2, padding=1))
@@ -1009,7 +1058,7 @@ def test_pool2x_and_interp_vs_torch(shape):
     # interpolate the pooled map back to (H, W)
     coarse = f32[..., Cc:2 * Cc].contiguous()
     up32 = torch.zeros(B, H, W, 2 * Cc, device=dev())
-    uph = torch.zeros(B, H, W, 2 * Cc, device=dev(), dtype=torch.bfloat16)
+    uph = torch.zeros(B, H, W, 2 * Cc, device=dev(), dtype=L16())
     upl = torch.zeros_like(uph)
     ops.interp(tensor_slice(coarse, None, None, 0, Cc), tensor_slice(up32, uph, upl, Cc, Cc), B, Hd, Wd, H, W)
     ref_up = _nhwc(F.interpolate(coarse.permute(0, 3, 1, 2).cpu(), (H, W), mode="bilinear", align_corners=True))

@@ -10,9 +10,10 @@ state_dict with or without the DataParallel ``module.`` prefix, or ``{'state_dic
 metrics (EPE, D1 / bad-tau with the per-dataset thresholds and validity masks of :89-90,152-154,
 259-261,321-322).  The datasets themselves are the reference's Python readers
 (``core.stereo_datasets``, out of scope here): pass ``--reference_root`` (or put the reference on
-PYTHONPATH) to run the five validators on real data.  Offline, ``--synthetic HxW`` runs the same
-padded batch-1 loop on synthetic pairs and reports throughput; ``--batch`` feeds the engine more
-than one pair per call.
+PYTHONPATH) to run the five validators on real data; ``--batch N`` (default 1 like the reference)
+groups same-shape samples into forwards of up to N pairs fed through ``HostPipeline`` (pinned upload
+of the next batch overlapped with the current forward, dataset decoding in a background thread --
+SURVEY 8f rank 3).  Offline, ``--synthetic HxW`` measures the same path on synthetic pairs.
 """
 from __future__ import annotations
 
@@ -35,13 +36,16 @@ from dkt_stereo_b200.utils import InputPadder     # noqa: E402
 
 DIVIDE_FACTOR = 32        # reference tools/evaluate_stereo.py:37
 
-# name -> (dataset factory kwargs, bad-pixel threshold, uses maxdisp bound, needs non-occlusion mask)
+# name -> dataset factory, bad-pixel threshold, whether the ground truth is bounded by maxdisp, which non-occlusion mask
+# file the validator needs, and how D1 is averaged: the reference pools the outlier flags of ALL pixels for KITTI
+# (tools/evaluate_stereo.py:160,162-166) but averages PER-IMAGE outlier rates for ETH3D, Middlebury and Booster
+# (:92-101, :263-272, :324-333)
 VALIDATORS = {
-    "eth3d": dict(cls="ETH3D", kw={}, thr=1.0, bound=False, nocc="eth3d"),
-    "middlebury-H": dict(cls="Middlebury", kw={"resolution": "H"}, thr=2.0, bound=True, nocc="middlebury"),
-    "kitti-2012": dict(cls="KITTI", kw={"split": "2012", "image_set": "training"}, thr=3.0, bound=True, nocc=None),
-    "kitti-2015": dict(cls="KITTI", kw={"split": "2015", "image_set": "training"}, thr=3.0, bound=True, nocc=None),
-    "booster-Q": dict(cls="Booster", kw={"resolution": "Q"}, thr=2.0, bound=True, nocc=None),
+    "eth3d": dict(cls="ETH3D", kw={}, thr=1.0, bound=False, nocc="eth3d", pool="image"),
+    "middlebury-H": dict(cls="Middlebury", kw={"resolution": "H"}, thr=2.0, bound=True, nocc="middlebury", pool="image"),
+    "kitti-2012": dict(cls="KITTI", kw={"split": "2012", "image_set": "training"}, thr=3.0, bound=True, nocc=None, pool="pixel"),
+    "kitti-2015": dict(cls="KITTI", kw={"split": "2015", "image_set": "training"}, thr=3.0, bound=True, nocc=None, pool="pixel"),
+    "booster-Q": dict(cls="Booster", kw={"resolution": "Q"}, thr=2.0, bound=True, nocc=None, pool="image"),
 }
 
 
@@ -59,51 +63,124 @@ def load_checkpoint(model: torch.nn.Module, path: str) -> None:
     model.load_state_dict(ckpt, strict=True)
 
 
-def _nocc_mask(kind, dataset, idx):
+def _nocc_mask(kind: str, sample) -> np.ndarray:
+    """The non-occlusion mask the reference opens next to the sample's files (:56-57 ETH3D, :236-237 Middlebury).  A
+    missing file is an error, as in the reference (PIL raises there) -- silently dropping the mask would change the metric."""
     from PIL import Image
+    files = sample[0]
     if kind == "eth3d":
-        gt = dataset.disparity_list[idx] if hasattr(dataset, "disparity_list") else None
-        path = gt.replace("disp0GT.pfm", "mask0nocc.png") if gt else None
-    else:
-        img = dataset.image_list[idx][0]
-        path = img.replace("im0.png", "mask0nocc.png")
-    if path is None or not os.path.exists(path):
-        return None
+        path = files[2].replace("disp0GT.pfm", "mask0nocc.png")
+        return np.ascontiguousarray(Image.open(path))
+    path = files[0].replace("im0.png", "mask0nocc.png")
     return np.ascontiguousarray(Image.open(path).convert("L"), dtype=np.float32)
 
 
+def sample_metrics(flow_pr: torch.Tensor, flow_gt: torch.Tensor, valid_gt: torch.Tensor, thr: float, bound: bool,
+                   occ_mask, maxdisp: int = 192):
+    """EPE and outlier flags of one image exactly as the reference computes them (:85-90 ETH3D, :151-158 KITTI,
+    :255-262 Middlebury, :318-323 Booster).  flow_pr / flow_gt (1,H,W) = -disparity.  -> (image EPE, outlier flags of
+    the valid pixels)."""
+    assert flow_pr.shape == flow_gt.shape, (flow_pr.shape, flow_gt.shape)
+    epe = torch.sum((flow_pr - flow_gt) ** 2, dim=0).sqrt().flatten()
+    val = (valid_gt.reshape(-1) >= 0.5) & (flow_gt[0].reshape(-1) < 0)
+    if bound:
+        val &= flow_gt[0].reshape(-1) > -maxdisp
+    if occ_mask is not None:
+        val &= torch.from_numpy(np.asarray(occ_mask).flatten() == 255)
+    return epe[val].mean().item(), (epe > thr)[val]
+
+
+class _Batch:
+    __slots__ = ("idx", "im1", "im2", "padder", "gts")
+
+
+def _batch_stream(dataset, batch: int, nocc, depth: int = 2):
+    """Background thread: reads samples in dataset order, pads each to /32 (replicate, reference :63-64) and groups
+    samples of EQUAL padded shape into pinned (B,3,H,W) batches of up to ``batch`` pairs; yields _Batch objects.
+    Decoding and padding of the next batches overlap the GPU work on the current one."""
+    import queue
+    import threading
+    q: "queue.Queue" = queue.Queue(maxsize=depth)
+    pin = torch.cuda.is_available()
+
+    def emit(bucket):
+        b = _Batch()
+        b.idx = [e[0] for e in bucket]
+        b.padder = bucket[0][3]
+        b.im1 = torch.stack([e[1] for e in bucket])
+        b.im2 = torch.stack([e[2] for e in bucket])
+        if pin:
+            b.im1, b.im2 = b.im1.pin_memory(), b.im2.pin_memory()
+        b.gts = [e[4] for e in bucket]
+        q.put(b)
+
+    def work():
+        try:
+            buckets = {}
+            for idx in range(len(dataset)):
+                sample = dataset[idx]
+                image1, image2, flow_gt, valid_gt = sample[-4:]
+                occ = _nocc_mask(nocc, sample) if nocc else None
+                padder = InputPadder(image1[None].shape, divis_by=DIVIDE_FACTOR)
+                p1, p2 = padder.pad(image1[None].float(), image2[None].float())
+                key = tuple(p1.shape[-2:]) + tuple(image1.shape[-2:])
+                bk = buckets.setdefault(key, [])
+                bk.append((idx, p1[0], p2[0], padder, (flow_gt, valid_gt, occ)))
+                if len(bk) == batch:
+                    emit(buckets.pop(key))
+            for bk in buckets.values():
+                emit(bk)
+            q.put(None)
+        except BaseException as e:            # noqa: BLE001 -- re-raised in the consumer
+            q.put(e)
+
+    threading.Thread(target=work, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is None:
+            return
+        if isinstance(item, BaseException):
+            raise item
+        yield item
+
+
 @torch.no_grad()
-def validate(model, dataset, name: str, thr: float, bound: bool, nocc, iters: int = 32, maxdisp: int = 192):
-    """One pass over a reference dataset object; batch 1, padded to /32 like the reference loops."""
+def validate(model, dataset, name: str, thr: float, bound: bool, nocc, iters: int = 32, maxdisp: int = 192,
+             pool: str = "image", batch: int = 8, feeder=None):
+    """One pass over a reference dataset object (reference validate_* loops, tools/evaluate_stereo.py:46-336), batched
+    and pipelined: same-shape samples ride in one forward of up to ``batch`` pairs; the pinned upload of batch i+1
+    overlaps the forward of batch i (``HostPipeline``) and the dataset decoding runs in a background thread.  The
+    metrics are the reference's, per sample, in dataset order.  ``feeder``: object with prefetch(im1, im2) / step(next)
+    (default: HostPipeline on the model)."""
     model.eval()
-    epe_list, out_list, elapsed = [], [], []
-    for idx in range(len(dataset)):
-        sample = dataset[idx]
-        image1, image2, flow_gt, valid_gt = sample[-4:]
-        image1, image2 = image1[None].cuda(), image2[None].cuda()
-        padder = InputPadder(image1.shape, divis_by=DIVIDE_FACTOR)
-        image1, image2 = padder.pad(image1, image2)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        _, flow_pr = model(image1, image2, iters=iters, test_mode=True)
-        torch.cuda.synchronize()
-        if idx > 2:
-            elapsed.append(time.perf_counter() - t0)
-        flow_pr = padder.unpad(flow_pr).cpu().squeeze(0)
-        assert flow_pr.shape == flow_gt.shape, (flow_pr.shape, flow_gt.shape)
-        epe = torch.sum((flow_pr - flow_gt) ** 2, dim=0).sqrt().flatten()
-        val = (valid_gt.reshape(-1) >= 0.5) & (flow_gt[0].reshape(-1) < 0)
-        if bound:
-            val &= flow_gt[0].reshape(-1) > -maxdisp
-        if nocc:
-            m = _nocc_mask(nocc, dataset, idx)
-            if m is not None:
-                val &= torch.from_numpy(m.flatten() == 255)
-        epe_list.append(epe[val].mean().item())
-        out_list.append((epe > thr)[val].float().numpy())
-    epe, d1 = float(np.mean(epe_list)), 100 * float(np.mean(np.concatenate(out_list)))
-    fps = 1.0 / float(np.mean(elapsed)) if elapsed else float("nan")
-    print(f"Validation {name}: EPE {epe:f}, D1 {d1:f}, {fps:.2f}-FPS")
+    if feeder is None:
+        from dkt_stereo_b200.pipeline import HostPipeline
+        feeder = HostPipeline(model, iters=iters)
+    epes, outs = {}, {}
+    t0, pairs = time.perf_counter(), 0
+    stream = _batch_stream(dataset, batch, nocc)
+    cur = next(stream, None)
+    if cur is not None:
+        feeder.prefetch(cur.im1, cur.im2)
+    while cur is not None:
+        nxt = next(stream, None)
+        up = feeder.step((nxt.im1, nxt.im2) if nxt is not None else None)      # pinned host (B,1,Hp,Wp), reused next step
+        up = cur.padder.unpad(up)
+        for j, idx in enumerate(cur.idx):
+            flow_gt, valid_gt, occ = cur.gts[j]
+            image_epe, flags = sample_metrics(up[j].float(), flow_gt, valid_gt, thr, bound, occ, maxdisp)
+            epes[idx] = image_epe
+            outs[idx] = flags.numpy() if pool == "pixel" else flags.float().mean().item()
+        pairs += len(cur.idx)
+        cur = nxt
+    order = sorted(epes)
+    epe = float(np.mean([epes[i] for i in order]))
+    if pool == "pixel":
+        d1 = 100 * float(np.mean(np.concatenate([outs[i] for i in order])))
+    else:
+        d1 = 100 * float(np.mean([outs[i] for i in order]))
+    fps = pairs / (time.perf_counter() - t0)
+    print(f"Validation {name}: EPE {epe:f}, D1 {d1:f}, {fps:.2f}-FPS (batch {batch}, pipelined)")
     return {f"{name}-epe": epe, f"{name}-d1": d1}
 
 
@@ -184,7 +261,8 @@ def main(argv=None):
         for name in args.datasets.split(","):
             v = VALIDATORS[name]
             ds = getattr(datasets, v["cls"])({}, **v["kw"])
-            results.update(validate(model, ds, name, v["thr"], v["bound"], v["nocc"], iters=args.valid_iters))
+            results.update(validate(model, ds, name, v["thr"], v["bound"], v["nocc"], iters=args.valid_iters,
+                                    pool=v["pool"], batch=max(1, args.batch)))
     if args.logdir:
         from torch.utils.tensorboard import SummaryWriter
         w = SummaryWriter(args.logdir)

@@ -15,11 +15,11 @@ disp = torch.rand(B, h, w, device=dev, generator=g) * 48
 wt = torch.randn(64, 162, 1, 1, device=dev, generator=g) / 12
 bias = torch.randn(64, device=dev, generator=g)
 W = ops.pack_conv(wt, bias, cin_pad=192, tc=True)
-out_hi = torch.zeros(B, h, w, 64, device=dev, dtype=torch.bfloat16)
+out_hi = torch.zeros(B, h, w, 64, device=dev, dtype=L.split_dtype())
 out_lo = torch.zeros_like(out_hi)
 enc_out = L.tensor_slice(None, out_hi, out_lo, 0, 64)
 plain = torch.zeros(B, h, w, 192, device=dev)
-p_hi = torch.zeros(B, h, w, 192, device=dev, dtype=torch.bfloat16)
+p_hi = torch.zeros(B, h, w, 192, device=dev, dtype=L.split_dtype())
 p_lo = torch.zeros_like(p_hi)
 
 def t(fn, reps=20):

@@ -14,7 +14,7 @@ pyr = [torch.randn(B, h, w, w >> l, device=dev, generator=g) for l in range(4)]
 cx = (torch.arange(w, device=dev).float().view(1, 1, w) - torch.rand(B, h, w, device=dev, generator=g) * 40).contiguous()
 wt = torch.randn(64, 36, 1, 1, device=dev, generator=g) / 6
 bias = torch.randn(64, device=dev, generator=g)
-hi = torch.zeros(B, h, w, 64, device=dev, dtype=torch.bfloat16); lo = torch.zeros_like(hi)
+hi = torch.zeros(B, h, w, 64, device=dev, dtype=L.split_dtype()); lo = torch.zeros_like(hi)
 out = L.tensor_slice(None, hi, lo, 0, 64)
 def t(fn, reps=30):
     for _ in range(5): fn()
