@@ -134,26 +134,47 @@ def host_info():
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU baseline (oracle port of the reference path) -- the only place bench.py executes oracle/
+# CPU baseline -- the only place bench.py executes oracle/: the reference's own RAFTStereo (compiled to bytecode into
+# oracle/_ref by oracle/build_ref.py, kind "reference") or, when that is absent, the oracle port (kind "port")
 # ---------------------------------------------------------------------------------------------
-def cpu_pairs_per_sec(height, width, iters, batch, steps, warmup, threads):
-    from oracle import hotpath as O
+def cpu_forward_fn(height, width, iters, batch, threads):
+    """-> (callable running ONE forward of `batch` pairs on the host cores, kind)."""
     from dkt_stereo_b200.raft_stereo import RAFTStereo
     from dkt_stereo_b200.synthetic import synthetic_pair
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    model = RAFTStereo(Namespace(mixed_precision=False, **RAFT_CFG)).eval()     # weights only
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    mine = RAFTStereo(Namespace(mixed_precision=False, **RAFT_CFG)).eval()     # weights only
+    sd = {k: v.detach().clone() for k, v in mine.state_dict().items()}
     im1, im2 = synthetic_pair(batch, height, width, seed=1234)
+    try:
+        from oracle import build_ref
+        import warnings
+        warnings.filterwarnings("ignore")
+        ref = build_ref.load("raft")(Namespace(mixed_precision=False, **RAFT_CFG)).eval()
+        ref.load_state_dict(sd, strict=True)
+
+        def fwd():
+            with torch.no_grad():
+                return ref(im1, im2, iters=iters, test_mode=True)
+        return fwd, "reference"
+    except Exception as e:                      # noqa: BLE001 -- bytecode not staged / other CPython: the port still runs
+        sys.stderr.write(f"[bench] reference bytecode unavailable ({type(e).__name__}: {e}); timing the oracle port\n")
+        from oracle import hotpath as O
+        return (lambda: O.raft_forward(sd, im1, im2, iters, RAFT_CFG)), "port"
+
+
+def cpu_pairs_per_sec(height, width, iters, batch, steps, warmup, threads):
+    """-> (pairs/s over the timed steps, mean ms per step, median ms per step, kind)"""
+    fwd, kind = cpu_forward_fn(height, width, iters, batch, threads)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.raft_forward(sd, im1, im2, iters, RAFT_CFG)
+        fwd()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     total = sum(times)
-    return batch * len(times) / total, 1e3 * total / len(times)
+    return batch * len(times) / total, 1e3 * total / len(times), 1e3 * statistics.median(times), kind
 
 
 def run_reference(args):
@@ -163,14 +184,16 @@ def run_reference(args):
     hi = host_info()
     threads = hi["cores"] or 1
     H, W, iters = args.height, args.width, args.iters
-    value, ms = cpu_pairs_per_sec(H, W, iters, 1, args.steps, args.warmup, threads)
-    sample = f"1 pair per step (B=1) of the same {H}x{W}, {iters}-iter workload; {args.steps} timed steps"
+    value, ms, _, kind = cpu_pairs_per_sec(H, W, iters, 1, args.steps, args.warmup, threads)
+    what = ("the reference's own RAFTStereo.forward(test_mode=True) (oracle/_ref bytecode of the unmodified modules)"
+            if kind == "reference" else "the oracle port of the reference path")
+    sample = f"1 pair per step (B=1) of the same {H}x{W}, {iters}-iter workload; {args.steps} timed steps; {what}"
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"RAFT-Stereo {H}x{W}, {iters} iters, CPU fp32, B=1 per step", "host": hi},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -180,10 +203,137 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
+def make_model(kind: str, dev, kernels: str = "tc", extractor_tf32: bool = False):
+    from dkt_stereo_b200 import parallel
+    torch.manual_seed(0)
+    if kind == "igev":
+        from dkt_stereo_b200.igev_stereo import IGEVStereo
+        model = IGEVStereo(Namespace(mixed_precision=False, corr_implementation="b200", **IGEV_CFG)).eval().to(dev)
+    else:
+        from dkt_stereo_b200.raft_stereo import RAFTStereo
+        cfg = dict(RAFT_CFG, corr_implementation="b200" if kernels == "tc" else "b200_fp32")
+        model = RAFTStereo(Namespace(mixed_precision=False, extractor_tf32=extractor_tf32, **cfg)).eval().to(dev)
+    nbytes = parallel.broadcast_weights(model, src=0)          # the one collective of the path
+    return model, nbytes
+
+
+def timed_steps(fn, steps, dev):
+    """K calls of fn between barrier + synchronize on both sides; CUDA events on the launch stream; max over ranks."""
+    from dkt_stereo_b200 import parallel
+    parallel.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    return parallel.all_reduce_max(a.elapsed_time(b), dev)
+
+
+def measure_config(kind, H, W, iters, Bg, steps, warmup, rank, world, dev, kernels="tc", extractor_tf32=False):
+    """One BASELINE configuration: forward(test_mode=True) on this rank's shard of Bg pairs, (a) inputs resident in HBM,
+    (b) end to end through HostPipeline (pinned H2D of both images + D2H of the disparity maps every step)."""
+    from dkt_stereo_b200 import _lib as L
+    from dkt_stereo_b200.pipeline import HostPipeline
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    model, bcast = make_model(kind, dev, kernels, extractor_tf32)
+    im1_h, im2_h = synthetic_pair(Bg, H, W, seed=1234 + rank)   # every rank works on its own shard (weak scaling)
+    im1_h, im2_h = im1_h.pin_memory(), im2_h.pin_memory()
+    im1_d, im2_d = im1_h.to(dev), im2_h.to(dev)
+    step_device = lambda: model(im1_d, im2_d, iters=iters, test_mode=True)      # noqa: E731
+    pipe = HostPipeline(model, iters=iters)
+    step_e2e = lambda: pipe.step((im1_h, im2_h))                                # noqa: E731
+    for _ in range(max(warmup, 3)):             # also builds the CUDA graph (2nd / 3rd call)
+        step_device()
+    torch.cuda.synchronize()
+    res = dict(model=model, pipe=pipe, step_device=step_device, step_e2e=step_e2e, im=(im1_h, im2_h, im1_d, im2_d),
+               bcast=bcast)
+    return res
+
+
+def finish_config(res, Bg, H, W, steps, world, dev):
+    ms_total = timed_steps(res["step_device"], steps, dev)
+    im1_h, im2_h = res["im"][:2]
+    res["pipe"].prefetch(im1_h, im2_h)      # the first batch's upload is the only one outside the timed region ...
+    res["step_e2e"]()                       # ... and this untimed step consumes it: K timed steps = K uploads + K reads
+    ms_e2e = timed_steps(res["step_e2e"], steps, dev)
+    return dict(value=world * Bg * steps / (ms_total * 1e-3), ms_per_step=ms_total / steps,
+                e2e={"value": world * Bg * steps / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e / steps,
+                     "h2d_bytes_per_step": 2 * im1_h.numel() * 4, "d2h_bytes_per_step": Bg * H * W * 4})
+
+
+def fixed_sample_checksum(model, iters, dev, H=544, W=960):
+    """Every rank runs the SAME fixed-seed pair (batch 1) through its own GPU: the CRC of the raw output bytes must be
+    identical on all ranks (per-sample results bit-identical between 1-GPU and N-GPU runs) and is printed so
+    that the N = 1 and N = 8 records can be compared too."""
+    import zlib
+    from dkt_stereo_b200 import parallel
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    im1, im2 = synthetic_pair(1, H, W, seed=4242)
+    _, up = model(im1.to(dev), im2.to(dev), iters=iters, test_mode=True)
+    crc = zlib.crc32(up.float().cpu().numpy().tobytes())
+    allc = parallel.all_gather_int(crc, dev)
+    return {"crc32": f"{crc:08x}", "ranks": len(allc), "identical": all(c == allc[0] for c in allc),
+            "sample": f"seed 4242, 1 x {H}x{W}, {iters} iters, full-resolution output"}
+
+
+def igev_lookup_roofline(model, Bg, h, w, peaks):
+    """Combined geometry-encoding lookup (a5) alone on the volumes of the last step; algorithmic bytes of SURVEY 8d."""
+    from dkt_stereo_b200 import ops
+    eng = model.engine
+    P = Bg * h * w
+    geo, init = model._vol
+    nplanes = 1 if eng.menc2 else 2
+    lk_bytes = P * (2 * 9 * 10 * 4 + 4 + nplanes * 64 * 2)       # tap reads + disparity, writes 64 ch 16-bit (fused convc1)
+    disp = eng.FLOW["f32"].view(Bg, h, w).clone()
+    for _ in range(3):
+        ops.geo_lookup_enc(geo, init, disp, 4, eng.weights["convc1"], eng.cor1_slice())
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        ops.geo_lookup_enc(geo, init, disp, 4, eng.weights["convc1"], eng.cor1_slice())
+    b.record()
+    torch.cuda.synchronize()
+    lk_ms = a.elapsed_time(b) / 20
+    tr = ncu_traffic("geo_lookup_enc") if (h, w, Bg) == (136, 240, 8) else None
+    return {"kernel": "geo_lookup_kernel<4, ENC> (Combined_Geo_Encoding_Volume lookup + convc1)", "bound": "hbm",
+            "achieved": lk_bytes / (lk_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": lk_bytes / (lk_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": tr["dram_bytes"] if tr else None,
+            "traffic_source": tr["source"] if tr else None, "ms_per_launch": lk_ms,
+            "bytes_per_launch": lk_bytes, "peak_source": peaks["source"]}
+
+
+# the BASELINE.json configurations beside the headline one: (key, model, H, W, iters, pairs per GPU, BASELINE wording)
+SECONDARY = [
+    ("igev_cfg3", "igev", 544, 960, 32, 8, "configs[2]: IGEV-Stereo 544x960, 32 iters, batch 8 per GPU"),
+    ("raft_cfg4", "raft", 736, 1280, 32, 8, "configs[3]: RAFT-Stereo 736x1280, 32 iters, batch 64 over 8 GPUs = 8 per GPU"),
+    ("igev_cfg5", "igev", 1024, 1536, 22, 4, "configs[4]: IGEV-Stereo 1024x1536, 22 iters, batch 32 over 8 GPUs = 4 per GPU"),
+]
+
+
+def run_secondary(rank, world, dev, peaks, steps=5):
+    """The other BASELINE configurations, measured after the headline region with the same method (device-resident and
+    end-to-end pairs/s, max over ranks; fixed batch per GPU)."""
+    out = {}
+    for key, kind, H, W, iters, Bg, wording in SECONDARY:
+        res = measure_config(kind, H, W, iters, Bg, steps, 3, rank, world, dev)
+        r = finish_config(res, Bg, H, W, steps, world, dev)
+        entry = {"workload": wording, "metric": "stereo pairs/sec", "unit": "pairs/s", "value": r["value"],
+                 "ms_per_step": r["ms_per_step"], "e2e": r["e2e"], "steps": steps, "warmup": 3,
+                 "global_batch": world * Bg, "n_gpus": world, "dtype": precision_tag(res["model"].engine)}
+        if key == "igev_cfg3":
+            entry["roofline"] = igev_lookup_roofline(res["model"], Bg, H // 4, W // 4, peaks)
+        out[key] = entry
+        del res
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     from dkt_stereo_b200 import _lib as L, ops, parallel
-    from dkt_stereo_b200.raft_stereo import RAFTStereo
-    from dkt_stereo_b200.synthetic import synthetic_pair
 
     rank, local, world = parallel.init_from_env()
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the engine)"
@@ -193,31 +343,9 @@ def run_b200(args):
     H, W, iters, Bg = args.height, args.width, args.iters, args.batch
     h, w = H // 4, W // 4
 
-    torch.manual_seed(0)
-    cfg = dict(RAFT_CFG, corr_implementation="b200" if args.kernels == "tc" else "b200_fp32")
-    model = RAFTStereo(Namespace(mixed_precision=False, extractor_tf32=args.extractor_tf32, **cfg)).eval().to(dev)
-    bcast_bytes = parallel.broadcast_weights(model, src=0)          # the one collective of the path
-
-    # every rank works on its own shard of the global batch (weak scaling: B per GPU fixed)
-    im1_h, im2_h = synthetic_pair(Bg, H, W, seed=1234 + rank)
-    im1_h, im2_h = im1_h.pin_memory(), im2_h.pin_memory()
-    im1_d, im2_d = im1_h.to(dev), im2_h.to(dev)
-
-    def step_device():
-        return model(im1_d, im2_d, iters=iters, test_mode=True)
-
-    # end to end through the public host API: every step uploads ITS pair of pinned host batches (overlapped with
-    # the previous step's compute by HostPipeline) and reads its disparity maps back into pinned host memory
-    from dkt_stereo_b200.pipeline import HostPipeline
-    pipe = HostPipeline(model, iters=iters)
-
-    def step_e2e():
-        return pipe.step((im1_h, im2_h))
-
-    # warm-up (also builds the CUDA graph on the 2nd call)
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    torch.cuda.synchronize()
+    res = measure_config("raft", H, W, iters, Bg, args.steps, args.warmup, rank, world, dev, args.kernels, args.extractor_tf32)
+    model, step_device, bcast_bytes = res["model"], res["step_device"], res["bcast"]
+    im1_h = res["im"][0]
 
     if args.ncu_step:
         # profiler window = exactly one step (ncu --profile-from-start off); nothing is timed or printed
@@ -247,27 +375,15 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-
-    def timed(fn, steps):
-        parallel.barrier()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(steps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        parallel.barrier()
-        return parallel.all_reduce_max(a.elapsed_time(b), dev)
-
-    ms_total = timed(step_device, args.steps)
-    pipe.prefetch(im1_h, im2_h)             # the first batch's upload is the only one outside the timed region ...
-    step_e2e()                              # ... and this untimed step consumes it, so K timed steps = K uploads + K reads
-    ms_e2e = timed(step_e2e, args.steps)
+    r = finish_config(res, Bg, H, W, args.steps, world, dev)
     clocks = sampler.stop() if rank == 0 else None
+    ms_step, value = r["ms_per_step"], r["value"]
 
     # ---- roofline of the dominant kernel: the gru08 z||r gate conv (3x3, 384 -> 256 at 1/4 res) ----
     eng = model.engine
+    dtype_tag = precision_tag(eng) if args.kernels == "tc" else "f32"
+    extractor_desc = ("libdkt tcgen05 convs (EncoderEngine), 3-MMA 16-bit (hi, lo) split" if model.encoder is not None
+                      else "PyTorch cuDNN fp32" + (" (TF32 allowed)" if args.extractor_tf32 else ""))
     P = Bg * h * w
     flops_zr = 2.0 * P * 256 * 9 * 384
     reps = 20
@@ -328,7 +444,7 @@ def run_b200(args):
     # CorrBlock1D.__call__: taps to HBM, fp32 NHWC) and (b) the fused lookup + convc1 the loop runs.
     # bytes per iteration (a) = P * [L*(2r+2)*4 + 4 + L*(2r+1)*4]  
     k2_bytes = P * (4 * 10 * 4 + 4 + 4 * 9 * 4)
-    k2_enc_bytes = P * (4 * 10 * 4 + 4 + 2 * 64 * 2)          # reads + coord, writes 64 ch bf16 hi/lo
+    k2_enc_bytes = P * (4 * 10 * 4 + 4 + (1 if eng.menc2 else 2) * 64 * 2)   # reads + coord, writes 64 ch 16-bit hi [+ lo]
     cx = eng.coords_x.clone()
     lk_out = torch.empty(Bg, h, w, 36, device=dev)
 
@@ -362,99 +478,72 @@ def run_b200(args):
                                "algorithmic bytes because each 40-byte tap run touches 2-3 sectors of its own volume row"},
     }
 
+    # every rank: the fixed-sample checksum (all-gather) and the other BASELINE configurations (barriers inside)
+    ident = fixed_sample_checksum(model, iters, dev, H, W)
+    del res, step_device
+    model = eng = pyr = None
+    torch.cuda.empty_cache()
+    secondary = None if args.no_secondary else run_secondary(rank, world, dev, peaks)
     if rank != 0:
         return
-    # CPU baseline on rank 0 at N=1 only: one pair of the same workload through the oracle port
+    # CPU baseline on rank 0 at N=1 only: one pair of the same workload through the reference's own modules
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         hi = host_info()
-        v, ms = cpu_pairs_per_sec(H, W, iters, 1, 1, 0, hi["cores"] or 1)
-        cpu = {"value": v, "unit": "pairs/s", "cores": hi["cores"], "kind": "port", "cpu": hi["cpu"],
-               "sample": f"1 pair (B=1) of the same {H}x{W}, {iters}-iter workload, 1 run, {ms / 1e3:.1f} s"}
+        _, _, med_ms, kind = cpu_pairs_per_sec(H, W, iters, 1, 3, 1, hi["cores"] or 1)
+        cpu = {"value": 1e3 / med_ms, "unit": "pairs/s", "cores": hi["cores"], "kind": kind, "cpu": hi["cpu"],
+               "sample": f"1 pair (B=1) of the same {H}x{W}, {iters}-iter workload; 1 warm-up + median of 3 runs "
+                         f"({med_ms / 1e3:.1f} s per pair)"}
 
-    ms_step = ms_total / args.steps
-    value = world * Bg * args.steps / (ms_total * 1e-3)
-    e2e_value = world * Bg * args.steps / (ms_e2e * 1e-3)
     top = sorted(breakdown.items(), key=lambda kv: -kv[1][1])[:40]
     total_prof = sum(t for _, t in breakdown.values())
     out = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": precision_tag(eng) if args.kernels == "tc" else "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": dtype_tag, "data": "synthetic",
         "config": {"workload": f"RAFT-Stereo {H}x{W}, {iters} iters, batch {Bg} per GPU (BASELINE configs[1])",
                    "global_batch": world * Bg, "parallelism": f"dp{world} (batch shards, no steady-state collective)",
                    "kernels": args.kernels,
-                   "extractor": ("libdkt tcgen05 convs (EncoderEngine), fp32-grade 3-term bf16 split" if model.encoder is not None
-                                 else "PyTorch cuDNN fp32" + (" (TF32 allowed)" if args.extractor_tf32 else "")),
+                   "extractor": extractor_desc,
                    "cache": "working set per step (470 MB volume + 1.3 GB activations) >> 126 MB L2; no flush needed",
                    "weight_broadcast_bytes": bcast_bytes},
-        "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": 2 * im1_h.numel() * 4, "d2h_bytes_per_step": Bg * H * W * 4},
+        "e2e": r["e2e"],
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline, "roofline_corr": roofline_corr, "cpu_baseline": cpu, "clocks": clocks,
         "breakdown_ms_per_step": {k: round(v[1], 3) for k, v in top},
         "breakdown_total_ms": round(total_prof, 3),
+        "rank_outputs_bit_identical": ident["identical"], "fixed_sample": ident,
+        "secondary": secondary,
     }
     emit(out)
 
 
 def run_b200_igev(args):
-    """Secondary line (BASELINE configs[2]): IGEV-Stereo forward(test_mode=True), pre-loop modules in PyTorch
-    (SURVEY 8f rank 2), Combined_Geo_Encoding_Volume + GRU loop + upsampling on the library's kernels."""
-    from dkt_stereo_b200 import _lib as L, ops, parallel
-    from dkt_stereo_b200.igev_stereo import IGEVStereo
-    from dkt_stereo_b200.synthetic import synthetic_pair
+    """`--model igev`: BASELINE configs[2] as its own line (the default run reports it under `secondary`): IGEV-Stereo
+    forward(test_mode=True); MobileNetV2 pyramid / 2-D stems in PyTorch, everything else on the library's kernels."""
+    from dkt_stereo_b200 import _lib as L, parallel
     rank, local, world = parallel.init_from_env()
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the engine)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     peaks = load_peaks()
     H, W, iters, Bg = args.height, args.width, args.iters, args.batch
-    h, w = H // 4, W // 4
-    torch.manual_seed(0)
-    model = IGEVStereo(Namespace(mixed_precision=False, corr_implementation="b200", **IGEV_CFG)).eval().to(dev)
-    parallel.broadcast_weights(model, src=0)
-    im1_h, im2_h = synthetic_pair(Bg, H, W, seed=1234 + rank)
-    im1_h, im2_h = im1_h.pin_memory(), im2_h.pin_memory()
-    im1_d, im2_d = im1_h.to(dev), im2_h.to(dev)
-
-    def step_device():
-        return model(im1_d, im2_d, iters=iters, test_mode=True)
-
-    def step_e2e():
-        _, up = model(im1_h.to(dev, non_blocking=True), im2_h.to(dev, non_blocking=True), iters=iters, test_mode=True)
-        return up.to("cpu")
-
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    torch.cuda.synchronize()
+    res = measure_config("igev", H, W, iters, Bg, args.steps, args.warmup, rank, world, dev)
+    model, step_device = res["model"], res["step_device"]
+    im1_d, im2_d = res["im"][2:]
     model.use_cuda_graph = False             # count the library's launches on one eager pass
     n0 = L.LAUNCHES
     step_device()
     torch.cuda.synchronize()
     launches_per_step = L.LAUNCHES - n0
     model.use_cuda_graph = True
-
-    def timed(fn, steps):
-        parallel.barrier()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(steps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        parallel.barrier()
-        return parallel.all_reduce_max(a.elapsed_time(b), dev)
-
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    ms_total = timed(step_device, args.steps)
-    ms_e2e = timed(step_e2e, args.steps)
+    r = finish_config(res, Bg, H, W, args.steps, world, dev)
     clocks = sampler.stop() if rank == 0 else None
-    # split: pre-loop (PyTorch) vs hot path (kernels)
+    # split: feature side + volume stage vs hot path
     with torch.no_grad():
         pre = model.prepare(im1_d, im2_d)
         torch.cuda.synchronize()
@@ -466,41 +555,21 @@ def run_b200_igev(args):
         c.record()
         torch.cuda.synchronize()
         pre_ms, hot_ms = a.elapsed_time(b), b.elapsed_time(c)
-    # combined lookup (a5) alone on the volumes of the last step; algorithmic bytes of SURVEY 8d
-    eng = model.engine
-    P = Bg * h * w
-    geo, init = model._vol
-    lk_bytes = P * (2 * 9 * 10 * 4 + 4 + 2 * 64 * 2)            # reads + disparity, writes 64 ch bf16 hi/lo (fused convc1)
-    disp = eng.FLOW["f32"].view(Bg, h, w).clone()
-    for _ in range(3):
-        ops.geo_lookup_enc(geo, init, disp, 4, eng.weights["convc1"], eng.cor1_slice())
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(20):
-        ops.geo_lookup_enc(geo, init, disp, 4, eng.weights["convc1"], eng.cor1_slice())
-    b.record()
-    torch.cuda.synchronize()
-    lk_ms = a.elapsed_time(b) / 20
+    roof = igev_lookup_roofline(model, Bg, H // 4, W // 4, peaks)
     if rank != 0:
         return
     out = {
-        "metric": METRIC + " (IGEV-Stereo)", "value": world * Bg * args.steps / (ms_total * 1e-3), "unit": "pairs/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision_tag(eng), "data": "synthetic",
+        "metric": METRIC + " (IGEV-Stereo)", "value": r["value"], "unit": "pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision_tag(model.engine), "data": "synthetic",
         "config": {"workload": f"IGEV-Stereo {H}x{W}, {iters} iters, batch {Bg} per GPU (BASELINE configs[2])",
                    "global_batch": world * Bg, "parallelism": f"dp{world} (batch shards, no steady-state collective)",
-                   "pre_loop": "PyTorch cuDNN fp32 (MobileNetV2 pyramid, GWC volume, 3-D hourglass): next row of SURVEY 8f",
+                   "pre_loop": "MobileNetV2 pyramid + 2-D stems in PyTorch fp32; context encoder, GWC volume, 3-D hourglass, "
+                               "classifier on libdkt kernels",
                    "cache": "volumes (init-corr 376 MB + GEV 602 MB) >> 126 MB L2; no flush needed"},
-        "e2e": {"value": world * Bg * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": 2 * im1_h.numel() * 4, "d2h_bytes_per_step": Bg * H * W * 4},
-        "gpu_launches": launches_per_step * args.steps,
+        "e2e": r["e2e"], "gpu_launches": launches_per_step * args.steps,
         "split_ms": {"pre_loop (PyTorch MobileNetV2 / stems + libdkt volume stage + context encoder)": pre_ms, "hot_path_kernels": hot_ms},
-        "roofline": {"kernel": "geo_lookup_kernel<4, ENC> (Combined_Geo_Encoding_Volume lookup + convc1)", "bound": "hbm",
-                     "achieved": lk_bytes / (lk_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": lk_bytes / (lk_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": lk_ms,
-                     "bytes_per_launch": lk_bytes, "peak_source": peaks["source"]},
-        "cpu_baseline": None, "clocks": clocks,
+        "roofline": roof, "cpu_baseline": None, "clocks": clocks,
     }
     emit(out)
 
@@ -539,6 +608,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
     ap.add_argument("--extractor-tf32", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configurations (`secondary` map)")
     ap.add_argument("--ncu-step", action="store_true",
                     help="warm up, then run ONE step inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -72,3 +72,13 @@ def shutdown() -> None:
     """Tear the process group down (silences NCCL's leak warning at interpreter exit)."""
     if dist.is_available() and dist.is_initialized():
         dist.destroy_process_group()
+
+
+def all_gather_int(value: int, device) -> list:
+    """Every rank's integer, in rank order (a list of one element without a process group)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [int(value)]
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [int(o.item()) for o in out]

@@ -201,12 +201,15 @@ def golden_igev_forward(m, height=64, width=96, iters=4, tag="igev_fwd_small", b
             super().__init__(f1, f2, gev, **kw)
 
     def pre_hook(mod, args, kwargs):
+        # first call of the update block: the initial hidden states / context terms (slow_fast_gru's extra coarse
+        # updates come first and carry no disparity); first call WITH a disparity: the initial disparity
         if "net0" not in cap:
-            net, inp, _, disp = args[:4]
+            net, inp = args[:2]
             for i in range(3):
                 cap[f"net{i}"] = net[i].clone()
                 cap[f"ctx{i}"] = torch.cat(list(inp[i]), 1).clone()
-            cap["init_disp"] = disp.clone()
+        if "init_disp" not in cap and len(args) > 3 and args[3] is not None:
+            cap["init_disp"] = args[3].clone()
 
     orig_up = model.upsample_disp
 

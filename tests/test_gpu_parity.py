@@ -399,10 +399,10 @@ def test_upsamplers_golden():
 # ---------------------------------------------------------------------------------------------
 # a12: the whole forward(test_mode=True) vs the reference's disparity maps
 # ---------------------------------------------------------------------------------------------
-def _model(impl, g):
+def _model(impl, g, **cfg_over):
     from dkt_stereo_b200.raft_stereo import RAFTStereo
     from dkt_stereo_b200.synthetic import synthetic_state_dict
-    cfg = dict(RAFT_CFG, corr_implementation="b200_fp32" if impl == "simt" else "b200")
+    cfg = dict(RAFT_CFG, corr_implementation="b200_fp32" if impl == "simt" else "b200", **cfg_over)
     model = RAFTStereo(Namespace(mixed_precision=False, **cfg)).eval()
     model.load_state_dict(synthetic_state_dict(golden_shapes(g), seed=golden_seeds(g)[0]), strict=True)
     if impl == "tc_torchenc":          # tensor-core hot path fed by the PyTorch (cuDNN fp32) encoders
@@ -478,6 +478,33 @@ def test_igev_forward_golden(tag, impl, monkeypatch):
         mean, mx = stats(up.cpu(), g["disp_up"])
         print(f"[parity] {tag} impl={impl} rep={rep}: mean-abs {mean:.3e} px, max-abs {mx:.3e} px")
         assert up.shape == (B, 1, H, W) and mean <= 1e-3, (tag, impl, rep, mean, mx)   # north-star gate
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_slow_fast_gru(impl, monkeypatch):
+    """args.slow_fast_gru=True (reference raft_stereo.py:157-160, igev_stereo.py:201-204): per iteration one extra update
+    of the coarsest GRU and one of the two coarse GRUs; against the real reference's outputs with that flag."""
+    from dkt_stereo_b200.synthetic import synthetic_pair, synthetic_state_dict
+    from dkt_stereo_b200.igev_stereo import IGEVStereo
+    g = load_golden("raft_fwd_slowfast")
+    B, H, W, iters = [int(v) for v in g["meta"]]
+    model = _model(impl, g, slow_fast_gru=True)
+    im1, im2 = synthetic_pair(B, H, W, seed=1234, mode=str(g["mode"]))
+    _, up = model(im1.to(dev()), im2.to(dev()), iters=iters, test_mode=True)
+    assert stats(up.cpu(), g["flow_up"])[0] <= 1e-3, stats(up.cpu(), g["flow_up"])
+    _, up0 = _model(impl, g)(im1.to(dev()), im2.to(dev()), iters=iters, test_mode=True)
+    assert stats(up0.cpu(), g["flow_up"])[0] > 1e-2                # without the flag the answer is a different one
+    monkeypatch.setenv("DKT_IMPL", impl)
+    g = load_golden("igev_fwd_slowfast")
+    B, H, W, iters = [int(v) for v in g["meta"]]
+    m = IGEVStereo(Namespace(mixed_precision=False, **dict(IGEV_CFG, slow_fast_gru=True))).eval()
+    m.load_state_dict(synthetic_state_dict(golden_shapes(g), seed=0), strict=False)
+    m = m.to(dev())
+    d = lambda k: g[k].to(dev())
+    with torch.no_grad():
+        up = m.hot_path(d("match_left"), d("match_right"), d("gev"), d("init_disp"),
+                        [d(f"net{i}") for i in range(3)], [d(f"ctx{i}") for i in range(3)], d("stem_2x"), iters)
+    assert stats(up.cpu(), g["disp_up"])[0] <= 1e-3, stats(up.cpu(), g["disp_up"])
 
 
 def test_flow_init_and_batch_independence():

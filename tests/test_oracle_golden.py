@@ -69,6 +69,27 @@ def test_raft_forward_small_and_shift():
         assert stats(lr, g["flow_lr"])[0] < 1e-4
 
 
+def test_slow_fast_gru_schedule():
+    """slow_fast_gru=True (reference raft_stereo.py:157-160, igev_stereo.py:201-204): the extra coarse-GRU updates."""
+    g = load_golden("raft_fwd_slowfast")
+    B, H, W, iters = [int(v) for v in g["meta"]]
+    sd = synthetic_state_dict(golden_shapes(g), seed=0)
+    im1, im2 = synthetic_pair(B, H, W, seed=1234, mode=str(g["mode"]))
+    cfg = dict(RAFT_CFG, slow_fast_gru=True)
+    lr, up = O.raft_forward(sd, im1, im2, iters, cfg)
+    assert stats(up, g["flow_up"])[0] < 1e-4
+    assert stats(O.raft_forward(sd, im1, im2, iters, RAFT_CFG)[1], g["flow_up"])[0] > 1e-2     # the flag matters
+    g = load_golden("igev_fwd_slowfast")
+    B, H, W, iters = [int(v) for v in g["meta"]]
+    sd = synthetic_state_dict(golden_shapes(g), seed=0)
+    net = [g[f"net{i}"] for i in range(3)]
+    inp = [list(g[f"ctx{i}"].split(128, dim=1)) for i in range(3)]
+    with torch.no_grad():
+        up = O.igev_loop(sd, g["match_left"], g["match_right"], g["gev"], g["init_disp"], net, inp,
+                         g["stem_2x"], iters, dict(IGEV_CFG, slow_fast_gru=True))
+    assert stats(up, g["disp_up"])[0] < 1e-4
+
+
 def test_raft_forward_headline_config():
     """The oracle at the benchmark's own resolution and iteration count (544 x 960, 32 iterations, one pair) against
     the real reference's disparity map (tests/golden/raft_fwd_cfg2.npz, oracle/make_golden.py --only raft_cfg2)."""

@@ -35,6 +35,7 @@ def _worker(rank: int, world: int, port: int, q):
     changed = not torch.equal(before, torch.cat([p.detach().reshape(-1) for p in model.update_block.parameters()]))
     mx = parallel.all_reduce_max(10.0 + rank, torch.device("cpu"))
     lo, hi = parallel.shard_range(13, rank, world)
+    assert parallel.all_gather_int(7 * rank + 1, torch.device("cpu")) == [1, 8]      # checksum exchange of bench.py
     parallel.barrier()
     q.put((rank, nbytes, same, changed, mx, lo, hi))
     dist.destroy_process_group()
