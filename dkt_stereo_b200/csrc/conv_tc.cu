@@ -56,11 +56,18 @@ struct TcConvParams {
     int stages;
     uint32_t acc_cols;              // TMEM columns per accumulator stage
     uint32_t acc_stages;            // accumulator stages in TMEM: 2 (N > 128), 4 (N <= 128), 8 (N <= 64)
+    uint32_t acc_lo_off;            // != 0: the lo-term MMAs (x_lo * w_hi, x_hi * w_lo) accumulate in a SECOND accumulator,
+                                    // acc_lo_off columns after the main one; the epilogue adds the two in fp32 (round to
+                                    // nearest).  Why: tcgen05.mma truncates (rounds toward zero) at every accumulate
+                                    // (tools/tc_accum_probe.py: a relative bias of -1.65e-8 per instruction on zero-mean
+                                    // data); keeping the small lo products out of the main accumulator divides the
+                                    // number of truncations it sees by the number of MMAs per K step.
     // patch kernel: one A stage = a (TILE_H + ygroup - 1)-row halo patch serving `ygroup` vertical taps
     int ygroup, a_stages, w_stages;
     uint32_t a_part_bytes;          // bytes of one precision (hi or lo) of an A stage
     uint32_t tmem_cols;
     int a_parts;                    // 2: activations are (hi, lo) pairs, 3 MMAs per K step; 1: hi only, 2 MMAs (x_hi * w_hi + x_hi * w_lo)
+    int b_parts;                    // 2: weights are (hi, lo) pairs; 1: hi only (w_lo == NULL): the x * w_lo MMA is dropped
     int w_resident;                 // pair kernel: the whole filter stays in the W ring (loaded once per CTA)
     uint32_t a_tx_bytes;            // pair kernel: bytes one CTA's TMA loads deliver per A stage (hi + lo boxes)
     int patch_rows;                 // pair kernel, x-major patch: RY = TILE_H + kh - 1 (shared-memory row = x * RY + y)
@@ -310,6 +317,19 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                 tmem_ld16(tbase + c0, v);
 #pragma unroll
                 for (int j = 16; j < 32; ++j) v[j] = 0.f;
+            }
+            if (prm.acc_lo_off) {               // main + lo accumulator, added here in fp32 round-to-nearest
+                float v2[32];
+                if (ncols == 32) {
+                    tmem_ld32(tbase + prm.acc_lo_off + c0, v2);
+                } else {
+                    tmem_ld16(tbase + prm.acc_lo_off + c0, v2);
+#pragma unroll
+                    for (int j = 16; j < 32; ++j) v2[j] = 0.f;
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += v2[j];
             }
             tmem_ld_wait();
             // thread = pixel `lane`: row of 8 x 16 B, chunk j stored at j ^ (lane & 7)
@@ -610,7 +630,7 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
 
     const uint32_t b_bytes = (uint32_t)prm.Npad * ROW;
     const uint32_t a_bytes = (uint32_t)prm.a_parts * A_BYTES;         // hi [+ lo]
-    const uint32_t stage_bytes = a_bytes + 2u * b_bytes;
+    const uint32_t stage_bytes = a_bytes + (uint32_t)prm.b_parts * b_bytes;
     uint8_t* epi_smem = smem + (size_t)prm.stages * stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + TC2_EPI_BYTES);
     uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
@@ -661,7 +681,7 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
                             tma_load_4d(st, &prm.act[s][0], &full_bar[stage], c, xs, ys, b);
                             if (prm.a_parts == 2) tma_load_4d(st + A_BYTES, &prm.act[s][1], &full_bar[stage], c, xs, ys, b);
                             tma_load_2d(st + a_bytes, &prm.wgt[0], &full_bar[stage], kofs + kb * BK, tap * prm.Npad);
-                            tma_load_2d(st + a_bytes + b_bytes, &prm.wgt[1], &full_bar[stage], kofs + kb * BK, tap * prm.Npad);
+                            if (prm.b_parts == 2) tma_load_2d(st + a_bytes + b_bytes, &prm.wgt[1], &full_bar[stage], kofs + kb * BK, tap * prm.Npad);
                         }
                         if (++stage == prm.stages) { stage = 0; phase ^= 1u; }
                     }
@@ -686,12 +706,12 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
                     const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint64_t dah = smem_desc_kmajor<BK>(a_hi), dal = smem_desc_kmajor<BK>(a_hi + A_BYTES);
                     const uint64_t dwh = smem_desc_kmajor<BK>(a_hi + a_bytes), dwl = smem_desc_kmajor<BK>(a_hi + a_bytes + b_bytes);
-                    const bool a_lo = prm.a_parts == 2;
+                    const bool a_lo = prm.a_parts == 2, b_lo = prm.b_parts == 2;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {           // +32 bytes per K16 step = +2 in the address field
                         umma_bf16(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, (it | k) != 0);
-                        if (a_lo) umma_bf16(tmem_d, dal + 2 * k, dwh + 2 * k, idesc, 1u);
-                        umma_bf16(tmem_d, dah + 2 * k, dwl + 2 * k, idesc, 1u);
+                        if (a_lo) umma_bf16(tmem_d + prm.acc_lo_off, dal + 2 * k, dwh + 2 * k, idesc, (prm.acc_lo_off == 0 || (it | k) != 0) ? 1u : 0u);
+                        if (b_lo) umma_bf16(tmem_d + prm.acc_lo_off, dah + 2 * k, dwl + 2 * k, idesc, (prm.acc_lo_off == 0 || a_lo || (it | k) != 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);               // smem slot reusable once these MMAs retire
                 }
@@ -736,7 +756,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const uint32_t a_part = prm.a_part_bytes, a_stage_bytes = (uint32_t)prm.a_parts * prm.a_part_bytes;
-    const uint32_t b_bytes = (uint32_t)prm.Npad * WROW, w_stage_bytes = 2u * b_bytes;
+    const uint32_t b_bytes = (uint32_t)prm.Npad * WROW, w_stage_bytes = (uint32_t)prm.b_parts * b_bytes;
     uint8_t* a_ring = smem;
     uint8_t* w_ring = a_ring + (size_t)prm.a_stages * a_stage_bytes;
     uint8_t* epi_smem = w_ring + (size_t)prm.w_stages * w_stage_bytes;
@@ -800,7 +820,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
                                         mbar_arrive_expect_tx(&wfull[ws], w_stage_bytes);
                                         const int kc = kofs + kb * 64 + wh * WK;
                                         tma_load_2d(wst, &prm.wgt[0], &wfull[ws], kc, tap * prm.Npad);
-                                        tma_load_2d(wst + b_bytes, &prm.wgt[1], &wfull[ws], kc, tap * prm.Npad);
+                                        if (prm.b_parts == 2) tma_load_2d(wst + b_bytes, &prm.wgt[1], &wfull[ws], kc, tap * prm.Npad);
                                     }
                                     if (++ws == prm.w_stages) { ws = 0; wph ^= 1u; }
                                 }
@@ -840,9 +860,10 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
                             const uint64_t dwh = smem_desc_kmajor<WK>(w_hi), dwl = smem_desc_kmajor<WK>(w_hi + b_bytes);
 #pragma unroll
                             for (int k = 0; k < WK / 16; ++k) {   // +32 bytes per K16 step = +2 in the address field
+                                const uint32_t acc_l = prm.acc_lo_off ? accumulate : 1u;      // first lo MMA of a tile overwrites
                                 umma_bf16(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, accumulate);
-                                if (prm.a_parts == 2) umma_bf16(tmem_d, dal + 2 * k, dwh + 2 * k, idesc, 1u);
-                                umma_bf16(tmem_d, dah + 2 * k, dwl + 2 * k, idesc, 1u);
+                                if (prm.a_parts == 2) umma_bf16(tmem_d + prm.acc_lo_off, dal + 2 * k, dwh + 2 * k, idesc, acc_l);
+                                if (prm.b_parts == 2) umma_bf16(tmem_d + prm.acc_lo_off, dah + 2 * k, dwl + 2 * k, idesc, prm.a_parts == 2 ? 1u : acc_l);
                                 accumulate = 1u;
                             }
                             umma_commit(&wempty[ws]);
@@ -902,7 +923,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
     const int Nh = prm.Npad >> 1;                                   // weight rows staged by this CTA
     const uint32_t a_part = prm.a_part_bytes, a_stage_bytes = (uint32_t)prm.a_parts * prm.a_part_bytes;
     constexpr uint32_t KROW = KB * 2;                               // bytes of one K block row (128 or 64) == swizzle span
-    const uint32_t b_bytes = (uint32_t)Nh * KROW, w_stage_bytes = 2u * b_bytes;    // K block of KB channels
+    const uint32_t b_bytes = (uint32_t)Nh * KROW, w_stage_bytes = (uint32_t)prm.b_parts * b_bytes;    // K block of KB channels
     uint8_t* a_ring = smem;
     uint8_t* w_ring = a_ring + (size_t)prm.a_stages * a_stage_bytes;
     uint8_t* epi_smem = w_ring + (size_t)prm.w_stages * w_stage_bytes;
@@ -982,7 +1003,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                                         if (leader) mbar_arrive_expect_tx(&wfull[ws], 2u * w_stage_bytes);
                                         const int kc = kofs + kb * KB;
                                         tma_load_2d_pair(wst, &prm.wgt[0], wfull_l + ws * 8u, kc, tap * prm.Npad + wrow0);
-                                        tma_load_2d_pair(wst + b_bytes, &prm.wgt[1], wfull_l + ws * 8u, kc, tap * prm.Npad + wrow0);
+                                        if (prm.b_parts == 2) tma_load_2d_pair(wst + b_bytes, &prm.wgt[1], wfull_l + ws * 8u, kc, tap * prm.Npad + wrow0);
                                     }
                                 }
                                 if (++ws == prm.w_stages) { ws = 0; wph ^= 1u; }
@@ -1004,7 +1025,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
             for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
             const int a_steps = kb_total * kx_n * ygroups;
             const uint32_t sbo = XMT ? (uint32_t)prm.patch_rows * KROW : 8u * KROW;      // bytes between 8-row atoms of A
-            const bool a_lo = prm.a_parts == 2;
+            const bool a_lo = prm.a_parts == 2, b_lo = prm.b_parts == 2;
             bool first = true;
             for (int item = pair_id; item < items; item += pairs) {
                 mbar_wait(&tmem_empty_bar[acs], aphase ^ 1u);     // both CTAs' epilogues drained this accumulator
@@ -1033,9 +1054,10 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                             const uint64_t dwh = smem_desc_kmajor<KB>(w_hi), dwl = smem_desc_kmajor<KB>(w_hi + b_bytes);
 #pragma unroll
                             for (int k = 0; k < KB / 16; ++k) {   // +32 bytes per K16 step = +2 in the address field
+                                const uint32_t acc_l = prm.acc_lo_off ? accumulate : 1u;      // first lo MMA of a tile overwrites
                                 umma_bf16_pair(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, accumulate);
-                                if (a_lo) umma_bf16_pair(tmem_d, dal + 2 * k, dwh + 2 * k, idesc, 1u);
-                                umma_bf16_pair(tmem_d, dah + 2 * k, dwl + 2 * k, idesc, 1u);
+                                if (a_lo) umma_bf16_pair(tmem_d + prm.acc_lo_off, dal + 2 * k, dwh + 2 * k, idesc, acc_l);
+                                if (b_lo) umma_bf16_pair(tmem_d + prm.acc_lo_off, dah + 2 * k, dwl + 2 * k, idesc, a_lo ? 1u : acc_l);
                                 accumulate = 1u;
                             }
                             if (!prm.w_resident) umma_commit_pair(&wempty[ws]);
@@ -1195,7 +1217,7 @@ static int launch_conv(ConvFamily fam, const TcConvParams& prm, unsigned grid, s
 extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t* w_hi, const uint16_t* w_lo,
                                 int kh, int kw, int stride, int N, const dkt_epilogue* epi,
                                 int B, int Hin, int Win, int H, int W, void* stream) {
-    DKT_CHECK_ARG(srcs && w_hi && w_lo && epi);
+    DKT_CHECK_ARG(srcs && w_hi && epi);
     DKT_CHECK_ARG(nsrc >= 1 && nsrc <= DKT_MAX_SRCS);
     DKT_CHECK_ARG(B > 0 && H > 0 && W > 0 && Hin > 0 && Win > 0 && N > 0);
     if (kh < 1 || kw < 1 || kh > 7 || kw > 7 || !(kh & 1) || !(kw & 1)) return DKT_E_UNSUPPORTED;
@@ -1241,6 +1263,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     for (int s = 0; s < nsrc; ++s) n_lo += srcs[s].lo != nullptr;
     if (n_lo != 0 && n_lo != nsrc) return DKT_E_INVALID;
     const uint32_t AP = n_lo ? 2u : 1u;
+    const uint32_t BP = w_lo ? 2u : 1u;             // w_lo == NULL: single-plane weights (x * w_lo MMA dropped)
     const uint32_t budget = 227u * 1024u - 1024u /*align*/ - TC2_EPI_BYTES - TC_BAR_BYTES;
 
     // ring geometry of the row-patch kernel
@@ -1265,7 +1288,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     if (xm && (patch_ry > 256 || patch_rx > 256)) use_pair = false;
     const uint32_t pair_a_part_bytes = xm ? (xm_box_bytes + 1023u) & ~1023u : a_part_bytes;
     int p_a_stages = 2, p_w_stages = 0, p_resident = 0;
-    const uint32_t p_w_stage_bytes = 2u * (uint32_t)(Npad / 2) * (uint32_t)KBLK * 2u;
+    const uint32_t p_w_stage_bytes = BP * (uint32_t)(Npad / 2) * (uint32_t)KBLK * 2u;
     if (use_pair) {
         const int w_steps = (cin_sum / KBLK) * kh * kw;            // weight blocks per tile
         if (AP * pair_a_part_bytes * 2 >= budget) use_pair = false;
@@ -1287,7 +1310,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     }
 
     const int WK = (Npad > 128) ? 32 : 64;
-    const uint32_t w_stage_bytes = 2u * (uint32_t)Npad * (uint32_t)WK * 2u;
+    const uint32_t w_stage_bytes = BP * (uint32_t)Npad * (uint32_t)WK * 2u;
     int a_stages = 2, w_stages = 0;
     bool use_patch = s_patch != 0;
     if (use_patch && !use_pair) {
@@ -1311,6 +1334,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     TcConvParams prm{};
     prm.nsrc = nsrc;
     prm.a_parts = (int)AP;
+    prm.b_parts = (int)BP;
     int cin_total = 0;
     for (int s = 0; s < nsrc; ++s) {
         const dkt_tensor& t = srcs[s];
@@ -1348,7 +1372,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         const uint32_t box[2] = {(uint32_t)WBK, (uint32_t)wbox_rows};
         if (!aligned16(w_hi) || !aligned16(w_lo)) return DKT_E_ALIGNMENT;
         if (!make_tmap_bf16(&prm.wgt[0], w_hi, 2, dims, strides, box, WBK * 2)) return DKT_E_DRIVER;
-        if (!make_tmap_bf16(&prm.wgt[1], w_lo, 2, dims, strides, box, WBK * 2)) return DKT_E_DRIVER;
+        if (!make_tmap_bf16(&prm.wgt[1], w_lo ? w_lo : w_hi, 2, dims, strides, box, WBK * 2)) return DKT_E_DRIVER;
     }
     prm.H = H;
     prm.W = W;
@@ -1359,6 +1383,17 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     prm.num_tiles = (int)tiles;
     uint32_t cols = 32;
     while (cols < (uint32_t)prm.Npad) cols <<= 1;
+    {
+        // second accumulator for the lo products (see TcConvParams::acc_lo_off) whenever two stages of two accumulators
+        // fit the 512 TMEM columns, i.e. N <= 128; LINEAR / GRU epilogues only (PROJ keeps its own tile walk).
+        // DKT_ACC_SPLIT=0 restores the single accumulator (A/B knob).
+        static const int s_split = [] { const char* v = getenv("DKT_ACC_SPLIT"); return (v && v[0] == '0') ? 0 : 1; }();
+        const bool lo_mmas = AP == 2 || BP == 2;
+        if (s_split && lo_mmas && cols <= 128 && e.kind != DKT_EPI_PROJ) {
+            prm.acc_lo_off = cols;
+            cols *= 2;
+        }
+    }
     prm.acc_cols = cols;
     prm.acc_stages = 512u / cols > (uint32_t)TC_MAX_ACC ? (uint32_t)TC_MAX_ACC : 512u / cols;
     {
@@ -1400,7 +1435,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         return launch_conv(WK == 32 ? FAM_PATCH32 : FAM_PATCH64, prm, grid, smem_bytes, (cudaStream_t)stream);
     }
     // per-tap kernel: the ring takes what the epilogue buffers and barriers leave of the 227 KB
-    const uint32_t stage_bytes = AP * 128u * (uint32_t)BK * 2u + 2u * (uint32_t)prm.Npad * (uint32_t)BK * 2u;
+    const uint32_t stage_bytes = AP * 128u * (uint32_t)BK * 2u + BP * (uint32_t)prm.Npad * (uint32_t)BK * 2u;
     int stages = (int)(budget / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) return DKT_E_UNSUPPORTED;

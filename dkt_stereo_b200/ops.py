@@ -447,7 +447,7 @@ def conv2d_ex(srcs: Sequence[DktTensor], w: ConvWeights, epi: DktEpilogue, B: in
     n = len(srcs)
     arr = (DktTensor * n)(*srcs)
     assert sum(t.c_count for t in srcs) == w.cin, (sum(t.c_count for t in srcs), w.cin)
-    L.check(lib.dkt_conv2d_tc_ex(arr, n, w.w_hi.data_ptr(), w.w_lo.data_ptr(), kh, kw, s, w.n, C.byref(epi),
+    L.check(lib.dkt_conv2d_tc_ex(arr, n, w.w_hi.data_ptr(), L.ptr(w.w_lo), kh, kw, s, w.n, C.byref(epi),
                                  B, Hin, Win, H, W, L.stream_ptr()), "conv2d_tc_ex")
     return H, W
 
@@ -514,7 +514,8 @@ def conv2d(srcs: Sequence[DktTensor], w: ConvWeights, epi: DktEpilogue, B: int, 
     cin = sum(s.c_count for s in srcs)
     assert cin == w.cin, (cin, w.cin)
     if impl == "tc":
-        L.check(lib.dkt_conv2d_tc(arr, n, w.w_hi.data_ptr(), w.w_lo.data_ptr(), w.ksize, w.n, C.byref(epi),
+        # w.w_lo None = single-plane weights: the x * w_lo MMA is dropped
+        L.check(lib.dkt_conv2d_tc(arr, n, w.w_hi.data_ptr(), L.ptr(w.w_lo), w.ksize, w.n, C.byref(epi),
                                   B, H, W, L.stream_ptr()), "conv2d_tc")
     else:
         L.check(lib.dkt_conv2d_simt(arr, n, w.w_simt.data_ptr(), w.ksize, w.n, C.byref(epi),

@@ -126,6 +126,10 @@ class UpdateEngine:
         half = impl == "tc" and L.split_dtype() == torch.float16
         self.gru2 = half and os.environ.get("DKT_GRU_TERMS", "2") == "2"
         self.menc2 = half and os.environ.get("DKT_MENC_TERMS", "2") == "2"
+        # the two COARSE GRUs (1/8 and 1/16 resolution) with ONE MMA per K step: half activations x half weights (the
+        # study's h_x1_w1 row: +5e-5 px for this group; every other group needs its weights as a pair).  Measured on
+        # B200 against the reference goldens (profiles/r2f_parity_accsplit.txt): +0.2..0.5e-4 px, -3 % step time.
+        self.coarse1 = self.gru2 and os.environ.get("DKT_COARSE_GRU_TERMS", "1") == "1"
         self.side_stream = None
         self.weights: Optional[Dict[str, ops.ConvWeights]] = None
         self._wsig = None
@@ -157,6 +161,8 @@ class UpdateEngine:
             g = getattr(b, name)
             w[f"zr{i}"] = ops.pack_conv_cat([g.convz.weight, g.convr.weight], tc=tc)
             w[f"q{i}"] = ops.pack_conv(g.convq.weight, None, tc=tc)
+            if self.coarse1 and i > 0:
+                w[f"zr{i}"].w_lo = w[f"q{i}"].w_lo = None
             self.gru_bias.append(torch.cat([g.convz.bias, g.convr.bias, g.convq.bias]).detach().float().contiguous())
         head = b.disp_head if self.igev else b.flow_head
         w["head1"] = ops.pack_conv(head.conv1.weight, head.conv1.bias, tc=tc)

@@ -20,7 +20,8 @@
  *     bits, hi + lo = 22) or bfloat16 (-DDKT_SPLIT_FP16=0; 8 / 16 bits).  Products are accumulated
  *     in fp32 as  hi*hi + lo*hi + hi*lo  (3 MMAs per K step; every tensor with both planes) or, for a
  *     conv whose SOURCE tensors are passed with lo == NULL, as  hi*w_hi + hi*w_lo  (2 MMAs: half
- *     activations against full-precision weights).  Which convs may run with 2 is a property of the
+ *     activations against full-precision weights); w_lo == NULL additionally drops the w_lo product
+ *     (1 MMA: plain half x half).  Which convs may run with 2 is a property of the
  *     network, measured in profiles/r2_precision_study_*.txt; the engine in dkt_stereo_b200/update.py
  *     makes that choice, this library only executes it.
  *   - 16-bit values are passed as uint16_t ("bf16" in entry-point names is historical: it means

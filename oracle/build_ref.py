@@ -3,8 +3,9 @@ where they lie under /root/reference, into oracle/_ref/ (git-ignored; travels to
 the repo's own built .so).
 
 The reference is pure Python, so "compiling" is ``py_compile``: every module RAFTStereo.forward / IGEVStereo.forward
-imports is translated to a sourceless ``.pyc`` that keeps the package layout (``meta_arch/raft_stereo/raft_stereo.pyc``
-...).  No reference source text enters the repository or oracle/_ref/; the bytecode is the UNMODIFIED reference and is
+imports is translated to sourceless bytecode that keeps the package layout (``meta_arch/raft_stereo/raft_stereo.rpyc`` ...; the
+extension is not ``.pyc`` because repository snapshots drop ``*.pyc`` files -- a small meta-path finder below imports
+them).  No reference source text enters the repository or oracle/_ref/; the bytecode is the UNMODIFIED reference and is
 what ``bench.py --impl reference`` times on the GPU box's host cores (``cpu_baseline.kind = "reference"``).  The GPU
 box has the same image, hence the same CPython: the .pyc magic matches (``load()`` falls back to the oracle port and
 says so if it does not).
@@ -17,6 +18,8 @@ oracle/make_golden.py does for the real sources).
 from __future__ import annotations
 
 import importlib
+import importlib.abc
+import importlib.machinery
 import importlib.util
 import os
 import py_compile
@@ -26,6 +29,7 @@ import types
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("DKT_REFERENCE", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
+EXT = ".rpyc"
 
 # modules on the import path of meta_arch.{raft_stereo.raft_stereo, igev_stereo.igev_stereo} (package __init__ files of
 # meta_arch itself are NOT staged: they pull the training-side families and timm)
@@ -47,7 +51,7 @@ def build() -> int:
     n = 0
     for rel in MODULES:
         src = os.path.join(REF, rel)
-        dst = os.path.join(OUT, rel[:-3] + ".pyc")
+        dst = os.path.join(OUT, rel[:-3] + EXT)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         if os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(src):
             continue
@@ -58,7 +62,22 @@ def build() -> int:
 
 
 def available() -> bool:
-    return os.path.exists(os.path.join(OUT, "meta_arch", "raft_stereo", "raft_stereo.pyc"))
+    return os.path.exists(os.path.join(OUT, "meta_arch", "raft_stereo", "raft_stereo" + EXT))
+
+
+class _RefFinder(importlib.abc.MetaPathFinder):
+    """Maps a dotted module name onto oracle/_ref/<path>.rpyc (or <path>/__init__.rpyc) and loads it as bytecode."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        rel = os.path.join(OUT, *fullname.split("."))
+        init = os.path.join(rel, "__init__" + EXT)
+        if os.path.exists(init):
+            return importlib.util.spec_from_file_location(
+                fullname, init, loader=importlib.machinery.SourcelessFileLoader(fullname, init), submodule_search_locations=[rel])
+        if os.path.exists(rel + EXT):
+            return importlib.util.spec_from_file_location(
+                fullname, rel + EXT, loader=importlib.machinery.SourcelessFileLoader(fullname, rel + EXT))
+        return None
 
 
 def _stub(name: str, path=None, **attrs):
@@ -78,8 +97,8 @@ def load(model: str = "raft"):
     if not available():
         raise ImportError("oracle/_ref is empty: run `python -m oracle.build_ref` where /root/reference exists")
     sys.dont_write_bytecode = True
-    if OUT not in sys.path:
-        sys.path.insert(0, OUT)
+    if not any(isinstance(f, _RefFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _RefFinder())
     _stub("meta_arch", os.path.join(OUT, "meta_arch"))
     _stub("meta_arch.raft_stereo", os.path.join(OUT, "meta_arch", "raft_stereo"))
     _stub("meta_arch.igev_stereo", os.path.join(OUT, "meta_arch", "igev_stereo"))

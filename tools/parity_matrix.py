@@ -18,6 +18,9 @@ LIB = os.path.join(ROOT, "dkt_stereo_b200", "lib")
 
 POLICIES = [
     ("f16: GRUs 2 MMA, motion enc 2 MMA (default)", {}),
+    ("f16: fine GRU 2 MMA, coarse GRUs 1 MMA, motion enc 2 MMA", {"DKT_COARSE_GRU_TERMS": "1"}),
+    ("f16 default, single accumulator (DKT_ACC_SPLIT=0)", {"DKT_ACC_SPLIT": "0"}),
+    ("f16: coarse GRUs 1 MMA, single accumulator", {"DKT_COARSE_GRU_TERMS": "1", "DKT_ACC_SPLIT": "0"}),
     ("f16: GRUs 2 MMA, motion enc 3 MMA", {"DKT_MENC_TERMS": "3"}),
     ("f16: GRUs 3 MMA, motion enc 2 MMA", {"DKT_GRU_TERMS": "3"}),
     ("f16: everything 3 MMA", {"DKT_GRU_TERMS": "3", "DKT_MENC_TERMS": "3"}),
@@ -62,8 +65,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-bench", action="store_true")
     ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--only", type=int, nargs="*", default=None, help="indices into POLICIES")
     a = ap.parse_args()
-    for name, env in POLICIES:
+    for idx, (name, env) in enumerate(POLICIES):
+        if a.only is not None and idx not in a.only:
+            continue
         e = dict(os.environ, **env)
         if "DKT_STEREO_LIB" in env and not os.path.exists(env["DKT_STEREO_LIB"]):
             print(f"{name}: variant library not built, skipped")
@@ -79,7 +85,7 @@ def main():
             print(f"   {tag:22s} mean |d - ref| {mean:.3e} px   max {mx:.3e} px   (gate 1e-3 mean)")
         if not a.no_bench:
             b = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(a.steps), "--warmup", "3",
-                                "--no-cpu-baseline"], env=e, capture_output=True, text=True)
+                                "--no-cpu-baseline", "--no-secondary"], env=e, capture_output=True, text=True)
             try:
                 d = json.loads([ln for ln in b.stdout.splitlines() if ln.startswith("{")][-1])
                 bd = d["breakdown_ms_per_step"]
