@@ -4,8 +4,9 @@ Every class keeps the reference call shape (reference meta_arch/raft_stereo/raft
 ``Block(fmap1, fmap2, num_levels=, radius=)`` then ``block(coords (B,2,h,w)) -> (B, L*(2r+1), h, w)``.
 
 * ``B200CorrBlock1D``      replaces ``CorrBlock1D`` (reference core/corr.py:110-156)
-* ``corr_sampler_forward`` replaces the un-vendored ``corr_sampler.forward`` extension that
-  ``CorrBlockFast1D`` binds (reference core/corr.py:17-29,49): ``(volume, coords, radius) -> (out,)``
+* ``corr_sampler_forward`` / ``corr_sampler_backward`` / ``CorrSampler`` replace the un-vendored ``corr_sampler``
+  extension that ``CorrBlockFast1D`` binds (reference core/corr.py:17-29,49): ``forward(volume, coords, radius) ->
+  (out,)``, ``backward(volume, coords, grad_output, radius) -> (grad_volume,)``
 """
 from __future__ import annotations
 
@@ -45,6 +46,38 @@ def corr_sampler_forward(volume: torch.Tensor, coords: torch.Tensor, radius: int
     out = torch.empty(B, 2 * radius + 1, H, W1, device=volume.device, dtype=torch.float32)
     ops.corr1d_lookup([volume.contiguous().float()], coords[:, 0].contiguous().float(), radius, out, out_layout="nchw")
     return (out,)
+
+
+def corr_sampler_backward(volume: torch.Tensor, coords: torch.Tensor, grad_output: torch.Tensor,
+                          radius: int) -> Tuple[torch.Tensor]:
+    """Drop-in for ``corr_sampler.backward`` (reference core/corr.py:25-29): volume (B,H,W1,W2_l), coords (B,1,H,W1),
+    grad_output (B, 2r+1, H, W1)  ->  (grad_volume (B,H,W1,W2_l),).  Only the volume's SHAPE is used."""
+    L.require_device(grad_output)
+    B, H, W1, W2 = volume.shape
+    assert grad_output.shape == (B, 2 * radius + 1, H, W1), grad_output.shape
+    g = grad_output.contiguous().float()
+    cx = coords[:, 0].contiguous().float()
+    grad_volume = torch.empty(B, H, W1, W2, device=g.device, dtype=torch.float32)
+    L.check(L.load().dkt_corr1d_lookup_backward(g.data_ptr(), cx.data_ptr(), radius, grad_volume.data_ptr(),
+                                                B, H, W1, W2, L.stream_ptr()), "corr1d_lookup_backward")
+    return (grad_volume,)
+
+
+class CorrSampler(torch.autograd.Function):
+    """The reference's autograd wrapper (core/corr.py:17-29) on this library's two kernels."""
+
+    @staticmethod
+    def forward(ctx, volume, coords, radius):
+        ctx.save_for_backward(volume, coords)
+        ctx.radius = radius
+        corr, = corr_sampler_forward(volume, coords, radius)
+        return corr
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        volume, coords = ctx.saved_tensors
+        grad_volume, = corr_sampler_backward(volume, coords, grad_output.contiguous(), ctx.radius)
+        return grad_volume, None, None
 
 
 class Combined_Geo_Encoding_Volume:

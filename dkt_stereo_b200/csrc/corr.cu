@@ -514,6 +514,53 @@ extern "C" int dkt_corr1d_lookup_enc(const float* const* pyr, int levels, int ra
     return corr1d_lookup_launch(pyr, levels, radius, coords_x, delta, delta_C, flow, o, true, true, B, H, W1, W2, stream);
 }
 
+// ---- adjoint of the one-level lookup: corr_sampler.backward (reference core/corr.py:25-29) ----
+// out[k] = (1-a) v[x0+k-r] + a v[x0+k-r+1]  =>  grad_v[j] = (1-a) g[j-x0+r] + a g[j-x0+r-1] (terms whose tap index falls
+// outside [0, 2r] vanish).  One warp per (b, y, x1) row of the volume; lanes stride over W2, so every row is written in
+// full, coalesced, zeros included -- no memset and no atomics (each row has exactly one owner).
+__global__ void __launch_bounds__(256)
+corr1d_lookup_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ coords_x, float* __restrict__ grad_vol,
+                         int radius, int64_t rows, int HW, int W2) {
+    const int lane = threadIdx.x & 31;
+    const int taps = 2 * radius + 1;
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+         row += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const float x = coords_x[row];
+        const bool finite = fabsf(x) < 1.0e9f;                 // also false for NaN
+        const float xf = floorf(finite ? x : 0.f);
+        const float a = finite ? x - xf : 0.f;
+        const int x0 = (int)xf;
+        const int64_t b = row / HW, p = row - b * HW;
+        // grad_out is (B, taps, H, W1): tap k of this row sits HW elements after tap k-1
+        float g = 0.f;
+        if (finite && lane < taps) g = __ldg(grad_out + (b * taps + lane) * HW + p);
+        float* dst = grad_vol + row * W2;
+        for (int j0 = 0; j0 < W2; j0 += 32) {
+            const int j = j0 + lane;
+            const int k = j - x0 + radius;                     // tap whose LEFT sample is j
+            const float g0 = __shfl_sync(0xffffffffu, g, k & 31);
+            const float g1 = __shfl_sync(0xffffffffu, g, (k - 1) & 31);
+            float v = 0.f;
+            if (k >= 0 && k < taps) v = (1.f - a) * g0;
+            if (k - 1 >= 0 && k - 1 < taps) v = fmaf(a, g1, v);
+            if (j < W2) dst[j] = v;
+        }
+    }
+}
+
+extern "C" int dkt_corr1d_lookup_backward(const float* grad_out, const float* coords_x, int radius, float* grad_volume,
+                                          int B, int H, int W1, int W2, void* stream) {
+    DKT_CHECK_ARG(grad_out && coords_x && grad_volume);
+    DKT_CHECK_ARG(B > 0 && H > 0 && W1 > 0 && W2 > 0);
+    if (radius < 0 || 2 * radius + 1 > 32) return DKT_E_UNSUPPORTED;
+    const int64_t rows = (int64_t)B * H * W1;
+    if ((int64_t)H * W1 > 0x7fffffff) return DKT_E_UNSUPPORTED;
+    const int64_t blocks = ceil_div64(rows, 8), cap = (int64_t)device_sms() * 16;
+    corr1d_lookup_bwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        grad_out, coords_x, grad_volume, radius, rows, H * W1, W2);
+    DKT_RETURN_LAST();
+}
+
 extern "C" int dkt_geo_pool(const float* gev, float* geo0, float* geo1, int B, int C, int D, int H, int W,
                             void* stream) {
     DKT_CHECK_ARG(gev && geo0 && geo1);

@@ -87,6 +87,15 @@ class IGEVStereo(nn.Module):
             if isinstance(m, nn.BatchNorm2d):
                 m.eval()
 
+    def invalidate_weights(self) -> None:
+        """Force a repack of the engine's weights (and with it the re-capture of the CUDA graphs) on the next forward.
+        `load_state_dict`, optimizer steps and `p.data = ...` assignments (the EMA teacher of reference
+        tools/ft_dkt.py:179-181) are noticed automatically through (data_ptr, version) of every parameter; in-place
+        edits THROUGH `.data` (`p.data.mul_(...)`) change neither and need this call."""
+        self.engine._wsig = None
+        if self.encoder is not None:
+            self.encoder._sig = None
+
     # ---- pre-loop (PyTorch): reference igev_stereo.py:154-189 -------------------------------------
     def prepare(self, image1: torch.Tensor, image2: torch.Tensor):
         """-> match_left, match_right (B,96,h,w), geo_encoding_volume (B,8,D,h,w), init_disp (B,1,h,w),

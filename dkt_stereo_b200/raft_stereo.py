@@ -100,6 +100,15 @@ class RAFTStereo(nn.Module):
             if isinstance(m, nn.BatchNorm2d):
                 m.eval()
 
+    def invalidate_weights(self) -> None:
+        """Force a repack of the engine's weights (and with it the re-capture of the CUDA graphs) on the next forward.
+        `load_state_dict`, optimizer steps and `p.data = ...` assignments (the EMA teacher of reference
+        tools/ft_dkt.py:179-181) are noticed automatically through (data_ptr, version) of every parameter; in-place
+        edits THROUGH `.data` (`p.data.mul_(...)`) change neither and need this call."""
+        self.engine._wsig = None
+        if self.encoder is not None:
+            self.encoder._sig = None
+
     # ---- L1: extractors (PyTorch) ---------------------------------------------------------------
     def extract(self, image1: torch.Tensor, image2: torch.Tensor):
         """reference raft_stereo.py:91-116 -> fmap1, fmap2, net_list, ctx_list (cz|cr|cq concatenated)."""

@@ -170,6 +170,16 @@ int dkt_corr1d_lookup_enc(const float* const* pyr, int levels, int radius,
                           const float* enc_w, const float* enc_b, const dkt_tensor* enc_out,
                           int B, int H, int W1, int W2, void* stream);
 
+/* Adjoint of the ONE-level lookup with respect to the volume: replaces corr_sampler.backward(volume, coords,
+ * grad_output, radius) -> (grad_volume,) of the un-vendored extension the reference binds in CorrSampler.backward
+ * (reference core/corr.py:25-29; used only when corr_implementation = "reg_cuda" is trained).
+ *   grad_out    : (B, 2r+1, H, W1) fp32 contiguous -- gradient of the (B, 2r+1, H, W1) tap tensor
+ *   coords_x    : (B, H, W1) fp32 -- the x coordinates of the forward call (already divided by 2^level)
+ *   grad_volume : (B, H, W1, W2) fp32 contiguous -- written in full (zeros where no tap landed)
+ * No gradient flows to the coordinates (the reference returns None for them too). */
+int dkt_corr1d_lookup_backward(const float* grad_out, const float* coords_x, int radius, float* grad_volume,
+                               int B, int H, int W1, int W2, void* stream);
+
 /* ---- IGEV: geometry-encoding-volume pyramid + combined lookup ------------------------------
  * dkt_geo_pool: (B,C,D,H,W) fp32 -> level 0 (B,H,W,C,D) and level 1 (B,H,W,C,D/2)
  *   (reference meta_arch/igev_stereo/geometry.py:17-26; levels == 2 as in configs/igev_stereo).

@@ -111,6 +111,32 @@ def test_corr1d_lookup_golden(tag):
     assert stats(o1.cpu(), g["out"][:, 9 * lvl:9 * (lvl + 1)])[1] < 2e-5
 
 
+@pytest.mark.parametrize("shape", [(2, 5, 40, 40, 4), (1, 3, 53, 26, 4), (1, 2, 33, 70, 2)])
+def test_corr_sampler_backward_vs_autograd(shape):
+    """corr_sampler.backward (reference core/corr.py:25-29): the gradient of the one-level lookup with respect to the
+    volume, against autograd through the oracle's differentiable restatement of the same lookup (fp64)."""
+    from dkt_stereo_b200.corr import CorrSampler, corr_sampler_backward
+    from oracle import hotpath as O
+    B, H, W1, W2, r = shape
+    g = torch.Generator().manual_seed(W1 + W2)
+    vol = torch.randn(B, H, W1, W2, generator=g)
+    cx = torch.rand(B, 1, H, W1, generator=g) * (W2 + 12) - 6             # some taps out of range on both sides
+    cx[0, 0, 0, :4] = torch.tensor([-1.0, 0.0, W2 - 1.0, float(W2)])
+    gout = torch.randn(B, 2 * r + 1, H, W1, generator=g)
+    v64 = vol.double().requires_grad_(True)
+    out = O.corr1d_lookup([v64], cx[:, 0].double(), r)
+    out.backward(gout.double())
+    (gv,) = corr_sampler_backward(vol.to(dev()), cx.to(dev()), gout.to(dev()), r)
+    assert gv.shape == vol.shape
+    assert stats(gv.cpu(), v64.grad.float())[1] < 1e-5, stats(gv.cpu(), v64.grad.float())
+    # the autograd wrapper the reference defines (CorrSampler.apply) end to end
+    vd = vol.to(dev()).requires_grad_(True)
+    o = CorrSampler.apply(vd, cx.to(dev()), r)
+    assert stats(o.detach().cpu(), out.detach().float())[1] < 2e-5
+    o.backward(gout.to(dev()))
+    assert stats(vd.grad.cpu(), v64.grad.float())[1] < 1e-5
+
+
 def test_lookup_fused_coordinate_update():
     """delta add + flow bookkeeping fused in front of the gather (raft_stereo.py:154-155,164-167)."""
     from dkt_stereo_b200 import ops
@@ -289,10 +315,10 @@ def _run_update(tag, igev, impl, terms=2, monkeypatch=None):
     policy -- see UpdateEngine.gru2 / coarse1)."""
     from dkt_stereo_b200.update import BasicMultiUpdateBlock, UpdateEngine
     if monkeypatch is not None:
+        monkeypatch.setenv("DKT_COARSE_GRU_TERMS", "1" if terms == 1 else "2")
+        terms = max(terms, 2)
         monkeypatch.setenv("DKT_GRU_TERMS", str(terms))
         monkeypatch.setenv("DKT_MENC_TERMS", str(terms))
-        monkeypatch.setenv("DKT_COARSE_GRU_TERMS", "1" if terms == 1 else "2")
-        terms = min(max(terms, 2), 3)
     from dkt_stereo_b200.synthetic import synthetic_state_dict
     from dkt_stereo_b200 import ops
     g = load_golden(f"update_{tag}")
@@ -516,6 +542,40 @@ def test_slow_fast_gru(impl, monkeypatch):
         up = m.hot_path(d("match_left"), d("match_right"), d("gev"), d("init_disp"),
                         [d(f"net{i}") for i in range(3)], [d(f"ctx{i}") for i in range(3)], d("stem_2x"), iters)
     assert stats(up.cpu(), g["disp_up"])[0] <= 1e-3, stats(up.cpu(), g["disp_up"])
+
+
+def test_serves_frozen_and_ema_teacher():
+    """The two teacher passes of the reference's fine-tuning step (tools/ft_dkt.py:179-199): DataParallel-wrapped,
+    frozen, `model_T(image1, image2, iters, test_mode=True)`; the EMA teacher's parameters are REASSIGNED every step.
+    The engine must follow the weights (repack + new CUDA graph) and give exactly what a freshly loaded model gives."""
+    from dkt_stereo_b200.raft_stereo import RAFTStereo
+    from dkt_stereo_b200.synthetic import synthetic_pair, synthetic_state_dict
+    g = load_golden("raft_fwd_small")
+    shapes = golden_shapes(g)
+    ns = Namespace(mixed_precision=False, **dict(RAFT_CFG, corr_implementation="b200"))
+    teacher = torch.nn.DataParallel(RAFTStereo(ns), device_ids=[0])
+    teacher.load_state_dict({"module." + k: v for k, v in synthetic_state_dict(shapes, seed=0).items()}, strict=True)
+    teacher.cuda()
+    for p in teacher.parameters():
+        p.requires_grad = False
+    teacher.eval()
+    teacher.module.freeze_bn()
+    student_sd = synthetic_state_dict(shapes, seed=5)
+    im1, im2 = synthetic_pair(2, 64, 96, seed=3)
+    im1, im2 = im1.to(dev()), im2.to(dev())
+    outs = [teacher(im1, im2, iters=3, test_mode=True)[1].clone() for _ in range(3)]     # eager, capture, replay
+    assert torch.equal(outs[0], outs[2])
+    ema = 0.5
+    for (name, t_params) in teacher.module.named_parameters():
+        t_params.data = (ema * t_params.data + (1 - ema) * student_sd[name].to(dev()))
+        t_params.requires_grad = False
+    after = [teacher(im1, im2, iters=3, test_mode=True)[1].clone() for _ in range(3)]
+    assert float((after[0] - outs[0]).abs().mean()) > 1e-3                 # the new weights are in use ...
+    assert torch.equal(after[0], after[2])                                 # ... also in the re-captured graph
+    fresh = RAFTStereo(ns).eval()
+    fresh.load_state_dict({k: v.detach().cpu() for k, v in teacher.module.state_dict().items()}, strict=True)
+    _, want = fresh.to(dev())(im1, im2, iters=3, test_mode=True)
+    assert torch.equal(after[0], want)
 
 
 def test_flow_init_and_batch_independence():

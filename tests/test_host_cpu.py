@@ -56,6 +56,43 @@ def test_pack_conv_layouts():
     assert torch.all(err <= torch.tensor([1.2345678, 3.1415927e-3, 1e4]) * 2.0 ** -16)
 
 
+def test_teacher_weight_updates_trigger_a_repack():
+    """The drop-in as frozen / EMA teacher of the reference's fine-tuning loop (tools/ft_dkt.py:140-151,179-199): a
+    DataParallel-wrapped model receives `load_state_dict` and, every step, the EMA assignment
+    `t_params.data = ema * t_params.data + (1 - ema) * s_params.data`.  Both must be noticed by the engine (packed
+    weights and captured CUDA graphs are stale afterwards); packing itself runs on the parameters' device, here the CPU."""
+    from dkt_stereo_b200.raft_stereo import RAFTStereo
+    torch.manual_seed(0)
+    teacher = torch.nn.DataParallel(RAFTStereo(Namespace(mixed_precision=False, **RAFT_CFG)))
+    student = torch.nn.DataParallel(RAFTStereo(Namespace(mixed_precision=False, **RAFT_CFG)))
+    for p in teacher.parameters():
+        p.requires_grad = False
+    teacher.eval()
+    teacher.module.freeze_bn()
+    eng = teacher.module.engine
+    assert eng.pack_weights() is True and eng.pack_weights() is False
+    w_before = eng.weights["zr0"].w_hi.clone()
+    # EMA step exactly as the reference writes it
+    for t_params, s_params in zip(teacher.parameters(), student.parameters()):
+        t_params.data = (0.9 * t_params.data + 0.1 * s_params.data)
+        t_params.requires_grad = False
+    assert eng.pack_weights() is True
+    assert not torch.equal(eng.weights["zr0"].w_hi, w_before)
+    g = teacher.module.update_block.gru08
+    ref = torch.cat([g.convz.weight, g.convr.weight]).detach().permute(2, 3, 0, 1).reshape(9, 256, 384)
+    assert torch.allclose(eng.weights["zr0"].w_hi.float() + eng.weights["zr0"].w_lo.float(), ref, rtol=1e-5, atol=1e-7)
+    assert eng.pack_weights() is False
+    # checkpoint load into the wrapper ("module." keys, reference ft_dkt.py:136-151)
+    teacher.load_state_dict(student.state_dict(), strict=True)
+    assert eng.pack_weights() is True
+    # in-place edits through .data bypass autograd's version counter: the explicit hook covers them
+    with torch.no_grad():
+        for p in teacher.parameters():
+            p.data.mul_(0.5)
+    teacher.module.invalidate_weights()
+    assert eng.pack_weights() is True
+
+
 def test_input_padder_roundtrip():
     from dkt_stereo_b200.utils import InputPadder, coords_grid
     x = torch.arange(2 * 3 * 37 * 50, dtype=torch.float32).view(2, 3, 37, 50)
