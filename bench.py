@@ -531,6 +531,14 @@ def run_b200_igev(args):
     res = measure_config("igev", H, W, iters, Bg, args.steps, args.warmup, rank, world, dev)
     model, step_device = res["model"], res["step_device"]
     im1_d, im2_d = res["im"][2:]
+    if args.ncu_step:                        # profiler window = exactly one eager step; nothing is timed or printed
+        model.use_cuda_graph = False
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     model.use_cuda_graph = False             # count the library's launches on one eager pass
     n0 = L.LAUNCHES
     step_device()

@@ -39,10 +39,12 @@ if ROOT not in sys.path:
 
 from oracle import hotpath as O  # noqa: E402
 
-GROUPS = ("enc", "menc", "gru08", "gru16_32", "head", "corr")
+GROUPS = ("enc", "menc", "gru08", "gru16_32", "head", "corr")     # + "convc1" (mixes only; exact fp32 otherwise)
 
 
 def group_of(name: str) -> str:
+    if name.endswith("encoder.convc1"):
+        return "convc1"
     if name.startswith(("cnet.", "fnet.", "context_zqr_convs.")):
         return "enc"
     if name.startswith("update_block.encoder."):
@@ -82,8 +84,6 @@ def run(sd, im1, im2, iters, cfg, assign):
 
     def conv(sd_, name, x, stride=1, padding=0):
         v = assign.get(group_of(name), "f32")
-        if name.endswith("encoder.convc1"):
-            v = "f32"
         return emulated_conv(x, sd_[name + ".weight"], sd_.get(name + ".bias"), stride, padding, v)
 
     orig_corr = O.corr1d_all_pairs
