@@ -284,22 +284,22 @@ def igev_lookup_roofline(model, Bg, h, w, peaks):
     from dkt_stereo_b200 import ops
     eng = model.engine
     P = Bg * h * w
-    geo, init = model._vol
     nplanes = 1 if eng.menc2 else 2
     lk_bytes = P * (2 * 9 * 10 * 4 + 4 + nplanes * 64 * 2)       # tap reads + disparity, writes 64 ch 16-bit (fused convc1)
-    disp = eng.FLOW["f32"].view(Bg, h, w).clone()
+    eng.DELTA["f32"].zero_()                                      # the fused `disp += delta` then leaves the disparities alone
     for _ in range(3):
-        ops.geo_lookup_enc(geo, init, disp, 4, eng.weights["convc1"], eng.cor1_slice())
+        model._lookup(eng)                                        # exactly the launch the loop makes
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(20):
-        ops.geo_lookup_enc(geo, init, disp, 4, eng.weights["convc1"], eng.cor1_slice())
+        model._lookup(eng)
     b.record()
     torch.cuda.synchronize()
     lk_ms = a.elapsed_time(b) / 20
     tr = ncu_traffic("geo_lookup_enc") if (h, w, Bg) == (136, 240, 8) else None
-    return {"kernel": "geo_lookup_kernel<4, ENC> (Combined_Geo_Encoding_Volume lookup + convc1)", "bound": "hbm",
+    return {"kernel": ("lookup_tc_kernel<GEO> (Combined_Geo_Encoding_Volume lookup + convc1 on tcgen05)" if eng.lookup_tc else
+                       "geo_lookup_kernel<4, ENC> (Combined_Geo_Encoding_Volume lookup + convc1, fp32 FMAs)"), "bound": "hbm",
             "achieved": lk_bytes / (lk_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": lk_bytes / (lk_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": tr["dram_bytes"] if tr else None,
             "traffic_source": tr["source"] if tr else None, "ms_per_launch": lk_ms,
@@ -461,7 +461,8 @@ def run_b200(args):
         return a.elapsed_time(b) / reps
 
     k2_ms = time_it(lambda: ops.corr1d_lookup(pyr, cx, 4, lk_out, "nhwc"))
-    k2e_ms = time_it(lambda: ops.corr1d_lookup_enc(pyr, cx, 4, eng.weights["convc1"], eng.cor1_slice()))
+    eng.DELTA["f32"].zero_()                                      # the fused `coords1 += delta` then leaves the coordinates alone
+    k2e_ms = time_it(lambda: model._lookup(eng))                  # exactly the launch the loop makes
     cfg2 = (H, W, Bg) == (544, 960, 8)
     tr_k1 = ncu_traffic("corr1d_build_tc") if cfg2 else None
     tr_k2 = ncu_traffic("corr1d_lookup_enc") if cfg2 else None
@@ -474,8 +475,9 @@ def run_b200(args):
         "lookup_enc": {"bound": "hbm", "achieved": k2_enc_bytes / (k2e_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                        "unit": "GB/s", "frac": k2_enc_bytes / (k2e_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": k2e_ms,
                        "bytes": k2_enc_bytes, "traffic": tr_k2["dram_bytes"] if tr_k2 else None,
-                       "note": "lookup fused with convc1 (1x1, 36->64, ReLU): taps never reach HBM; DRAM traffic is ~2x the "
-                               "algorithmic bytes because each 40-byte tap run touches 2-3 sectors of its own volume row"},
+                       "kernel": "lookup_tc_kernel (tcgen05 convc1)" if eng.lookup_tc else "corr1d_lookup_kernel<ENC> (fp32 FMAs)",
+                       "note": "lookup fused with convc1 (1x1, 36->64, ReLU): taps never reach HBM; DRAM traffic is ~2.5x the "
+                               "algorithmic bytes because each 40-byte tap run costs a 128-byte line of its own volume row"},
     }
 
     # every rank: the fixed-sample checksum (all-gather) and the other BASELINE configurations (barriers inside)

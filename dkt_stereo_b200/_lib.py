@@ -52,6 +52,9 @@ SIGNATURES = {
     "dkt_corr1d_build_f32": [_P, _P, _I64, _I64, _I64, _I64, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "dkt_corr1d_build_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "dkt_corr1d_lookup": [_P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _I64, _I64, _I64, _I, _I, _I, _I, _P],
+    "dkt_corr1d_lookup_enc_tc": [_P, _I, _I, _P, _P, _I, _P, _P, _P, _TP, _I, _I, _I, _I, _I, _P],
+    "dkt_geo_pool_dc": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "dkt_geo_lookup_enc_tc": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _TP, _I, _I, _I, _I, _P],
     "dkt_corr1d_lookup_backward": [_P, _P, _I, _P, _I, _I, _I, _I, _P],
     "dkt_geo_pool": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dkt_gwc_volume": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

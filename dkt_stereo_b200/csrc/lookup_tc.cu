@@ -1,0 +1,377 @@
+// K2 on tensor cores: the indexed multi-level lookup fused with the motion encoder's 1x1 `convc1` + ReLU, with the
+// 36 -> 64 (RAFT-Stereo) / 162 -> 64 (IGEV-Stereo) contraction on tcgen05 instead of fp32 FMAs.
+//
+// Why (profiles/r03m_lookup_phases.txt, profiles/r2g_corr_full.csv): in the CUDA-core kernel (corr.cu) the gather and the
+// exact-fp32 encode each take about half of the run time and do not overlap -- both live on the shared-memory pipe
+// (scattered 4-byte tap stores, two 16-byte loads per 8 FFMA2).  Here the gather threads write the taps as 16-bit
+// (hi, lo) values straight into a K-major SWIZZLE_128B operand tile, one elected thread issues a handful of
+// tcgen05.mma (M = 128 pixels, N = 64, K = 48 / 176), and the epilogue pulls the 64 results of a pixel from TMEM.
+// The encode leaves the shared-memory pipe and the FMA pipe; what remains is the gather, which is bound by the DRAM
+// traffic of its 40-byte tap runs (each costs a 128-byte line).
+//
+//   CTA            128 pixels per chunk, 256 threads, persistent over chunks
+//   shared memory  A[NBUF][AP planes][KB][128 rows x 128 B]   taps, K-major, 128-byte swizzle, written by the gather
+//                  W[2 planes][KB][64 rows x 128 B]            convc1, pre-swizzled on the host (ops.pack_lookup_tc)
+//   TMEM           128 columns: [0, 64) = taps_hi * w_hi, [64, 128) = the lo products (added in the epilogue in fp32
+//                  round-to-nearest: tcgen05 accumulates with round-toward-zero, see conv_tc.cu acc_lo_off)
+//   schedule       NBUF = 2: the gather of chunk i+1 runs while the MMAs of chunk i are in flight;
+//                  NBUF = 1 (IGEV, 48 KB per tile): two CTAs per SM overlap each other instead.
+//   AP             2: taps as (hi, lo) pairs, 3 MMAs per K step; 1: hi only, 2 MMAs (engine policy, update.py menc2)
+//
+// IGEV reads the geometry volume in the (B,H,W,D,C) layout of dkt_geo_pool_dc: the 10 taps x 8 channels of a
+// (pixel, level) are ONE 320-byte run instead of 8 runs of 40 bytes in 8 different 192-byte rows.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace dkt {
+
+using namespace tc;
+
+constexpr int LT_M = 128;            // pixels per chunk
+constexpr int LT_N = 64;             // convc1 output channels
+constexpr int LT_THREADS = 256;
+constexpr uint32_t LT_A_KB_BYTES = LT_M * 128;     // one 64-wide K block of an A plane
+constexpr uint32_t LT_W_KB_BYTES = LT_N * 128;
+
+struct LookupTcParams {
+    // RAFT: pyramid levels; IGEV: geo[l] (B,H,W,D>>l,Cg) and init[l] (B,H,W,W>>l)
+    const float* vol[DKT_MAX_LEVELS];
+    int          vw[DKT_MAX_LEVELS];
+    const float* geo[2];
+    int levels, Cg, D, W1;
+    float* coords;                   // RAFT: coords_x; IGEV: disparity
+    const float* delta;
+    int delta_C;
+    float* flow;
+    const uint16_t* w_img;           // [2][KB][64 x 64] 16-bit, already in the swizzled shared-memory order
+    const float* bias;
+    dkt_tensor out;                  // 64-channel NHWC slice
+    int64_t P;
+    int C;                           // real K: levels * 9 (RAFT) or 2 * (Cg + 1) * 9 (IGEV)
+};
+
+// byte offset of element (row m, column k) inside one plane [KB][rows][128 B] of a K-major SWIZZLE_128B tile whose
+// base is 1024-byte aligned: 8-row atoms of 1024 bytes, 16-byte chunks XOR-ed with the row index inside the atom
+__device__ __forceinline__ uint32_t sw128_off(int m, int k, uint32_t kb_bytes) {
+    return (uint32_t)(k >> 6) * kb_bytes + (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u +
+           (uint32_t)((((k & 63) >> 3) ^ (m & 7)) << 4) + (uint32_t)(k & 7) * 2u;
+}
+
+template <int AP>
+__device__ __forceinline__ void put_tap(uint8_t* a_buf, uint32_t plane_bytes, int m, int k, float v) {
+    const uint32_t off = sw128_off(m, k, LT_A_KB_BYTES);
+    uint16_t hi, lo;
+    split16(v, hi, lo);
+    *reinterpret_cast<uint16_t*>(a_buf + off) = hi;
+    if (AP == 2) *reinterpret_cast<uint16_t*>(a_buf + plane_bytes + off) = lo;
+}
+
+template <int R, int KB, int AP, int NBUF, bool GEO>
+__global__ void __launch_bounds__(LT_THREADS)
+lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
+    constexpr int T = 2 * R + 1;
+    constexpr uint32_t A_PLANE = KB * LT_A_KB_BYTES;
+    constexpr uint32_t A_BUF = AP * A_PLANE;
+    constexpr uint32_t W_PLANE = KB * LT_W_KB_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_ring = smem;                                   // [NBUF][AP][KB][128 x 128 B]
+    uint8_t* w_tile = a_ring + NBUF * A_BUF;                  // [2][KB][64 x 128 B]
+    float* s_x = reinterpret_cast<float*>(w_tile + 2 * W_PLANE);     // [128]
+    float* s_bias = s_x + LT_M;                               // [64]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_bias + LT_N);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    // zero the operand tiles once: the K padding [C, 64 * KB) is never written again and must not hold NaN patterns
+    for (uint32_t i = tid; i < NBUF * A_BUF / 16; i += LT_THREADS) reinterpret_cast<uint4*>(a_ring)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < 2 * W_PLANE / 16; i += LT_THREADS)
+        reinterpret_cast<uint4*>(w_tile)[i] = __ldg(reinterpret_cast<const uint4*>(prm.w_img) + i);
+    if (tid < LT_N) s_bias[tid] = __ldg(prm.bias + tid);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 128);
+    fence_proxy_async();                                      // W tile + zeros -> visible to the tensor core's proxy
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t idesc = idesc_bf16_m128(LT_N);
+    const int ksteps = (prm.C + 15) >> 4;                     // K16 steps that hold real channels
+
+    const int64_t nchunks = (prm.P + LT_M - 1) / LT_M;
+
+    // ---- coordinate bookkeeping + gather of one chunk into A[buf] (all threads; ends with a CTA barrier) ----
+    auto gather = [&](int64_t chunk, int buf) {
+        const int64_t p0 = chunk * LT_M;
+        const int npix = (int)((prm.P - p0) < LT_M ? (prm.P - p0) : LT_M);
+        if (tid < npix) {
+            const int64_t p = p0 + tid;
+            float cx = prm.coords[p];
+            if (prm.delta) {
+                cx += prm.delta[p * prm.delta_C];
+                prm.coords[p] = cx;
+            }
+            if (!GEO && prm.flow) prm.flow[p * 2] = cx - (float)(p % prm.W1);
+            s_x[tid] = cx;
+        }
+        __syncthreads();
+        uint8_t* a_buf = a_ring + (uint32_t)buf * A_BUF;
+        if (!GEO) {
+            // RAFT: unit = (pixel, level); 4 lanes per pixel
+            for (int u = tid; u < npix * DKT_MAX_LEVELS; u += LT_THREADS) {
+                const int px = u >> 2, l = u & 3;
+                if (l >= prm.levels) continue;
+                float v[2 * R + 2], a;
+                sample_row_load<R>(prm.vol[l] + (p0 + px) * prm.vw[l], prm.vw[l], s_x[px] * (1.f / (float)(1 << l)), v, a);
+#pragma unroll
+                for (int k = 0; k < T; ++k) put_tap<AP>(a_buf, A_PLANE, px, l * T + k, (1.f - a) * v[k] + a * v[k + 1]);
+            }
+        } else {
+            // IGEV: unit = (pixel, level, j): j < Cg one geometry channel (its taps sit Cg floats apart in the
+            // (.., D, Cg) layout, so the Cg lanes of a (pixel, level) read consecutive floats), j == Cg the init-corr row.
+            // Output channel order of the reference (geometry.py:36-57): per level [geo (c-major, tap-minor), init].
+            const int Cg = prm.Cg, G1 = Cg + 1, G = 2 * G1;
+            constexpr int GU = 3;                 // row samples whose loads a thread has in flight before interpolating
+            for (int u0 = tid; u0 < npix * G; u0 += LT_THREADS * GU) {
+                float v[GU][2 * R + 2], av[GU];
+#pragma unroll
+                for (int g = 0; g < GU; ++g) {
+                    const int u = u0 + g * LT_THREADS;
+                    if (u >= npix * G) continue;
+                    const int px = u / G, gi = u - px * G;
+                    const int l = gi / G1, j = gi - l * G1;
+                    const int64_t p = p0 + px;
+                    const float d = s_x[px];
+                    const float inv = l ? 0.5f : 1.f;
+                    if (j < Cg) {
+                        const int Dl = l ? prm.D / 2 : prm.D;
+                        const float x = d * inv, xf = floorf(x);
+                        av[g] = x - xf;
+                        const int i0 = (int)xf - R;
+                        const float* row = prm.geo[l] + p * Dl * Cg + j;
+#pragma unroll
+                        for (int k = 0; k < 2 * R + 2; ++k) {
+                            const int idx = i0 + k;
+                            v[g][k] = (idx >= 0 && idx < Dl) ? __ldg(row + (int64_t)idx * Cg) : 0.f;
+                        }
+                    } else {
+                        const int Wl = prm.vw[l];
+                        const float x = (float)(p % prm.W1);
+                        sample_row_load<R>(prm.vol[l] + p * Wl, Wl, x * inv - d * inv, v[g], av[g]);
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < GU; ++g) {
+                    const int u = u0 + g * LT_THREADS;
+                    if (u >= npix * G) continue;
+                    const int px = u / G, gi = u - px * G;
+#pragma unroll
+                    for (int k = 0; k < T; ++k)
+                        put_tap<AP>(a_buf, A_PLANE, px, gi * T + k, (1.f - av[g]) * v[g][k] + av[g] * v[g][k + 1]);
+                }
+            }
+        }
+        fence_proxy_async();                                  // generic-proxy stores -> async proxy (tcgen05.mma operand reads)
+        __syncthreads();
+    };
+
+    int buf = 0;
+    uint32_t phase = 0;
+    int64_t chunk = blockIdx.x;
+    if (chunk < nchunks) gather(chunk, 0);
+    for (; chunk < nchunks; chunk += gridDim.x) {
+        // ---- MMAs of this chunk: one elected lane of warp 0 ----
+        if (warp == 0) {
+            tcgen05_fence_after();
+            if (elect_one()) {
+                const uint32_t a_hi = smem_u32(a_ring + (uint32_t)buf * A_BUF), a_lo = a_hi + A_PLANE;
+                const uint32_t w_hi = smem_u32(w_tile), w_lo = w_hi + W_PLANE;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint32_t ao = (uint32_t)(ks >> 2) * LT_A_KB_BYTES + (uint32_t)(ks & 3) * 32u;
+                    const uint32_t wo = (uint32_t)(ks >> 2) * LT_W_KB_BYTES + (uint32_t)(ks & 3) * 32u;
+                    const uint32_t acc = ks != 0;
+                    umma_bf16(tmem_base, smem_desc_sw128(a_hi + ao), smem_desc_sw128(w_hi + wo), idesc, acc);
+                    if (AP == 2) umma_bf16(tmem_base + LT_N, smem_desc_sw128(a_lo + ao), smem_desc_sw128(w_hi + wo), idesc, acc);
+                    umma_bf16(tmem_base + LT_N, smem_desc_sw128(a_hi + ao), smem_desc_sw128(w_lo + wo), idesc, AP == 2 ? 1u : acc);
+                }
+                umma_commit(bar);
+            }
+            __syncwarp();
+        }
+        const int64_t next = chunk + gridDim.x;
+        if (NBUF == 2 && next < nchunks) gather(next, buf ^ 1);          // overlaps the MMAs in flight
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tcgen05_fence_after();
+        // ---- epilogue: warp = TMEM lane quarter (warp & 3) x column half (warp >> 2); thread = pixel ----
+        {
+            const int64_t p0 = chunk * LT_M;
+            const int npix = (int)((prm.P - p0) < LT_M ? (prm.P - p0) : LT_M);
+            const int q = warp & 3, c0 = (warp >> 2) * 32;
+            const int m = q * 32 + lane;
+            float v[32], v2[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            tmem_ld32(taddr, v);
+            tmem_ld32(taddr + LT_N, v2);
+            tmem_ld_wait();
+            if (m < npix) {
+                const dkt_tensor& o = prm.out;
+                const int64_t off = (p0 + m) * o.C + o.c_begin + c0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + v2[j] + s_bias[c0 + j], 0.f);
+                if (o.f32) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(o.f32 + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+                if (o.hi) {
+                    if (o.lo) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint32_t h[4], l[4];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) split16x2(v[j + 2 * t], v[j + 2 * t + 1], h[t], l[t]);
+                            *reinterpret_cast<uint4*>(o.hi + off + j) = make_uint4(h[0], h[1], h[2], h[3]);
+                            *reinterpret_cast<uint4*>(o.lo + off + j) = make_uint4(l[0], l[1], l[2], l[3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8)
+                            *reinterpret_cast<uint4*>(o.hi + off + j) =
+                                make_uint4(pack_hi16x2(v[j], v[j + 1]), pack_hi16x2(v[j + 2], v[j + 3]),
+                                           pack_hi16x2(v[j + 4], v[j + 5]), pack_hi16x2(v[j + 6], v[j + 7]));
+                    }
+                }
+            }
+        }
+        tcgen05_fence_before();
+        __syncthreads();                                      // accumulator drained before the next chunk's MMAs overwrite it
+        if (NBUF == 2) buf ^= 1;
+        else if (next < nchunks) gather(next, 0);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// ---- IGEV geometry encoding volume: (B,C,D,H,W) -> level 0 (B,H,W,D,C) + pooled level 1 (B,H,W,D/2,C) ----
+// one CTA per (b, y, 32-pixel segment): the [C*D][32] slab is read along w (coalesced) and written per pixel as D x C
+// contiguous floats.
+__global__ void __launch_bounds__(256)
+geo_pool_dc_kernel(const float* __restrict__ gev, float* __restrict__ geo0, float* __restrict__ geo1,
+                   int C, int D, int H, int W) {
+    extern __shared__ float slab[];              // [C*D][33]
+    const int by = blockIdx.y;                   // b*H + y
+    const int b = by / H, y = by - b * H;
+    const int w0 = blockIdx.x * 32;
+    const int CD = C * D;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const float* src = gev + (int64_t)b * CD * H * W + (int64_t)y * W + w0;
+    for (int r = wrp; r < CD; r += 8)            // r = c*D + d
+        slab[r * 33 + lane] = (w0 + lane < W) ? __ldg(src + (int64_t)r * H * W + lane) : 0.f;
+    __syncthreads();
+    const int D1 = D / 2;
+    for (int px = 0; px < 32 && w0 + px < W; ++px) {
+        const int64_t pix = ((int64_t)b * H + y) * W + w0 + px;
+        float* o0 = geo0 + pix * D * C;
+        float* o1 = geo1 + pix * D1 * C;
+        for (int i = threadIdx.x; i < CD; i += 256) {         // i = d*C + c (output order)
+            const int d = i / C, c = i - d * C;
+            o0[i] = slab[(c * D + d) * 33 + px];
+        }
+        for (int i = threadIdx.x; i < D1 * C; i += 256) {
+            const int d = i / C, c = i - d * C;
+            o1[i] = (slab[(c * D + 2 * d) * 33 + px] + slab[(c * D + 2 * d + 1) * 33 + px]) * 0.5f;
+        }
+    }
+}
+
+}  // namespace dkt
+
+using namespace dkt;
+
+static int check_enc_out(const dkt_tensor* t) {
+    if (!t || !(t->f32 || t->hi) || t->c_count != LT_N) return DKT_E_INVALID;
+    if ((t->C % 8) || (t->c_begin % 8)) return DKT_E_ALIGNMENT;
+    if ((reinterpret_cast<uintptr_t>(t->f32) & 15) || (reinterpret_cast<uintptr_t>(t->hi) & 15) ||
+        (reinterpret_cast<uintptr_t>(t->lo) & 15))
+        return DKT_E_ALIGNMENT;
+    return 0;
+}
+
+template <int KB, int AP, int NBUF, bool GEO>
+static int launch_lookup_tc(const LookupTcParams& prm, cudaStream_t st) {
+    constexpr size_t smem = 1024 + (size_t)NBUF * AP * KB * LT_A_KB_BYTES + 2 * (size_t)KB * LT_W_KB_BYTES + (LT_M + LT_N) * 4 + 64;
+    DKT_ENSURE_SMEM(smem, lookup_tc_kernel<4, KB, AP, NBUF, GEO>);
+    const int per_sm = (int)((227 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((227 * 1024) / (smem + 1024));
+    const int ctas_sm = per_sm > 4 ? 4 : per_sm;             // TMEM: 128 columns per CTA, 512 per SM
+    const int64_t chunks = ceil_div64(prm.P, LT_M), cap = (int64_t)device_sms() * ctas_sm;
+    lookup_tc_kernel<4, KB, AP, NBUF, GEO><<<(unsigned)(chunks < cap ? chunks : cap), LT_THREADS, smem, st>>>(prm);
+    DKT_RETURN_LAST();
+}
+
+extern "C" int dkt_corr1d_lookup_enc_tc(const float* const* pyr, int levels, int radius,
+                                        float* coords_x, const float* delta, int delta_C, float* flow,
+                                        const uint16_t* w_img, const float* enc_b, const dkt_tensor* enc_out, int tap_planes,
+                                        int B, int H, int W1, int W2, void* stream) {
+    DKT_CHECK_ARG(pyr && coords_x && w_img && enc_b);
+    DKT_CHECK_ARG(B > 0 && H > 0 && W1 > 0 && W2 > 0);
+    if (int rc = check_enc_out(enc_out)) return rc;
+    if (radius != 4 || levels < 1 || levels > DKT_MAX_LEVELS) return DKT_E_UNSUPPORTED;
+    if (tap_planes != 1 && tap_planes != 2) return DKT_E_INVALID;
+    if (delta) DKT_CHECK_ARG(delta_C > 0);
+    if (reinterpret_cast<uintptr_t>(w_img) & 15) return DKT_E_ALIGNMENT;
+    LookupTcParams prm{};
+    int w = W2;
+    for (int l = 0; l < DKT_MAX_LEVELS; ++l) {
+        prm.vol[l] = l < levels ? pyr[l] : nullptr;
+        prm.vw[l] = w;
+        if (l < levels) DKT_CHECK_ARG(pyr[l] != nullptr && w > 0);
+        w /= 2;
+    }
+    prm.levels = levels; prm.W1 = W1;
+    prm.coords = coords_x; prm.delta = delta; prm.delta_C = delta_C; prm.flow = flow;
+    prm.w_img = w_img; prm.bias = enc_b; prm.out = *enc_out;
+    prm.P = (int64_t)B * H * W1;
+    prm.C = levels * 9;
+    return tap_planes == 2 ? launch_lookup_tc<1, 2, 2, false>(prm, (cudaStream_t)stream)
+                           : launch_lookup_tc<1, 1, 2, false>(prm, (cudaStream_t)stream);
+}
+
+extern "C" int dkt_geo_pool_dc(const float* gev, float* geo0, float* geo1, int B, int C, int D, int H, int W, void* stream) {
+    DKT_CHECK_ARG(gev && geo0 && geo1);
+    DKT_CHECK_ARG(B > 0 && C > 0 && D > 1 && H > 0 && W > 0);
+    const size_t smem = (size_t)C * D * 33 * 4;
+    if (smem > 200 * 1024 || (int64_t)B * H > 65535) return DKT_E_UNSUPPORTED;
+    DKT_ENSURE_SMEM(200 * 1024, geo_pool_dc_kernel);
+    geo_pool_dc_kernel<<<dim3(ceil_div(W, 32), B * H), 256, smem, (cudaStream_t)stream>>>(gev, geo0, geo1, C, D, H, W);
+    DKT_RETURN_LAST();
+}
+
+extern "C" int dkt_geo_lookup_enc_tc(const float* geo0, const float* geo1, const float* init0, const float* init1,
+                                     float* disp, const float* delta, int delta_C, int radius, int C, int D,
+                                     const uint16_t* w_img, const float* enc_b, const dkt_tensor* enc_out, int tap_planes,
+                                     int B, int H, int W, void* stream) {
+    DKT_CHECK_ARG(geo0 && geo1 && init0 && init1 && disp && w_img && enc_b);
+    DKT_CHECK_ARG(B > 0 && H > 0 && W > 1 && C > 0 && D > 1);
+    if (int rc = check_enc_out(enc_out)) return rc;
+    if (radius != 4 || 2 * (C + 1) * 9 > 192) return DKT_E_UNSUPPORTED;
+    if (tap_planes != 1 && tap_planes != 2) return DKT_E_INVALID;
+    if (delta) DKT_CHECK_ARG(delta_C > 0);
+    if (reinterpret_cast<uintptr_t>(w_img) & 15) return DKT_E_ALIGNMENT;
+    LookupTcParams prm{};
+    prm.geo[0] = geo0; prm.geo[1] = geo1;
+    prm.vol[0] = init0; prm.vol[1] = init1;
+    prm.vw[0] = W; prm.vw[1] = W / 2;
+    prm.levels = 2; prm.Cg = C; prm.D = D; prm.W1 = W;
+    prm.coords = disp; prm.delta = delta; prm.delta_C = delta_C; prm.flow = nullptr;
+    prm.w_img = w_img; prm.bias = enc_b; prm.out = *enc_out;
+    prm.P = (int64_t)B * H * W;
+    prm.C = 2 * (C + 1) * 9;
+    return tap_planes == 2 ? launch_lookup_tc<3, 2, 1, true>(prm, (cudaStream_t)stream)
+                           : launch_lookup_tc<3, 1, 1, true>(prm, (cudaStream_t)stream);
+}

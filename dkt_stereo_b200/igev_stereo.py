@@ -155,6 +155,10 @@ class IGEVStereo(nn.Module):
         geo, init = self._vol
         r = self.args.corr_radius
         disp = eng.FLOW["f32"].view(eng.B, *eng.hw[0])            # (B,h,w,1) -> (B,h,w)
+        if eng.lookup_tc:
+            ops.geo_lookup_enc_tc(geo, init, disp, r, *eng.lookup_tc_w, eng.cor1_slice(), eng.lookup_tap_planes,
+                                  delta=eng.DELTA["f32"])
+            return
         if eng.fused_enc:
             ops.geo_lookup_enc(geo, init, disp, r, eng.weights["convc1"], eng.cor1_slice(), delta=eng.DELTA["f32"])
         else:
@@ -183,18 +187,20 @@ class IGEVStereo(nn.Module):
             self._graphs.clear()
             self._seen.clear()
         eng.allocate(B, h, w, dev)
-        key = (B, D, h, w, tuple(gev.shape), str(dev))
+        dc = eng.lookup_tc               # the tensor-core lookup reads the geometry volume as (B,h,w,D,C)
+        key = (B, D, h, w, tuple(gev.shape), str(dev), dc)
         if self._vol_key != key:
             self._graphs.clear()
             self._seen.clear()
             self._vol_key = key
             self._init_pyr = ops.alloc_pyramid(B, h, w, w, 2, dev)
             Cg, Dg = gev.shape[1], gev.shape[2]
-            self._geo_pyr = (torch.empty(B, h, w, Cg, Dg, device=dev), torch.empty(B, h, w, Cg, Dg // 2, device=dev))
+            self._geo_pyr = ((torch.empty(B, h, w, Dg, Cg, device=dev), torch.empty(B, h, w, Dg // 2, Cg, device=dev)) if dc else
+                             (torch.empty(B, h, w, Cg, Dg, device=dev), torch.empty(B, h, w, Cg, Dg // 2, device=dev)))
         # volumes: init-corr pyramid = K1 with scale 1 (geometry.py:14,61-69), GEV pyramid (geometry.py:17-26);
         # the buffers persist per shape because the captured loop graph holds their addresses
         init = ops.corr1d_build(match_left, match_right, 2, 1.0, impl=self.impl, pyr=self._init_pyr)
-        geo = ops.geo_pool(gev, out=self._geo_pyr)
+        geo = (ops.geo_pool_dc if dc else ops.geo_pool)(gev, out=self._geo_pyr)
         self._vol = (geo, init)
         if net_list is not None:
             eng.load_state(net_list, ctx_list)   # else: EncoderEngine.run already filled X[i][:, :128] and CTX[i]

@@ -269,6 +269,66 @@ def corr1d_lookup_enc(pyr: Sequence[torch.Tensor], coords_x: torch.Tensor, radiu
                                       B, H, W1, pyr[0].shape[-1], L.stream_ptr()), "corr1d_lookup_enc")
 
 
+def pack_lookup_tc(weight: torch.Tensor, bias: torch.Tensor):
+    """convc1 (64, C, 1, 1) -> (w_img, bias): the tensor-core lookup's shared-memory image of the weights,
+    [2 planes (hi, lo)][KB][64 rows x 64 k] 16-bit in K-major SWIZZLE_128B order (csrc/lookup_tc.cu sw128_off)."""
+    dev, weight, bias = _pack_src(weight, bias)
+    N, C = weight.shape[0], weight.shape[1]
+    assert N == 64
+    KB = (C + 63) // 64
+    w = weight.detach().float().reshape(N, C)
+    hi, lo = split16(w)
+    n = torch.arange(N, device=w.device).view(N, 1).expand(N, C)
+    k = torch.arange(C, device=w.device).view(1, C).expand(N, C)
+    off = (k >> 6) * (64 * 128) + (n >> 3) * 1024 + (n & 7) * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + (k & 7) * 2
+    idx = (off // 2).reshape(-1)
+    img = torch.zeros(2, KB * 64 * 64, dtype=hi.dtype, device=w.device)
+    img[0, idx] = hi.reshape(-1)
+    img[1, idx] = lo.reshape(-1)
+    return _to(img.contiguous(), dev), _to(bias.detach().float().contiguous(), dev)
+
+
+def corr1d_lookup_enc_tc(pyr: Sequence[torch.Tensor], coords_x: torch.Tensor, radius: int, w_img: torch.Tensor,
+                         bias: torch.Tensor, enc_out: DktTensor, tap_planes: int = 2,
+                         delta: Optional[torch.Tensor] = None, flow: Optional[torch.Tensor] = None) -> None:
+    """corr1d_lookup_enc with the 1x1 ``convc1`` on tensor cores (csrc/lookup_tc.cu)."""
+    lib = L.load()
+    L.require_device(coords_x)
+    B, H, W1 = coords_x.shape
+    L.check(lib.dkt_corr1d_lookup_enc_tc(L.pointer_array(pyr), len(pyr), radius, coords_x.data_ptr(),
+                                         L.ptr(delta), delta.shape[-1] if delta is not None else 0, L.ptr(flow),
+                                         w_img.data_ptr(), bias.data_ptr(), C.byref(enc_out), tap_planes,
+                                         B, H, W1, pyr[0].shape[-1], L.stream_ptr()), "corr1d_lookup_enc_tc")
+
+
+def geo_pool_dc(gev: torch.Tensor, out: Optional[Sequence[torch.Tensor]] = None):
+    """(B,C,D,H,W) -> (B,H,W,D,C), (B,H,W,D//2,C): the layout ``geo_lookup_enc_tc`` reads."""
+    lib = L.load()
+    L.require_device(gev)
+    gev = gev.contiguous().float()
+    B, Cc, D, H, W = gev.shape
+    if out is not None:
+        g0, g1 = out
+        assert g0.shape == (B, H, W, D, Cc) and g1.shape == (B, H, W, D // 2, Cc)
+    else:
+        g0 = torch.empty(B, H, W, D, Cc, device=gev.device, dtype=torch.float32)
+        g1 = torch.empty(B, H, W, D // 2, Cc, device=gev.device, dtype=torch.float32)
+    L.check(lib.dkt_geo_pool_dc(gev.data_ptr(), g0.data_ptr(), g1.data_ptr(), B, Cc, D, H, W, L.stream_ptr()), "geo_pool_dc")
+    return g0, g1
+
+
+def geo_lookup_enc_tc(geo: Sequence[torch.Tensor], init: Sequence[torch.Tensor], disp: torch.Tensor, radius: int,
+                      w_img: torch.Tensor, bias: torch.Tensor, enc_out: DktTensor, tap_planes: int = 1,
+                      delta: Optional[torch.Tensor] = None) -> None:
+    """geo_lookup_enc on tensor cores; ``geo`` in the (B,H,W,D,C) layout of ``geo_pool_dc``."""
+    lib = L.load()
+    B, H, W, D, Cc = geo[0].shape
+    L.check(lib.dkt_geo_lookup_enc_tc(geo[0].data_ptr(), geo[1].data_ptr(), init[0].data_ptr(), init[1].data_ptr(),
+                                      disp.data_ptr(), L.ptr(delta), delta.shape[-1] if delta is not None else 0,
+                                      radius, Cc, D, w_img.data_ptr(), bias.data_ptr(), C.byref(enc_out), tap_planes,
+                                      B, H, W, L.stream_ptr()), "geo_lookup_enc_tc")
+
+
 def geo_lookup(geo: Sequence[torch.Tensor], init: Sequence[torch.Tensor], disp: torch.Tensor, radius: int,
                out: torch.Tensor, out_layout: str = "nhwc",
                out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None,
@@ -634,4 +694,6 @@ convex_upsample = _profiled(lambda *a, **k: "convex_upsample")(convex_upsample)
 nchw_to_nhwc = _profiled(lambda *a, **k: "nchw_to_nhwc")(nchw_to_nhwc)
 geo_lookup = _profiled(lambda *a, **k: "geo_lookup")(geo_lookup)
 corr1d_lookup_enc = _profiled(lambda *a, **k: "corr1d_lookup_enc")(corr1d_lookup_enc)
+corr1d_lookup_enc_tc = _profiled(lambda *a, **k: "corr1d_lookup_enc_tc")(corr1d_lookup_enc_tc)
+geo_lookup_enc_tc = _profiled(lambda *a, **k: "geo_lookup_enc_tc")(geo_lookup_enc_tc)
 geo_lookup_enc = _profiled(lambda *a, **k: "geo_lookup_enc")(geo_lookup_enc)

@@ -131,6 +131,10 @@ class RAFTStereo(nn.Module):
 
     # ---- L2: hot path (B200 kernels) ----------------------------------------------------------------
     def _lookup(self, eng: UpdateEngine) -> None:
+        if eng.lookup_tc:
+            ops.corr1d_lookup_enc_tc(self._pyr, eng.coords_x, self.args.corr_radius, *eng.lookup_tc_w, eng.cor1_slice(),
+                                     eng.lookup_tap_planes, delta=eng.DELTA["f32"], flow=eng.FLOW["f32"])
+            return
         if eng.fused_enc:
             ops.corr1d_lookup_enc(self._pyr, eng.coords_x, self.args.corr_radius, eng.weights["convc1"],
                                   eng.cor1_slice(), delta=eng.DELTA["f32"], flow=eng.FLOW["f32"])

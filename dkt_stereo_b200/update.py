@@ -130,6 +130,13 @@ class UpdateEngine:
         # study's h_x1_w1 row: +5e-5 px for this group; every other group needs its weights as a pair).  Measured on
         # B200 against the reference goldens (profiles/r2f_parity_accsplit.txt): +0.2..0.5e-4 px, -3 % step time.
         self.coarse1 = self.gru2 and os.environ.get("DKT_COARSE_GRU_TERMS", "1") == "1"
+        # fused lookup + convc1 with the 1x1 contraction on tcgen05 (csrc/lookup_tc.cu); 0 = the exact-fp32 CUDA-core form.
+        # Taps as (hi, lo) pairs (3 MMAs per K step) for RAFT-Stereo; IGEV-Stereo's 162-channel tile follows the motion
+        # encoder's policy (hi only when menc2: a pair would leave one CTA per SM).
+        self.lookup_tc = impl == "tc" and self.fused_enc and os.environ.get("DKT_LOOKUP_TC", "1") == "1"
+        taps = os.environ.get("DKT_LOOKUP_TAP_PLANES")
+        self.lookup_tap_planes = int(taps) if taps else (1 if (self.igev and self.menc2) else 2)
+        self.lookup_tc_w = None
         self.side_stream = None
         self.weights: Optional[Dict[str, ops.ConvWeights]] = None
         self._wsig = None
@@ -150,6 +157,8 @@ class UpdateEngine:
         self.corr_planes = enc.convc1.in_channels
         self.corr_pad = _pad64(self.corr_planes)
         w["convc1"] = ops.pack_conv(enc.convc1.weight, enc.convc1.bias, cin_pad=self.corr_pad, tc=tc)
+        if self.lookup_tc:
+            self.lookup_tc_w = ops.pack_lookup_tc(enc.convc1.weight, enc.convc1.bias)
         w["convc2"] = ops.pack_conv(enc.convc2.weight, enc.convc2.bias, tc=tc)
         stem1 = enc.convd1 if self.igev else enc.convf1
         stem2 = enc.convd2 if self.igev else enc.convf2

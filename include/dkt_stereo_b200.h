@@ -170,6 +170,17 @@ int dkt_corr1d_lookup_enc(const float* const* pyr, int levels, int radius,
                           const float* enc_w, const float* enc_b, const dkt_tensor* enc_out,
                           int B, int H, int W1, int W2, void* stream);
 
+/* Tensor-core form of dkt_corr1d_lookup_enc (tcgen05, csrc/lookup_tc.cu): same lookup, same coordinate bookkeeping,
+ * `convc1` + ReLU as a 16-bit split contraction with fp32 accumulation instead of fp32 FMAs.
+ *   w_img      : convc1 as the kernel's shared-memory image, [2 planes (hi, lo)][KB][64 rows x 64 k] 16-bit values in
+ *                K-major SWIZZLE_128B order, KB = ceil(C / 64) (dkt_stereo_b200.ops.pack_lookup_tc writes it)
+ *   tap_planes : 2 = taps as (hi, lo) pairs, 3 MMAs per K step; 1 = hi only, 2 MMAs (see the header comment)
+ *   enc_out    : 64-channel NHWC slice, C and c_begin multiples of 8, planes 16-byte aligned */
+int dkt_corr1d_lookup_enc_tc(const float* const* pyr, int levels, int radius,
+                             float* coords_x, const float* delta, int delta_C, float* flow,
+                             const uint16_t* w_img, const float* enc_b, const dkt_tensor* enc_out, int tap_planes,
+                             int B, int H, int W1, int W2, void* stream);
+
 /* Adjoint of the ONE-level lookup with respect to the volume: replaces corr_sampler.backward(volume, coords,
  * grad_output, radius) -> (grad_volume,) of the un-vendored extension the reference binds in CorrSampler.backward
  * (reference core/corr.py:25-29; used only when corr_implementation = "reg_cuda" is trained).
@@ -188,6 +199,9 @@ int dkt_corr1d_lookup_backward(const float* grad_out, const float* coords_x, int
  *   (`disp = disp + delta_disp`, reference meta_arch/igev_stereo/igev_stereo.py:210).
  * dkt_geo_lookup_enc: same + the IGEV motion encoder's convc1 (igev update.py:76,85), see above. */
 int dkt_geo_pool(const float* gev, float* geo0, float* geo1, int B, int C, int D, int H, int W, void* stream);
+/* The same pyramid in the layout the tensor-core lookup reads: level 0 (B,H,W,D,C), level 1 (B,H,W,D/2,C) -- the
+ * 2r+2 disparity samples x C channels one lookup needs from a (pixel, level) are ONE contiguous run. */
+int dkt_geo_pool_dc(const float* gev, float* geo0, float* geo1, int B, int C, int D, int H, int W, void* stream);
 int dkt_geo_lookup(const float* geo0, const float* geo1, const float* init0, const float* init1,
                    float* disp, const float* delta, int delta_C, int radius, int C, int D,
                    float* out, uint16_t* out_hi, uint16_t* out_lo,
@@ -197,6 +211,11 @@ int dkt_geo_lookup_enc(const float* geo0, const float* geo1, const float* init0,
                        float* disp, const float* delta, int delta_C, int radius, int C, int D,
                        const float* enc_w, const float* enc_b, const dkt_tensor* enc_out,
                        int B, int H, int W, void* stream);
+/* Tensor-core form of dkt_geo_lookup_enc (see dkt_corr1d_lookup_enc_tc); geo0 / geo1 in the dkt_geo_pool_dc layout. */
+int dkt_geo_lookup_enc_tc(const float* geo0, const float* geo1, const float* init0, const float* init1,
+                          float* disp, const float* delta, int delta_C, int radius, int C, int D,
+                          const uint16_t* w_img, const float* enc_b, const dkt_tensor* enc_out, int tap_planes,
+                          int B, int H, int W, void* stream);
 
 /* ---- IGEV pre-loop volume kernels, exact fp32 ------------------------------
  * dkt_gwc_volume: group-wise correlation volume, replaces build_gwc_volume + groupwise_correlation

@@ -239,6 +239,83 @@ def test_geo_lookup_update_nhwc_and_enc():
     assert stats(enc.permute(0, 3, 1, 2).cpu(), enc_ref)[1] < 2e-4
 
 
+@pytest.mark.parametrize("planes", [2, 1])
+@pytest.mark.parametrize("shape", [(2, 32, 5, 43), (1, 64, 9, 240), (3, 16, 2, 130)])
+def test_corr1d_lookup_enc_tensor_core(shape, planes):
+    """The lookup fused with convc1 on tcgen05 (csrc/lookup_tc.cu): taps + coordinate bookkeeping identical to the
+    fp32 kernel, the 36 -> 64 contraction as a 16-bit split with fp32 accumulation.  Ragged chunk (P % 128 != 0),
+    several chunks per CTA, out-of-range coordinates; every output plane (fp32, hi, lo / hi only)."""
+    from dkt_stereo_b200 import ops, _lib as L
+    from oracle import hotpath as O
+    B, D, H, W = shape
+    g = torch.Generator().manual_seed(D + W)
+    f1, f2 = torch.randn(B, D, H, W, generator=g), torch.randn(B, D, H, W, generator=g)
+    pyr_ref = O.corr1d_pyramid(f1, f2, 4)
+    cx = torch.arange(W).view(1, 1, W).float() + (torch.rand(B, H, W, generator=g) * (W + 16) - W / 2 - 8)
+    delta = torch.randn(B, H, W, 2, generator=g)
+    ref = O.corr1d_lookup(pyr_ref, cx + delta[..., 0], 4)              # (B,36,H,W)
+    wt = torch.randn(64, 36, 1, 1, generator=g) / 6.0
+    bias = torch.randn(64, generator=g)
+    if planes == 1:
+        ref = ref.half().float()                                      # hi-only taps: the half-rounded taps, exactly
+    enc_ref = torch.relu(torch.nn.functional.conv2d(ref, wt, bias))
+    pyr = ops.corr1d_build(f1.to(dev()), f2.to(dev()), 4, 1.0 / D ** 0.5, impl="simt")
+    w_img, b_dev = ops.pack_lookup_tc(wt.to(dev()), bias.to(dev()))
+    enc = torch.zeros(B, H, W, 128, device=dev())
+    ehi = torch.zeros(B, H, W, 128, device=dev(), dtype=L16())
+    elo = torch.zeros_like(ehi)
+    flow = torch.zeros(B, H, W, 2, device=dev())
+    cxd = cx.to(dev()).contiguous()
+    ops.corr1d_lookup_enc_tc(pyr, cxd, 4, w_img, b_dev, L.tensor_slice(enc, ehi, elo, 64, 64), planes,
+                             delta=delta.to(dev()), flow=flow)
+    torch.cuda.synchronize()
+    assert torch.equal(cxd.cpu(), cx + delta[..., 0])                  # coords1 += delta
+    assert torch.equal(flow[..., 0].cpu(), cxd.cpu() - torch.arange(W).view(1, 1, W))
+    got = enc[..., 64:].permute(0, 3, 1, 2).cpu()
+    # O(1..10) outputs; 3-MMA split ~2^-22 per operand, dominated by the pyramid's own fp32 rounding
+    assert stats(got, enc_ref)[1] < (2e-4 if planes == 2 else 1e-3), (shape, planes, stats(got, enc_ref))
+    assert float(enc[..., :64].abs().max()) == 0 and float(ehi[..., :64].float().abs().max()) == 0
+    assert stats((ehi.float() + elo.float())[..., 64:].cpu(), enc[..., 64:].cpu())[1] < 1e-5
+    ehi2 = torch.zeros_like(ehi)
+    cxd2 = cx.to(dev()).contiguous()
+    ops.corr1d_lookup_enc_tc(pyr, cxd2, 4, w_img, b_dev, L.tensor_slice(None, ehi2, None, 64, 64), planes, delta=delta.to(dev()))
+    assert torch.equal(ehi2, ehi)                                      # hi-only destination = the hi plane
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+def test_geo_lookup_enc_tensor_core(planes):
+    """IGEV combined lookup + 162 -> 64 convc1 on tcgen05, reading the geometry volume in the (B,H,W,D,C) layout of
+    dkt_geo_pool_dc; channel order and `disp += delta` as the reference (geometry.py:34-58, igev_stereo.py:210)."""
+    from dkt_stereo_b200 import ops, _lib as L
+    from oracle import hotpath as O
+    g = load_golden("geo_a")
+    f1, f2, gev, disp = (g[k] for k in ("fmap1", "fmap2", "gev", "disp"))
+    gen = torch.Generator().manual_seed(5)
+    B, _, H, W = disp.shape
+    delta = torch.randn(B, H, W, 1, generator=gen)
+    geo_ref, init_ref = O.geo_pyramids(f1, f2, gev, 2)
+    ref = O.geo_lookup(geo_ref, init_ref, disp + delta.permute(0, 3, 1, 2), 4)       # (B,162,H,W)
+    if planes == 1:
+        ref = ref.half().float()
+    wt = torch.randn(64, 162, 1, 1, generator=gen) / 12.0
+    bias = torch.randn(64, generator=gen)
+    enc_ref = torch.relu(torch.nn.functional.conv2d(ref, wt, bias))
+    init = ops.corr1d_build(f1.to(dev()), f2.to(dev()), 2, 1.0, impl="simt")
+    geo = ops.geo_pool_dc(gev.to(dev()))
+    old = ops.geo_pool(gev.to(dev()))
+    assert torch.equal(geo[0], old[0].permute(0, 1, 2, 4, 3).contiguous())       # same numbers, (.., D, C) order
+    assert torch.equal(geo[1], old[1].permute(0, 1, 2, 4, 3).contiguous())
+    w_img, b_dev = ops.pack_lookup_tc(wt.to(dev()), bias.to(dev()))
+    enc = torch.zeros(B, H, W, 64, device=dev())
+    d = disp[:, 0].contiguous().to(dev())
+    ops.geo_lookup_enc_tc(geo, init, d, 4, w_img, b_dev, L.tensor_slice(enc, None, None, 0, 64), planes, delta=delta.to(dev()))
+    torch.cuda.synchronize()
+    assert torch.equal(d.cpu(), disp[:, 0] + delta[..., 0])
+    got = enc.permute(0, 3, 1, 2).cpu()
+    # init-corr taps are unscaled dot products (|v| up to ~20): outputs O(10)
+    assert stats(got, enc_ref)[1] < (5e-4 if planes == 2 else 5e-3), (planes, stats(got, enc_ref))
+
+
 # ---------------------------------------------------------------------------------------------
 # K3: single convs with each epilogue vs torch conv2d (fp32 reference of the same op)
 # ---------------------------------------------------------------------------------------------
