@@ -5,7 +5,7 @@
 // exact-fp32 encode each take about half of the run time and do not overlap -- both live on the shared-memory pipe
 // (scattered 4-byte tap stores, two 16-byte loads per 8 FFMA2).  Here the gather threads write the taps as 16-bit
 // (hi, lo) values straight into a K-major SWIZZLE_128B operand tile, one elected thread issues a handful of
-// tcgen05.mma (M = 128 pixels, N = 64, K = 48 / 176), and the epilogue pulls the 64 results of a pixel from TMEM.
+// tcgen05.mma (M = 128 pixels, N = 64, K = 48 / 192), and the epilogue pulls the 64 results of a pixel from TMEM.
 // The encode leaves the shared-memory pipe and the FMA pipe; what remains is the gather, which is bound by the DRAM
 // traffic of its 40-byte tap runs (each costs a 128-byte line).
 //
@@ -47,7 +47,7 @@ struct LookupTcParams {
     const float* bias;
     dkt_tensor out;                  // 64-channel NHWC slice
     int64_t P;
-    int C;                           // real K: levels * 9 (RAFT) or 2 * (Cg + 1) * 9 (IGEV)
+    int C;                           // K slots in use: row samples per pixel * LT_TS
 };
 
 // byte offset of element (row m, column k) inside one plane [KB][rows][128 B] of a K-major SWIZZLE_128B tile whose
@@ -57,19 +57,42 @@ __device__ __forceinline__ uint32_t sw128_off(int m, int k, uint32_t kb_bytes) {
            (uint32_t)((((k & 63) >> 3) ^ (m & 7)) << 4) + (uint32_t)(k & 7) * 2u;
 }
 
+// K slots per row sample: its 2r+1 = 9 taps + one zero.  Every sample then starts on an even k, so its taps leave as
+// five packed 32-bit stores (a pair never straddles a 16-byte swizzle chunk), and a row's byte offset is simply
+// ((k >> 6) * 16 KB + (k & 63) * 2) ^ ((m & 7) << 4).
+constexpr int LT_TS = 10;
+// staging buffer shared by (a) the RAFT gather's tap windows, [256 samples][LT_WS floats] (a sample's 10 taps lie in an
+// ALIGNED 16-float window that four lanes fetch with one 16-byte load each: a request then touches 8 lines instead of
+// 32, the L1 wavefronts that bounded the one-thread-per-sample gather, ncu r2j) and (b) the epilogue's output tile,
+// [128 pixels][64 x 16 bit], written per pixel and copied out as whole 128-byte rows.
+constexpr int LT_WS = 18;                        // window row stride in floats (18: 8-byte aligned, 2-way bank conflicts)
+constexpr uint32_t LT_STAGE_BYTES = 256 * LT_WS * 4;          // 18432 >= 128 * 128
+
 template <int AP>
-__device__ __forceinline__ void put_tap(uint8_t* a_buf, uint32_t plane_bytes, int m, int k, float v) {
-    const uint32_t off = sw128_off(m, k, LT_A_KB_BYTES);
-    uint16_t hi, lo;
-    split16(v, hi, lo);
-    *reinterpret_cast<uint16_t*>(a_buf + off) = hi;
-    if (AP == 2) *reinterpret_cast<uint16_t*>(a_buf + plane_bytes + off) = lo;
+__device__ __forceinline__ void put_taps(uint8_t* a_buf, uint32_t plane_bytes, int m, int k0, const float* v, float a) {
+    uint8_t* row = a_buf + (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u;
+    const uint32_t sw = (uint32_t)(m & 7) << 4;
+#pragma unroll
+    for (int t = 0; t < LT_TS; t += 2) {
+        const float t0 = (1.f - a) * v[t] + a * v[t + 1];
+        const float t1 = (t + 1 < LT_TS - 1) ? (1.f - a) * v[t + 1] + a * v[t + 2] : 0.f;
+        const int k = k0 + t;
+        const uint32_t off = (((uint32_t)(k >> 6) * LT_A_KB_BYTES) + (uint32_t)(k & 63) * 2u) ^ sw;
+        if (AP == 2) {
+            uint32_t hi, lo;
+            split16x2(t0, t1, hi, lo);
+            *reinterpret_cast<uint32_t*>(row + off) = hi;
+            *reinterpret_cast<uint32_t*>(row + plane_bytes + off) = lo;
+        } else {
+            *reinterpret_cast<uint32_t*>(row + off) = pack_hi16x2(t0, t1);
+        }
+    }
 }
 
 template <int R, int KB, int AP, int NBUF, bool GEO>
-__global__ void __launch_bounds__(LT_THREADS)
+__global__ void __launch_bounds__(LT_THREADS, GEO ? 2 : 3)
 lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
-    constexpr int T = 2 * R + 1;
+    static_assert(2 * R + 2 == LT_TS, "tap slots");
     constexpr uint32_t A_PLANE = KB * LT_A_KB_BYTES;
     constexpr uint32_t A_BUF = AP * A_PLANE;
     constexpr uint32_t W_PLANE = KB * LT_W_KB_BYTES;
@@ -77,7 +100,8 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;                                   // [NBUF][AP][KB][128 x 128 B]
     uint8_t* w_tile = a_ring + NBUF * A_BUF;                  // [2][KB][64 x 128 B]
-    float* s_x = reinterpret_cast<float*>(w_tile + 2 * W_PLANE);     // [128]
+    uint8_t* stage = w_tile + 2 * W_PLANE;                    // 18 KB: RAFT gather windows, then the epilogue's output rows
+    float* s_x = reinterpret_cast<float*>(stage + LT_STAGE_BYTES);   // [128]
     float* s_bias = s_x + LT_M;                               // [64]
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_bias + LT_N);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
@@ -100,7 +124,7 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc = idesc_bf16_m128(LT_N);
-    const int ksteps = (prm.C + 15) >> 4;                     // K16 steps that hold real channels
+    const int ksteps = (prm.C + 15) >> 4;                     // K16 steps that hold tap slots (prm.C = samples * LT_TS)
 
     const int64_t nchunks = (prm.P + LT_M - 1) / LT_M;
 
@@ -121,43 +145,85 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
         __syncthreads();
         uint8_t* a_buf = a_ring + (uint32_t)buf * A_BUF;
         if (!GEO) {
-            // RAFT: unit = (pixel, level); 4 lanes per pixel
-            for (int u = tid; u < npix * DKT_MAX_LEVELS; u += LT_THREADS) {
-                const int px = u >> 2, l = u & 3;
-                if (l >= prm.levels) continue;
-                float v[2 * R + 2], a;
-                sample_row_load<R>(prm.vol[l] + (p0 + px) * prm.vw[l], prm.vw[l], s_x[px] * (1.f / (float)(1 << l)), v, a);
+            // RAFT: a row sample = (pixel, level), 4 per pixel; two halves of 64 pixels = 256 samples each.
+            float* win = reinterpret_cast<float*>(stage);
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int half = 0; half < 2; ++half) {
+                // pass 1: lane (sample, part) fetches elements [a0, a0 + 4) of the sample's aligned 16-float window
 #pragma unroll
-                for (int k = 0; k < T; ++k) put_tap<AP>(a_buf, A_PLANE, px, l * T + k, (1.f - a) * v[k] + a * v[k + 1]);
+                for (int it = 0; it < 4; ++it) {
+                    const int u = tid + it * LT_THREADS;
+                    const int sl = u >> 2, part = u & 3;
+                    const int px = half * 64 + (sl >> 2), l = sl & 3;
+                    float4 val = zero4;
+                    if (px < npix && l < prm.levels) {
+                        const int Wl = prm.vw[l];
+                        const float xf = floorf(fminf(fmaxf(s_x[px] * (1.f / (float)(1 << l)), -1.0e6f), 1.0e6f));
+                        const int64_t rs = (p0 + px) * Wl;                 // first element of this pixel's row
+                        const int64_t e = rs + ((int)xf - R);              // first element the taps need
+                        const int64_t a0 = ((e >> 2) << 2) + 4 * part;     // this lane's 4 elements (16-byte aligned)
+                        if (a0 + 3 >= rs && a0 < rs + Wl) {
+                            const float* src = prm.vol[l] + a0;
+                            if (a0 >= rs && a0 + 4 <= rs + Wl) {
+                                val = __ldg(reinterpret_cast<const float4*>(src));
+                            } else {                                       // straddles a row end: zero outside the row
+                                val.x = (a0 + 0 >= rs && a0 + 0 < rs + Wl) ? __ldg(src + 0) : 0.f;
+                                val.y = (a0 + 1 >= rs && a0 + 1 < rs + Wl) ? __ldg(src + 1) : 0.f;
+                                val.z = (a0 + 2 >= rs && a0 + 2 < rs + Wl) ? __ldg(src + 2) : 0.f;
+                                val.w = (a0 + 3 >= rs && a0 + 3 < rs + Wl) ? __ldg(src + 3) : 0.f;
+                            }
+                        }
+                    }
+                    float2* dst = reinterpret_cast<float2*>(win + sl * LT_WS + part * 4);
+                    dst[0] = make_float2(val.x, val.y);
+                    dst[1] = make_float2(val.z, val.w);
+                }
+                __syncthreads();
+                // pass 2: one thread per sample interpolates its 9 taps out of the window
+                {
+                    const int sl = tid;
+                    const int px = half * 64 + (sl >> 2), l = sl & 3;
+                    if (px < npix && l < prm.levels) {
+                        const float x = fminf(fmaxf(s_x[px] * (1.f / (float)(1 << l)), -1.0e6f), 1.0e6f);
+                        const float xf = floorf(x);
+                        const int64_t e = (p0 + px) * prm.vw[l] + ((int)xf - R);
+                        const float* wv = win + sl * LT_WS + (int)(e - ((e >> 2) << 2));
+                        float v[2 * R + 3];
+#pragma unroll
+                        for (int k = 0; k < 2 * R + 2; ++k) v[k] = wv[k];
+                        v[2 * R + 2] = 0.f;
+                        put_taps<AP>(a_buf, A_PLANE, px, l * LT_TS, v, x - xf);
+                    }
+                }
+                __syncthreads();
             }
         } else {
             // IGEV: unit = (pixel, level, j): j < Cg one geometry channel (its taps sit Cg floats apart in the
             // (.., D, Cg) layout, so the Cg lanes of a (pixel, level) read consecutive floats), j == Cg the init-corr row.
             // Output channel order of the reference (geometry.py:36-57): per level [geo (c-major, tap-minor), init].
-            const int Cg = prm.Cg, G1 = Cg + 1, G = 2 * G1;
+            constexpr int Cg = 8, G1 = Cg + 1, G = 2 * G1;      // host checks prm.Cg == 8 (IGEV's 8 geometry channels)
             constexpr int GU = 3;                 // row samples whose loads a thread has in flight before interpolating
             for (int u0 = tid; u0 < npix * G; u0 += LT_THREADS * GU) {
-                float v[GU][2 * R + 2], av[GU];
+                float v[GU][2 * R + 3], av[GU];
 #pragma unroll
                 for (int g = 0; g < GU; ++g) {
                     const int u = u0 + g * LT_THREADS;
                     if (u >= npix * G) continue;
                     const int px = u / G, gi = u - px * G;
-                    const int l = gi / G1, j = gi - l * G1;
+                    const int l = gi >= G1, j = gi - l * G1;
                     const int64_t p = p0 + px;
                     const float d = s_x[px];
                     const float inv = l ? 0.5f : 1.f;
+                    v[g][2 * R + 2] = 0.f;
                     if (j < Cg) {
                         const int Dl = l ? prm.D / 2 : prm.D;
                         const float x = d * inv, xf = floorf(x);
                         av[g] = x - xf;
-                        const int i0 = (int)xf - R;
-                        const float* row = prm.geo[l] + p * Dl * Cg + j;
+                        const int i0 = (int)fminf(fmaxf(xf, -1.0e6f), 1.0e6f) - R;
+                        const float* ptr = prm.geo[l] + (p * Dl + i0) * Cg + j;     // only dereferenced inside [0, Dl)
 #pragma unroll
-                        for (int k = 0; k < 2 * R + 2; ++k) {
-                            const int idx = i0 + k;
-                            v[g][k] = (idx >= 0 && idx < Dl) ? __ldg(row + (int64_t)idx * Cg) : 0.f;
-                        }
+                        for (int k = 0; k < 2 * R + 2; ++k)
+                            v[g][k] = ((unsigned)(i0 + k) < (unsigned)Dl) ? __ldg(ptr + k * Cg) : 0.f;
                     } else {
                         const int Wl = prm.vw[l];
                         const float x = (float)(p % prm.W1);
@@ -169,9 +235,7 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
                     const int u = u0 + g * LT_THREADS;
                     if (u >= npix * G) continue;
                     const int px = u / G, gi = u - px * G;
-#pragma unroll
-                    for (int k = 0; k < T; ++k)
-                        put_tap<AP>(a_buf, A_PLANE, px, gi * T + k, (1.f - av[g]) * v[g][k] + av[g] * v[g][k + 1]);
+                    put_taps<AP>(a_buf, A_PLANE, px, gi * LT_TS, v[g], av[g]);
                 }
             }
         }
@@ -213,38 +277,52 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
             const int npix = (int)((prm.P - p0) < LT_M ? (prm.P - p0) : LT_M);
             const int q = warp & 3, c0 = (warp >> 2) * 32;
             const int m = q * 32 + lane;
-            float v[32], v2[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            tmem_ld32(taddr, v);
-            tmem_ld32(taddr + LT_N, v2);
-            tmem_ld_wait();
-            if (m < npix) {
-                const dkt_tensor& o = prm.out;
-                const int64_t off = (p0 + m) * o.C + o.c_begin + c0;
+            const dkt_tensor& o = prm.out;
+            const int64_t off0 = (p0 + m) * o.C + o.c_begin + c0;
+            // 16-bit planes leave through the staging tile: a thread owns a pixel's 32 channels (its TMEM lane), the copy-out
+            // writes whole 128-byte rows.  Row r keeps its 16-byte chunk c at position c ^ (r & 7): conflict-free both ways.
+            const int nplanes = o.hi ? (o.lo ? 2 : 1) : 0;
+            for (int pl = 0; pl < (nplanes ? nplanes : 1); ++pl) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + v2[j] + s_bias[c0 + j], 0.f);
-                if (o.f32) {
+                for (int cc = 0; cc < 32; cc += 16) {         // 16 columns at a time: 32 live accumulator registers
+                    float v[16], v2[16];
+                    tmem_ld16(taddr + cc, v);
+                    tmem_ld16(taddr + LT_N + cc, v2);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(o.f32 + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-                if (o.hi) {
-                    if (o.lo) {
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + v2[j] + s_bias[c0 + cc + j], 0.f);
+                    if (pl == 0 && o.f32 && m < npix) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint32_t h[4], l[4];
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) split16x2(v[j + 2 * t], v[j + 2 * t + 1], h[t], l[t]);
-                            *reinterpret_cast<uint4*>(o.hi + off + j) = make_uint4(h[0], h[1], h[2], h[3]);
-                            *reinterpret_cast<uint4*>(o.lo + off + j) = make_uint4(l[0], l[1], l[2], l[3]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            *reinterpret_cast<uint4*>(o.hi + off + j) =
-                                make_uint4(pack_hi16x2(v[j], v[j + 1]), pack_hi16x2(v[j + 2], v[j + 3]),
-                                           pack_hi16x2(v[j + 4], v[j + 5]), pack_hi16x2(v[j + 6], v[j + 7]));
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(o.f32 + off0 + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     }
+                    if (nplanes) {
+                        uint32_t w16[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            uint32_t h, l;
+                            split16x2(v[2 * t], v[2 * t + 1], h, l);
+                            w16[t] = pl == 0 ? h : l;
+                        }
+                        const int ch0 = (c0 + cc) >> 3;       // first of this pass's two 16-byte chunks
+                        uint8_t* rowp = stage + m * 128;
+                        *reinterpret_cast<uint4*>(rowp + (((ch0 + 0) ^ (m & 7)) << 4)) = make_uint4(w16[0], w16[1], w16[2], w16[3]);
+                        *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ (m & 7)) << 4)) = make_uint4(w16[4], w16[5], w16[6], w16[7]);
+                    }
+                }
+                if (nplanes) {
+                    __syncthreads();
+                    uint16_t* const dstp = pl == 0 ? o.hi : o.lo;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int idx = tid + i * LT_THREADS;  // 128 rows x 8 chunks
+                        const int r = idx >> 3, c = idx & 7;
+                        if (r < npix)
+                            *reinterpret_cast<uint4*>(dstp + (p0 + r) * o.C + o.c_begin + c * 8) =
+                                *reinterpret_cast<const uint4*>(stage + r * 128 + ((c ^ (r & 7)) << 4));
+                    }
+                    if (pl + 1 < nplanes) __syncthreads();    // the lo plane reuses the tile
                 }
             }
         }
@@ -305,10 +383,12 @@ static int check_enc_out(const dkt_tensor* t) {
 
 template <int KB, int AP, int NBUF, bool GEO>
 static int launch_lookup_tc(const LookupTcParams& prm, cudaStream_t st) {
-    constexpr size_t smem = 1024 + (size_t)NBUF * AP * KB * LT_A_KB_BYTES + 2 * (size_t)KB * LT_W_KB_BYTES + (LT_M + LT_N) * 4 + 64;
+    constexpr size_t smem = 1024 + (size_t)NBUF * AP * KB * LT_A_KB_BYTES + 2 * (size_t)KB * LT_W_KB_BYTES + LT_STAGE_BYTES +
+                            (LT_M + LT_N) * 4 + 64;
     DKT_ENSURE_SMEM(smem, lookup_tc_kernel<4, KB, AP, NBUF, GEO>);
     const int per_sm = (int)((227 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((227 * 1024) / (smem + 1024));
-    const int ctas_sm = per_sm > 4 ? 4 : per_sm;             // TMEM: 128 columns per CTA, 512 per SM
+    const int by_regs = GEO ? 2 : 3;                         // __launch_bounds__ of the kernel
+    const int ctas_sm = per_sm > by_regs ? by_regs : per_sm;  // (TMEM: 128 columns per CTA, 512 per SM)
     const int64_t chunks = ceil_div64(prm.P, LT_M), cap = (int64_t)device_sms() * ctas_sm;
     lookup_tc_kernel<4, KB, AP, NBUF, GEO><<<(unsigned)(chunks < cap ? chunks : cap), LT_THREADS, smem, st>>>(prm);
     DKT_RETURN_LAST();
@@ -330,16 +410,21 @@ extern "C" int dkt_corr1d_lookup_enc_tc(const float* const* pyr, int levels, int
     for (int l = 0; l < DKT_MAX_LEVELS; ++l) {
         prm.vol[l] = l < levels ? pyr[l] : nullptr;
         prm.vw[l] = w;
-        if (l < levels) DKT_CHECK_ARG(pyr[l] != nullptr && w > 0);
+        if (l < levels) {
+            DKT_CHECK_ARG(pyr[l] != nullptr && w > 0);
+            if (reinterpret_cast<uintptr_t>(pyr[l]) & 15) return DKT_E_ALIGNMENT;      // 16-byte window loads
+        }
         w /= 2;
     }
     prm.levels = levels; prm.W1 = W1;
     prm.coords = coords_x; prm.delta = delta; prm.delta_C = delta_C; prm.flow = flow;
     prm.w_img = w_img; prm.bias = enc_b; prm.out = *enc_out;
     prm.P = (int64_t)B * H * W1;
-    prm.C = levels * 9;
-    return tap_planes == 2 ? launch_lookup_tc<1, 2, 2, false>(prm, (cudaStream_t)stream)
-                           : launch_lookup_tc<1, 1, 2, false>(prm, (cudaStream_t)stream);
+    prm.C = levels * LT_TS;
+    // one tap tile per CTA (48 / 32 KB of shared memory): three CTAs per SM hide the gather's latency better than a
+    // second tile per CTA would
+    return tap_planes == 2 ? launch_lookup_tc<1, 2, 1, false>(prm, (cudaStream_t)stream)
+                           : launch_lookup_tc<1, 1, 1, false>(prm, (cudaStream_t)stream);
 }
 
 extern "C" int dkt_geo_pool_dc(const float* gev, float* geo0, float* geo1, int B, int C, int D, int H, int W, void* stream) {
@@ -359,7 +444,7 @@ extern "C" int dkt_geo_lookup_enc_tc(const float* geo0, const float* geo1, const
     DKT_CHECK_ARG(geo0 && geo1 && init0 && init1 && disp && w_img && enc_b);
     DKT_CHECK_ARG(B > 0 && H > 0 && W > 1 && C > 0 && D > 1);
     if (int rc = check_enc_out(enc_out)) return rc;
-    if (radius != 4 || 2 * (C + 1) * 9 > 192) return DKT_E_UNSUPPORTED;
+    if (radius != 4 || C != 8) return DKT_E_UNSUPPORTED;      // IGEV's 8 geometry channels: 18 row samples x 10 slots = 180 <= 192
     if (tap_planes != 1 && tap_planes != 2) return DKT_E_INVALID;
     if (delta) DKT_CHECK_ARG(delta_C > 0);
     if (reinterpret_cast<uintptr_t>(w_img) & 15) return DKT_E_ALIGNMENT;
@@ -371,7 +456,7 @@ extern "C" int dkt_geo_lookup_enc_tc(const float* geo0, const float* geo1, const
     prm.coords = disp; prm.delta = delta; prm.delta_C = delta_C; prm.flow = nullptr;
     prm.w_img = w_img; prm.bias = enc_b; prm.out = *enc_out;
     prm.P = (int64_t)B * H * W;
-    prm.C = 2 * (C + 1) * 9;
+    prm.C = 2 * (C + 1) * LT_TS;
     return tap_planes == 2 ? launch_lookup_tc<3, 2, 1, true>(prm, (cudaStream_t)stream)
                            : launch_lookup_tc<3, 1, 1, true>(prm, (cudaStream_t)stream);
 }

@@ -274,12 +274,13 @@ def pack_lookup_tc(weight: torch.Tensor, bias: torch.Tensor):
     [2 planes (hi, lo)][KB][64 rows x 64 k] 16-bit in K-major SWIZZLE_128B order (csrc/lookup_tc.cu sw128_off)."""
     dev, weight, bias = _pack_src(weight, bias)
     N, C = weight.shape[0], weight.shape[1]
-    assert N == 64
-    KB = (C + 63) // 64
+    assert N == 64 and C % 9 == 0
     w = weight.detach().float().reshape(N, C)
     hi, lo = split16(w)
     n = torch.arange(N, device=w.device).view(N, 1).expand(N, C)
-    k = torch.arange(C, device=w.device).view(1, C).expand(N, C)
+    c = torch.arange(C, device=w.device).view(1, C).expand(N, C)
+    k = (c // 9) * 10 + c % 9              # the kernel gives every row sample 10 K slots: its 9 taps + one zero (LT_TS)
+    KB = ((C // 9) * 10 + 63) // 64
     off = (k >> 6) * (64 * 128) + (n >> 3) * 1024 + (n & 7) * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + (k & 7) * 2
     idx = (off // 2).reshape(-1)
     img = torch.zeros(2, KB * 64 * 64, dtype=hi.dtype, device=w.device)
