@@ -22,6 +22,8 @@
 // (pixel, level) are ONE 320-byte run instead of 8 runs of 40 bytes in 8 different 192-byte rows.
 #include "common.cuh"
 #include "tc.cuh"
+#include <stdlib.h>
+#include <stdio.h>
 
 namespace dkt {
 
@@ -48,6 +50,8 @@ struct LookupTcParams {
     dkt_tensor out;                  // 64-channel NHWC slice
     int64_t P;
     int C;                           // K slots in use: row samples per pixel * LT_TS
+    int flags;                       // bit 0: RAFT gather through aligned 16-byte windows (else one thread per row sample);
+                                     // bit 1: 16-bit output planes through the staging tile (else per-thread stores)
 };
 
 // byte offset of element (row m, column k) inside one plane [KB][rows][128 B] of a K-major SWIZZLE_128B tile whose
@@ -67,6 +71,7 @@ constexpr int LT_TS = 10;
 // [128 pixels][64 x 16 bit], written per pixel and copied out as whole 128-byte rows.
 constexpr int LT_WS = 18;                        // window row stride in floats (18: 8-byte aligned, 2-way bank conflicts)
 constexpr uint32_t LT_STAGE_BYTES = 256 * LT_WS * 4;          // 18432 >= 128 * 128
+constexpr int LT_DEFAULT_FLAGS = 2;              // staged epilogue, one-thread-per-sample gather (profiles/r2o_lookup_tc_sweep.txt)
 
 template <int AP>
 __device__ __forceinline__ void put_taps(uint8_t* a_buf, uint32_t plane_bytes, int m, int k0, const float* v, float a) {
@@ -100,8 +105,11 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;                                   // [NBUF][AP][KB][128 x 128 B]
     uint8_t* w_tile = a_ring + NBUF * A_BUF;                  // [2][KB][64 x 128 B]
-    uint8_t* stage = w_tile + 2 * W_PLANE;                    // 18 KB: RAFT gather windows, then the epilogue's output rows
-    float* s_x = reinterpret_cast<float*>(stage + LT_STAGE_BYTES);   // [128]
+    // staging tile: RAFT has room for its own; IGEV (2 x 48 KB of operands) lets it alias the first K block of the tap
+    // tile, which is dead between the MMAs' completion and the next gather and holds tap slots only (every column is
+    // rewritten by the next gather, so no stale value can meet a zero weight as inf x 0)
+    uint8_t* stage = GEO ? a_ring : w_tile + 2 * W_PLANE;
+    float* s_x = reinterpret_cast<float*>(w_tile + 2 * W_PLANE + (GEO ? 0 : LT_STAGE_BYTES));   // [128]
     float* s_bias = s_x + LT_M;                               // [64]
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_bias + LT_N);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
@@ -145,6 +153,17 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
         __syncthreads();
         uint8_t* a_buf = a_ring + (uint32_t)buf * A_BUF;
         if (!GEO) {
+            if (!(prm.flags & 1)) {
+                // RAFT: unit = (pixel, level); 4 lanes per pixel; a thread issues its 10 loads back to back
+                for (int u = tid; u < npix * DKT_MAX_LEVELS; u += LT_THREADS) {
+                    const int px = u >> 2, l = u & 3;
+                    if (l >= prm.levels) continue;
+                    float v[2 * R + 3], a;
+                    sample_row_load<R>(prm.vol[l] + (p0 + px) * prm.vw[l], prm.vw[l], s_x[px] * (1.f / (float)(1 << l)), v, a);
+                    v[2 * R + 2] = 0.f;
+                    put_taps<AP>(a_buf, A_PLANE, px, l * LT_TS, v, a);
+                }
+            } else {
             // RAFT: a row sample = (pixel, level), 4 per pixel; two halves of 64 pixels = 256 samples each.
             float* win = reinterpret_cast<float*>(stage);
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -196,6 +215,7 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
                     }
                 }
                 __syncthreads();
+            }
             }
         } else {
             // IGEV: unit = (pixel, level, j): j < Cg one geometry channel (its taps sit Cg floats apart in the
@@ -283,6 +303,7 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
             // 16-bit planes leave through the staging tile: a thread owns a pixel's 32 channels (its TMEM lane), the copy-out
             // writes whole 128-byte rows.  Row r keeps its 16-byte chunk c at position c ^ (r & 7): conflict-free both ways.
             const int nplanes = o.hi ? (o.lo ? 2 : 1) : 0;
+            const bool staged = (prm.flags & 2) != 0;
             for (int pl = 0; pl < (nplanes ? nplanes : 1); ++pl) {
 #pragma unroll
                 for (int cc = 0; cc < 32; cc += 16) {         // 16 columns at a time: 32 live accumulator registers
@@ -305,13 +326,19 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
                             split16x2(v[2 * t], v[2 * t + 1], h, l);
                             w16[t] = pl == 0 ? h : l;
                         }
-                        const int ch0 = (c0 + cc) >> 3;       // first of this pass's two 16-byte chunks
-                        uint8_t* rowp = stage + m * 128;
-                        *reinterpret_cast<uint4*>(rowp + (((ch0 + 0) ^ (m & 7)) << 4)) = make_uint4(w16[0], w16[1], w16[2], w16[3]);
-                        *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ (m & 7)) << 4)) = make_uint4(w16[4], w16[5], w16[6], w16[7]);
+                        if (staged) {
+                            const int ch0 = (c0 + cc) >> 3;   // first of this pass's two 16-byte chunks
+                            uint8_t* rowp = stage + m * 128;
+                            *reinterpret_cast<uint4*>(rowp + (((ch0 + 0) ^ (m & 7)) << 4)) = make_uint4(w16[0], w16[1], w16[2], w16[3]);
+                            *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ (m & 7)) << 4)) = make_uint4(w16[4], w16[5], w16[6], w16[7]);
+                        } else if (m < npix) {
+                            uint16_t* const dp = (pl == 0 ? o.hi : o.lo) + off0 + cc;
+                            *reinterpret_cast<uint4*>(dp) = make_uint4(w16[0], w16[1], w16[2], w16[3]);
+                            *reinterpret_cast<uint4*>(dp + 8) = make_uint4(w16[4], w16[5], w16[6], w16[7]);
+                        }
                     }
                 }
-                if (nplanes) {
+                if (nplanes && staged) {
                     __syncthreads();
                     uint16_t* const dstp = pl == 0 ? o.hi : o.lo;
 #pragma unroll
@@ -382,13 +409,38 @@ static int check_enc_out(const dkt_tensor* t) {
 }
 
 template <int KB, int AP, int NBUF, bool GEO>
-static int launch_lookup_tc(const LookupTcParams& prm, cudaStream_t st) {
-    constexpr size_t smem = 1024 + (size_t)NBUF * AP * KB * LT_A_KB_BYTES + 2 * (size_t)KB * LT_W_KB_BYTES + LT_STAGE_BYTES +
-                            (LT_M + LT_N) * 4 + 64;
+static int launch_lookup_tc(LookupTcParams prm, cudaStream_t st) {
+    // A/B knob (default = what measured best on B200, profiles/r2m_lookup_variants.txt)
+    static const int s_flags = [] { const char* v = getenv("DKT_LOOKUP_FLAGS"); return v ? atoi(v) : -1; }();
+    prm.flags = s_flags >= 0 ? s_flags : LT_DEFAULT_FLAGS;
+    constexpr size_t smem = 1024 + (size_t)NBUF * AP * KB * LT_A_KB_BYTES + 2 * (size_t)KB * LT_W_KB_BYTES +
+                            (GEO ? 0 : LT_STAGE_BYTES) + (LT_M + LT_N) * 4 + 64;
     DKT_ENSURE_SMEM(smem, lookup_tc_kernel<4, KB, AP, NBUF, GEO>);
-    const int per_sm = (int)((227 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((227 * 1024) / (smem + 1024));
-    const int by_regs = GEO ? 2 : 3;                         // __launch_bounds__ of the kernel
-    const int ctas_sm = per_sm > by_regs ? by_regs : per_sm;  // (TMEM: 128 columns per CTA, 512 per SM)
+    // The gather lives on the L1 cache (a row sample's 10 loads touch one or two lines; with the carve-out at its maximum
+    // the same kernel is 2x slower, profiles/r2n_lookup_variants.txt), so the shared-memory carve-out is requested
+    // explicitly: just enough for the CTAs the grid is sized for.
+    static const int s_carve = [] { const char* v = getenv("DKT_LOOKUP_CARVEOUT"); return v ? atoi(v) : -2; }();
+    static const int s_ctas = [] { const char* v = getenv("DKT_LOOKUP_CTAS"); return v ? atoi(v) : 0; }();
+    const int by_smem = (int)((227 * 1024) / (smem + 1024));
+    // __launch_bounds__ of the kernel; RAFT with (hi, lo) taps: 2 CTAs of 68 KB leave the L1 more than a third CTA gives
+    const int by_regs = GEO ? 2 : (AP == 2 ? 2 : 3);
+    int ctas_sm = by_smem < 1 ? 1 : (by_smem > by_regs ? by_regs : by_smem);
+    if (s_ctas > 0 && s_ctas < ctas_sm) ctas_sm = s_ctas;
+    {
+        static std::atomic<uint64_t> done{0};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+        const uint64_t bit = 1ull << (dev & 63);
+        if (dev > 63 || !(done.load(std::memory_order_acquire) & bit)) {
+            // percent of the 228 KB maximum that holds ctas_sm CTAs (+1 KB each of system use), rounded up
+            int pct = s_carve != -2 ? s_carve : (int)((ctas_sm * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+            if (pct > 100) pct = 100;
+            cudaError_t ce = cudaFuncSetAttribute(lookup_tc_kernel<4, KB, AP, NBUF, GEO>,
+                                                  cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            if (ce != cudaSuccess) return (int)ce;
+            done.fetch_or(bit, std::memory_order_release);
+        }
+    }
     const int64_t chunks = ceil_div64(prm.P, LT_M), cap = (int64_t)device_sms() * ctas_sm;
     lookup_tc_kernel<4, KB, AP, NBUF, GEO><<<(unsigned)(chunks < cap ? chunks : cap), LT_THREADS, smem, st>>>(prm);
     DKT_RETURN_LAST();

@@ -131,11 +131,11 @@ class UpdateEngine:
         # B200 against the reference goldens (profiles/r2f_parity_accsplit.txt): +0.2..0.5e-4 px, -3 % step time.
         self.coarse1 = self.gru2 and os.environ.get("DKT_COARSE_GRU_TERMS", "1") == "1"
         # fused lookup + convc1 with the 1x1 contraction on tcgen05 (csrc/lookup_tc.cu); 0 = the exact-fp32 CUDA-core form.
-        # Taps as (hi, lo) pairs (3 MMAs per K step) for RAFT-Stereo; IGEV-Stereo's 162-channel tile follows the motion
-        # encoder's policy (hi only when menc2: a pair would leave one CTA per SM).
+        # The taps follow the motion encoder's policy: hi plane only (2 MMAs per K step) when menc2 -- the study's convc1
+        # row: +6.8e-5 px; RAFT 43.7 vs 51.6 us per launch, IGEV 130 vs 231 us (a (hi, lo) tile leaves one CTA per SM).
         self.lookup_tc = impl == "tc" and self.fused_enc and os.environ.get("DKT_LOOKUP_TC", "1") == "1"
         taps = os.environ.get("DKT_LOOKUP_TAP_PLANES")
-        self.lookup_tap_planes = int(taps) if taps else (1 if (self.igev and self.menc2) else 2)
+        self.lookup_tap_planes = int(taps) if taps else (1 if self.menc2 else 2)
         self.lookup_tc_w = None
         self.side_stream = None
         self.weights: Optional[Dict[str, ops.ConvWeights]] = None
