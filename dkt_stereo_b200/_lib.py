@@ -34,7 +34,7 @@ class DktEpilogue(C.Structure):
 
 
 ABI_VERSION = 3      # include/dkt_stereo_b200.h: DKT_ABI_VERSION
-ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_LEAKY = 0, 1, 2, 3, 4
 EPI_LINEAR, EPI_GRU_ZR, EPI_GRU_Q, EPI_PROJ = 0, 1, 2, 3
 PROJ_LD = 12
 MAX_LEVELS = 4
@@ -73,6 +73,8 @@ SIGNATURES = {
     "dkt_interp": [_TP, _TP, _I, _I, _I, _I, _I, _P],
     "dkt_convex_upsample": [_P, _I, _P, _P, _I, _I, _I, _I, _P],
     "dkt_context_upsample": [_P, _P, _P, _F, _F, _I, _I, _I, _P],
+    "dkt_pixel_shuffle2": [_P, _I, _I, _TP, _I, _I, _I, _P],
+    "dkt_context_upsample_logits": [_P, _P, _I, _P, _F, _F, _I, _I, _I, _P],
     "dkt_nchw_to_nhwc": [_P, _P, _TP, _I, _I, _I, _I, _P],
     "dkt_nhwc_to_nchw": [_TP, _P, _I, _I, _I, _I, _P],
     "dkt_stem_rows_bf16x2": [_P, _I64, _I64, _I64, _I64, _F, _F, _P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -131,6 +131,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
         case DKT_ACT_RELU:    return fmaxf(x, 0.0f);
         case DKT_ACT_SIGMOID: return sigmoidf_acc(x);
         case DKT_ACT_TANH:    return tanhf(x);
+        case DKT_ACT_LEAKY:   return x > 0.f ? x : 0.01f * x;
         default:              return x;
     }
 }

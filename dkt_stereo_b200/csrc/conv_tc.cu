@@ -94,6 +94,7 @@ __device__ __forceinline__ float act_ct(float x) {
     if constexpr (ACT == DKT_ACT_RELU) return fmaxf(x, 0.0f);
     else if constexpr (ACT == DKT_ACT_SIGMOID) return sigmoidf_acc(x);
     else if constexpr (ACT == DKT_ACT_TANH) return tanhf(x);
+    else if constexpr (ACT == DKT_ACT_LEAKY) return x > 0.f ? x : 0.01f * x;
     else return x;
 }
 
@@ -1210,6 +1211,7 @@ static int launch_conv(ConvFamily fam, const TcConvParams& prm, unsigned grid, s
         case DKT_ACT_RELU:    return launch_conv_ka<DKT_EPI_LINEAR, DKT_ACT_RELU>(fam, prm, grid, smem_bytes, st);
         case DKT_ACT_SIGMOID: return launch_conv_ka<DKT_EPI_LINEAR, DKT_ACT_SIGMOID>(fam, prm, grid, smem_bytes, st);
         case DKT_ACT_TANH:    return launch_conv_ka<DKT_EPI_LINEAR, DKT_ACT_TANH>(fam, prm, grid, smem_bytes, st);
+        case DKT_ACT_LEAKY:   return launch_conv_ka<DKT_EPI_LINEAR, DKT_ACT_LEAKY>(fam, prm, grid, smem_bytes, st);
         default:              return DKT_E_INVALID;
     }
 }

@@ -174,6 +174,51 @@ context_upsample_kernel(const float* __restrict__ disp, const float* __restrict_
     out[t] = out_scale * acc;
 }
 
+// ---- IGEV upsample_disp plumbing -------------------------------------------------------------------
+// sub-pixel rearrangement of a deconv-as-conv result: one thread per (input pixel, parity, 4-channel group)
+__global__ void __launch_bounds__(256)
+pixel_shuffle2_kernel(const float* __restrict__ src, int src_C, int group, dkt_tensor dst, int C4, int H, int W, int64_t total) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int q = (int)(t % C4);
+    int64_t r = t / C4;
+    const int par = (int)(r & 3);
+    r >>= 2;                                      // input pixel index (b*H + y)*W + x
+    const int x = (int)(r % W);
+    const int64_t by = r / W;                     // b*H + y
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * src_C + par * group + q * 4));
+    const int64_t po = (by * 2 + (par >> 1)) * (2 * W) + 2 * x + (par & 1);      // b*(2H) + 2y+py rows of 2W pixels
+    store_all4(dst, po, q * 4, v);
+}
+
+// softmax over the 9 logits of a full-resolution pixel + the 3x3 neighbourhood combination of context_upsample
+__global__ void __launch_bounds__(256)
+context_upsample_logits_kernel(const float* __restrict__ disp, const float* __restrict__ logits, int logit_C,
+                               float* __restrict__ out, float in_scale, float out_scale, int H, int W, int64_t total) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int W4 = W * 4, H4 = H * 4;
+    const int X = (int)(t % W4);
+    int64_t r = t / W4;
+    const int Y = (int)(r % H4);
+    const int64_t b = r / H4;
+    const int y = Y >> 2, x = X >> 2;
+    // logits live at half resolution, parity-major: pixel (Y >> 1, X >> 1), group (Y & 1) * 2 + (X & 1)
+    const float* lp = logits + ((b * (2 * H) + (Y >> 1)) * (int64_t)(2 * W) + (X >> 1)) * logit_C + (((Y & 1) << 1) | (X & 1)) * 9;
+    float l[9], mx = -3.0e38f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { l[k] = __ldg(lp + k); mx = fmaxf(mx, l[k]); }
+    float den = 0.f, acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float e = expf(l[k] - mx);
+        den += e;
+        const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc = fmaf(e, in_scale * __ldg(disp + (b * H + yy) * (int64_t)W + xx), acc);
+    }
+    out[t] = out_scale * (acc / den);
+}
+
 // ---- layout conversions ------------------------------------------------------------------------
 // generic strided (b, c, y, x) fp32 source -> NHWC slice, 32x32 smem transpose over (c, x) of one (b,y)
 __global__ void __launch_bounds__(256)
@@ -295,6 +340,31 @@ extern "C" int dkt_context_upsample(const float* disp, const float* weights, flo
     const int64_t total = (int64_t)B * H * W * 16;
     context_upsample_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
         disp, weights, out, in_scale, out_scale, H, W, total);
+    DKT_RETURN_LAST();
+}
+
+extern "C" int dkt_pixel_shuffle2(const float* src, int src_C, int group, const dkt_tensor* dst, int B, int H, int W,
+                                  void* stream) {
+    DKT_CHECK_ARG(src);
+    int rc = check_slice(dst, false);
+    if (rc) return rc;
+    rc = check_vec4(dst);
+    if (rc) return rc;
+    const int C = dst->c_count;
+    DKT_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && group >= C && src_C >= 3 * group + C);
+    if ((C % 4) || (group % 4) || (src_C % 4) || (reinterpret_cast<uintptr_t>(src) & 15)) return DKT_E_ALIGNMENT;
+    const int64_t total = (int64_t)B * H * W * 4 * (C / 4);
+    pixel_shuffle2_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(src, src_C, group, *dst, C / 4, H, W, total);
+    DKT_RETURN_LAST();
+}
+
+extern "C" int dkt_context_upsample_logits(const float* disp, const float* logits, int logit_C, float* out, float in_scale,
+                                           float out_scale, int B, int H, int W, void* stream) {
+    DKT_CHECK_ARG(disp && logits && out);
+    DKT_CHECK_ARG(B > 0 && H > 0 && W > 0 && logit_C >= 36);
+    const int64_t total = (int64_t)B * H * W * 16;
+    context_upsample_logits_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        disp, logits, logit_C, out, in_scale, out_scale, H, W, total);
     DKT_RETURN_LAST();
 }
 

@@ -81,6 +81,12 @@ class IGEVStereo(nn.Module):
         self._seen = set()
         self._vol = None
         self._vol_key = None
+        # upsample_disp (spx_2_gru deconv + conv, spx_gru deconv, softmax, context_upsample) on the library's kernels
+        self.native_upsample = (os.environ.get("DKT_NATIVE_UPSAMPLE", "1") == "1" and self.impl == "tc"
+                                and not getattr(args, "mixed_precision", False))
+        self._up_w = None
+        self._up_sig = None
+        self._up_buf = None
 
     def freeze_bn(self):
         for m in self.modules():
@@ -169,9 +175,62 @@ class IGEVStereo(nn.Module):
         for _ in range(iters):
             self.engine.step(self._lookup, with_mask=False)
 
+    # ---- upsample_disp on libdkt kernels ------------------------------------------------------------
+    def _pack_upsample(self) -> None:
+        """spx_2_gru.conv1 (ConvTranspose2d 32->32, k4 s2 p1, + BN + LeakyReLU), spx_2_gru.conv2 (3x3 64->64 + BN + LeakyReLU)
+        and spx_gru (ConvTranspose2d 64->9, k4 s2 p1, bias) as three 3x3 tensor-core convs: a k4 s2 p1 transposed conv is a
+        3x3 conv producing the four output parities as channel groups (ops.deconv4x4s2_as_conv3x3); eval-mode BatchNorm is
+        folded into weights and bias."""
+        mods = (self.spx_2_gru, self.spx_gru)
+        sig = tuple((p.data_ptr(), p._version) for m in mods for p in list(m.parameters()) + list(m.buffers()))
+        if self._up_w is not None and sig == self._up_sig:
+            return
+        c1, c2, dg = self.spx_2_gru.conv1, self.spx_2_gru.conv2, self.spx_gru[0]
+        assert c1.conv.weight.shape == (32, 32, 4, 4) and c2.conv.weight.shape == (64, 64, 3, 3) and dg.weight.shape == (64, 9, 4, 4)
+
+        def bn4(bn, rep):
+            return tuple(t.detach().repeat(rep) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var))
+
+        w = {}
+        w["d1"] = ops.pack_conv_general(ops.deconv4x4s2_as_conv3x3(c1.conv.weight.detach()), None, cin_pad=64,
+                                        bn=bn4(c1.bn, 4), bn_eps=c1.bn.eps)
+        w["c2"] = ops.pack_conv_general(c2.conv.weight.detach(), None, bn=bn4(c2.bn, 1), bn_eps=c2.bn.eps)
+        w["d3"] = ops.pack_conv_general(ops.deconv4x4s2_as_conv3x3(dg.weight.detach()), dg.bias.detach().repeat(4))
+        self._up_w, self._up_sig = w, sig
+
+    def _upsample_native(self, disp: torch.Tensor, stem_2x: torch.Tensor) -> torch.Tensor:
+        """reference igev_stereo.py:140-148 on kernels; mask_feat_4 is read from the engine's MH buffer (NHWC, 64 channels of
+        which 32 are real), where the mask head left it as a 16-bit (hi, lo) pair."""
+        eng = self.engine
+        B, (h, w), dev = eng.B, eng.hw[0], eng.device
+        assert stem_2x.shape == (B, 32, 2 * h, 2 * w), "upsample_disp: stem_2x must be at twice the mask features' resolution"
+        self._pack_upsample()
+        key = (B, h, w, str(dev))
+        if self._up_buf is None or self._up_buf[0] != key:
+            dt = L.split_dtype()
+            z = lambda *sh, d=torch.float32: torch.zeros(*sh, device=dev, dtype=d)       # noqa: E731
+            self._up_buf = (key, dict(u1=z(B, h, w, 128), x2h=z(B, 2 * h, 2 * w, 64, d=dt), x2l=z(B, 2 * h, 2 * w, 64, d=dt),
+                                      yh=z(B, 2 * h, 2 * w, 64, d=dt), yl=z(B, 2 * h, 2 * w, 64, d=dt), zl=z(B, 2 * h, 2 * w, 36)))
+        b, Wt, TS, E = self._up_buf[1], self._up_w, L.tensor_slice, ops.make_epilogue
+        mh = eng.MH
+        # spx_2_gru.conv1: deconv + BN + LeakyReLU -> four parities as 4 x 32 channels at 1/4 resolution, then to 1/2
+        ops.conv2d_ex([TS(None, mh["hi"], mh["lo"], 0, 64)], Wt["d1"],
+                      E(L.EPI_LINEAR, TS(b["u1"], None, None, 0, 128), act=L.ACT_LEAKY, bias=Wt["d1"].bias), B, h, w)
+        ops.pixel_shuffle2(b["u1"], 32, TS(None, b["x2h"], b["x2l"], 0, 32), B, h, w)
+        ops.nchw_to_nhwc(stem_2x, TS(None, b["x2h"], b["x2l"], 32, 32))                  # torch.cat((x, rem), 1)
+        # spx_2_gru.conv2: 3x3 64 -> 64 + BN + LeakyReLU at 1/2 resolution
+        ops.conv2d_ex([TS(None, b["x2h"], b["x2l"], 0, 64)], Wt["c2"],
+                      E(L.EPI_LINEAR, TS(None, b["yh"], b["yl"], 0, 64), act=L.ACT_LEAKY, bias=Wt["c2"].bias), B, 2 * h, 2 * w)
+        # spx_gru: deconv 64 -> 9 (+ bias) as 4 x 9 logits per half-resolution pixel; softmax + context_upsample fused
+        ops.conv2d_ex([TS(None, b["yh"], b["yl"], 0, 64)], Wt["d3"],
+                      E(L.EPI_LINEAR, TS(b["zl"], None, None, 0, 36), bias=Wt["d3"].bias), B, 2 * h, 2 * w)
+        return ops.context_upsample_logits(disp, b["zl"], in_scale=4.0, out_scale=-1.0)  # reference :216 negates
+
     def upsample_disp(self, disp: torch.Tensor, mask_feat_4: torch.Tensor, stem_2x: torch.Tensor) -> torch.Tensor:
         """reference igev_stereo.py:140-148.  disp (B,h,w) fp32, mask_feat_4 (B,32,h,w), stem_2x (B,32,2h,2w)
         -> (B,1,4h,4w) = -context_upsample(4 * disp, softmax(spx_gru(spx_2_gru(...))))."""
+        if self.native_upsample and disp.is_cuda and not self.spx_2_gru.conv1.bn.training:
+            return self._upsample_native(disp, stem_2x.float())
         with _fp32_math(self.extractor_fp32):
             spx = F.softmax(self.spx_gru(self.spx_2_gru(mask_feat_4, stem_2x)), 1)
         return ops.context_upsample(disp, spx, in_scale=4.0, out_scale=-1.0)      # reference :216 negates
@@ -223,7 +282,7 @@ class IGEVStereo(nn.Module):
         disp = eng.FLOW["f32"].view(B, h, w)
         ops.corr1d_lookup([], disp, args.corr_radius, None, delta=eng.DELTA["f32"])
         eng.mask_head()
-        mask_feat_4 = eng.MH["f32"].permute(0, 3, 1, 2)
+        mask_feat_4 = eng.MH["f32"][..., :32].permute(0, 3, 1, 2)
         return self.upsample_disp(disp, mask_feat_4, stem_2x)
 
     def forward(self, image1, image2, iters=12, flow_init=None, test_mode=False):

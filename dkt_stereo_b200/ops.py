@@ -615,6 +615,39 @@ def context_upsample(disp: torch.Tensor, weights: torch.Tensor, in_scale: float 
     return out
 
 
+def deconv4x4s2_as_conv3x3(weight: torch.Tensor) -> torch.Tensor:
+    """ConvTranspose2d(kernel 4, stride 2, padding 1) weight (Cin, Cout, 4, 4) -> Conv2d(3x3, padding 1) weight
+    (4*Cout, Cin, 3, 3) whose output channel (py*2+px)*Cout + co is the deconv's output at (2y+py, 2x+px):
+    out[2y+py] = sum_iy in[iy] W[2y+py+1-2iy], i.e. per parity a 2-tap subset of the 4 kernel rows."""
+    Cin, Cout = weight.shape[:2]
+    tap = ({0: 3, 1: 1}, {1: 2, 2: 0})          # parity -> {dy (3x3 row, input row y+dy-1): ky (4x4 row)}
+    w3 = torch.zeros(4 * Cout, Cin, 3, 3, dtype=weight.dtype, device=weight.device)
+    for py in range(2):
+        for px in range(2):
+            g = (py * 2 + px) * Cout
+            for dy, ky in tap[py].items():
+                for dx, kx in tap[px].items():
+                    w3[g:g + Cout, :, dy, dx] = weight[:, :, ky, kx].t()
+    return w3
+
+
+def pixel_shuffle2(src: torch.Tensor, group: int, dst: DktTensor, B: int, H: int, W: int) -> None:
+    """src fp32 NHWC (B,H,W,Csrc), channel (py*2+px)*group + c  ->  dst slice at (B,2H,2W)."""
+    L.check(L.load().dkt_pixel_shuffle2(src.data_ptr(), src.shape[-1], group, C.byref(dst), B, H, W, L.stream_ptr()),
+            "pixel_shuffle2")
+
+
+def context_upsample_logits(disp: torch.Tensor, logits: torch.Tensor, in_scale: float = 4.0,
+                            out_scale: float = 1.0) -> torch.Tensor:
+    """disp (B,H,W) fp32, logits fp32 NHWC (B,2H,2W,>=36) parity-major (see the header) -> (B,1,4H,4W)."""
+    B, H, W = disp.shape
+    assert logits.shape[:3] == (B, 2 * H, 2 * W) and logits.is_contiguous() and logits.dtype == torch.float32
+    out = torch.empty(B, 1, 4 * H, 4 * W, device=disp.device, dtype=torch.float32)
+    L.check(L.load().dkt_context_upsample_logits(disp.data_ptr(), logits.data_ptr(), logits.shape[-1], out.data_ptr(),
+                                                 in_scale, out_scale, B, H, W, L.stream_ptr()), "context_upsample_logits")
+    return out
+
+
 def nchw_to_nhwc(src: torch.Tensor, dst: DktTensor, bias: Optional[torch.Tensor] = None) -> None:
     src = src.contiguous().float()
     B, Cc, H, W = src.shape
@@ -693,6 +726,8 @@ pool2x = _profiled(lambda *a, **k: "pool2x")(pool2x)
 interp = _profiled(lambda *a, **k: "interp")(interp)
 convex_upsample = _profiled(lambda *a, **k: "convex_upsample")(convex_upsample)
 nchw_to_nhwc = _profiled(lambda *a, **k: "nchw_to_nhwc")(nchw_to_nhwc)
+pixel_shuffle2 = _profiled(lambda *a, **k: "pixel_shuffle2")(pixel_shuffle2)
+context_upsample_logits = _profiled(lambda *a, **k: "context_upsample_logits")(context_upsample_logits)
 geo_lookup = _profiled(lambda *a, **k: "geo_lookup")(geo_lookup)
 corr1d_lookup_enc = _profiled(lambda *a, **k: "corr1d_lookup_enc")(corr1d_lookup_enc)
 corr1d_lookup_enc_tc = _profiled(lambda *a, **k: "corr1d_lookup_enc_tc")(corr1d_lookup_enc_tc)

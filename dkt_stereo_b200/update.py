@@ -244,7 +244,9 @@ class UpdateEngine:
         self.FH = self._buf(B, h0, w0, 256, f32=simt)
         self.FLOW = self._buf(B, h0, w0, nflow, split=False)     # flow (x,y) or disparity
         self.DELTA = self._buf(B, h0, w0, nflow, split=False)
-        self.MH = self._buf(B, h0, w0, 256 if not self.igev else 32, f32=True)
+        # mask-head features; IGEV's 32 mask_feat_4 channels sit in a 64-channel buffer (upper half zero) because they
+        # feed the 64-channel K blocks of the upsampling convs (igev_stereo.py::_upsample_native)
+        self.MH = self._buf(B, h0, w0, 256 if not self.igev else 64, f32=True)
         if not self.igev:
             factor = 2 ** self.block.args.n_downsample
             self.MASK = self._buf(B, h0, w0, 9 * factor * factor, split=False)
@@ -389,7 +391,7 @@ class UpdateEngine:
         S, E, Wt = self._slice, ops.make_epilogue, self.weights
         if self.igev:
             ops.conv2d([S(self.X[0], 0, 128, simt, split)], Wt["mask0"],
-                       E(L.EPI_LINEAR, S(self.MH, 0, 32, True, False), act=L.ACT_RELU, bias=Wt["mask0"].bias), B, h0, w0, impl)
+                       E(L.EPI_LINEAR, S(self.MH, 0, 32, True, split), act=L.ACT_RELU, bias=Wt["mask0"].bias), B, h0, w0, impl)
         else:
             ops.conv2d([S(self.X[0], 0, 128, simt, split)], Wt["mask0"],
                        E(L.EPI_LINEAR, S(self.MH, 0, 256, True, split), act=L.ACT_RELU, bias=Wt["mask0"].bias), B, h0, w0, impl)

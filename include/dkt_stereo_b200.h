@@ -57,6 +57,7 @@ extern "C" {
 #define DKT_ACT_RELU    1
 #define DKT_ACT_SIGMOID 2
 #define DKT_ACT_TANH    3
+#define DKT_ACT_LEAKY   4  /* LeakyReLU, negative slope 0.01 (nn.LeakyReLU() of the reference's BasicConv, igev submodule.py:29) */
 
 /* epilogue kinds of dkt_conv2d_* */
 #define DKT_EPI_LINEAR 0  /* y = scale * act(acc + bias[n] + ctx[p][n])                          */
@@ -291,6 +292,18 @@ int dkt_convex_upsample(const float* flow, int flow_C, const float* mask, float*
                         int B, int H, int W, int factor, void* stream);
 int dkt_context_upsample(const float* disp, const float* weights, float* out, float in_scale, float out_scale,
                          int B, int H, int W, void* stream);
+/* IGEV upsample_disp on the library's kernels (reference meta_arch/igev_stereo/igev_stereo.py:140-148): the two
+ * ConvTranspose2d(kernel 4, stride 2, padding 1) run as 3x3 convolutions that produce the four output parities as
+ * channel groups (dkt_conv2d_tc with weights from dkt_stereo_b200.ops.deconv4x4s2_as_conv3x3), then
+ * dkt_pixel_shuffle2 : src fp32 NHWC (B,H,W,src_C), channel (py*2+px)*group + c, c < C  ->  dst (B,2H,2W) slice of C
+ *                      channels, dst[b][2y+py][2x+px][c] (every non-null plane of dst is written);
+ * dkt_context_upsample_logits : softmax over the 9 logits + context_upsample in one pass.  logits fp32 NHWC
+ *                      (B,2H,2W,logit_C) with channel (py*2+px)*9 + k = logit k of full-resolution pixel
+ *                      (2*(2y')+py.., see above), disp (B,H,W) fp32  ->  out (B,4H,4W) = out_scale * sum_k softmax_k *
+ *                      in_scale * disp[neighbour k] (reference submodule.py:242-254 after F.softmax, :145-146). */
+int dkt_pixel_shuffle2(const float* src, int src_C, int group, const dkt_tensor* dst, int B, int H, int W, void* stream);
+int dkt_context_upsample_logits(const float* disp, const float* logits, int logit_C, float* out, float in_scale,
+                                float out_scale, int B, int H, int W, void* stream);
 
 /* ---- layout / precision plumbing ---------------------------------------------------------------
  * dkt_nchw_to_nhwc : fp32 (B,C,H,W) -> every non-null member of dst (NHWC slice), y = x + bias[c].

@@ -437,7 +437,7 @@ def _run_update(tag, igev, impl, terms=2, monkeypatch=None):
     # raft_stereo.py:164); the generic kernels (simt, or DKT_FAST_SMALL_CONVS=0) produce every channel
     nd = 1 if (impl == "tc" and eng.fast_small_convs) else delta.shape[1]
     assert stats(delta[:, :nd], g["delta"][:, :nd])[1] < tol * 3, stats(delta[:, :nd], g["delta"][:, :nd])
-    mask = (eng.MH if igev else eng.MASK)["f32"].permute(0, 3, 1, 2).cpu()
+    mask = (eng.MH["f32"][..., :32] if igev else eng.MASK["f32"]).permute(0, 3, 1, 2).cpu()
     assert stats(mask, g["mask"])[1] < tol * 3, stats(mask, g["mask"])
 
 
@@ -655,6 +655,61 @@ def test_serves_frozen_and_ema_teacher():
     fresh.load_state_dict({k: v.detach().cpu() for k, v in teacher.module.state_dict().items()}, strict=True)
     _, want = fresh.to(dev())(im1, im2, iters=3, test_mode=True)
     assert torch.equal(after[0], want)
+
+
+def test_igev_upsample_disp_native_vs_modules():
+    """IGEV upsample_disp (reference igev_stereo.py:140-148) on the library's kernels -- both transposed convs as
+    parity-grouped 3x3 tensor-core convs, folded BatchNorm + LeakyReLU, softmax + context_upsample fused -- against the
+    PyTorch modules with the same (non-trivial) parameters, and the small kernels against their definitions."""
+    from dkt_stereo_b200 import ops, _lib as L
+    from dkt_stereo_b200.igev_stereo import IGEVStereo
+    g = torch.Generator().manual_seed(21)
+    # (1) deconv-as-conv weights: F.conv2d + pixel shuffle == F.conv_transpose2d
+    wt = torch.randn(6, 5, 4, 4, generator=g)
+    x = torch.randn(2, 6, 7, 9, generator=g)
+    ref = torch.nn.functional.conv_transpose2d(x, wt, None, stride=2, padding=1)
+    y = torch.nn.functional.conv2d(x, ops.deconv4x4s2_as_conv3x3(wt), None, padding=1)           # (2, 4*5, 7, 9)
+    y = y.view(2, 2, 2, 5, 7, 9).permute(0, 3, 4, 1, 5, 2).reshape(2, 5, 14, 18)
+    assert stats(y, ref)[1] < 1e-5
+    # (2) pixel shuffle kernel
+    B, H, W, Cc = 2, 5, 7, 8
+    src = torch.randn(B, H, W, 4 * Cc + 4, generator=g).to(dev())
+    dst = torch.zeros(B, 2 * H, 2 * W, 16, device=dev())
+    ops.pixel_shuffle2(src, Cc, L.tensor_slice(dst, None, None, 8, Cc), B, H, W)
+    want = src[..., :4 * Cc].view(B, H, W, 2, 2, Cc).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, Cc)
+    assert torch.equal(dst[..., 8:], want) and float(dst[..., :8].abs().max()) == 0
+    # (3) the whole tail through the model
+    monkey_cfg = dict(IGEV_CFG)
+    model = IGEVStereo(Namespace(mixed_precision=False, **monkey_cfg)).eval()
+    with torch.no_grad():
+        for name, prm in list(model.spx_2_gru.named_parameters()) + list(model.spx_gru.named_parameters()):
+            prm.copy_(torch.randn(prm.shape, generator=g) * (0.15 if prm.dim() > 1 else 0.3) + (1.0 if name.endswith("bn.weight") else 0.0))
+        for name, buf in model.spx_2_gru.named_buffers():
+            if name.endswith("running_mean"):
+                buf.copy_(torch.randn(buf.shape, generator=g) * 0.2)
+            elif name.endswith("running_var"):
+                buf.copy_(torch.rand(buf.shape, generator=g) + 0.5)
+    model = model.to(dev())
+    assert model.native_upsample
+    B, h, w = 2, 12, 20
+    eng = model.engine
+    eng.pack_weights()
+    eng.allocate(B, h, w, dev())
+    mf = torch.relu(torch.randn(B, 32, h, w, generator=g)).to(dev())
+    stem = torch.randn(B, 32, 2 * h, 2 * w, generator=g).to(dev())
+    disp = (torch.rand(B, h, w, generator=g) * 40).to(dev())
+    nh = mf.permute(0, 2, 3, 1).contiguous()
+    eng.MH["f32"][..., :32].copy_(nh)
+    hi, lo = ops.split16(nh)
+    eng.MH["hi"][..., :32].copy_(hi)
+    eng.MH["lo"][..., :32].copy_(lo)
+    with torch.no_grad():
+        got = model.upsample_disp(disp, mf, stem)
+        model.native_upsample = False
+        want = model.upsample_disp(disp, mf, stem)
+    assert got.shape == want.shape == (B, 1, 4 * h, 4 * w)
+    assert stats(got.cpu(), want.cpu())[1] < 2e-3, stats(got.cpu(), want.cpu())        # disparities up to 160 px (4 x 40)
+    assert stats(got.cpu(), want.cpu())[0] < 2e-4
 
 
 def test_flow_init_and_batch_independence():
