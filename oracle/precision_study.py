@@ -42,9 +42,23 @@ from oracle import hotpath as O  # noqa: E402
 GROUPS = ("enc", "menc", "gru08", "gru16_32", "head", "corr")     # + "convc1" (mixes only; exact fp32 otherwise)
 
 
+FINE_ENC = False      # --fine-enc: the encoders split into stem / layer1 / layer2 / layer3 / output groups per network
+
+
 def group_of(name: str) -> str:
     if name.endswith("encoder.convc1"):
         return "convc1"
+    if FINE_ENC and name.startswith(("cnet.", "fnet.", "context_zqr_convs.")):
+        if name.startswith("context_zqr_convs."):
+            return "zqr"
+        net, rest = name.split(".", 1)
+        tag = net[0]
+        if rest.startswith("conv1"):
+            return tag + ".stem"
+        for l in ("layer1", "layer2", "layer3"):
+            if rest.startswith(l):
+                return tag + "." + l
+        return tag + ".rest"          # fnet.conv2; cnet.layer4/5 and the output heads
     if name.startswith(("cnet.", "fnet.", "context_zqr_convs.")):
         return "enc"
     if name.startswith("update_block.encoder."):
@@ -121,9 +135,12 @@ def main():
     ap.add_argument("--variants", default="bf16x3,h_x1_w2,hb_x1_w2,h_x2_w1,b_x1_w2,h_x1_w1")
     ap.add_argument("--mixes", default="")
     ap.add_argument("--out", default="")
+    ap.add_argument("--fine-enc", action="store_true")
     ap.add_argument("--wseed", type=int, default=0)
     ap.add_argument("--iseed", type=int, default=1234)
     a = ap.parse_args()
+    global FINE_ENC
+    FINE_ENC = a.fine_enc
     from dkt_stereo_b200.synthetic import synthetic_pair, synthetic_state_dict
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import RAFT_CFG, load_golden, golden_shapes
