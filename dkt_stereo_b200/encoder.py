@@ -111,7 +111,9 @@ class EncoderEngine:
                 for i, blk in enumerate(getattr(net, lname)):
                     self._pack_block(w, f"{tag}.{lname}.{i}", blk)
         if self.fnet is not None:
-            w["f.conv2"] = ops.pack_conv_general(self.fnet.conv2.weight, self.fnet.conv2.bias)
+            c2 = self.fnet.conv2                  # 128 -> 256 as two N = 128 halves (second accumulator for the lo products)
+            for g in range(2):
+                w[f"f.conv2.{g}"] = ops.pack_conv_general(c2.weight[128 * g:128 * (g + 1)], c2.bias[128 * g:128 * (g + 1)])
         heads = [getattr(self.cnet, n) for n in self.cnet.head_names]
         for i, hl in enumerate(heads):
             for j, head in enumerate(hl):
@@ -123,8 +125,11 @@ class EncoderEngine:
                 w[f"c.head{i}.{j}.conv"] = ops.pack_conv_general(conv.weight, conv.bias)
             z = self.zqr[i]
             bias = z.bias.detach() + self.update.gru_bias[i].to(z.bias.device)      # fold the GRU gate biases
-            w[f"c.zqr{i}.zr"] = ops.pack_conv_general(z.weight[:256], bias[:256])
-            w[f"c.zqr{i}.q"] = ops.pack_conv_general(z.weight[256:], bias[256:])
+            # three N = 128 convs, not N = 256 + 128: with N <= 128 the lo products get their own TMEM accumulator (the
+            # context terms are constant over the iterations, so a bias in them is the most expensive error of the whole
+            # forward: 1.3e-3 px for a half-precision activation here, profiles/r2_precision_study_encoder_layers.txt)
+            for g, name in enumerate("zrq"):
+                w[f"c.zqr{i}.{name}"] = ops.pack_conv_general(z.weight[128 * g:128 * (g + 1)], bias[128 * g:128 * (g + 1)])
         self.w, self._sig = w, sig
         return True
 
@@ -264,7 +269,8 @@ class EncoderEngine:
             im2 = image2.contiguous().float()
             ops.stem_rows(im2, self.STEM.hi[B:], self.STEM.lo[B:])
             x = self._trunk("f", self.fnet, 2 * B)
-            self._conv("f.conv2", x, self.FMAP.s(f32=False), x.H, x.W)
+            for g in range(2):
+                self._conv(f"f.conv2.{g}", x, self.FMAP.s(f32=False, c0=128 * g, cnt=128), x.H, x.W)
         # ---- cnet on left (reference raft_stereo.py:101); the stem rows of the left images are still there ----
         x = self._trunk("c", self.cnet, B)
         feats = [x]
@@ -291,5 +297,5 @@ class EncoderEngine:
                 else:           # context: relu -> zqr conv (+ folded gate biases) -> CTX
                     self._conv(f"c.head{i}.1.conv", src, self.CIN[i].s(f32=False), src.H, src.W, act=L.ACT_RELU)
                     ctx = eng.CTX[i]
-                    self._conv(f"c.zqr{i}.zr", self.CIN[i], TS(ctx["f32"], None, None, 0, 256), src.H, src.W)
-                    self._conv(f"c.zqr{i}.q", self.CIN[i], TS(ctx["f32"], None, None, 256, 128), src.H, src.W)
+                    for g, name in enumerate("zrq"):
+                        self._conv(f"c.zqr{i}.{name}", self.CIN[i], TS(ctx["f32"], None, None, 128 * g, 128), src.H, src.W)
