@@ -68,6 +68,12 @@ struct TcConvParams {
     uint32_t tmem_cols;
     int a_parts;                    // 2: activations are (hi, lo) pairs, 3 MMAs per K step; 1: hi only, 2 MMAs (x_hi * w_hi + x_hi * w_lo)
     int b_parts;                    // 2: weights are (hi, lo) pairs; 1: hi only (w_lo == NULL): the x * w_lo MMA is dropped
+    int merged_n;                   // pair kernel, 2-MMA convs with N = 64 | 128: the two weight planes are ONE B operand of
+                                    // 2N rows (CTA 0 stages w_hi, CTA 1 stages w_lo), so x_hi * w_hi and x_hi * w_lo are one
+                                    // MMA of N' = 2N whose columns [N, 2N) are exactly the lo accumulator (acc_lo_off = N).
+                                    // Why: an N = 128 MMA reads 4 KB of A and 4 KB of B per 64 clocks = the whole 128 B/clk
+                                    // of an SM's shared memory (67 % tensor-active with the TMA writes and the epilogue's
+                                    // transposes on top, ncu r2g); merged, A is read once per K step instead of twice.
     int w_resident;                 // pair kernel: the whole filter stays in the W ring (loaded once per CTA)
     uint32_t a_tx_bytes;            // pair kernel: bytes one CTA's TMA loads deliver per A stage (hi + lo boxes)
     int patch_rows;                 // pair kernel, x-major patch: RY = TILE_H + kh - 1 (shared-memory row = x * RY + y)
@@ -1003,8 +1009,12 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                                         uint8_t* wst = w_ring + (size_t)ws * w_stage_bytes;
                                         if (leader) mbar_arrive_expect_tx(&wfull[ws], 2u * w_stage_bytes);
                                         const int kc = kofs + kb * KB;
-                                        tma_load_2d_pair(wst, &prm.wgt[0], wfull_l + ws * 8u, kc, tap * prm.Npad + wrow0);
-                                        if (prm.b_parts == 2) tma_load_2d_pair(wst + b_bytes, &prm.wgt[1], wfull_l + ws * 8u, kc, tap * prm.Npad + wrow0);
+                                        if (prm.merged_n) {       // this CTA's half of B' = [w_hi; w_lo]: one whole plane
+                                            tma_load_2d_pair(wst, &prm.wgt[rank], wfull_l + ws * 8u, kc, tap * prm.Npad);
+                                        } else {
+                                            tma_load_2d_pair(wst, &prm.wgt[0], wfull_l + ws * 8u, kc, tap * prm.Npad + wrow0);
+                                            if (prm.b_parts == 2) tma_load_2d_pair(wst + b_bytes, &prm.wgt[1], wfull_l + ws * 8u, kc, tap * prm.Npad + wrow0);
+                                        }
                                     }
                                 }
                                 if (++ws == prm.w_stages) { ws = 0; wph ^= 1u; }
@@ -1019,7 +1029,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
     } else if (warp == 1) {
         if (leader) {
             // ===== MMA issuer (leader): M = 256 over both CTAs' tiles =====
-            const uint32_t idesc = idesc_bf16_m256((uint32_t)prm.Npad);
+            const uint32_t idesc = idesc_bf16_m256((uint32_t)(prm.merged_n ? 2 * prm.Npad : prm.Npad));
             int as = 0, ws = 0;
             uint32_t aph = 0, wph = 0, acs = 0, aphase = 0;
             int kb_total = 0;
@@ -1057,8 +1067,10 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                             for (int k = 0; k < KB / 16; ++k) {   // +32 bytes per K16 step = +2 in the address field
                                 const uint32_t acc_l = prm.acc_lo_off ? accumulate : 1u;      // first lo MMA of a tile overwrites
                                 umma_bf16_pair(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, accumulate);
-                                if (a_lo) umma_bf16_pair(tmem_d + prm.acc_lo_off, dal + 2 * k, dwh + 2 * k, idesc, acc_l);
-                                if (b_lo) umma_bf16_pair(tmem_d + prm.acc_lo_off, dah + 2 * k, dwl + 2 * k, idesc, a_lo ? 1u : acc_l);
+                                if (!prm.merged_n) {
+                                    if (a_lo) umma_bf16_pair(tmem_d + prm.acc_lo_off, dal + 2 * k, dwh + 2 * k, idesc, acc_l);
+                                    if (b_lo) umma_bf16_pair(tmem_d + prm.acc_lo_off, dah + 2 * k, dwl + 2 * k, idesc, a_lo ? 1u : acc_l);
+                                }
                                 accumulate = 1u;
                             }
                             if (!prm.w_resident) umma_commit_pair(&wempty[ws]);
@@ -1331,12 +1343,19 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     if (k32 && !use_pair) return DKT_E_UNSUPPORTED;           // 32-channel K blocks exist in the pair kernel only
     const int BK = KBLK;
     const int WBK = use_pair ? KBLK : (use_patch ? WK : BK);  // K extent of a weight box
-    const int wbox_rows = use_pair ? Npad / 2 : Npad;         // N extent of a weight box
+    // merged weight planes (TcConvParams::merged_n): pair kernel, hi-plane activations, (hi, lo) weights, N a power of two
+    // <= 128 so that the lo accumulator starts exactly N columns after the main one
+    static const int s_merge = [] { const char* v = getenv("DKT_CONV_MERGE_N"); return (v && v[0] == '0') ? 0 : 1; }();
+    static const int s_split_m = [] { const char* v = getenv("DKT_ACC_SPLIT"); return (v && v[0] == '0') ? 0 : 1; }();
+    const bool merged = s_merge && s_split_m && use_pair && AP == 1 && BP == 2 && (Npad == 64 || Npad == 128) &&
+                        epi->kind != DKT_EPI_PROJ;
+    const int wbox_rows = use_pair ? (merged ? Npad : Npad / 2) : Npad;         // N extent of a weight box
 
     TcConvParams prm{};
     prm.nsrc = nsrc;
     prm.a_parts = (int)AP;
     prm.b_parts = (int)BP;
+    prm.merged_n = merged ? 1 : 0;
     int cin_total = 0;
     for (int s = 0; s < nsrc; ++s) {
         const dkt_tensor& t = srcs[s];
