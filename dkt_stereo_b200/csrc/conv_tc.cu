@@ -74,6 +74,11 @@ struct TcConvParams {
                                     // Why: an N = 128 MMA reads 4 KB of A and 4 KB of B per 64 clocks = the whole 128 B/clk
                                     // of an SM's shared memory (67 % tensor-active with the TMA writes and the epilogue's
                                     // transposes on top, ncu r2g); merged, A is read once per K step instead of twice.
+                                    // merged_n == 2 (3-MMA convs, N = 64: the encoders' full-resolution layers, 192 B/clk
+                                    // of operand reads unmerged): the weight stage of a CTA already is [w_hi half | w_lo
+                                    // half], so x_hi against all 64 rows of it is one MMA of N' = 128 whose columns come
+                                    // out as [main(0:32) | lo(0:32) | main(32:64) | lo(32:64)]; x_lo * w_hi goes to a third
+                                    // accumulator at column 128; the epilogue adds the three.
     int w_resident;                 // pair kernel: the whole filter stays in the W ring (loaded once per CTA)
     uint32_t a_tx_bytes;            // pair kernel: bytes one CTA's TMA loads deliver per A stage (hi + lo boxes)
     int patch_rows;                 // pair kernel, x-major patch: RY = TILE_H + kh - 1 (shared-memory row = x * RY + y)
@@ -318,7 +323,15 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                 }
             }
             __syncwarp();                       // tcgen05.ld is .sync.aligned; also: previous chunk's reads done
-            if (ncols == 32) {
+            if (prm.merged_n == 2) {            // N = 64: chunk c0 in {0, 32}: main at 2*c0, x_hi*w_lo at 2*c0 + 32, x_lo*w_hi at 128 + c0
+                float v2[32], v3[32];
+                tmem_ld32(tbase + 2 * c0, v);
+                tmem_ld32(tbase + 2 * c0 + 32, v2);
+                tmem_ld32(tbase + 128 + c0, v3);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += v2[j] + v3[j];
+            } else if (ncols == 32) {
                 tmem_ld32(tbase + c0, v);
             } else {
                 tmem_ld16(tbase + c0, v);
@@ -1009,7 +1022,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                                         uint8_t* wst = w_ring + (size_t)ws * w_stage_bytes;
                                         if (leader) mbar_arrive_expect_tx(&wfull[ws], 2u * w_stage_bytes);
                                         const int kc = kofs + kb * KB;
-                                        if (prm.merged_n) {       // this CTA's half of B' = [w_hi; w_lo]: one whole plane
+                                        if (prm.merged_n == 1) {  // this CTA's half of B' = [w_hi; w_lo]: one whole plane
                                             tma_load_2d_pair(wst, &prm.wgt[rank], wfull_l + ws * 8u, kc, tap * prm.Npad);
                                         } else {
                                             tma_load_2d_pair(wst, &prm.wgt[0], wfull_l + ws * 8u, kc, tap * prm.Npad + wrow0);
@@ -1030,6 +1043,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
         if (leader) {
             // ===== MMA issuer (leader): M = 256 over both CTAs' tiles =====
             const uint32_t idesc = idesc_bf16_m256((uint32_t)(prm.merged_n ? 2 * prm.Npad : prm.Npad));
+            const uint32_t idesc_n = idesc_bf16_m256((uint32_t)prm.Npad);          // merged_n == 2: the x_lo * w_hi MMA
             int as = 0, ws = 0;
             uint32_t aph = 0, wph = 0, acs = 0, aphase = 0;
             int kb_total = 0;
@@ -1067,6 +1081,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                             for (int k = 0; k < KB / 16; ++k) {   // +32 bytes per K16 step = +2 in the address field
                                 const uint32_t acc_l = prm.acc_lo_off ? accumulate : 1u;      // first lo MMA of a tile overwrites
                                 umma_bf16_pair(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, accumulate);
+                                if (prm.merged_n == 2) umma_bf16_pair(tmem_d + 128u, dal + 2 * k, dwh + 2 * k, idesc_n, accumulate);
                                 if (!prm.merged_n) {
                                     if (a_lo) umma_bf16_pair(tmem_d + prm.acc_lo_off, dal + 2 * k, dwh + 2 * k, idesc, acc_l);
                                     if (b_lo) umma_bf16_pair(tmem_d + prm.acc_lo_off, dah + 2 * k, dwl + 2 * k, idesc, a_lo ? 1u : acc_l);
@@ -1347,15 +1362,18 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     // <= 128 so that the lo accumulator starts exactly N columns after the main one
     static const int s_merge = [] { const char* v = getenv("DKT_CONV_MERGE_N"); return (v && v[0] == '0') ? 0 : 1; }();
     static const int s_split_m = [] { const char* v = getenv("DKT_ACC_SPLIT"); return (v && v[0] == '0') ? 0 : 1; }();
+    static const int s_merge3 = [] { const char* v = getenv("DKT_CONV_MERGE3"); return (v && v[0] == '0') ? 0 : 1; }();
     const bool merged = s_merge && s_split_m && use_pair && AP == 1 && BP == 2 && (Npad == 64 || Npad == 128) &&
                         epi->kind != DKT_EPI_PROJ;
+    const bool merged3 = s_merge >= 1 && s_split_m && use_pair && AP == 2 && BP == 2 && Npad == 64 && epi->kind == DKT_EPI_LINEAR &&
+                         s_merge3;
     const int wbox_rows = use_pair ? (merged ? Npad : Npad / 2) : Npad;         // N extent of a weight box
 
     TcConvParams prm{};
     prm.nsrc = nsrc;
     prm.a_parts = (int)AP;
     prm.b_parts = (int)BP;
-    prm.merged_n = merged ? 1 : 0;
+    prm.merged_n = merged ? 1 : (merged3 ? 2 : 0);
     int cin_total = 0;
     for (int s = 0; s < nsrc; ++s) {
         const dkt_tensor& t = srcs[s];
@@ -1410,7 +1428,9 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         // DKT_ACC_SPLIT=0 restores the single accumulator (A/B knob).
         static const int s_split = [] { const char* v = getenv("DKT_ACC_SPLIT"); return (v && v[0] == '0') ? 0 : 1; }();
         const bool lo_mmas = AP == 2 || BP == 2;
-        if (s_split && lo_mmas && cols <= 128 && e.kind != DKT_EPI_PROJ) {
+        if (prm.merged_n == 2) {
+            cols = 256;                         // [main | lo_w] interleaved in 128 columns + x_lo * w_hi in 64 more
+        } else if (s_split && lo_mmas && cols <= 128 && e.kind != DKT_EPI_PROJ) {
             prm.acc_lo_off = cols;
             cols *= 2;
         }
