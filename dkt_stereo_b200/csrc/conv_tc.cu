@@ -49,6 +49,10 @@ struct TcConvParams {
     int nsrc;
     int c_begin[DKT_MAX_SRCS];
     int kblocks[DKT_MAX_SRCS];
+    int c_count[DKT_MAX_SRCS];      // channels of the source's slice (weights: the source's K range starts at the sum before it)
+    int klast[DKT_MAX_SRCS];        // K16 steps of the source's LAST K block (4 = full 64 channels; 2 for a 96-channel
+                                    // source: the box is still 64 wide -- channels past the tensor are zero-filled by the
+                                    // TMA unit, channels past the slice are simply never read by an MMA)
     int kh, kw, pad_y, pad_x, stride, taps;
     int N, Npad;
     int H, W, tiles_x, tiles_y;
@@ -660,10 +664,6 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
 
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
 
-    int kb_total = 0;
-    for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
-    const int ksteps = prm.taps * kb_total;                  // per tile
-
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < prm.nsrc; ++s) { tma_prefetch_desc(&prm.act[s][0]); tma_prefetch_desc(&prm.act[s][1]); }
         tma_prefetch_desc(&prm.wgt[0]);
@@ -705,7 +705,7 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
                         }
                         if (++stage == prm.stages) { stage = 0; phase ^= 1u; }
                     }
-                    kofs += prm.kblocks[s] * BK;
+                    kofs += prm.c_count[s];
                 }
             }
         }
@@ -719,7 +719,11 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
             mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);          // epilogue drained this accumulator
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + as * prm.acc_cols;
-            for (int it = 0; it < ksteps; ++it) {
+            int it = 0;
+            for (int tap = 0; tap < prm.taps; ++tap)
+            for (int s = 0; s < prm.nsrc; ++s)
+            for (int kb = 0; kb < prm.kblocks[s]; ++kb, ++it) {
+                const int kn = (kb == prm.kblocks[s] - 1) ? prm.klast[s] : BK / 16;   // K16 steps of this block
                 mbar_wait(&full_bar[stage], phase);
                 tcgen05_fence_after();
                 if (elect_one()) {
@@ -729,6 +733,7 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
                     const bool a_lo = prm.a_parts == 2, b_lo = prm.b_parts == 2;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {           // +32 bytes per K16 step = +2 in the address field
+                        if (k >= kn) break;
                         umma_bf16(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, (it | k) != 0);
                         if (a_lo) umma_bf16(tmem_d + prm.acc_lo_off, dal + 2 * k, dwh + 2 * k, idesc, (prm.acc_lo_off == 0 || (it | k) != 0) ? 1u : 0u);
                         if (b_lo) umma_bf16(tmem_d + prm.acc_lo_off, dah + 2 * k, dwl + 2 * k, idesc, (prm.acc_lo_off == 0 || a_lo || (it | k) != 0) ? 1u : 0u);
@@ -819,6 +824,8 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
             for (int s = 0; s < prm.nsrc; ++s) {
                 for (int kb = 0; kb < prm.kblocks[s]; ++kb) {
                     const int c = prm.c_begin[s] + kb * 64;
+                    const int kn = (kb == prm.kblocks[s] - 1) ? prm.klast[s] : 4;     // K16 steps of this block
+                    const int wsn = (kn * 16 + WK - 1) / WK;                          // weight steps that hold them
                     for (int kx = 0; kx < prm.kw; ++kx) {
                         const int xs = x0 * prm.stride + kx - prm.pad_x;
                         for (int yg = 0; yg < ygroups; ++yg) {
@@ -833,7 +840,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
                             if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
                             for (int kyi = 0; kyi < prm.ygroup; ++kyi) {
                                 const int tap = (yg * prm.ygroup + kyi) * prm.kw + kx;
-                                for (int wh = 0; wh < WSPLIT; ++wh) {
+                                for (int wh = 0; wh < wsn; ++wh) {
                                     mbar_wait(&wempty[ws], wph ^ 1u);
                                     if (elect_one()) {
                                         uint8_t* wst = w_ring + (size_t)ws * w_stage_bytes;
@@ -848,7 +855,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
                         }
                     }
                 }
-                kofs += prm.kblocks[s] * 64;
+                kofs += prm.c_count[s];
             }
         }
     } else if (warp == 1) {
@@ -856,15 +863,17 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
         const uint32_t idesc = idesc_bf16_m128((uint32_t)prm.Npad);
         int as = 0, ws = 0;
         uint32_t aph = 0, wph = 0, acs = 0, aphase = 0;
-        int kb_total = 0;
-        for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
-        const int a_steps = kb_total * prm.kw * ygroups;
+        const int steps_per_kb = prm.kw * ygroups;               // A steps per K block
         for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
             mbar_wait(&tmem_empty_bar[acs], aphase ^ 1u);
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + acs * prm.acc_cols;
             uint32_t accumulate = 0;
-            for (int ai = 0; ai < a_steps; ++ai) {
+            for (int s = 0; s < prm.nsrc; ++s)
+            for (int kb = 0; kb < prm.kblocks[s]; ++kb)
+            for (int ai = 0; ai < steps_per_kb; ++ai) {
+                const int kn = (kb == prm.kblocks[s] - 1) ? prm.klast[s] : 4;         // K16 steps of this block
+                const int wsn = (kn * 16 + WK - 1) / WK;
                 mbar_wait(&afull[as], aph);
                 tcgen05_fence_after();
                 const uint32_t a_hi0 = smem_u32(a_ring + (size_t)as * a_stage_bytes);
@@ -872,6 +881,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
                     const uint32_t a_hi = a_hi0 + (uint32_t)kyi * (TC_TILE_W * 128u);
 #pragma unroll
                     for (int wh = 0; wh < WSPLIT; ++wh) {
+                        if (wh >= wsn) break;
                         mbar_wait(&wfull[ws], wph);
                         tcgen05_fence_after();
                         if (elect_one()) {
@@ -880,6 +890,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
                             const uint64_t dwh = smem_desc_kmajor<WK>(w_hi), dwl = smem_desc_kmajor<WK>(w_hi + b_bytes);
 #pragma unroll
                             for (int k = 0; k < WK / 16; ++k) {   // +32 bytes per K16 step = +2 in the address field
+                                if (wh * (WK / 16) + k >= kn) break;
                                 const uint32_t acc_l = prm.acc_lo_off ? accumulate : 1u;      // first lo MMA of a tile overwrites
                                 umma_bf16(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, accumulate);
                                 if (prm.a_parts == 2) umma_bf16(tmem_d + prm.acc_lo_off, dal + 2 * k, dwh + 2 * k, idesc, acc_l);
@@ -1035,7 +1046,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                         }
                     }
                 }
-                kofs += prm.kblocks[s] * KB;
+                kofs += prm.c_count[s];
             }
             first = false;
         }
@@ -1046,9 +1057,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
             const uint32_t idesc_n = idesc_bf16_m256((uint32_t)prm.Npad);          // merged_n == 2: the x_lo * w_hi MMA
             int as = 0, ws = 0;
             uint32_t aph = 0, wph = 0, acs = 0, aphase = 0;
-            int kb_total = 0;
-            for (int s = 0; s < prm.nsrc; ++s) kb_total += prm.kblocks[s];
-            const int a_steps = kb_total * kx_n * ygroups;
+            const int steps_per_kb = kx_n * ygroups;             // A steps per K block
             const uint32_t sbo = XMT ? (uint32_t)prm.patch_rows * KROW : 8u * KROW;      // bytes between 8-row atoms of A
             const bool a_lo = prm.a_parts == 2, b_lo = prm.b_parts == 2;
             bool first = true;
@@ -1057,7 +1066,10 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acs * prm.acc_cols;
                 uint32_t accumulate = 0;
-                for (int ai = 0; ai < a_steps; ++ai) {
+                for (int s = 0; s < prm.nsrc; ++s)
+                for (int kb = 0; kb < prm.kblocks[s]; ++kb)
+                for (int ai = 0; ai < steps_per_kb; ++ai) {
+                    const int kn = (kb == prm.kblocks[s] - 1) ? prm.klast[s] : KB / 16;   // K16 steps of this block
                     mbar_wait(&afull[as], aph);
                     tcgen05_fence_after();
                     const uint32_t a_hi0 = smem_u32(a_ring + (size_t)as * a_stage_bytes);
@@ -1079,6 +1091,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                             const uint64_t dwh = smem_desc_kmajor<KB>(w_hi), dwl = smem_desc_kmajor<KB>(w_hi + b_bytes);
 #pragma unroll
                             for (int k = 0; k < KB / 16; ++k) {   // +32 bytes per K16 step = +2 in the address field
+                                if (k >= kn) break;
                                 const uint32_t acc_l = prm.acc_lo_off ? accumulate : 1u;      // first lo MMA of a tile overwrites
                                 umma_bf16_pair(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, accumulate);
                                 if (prm.merged_n == 2) umma_bf16_pair(tmem_d + 128u, dal + 2 * k, dwh + 2 * k, idesc_n, accumulate);
@@ -1298,8 +1311,8 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     // ring geometry of the row-patch kernel
     const int ygroup = (stride == 1) ? kh : 1;
     const int rows_loaded = (stride == 1) ? TC_TILE_H + ygroup - 1 : TC_TILE_H;
-    int cin_sum = 0;
-    for (int s = 0; s < nsrc; ++s) cin_sum += srcs[s].c_count;
+    int kb_sum = 0;        // kb_sum: 64-channel K blocks (a source's last one may be partial: c_count % 16 == 0)
+    for (int s = 0; s < nsrc; ++s) { kb_sum += (srcs[s].c_count + 63) / 64; }
     const int64_t tiles64 = (int64_t)ceil_div(W, TC_TILE_W) * ceil_div(H, TC_TILE_H) * B;
     // K blocks of 32 channels (64-byte rows): a single 32-channel source, i.e. the x-im2col rows of a 7x7 stem
     const bool k32 = nsrc == 1 && srcs[0].c_count == 32 && (srcs[0].c_begin % 32) == 0;
@@ -1307,7 +1320,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     const uint32_t a_part_bytes = (uint32_t)rows_loaded * TC_TILE_W * (uint32_t)KBLK * 2u;
 
     // CTA-pair kernel (default for stride 1): each CTA stages half of a KBLK-channel weight block
-    bool use_pair = s_pair != 0 && s_patch != 0 && stride == 1 && tiles64 >= 2 && (cin_sum % KBLK) == 0;
+    bool use_pair = s_pair != 0 && s_patch != 0 && stride == 1 && tiles64 >= 2;
     // 64-channel K blocks of the pair kernel: ONE x-major halo patch (RY x RX pixels, shared-memory row = x * RY + y) per
     // K block serves every tap (tools/umma_stride_probe.cu: the SW128 descriptor takes any 128-byte-aligned start and any
     // atom stride); each precision's slot is rounded up to the 1024-byte swizzle period
@@ -1319,7 +1332,7 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     int p_a_stages = 2, p_w_stages = 0, p_resident = 0;
     const uint32_t p_w_stage_bytes = BP * (uint32_t)(Npad / 2) * (uint32_t)KBLK * 2u;
     if (use_pair) {
-        const int w_steps = (cin_sum / KBLK) * kh * kw;            // weight blocks per tile
+        const int w_steps = (k32 ? 1 : kb_sum) * kh * kw;          // weight blocks per tile
         if (AP * pair_a_part_bytes * 2 >= budget) use_pair = false;
         else if (w_steps <= TCP_MAX_W && AP * pair_a_part_bytes * 2 + (uint32_t)w_steps * p_w_stage_bytes <= budget) {
             p_resident = 1;                                        // whole filter half stays in the ring
@@ -1378,10 +1391,12 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     for (int s = 0; s < nsrc; ++s) {
         const dkt_tensor& t = srcs[s];
         DKT_CHECK_ARG(t.hi && t.c_count > 0 && t.c_begin >= 0 && t.c_begin + t.c_count <= t.C);
-        if ((t.c_begin % BK) || (t.c_count % BK) || (t.C % 8) || !aligned16(t.hi) || !aligned16(t.lo))
+        if ((t.c_begin % BK) || (t.c_count % 16) || (t.C % 8) || !aligned16(t.hi) || !aligned16(t.lo))
             return DKT_E_ALIGNMENT;
         prm.c_begin[s] = t.c_begin;
-        prm.kblocks[s] = t.c_count / BK;
+        prm.kblocks[s] = (t.c_count + BK - 1) / BK;
+        prm.c_count[s] = t.c_count;
+        prm.klast[s] = (t.c_count - (prm.kblocks[s] - 1) * BK) / 16;
         cin_total += t.c_count;
         if (use_pair && xm) {
             // x-major patch: the tensor is described as {C, y, x, b} so that the box lands with y fastest

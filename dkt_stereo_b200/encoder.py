@@ -16,8 +16,8 @@ tensor-core convolution kernel as the GRU loop (3-term bf16 split, fp32 accumula
                   (``context_zqr_convs`` + folded GRU gate biases, reference raft_stereo.py:110-114)
                   straight into the per-scale context buffers of ``UpdateEngine``.
 
-96-channel stages run with their channels zero-padded to 128 (K blocks are 64 wide); the padded
-channels stay exactly zero through conv, norm and residual.
+96-channel stages run as 96 channels (N = 96; the second 64-channel K block of a 96-channel source is half
+used, conv_tc.cu `klast`).
 """
 from __future__ import annotations
 
@@ -34,8 +34,13 @@ from .extractor import BasicEncoder, MultiBasicEncoder, ResidualBlock
 from .update import UpdateEngine
 
 
+# 96-channel stages (layer2) run as 96 channels: N = 96 is a legal UMMA shape and a source's last 64-channel K block
+# may be partial (conv_tc.cu `klast`).  DKT_ENC_PAD64=1 restores the zero-padding to 128 (1.78x the MMA work of those layers).
+_PAD = 64 if os.environ.get("DKT_ENC_PAD64", "0") == "1" else 16
+
+
 def _pad64(c: int) -> int:
-    return (c + 63) // 64 * 64
+    return (c + _PAD - 1) // _PAD * _PAD
 
 
 class _Act:
@@ -147,7 +152,7 @@ class EncoderEngine:
             dims.append(((h - 1) // 2 + 1, (w_ - 1) // 2 + 1))
         self.dims = dims                                   # full, 1/2, 1/4, 1/8, 1/16
         B2 = 2 * B if self.fnet is not None else B
-        chans = [64, 128, 128, 128, 128]
+        chans = [64, _pad64(self.cnet.layer2[0].conv1.out_channels), 128, 128, 128]
         nimg = [B2, B2, B2, B, B]
         # block inputs / outputs live as bf16 (hi, lo) only: the residual x of relu(x + y) is read back as hi + lo
         # (16 mantissa bits, the precision every conv already consumes), so no fp32 copy of them is written or read.
