@@ -52,6 +52,8 @@ struct LookupTcParams {
     int C;                           // K slots in use: row samples per pixel * LT_TS
     int flags;                       // bit 0: RAFT gather through aligned 16-byte windows (else one thread per row sample);
                                      // bit 1: 16-bit output planes through the staging tile (else per-thread stores)
+                                     // bit 2: batched gather (RAFT: both samples of a thread in flight; IGEV: 16-byte loads)
+                                     // bit 3: cooperative gather (the lanes of one load instruction cover a whole run)
 };
 
 // byte offset of element (row m, column k) inside one plane [KB][rows][128 B] of a K-major SWIZZLE_128B tile whose
@@ -153,7 +155,77 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
         __syncthreads();
         uint8_t* a_buf = a_ring + (uint32_t)buf * A_BUF;
         if (!GEO) {
-            if (!(prm.flags & 1)) {
+            if (prm.flags & 8) {
+                // RAFT, cooperative gather: TEN LANES read the ten floats of a row sample with one load instruction, three
+                // samples per warp pass.  Why (tools/dram_random_probe.cu, profiles/r2w_dram_random_probe.txt): a gather is
+                // bound by the number of L1 -> L2 REQUESTS, ~50 G/s on the whole chip whether a request carries one
+                // 32-byte sector or a whole line; a thread walking its own run issues one request per sector it touches
+                // (2.1 per run), the ten lanes of one instruction one per LINE (1.3 per run).  The interpolation pairs come
+                // from the neighbour lane by shuffle; even lanes store two packed 16-bit taps.
+                constexpr int U = 6;                                    // passes whose loads are in flight together
+                constexpr int RUNS_W = LT_M * DKT_MAX_LEVELS / 8;        // 64 runs per warp
+                constexpr int PASSES = (RUNS_W + 2) / 3;
+                const int sub = lane / 10, k = lane - sub * 10;        // lanes 30, 31: sub == 3, idle
+                for (int ps0 = 0; ps0 < PASSES; ps0 += U) {
+                    float v[U], a[U];
+#pragma unroll
+                    for (int g = 0; g < U; ++g) {
+                        const int rr = (ps0 + g) * 3 + sub;
+                        const int u = warp * RUNS_W + rr, px = u >> 2, l = u & 3;
+                        v[g] = 0.f;
+                        a[g] = 0.f;
+                        if (sub < 3 && rr < RUNS_W && ps0 + g < PASSES && px < npix && l < prm.levels) {
+                            const int Wl = prm.vw[l];
+                            const float x = s_x[px] * (1.f / (float)(1 << l)), xf = floorf(x);
+                            a[g] = x - xf;
+                            const int idx = (int)xf - R + k;
+                            if (idx >= 0 && idx < Wl) v[g] = __ldg(prm.vol[l] + (p0 + px) * Wl + idx);
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < U; ++g) {
+                        const int rr = (ps0 + g) * 3 + sub;
+                        const int u = warp * RUNS_W + rr, px = u >> 2, l = u & 3;
+                        const float v1 = __shfl_down_sync(0xffffffffu, v[g], 1);
+                        const float t = (k < 2 * R + 1) ? (1.f - a[g]) * v[g] + a[g] * v1 : 0.f;
+                        const float t1 = __shfl_down_sync(0xffffffffu, t, 1);
+                        if (sub < 3 && rr < RUNS_W && ps0 + g < PASSES && px < npix && l < prm.levels && !(k & 1)) {
+                            uint8_t* row = a_buf + (uint32_t)(px >> 3) * 1024u + (uint32_t)(px & 7) * 128u;
+                            const int kk = l * LT_TS + k;
+                            const uint32_t off = (((uint32_t)(kk >> 6) * LT_A_KB_BYTES) + (uint32_t)(kk & 63) * 2u) ^ ((uint32_t)(px & 7) << 4);
+                            if (AP == 2) {
+                                uint32_t hi, lo;
+                                split16x2(t, t1, hi, lo);
+                                *reinterpret_cast<uint32_t*>(row + off) = hi;
+                                *reinterpret_cast<uint32_t*>(row + A_PLANE + off) = lo;
+                            } else {
+                                *reinterpret_cast<uint32_t*>(row + off) = pack_hi16x2(t, t1);
+                            }
+                        }
+                    }
+                }
+            } else if (prm.flags & 4) {
+                // RAFT: unit = (pixel, level); 4 lanes per pixel; the loads of BOTH of a thread's samples (128 pixels x 4
+                // levels = 2 x 256 threads) are in flight before either is interpolated (the kernel is bound by the
+                // latency of these loads: ncu r2t, long-scoreboard stalls 9 of 13 warp-cycles per issue)
+                float v[2][2 * R + 3], a[2];
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int u = tid + g * LT_THREADS;
+                    const int px = u >> 2, l = u & 3;
+                    if (px < npix && l < prm.levels)
+                        sample_row_load<R>(prm.vol[l] + (p0 + px) * prm.vw[l], prm.vw[l], s_x[px] * (1.f / (float)(1 << l)), v[g], a[g]);
+                }
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int u = tid + g * LT_THREADS;
+                    const int px = u >> 2, l = u & 3;
+                    if (px < npix && l < prm.levels) {
+                        v[g][2 * R + 2] = 0.f;
+                        put_taps<AP>(a_buf, A_PLANE, px, l * LT_TS, v[g], a[g]);
+                    }
+                }
+            } else if (!(prm.flags & 1)) {
                 // RAFT: unit = (pixel, level); 4 lanes per pixel; a thread issues its 10 loads back to back
                 for (int u = tid; u < npix * DKT_MAX_LEVELS; u += LT_THREADS) {
                     const int px = u >> 2, l = u & 3;
@@ -223,6 +295,137 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
             // Output channel order of the reference (geometry.py:36-57): per level [geo (c-major, tap-minor), init].
             constexpr int Cg = 8, G1 = Cg + 1, G = 2 * G1;      // host checks prm.Cg == 8 (IGEV's 8 geometry channels)
             constexpr int GU = 3;                 // row samples whose loads a thread has in flight before interpolating
+            if (prm.flags & 8) {
+                // cooperative gather (see the RAFT branch): one warp pass = one (pixel, level): lanes 0..19 fetch the 320-byte
+                // geometry run with ONE 16-byte load each (lane = (sample k, channel half): 3.25 line requests instead of
+                // ten sector requests), lanes 20..29 the ten floats of the init-corr row; neighbours by shuffle.
+                constexpr int U = 4;                                    // passes whose loads are in flight together
+                constexpr int PASSES = LT_M * 2 / 8;                    // 32 (pixel, level) passes per warp
+                const bool is_geo = lane < 20, is_init = lane >= 20 && lane < 30;
+                const int k = is_geo ? (lane >> 1) : lane - 20, hh = lane & 1;
+                for (int ps0 = 0; ps0 < PASSES; ps0 += U) {
+                    float4 q[U];
+                    float a[U];
+#pragma unroll
+                    for (int g = 0; g < U; ++g) {
+                        const int ps = ps0 + g, px = warp * (LT_M / 8) + (ps >> 1), l = ps & 1;
+                        q[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        a[g] = 0.f;
+                        if (px < npix) {
+                            const int64_t p = p0 + px;
+                            const float d = s_x[px], inv = l ? 0.5f : 1.f;
+                            if (is_geo) {
+                                const int Dl = l ? prm.D / 2 : prm.D;
+                                const float x = d * inv, xf = floorf(x);
+                                a[g] = x - xf;
+                                const int i = (int)fminf(fmaxf(xf, -1.0e6f), 1.0e6f) - R + k;
+                                if ((unsigned)i < (unsigned)Dl)
+                                    q[g] = __ldg(reinterpret_cast<const float4*>(prm.geo[l] + (p * Dl + i) * Cg + 4 * hh));
+                            } else if (is_init) {
+                                const int Wl = prm.vw[l];
+                                const float x = (float)(p % prm.W1) * inv - d * inv, xf = floorf(x);
+                                a[g] = x - xf;
+                                const int i = (int)fminf(fmaxf(xf, -1.0e6f), 1.0e6f) - R + k;
+                                if ((unsigned)i < (unsigned)Wl) q[g].x = __ldg(prm.vol[l] + p * Wl + i);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < U; ++g) {
+                        const int ps = ps0 + g, px = warp * (LT_M / 8) + (ps >> 1), l = ps & 1;
+                        const float b0 = a[g], b1 = 1.f - a[g];
+                        // sample k + 1 of the same channels: two lanes up (geometry) / one lane up (init row)
+                        const float nx2 = __shfl_down_sync(0xffffffffu, q[g].x, 2), nx1 = __shfl_down_sync(0xffffffffu, q[g].x, 1);
+                        const float ny = __shfl_down_sync(0xffffffffu, q[g].y, 2), nz = __shfl_down_sync(0xffffffffu, q[g].z, 2);
+                        const float nw = __shfl_down_sync(0xffffffffu, q[g].w, 2);
+                        const bool tapk = k < 2 * R + 1;                // slot 9 of a sample is the zero pad
+                        float4 t;
+                        t.x = tapk ? b1 * q[g].x + b0 * (is_geo ? nx2 : nx1) : 0.f;
+                        t.y = tapk ? b1 * q[g].y + b0 * ny : 0.f;
+                        t.z = tapk ? b1 * q[g].z + b0 * nz : 0.f;
+                        t.w = tapk ? b1 * q[g].w + b0 * nw : 0.f;
+                        const float ux2 = __shfl_down_sync(0xffffffffu, t.x, 2), ux1 = __shfl_down_sync(0xffffffffu, t.x, 1);
+                        const float uy = __shfl_down_sync(0xffffffffu, t.y, 2), uz = __shfl_down_sync(0xffffffffu, t.z, 2);
+                        const float uw = __shfl_down_sync(0xffffffffu, t.w, 2);
+                        if (px < npix && !(k & 1) && (is_geo || is_init)) {
+                            uint8_t* row = a_buf + (uint32_t)(px >> 3) * 1024u + (uint32_t)(px & 7) * 128u;
+                            const uint32_t sw = (uint32_t)(px & 7) << 4;
+                            auto put = [&](int kk, float t0, float t1) {
+                                const uint32_t off = (((uint32_t)(kk >> 6) * LT_A_KB_BYTES) + (uint32_t)(kk & 63) * 2u) ^ sw;
+                                if (AP == 2) {
+                                    uint32_t hi, lo;
+                                    split16x2(t0, t1, hi, lo);
+                                    *reinterpret_cast<uint32_t*>(row + off) = hi;
+                                    *reinterpret_cast<uint32_t*>(row + A_PLANE + off) = lo;
+                                } else {
+                                    *reinterpret_cast<uint32_t*>(row + off) = pack_hi16x2(t0, t1);
+                                }
+                            };
+                            if (is_geo) {
+                                const int kk = (l * G1 + 4 * hh) * LT_TS + k;
+                                put(kk, t.x, ux2);
+                                put(kk + LT_TS, t.y, uy);
+                                put(kk + 2 * LT_TS, t.z, uz);
+                                put(kk + 3 * LT_TS, t.w, uw);
+                            } else {
+                                put((l * G1 + Cg) * LT_TS + k, t.x, ux1);
+                            }
+                        }
+                    }
+                }
+            } else if (prm.flags & 4) {
+                // vector gather: a geometry unit = (pixel, level, channel half): ten 16-byte loads fetch the 4 channels x 10
+                // disparity samples (the (.., D, 8) layout keeps a sample's 8 channels in 32 contiguous bytes), a quarter of
+                // the load instructions of the scalar form for 4/3 of the bytes in flight; the init-corr row of (pixel,
+                // level) is a third unit of the same thread whose loads overlap the first unit's interpolation.
+                auto geo_load = [&](int u, float4* q, float& a) {
+                    const int px = u >> 2, l = (u >> 1) & 1, hh = u & 1;
+                    const int Dl = l ? prm.D / 2 : prm.D;
+                    const float x = s_x[px] * (l ? 0.5f : 1.f), xf = floorf(x);
+                    a = x - xf;
+                    const int i0 = (int)fminf(fmaxf(xf, -1.0e6f), 1.0e6f) - R;
+                    const float* ptr = prm.geo[l] + ((p0 + px) * Dl + i0) * Cg + 4 * hh;   // only dereferenced inside [0, Dl)
+#pragma unroll
+                    for (int k = 0; k < 2 * R + 2; ++k)
+                        q[k] = ((unsigned)(i0 + k) < (unsigned)Dl) ? __ldg(reinterpret_cast<const float4*>(ptr + k * Cg))
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                };
+                auto geo_put = [&](int u, const float4* q, float a) {
+                    const int px = u >> 2, l = (u >> 1) & 1, hh = u & 1;
+                    float v[2 * R + 3];
+                    v[2 * R + 2] = 0.f;
+                    const int k0 = (l * G1 + 4 * hh) * LT_TS;
+#pragma unroll
+                    for (int k = 0; k < 2 * R + 2; ++k) v[k] = q[k].x;
+                    put_taps<AP>(a_buf, A_PLANE, px, k0, v, a);
+#pragma unroll
+                    for (int k = 0; k < 2 * R + 2; ++k) v[k] = q[k].y;
+                    put_taps<AP>(a_buf, A_PLANE, px, k0 + LT_TS, v, a);
+#pragma unroll
+                    for (int k = 0; k < 2 * R + 2; ++k) v[k] = q[k].z;
+                    put_taps<AP>(a_buf, A_PLANE, px, k0 + 2 * LT_TS, v, a);
+#pragma unroll
+                    for (int k = 0; k < 2 * R + 2; ++k) v[k] = q[k].w;
+                    put_taps<AP>(a_buf, A_PLANE, px, k0 + 3 * LT_TS, v, a);
+                };
+                const int ua = tid, ub = tid + LT_THREADS;              // 128 pixels x 4 = 2 x 256 geometry units
+                float4 q[2 * R + 2];
+                float vi[2 * R + 3], aq, ai = 0.f;
+                const int ipx = tid >> 1, il = tid & 1;                // init-corr unit
+                const bool a_ok = (ua >> 2) < npix, b_ok = (ub >> 2) < npix, i_ok = ipx < npix;
+                if (a_ok) geo_load(ua, q, aq);
+                if (i_ok) {
+                    const int64_t p = p0 + ipx;
+                    const int Wl = prm.vw[il];
+                    const float inv = il ? 0.5f : 1.f;
+                    sample_row_load<R>(prm.vol[il] + p * Wl, Wl, (float)(p % prm.W1) * inv - s_x[ipx] * inv, vi, ai);
+                    vi[2 * R + 2] = 0.f;
+                }
+                if (a_ok) geo_put(ua, q, aq);
+                if (b_ok) geo_load(ub, q, aq);
+                if (i_ok) put_taps<AP>(a_buf, A_PLANE, ipx, (il * G1 + Cg) * LT_TS, vi, ai);
+                if (b_ok) geo_put(ub, q, aq);
+            } else
             for (int u0 = tid; u0 < npix * G; u0 += LT_THREADS * GU) {
                 float v[GU][2 * R + 3], av[GU];
 #pragma unroll
@@ -361,6 +564,310 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// IGEV lookup with the geometry runs fetched by the TMA unit (default for hi-plane taps).
+//
+// Why (tools/dram_random_probe.cu, profiles/r2w_dram_random_probe.txt, measured on B200): a gather made of per-thread
+// loads is bound by the number of L1 -> L2 sector REQUESTS, ~50 G/s on the whole chip no matter how many are in flight
+// (10-float runs 24 G runs/s, 80-float runs 5 G runs/s = 1.6 TB/s, against 6.7 TB/s streaming): the 320-byte run a
+// (pixel, level) needs from the (B,H,W,D,8) geometry volume costs ten of them.  One cp.async.bulk (1-D TMA) per run
+// moves the same bytes as whole-line requests: 17.8 G runs/s = 5.7 TB/s in the same probe.
+//
+//   warps 0..7    producers: per 32-pixel sub-chunk, lanes 0..15 of each warp own one (pixel, volume) each: read disp
+//                 (+ delta; written back), wait for the stage to be free, add their byte count to its mbarrier and issue
+//                 one bulk copy -- clamped to the samples inside [0, D) / to the array -- into a 4-stage ring.  (One warp
+//                 issues a bulk copy every ~59 clocks through its elect / uniform-register loop: a single producer warp
+//                 was the bottleneck of the first version; eight of them overlap.)
+//   warps 8..15   gather: wait for a stage, read a (pixel, level, channel pair)'s ten samples back from shared memory
+//                 (slot stride 88 floats: conflict-free), interpolate, store the taps as 16-bit values into the K-major
+//                 SWIZZLE_128B A tile (put_taps); the init-corr rows come the same way as the aligned 64-byte window
+//                 around their 10 floats.  After 4 sub-chunks one elected thread issues the 12 x 2 tcgen05.mma of the
+//                 chunk into one of TWO TMEM accumulators and the warps go on to the next chunk
+//   warps 16..19  epilogue: accumulator -> bias, ReLU -> fp32 / 16-bit planes through a staging tile -> 128-byte rows
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GT_SUB = 32;                       // pixels per ring stage
+constexpr int GT_NST = 4;                        // ring stages
+constexpr int GT_RUN = 88;                       // floats per (pixel, level) slot (80 used)
+constexpr int GT_WIN = 16;                       // floats per init-corr window (the aligned 64 bytes that hold a 10-float run)
+constexpr uint32_t GT_GEO_BYTES = GT_SUB * 2 * GT_RUN * 4;        // 22528
+constexpr uint32_t GT_STAGE_BYTES = GT_GEO_BYTES + GT_SUB * 2 * GT_WIN * 4;      // + 4096 = 26 x 1024
+constexpr int GT_PROD_WARPS = 8, GT_GATHER_WARPS = 8, GT_EPI_WARPS = 4;
+constexpr int GT_ISSUE_LANES = LT_M / GT_PROD_WARPS;        // 128 bulk copies per sub-chunk: lanes 0..15 of each producer warp
+constexpr int GT_THREADS = 32 * (GT_PROD_WARPS + GT_GATHER_WARPS + GT_EPI_WARPS);
+constexpr int GT_KB = 3;
+constexpr size_t GT_SMEM = 1024 + (size_t)GT_KB * LT_A_KB_BYTES + 2 * (size_t)GT_KB * LT_W_KB_BYTES + GT_NST * GT_STAGE_BYTES +
+                           LT_M * 128 + (GT_NST * GT_SUB + LT_N) * 4 + 16 * 8 + 64;
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int R>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+geo_lookup_tma_kernel(const __grid_constant__ LookupTcParams prm) {
+    static_assert(2 * R + 2 == LT_TS, "tap slots");
+    constexpr int Cg = 8, G1 = Cg + 1;
+    constexpr uint32_t A_PLANE = GT_KB * LT_A_KB_BYTES;
+    constexpr uint32_t W_PLANE = GT_KB * LT_W_KB_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_tile = smem;                                   // [KB][128 x 128 B], hi plane
+    uint8_t* w_tile = a_tile + A_PLANE;                       // [2][KB][64 x 128 B]
+    uint8_t* ring = w_tile + 2 * W_PLANE;                     // [NST][32 pixels][2 levels][GT_RUN floats]
+    uint8_t* ostage = ring + GT_NST * GT_STAGE_BYTES;         // [128][128 B] output rows
+    float* s_xr = reinterpret_cast<float*>(ostage + LT_M * 128);       // [NST][32] disparity of the staged pixels
+    float* s_bias = s_xr + GT_NST * GT_SUB;
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_bias + LT_N);       // [NST]
+    uint64_t* empty = full + GT_NST;                                    // [NST]
+    uint64_t* a_free = empty + GT_NST;                                  // MMAs of a chunk retired: A tile reusable
+    uint64_t* acc_full = a_free + 1;                                    // [2]
+    uint64_t* acc_empty = acc_full + 2;                                 // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    for (uint32_t i = tid; i < A_PLANE / 16; i += GT_THREADS) reinterpret_cast<uint4*>(a_tile)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < 2 * W_PLANE / 16; i += GT_THREADS)
+        reinterpret_cast<uint4*>(w_tile)[i] = __ldg(reinterpret_cast<const uint4*>(prm.w_img) + i);
+    if (tid < LT_N) s_bias[tid] = __ldg(prm.bias + tid);
+    if (tid == 0) {
+        for (int i = 0; i < GT_NST; ++i) { mbar_init(&full[i], GT_PROD_WARPS * GT_ISSUE_LANES); mbar_init(&empty[i], GT_GATHER_WARPS); }
+        mbar_init(a_free, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], GT_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == GT_PROD_WARPS) tmem_alloc(tmem_slot, 256);
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t nchunks = (prm.P + LT_M - 1) / LT_M;
+    const int D0 = prm.D, D1 = prm.D / 2;
+
+    constexpr int SUBS = LT_M / GT_SUB;                        // sub-chunks per chunk
+    // this CTA's sub-chunk sequence n -> (chunk, sb)
+    const int64_t my_chunks = blockIdx.x < nchunks ? (nchunks - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int64_t nsub = my_chunks * SUBS;
+    auto sub_pixel0 = [&](int64_t n) { return ((int64_t)blockIdx.x + (n / SUBS) * gridDim.x) * LT_M + (n % SUBS) * GT_SUB; };
+
+    if (warp < GT_PROD_WARPS) {
+        // ===== producer warps: op = warp * 16 + lane (lane < 16): pixel op >> 2 of the sub-chunk, kind op & 3 = geo L0, geo L1,
+        // init L0, init L1.  Every issuing thread arrives once per stage use with its own byte count.
+        if (lane < GT_ISSUE_LANES) {
+            const int op = warp * GT_ISSUE_LANES + lane, opx = op >> 2, okind = op & 3, l = okind & 1;
+            // disp and delta of the NEXT sub-chunk are requested one iteration ahead and only added when that iteration
+            // starts: an add right behind the loads would park the warp for a full memory latency per sub-chunk
+            // (ncu r2z: that wait, not the copies, set the pace of the whole kernel)
+            auto load_x = [&](int64_t n, float& c0, float& d0) {
+                c0 = 0.f;
+                d0 = 0.f;
+                if (n < nsub) {
+                    const int64_t p = sub_pixel0(n) + opx;
+                    if (p < prm.P) {
+                        c0 = prm.coords[p];
+                        if (prm.delta) d0 = __ldg(prm.delta + p * prm.delta_C);
+                    }
+                }
+            };
+            float c_nx, d_nx;
+            load_x(0, c_nx, d_nx);
+            for (int64_t n = 0; n < nsub; ++n) {
+                const int st = (int)(n % GT_NST);
+                const uint32_t ph = (uint32_t)(n / GT_NST) & 1u;
+                const float cx = c_nx + d_nx;
+                load_x(n + 1, c_nx, d_nx);
+                const int64_t p = sub_pixel0(n) + opx;
+                uint32_t bytes = 0u, dst = 0u;
+                const float* src = nullptr;
+                if (p < prm.P) {
+                    if (okind < 2) {
+                        const int Dl = l ? D1 : D0;
+                        const float xf = floorf(cx * (l ? 0.5f : 1.f));
+                        const int i0 = (int)fminf(fmaxf(xf, -1.0e6f), 1.0e6f) - R;
+                        const int klo = i0 < 0 ? -i0 : 0;
+                        const int khi = (Dl - i0) < (2 * R + 2) ? (Dl - i0) : (2 * R + 2);
+                        if (khi > klo) {
+                            bytes = (uint32_t)(khi - klo) * (Cg * 4);
+                            src = prm.geo[l] + (p * Dl + i0 + klo) * Cg;
+                            dst = smem_u32(ring + (size_t)st * GT_STAGE_BYTES) + (uint32_t)(((opx * 2 + l) * GT_RUN + klo * Cg) * 4);
+                        }
+                    } else {
+                        // init-corr row: the aligned 16-float window around the 10-float run, clipped to the level's array (the
+                        // host checks that its length is a multiple of 4 floats); a neighbouring row's elements are masked by the reader
+                        const int Wl = prm.vw[l];
+                        const float inv = l ? 0.5f : 1.f;
+                        const float xf = floorf((float)(p % prm.W1) * inv - cx * inv);
+                        const int i0 = (int)fminf(fmaxf(xf, -1.0e6f), 1.0e6f) - R;
+                        if (i0 + 2 * R + 1 >= 0 && i0 < Wl) {
+                            const int64_t e = p * Wl + i0, total = prm.P * Wl;
+                            const int64_t a0 = (e >> 2) << 2;
+                            const int64_t lo = a0 < 0 ? 0 : a0, hi = (a0 + GT_WIN) > total ? total : (a0 + GT_WIN);
+                            if (hi > lo) {
+                                bytes = (uint32_t)(hi - lo) * 4u;
+                                src = prm.vol[l] + lo;
+                                dst = smem_u32(ring + (size_t)st * GT_STAGE_BYTES + GT_GEO_BYTES) +
+                                      (uint32_t)(((opx * 2 + l) * GT_WIN + (int)(lo - a0)) * 4);
+                            }
+                        }
+                    }
+                }
+                mbar_wait_backoff(&empty[st], ph ^ 1u, 64);    // the gather warps are done with the stage's previous use
+                if (okind == 0 && p < prm.P) {
+                    if (prm.delta) prm.coords[p] = cx;
+                    s_xr[st * GT_SUB + opx] = cx;
+                }
+                mbar_arrive_expect_tx(&full[st], bytes);       // release: this thread's s_xr store is ordered before it
+                if (bytes) bulk_g2s(dst, src, bytes, &full[st]);
+            }
+        }
+    } else if (warp < GT_PROD_WARPS + GT_GATHER_WARPS) {
+        // ===== gather warps =====
+        const int ct = tid - 32 * GT_PROD_WARPS;               // 0..255
+        const uint32_t idesc = idesc_bf16_m128(LT_N);
+        const int ksteps = (prm.C + 15) >> 4;
+        int64_t n = 0;
+        int ci = 0;
+        for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++ci) {
+            if (ci > 0) mbar_wait(a_free, (uint32_t)(ci - 1) & 1u);
+            for (int sb = 0; sb < SUBS; ++sb, ++n) {
+                const int st = (int)(n % GT_NST);
+                const uint32_t ph = (uint32_t)(n / GT_NST) & 1u;
+                const int64_t pb = chunk * LT_M + sb * GT_SUB;
+                const int npix_s = (int)((prm.P - pb) < GT_SUB ? (prm.P - pb) : GT_SUB);      // may be <= 0
+                mbar_wait(&full[st], ph);
+                const float* stg = reinterpret_cast<const float*>(ring + (size_t)st * GT_STAGE_BYTES);
+                const float* sx = s_xr + st * GT_SUB;
+                {   // geometry unit of this thread: (pixel, level, channel pair): ten 8-byte reads, two tap rows
+                    const int cp = ct & 3, l = (ct >> 2) & 1, px = ct >> 3;
+                    if (px < npix_s) {
+                        const int Dl = l ? D1 : D0;
+                        const float x = sx[px] * (l ? 0.5f : 1.f), xf = floorf(x);
+                        const int i0 = (int)fminf(fmaxf(xf, -1.0e6f), 1.0e6f) - R;
+                        const float2* base = reinterpret_cast<const float2*>(stg + (px * 2 + l) * GT_RUN + 2 * cp);
+                        float v0[2 * R + 3], v1[2 * R + 3];
+#pragma unroll
+                        for (int k = 0; k < 2 * R + 2; ++k) {
+                            const float2 q = ((unsigned)(i0 + k) < (unsigned)Dl) ? base[k * (Cg / 2)] : make_float2(0.f, 0.f);
+                            v0[k] = q.x;
+                            v1[k] = q.y;
+                        }
+                        v0[2 * R + 2] = 0.f;
+                        v1[2 * R + 2] = 0.f;
+                        put_taps<1>(a_tile, A_PLANE, sb * GT_SUB + px, (l * G1 + 2 * cp) * LT_TS, v0, x - xf);
+                        put_taps<1>(a_tile, A_PLANE, sb * GT_SUB + px, (l * G1 + 2 * cp + 1) * LT_TS, v1, x - xf);
+                    }
+                }
+                // init-corr row of (pixel, level): the 64 threads of the first two gather warps have one each (whole warps)
+                const int ipx = ct >> 1, il = ct & 1;
+                if (ct < 2 * GT_SUB && ipx < npix_s) {
+                    const int64_t p = pb + ipx;
+                    const int Wl = prm.vw[il];
+                    const float inv = il ? 0.5f : 1.f;
+                    const float x = (float)(p % prm.W1) * inv - sx[ipx] * inv, xf = floorf(x);
+                    const int i0 = (int)fminf(fmaxf(xf, -1.0e6f), 1.0e6f) - R;
+                    const int64_t e = p * Wl + i0;
+                    const float* win = stg + GT_GEO_BYTES / 4 + (ipx * 2 + il) * GT_WIN + (int)(e - ((e >> 2) << 2));
+                    float vi[2 * R + 3];
+#pragma unroll
+                    for (int k = 0; k < 2 * R + 2; ++k) vi[k] = ((unsigned)(i0 + k) < (unsigned)Wl) ? win[k] : 0.f;
+                    vi[2 * R + 2] = 0.f;
+                    put_taps<1>(a_tile, A_PLANE, sb * GT_SUB + ipx, (il * G1 + Cg) * LT_TS, vi, x - xf);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[st]);
+            }
+            fence_proxy_async();                               // tap stores -> visible to the tensor core's proxy
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (warp == GT_PROD_WARPS) {
+                const uint32_t acc = (uint32_t)ci & 1u;
+                if (ci >= 2) mbar_wait(&acc_empty[acc], (uint32_t)((ci >> 1) - 1) & 1u);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_hi = smem_u32(a_tile), w_hi = smem_u32(w_tile), w_lo = w_hi + W_PLANE;
+                    const uint32_t d = tmem_base + acc * 128u;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t ao = (uint32_t)(ks >> 2) * LT_A_KB_BYTES + (uint32_t)(ks & 3) * 32u;
+                        const uint32_t wo = (uint32_t)(ks >> 2) * LT_W_KB_BYTES + (uint32_t)(ks & 3) * 32u;
+                        umma_bf16(d, smem_desc_sw128(a_hi + ao), smem_desc_sw128(w_hi + wo), idesc, ks != 0);
+                        umma_bf16(d + LT_N, smem_desc_sw128(a_hi + ao), smem_desc_sw128(w_lo + wo), idesc, ks != 0);
+                    }
+                    umma_commit(a_free);
+                    umma_commit(&acc_full[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quarter = warp % 4, thread = pixel =====
+        const int et = tid - 32 * (GT_PROD_WARPS + GT_GATHER_WARPS);          // 0..127
+        const int q = warp & 3, m = q * 32 + lane;
+        const dkt_tensor& o = prm.out;
+        const int nplanes = o.hi ? (o.lo ? 2 : 1) : 0;
+        int ci = 0;
+        for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++ci) {
+            const uint32_t acc = (uint32_t)ci & 1u;
+            const int64_t p0 = chunk * LT_M;
+            const int npix = (int)((prm.P - p0) < LT_M ? (prm.P - p0) : LT_M);
+            mbar_wait_backoff(&acc_full[acc], (uint32_t)(ci >> 1) & 1u, 256);   // sleep between polls: a spinning warp per
+            tcgen05_fence_after();                                              // scheduler took a quarter of the issue slots
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128u;
+            const int64_t off0 = (p0 + m) * o.C + o.c_begin;
+            for (int pl = 0; pl < (nplanes ? nplanes : 1); ++pl) {
+#pragma unroll
+                for (int cc = 0; cc < LT_N; cc += 16) {
+                    float v[16], v2[16];
+                    tmem_ld16(taddr + cc, v);
+                    tmem_ld16(taddr + LT_N + cc, v2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + v2[j] + s_bias[cc + j], 0.f);
+                    if (pl == 0 && o.f32 && m < npix) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(o.f32 + off0 + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                    if (nplanes) {
+                        uint32_t w16[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            uint32_t h, l;
+                            split16x2(v[2 * t], v[2 * t + 1], h, l);
+                            w16[t] = pl == 0 ? h : l;
+                        }
+                        const int ch0 = cc >> 3;
+                        uint8_t* rowp = ostage + m * 128;
+                        *reinterpret_cast<uint4*>(rowp + (((ch0 + 0) ^ (m & 7)) << 4)) = make_uint4(w16[0], w16[1], w16[2], w16[3]);
+                        *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ (m & 7)) << 4)) = make_uint4(w16[4], w16[5], w16[6], w16[7]);
+                    }
+                }
+                if (pl + 1 >= nplanes) {                       // last read of this accumulator: hand it back to the MMA issuer
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                }
+                if (nplanes) {
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    uint16_t* const dstp = pl == 0 ? o.hi : o.lo;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int idx = et + i * 128;          // 128 rows x 8 chunks
+                        const int r = idx >> 3, c = idx & 7;
+                        if (r < npix)
+                            *reinterpret_cast<uint4*>(dstp + (p0 + r) * o.C + o.c_begin + c * 8) =
+                                *reinterpret_cast<const uint4*>(ostage + r * 128 + ((c ^ (r & 7)) << 4));
+                    }
+                    asm volatile("bar.sync 2, 128;" ::: "memory");   // the next plane / chunk reuses the tile
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == GT_PROD_WARPS) tmem_dealloc(tmem_base, 256);
 }
 
 // ---- IGEV geometry encoding volume: (B,C,D,H,W) -> level 0 (B,H,W,D,C) + pooled level 1 (B,H,W,D/2,C) ----
@@ -509,6 +1016,19 @@ extern "C" int dkt_geo_lookup_enc_tc(const float* geo0, const float* geo1, const
     prm.w_img = w_img; prm.bias = enc_b; prm.out = *enc_out;
     prm.P = (int64_t)B * H * W;
     prm.C = 2 * (C + 1) * LT_TS;
+    {
+        // hi-plane taps (what the update loop runs): geometry runs through the TMA unit; DKT_LOOKUP_TMA=0 keeps the
+        // per-thread gather.  The bulk copies need 16-byte aligned volumes (32-byte runs of 8 channels).
+        static const int s_tma = [] { const char* v = getenv("DKT_LOOKUP_TMA"); return (v && v[0] == '0') ? 0 : 1; }();
+        const bool win_ok = (prm.P * prm.vw[0]) % 4 == 0 && (prm.P * prm.vw[1]) % 4 == 0 &&
+                            !((reinterpret_cast<uintptr_t>(init0) | reinterpret_cast<uintptr_t>(init1)) & 15);
+        if (s_tma && tap_planes == 1 && win_ok && !((reinterpret_cast<uintptr_t>(geo0) | reinterpret_cast<uintptr_t>(geo1)) & 15)) {
+            DKT_ENSURE_SMEM(GT_SMEM, geo_lookup_tma_kernel<4>);
+            const int64_t chunks = ceil_div64(prm.P, LT_M), cap = device_sms();
+            geo_lookup_tma_kernel<4><<<(unsigned)(chunks < cap ? chunks : cap), GT_THREADS, GT_SMEM, (cudaStream_t)stream>>>(prm);
+            DKT_RETURN_LAST();
+        }
+    }
     return tap_planes == 2 ? launch_lookup_tc<3, 2, 1, true>(prm, (cudaStream_t)stream)
                            : launch_lookup_tc<3, 1, 1, true>(prm, (cudaStream_t)stream);
 }
