@@ -119,7 +119,7 @@ class EncoderEngine:
             c2 = self.fnet.conv2                  # 128 -> 256 as two N = 128 halves (second accumulator for the lo products)
             for g in range(2):
                 w[f"f.conv2.{g}"] = ops.pack_conv_general(c2.weight[128 * g:128 * (g + 1)], c2.bias[128 * g:128 * (g + 1)])
-        heads = [getattr(self.cnet, n) for n in self.cnet.head_names]
+        heads = [getattr(self.cnet, n) for n in self.cnet.head_names][:len(self.zqr)]     # n_gru_layers levels
         for i, hl in enumerate(heads):
             for j, head in enumerate(hl):
                 if isinstance(head, nn.Sequential):
@@ -279,7 +279,8 @@ class EncoderEngine:
         # ---- cnet on left (reference raft_stereo.py:101); the stem rows of the left images are still there ----
         x = self._trunk("c", self.cnet, B)
         feats = [x]
-        for li, lname in ((3, "layer4"), (4, "layer5")):
+        nl = len(self.zqr)                                # args.n_gru_layers (reference core/extractor.py:288-295)
+        for li, lname in ((3, "layer4"), (4, "layer5"))[:nl - 1]:
             cur = feats[-1]
             for i in range(2):
                 scratch = self.lvl[li]
@@ -288,7 +289,7 @@ class EncoderEngine:
                 self._block(f"c.{lname}.{i}", cur, out, scratch, False)
                 cur = out
             feats.append(cur)
-        for i in range(3):
+        for i in range(nl):
             f = feats[i]
             scratch = dict(Y=self.HY[i], RAW=self.lvl[2 + i]["RAW"], RAWD=self.lvl[2 + i]["RAWD"])
             for j in range(2):

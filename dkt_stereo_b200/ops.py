@@ -59,6 +59,7 @@ def corr1d_build(fmap1: torch.Tensor, fmap2: torch.Tensor, levels: int, scale: f
         pyr = alloc_pyramid(B, H, W1, W2, levels, fmap1.device)
     ptrs = L.pointer_array(pyr)
     sb, sd, sh, sw = fmap1.stride()
+    sb2, sd2, sh2, sw2 = fmap2.stride()        # W2 != W1: the right map has its own batch / channel / row strides
     if impl == "tc" and D % 8 == 0:
         hi1 = torch.empty(B, H, W1, D, device=fmap1.device, dtype=L.split_dtype())
         lo1, hi2, lo2 = torch.empty_like(hi1), torch.empty(B, H, W2, D, device=fmap1.device, dtype=L.split_dtype()), None
@@ -66,11 +67,14 @@ def corr1d_build(fmap1: torch.Tensor, fmap2: torch.Tensor, levels: int, scale: f
         s = L.stream_ptr()
         L.check(lib.dkt_split_nchw_to_nhwc_bf16x2(fmap1.data_ptr(), sb, sd, sh, sw, hi1.data_ptr(), lo1.data_ptr(),
                                                   B, D, H, W1, s), "split fmap1")
-        L.check(lib.dkt_split_nchw_to_nhwc_bf16x2(fmap2.data_ptr(), sb, sd, sh, sw, hi2.data_ptr(), lo2.data_ptr(),
+        L.check(lib.dkt_split_nchw_to_nhwc_bf16x2(fmap2.data_ptr(), sb2, sd2, sh2, sw2, hi2.data_ptr(), lo2.data_ptr(),
                                                   B, D, H, W2, s), "split fmap2")
         L.check(lib.dkt_corr1d_build_tc(hi1.data_ptr(), lo1.data_ptr(), hi2.data_ptr(), lo2.data_ptr(), ptrs,
                                         B, D, H, W1, W2, levels, float(scale), s), "corr1d_build_tc")
     else:
+        if (sb2, sd2, sh2, sw2) != (sb, sd, sh, sw):
+            raise L.DktError("corr1d_build (fp32 kernel): dkt_corr1d_build_f32 takes ONE stride set for both feature maps; "
+                             "W2 != W1 is served by the tensor-core path (impl='tc', D % 8 == 0)")
         L.check(lib.dkt_corr1d_build_f32(fmap1.data_ptr(), fmap2.data_ptr(), sb, sd, sh, sw, ptrs,
                                          B, D, H, W1, W2, levels, float(scale), L.stream_ptr()), "corr1d_build_f32")
     return pyr

@@ -65,12 +65,14 @@ class BasicMultiUpdateBlock(nn.Module):
         self.args = args
         self.igev = igev
         hd = list(hidden_dims)
-        assert hd == [128, 128, 128] and args.n_gru_layers == 3, \
-            "the B200 engine is built for the shipped configs (3 GRU levels, 128 hidden channels)"
+        n = args.n_gru_layers
+        assert hd == [128, 128, 128] and n in (1, 2, 3), \
+            "the B200 engine serves 128 hidden channels (the shipped configs) with 1, 2 or 3 GRU levels"
         self.encoder = BasicMotionEncoder(args, igev)
         names = ("gru04", "gru08", "gru16") if igev else ("gru08", "gru16", "gru32")
-        setattr(self, names[0], ConvGRU(hd[2], 128 + hd[1]))
-        setattr(self, names[1], ConvGRU(hd[1], hd[0] + hd[2]))
+        # input widths as in the reference (core/update.py:104-106): a level that does not run contributes no input
+        setattr(self, names[0], ConvGRU(hd[2], 128 + hd[1] * (n > 1)))
+        setattr(self, names[1], ConvGRU(hd[1], hd[0] * (n == 3) + hd[2]))
         setattr(self, names[2], ConvGRU(hd[0], hd[1]))
         self.gru_names = names
         if igev:
@@ -118,6 +120,8 @@ class UpdateEngine:
         # args.slow_fast_gru (reference raft_stereo.py:157-160, igev_stereo.py:201-204): per iteration one extra
         # update of the coarsest GRU, then one of the two coarse GRUs, before the full update
         self.slow_fast = bool(getattr(block.args, "slow_fast_gru", False))
+        # GRU levels that run (args.n_gru_layers, reference core/update.py:117-132): level i lives at 1 / (4 * 2^i) resolution
+        self.n = int(block.args.n_gru_layers)
         # MMAs per K step of the GRU convs and of the motion encoder's 64/128-channel convs (tensor-core path): 3 = every
         # operand a 16-bit (hi, lo) pair; 2 = activations as ONE half value (hi plane only) against (hi, lo) weights.
         # The per-group error study on the headline workload (profiles/r2_precision_study_*)
@@ -166,7 +170,7 @@ class UpdateEngine:
         w["stem2"] = ops.pack_conv(stem2.weight, stem2.bias, tc=tc)
         w["conv"] = ops.pack_conv(enc.conv.weight, enc.conv.bias, tc=tc)
         self.gru_bias = []
-        for i, name in enumerate(b.gru_names):
+        for i, name in enumerate(b.gru_names[:self.n]):
             g = getattr(b, name)
             w[f"zr{i}"] = ops.pack_conv_cat([g.convz.weight, g.convr.weight], tc=tc)
             w[f"q{i}"] = ops.pack_conv(g.convq.weight, None, tc=tc)
@@ -225,18 +229,21 @@ class UpdateEngine:
         self.device = device
         self.B = B
         self.hw = [(h, w)]
-        for _ in range(2):
+        for _ in range(self.n - 1):
             ph, pw = self.hw[-1]
             self.hw.append(((ph - 1) // 2 + 1, (pw - 1) // 2 + 1))
-        (h0, w0), (h1, w1), (h2, w2) = self.hw
+        h0, w0 = self.hw[0]
+        n = self.n
         simt = self.impl == "simt"
         nflow = 1 if self.igev else 2
         self.nflow = nflow
         # in "tc" mode fp32 copies are only kept where an elementwise consumer needs them
-        self.X = [self._buf(B, h0, w0, 384), self._buf(B, h1, w1, 384), self._buf(B, h2, w2, 256)]
-        self.RH = [self._buf(B, *self.hw[i], 128, f32=simt) for i in range(3)]
-        self.Z = [self._buf(B, *self.hw[i], 128, split=False) for i in range(3)]
-        self.CTX = [self._buf(B, *self.hw[i], 384, split=False) for i in range(3)]
+        # X[i] = [h_i | x]: level 0 x = motion (+ up(h1)), level 1 x = pool(h0) (+ up(h2)), level 2 x = pool(h1)
+        self.xc = [128 + (128 if n > 1 else 0), 128 + (128 if n == 3 else 0), 128][:n]
+        self.X = [self._buf(B, *self.hw[i], 128 + self.xc[i]) for i in range(n)]
+        self.RH = [self._buf(B, *self.hw[i], 128, f32=simt) for i in range(n)]
+        self.Z = [self._buf(B, *self.hw[i], 128, split=False) for i in range(n)]
+        self.CTX = [self._buf(B, *self.hw[i], 384, split=False) for i in range(n)]
         self.CORR = self._buf(B, h0, w0, self.corr_pad)
         self.COR1 = self._buf(B, h0, w0, 64, f32=simt)
         self.FLO1 = self._buf(B, h0, w0, 64, f32=simt)
@@ -262,7 +269,7 @@ class UpdateEngine:
         terms (reference raft_stereo.py:110-114).  Conv biases of the gates are folded into the
         context term once here."""
         split = self.impl == "tc"
-        for i in range(3):
+        for i in range(self.n):
             ops.nchw_to_nhwc(net_list[i], self._slice(self.X[i], 0, 128, True, split))
             ctx = inp_list[i]
             ctx = ctx if torch.is_tensor(ctx) else torch.cat(list(ctx), dim=1)
@@ -270,7 +277,7 @@ class UpdateEngine:
 
     def hidden_states(self) -> List[torch.Tensor]:
         return [ops.nhwc_to_nchw(self._slice(self.X[i], 0, 128, True, False), self.B, *self.hw[i], self.device)
-                for i in range(3)]
+                for i in range(self.n)]
 
     # ---- one GRU ---------------------------------------------------------------------------------
     def _gru(self, i: int, x_cnt: int) -> None:
@@ -289,7 +296,10 @@ class UpdateEngine:
                    self.weights[f"q{i}"], e, B, H, W, impl)
 
     def _coarsest_gru(self) -> None:
-        """gru32 alone: update_block(iter32=True, iter16=False, iter08=False, update=False), reference core/update.py:117-118."""
+        """gru32 alone: update_block(iter32=True, iter16=False, iter08=False, update=False), reference core/update.py:117-118
+        (only with three levels)."""
+        if self.n < 3:
+            return
         B, split, simt = self.B, self.impl == "tc", self.impl == "simt"
         h1, w1 = self.hw[1]
         S = self._slice
@@ -298,30 +308,34 @@ class UpdateEngine:
 
     def _coarse_grus(self) -> None:
         """gru32 then gru16 (reference core/update.py:118-128): coarse -> fine; every GRU sees the OLD finer state
-        pooled and the NEW coarser state upsampled."""
+        pooled and the NEW coarser state upsampled.  Two levels: gru16 sees pool(h0) alone; one level: nothing to do."""
+        if self.n < 2:
+            return
         B, split, simt = self.B, self.impl == "tc", self.impl == "simt"
-        (h0, w0), (h1, w1), (h2, w2) = self.hw
-        X0, X1, X2 = self.X
+        (h0, w0), (h1, w1) = self.hw[:2]
+        X0, X1 = self.X[:2]
         S = self._slice
         self._coarsest_gru()
         ops.pool2x(S(X0, 0, 128, True, False), S(X1, 128, 128, simt, split, not self.gru2), B, h0, w0)
-        ops.interp(S(X2, 0, 128, True, False), S(X1, 256, 128, simt, split, not self.gru2), B, h2, w2, h1, w1)
-        self._gru(1, 256)
+        if self.n == 3:
+            h2, w2 = self.hw[2]
+            ops.interp(S(self.X[2], 0, 128, True, False), S(X1, 256, 128, simt, split, not self.gru2), B, h2, w2, h1, w1)
+        self._gru(1, self.xc[1])
 
     # ---- one update-block call (reference core/update.py:115-138) -------------------------------
     def step(self, lookup, with_mask: bool = False) -> None:
         """lookup(engine) does the coords / disparity bookkeeping of this iteration and fills self.COR1
         (fused_enc: lookup + convc1 in one kernel) or self.CORR (unfused)."""
         B, impl, split, simt = self.B, self.impl, self.impl == "tc", self.impl == "simt"
-        (h0, w0), (h1, w1), (h2, w2) = self.hw
-        X0, X1, X2 = self.X
+        h0, w0 = self.hw[0]
+        X0 = self.X[0]
         Wt = self.weights
         S = self._slice
         E = ops.make_epilogue
         # The two coarse GRUs and the motion encoder are independent until gru08: they run on two streams (fork /
         # join with events, also inside a CUDA-graph capture) so that the tail of one branch's persistent kernels
         # (1/8 and 1/16 resolution fill 3.4 and 0.9 waves of CTA pairs) overlaps the other branch's work.
-        fork = self.two_streams and LaunchProfilerActive() is None
+        fork = self.two_streams and LaunchProfilerActive() is None and self.n > 1
         main = torch.cuda.current_stream()
         if self.slow_fast:
             self._coarsest_gru()
@@ -361,8 +375,10 @@ class UpdateEngine:
                      tail=self.FLOW["f32"]), B, h0, w0, impl)
         if fork:
             main.wait_event(ev2)
-        ops.interp(S(X1, 0, 128, True, False), S(X0, 256, 128, simt, split, glo), B, h1, w1, h0, w0)
-        self._gru(0, 256)
+        if self.n > 1:
+            h1, w1 = self.hw[1]
+            ops.interp(S(self.X[1], 0, 128, True, False), S(X0, 256, 128, simt, split, glo), B, h1, w1, h0, w0)
+        self._gru(0, self.xc[0])
         # flow / disparity head (reference core/update.py:13-14)
         if split and self.fast_small_convs and self.fused_head:
             ops.conv2d([S(X0, 0, 128, False, True)], Wt["head1"],

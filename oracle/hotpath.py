@@ -301,7 +301,8 @@ def raft_prepare(sd: SD, image1: Tensor, image2: Tensor, cfg: dict):
     ds = cfg.get("n_downsample", 2)
     image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
     image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
-    cnet = multi_basic_encoder(sd, "cnet.", image1, cfg.get("context_norm", "batch"), ds)
+    # num_layers = n_gru_layers (raft_stereo.py:101, core/extractor.py:288-295): only the scales that have a GRU
+    cnet = multi_basic_encoder(sd, "cnet.", image1, cfg.get("context_norm", "batch"), ds)[:cfg.get("n_gru_layers", 3)]
     fmaps = basic_encoder(sd, "fnet.", torch.cat([image1, image2], 0), "instance", ds)
     fmap1, fmap2 = fmaps.split(image1.shape[0], 0)
     net = [torch.tanh(s[0]) for s in cnet]

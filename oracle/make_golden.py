@@ -205,7 +205,7 @@ def golden_igev_forward(m, height=64, width=96, iters=4, tag="igev_fwd_small", b
         # updates come first and carry no disparity); first call WITH a disparity: the initial disparity
         if "net0" not in cap:
             net, inp = args[:2]
-            for i in range(3):
+            for i in range(len(net)):
                 cap[f"net{i}"] = net[i].clone()
                 cap[f"ctx{i}"] = torch.cat(list(inp[i]), 1).clone()
         if "init_disp" not in cap and len(args) > 3 and args[3] is not None:
@@ -330,6 +330,10 @@ def main():
         # slow_fast_gru=True (raft_stereo.py:157-160 / igev_stereo.py:201-204): extra coarse-GRU updates per iteration
         "raft_slowfast": lambda: golden_raft_forward(m, 64, 96, 4, "raft_fwd_slowfast", 1, "noise", slow_fast_gru=True),
         "igev_slowfast": lambda: golden_igev_forward(m, 64, 96, 4, "igev_fwd_slowfast", 1, slow_fast_gru=True),
+        # n_gru_layers 1 / 2 (core/update.py:104-105,121-132; meta_arch/igev_stereo/update.py:111-112,126-135)
+        "raft_gru1": lambda: golden_raft_forward(m, 64, 96, 4, "raft_fwd_gru1", 1, "noise", n_gru_layers=1),
+        "raft_gru2": lambda: golden_raft_forward(m, 64, 96, 4, "raft_fwd_gru2", 1, "noise", n_gru_layers=2, slow_fast_gru=True),
+        "igev_gru2": lambda: golden_igev_forward(m, 64, 96, 4, "igev_fwd_gru2", 1, n_gru_layers=2),
         "igev_small": lambda: golden_igev_forward(m),
         "igev_mid": lambda: golden_igev_forward(m, 96, 160, 8, "igev_fwd_mid", 1),
         "igev_volume": lambda: golden_igev_volume(m),

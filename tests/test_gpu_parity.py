@@ -82,6 +82,22 @@ def test_corr1d_build_wide_rows(impl, w):
         assert stats(pyr[i].cpu(), ref[i])[1] < tol, (impl, w, i, stats(pyr[i].cpu(), ref[i]))
 
 
+def test_corr1d_build_right_map_narrower_than_left():
+    """W2 != W1 (the API and the C ABI carry both): the right map is read with its OWN strides (round-1 advisor finding:
+    it used to be read with the left map's); the fp32 entry point, which has one stride set, must refuse instead."""
+    from dkt_stereo_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(11)
+    f1 = torch.randn(2, 64, 3, 48, generator=g)
+    f2 = torch.randn(2, 64, 3, 32, generator=g)
+    ref = torch.einsum("bdhi,bdhj->bhij", f1, f2) / 8.0
+    pyr = ops.corr1d_build(f1.to(dev()), f2.to(dev()), 2, 1.0 / 8.0, impl="tc")
+    assert pyr[0].shape == (2, 3, 48, 32) and pyr[1].shape == (2, 3, 48, 16)
+    assert stats(pyr[0].cpu(), ref)[1] < 5e-4, stats(pyr[0].cpu(), ref)
+    assert stats(pyr[1].cpu(), 0.5 * (ref[..., 0::2] + ref[..., 1::2]))[1] < 5e-4
+    with pytest.raises(L.DktError):
+        ops.corr1d_build(f1.to(dev()), f2.to(dev()), 2, 1.0 / 8.0, impl="simt")
+
+
 def test_raft_forward_wide_image_runs_native():
     """736 x 1280 (BASELINE configs[3], w = 320 > 256) goes through the native tensor-core path end to end and agrees with
     the exact-fp32 CUDA-core path of the same engine within the end-to-end gate."""
@@ -620,6 +636,33 @@ def test_slow_fast_gru(impl, monkeypatch):
     with torch.no_grad():
         up = m.hot_path(d("match_left"), d("match_right"), d("gev"), d("init_disp"),
                         [d(f"net{i}") for i in range(3)], [d(f"ctx{i}") for i in range(3)], d("stem_2x"), iters)
+    assert stats(up.cpu(), g["disp_up"])[0] <= 1e-3, stats(up.cpu(), g["disp_up"])
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_n_gru_layers_one_and_two(impl, monkeypatch):
+    """args.n_gru_layers = 1 / 2 through the public forward() against the REAL reference's output (oracle/make_golden.py
+    --only raft_gru1,raft_gru2,igev_gru2); n = 2 with slow_fast_gru (its extra update runs the mid level alone)."""
+    from dkt_stereo_b200.igev_stereo import IGEVStereo
+    from dkt_stereo_b200.synthetic import synthetic_pair, synthetic_state_dict
+    for tag, over in (("raft_fwd_gru1", dict(n_gru_layers=1)), ("raft_fwd_gru2", dict(n_gru_layers=2, slow_fast_gru=True))):
+        g = load_golden(tag)
+        B, H, W, iters = [int(v) for v in g["meta"]]
+        model = _model(impl, g, **over)
+        im1, im2 = synthetic_pair(B, H, W, seed=1234, mode=str(g["mode"]))
+        for _ in range(3):                                       # eager, graph capture, graph replay
+            _, up = model(im1.to(dev()), im2.to(dev()), iters=iters, test_mode=True)
+        assert stats(up.cpu(), g["flow_up"])[0] <= 1e-3, (tag, stats(up.cpu(), g["flow_up"]))
+    monkeypatch.setenv("DKT_IMPL", impl)
+    g = load_golden("igev_fwd_gru2")
+    B, H, W, iters = [int(v) for v in g["meta"]]
+    m = IGEVStereo(Namespace(mixed_precision=False, **dict(IGEV_CFG, n_gru_layers=2))).eval()
+    m.load_state_dict(synthetic_state_dict(golden_shapes(g), seed=0), strict=False)
+    m = m.to(dev())
+    d = lambda k: g[k].to(dev())
+    with torch.no_grad():
+        up = m.hot_path(d("match_left"), d("match_right"), d("gev"), d("init_disp"),
+                        [d(f"net{i}") for i in range(2)], [d(f"ctx{i}") for i in range(2)], d("stem_2x"), iters)
     assert stats(up.cpu(), g["disp_up"])[0] <= 1e-3, stats(up.cpu(), g["disp_up"])
 
 

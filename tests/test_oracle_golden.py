@@ -90,6 +90,28 @@ def test_slow_fast_gru_schedule():
     assert stats(up, g["disp_up"])[0] < 1e-4
 
 
+def test_n_gru_layers_one_and_two():
+    """args.n_gru_layers = 1 / 2 (reference core/update.py:104-105,121-132; igev update.py:111-112,126-135): levels that do
+    not run contribute no GRU input; n = 2 is generated with slow_fast_gru so that its mid-level-only extra update
+    (raft_stereo.py:159-160) is pinned too."""
+    for tag, over in (("raft_fwd_gru1", dict(n_gru_layers=1)), ("raft_fwd_gru2", dict(n_gru_layers=2, slow_fast_gru=True))):
+        g = load_golden(tag)
+        B, H, W, iters = [int(v) for v in g["meta"]]
+        sd = synthetic_state_dict(golden_shapes(g), seed=0)
+        im1, im2 = synthetic_pair(B, H, W, seed=1234, mode=str(g["mode"]))
+        lr, up = O.raft_forward(sd, im1, im2, iters, dict(RAFT_CFG, **over))
+        assert stats(up, g["flow_up"])[0] < 1e-4, (tag, stats(up, g["flow_up"]))
+    g = load_golden("igev_fwd_gru2")
+    B, H, W, iters = [int(v) for v in g["meta"]]
+    sd = synthetic_state_dict(golden_shapes(g), seed=0)
+    net = [g[f"net{i}"] for i in range(2)]
+    inp = [list(g[f"ctx{i}"].split(128, dim=1)) for i in range(2)]
+    with torch.no_grad():
+        up = O.igev_loop(sd, g["match_left"], g["match_right"], g["gev"], g["init_disp"], net, inp,
+                         g["stem_2x"], iters, dict(IGEV_CFG, n_gru_layers=2))
+    assert stats(up, g["disp_up"])[0] < 1e-4
+
+
 def test_raft_forward_headline_config():
     """The oracle at the benchmark's own resolution and iteration count (544 x 960, 32 iterations, one pair) against
     the real reference's disparity map (tests/golden/raft_fwd_cfg2.npz, oracle/make_golden.py --only raft_cfg2)."""
