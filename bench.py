@@ -298,7 +298,9 @@ def igev_lookup_roofline(model, Bg, h, w, peaks):
     torch.cuda.synchronize()
     lk_ms = a.elapsed_time(b) / 20
     tr = ncu_traffic("geo_lookup_enc") if (h, w, Bg) == (136, 240, 8) else None
-    return {"kernel": ("lookup_tc_kernel<GEO> (Combined_Geo_Encoding_Volume lookup + convc1 on tcgen05)" if eng.lookup_tc else
+    tma = eng.lookup_tc and eng.lookup_tap_planes == 1 and os.environ.get("DKT_LOOKUP_TMA", "1") != "0"
+    return {"kernel": ("geo_lookup_tma_kernel (Combined_Geo_Encoding_Volume lookup: TMA bulk-copy gather, convc1 on tcgen05)" if tma else
+                       "lookup_tc_kernel<GEO> (Combined_Geo_Encoding_Volume lookup + convc1 on tcgen05)" if eng.lookup_tc else
                        "geo_lookup_kernel<4, ENC> (Combined_Geo_Encoding_Volume lookup + convc1, fp32 FMAs)"), "bound": "hbm",
             "achieved": lk_bytes / (lk_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": lk_bytes / (lk_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": tr["dram_bytes"] if tr else None,

@@ -120,6 +120,7 @@ class IGEVStereo(nn.Module):
             stem_4 = self.stem_4(stem_2)
             stem_2x = stem_2[:B]
             feats[0] = torch.cat((feats[0], stem_4), 1)
+            self._feat4 = feats[0][:B]            # left 1/4 features: input of spx_4 (test_mode=False only, reference :179)
             match = self.desc(self.conv(feats[0]))
             match_left, match_right = match[:B], match[B:]
             fl = [f[:B] for f in feats]
@@ -235,8 +236,10 @@ class IGEVStereo(nn.Module):
             spx = F.softmax(self.spx_gru(self.spx_2_gru(mask_feat_4, stem_2x)), 1)
         return ops.context_upsample(disp, spx, in_scale=4.0, out_scale=-1.0)      # reference :216 negates
 
-    def hot_path(self, match_left, match_right, gev, init_disp, net_list, ctx_list, stem_2x, iters: int) -> torch.Tensor:
-        """-> disp_up (B,1,H,W), already negated like the reference's return value."""
+    def hot_path(self, match_left, match_right, gev, init_disp, net_list, ctx_list, stem_2x, iters: int,
+                 all_preds: bool = False):
+        """-> disp_up (B,1,H,W), already negated like the reference's return value (``all_preds``: the list of every
+        iteration's disp_up, reference igev_stereo.py:213-217 with test_mode=False)."""
         args, eng = self.args, self.engine
         L.require_device(match_left)
         assert args.corr_levels == 2, "IGEV configs use a 2-level geometry pyramid (configs/igev_stereo/base.json)"
@@ -265,6 +268,16 @@ class IGEVStereo(nn.Module):
             eng.load_state(net_list, ctx_list)   # else: EncoderEngine.run already filled X[i][:, :128] and CTX[i]
         eng.DELTA["f32"].zero_()
         eng.FLOW["f32"].copy_(init_disp.permute(0, 2, 3, 1))
+        if all_preds:
+            preds = []
+            for _ in range(iters):
+                eng.step(self._lookup, with_mask=False)
+                dsp = eng.FLOW["f32"].view(B, h, w)
+                ops.corr1d_lookup([], dsp, args.corr_radius, None, delta=eng.DELTA["f32"])      # disp += delta_disp
+                eng.DELTA["f32"].zero_()          # applied: the next iteration's lookup must not add it again
+                eng.mask_head()
+                preds.append(self.upsample_disp(dsp, eng.MH["f32"][..., :32].permute(0, 3, 1, 2), stem_2x).clone())
+            return preds
         gkey = (iters,)
         if self.use_cuda_graph and gkey in self._graphs:
             self._graphs[gkey].replay()
@@ -287,14 +300,27 @@ class IGEVStereo(nn.Module):
 
     def forward(self, image1, image2, iters=12, flow_init=None, test_mode=False):
         """Estimate disparity between a stereo pair; returns (None, -disparity) like the reference."""
-        if not test_mode:
+        if not test_mode and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
-                "the B200 engine serves inference (test_mode=True); train with the reference graph and "
-                "load the resulting checkpoint here")
+                "test_mode=False with trainable parameters asks for the autograd graph: train with the reference graph and "
+                "load the checkpoint here (under torch.no_grad() this call returns every iteration's prediction)")
         if not image1.is_cuda:
             raise L.DktError("IGEVStereo (B200 engine) needs CUDA inputs; there is no CPU fallback")
         with torch.no_grad():
             pre = self.prepare(image1, image2)
+            if not test_mode:
+                # reference igev_stereo.py:178-189,222-226: {'init_disp': ..., 'disp_preds': [...]}, no autograd graph
+                if self.encoder is not None:
+                    if self.encoder.pack_weights():
+                        self._graphs.clear()
+                        self._seen.clear()
+                    self.encoder.run(image1)
+                init_disp, stem_2x = pre[3], pre[6]
+                xspx = self.spx_4(self._feat4)
+                spx_pred = F.softmax(self.spx(self.spx_2(xspx, stem_2x)), 1)
+                init_up = -ops.context_upsample(init_disp.squeeze(1).contiguous(), spx_pred.float().contiguous(),
+                                                in_scale=4.0, out_scale=1.0)
+                return {"init_disp": init_up, "disp_preds": self.hot_path(*pre, iters, all_preds=True)}
             if self.encoder is not None:
                 if self.encoder.pack_weights():
                     self._graphs.clear()

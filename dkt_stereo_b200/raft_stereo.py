@@ -170,7 +170,7 @@ class RAFTStereo(nn.Module):
             self._graphs.clear()
             self._seen.clear()
 
-    def _loop_and_upsample(self, B, h, w, iters, flow_init):
+    def _loop_and_upsample(self, B, h, w, iters, flow_init, all_preds: bool = False):
         args, eng = self.args, self.engine
         dev = eng.device
         # loop state: coords0 = pixel grid; coords1 = coords0 (+ flow_init); flow = coords1 - coords0
@@ -182,6 +182,16 @@ class RAFTStereo(nn.Module):
             eng.FLOW["f32"][..., 1].copy_(flow_init[:, 1].float())
         else:
             eng.coords_x.copy_(xs)
+        if all_preds:
+            # test_mode=False (reference raft_stereo.py:170-187): the mask head and the convex upsampling run after EVERY
+            # iteration and every prediction is returned; launched eagerly (a training-time validation path, no graph)
+            preds = []
+            for _ in range(iters):
+                eng.step(self._lookup, with_mask=True)
+                ops.corr1d_lookup([], eng.coords_x, args.corr_radius, None, delta=eng.DELTA["f32"], flow=eng.FLOW["f32"])
+                eng.DELTA["f32"].zero_()          # applied: the next iteration's lookup must not add it again
+                preds.append(ops.convex_upsample(eng.FLOW["f32"], eng.MASK["f32"], 2 ** args.n_downsample))
+            return preds
         gkey = (iters,)
         if self._capturing:                      # inside the whole-forward capture: the loop joins that graph
             self._run_loop(iters)
@@ -204,7 +214,7 @@ class RAFTStereo(nn.Module):
         flow_lr = eng.FLOW["f32"].permute(0, 3, 1, 2).contiguous()
         return flow_lr, flow_up
 
-    def _forward_native_eager(self, image1, image2, iters: int, flow_init=None):
+    def _forward_native_eager(self, image1, image2, iters: int, flow_init=None, all_preds: bool = False):
         args, enc = self.args, self.encoder
         B = image1.shape[0]
         enc.run(image1, image2)
@@ -213,7 +223,7 @@ class RAFTStereo(nn.Module):
         self._ensure_volume(B, D, h, w, image1.device)
         f = enc.FMAP
         ops.corr1d_build_split(f.hi[:B], f.lo[:B], f.hi[B:], f.lo[B:], args.corr_levels, 1.0 / (D ** 0.5), self._pyr)
-        return self._loop_and_upsample(B, h, w, iters, flow_init)
+        return self._loop_and_upsample(B, h, w, iters, flow_init, all_preds)
 
     def forward_native(self, image1, image2, iters: int, flow_init=None):
         """Whole forward on libdkt kernels: encoders (EncoderEngine) -> K1 from the bf16 (hi, lo) feature maps
@@ -258,12 +268,31 @@ class RAFTStereo(nn.Module):
 
     def forward(self, image1, image2, iters=12, flow_init=None, test_mode=False):
         """Estimate disparity (returned as negative flow, like the reference) between a stereo pair."""
-        if not test_mode:
+        # test_mode=False, reference raft_stereo.py:185-187: {'disp_preds': [one full-resolution prediction per iteration]}.
+        # The engine computes them without an autograd graph: fine for validation / pseudo-labelling under
+        # torch.no_grad() or with frozen parameters, refused where a backward pass would silently get no gradients.
+        if not test_mode and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
-                "the B200 engine serves inference (test_mode=True); train with the reference graph and "
-                "load the resulting checkpoint here")
+                "test_mode=False with trainable parameters asks for the autograd graph: train with the reference "
+                "graph and load the checkpoint here (under torch.no_grad() this call returns every iteration's prediction)")
         if not image1.is_cuda:
             raise L.DktError("RAFTStereo (B200 engine) needs CUDA inputs; there is no CPU fallback")
+        if not test_mode:
+            with torch.no_grad():
+                if self.encoder is not None:
+                    if self.encoder.pack_weights():
+                        self._graphs.clear(); self._seen.clear(); self._full.clear(); self._full_seen.clear()
+                    return {"disp_preds": self._forward_native_eager(image1, image2, iters, flow_init, all_preds=True)}
+                fmap1, fmap2, net_list, ctx_list = self.extract(image1, image2)
+                args, eng = self.args, self.engine
+                B, D, h, w = fmap1.shape
+                if eng.pack_weights():
+                    self._graphs.clear(); self._seen.clear()
+                eng.allocate(B, h, w, fmap1.device)
+                self._ensure_volume(B, D, h, w, fmap1.device)
+                ops.corr1d_build(fmap1, fmap2, args.corr_levels, 1.0 / (D ** 0.5), impl=self.impl, pyr=self._pyr)
+                eng.load_state(net_list, ctx_list)
+                return {"disp_preds": self._loop_and_upsample(B, h, w, iters, flow_init, all_preds=True)}
         with torch.no_grad():
             if self.encoder is not None:
                 return self.forward_native(image1, image2, iters, flow_init)

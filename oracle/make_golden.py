@@ -248,6 +248,34 @@ def golden_igev_forward_full(m, height, width, iters, tag, batch=1, mode="noise"
          mode=np.array(mode), keys=np.array(keys), key_shapes=np.array([json.dumps(list(sd[k].shape)) for k in keys]))
 
 
+def golden_all_predictions(m, height=64, width=96, iters=3):
+    """forward(test_mode=False) of both reference models under no_grad: every iteration's full-resolution prediction
+    (raft_stereo.py:170-187) and, for IGEV, the upsampled initial disparity as well (igev_stereo.py:178-183,222-226)."""
+    from dkt_stereo_b200.synthetic import synthetic_state_dict, shapes_of, synthetic_pair
+    im1, im2 = synthetic_pair(1, height, width, seed=1234, mode="noise")
+    model = m["raft"].RAFTStereo(_ns(raft_cfg())).eval()
+    sd = synthetic_state_dict(shapes_of(model.state_dict()), seed=0)
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        res = model(im1, im2, iters=iters)
+    keys = sorted(sd.keys())
+    save("raft_all_preds", disp_preds=torch.stack(res["disp_preds"]), meta=np.array([1, height, width, iters]),
+         seeds=np.array([0, 1234]), mode=np.array("noise"), keys=np.array(keys),
+         key_shapes=np.array([json.dumps(list(sd[k].shape)) for k in keys]))
+    _timm_stub()
+    igev = importlib.import_module("meta_arch.igev_stereo.igev_stereo")
+    torch.manual_seed(0)
+    model = igev.IGEVStereo(_ns(igev_cfg())).eval()
+    sd = synthetic_state_dict(shapes_of(model.state_dict()), seed=0)
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        res = model(im1, im2, iters=iters)
+    keys = sorted(sd.keys())
+    save("igev_all_preds", disp_preds=torch.stack(res["disp_preds"]), init_disp=res["init_disp"],
+         meta=np.array([1, height, width, iters]), seeds=np.array([0, 1234]), mode=np.array("noise"), keys=np.array(keys),
+         key_shapes=np.array([json.dumps(list(sd[k].shape)) for k in keys]))
+
+
 def golden_igev_volume(m, B=1, C=96, H=9, W=37, D=20, tag="igev_volume"):
     """The volume stage of the IGEV pre-loop through the REAL reference modules: build_gwc_volume,
     corr_stem (BasicConv 3-D, eval-mode BatchNorm with non-trivial running statistics), FeatureAtt, the classifier
@@ -334,6 +362,7 @@ def main():
         "raft_gru1": lambda: golden_raft_forward(m, 64, 96, 4, "raft_fwd_gru1", 1, "noise", n_gru_layers=1),
         "raft_gru2": lambda: golden_raft_forward(m, 64, 96, 4, "raft_fwd_gru2", 1, "noise", n_gru_layers=2, slow_fast_gru=True),
         "igev_gru2": lambda: golden_igev_forward(m, 64, 96, 4, "igev_fwd_gru2", 1, n_gru_layers=2),
+        "all_preds": lambda: golden_all_predictions(m),
         "igev_small": lambda: golden_igev_forward(m),
         "igev_mid": lambda: golden_igev_forward(m, 96, 160, 8, "igev_fwd_mid", 1),
         "igev_volume": lambda: golden_igev_volume(m),

@@ -613,6 +613,36 @@ def test_igev_forward_golden(tag, impl, monkeypatch):
 
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_forward_all_predictions(impl, monkeypatch):
+    """forward(test_mode=False) -- the reference's DEFAULT call (raft_stereo.py:85,185-187; igev_stereo.py:151,222-226):
+    {'disp_preds': [prediction after every iteration]} (+ 'init_disp' for IGEV) against the real reference run under
+    no_grad; with trainable parameters and autograd on, the engine refuses instead of returning graph-less tensors."""
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    g = load_golden("raft_all_preds")
+    B, H, W, iters = [int(v) for v in g["meta"]]
+    im1, im2 = synthetic_pair(B, H, W, seed=golden_seeds(g)[1], mode=str(g["mode"]))
+    model = _model(impl, g)
+    with pytest.raises(NotImplementedError):
+        model(im1.to(dev()), im2.to(dev()), iters=iters)
+    with torch.no_grad():
+        res = model(im1.to(dev()), im2.to(dev()), iters=iters)
+    assert len(res["disp_preds"]) == iters
+    for i, p in enumerate(res["disp_preds"]):
+        assert p.shape == (B, 1, H, W) and stats(p.cpu(), g["disp_preds"][i])[0] <= 1e-3, (i, stats(p.cpu(), g["disp_preds"][i]))
+    _, up = model(im1.to(dev()), im2.to(dev()), iters=iters, test_mode=True)            # and test mode still agrees
+    assert stats(up.cpu(), g["disp_preds"][-1])[0] <= 1e-3
+    g = load_golden("igev_all_preds")
+    model = _igev_model_from_golden(g, impl, monkeypatch)
+    for p_ in model.parameters():
+        p_.requires_grad = False                                   # a frozen teacher may call it with autograd on
+    res = model(im1.to(dev()), im2.to(dev()), iters=iters)
+    assert stats(res["init_disp"].cpu(), g["init_disp"])[0] <= 1e-3, stats(res["init_disp"].cpu(), g["init_disp"])
+    assert len(res["disp_preds"]) == iters
+    for i, p in enumerate(res["disp_preds"]):
+        assert p.shape == (B, 1, H, W) and stats(p.cpu(), g["disp_preds"][i])[0] <= 1e-3, (i, stats(p.cpu(), g["disp_preds"][i]))
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
 def test_slow_fast_gru(impl, monkeypatch):
     """args.slow_fast_gru=True (reference raft_stereo.py:157-160, igev_stereo.py:201-204): per iteration one extra update
     of the coarsest GRU and one of the two coarse GRUs; against the real reference's outputs with that flag."""
