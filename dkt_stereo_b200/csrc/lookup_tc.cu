@@ -52,8 +52,6 @@ struct LookupTcParams {
     int C;                           // K slots in use: row samples per pixel * LT_TS
     int flags;                       // bit 0: RAFT gather through aligned 16-byte windows (else one thread per row sample);
                                      // bit 1: 16-bit output planes through the staging tile (else per-thread stores)
-                                     // bit 2: batched gather (RAFT: both samples of a thread in flight; IGEV: 16-byte loads)
-                                     // bit 3: cooperative gather (the lanes of one load instruction cover a whole run)
 };
 
 // byte offset of element (row m, column k) inside one plane [KB][rows][128 B] of a K-major SWIZZLE_128B tile whose
@@ -155,77 +153,7 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
         __syncthreads();
         uint8_t* a_buf = a_ring + (uint32_t)buf * A_BUF;
         if (!GEO) {
-            if (prm.flags & 8) {
-                // RAFT, cooperative gather: TEN LANES read the ten floats of a row sample with one load instruction, three
-                // samples per warp pass.  Why (tools/dram_random_probe.cu, profiles/r2w_dram_random_probe.txt): a gather is
-                // bound by the number of L1 -> L2 REQUESTS, ~50 G/s on the whole chip whether a request carries one
-                // 32-byte sector or a whole line; a thread walking its own run issues one request per sector it touches
-                // (2.1 per run), the ten lanes of one instruction one per LINE (1.3 per run).  The interpolation pairs come
-                // from the neighbour lane by shuffle; even lanes store two packed 16-bit taps.
-                constexpr int U = 6;                                    // passes whose loads are in flight together
-                constexpr int RUNS_W = LT_M * DKT_MAX_LEVELS / 8;        // 64 runs per warp
-                constexpr int PASSES = (RUNS_W + 2) / 3;
-                const int sub = lane / 10, k = lane - sub * 10;        // lanes 30, 31: sub == 3, idle
-                for (int ps0 = 0; ps0 < PASSES; ps0 += U) {
-                    float v[U], a[U];
-#pragma unroll
-                    for (int g = 0; g < U; ++g) {
-                        const int rr = (ps0 + g) * 3 + sub;
-                        const int u = warp * RUNS_W + rr, px = u >> 2, l = u & 3;
-                        v[g] = 0.f;
-                        a[g] = 0.f;
-                        if (sub < 3 && rr < RUNS_W && ps0 + g < PASSES && px < npix && l < prm.levels) {
-                            const int Wl = prm.vw[l];
-                            const float x = s_x[px] * (1.f / (float)(1 << l)), xf = floorf(x);
-                            a[g] = x - xf;
-                            const int idx = (int)xf - R + k;
-                            if (idx >= 0 && idx < Wl) v[g] = __ldg(prm.vol[l] + (p0 + px) * Wl + idx);
-                        }
-                    }
-#pragma unroll
-                    for (int g = 0; g < U; ++g) {
-                        const int rr = (ps0 + g) * 3 + sub;
-                        const int u = warp * RUNS_W + rr, px = u >> 2, l = u & 3;
-                        const float v1 = __shfl_down_sync(0xffffffffu, v[g], 1);
-                        const float t = (k < 2 * R + 1) ? (1.f - a[g]) * v[g] + a[g] * v1 : 0.f;
-                        const float t1 = __shfl_down_sync(0xffffffffu, t, 1);
-                        if (sub < 3 && rr < RUNS_W && ps0 + g < PASSES && px < npix && l < prm.levels && !(k & 1)) {
-                            uint8_t* row = a_buf + (uint32_t)(px >> 3) * 1024u + (uint32_t)(px & 7) * 128u;
-                            const int kk = l * LT_TS + k;
-                            const uint32_t off = (((uint32_t)(kk >> 6) * LT_A_KB_BYTES) + (uint32_t)(kk & 63) * 2u) ^ ((uint32_t)(px & 7) << 4);
-                            if (AP == 2) {
-                                uint32_t hi, lo;
-                                split16x2(t, t1, hi, lo);
-                                *reinterpret_cast<uint32_t*>(row + off) = hi;
-                                *reinterpret_cast<uint32_t*>(row + A_PLANE + off) = lo;
-                            } else {
-                                *reinterpret_cast<uint32_t*>(row + off) = pack_hi16x2(t, t1);
-                            }
-                        }
-                    }
-                }
-            } else if (prm.flags & 4) {
-                // RAFT: unit = (pixel, level); 4 lanes per pixel; the loads of BOTH of a thread's samples (128 pixels x 4
-                // levels = 2 x 256 threads) are in flight before either is interpolated (the kernel is bound by the
-                // latency of these loads: ncu r2t, long-scoreboard stalls 9 of 13 warp-cycles per issue)
-                float v[2][2 * R + 3], a[2];
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int u = tid + g * LT_THREADS;
-                    const int px = u >> 2, l = u & 3;
-                    if (px < npix && l < prm.levels)
-                        sample_row_load<R>(prm.vol[l] + (p0 + px) * prm.vw[l], prm.vw[l], s_x[px] * (1.f / (float)(1 << l)), v[g], a[g]);
-                }
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int u = tid + g * LT_THREADS;
-                    const int px = u >> 2, l = u & 3;
-                    if (px < npix && l < prm.levels) {
-                        v[g][2 * R + 2] = 0.f;
-                        put_taps<AP>(a_buf, A_PLANE, px, l * LT_TS, v[g], a[g]);
-                    }
-                }
-            } else if (!(prm.flags & 1)) {
+            if (!(prm.flags & 1)) {
                 // RAFT: unit = (pixel, level); 4 lanes per pixel; a thread issues its 10 loads back to back
                 for (int u = tid; u < npix * DKT_MAX_LEVELS; u += LT_THREADS) {
                     const int px = u >> 2, l = u & 3;
@@ -295,137 +223,6 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
             // Output channel order of the reference (geometry.py:36-57): per level [geo (c-major, tap-minor), init].
             constexpr int Cg = 8, G1 = Cg + 1, G = 2 * G1;      // host checks prm.Cg == 8 (IGEV's 8 geometry channels)
             constexpr int GU = 3;                 // row samples whose loads a thread has in flight before interpolating
-            if (prm.flags & 8) {
-                // cooperative gather (see the RAFT branch): one warp pass = one (pixel, level): lanes 0..19 fetch the 320-byte
-                // geometry run with ONE 16-byte load each (lane = (sample k, channel half): 3.25 line requests instead of
-                // ten sector requests), lanes 20..29 the ten floats of the init-corr row; neighbours by shuffle.
-                constexpr int U = 4;                                    // passes whose loads are in flight together
-                constexpr int PASSES = LT_M * 2 / 8;                    // 32 (pixel, level) passes per warp
-                const bool is_geo = lane < 20, is_init = lane >= 20 && lane < 30;
-                const int k = is_geo ? (lane >> 1) : lane - 20, hh = lane & 1;
-                for (int ps0 = 0; ps0 < PASSES; ps0 += U) {
-                    float4 q[U];
-                    float a[U];
-#pragma unroll
-                    for (int g = 0; g < U; ++g) {
-                        const int ps = ps0 + g, px = warp * (LT_M / 8) + (ps >> 1), l = ps & 1;
-                        q[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        a[g] = 0.f;
-                        if (px < npix) {
-                            const int64_t p = p0 + px;
-                            const float d = s_x[px], inv = l ? 0.5f : 1.f;
-                            if (is_geo) {
-                                const int Dl = l ? prm.D / 2 : prm.D;
-                                const float x = d * inv, xf = floorf(x);
-                                a[g] = x - xf;
-                                const int i = (int)fminf(fmaxf(xf, -1.0e6f), 1.0e6f) - R + k;
-                                if ((unsigned)i < (unsigned)Dl)
-                                    q[g] = __ldg(reinterpret_cast<const float4*>(prm.geo[l] + (p * Dl + i) * Cg + 4 * hh));
-                            } else if (is_init) {
-                                const int Wl = prm.vw[l];
-                                const float x = (float)(p % prm.W1) * inv - d * inv, xf = floorf(x);
-                                a[g] = x - xf;
-                                const int i = (int)fminf(fmaxf(xf, -1.0e6f), 1.0e6f) - R + k;
-                                if ((unsigned)i < (unsigned)Wl) q[g].x = __ldg(prm.vol[l] + p * Wl + i);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int g = 0; g < U; ++g) {
-                        const int ps = ps0 + g, px = warp * (LT_M / 8) + (ps >> 1), l = ps & 1;
-                        const float b0 = a[g], b1 = 1.f - a[g];
-                        // sample k + 1 of the same channels: two lanes up (geometry) / one lane up (init row)
-                        const float nx2 = __shfl_down_sync(0xffffffffu, q[g].x, 2), nx1 = __shfl_down_sync(0xffffffffu, q[g].x, 1);
-                        const float ny = __shfl_down_sync(0xffffffffu, q[g].y, 2), nz = __shfl_down_sync(0xffffffffu, q[g].z, 2);
-                        const float nw = __shfl_down_sync(0xffffffffu, q[g].w, 2);
-                        const bool tapk = k < 2 * R + 1;                // slot 9 of a sample is the zero pad
-                        float4 t;
-                        t.x = tapk ? b1 * q[g].x + b0 * (is_geo ? nx2 : nx1) : 0.f;
-                        t.y = tapk ? b1 * q[g].y + b0 * ny : 0.f;
-                        t.z = tapk ? b1 * q[g].z + b0 * nz : 0.f;
-                        t.w = tapk ? b1 * q[g].w + b0 * nw : 0.f;
-                        const float ux2 = __shfl_down_sync(0xffffffffu, t.x, 2), ux1 = __shfl_down_sync(0xffffffffu, t.x, 1);
-                        const float uy = __shfl_down_sync(0xffffffffu, t.y, 2), uz = __shfl_down_sync(0xffffffffu, t.z, 2);
-                        const float uw = __shfl_down_sync(0xffffffffu, t.w, 2);
-                        if (px < npix && !(k & 1) && (is_geo || is_init)) {
-                            uint8_t* row = a_buf + (uint32_t)(px >> 3) * 1024u + (uint32_t)(px & 7) * 128u;
-                            const uint32_t sw = (uint32_t)(px & 7) << 4;
-                            auto put = [&](int kk, float t0, float t1) {
-                                const uint32_t off = (((uint32_t)(kk >> 6) * LT_A_KB_BYTES) + (uint32_t)(kk & 63) * 2u) ^ sw;
-                                if (AP == 2) {
-                                    uint32_t hi, lo;
-                                    split16x2(t0, t1, hi, lo);
-                                    *reinterpret_cast<uint32_t*>(row + off) = hi;
-                                    *reinterpret_cast<uint32_t*>(row + A_PLANE + off) = lo;
-                                } else {
-                                    *reinterpret_cast<uint32_t*>(row + off) = pack_hi16x2(t0, t1);
-                                }
-                            };
-                            if (is_geo) {
-                                const int kk = (l * G1 + 4 * hh) * LT_TS + k;
-                                put(kk, t.x, ux2);
-                                put(kk + LT_TS, t.y, uy);
-                                put(kk + 2 * LT_TS, t.z, uz);
-                                put(kk + 3 * LT_TS, t.w, uw);
-                            } else {
-                                put((l * G1 + Cg) * LT_TS + k, t.x, ux1);
-                            }
-                        }
-                    }
-                }
-            } else if (prm.flags & 4) {
-                // vector gather: a geometry unit = (pixel, level, channel half): ten 16-byte loads fetch the 4 channels x 10
-                // disparity samples (the (.., D, 8) layout keeps a sample's 8 channels in 32 contiguous bytes), a quarter of
-                // the load instructions of the scalar form for 4/3 of the bytes in flight; the init-corr row of (pixel,
-                // level) is a third unit of the same thread whose loads overlap the first unit's interpolation.
-                auto geo_load = [&](int u, float4* q, float& a) {
-                    const int px = u >> 2, l = (u >> 1) & 1, hh = u & 1;
-                    const int Dl = l ? prm.D / 2 : prm.D;
-                    const float x = s_x[px] * (l ? 0.5f : 1.f), xf = floorf(x);
-                    a = x - xf;
-                    const int i0 = (int)fminf(fmaxf(xf, -1.0e6f), 1.0e6f) - R;
-                    const float* ptr = prm.geo[l] + ((p0 + px) * Dl + i0) * Cg + 4 * hh;   // only dereferenced inside [0, Dl)
-#pragma unroll
-                    for (int k = 0; k < 2 * R + 2; ++k)
-                        q[k] = ((unsigned)(i0 + k) < (unsigned)Dl) ? __ldg(reinterpret_cast<const float4*>(ptr + k * Cg))
-                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-                };
-                auto geo_put = [&](int u, const float4* q, float a) {
-                    const int px = u >> 2, l = (u >> 1) & 1, hh = u & 1;
-                    float v[2 * R + 3];
-                    v[2 * R + 2] = 0.f;
-                    const int k0 = (l * G1 + 4 * hh) * LT_TS;
-#pragma unroll
-                    for (int k = 0; k < 2 * R + 2; ++k) v[k] = q[k].x;
-                    put_taps<AP>(a_buf, A_PLANE, px, k0, v, a);
-#pragma unroll
-                    for (int k = 0; k < 2 * R + 2; ++k) v[k] = q[k].y;
-                    put_taps<AP>(a_buf, A_PLANE, px, k0 + LT_TS, v, a);
-#pragma unroll
-                    for (int k = 0; k < 2 * R + 2; ++k) v[k] = q[k].z;
-                    put_taps<AP>(a_buf, A_PLANE, px, k0 + 2 * LT_TS, v, a);
-#pragma unroll
-                    for (int k = 0; k < 2 * R + 2; ++k) v[k] = q[k].w;
-                    put_taps<AP>(a_buf, A_PLANE, px, k0 + 3 * LT_TS, v, a);
-                };
-                const int ua = tid, ub = tid + LT_THREADS;              // 128 pixels x 4 = 2 x 256 geometry units
-                float4 q[2 * R + 2];
-                float vi[2 * R + 3], aq, ai = 0.f;
-                const int ipx = tid >> 1, il = tid & 1;                // init-corr unit
-                const bool a_ok = (ua >> 2) < npix, b_ok = (ub >> 2) < npix, i_ok = ipx < npix;
-                if (a_ok) geo_load(ua, q, aq);
-                if (i_ok) {
-                    const int64_t p = p0 + ipx;
-                    const int Wl = prm.vw[il];
-                    const float inv = il ? 0.5f : 1.f;
-                    sample_row_load<R>(prm.vol[il] + p * Wl, Wl, (float)(p % prm.W1) * inv - s_x[ipx] * inv, vi, ai);
-                    vi[2 * R + 2] = 0.f;
-                }
-                if (a_ok) geo_put(ua, q, aq);
-                if (b_ok) geo_load(ub, q, aq);
-                if (i_ok) put_taps<AP>(a_buf, A_PLANE, ipx, (il * G1 + Cg) * LT_TS, vi, ai);
-                if (b_ok) geo_put(ub, q, aq);
-            } else
             for (int u0 = tid; u0 < npix * G; u0 += LT_THREADS * GU) {
                 float v[GU][2 * R + 3], av[GU];
 #pragma unroll
@@ -580,12 +377,12 @@ lookup_tc_kernel(const __grid_constant__ LookupTcParams prm) {
 //                 one bulk copy -- clamped to the samples inside [0, D) / to the array -- into a 4-stage ring.  (One warp
 //                 issues a bulk copy every ~59 clocks through its elect / uniform-register loop: a single producer warp
 //                 was the bottleneck of the first version; eight of them overlap.)
-//   warps 8..15   gather: wait for a stage, read a (pixel, level, channel pair)'s ten samples back from shared memory
+//   warps 8..17   gather: wait for a stage, read a (pixel, level, channel pair)'s ten samples back from shared memory
 //                 (slot stride 88 floats: conflict-free), interpolate, store the taps as 16-bit values into the K-major
 //                 SWIZZLE_128B A tile (put_taps); the init-corr rows come the same way as the aligned 64-byte window
 //                 around their 10 floats.  After 4 sub-chunks one elected thread issues the 12 x 2 tcgen05.mma of the
 //                 chunk into one of TWO TMEM accumulators and the warps go on to the next chunk
-//   warps 16..19  epilogue: accumulator -> bias, ReLU -> fp32 / 16-bit planes through a staging tile -> 128-byte rows
+//   warps 18..21  epilogue: accumulator -> bias, ReLU -> fp32 / 16-bit planes through a staging tile -> 128-byte rows
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int GT_SUB = 32;                       // pixels per ring stage
 constexpr int GT_NST = 4;                        // ring stages
@@ -593,7 +390,7 @@ constexpr int GT_RUN = 88;                       // floats per (pixel, level) sl
 constexpr int GT_WIN = 16;                       // floats per init-corr window (the aligned 64 bytes that hold a 10-float run)
 constexpr uint32_t GT_GEO_BYTES = GT_SUB * 2 * GT_RUN * 4;        // 22528
 constexpr uint32_t GT_STAGE_BYTES = GT_GEO_BYTES + GT_SUB * 2 * GT_WIN * 4;      // + 4096 = 26 x 1024
-constexpr int GT_PROD_WARPS = 8, GT_GATHER_WARPS = 8, GT_EPI_WARPS = 4;
+constexpr int GT_PROD_WARPS = 8, GT_GATHER_WARPS = 10, GT_EPI_WARPS = 4;   // gather: 8 warps of geometry units + 2 of init rows
 constexpr int GT_ISSUE_LANES = LT_M / GT_PROD_WARPS;        // 128 bulk copies per sub-chunk: lanes 0..15 of each producer warp
 constexpr int GT_THREADS = 32 * (GT_PROD_WARPS + GT_GATHER_WARPS + GT_EPI_WARPS);
 constexpr int GT_KB = 3;
@@ -726,7 +523,7 @@ geo_lookup_tma_kernel(const __grid_constant__ LookupTcParams prm) {
         }
     } else if (warp < GT_PROD_WARPS + GT_GATHER_WARPS) {
         // ===== gather warps =====
-        const int ct = tid - 32 * GT_PROD_WARPS;               // 0..255
+        const int ct = tid - 32 * GT_PROD_WARPS;               // 0..319
         const uint32_t idesc = idesc_bf16_m128(LT_N);
         const int ksteps = (prm.C + 15) >> 4;
         int64_t n = 0;
@@ -741,7 +538,7 @@ geo_lookup_tma_kernel(const __grid_constant__ LookupTcParams prm) {
                 mbar_wait(&full[st], ph);
                 const float* stg = reinterpret_cast<const float*>(ring + (size_t)st * GT_STAGE_BYTES);
                 const float* sx = s_xr + st * GT_SUB;
-                {   // geometry unit of this thread: (pixel, level, channel pair): ten 8-byte reads, two tap rows
+                if (ct < 8 * GT_SUB) {   // geometry unit of this thread: (pixel, level, channel pair): ten 8-byte reads, two tap rows
                     const int cp = ct & 3, l = (ct >> 2) & 1, px = ct >> 3;
                     if (px < npix_s) {
                         const int Dl = l ? D1 : D0;
@@ -761,9 +558,9 @@ geo_lookup_tma_kernel(const __grid_constant__ LookupTcParams prm) {
                         put_taps<1>(a_tile, A_PLANE, sb * GT_SUB + px, (l * G1 + 2 * cp + 1) * LT_TS, v1, x - xf);
                     }
                 }
-                // init-corr row of (pixel, level): the 64 threads of the first two gather warps have one each (whole warps)
-                const int ipx = ct >> 1, il = ct & 1;
-                if (ct < 2 * GT_SUB && ipx < npix_s) {
+                // init-corr row of (pixel, level): the 64 threads of the last two gather warps have one each
+                const int ipx = (ct - 8 * GT_SUB) >> 1, il = ct & 1;
+                if (ct >= 8 * GT_SUB && ipx < npix_s) {
                     const int64_t p = pb + ipx;
                     const int Wl = prm.vw[il];
                     const float inv = il ? 0.5f : 1.f;
@@ -781,7 +578,7 @@ geo_lookup_tma_kernel(const __grid_constant__ LookupTcParams prm) {
                 if (lane == 0) mbar_arrive(&empty[st]);
             }
             fence_proxy_async();                               // tap stores -> visible to the tensor core's proxy
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * GT_GATHER_WARPS) : "memory");
             if (warp == GT_PROD_WARPS) {
                 const uint32_t acc = (uint32_t)ci & 1u;
                 if (ci >= 2) mbar_wait(&acc_empty[acc], (uint32_t)((ci >> 1) - 1) & 1u);
