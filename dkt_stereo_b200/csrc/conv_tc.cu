@@ -1475,7 +1475,8 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
         const int items = (int)((tiles + 1) / 2);
         // as few CTA pairs as finish in the same number of rounds (255 items: 64 pairs x 4 rounds, not 74 x 3.45): the
         // SMs left free run the other stream's kernels (the coarse GRUs and the motion encoder overlap, update.py)
-        const int max_pairs = s_sms / 2;
+        static const int s_max_pairs = [] { const char* v = getenv("DKT_CONV_MAX_PAIRS"); return v ? atoi(v) : 0; }();   // A/B knob
+        const int max_pairs = (s_max_pairs > 0 && s_max_pairs < s_sms / 2) ? s_max_pairs : s_sms / 2;
         const int rounds = (items + max_pairs - 1) / max_pairs;
         const int pairs = (items + rounds - 1) / rounds;
         const size_t smem_bytes = (size_t)p_a_stages * AP * a_part_bytes + (size_t)p_w_stages * p_w_stage_bytes + TC2_EPI_BYTES + 1024 + TC_BAR_BYTES;
