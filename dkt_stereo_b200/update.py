@@ -196,7 +196,12 @@ class UpdateEngine:
             w["mask0"] = ops.pack_conv(b.mask_feat_4[0].weight, b.mask_feat_4[0].bias, tc=tc)
         else:
             w["mask0"] = ops.pack_conv(b.mask[0].weight, b.mask[0].bias, tc=tc)
-            w["mask2"] = ops.pack_conv(b.mask[2].weight, b.mask[2].bias, tc=tc)
+            # 9 * factor^2 output channels: 144 at n_downsample = 2, 576 at 3 -- more than one conv launch holds (N <= 256)
+            m2 = b.mask[2]
+            self.mask2_chunks = [(c0, min(c0 + 192, m2.out_channels)) for c0 in range(0, m2.out_channels, 192)] \
+                if m2.out_channels > 256 else [(0, m2.out_channels)]
+            for j, (c0, c1) in enumerate(self.mask2_chunks):
+                w[f"mask2.{j}"] = ops.pack_conv(m2.weight[c0:c1], m2.bias[c0:c1], tc=tc)
         self.weights, self._wsig = w, sig
         return True
 
@@ -411,6 +416,7 @@ class UpdateEngine:
         else:
             ops.conv2d([S(self.X[0], 0, 128, simt, split)], Wt["mask0"],
                        E(L.EPI_LINEAR, S(self.MH, 0, 256, True, split), act=L.ACT_RELU, bias=Wt["mask0"].bias), B, h0, w0, impl)
-            ops.conv2d([S(self.MH, 0, 256, simt, split)], Wt["mask2"],
-                       E(L.EPI_LINEAR, S(self.MASK, 0, self.MASK["C"], True, False), scale=0.25, bias=Wt["mask2"].bias),
-                       B, h0, w0, impl)
+            for j, (c0, c1) in enumerate(self.mask2_chunks):
+                wj = Wt[f"mask2.{j}"]
+                ops.conv2d([S(self.MH, 0, 256, simt, split)], wj,
+                           E(L.EPI_LINEAR, S(self.MASK, c0, c1 - c0, True, False), scale=0.25, bias=wj.bias), B, h0, w0, impl)

@@ -362,6 +362,9 @@ def main():
         "raft_gru1": lambda: golden_raft_forward(m, 64, 96, 4, "raft_fwd_gru1", 1, "noise", n_gru_layers=1),
         "raft_gru2": lambda: golden_raft_forward(m, 64, 96, 4, "raft_fwd_gru2", 1, "noise", n_gru_layers=2, slow_fast_gru=True),
         "igev_gru2": lambda: golden_igev_forward(m, 64, 96, 4, "igev_fwd_gru2", 1, n_gru_layers=2),
+        # the upstream "real-time" RAFT-Stereo settings: shared backbone, 1/8 resolution, two GRU levels, slow-fast schedule
+        "raft_realtime": lambda: golden_raft_forward(m, 128, 192, 5, "raft_fwd_realtime", 1, "noise", shared_backbone=True,
+                                                     n_downsample=3, n_gru_layers=2, slow_fast_gru=True),
         "all_preds": lambda: golden_all_predictions(m),
         "igev_small": lambda: golden_igev_forward(m),
         "igev_mid": lambda: golden_igev_forward(m, 96, 160, 8, "igev_fwd_mid", 1),

@@ -613,6 +613,28 @@ def test_igev_forward_golden(tag, impl, monkeypatch):
 
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_raft_realtime_settings(impl):
+    """The upstream "real-time" RAFT-Stereo settings the reference's switches allow (raft_stereo.py:37-49,96-100): shared
+    backbone, n_downsample = 3 (1/8 resolution, 8x convex upsampling with a 576-channel mask), two GRU levels, slow-fast
+    schedule.  The encoders of these settings run on the PyTorch extractor path; volume, loop and upsampling on the kernels."""
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    g = load_golden("raft_fwd_realtime")
+    B, H, W, iters = [int(v) for v in g["meta"]]
+    over = dict(shared_backbone=True, n_downsample=3, n_gru_layers=2, slow_fast_gru=True)
+    from dkt_stereo_b200.raft_stereo import RAFTStereo
+    from dkt_stereo_b200.synthetic import synthetic_state_dict
+    cfg = dict(RAFT_CFG, corr_implementation="b200_fp32" if impl == "simt" else "b200", **over)
+    model = RAFTStereo(Namespace(mixed_precision=False, **cfg)).eval()
+    model.load_state_dict(synthetic_state_dict(golden_shapes(g), seed=golden_seeds(g)[0]), strict=True)
+    model = model.to(dev())
+    im1, im2 = synthetic_pair(B, H, W, seed=golden_seeds(g)[1], mode=str(g["mode"]))
+    for _ in range(3):                                           # eager, graph capture, graph replay
+        lr, up = model(im1.to(dev()), im2.to(dev()), iters=iters, test_mode=True)
+    assert up.shape == (B, 1, H, W) and lr.shape == (B, 2, H // 8, W // 8)
+    assert stats(up.cpu(), g["flow_up"])[0] <= 1e-3, stats(up.cpu(), g["flow_up"])
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
 def test_forward_all_predictions(impl, monkeypatch):
     """forward(test_mode=False) -- the reference's DEFAULT call (raft_stereo.py:85,185-187; igev_stereo.py:151,222-226):
     {'disp_preds': [prediction after every iteration]} (+ 'init_disp' for IGEV) against the real reference run under
