@@ -212,7 +212,10 @@ int dkt_geo_lookup_enc(const float* geo0, const float* geo1, const float* init0,
                        float* disp, const float* delta, int delta_C, int radius, int C, int D,
                        const float* enc_w, const float* enc_b, const dkt_tensor* enc_out,
                        int B, int H, int W, void* stream);
-/* Tensor-core form of dkt_geo_lookup_enc (see dkt_corr1d_lookup_enc_tc); geo0 / geo1 in the dkt_geo_pool_dc layout. */
+/* Tensor-core form of dkt_geo_lookup_enc (see dkt_corr1d_lookup_enc_tc); geo0 / geo1 in the dkt_geo_pool_dc layout.
+ * With tap_planes == 1 and 16-byte aligned volumes whose lengths are multiples of 4 floats (always true for the model's
+ * buffers) the geometry runs and the init-corr windows are fetched by the TMA unit (cp.async.bulk into a shared-memory
+ * ring, csrc/lookup_tc.cu geo_lookup_tma_kernel); otherwise, or with DKT_LOOKUP_TMA=0, by per-thread loads.  Same results. */
 int dkt_geo_lookup_enc_tc(const float* geo0, const float* geo1, const float* init0, const float* init1,
                           float* disp, const float* delta, int delta_C, int radius, int C, int D,
                           const uint16_t* w_img, const float* enc_b, const dkt_tensor* enc_out, int tap_planes,
@@ -261,8 +264,10 @@ int dkt_softargmin(const float* logits, float* disp, int B, int D, int H, int W,
  *          (tensor core; K contiguous, Npad = N rounded up to 16).
  *   dkt_conv2d_simt : exact fp32 CUDA-core implicit GEMM (any Cin / N); reads src.f32.
  *   dkt_conv2d_tc   : tcgen05 implicit GEMM, TMA im2col-free tap loads with zero-filled halos,
- *                     3-term bf16 split; reads src.hi/lo; needs c_begin, c_count % 64 == 0 (or one
- *                     32-channel source: the 7x7 stems' x-im2col rows), ksize in {1,3}, N <= 256.
+ *                     3-term bf16 split; reads src.hi/lo; needs c_begin % 64 == 0 and c_count % 16 == 0 (a source's
+ *                     last 64-channel K block may be partial, e.g. the encoders' 96-channel stages; or one
+ *                     32-channel source: the 7x7 stems' x-im2col rows), ksize in {1,3}, N <= 256 (any multiple of 16
+ *                     is a native UMMA width; other N are zero-padded to the next one).
  *                     Stride-1 convs with >= 2 output tiles run as CTA pairs (tcgen05 cta_group::2). */
 int dkt_conv2d_simt(const dkt_tensor* srcs, int nsrc, const float* weight, int ksize, int N,
                     const dkt_epilogue* epi, int B, int H, int W, void* stream);
