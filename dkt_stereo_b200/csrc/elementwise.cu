@@ -272,9 +272,79 @@ to_nchw_kernel(const float* __restrict__ src, int sC, int sc0, float* __restrict
     }
 }
 
+// ---- depth-padded NDHWC <-> NCDHW (IGEV hourglass layers on the 2-D tensor-core conv: depth planes are its images) ----
+// src (B,C,D,H,W) fp32 -> 16-bit (hi, lo) (B,D+2,H,W,C), interior planes 1..D (planes 0 and D+1 are the conv's zero padding
+// in depth: zeroed once by the caller, never written here); 32x32 smem transpose over (c, x) of one (b, d, y)
+__global__ void __launch_bounds__(256)
+ncdhw_to_ndhwc_pad_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                          int C, int D, int H, int W) {
+    __shared__ float tile[32][33];
+    const int bdy = blockIdx.z;
+    const int y = bdy % H, d = (bdy / H) % D;
+    const int64_t b = bdy / (H * D);
+    const int c0 = blockIdx.y * 32, x0 = blockIdx.x * 32;
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+    for (int i = ty; i < 32; i += 8) {          // rows = c, fast = x
+        const int c = c0 + i, x = x0 + tx;
+        tile[i][tx] = (c < C && x < W) ? __ldg(src + (((b * C + c) * D + d) * H + y) * (int64_t)W + x) : 0.f;
+    }
+    __syncthreads();
+    const dkt_tensor dst{nullptr, hi, lo, C, 0, C};
+    for (int i = ty; i < 32; i += 8) {
+        const int x = x0 + i, c = c0 + tx;
+        if (x < W && c < C) store_all(dst, ((b * (D + 2) + d + 1) * H + y) * (int64_t)W + x, c, tile[tx][i]);
+    }
+}
+
+// src fp32 (B,D+2,H,W,C) interior planes -> dst (B,C,D,H,W) fp32, times sigmoid(att[b,c,y,x]) when att != NULL
+// (FeatureAtt, reference meta_arch/igev_stereo/submodule.py:227-240)
+__global__ void __launch_bounds__(256)
+ndhwc_pad_to_ncdhw_kernel(const float* __restrict__ src, const float* __restrict__ att, float* __restrict__ dst,
+                          int C, int D, int H, int W) {
+    __shared__ float tile[32][33];
+    const int bdy = blockIdx.z;
+    const int y = bdy % H, d = (bdy / H) % D;
+    const int64_t b = bdy / (H * D);
+    const int c0 = blockIdx.y * 32, x0 = blockIdx.x * 32;
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+    for (int i = ty; i < 32; i += 8) {          // rows = x, fast = c
+        const int x = x0 + i, c = c0 + tx;
+        tile[i][tx] = (x < W && c < C) ? __ldg(src + (((b * (D + 2) + d + 1) * H + y) * (int64_t)W + x) * C + c) : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, x = x0 + tx;
+        if (c < C && x < W) {
+            float v = tile[tx][i];
+            if (att) v *= sigmoidf_acc(__ldg(att + ((b * C + c) * H + y) * (int64_t)W + x));
+            dst[(((b * C + c) * D + d) * H + y) * (int64_t)W + x] = v;
+        }
+    }
+}
+
 }  // namespace dkt
 
 using namespace dkt;
+
+extern "C" int dkt_ncdhw_to_ndhwc_pad(const float* src, uint16_t* hi, uint16_t* lo, int B, int C, int D, int H, int W,
+                                      void* stream) {
+    DKT_CHECK_ARG(src && hi && lo);
+    DKT_CHECK_ARG(B > 0 && C > 0 && D > 0 && H > 0 && W > 0);
+    if ((int64_t)B * D * H > 65535) return DKT_E_UNSUPPORTED;
+    dim3 grid(ceil_div(W, 32), ceil_div(C, 32), B * D * H);
+    ncdhw_to_ndhwc_pad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, hi, lo, C, D, H, W);
+    DKT_RETURN_LAST();
+}
+
+extern "C" int dkt_ndhwc_pad_to_ncdhw(const float* src, const float* att, float* dst, int B, int C, int D, int H, int W,
+                                      void* stream) {
+    DKT_CHECK_ARG(src && dst);
+    DKT_CHECK_ARG(B > 0 && C > 0 && D > 0 && H > 0 && W > 0);
+    if ((int64_t)B * D * H > 65535) return DKT_E_UNSUPPORTED;
+    dim3 grid(ceil_div(W, 32), ceil_div(C, 32), B * D * H);
+    ndhwc_pad_to_ncdhw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, att, dst, C, D, H, W);
+    DKT_RETURN_LAST();
+}
 
 static int check_slice(const dkt_tensor* t, bool need_f32) {
     if (!t) return DKT_E_INVALID;

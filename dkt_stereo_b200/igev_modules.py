@@ -132,15 +132,74 @@ class Hourglass(nn.Module):
             sc, sh, sl = fold(m)
             return ops.conv3d_k1(a, b, m.conv.weight, sc, sh, sl)
 
+        # stride-1 3x3x3 layers with 32 / 48 channels on the tensor-core conv kernel (see _k3_tc): 405 -> 256 us and
+        # 165 -> 88 us per layer at cfg3 (tools/hourglass_tc_probe.py, profiles/r3j_hourglass_tc_probe.txt).  The
+        # 16-channel layers stay on the exact-fp32 kernel: a 16-channel source fills a quarter of a 64-channel K block and
+        # N = 16 a sixteenth of the MMA width (1105 us against 628); so do the strided and the 8-channel layers, the
+        # transposed convs and the 1x1x1 convs.
+        tc = self.tc_ok()
+
+        def k3s(m, v, att=None):
+            return self._k3_tc(m, v, att) if (tc and m.conv.in_channels >= 32) else k3(m, v, 1, att)
+
         att = lambda fa, f: fa.feat_att(f).float()
-        c1 = k3(self.conv1[1], k3(self.conv1[0], x, 2), att=att(self.feature_att_8, feats[1]))
-        c2 = k3(self.conv2[1], k3(self.conv2[0], c1, 2), att=att(self.feature_att_16, feats[2]))
-        c3 = k3(self.conv3[1], k3(self.conv3[0], c2, 2), att=att(self.feature_att_32, feats[3]))
-        a = k3(self.agg_0[1], k1(self.agg_0[0], up(self.conv3_up, c3), c2))
-        c2 = k3(self.agg_0[2], a, att=att(self.feature_att_up_16, feats[2]))
-        a = k3(self.agg_1[1], k1(self.agg_1[0], up(self.conv2_up, c2), c1))
-        c1 = k3(self.agg_1[2], a, att=att(self.feature_att_up_8, feats[1]))
+        c1 = k3s(self.conv1[1], k3(self.conv1[0], x, 2), att=att(self.feature_att_8, feats[1]))
+        c2 = k3s(self.conv2[1], k3(self.conv2[0], c1, 2), att=att(self.feature_att_16, feats[2]))
+        c3 = k3s(self.conv3[1], k3(self.conv3[0], c2, 2), att=att(self.feature_att_32, feats[3]))
+        a = k3s(self.agg_0[1], k1(self.agg_0[0], up(self.conv3_up, c3), c2))
+        c2 = k3s(self.agg_0[2], a, att=att(self.feature_att_up_16, feats[2]))
+        a = k3s(self.agg_1[1], k1(self.agg_1[0], up(self.conv2_up, c2), c1))
+        c1 = k3s(self.agg_1[2], a, att=att(self.feature_att_up_8, feats[1]))
         return up(self.conv1_up, c1)
+
+    # ---- 3x3x3 convolutions on tcgen05 ------------------------------------------------------------------------------
+    @staticmethod
+    def tc_ok() -> bool:
+        import os
+        from . import _lib as L
+        return os.environ.get("DKT_HOURGLASS_TC", "1") == "1" and L.split_dtype() == torch.float16
+
+    def _k3_tc(self, m: "ConvNormAct", v: torch.Tensor, att=None) -> torch.Tensor:
+        """A stride-1 3x3x3 BasicConv (eval-mode BatchNorm folded, LeakyReLU; reference submodule.py:10-36) as ONE launch of
+        the 2-D tensor-core conv (csrc/conv_tc.cu): the depth planes of a depth-padded NDHWC copy of the volume are the
+        images of the batch, and the three kz taps are three channel-concatenated SOURCES -- the planes d-1, d, d+1, i.e. the
+        same buffer at three plane offsets.  K = 3 x 9 x CI with 16-bit (hi, lo) operands, 3 MMAs per K step (22 mantissa
+        bits: 1e-6 relative against the exact-fp32 kernel).  The attention product of FeatureAtt (submodule.py:227-240) rides
+        on the layout pass on the way out (dkt_ndhwc_pad_to_ncdhw).  v (B,CI,D,H,W) fp32 -> (B,CO,D,H,W) fp32."""
+        from . import _lib as L, ops
+        B, CI, D, H, W = v.shape
+        CO = m.conv.out_channels
+        cache = self.__dict__.setdefault("_tc_cache", {})
+        wkey = ("w", id(m))
+        sig = tuple((t.data_ptr(), t._version) for t in (m.conv.weight, m.bn.weight, m.bn.bias, m.bn.running_mean, m.bn.running_var))
+        if wkey not in cache or cache[wkey][0] != sig:
+            # (CO, CI, kz, ky, kx) -> 2-D filter (CO, kz*CI + ci, ky, kx): source s of the conv carries the taps kz = s
+            w2 = m.conv.weight.detach().permute(0, 2, 1, 3, 4).reshape(CO, 3 * CI, 3, 3)
+            cache[wkey] = (sig, ops.pack_conv_general(w2, None, bn=(m.bn.weight, m.bn.bias, m.bn.running_mean, m.bn.running_var),
+                                                      bn_eps=m.bn.eps))
+        pack = cache[wkey][1]
+        bkey = ("b", B, CI, CO, D, H, W, str(v.device))
+        if bkey not in cache:
+            dt = L.split_dtype()
+            cache[bkey] = (torch.zeros(B, D + 2, H, W, CI, device=v.device, dtype=dt),      # zero planes at d = -1 and d = D
+                           torch.zeros(B, D + 2, H, W, CI, device=v.device, dtype=dt),
+                           torch.empty(B, D + 2, H, W, CO, device=v.device, dtype=torch.float32))
+        xh, xl, of = cache[bkey]
+        lib = L.load()
+        v = v.contiguous()
+        L.check(lib.dkt_ncdhw_to_ndhwc_pad(v.data_ptr(), xh.data_ptr(), xl.data_ptr(), B, CI, D, H, W, L.stream_ptr()),
+                "ncdhw_to_ndhwc_pad")
+        ni = B * (D + 2) - 2         # images: every plane but the first and the last (inter-sample planes: results unused)
+        fh, fl, fo = xh.view(B * (D + 2), H, W, CI), xl.view(B * (D + 2), H, W, CI), of.view(B * (D + 2), H, W, CO)
+        srcs = [L.tensor_slice(None, fh[sft:sft + ni], fl[sft:sft + ni], 0, CI) for sft in range(3)]
+        epi = ops.make_epilogue(L.EPI_LINEAR, L.tensor_slice(fo[1:1 + ni], None, None, 0, CO),
+                                act=L.ACT_LEAKY if m.act else L.ACT_NONE, bias=pack.bias)
+        ops.conv2d_ex(srcs, pack, epi, ni, H, W)
+        out = torch.empty(B, CO, D, H, W, device=v.device, dtype=torch.float32)
+        att = att.contiguous() if att is not None else None
+        L.check(lib.dkt_ndhwc_pad_to_ncdhw(of.data_ptr(), L.ptr(att), out.data_ptr(), B, CO, D, H, W, L.stream_ptr()),
+                "ndhwc_pad_to_ncdhw")
+        return out
 
     def native_ok(self, x: torch.Tensor) -> bool:
         """Even sizes down the three stride-2 levels (the deconvolutions then return exactly the skip shapes)."""

@@ -659,8 +659,10 @@ def nchw_to_nhwc(src: torch.Tensor, dst: DktTensor, bias: Optional[torch.Tensor]
             "nchw_to_nhwc")
 
 
-def nhwc_to_nchw(src: DktTensor, B: int, H: int, W: int, device) -> torch.Tensor:
-    out = torch.empty(B, src.c_count, H, W, device=device, dtype=torch.float32)
+def nhwc_to_nchw(src: DktTensor, B: int, H: int, W: int, device, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(B, src.c_count, H, W, device=device, dtype=torch.float32)
+    assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == B * src.c_count * H * W
     L.check(L.load().dkt_nhwc_to_nchw(C.byref(src), out.data_ptr(), B, src.c_count, H, W, L.stream_ptr()),
             "nhwc_to_nchw")
     return out

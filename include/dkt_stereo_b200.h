@@ -254,6 +254,15 @@ int dkt_conv3d_k1(const float* in0, int C0, const float* in1, int C1, const floa
                   const float* shift, const float* att, float slope, float* out, int B, int CO, int D, int H, int W,
                   void* stream);
 int dkt_softargmin(const float* logits, float* disp, int B, int D, int H, int W, void* stream);
+/* The hourglass's stride-1 3x3x3 layers with 16 / 32 / 48 channels run on the 2-D tensor-core conv (dkt_conv2d_tc_ex):
+ * the depth planes of a depth-padded NDHWC copy of the volume are its images and the three kz taps three channel-
+ * concatenated sources (the same buffer at plane offsets 0, 1, 2).  These two passes are the way in and out:
+ * dkt_ncdhw_to_ndhwc_pad : src (B,C,D,H,W) fp32 -> 16-bit (hi, lo) planes (B,D+2,H,W,C), interior depth planes 1..D; planes
+ *   0 and D+1 of every sample are the zero padding in depth (the caller zeroes them once; never written here).
+ * dkt_ndhwc_pad_to_ncdhw : src fp32 (B,D+2,H,W,C), interior planes -> dst (B,C,D,H,W) fp32, multiplied by
+ *   sigmoid(att[b,c,y,x]) when att != NULL (FeatureAtt, reference submodule.py:227-240).  B*D*H <= 65535. */
+int dkt_ncdhw_to_ndhwc_pad(const float* src, uint16_t* hi, uint16_t* lo, int B, int C, int D, int H, int W, void* stream);
+int dkt_ndhwc_pad_to_ncdhw(const float* src, const float* att, float* dst, int B, int C, int D, int H, int W, void* stream);
 
 /* ---- K3: convolutions of the update block with fused epilogues ------------------------------
  * Replaces nn.Conv2d + bias + activation + the GRU gate algebra of reference core/update.py

@@ -1353,6 +1353,35 @@ def test_igev_hourglass_golden():
     assert stats(out_t.cpu(), g["out"])[1] < 3e-5 * scale
 
 
+@pytest.mark.parametrize("C,shape", [(32, (2, 32, 12, 34, 60)), (48, (1, 48, 6, 17, 30)), (16, (1, 16, 8, 20, 44))])
+def test_hourglass_layer_on_tensor_cores_vs_fp32_kernel(C, shape):
+    """Hourglass._k3_tc -- a stride-1 3x3x3 BasicConv + FeatureAtt as one launch of the 2-D tcgen05 conv over the depth planes
+    of a depth-padded NDHWC copy (dkt_ncdhw_to_ndhwc_pad / dkt_ndhwc_pad_to_ncdhw) -- against the exact-fp32 3-D kernel:
+    ragged tiles, zero padding in depth at both ends of every sample, non-trivial BatchNorm statistics.  Gate 2e-5 of the
+    output range (16-bit (hi, lo) operands, 3 MMAs per K step)."""
+    from dkt_stereo_b200 import ops
+    from dkt_stereo_b200.igev_modules import ConvNormAct, Hourglass
+    torch.manual_seed(C)
+    hg = Hourglass(8).eval().to(dev())
+    m = ConvNormAct(C, C, is_3d=True, kernel_size=3, padding=1, stride=1).eval().to(dev())
+    with torch.no_grad():
+        m.bn.running_mean.normal_(0, 0.3); m.bn.running_var.uniform_(0.5, 2.0); m.bn.weight.uniform_(0.5, 1.5); m.bn.bias.normal_(0, 0.2)
+    v = torch.randn(*shape, device=dev())
+    att = torch.randn(shape[0], C, shape[3], shape[4], device=dev())
+    scale = (m.bn.weight / torch.sqrt(m.bn.running_var + m.bn.eps)).detach()
+    shift = (m.bn.bias - m.bn.running_mean * scale).detach()
+    with torch.no_grad():
+        ref = ops.conv3d_k3(v, m.conv.weight, scale, shift, 0.01, att, 1)
+        for _ in range(2):                                          # second call: cached packs / buffers
+            out = hg._k3_tc(m, v, att)
+        from dkt_stereo_b200.raft_stereo import _fp32_math
+        with _fp32_math(True):                                      # cuDNN would run the module in TF32 otherwise
+            ref_t = torch.sigmoid(att).unsqueeze(2) * m(v)
+    rng = float(ref.abs().max())
+    assert out.shape == ref.shape and stats(out.cpu(), ref.cpu())[1] < 2e-5 * rng, stats(out.cpu(), ref.cpu())
+    assert stats(out.cpu(), ref_t.cpu())[1] < 5e-5 * rng
+
+
 # ---------------------------------------------------------------------------------------------
 # a8: pool2x / interp between the GRU scales (reference core/update.py:87-95), called directly
 # ---------------------------------------------------------------------------------------------
