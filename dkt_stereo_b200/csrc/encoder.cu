@@ -188,7 +188,11 @@ instnorm_apply_kernel(const float* __restrict__ x, int xC, int xc0, const float*
     const float4 st0 = __ldg(reinterpret_cast<const float4*>(stats + ((int64_t)b * C + c) * 2));       // m0 r0 m1 r1
     const float4 st1 = __ldg(reinterpret_cast<const float4*>(stats + ((int64_t)b * C + c) * 2 + 4));   // m2 r2 m3 r3
     float4 y = make_float4((v.x - st0.x) * st0.y, (v.y - st0.z) * st0.w, (v.z - st1.x) * st1.y, (v.w - st1.z) * st1.w);
-    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+    if (relu == 1) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+    else if (relu == 2) {                      // LeakyReLU(0.01): BasicConv_IN of the IGEV feature side
+        y.x = y.x > 0.f ? y.x : 0.01f * y.x; y.y = y.y > 0.f ? y.y : 0.01f * y.y;
+        y.z = y.z > 0.f ? y.z : 0.01f * y.z; y.w = y.w > 0.f ? y.w : 0.01f * y.w;
+    }
     if (res || res_hi) {
         const float4 r = res ? *reinterpret_cast<const float4*>(res + p * res_C + res_c0 + c)
                              : load_split4(res_hi, res_lo, p * res_C + res_c0 + c);

@@ -566,9 +566,11 @@ def instnorm_finalize_tiles(partial: torch.Tensor, workspace: torch.Tensor, stat
 
 
 def instnorm_apply(x: DktTensor, stats: torch.Tensor, out: DktTensor, B: int, H: int, W: int,
-                   relu: bool = True, res: Optional[DktTensor] = None) -> None:
+                   relu=True, res: Optional[DktTensor] = None) -> None:
+    """``relu``: False / True, or "leaky" for LeakyReLU(0.01)."""
+    act = 2 if relu == "leaky" else int(bool(relu))
     L.check(L.load().dkt_instnorm_apply(C.byref(x), stats.data_ptr(), C.byref(res) if res is not None else None,
-                                        C.byref(out), int(relu), B, H, W, L.stream_ptr()), "instnorm_apply")
+                                        C.byref(out), act, B, H, W, L.stream_ptr()), "instnorm_apply")
 
 
 def conv2d(srcs: Sequence[DktTensor], w: ConvWeights, epi: DktEpilogue, B: int, H: int, W: int,

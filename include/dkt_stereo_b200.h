@@ -337,7 +337,8 @@ int dkt_split_nchw_to_nhwc_bf16x2(const float* src, int64_t sb, int64_t sd, int6
  *   The motion encoder's 7x7 flow stem (core/update.py:73,81) uses the same pair on the NHWC flow field.
  * dkt_instnorm_stats   : nn.InstanceNorm2d statistics (biased variance) of an NHWC fp32 slice ->
  *   stats (B,C,2) = (mean, 1/sqrt(var+eps)); workspace >= dkt_instnorm_workspace_floats(B,C) floats.
- * dkt_instnorm_apply   : out = (x - mean)*rstd, then ReLU if relu != 0, then relu(res + out) if res != NULL
+ * dkt_instnorm_apply   : out = (x - mean)*rstd, then ReLU if relu == 1 / LeakyReLU(0.01) if relu == 2 (BasicConv_IN, igev
+ *   submodule.py:80-106), then relu(res + out) if res != NULL
  *   (the ResidualBlock tail, core/extractor.py:56-60; res is read as fp32 if res->f32 != NULL, else as hi + lo);
  *   writes every non-null precision of `out`. */
 int dkt_stem_rows_bf16x2(const float* img, int64_t sb, int64_t sc, int64_t sy, int64_t sx,

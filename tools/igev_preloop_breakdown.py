@@ -30,7 +30,10 @@ def run():
         fl, fr = m.feature(i1), m.feature(i2); mark("feature(MobileNetV2) x2")
         s2 = m.stem_2(i1); s4 = m.stem_4(s2); s4y = m.stem_4(m.stem_2(i2)); mark("stems")
         fl[0] = torch.cat((fl[0], s4), 1); fr[0] = torch.cat((fr[0], s4y), 1)
-        ml = m.desc(m.conv(fl[0])); mr = m.desc(m.conv(fr[0])); mark("conv+desc")
+        if m.native_match:
+            mt = m._match_native(torch.cat((fl[0], fr[0]), 0)); ml, mr = mt[:8], mt[8:]; mark("conv+desc (dkt kernels)")
+        else:
+            ml = m.desc(m.conv(fl[0])); mr = m.desc(m.conv(fr[0])); mark("conv+desc")
         D = a.max_disp // 4
         if NATIVE:
             g = ops.gwc_volume(ml, mr, D, 8); mark("dkt_gwc_volume")
