@@ -1315,7 +1315,8 @@ extern "C" int dkt_conv2d_tc_ex(const dkt_tensor* srcs, int nsrc, const uint16_t
     for (int s = 0; s < nsrc; ++s) { kb_sum += (srcs[s].c_count + 63) / 64; }
     const int64_t tiles64 = (int64_t)ceil_div(W, TC_TILE_W) * ceil_div(H, TC_TILE_H) * B;
     // K blocks of 32 channels (64-byte rows): a single 32-channel source, i.e. the x-im2col rows of a 7x7 stem
-    const bool k32 = nsrc == 1 && srcs[0].c_count == 32 && (srcs[0].c_begin % 32) == 0;
+    // (any other 32-channel source is the first half of a 64-channel block: klast = 2)
+    const bool k32 = nsrc == 1 && srcs[0].c_count == 32 && (srcs[0].c_begin % 32) == 0 && kw == 1 && stride == 1;
     const int KBLK = k32 ? 32 : 64;
     const uint32_t a_part_bytes = (uint32_t)rows_loaded * TC_TILE_W * (uint32_t)KBLK * 2u;
 

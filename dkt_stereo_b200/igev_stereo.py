@@ -92,6 +92,8 @@ class IGEVStereo(nn.Module):
                              and not getattr(args, "mixed_precision", False))
         self._match_w = None
         self._match_buf = None
+        self._stem_w = None
+        self._stem_buf = None
 
     def freeze_bn(self):
         for m in self.modules():
@@ -121,8 +123,11 @@ class IGEVStereo(nn.Module):
             B = image1.shape[0]
             both = torch.cat((image1, image2), 0)
             feats = self.feature(both)
-            stem_2 = self.stem_2(both)
-            stem_4 = self.stem_4(stem_2)
+            if self.native_match and both.is_cuda and both.dtype == torch.float32:
+                stem_2, stem_4 = self._stems_native(both)
+            else:
+                stem_2 = self.stem_2(both)
+                stem_4 = self.stem_4(stem_2)
             stem_2x = stem_2[:B]
             feats[0] = torch.cat((feats[0], stem_4), 1)
             self._feat4 = feats[0][:B]            # left 1/4 features: input of spx_4 (test_mode=False only, reference :179)
@@ -164,6 +169,49 @@ class IGEVStereo(nn.Module):
                 net_list = [torch.tanh(x[0]).float() for x in cnet_list]
                 ctx_list = [conv(torch.relu(x[1])).float() for x, conv in zip(cnet_list, self.context_zqr_convs)]
         return (match_left.float(), match_right.float(), gev.float(), init_disp.float(), net_list, ctx_list, stem_2x.float())
+
+    def _stems_native(self, both: torch.Tensor):
+        """stem_2 / stem_4 (reference igev_stereo.py:96-107,159-160): the first conv (3 -> 32, stride 2, + InstanceNorm +
+        LeakyReLU) stays on cuDNN (3 input channels); everything after it -- conv 32 -> 32 + IN + ReLU, conv 32 -> 48 stride 2
+        + IN + LeakyReLU, conv 48 -> 48 + IN + ReLU -- runs on the library's kernels in NHWC 16-bit pairs.
+        -> (stem_2 (Bt,32,H/2,W/2), stem_4 (Bt,48,H/4,W/4)) fp32 NCHW."""
+        TS, E = L.tensor_slice, ops.make_epilogue
+        x2 = self.stem_2[0](both)
+        Bt, _, h2, w2 = x2.shape
+        c2b, c4a, c4b = self.stem_2[1], self.stem_4[0].conv, self.stem_4[1]
+        sig = tuple((p.data_ptr(), p._version) for p in (c2b.weight, c4a.weight, c4b.weight))
+        if self._stem_w is None or self._stem_w[0] != sig:
+            self._stem_w = (sig, ops.pack_conv_general(c2b.weight, None), ops.pack_conv_general(c4a.weight, None, stride=2),
+                            ops.pack_conv_general(c4b.weight, None))
+        _, w2b, w4a, w4b = self._stem_w
+        h4, w4 = (h2 - 1) // 2 + 1, (w2 - 1) // 2 + 1
+        key = (Bt, h2, w2, str(both.device))
+        if self._stem_buf is None or self._stem_buf[0] != key:
+            dt, dev = L.split_dtype(), both.device
+            z = lambda *sh, d=torch.float32: torch.zeros(*sh, device=dev, dtype=d)       # noqa: E731
+            self._stem_buf = (key, dict(
+                ah=z(Bt, h2, w2, 32, d=dt), al=z(Bt, h2, w2, 32, d=dt), raw2=z(Bt, h2, w2, 32),
+                s2=z(Bt, h2, w2, 32), s2h=z(Bt, h2, w2, 32, d=dt), s2l=z(Bt, h2, w2, 32, d=dt),
+                raw4=z(Bt, h4, w4, 48), th=z(Bt, h4, w4, 48, d=dt), tl=z(Bt, h4, w4, 48, d=dt), raw4b=z(Bt, h4, w4, 48), u=z(Bt, h4, w4, 48),
+                part=z(Bt * ops.conv_tiles(h2, w2) * 2 * 32), tws=ops.instnorm_tiles_workspace(Bt, 32, dev),
+                ws=ops.instnorm_workspace(Bt, 48, dev), st32=z(Bt, 32, 2), st48=z(Bt, 48, 2)))
+        b = self._stem_buf[1]
+        ops.nchw_to_nhwc(x2, TS(None, b["ah"], b["al"], 0, 32))
+        # stem_2: conv 32 -> 32, InstanceNorm (statistics from the conv epilogue), ReLU
+        ops.conv2d_ex([TS(None, b["ah"], b["al"], 0, 32)], w2b, E(L.EPI_LINEAR, TS(b["raw2"], None, None, 0, 32), stats_partial=b["part"]),
+                      Bt, h2, w2)
+        ops.instnorm_finalize_tiles(b["part"], b["tws"], b["st32"], Bt, 32, h2, w2)
+        ops.instnorm_apply(TS(b["raw2"], None, None, 0, 32), b["st32"], TS(b["s2"], b["s2h"], b["s2l"], 0, 32), Bt, h2, w2, relu=True)
+        stem_2 = ops.nhwc_to_nchw(TS(b["s2"], None, None, 0, 32), Bt, h2, w2, both.device)
+        # stem_4: conv 32 -> 48 stride 2, InstanceNorm, LeakyReLU
+        ops.conv2d_ex([TS(None, b["s2h"], b["s2l"], 0, 32)], w4a, E(L.EPI_LINEAR, TS(b["raw4"], None, None, 0, 48)), Bt, h2, w2)
+        ops.instnorm_stats(TS(b["raw4"], None, None, 0, 48), b["ws"], b["st48"], Bt, h4, w4)
+        ops.instnorm_apply(TS(b["raw4"], None, None, 0, 48), b["st48"], TS(None, b["th"], b["tl"], 0, 48), Bt, h4, w4, relu="leaky")
+        #         conv 48 -> 48, InstanceNorm, ReLU
+        ops.conv2d_ex([TS(None, b["th"], b["tl"], 0, 48)], w4b, E(L.EPI_LINEAR, TS(b["raw4b"], None, None, 0, 48)), Bt, h4, w4)
+        ops.instnorm_stats(TS(b["raw4b"], None, None, 0, 48), b["ws"], b["st48"], Bt, h4, w4)
+        ops.instnorm_apply(TS(b["raw4b"], None, None, 0, 48), b["st48"], TS(b["u"], None, None, 0, 48), Bt, h4, w4, relu=True)
+        return stem_2, ops.nhwc_to_nchw(TS(b["u"], None, None, 0, 48), Bt, h4, w4, both.device)
 
     def _match_native(self, x: torch.Tensor) -> torch.Tensor:
         """Matching-feature head ``desc(conv(x))`` (reference igev_stereo.py:127-128,166-167: BasicConv_IN 3x3 96 -> 96 =

@@ -28,7 +28,10 @@ def run():
         i1 = (2 * (im1 / 255.0) - 1.0).contiguous(); i2 = (2 * (im2 / 255.0) - 1.0).contiguous()
         mark("start")
         fl, fr = m.feature(i1), m.feature(i2); mark("feature(MobileNetV2) x2")
-        s2 = m.stem_2(i1); s4 = m.stem_4(s2); s4y = m.stem_4(m.stem_2(i2)); mark("stems")
+        if m.native_match:
+            _, s44 = m._stems_native(torch.cat((i1, i2), 0)); s4, s4y = s44[:8], s44[8:]; mark("stems (dkt kernels after the first conv)")
+        else:
+            s2 = m.stem_2(i1); s4 = m.stem_4(s2); s4y = m.stem_4(m.stem_2(i2)); mark("stems")
         fl[0] = torch.cat((fl[0], s4), 1); fr[0] = torch.cat((fr[0], s4y), 1)
         if m.native_match:
             mt = m._match_native(torch.cat((fl[0], fr[0]), 0)); ml, mr = mt[:8], mt[8:]; mark("conv+desc (dkt kernels)")
