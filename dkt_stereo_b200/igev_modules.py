@@ -296,10 +296,104 @@ class Feature(nn.Module):
         x8 = self.block2(x4)
         x16 = self.block3(x8)
         x32 = self.block4(x16)
+        if self.native_decoder_ok(x4, x8, x16, x32):
+            return self.decode_native(x4, x8, x16, x32)
         x16 = self.deconv32_16(x32, x16)
         x8 = self.deconv16_8(x16, x8)
         x4 = self.conv4(self.deconv8_4(x8, x4))
         return [x4, x8, x16, x32]
+
+    # ---- U-Net decoder (FeatUp, reference meta_arch/igev_stereo/extractor.py:296-325) on the library's kernels ----------
+    def native_decoder_ok(self, x4, x8, x16, x32) -> bool:
+        import os
+        from . import _lib as L
+        if os.environ.get("DKT_NATIVE_FEATUP", "1") != "1" or self.training or not x4.is_cuda or x4.dtype != torch.float32:
+            return False
+        if os.environ.get("DKT_IMPL", "tc") != "tc" or L.split_dtype() != torch.float16:
+            return False
+        return all(tuple(a.shape[-2:]) == (2 * b.shape[-2], 2 * b.shape[-1]) for a, b in ((x4, x8), (x8, x16), (x16, x32)))
+
+    def decode_native(self, x4, x8, x16, x32) -> List[torch.Tensor]:
+        """Three UpFuse steps + conv4: every transposed conv (kernel 4, stride 2, padding 1) is a 3x3 tensor-core conv that
+        produces the four output parities as channel groups (ops.deconv4x4s2_as_conv3x3) + a pixel shuffle; InstanceNorm +
+        LeakyReLU through the library's statistics / apply kernels; ``torch.cat`` never materialises (the skip tensor and the
+        upsampled tensor are written into channel slices of the next conv's source).  NHWC 16-bit pairs in between; the four
+        returned maps are fp32 NCHW like the module's."""
+        from . import _lib as L, ops
+        TS, E = L.tensor_slice, ops.make_epilogue
+        dev, Bt = x4.device, x4.shape[0]
+        steps = (("deconv32_16", x32, x16), ("deconv16_8", None, x8), ("deconv8_4", None, x4))
+        cache = self.__dict__.setdefault("_dec_cache", {})
+        mods = [getattr(self, n) for n, _, _ in steps]
+        sig = tuple((p.data_ptr(), p._version) for m in mods + [self.conv4] for p in m.parameters())
+        if cache.get("sig") != sig:
+            w = {}
+            for (name, _, _), m in zip(steps, mods):
+                w3 = ops.deconv4x4s2_as_conv3x3(m.conv1.conv.weight.detach())          # (4*CO, CI, 3, 3)
+                co4 = w3.shape[0]
+                nl = 2 if co4 > 256 else 1                                             # N <= 256 per launch
+                w[name + ".d"] = [ops.pack_conv_general(w3[i * co4 // nl:(i + 1) * co4 // nl], None) for i in range(nl)]
+                w[name + ".c"] = ops.pack_conv_general(m.conv2.conv.weight.detach(), None)
+            w["conv4"] = ops.pack_conv_general(self.conv4.conv.weight.detach(), None)
+            cache.clear()
+            cache.update(sig=sig, w=w)
+        w = cache["w"]
+        dt = L.split_dtype()
+
+        def buf(key, *shape, d=torch.float32):
+            k = (key,) + shape + (str(dev), d)
+            if k not in cache:
+                cache[k] = torch.zeros(*shape, device=dev, dtype=d)
+            return cache[k]
+
+        def inorm(raw, Cc, h, wd, dst, tag):
+            st = buf("st" + tag, Bt, Cc, 2)
+            ops.instnorm_stats(TS(raw, None, None, 0, Cc), buf("ws" + tag, ops.instnorm_workspace(Bt, Cc, dev).numel()), st, Bt, h, wd)
+            ops.instnorm_apply(TS(raw, None, None, 0, Cc), st, dst, Bt, h, wd, relu="leaky")
+
+        outs = []
+        cur = None                                   # (hi, lo) NHWC of the running coarse map
+        for (name, first, skip), m in zip(steps, mods):
+            CO = m.conv1.conv.out_channels
+            hs, ws_ = skip.shape[-2:]
+            hc, wc = hs // 2, ws_ // 2
+            if cur is None:                          # coarsest input comes from MobileNetV2 as NCHW fp32
+                CI = first.shape[1]
+                cur = (buf(name + "ih", Bt, hc, wc, CI, d=dt), buf(name + "il", Bt, hc, wc, CI, d=dt))
+                ops.nchw_to_nhwc(first, TS(None, cur[0], cur[1], 0, CI))
+            CI = cur[0].shape[-1]
+            # transposed conv as a parity-grouped 3x3 conv, shuffled to the skip's resolution
+            u = buf(name + "u", Bt, hc, wc, 4 * CO)
+            packs = w[name + ".d"]
+            for i, pk in enumerate(packs):
+                n_i = 4 * CO // len(packs)
+                ops.conv2d_ex([TS(None, cur[0], cur[1], 0, CI)], pk, E(L.EPI_LINEAR, TS(u, None, None, i * n_i, n_i)), Bt, hc, wc)
+            up_raw = buf(name + "ur", Bt, hs, ws_, CO)
+            ops.pixel_shuffle2(u, CO, TS(up_raw, None, None, 0, CO), Bt, hc, wc)
+            cat_h, cat_l = buf(name + "ch", Bt, hs, ws_, 2 * CO, d=dt), buf(name + "cl", Bt, hs, ws_, 2 * CO, d=dt)
+            inorm(up_raw, CO, hs, ws_, TS(None, cat_h, cat_l, 0, CO), name + "a")              # cat((x, skip), 1): x first
+            ops.nchw_to_nhwc(skip, TS(None, cat_h, cat_l, CO, CO))
+            # conv2: 3x3 over the concatenation, InstanceNorm, LeakyReLU
+            keep = name != "deconv8_4"               # deconv8_4.conv2 keeps 2*CO channels -> conv4 follows; others are outputs
+            C2 = m.conv2.conv.out_channels
+            raw = buf(name + "r", Bt, hs, ws_, C2)
+            ops.conv2d_ex([TS(None, cat_h, cat_l, 0, 2 * CO)], w[name + ".c"], E(L.EPI_LINEAR, TS(raw, None, None, 0, C2)), Bt, hs, ws_)
+            o_f = buf(name + "of", Bt, hs, ws_, C2) if keep else None
+            o_h, o_l = buf(name + "oh", Bt, hs, ws_, C2, d=dt), buf(name + "ol", Bt, hs, ws_, C2, d=dt)
+            inorm(raw, C2, hs, ws_, TS(o_f, o_h, o_l, 0, C2), name + "b")
+            if keep:
+                outs.append(ops.nhwc_to_nchw(TS(o_f, None, None, 0, C2), Bt, hs, ws_, dev))
+            cur = (o_h, o_l)
+        # conv4 on the 1/4 map
+        C4 = self.conv4.conv.out_channels
+        h4, w4 = x4.shape[-2:]
+        raw = buf("c4r", Bt, h4, w4, C4)
+        ops.conv2d_ex([TS(None, cur[0], cur[1], 0, cur[0].shape[-1])], w["conv4"], E(L.EPI_LINEAR, TS(raw, None, None, 0, C4)), Bt, h4, w4)
+        o4 = buf("c4o", Bt, h4, w4, C4)
+        inorm(raw, C4, h4, w4, TS(o4, None, None, 0, C4), "c4")
+        x4o = ops.nhwc_to_nchw(TS(o4, None, None, 0, C4), Bt, h4, w4, dev)
+        x16o, x8o = outs
+        return [x4o, x8o, x16o, x32]
 
 
 # ---------------------------------------------------------------------------------------------
