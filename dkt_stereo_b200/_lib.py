@@ -77,6 +77,7 @@ SIGNATURES = {
     "dkt_context_upsample_logits": [_P, _P, _I, _P, _F, _F, _I, _I, _I, _P],
     "dkt_nchw_to_nhwc": [_P, _P, _TP, _I, _I, _I, _I, _P],
     "dkt_nhwc_to_nchw": [_TP, _P, _I, _I, _I, _I, _P],
+    "dkt_dwconv3x3": [_TP, _P, _P, _F, _F, _F, _TP, _I, _I, _I, _I, _P],
     "dkt_ncdhw_to_ndhwc_pad": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dkt_ndhwc_pad_to_ncdhw": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dkt_stem_rows_bf16x2": [_P, _I64, _I64, _I64, _I64, _F, _F, _P, _P, _I, _I, _I, _I, _I, _I, _P],

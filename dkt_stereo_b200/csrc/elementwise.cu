@@ -272,6 +272,41 @@ to_nchw_kernel(const float* __restrict__ src, int sC, int sc0, float* __restrict
     }
 }
 
+// ---- depthwise 3x3 convolution, NHWC (MobileNetV2 of the IGEV feature pyramid: timm conv_dw + folded BatchNorm + ReLU6) ----
+// thread = (output pixel, group of 4 channels): nine 16-byte loads (zero outside the image), fp32 FMAs, bias, clamp, every
+// non-null precision of dst written.  in_max clamps the INPUT on load: the expand conv that produced it applied ReLU in its
+// epilogue, min(., 6) completes its ReLU6 here.
+__global__ void __launch_bounds__(256)
+dwconv3x3_kernel(const float* __restrict__ src, int sC, int sc0, const float* __restrict__ w, const float* __restrict__ bias,
+                 float in_max, float out_min, float out_max, dkt_tensor dst, int C4, int Hin, int Win, int H, int W,
+                 int stride, int64_t total) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int g = (int)(t % C4);
+    const int64_t p = t / C4;
+    const int x = (int)(p % W), y = (int)((p / W) % H);
+    const int64_t b = p / ((int64_t)W * H);
+    const int c = g * 4;
+    float4 acc = __ldg(reinterpret_cast<const float4*>(bias + c));
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = y * stride + ky - 1;
+        if (iy < 0 || iy >= Hin) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = x * stride + kx - 1;
+            if (ix < 0 || ix >= Win) continue;
+            float4 v = __ldg(reinterpret_cast<const float4*>(src + ((b * Hin + iy) * (int64_t)Win + ix) * sC + sc0 + c));
+            const float4 k = __ldg(reinterpret_cast<const float4*>(w + (int64_t)(ky * 3 + kx) * C4 * 4 + c));   // [tap][C]
+            v.x = fminf(v.x, in_max); v.y = fminf(v.y, in_max); v.z = fminf(v.z, in_max); v.w = fminf(v.w, in_max);
+            acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y); acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+        }
+    }
+    acc.x = fminf(fmaxf(acc.x, out_min), out_max); acc.y = fminf(fmaxf(acc.y, out_min), out_max);
+    acc.z = fminf(fmaxf(acc.z, out_min), out_max); acc.w = fminf(fmaxf(acc.w, out_min), out_max);
+    store_all4(dst, p, c, acc);
+}
+
 // ---- depth-padded NDHWC <-> NCDHW (IGEV hourglass layers on the 2-D tensor-core conv: depth planes are its images) ----
 // src (B,C,D,H,W) fp32 -> 16-bit (hi, lo) (B,D+2,H,W,C), interior planes 1..D (planes 0 and D+1 are the conv's zero padding
 // in depth: zeroed once by the caller, never written here); 32x32 smem transpose over (c, x) of one (b, d, y)
@@ -325,6 +360,24 @@ ndhwc_pad_to_ncdhw_kernel(const float* __restrict__ src, const float* __restrict
 }  // namespace dkt
 
 using namespace dkt;
+
+extern "C" int dkt_dwconv3x3(const dkt_tensor* src, const float* weight, const float* bias, float in_max, float out_min,
+                             float out_max, const dkt_tensor* dst, int B, int Hin, int Win, int stride, void* stream) {
+    DKT_CHECK_ARG(src && src->f32 && weight && bias && dst && (dst->f32 || dst->hi));
+    DKT_CHECK_ARG(B > 0 && Hin > 0 && Win > 0 && (stride == 1 || stride == 2));
+    const int C = src->c_count;
+    DKT_CHECK_ARG(C > 0 && dst->c_count == C);
+    if ((C % 4) || (src->C % 4) || (src->c_begin % 4) || (dst->C % 4) || (dst->c_begin % 4)) return DKT_E_ALIGNMENT;
+    if ((reinterpret_cast<uintptr_t>(src->f32) & 15) || (reinterpret_cast<uintptr_t>(weight) & 15) ||
+        (reinterpret_cast<uintptr_t>(bias) & 15) || (reinterpret_cast<uintptr_t>(dst->f32) & 15) ||
+        (reinterpret_cast<uintptr_t>(dst->hi) & 7) || (reinterpret_cast<uintptr_t>(dst->lo) & 7))
+        return DKT_E_ALIGNMENT;
+    const int H = (Hin - 1) / stride + 1, W = (Win - 1) / stride + 1;        // kernel 3, padding 1
+    const int64_t total = (int64_t)B * H * W * (C / 4);
+    dwconv3x3_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        src->f32, src->C, src->c_begin, weight, bias, in_max, out_min, out_max, *dst, C / 4, Hin, Win, H, W, stride, total);
+    DKT_RETURN_LAST();
+}
 
 extern "C" int dkt_ncdhw_to_ndhwc_pad(const float* src, uint16_t* hi, uint16_t* lo, int B, int C, int D, int H, int W,
                                       void* stream) {

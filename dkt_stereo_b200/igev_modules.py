@@ -291,17 +291,122 @@ class Feature(nn.Module):
         self.conv4 = ConvNormAct(chans[1] * 2, chans[1] * 2, "in", kernel_size=3, stride=1, padding=1)
 
     def forward(self, x) -> List[torch.Tensor]:
-        x2 = self.block0(self.act1(self.bn1(self.conv_stem(x))))
-        x4 = self.block1(x2)
-        x8 = self.block2(x4)
-        x16 = self.block3(x8)
-        x32 = self.block4(x16)
+        if self.native_encoder_ok(x):
+            x4, x8, x16, x32 = self.encode_native(x)
+        else:
+            x2 = self.block0(self.act1(self.bn1(self.conv_stem(x))))
+            x4 = self.block1(x2)
+            x8 = self.block2(x4)
+            x16 = self.block3(x8)
+            x32 = self.block4(x16)
         if self.native_decoder_ok(x4, x8, x16, x32):
             return self.decode_native(x4, x8, x16, x32)
         x16 = self.deconv32_16(x32, x16)
         x8 = self.deconv16_8(x16, x8)
         x4 = self.conv4(self.deconv8_4(x8, x4))
         return [x4, x8, x16, x32]
+
+    # ---- MobileNetV2 encoder (reference meta_arch/igev_stereo/extractor.py:331-361) on the library's kernels --------------
+    def native_encoder_ok(self, x) -> bool:
+        import os
+        from . import _lib as L
+        return (os.environ.get("DKT_NATIVE_MBV2", "1") == "1" and not self.training and x.is_cuda and x.dtype == torch.float32
+                and os.environ.get("DKT_IMPL", "tc") == "tc" and L.split_dtype() == torch.float16
+                and x.shape[-2] % 32 == 0 and x.shape[-1] % 32 == 0)
+
+    def encode_native(self, x):
+        """block0 .. block4 after the 3-channel stem conv (which stays on cuDNN with its BatchNorm + ReLU6): every 1x1 conv
+        is a tensor-core conv over NHWC 16-bit pairs with its eval-mode BatchNorm folded into weights and bias, every
+        depthwise conv one pass of dkt_dwconv3x3 (BatchNorm folded, ReLU6), the linear-bottleneck residual rides on the
+        project conv's epilogue as its additive per-pixel term.  ReLU6 of an expand conv = ReLU in its epilogue + min(., 6) on
+        the depthwise kernel's loads.  24-channel maps live in 32-channel buffers (zero upper channels, zero weight columns);
+        expand convs wider than 256 channels run as several launches.  -> x4 (24), x8 (32), x16 (96), x32 (160), NCHW fp32."""
+        from . import _lib as L, ops
+        TS, E = L.tensor_slice, ops.make_epilogue
+        lib = L.load()
+        dev, Bt = x.device, x.shape[0]
+        cache = self.__dict__.setdefault("_enc_cache", {})
+        blocks = [b for stage in (self.block0, self.block1, self.block2, self.block3, self.block4) for seq in stage for b in seq]
+        sig = tuple((p.data_ptr(), p._version) for b in blocks for p in list(b.parameters()) + list(b.buffers()))
+        pad16 = lambda c: (c + 15) // 16 * 16                  # noqa: E731
+
+        def bn4(bn):
+            return (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+
+        def pack_dw(conv, bn):
+            s_ = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().double()
+            wd = (conv.weight.detach().double()[:, 0] * s_.view(-1, 1, 1)).permute(1, 2, 0).reshape(9, -1)     # [tap][C]
+            bd = (bn.bias.detach().double() - bn.running_mean.detach().double() * s_)
+            return wd.float().contiguous(), bd.float().contiguous()
+
+        def pack_pw(conv, bn, cin_pad):
+            w_ = conv.weight.detach()
+            N = w_.shape[0]
+            chunks = [(0, N)] if N <= 256 else [(i, min(i + 192, N)) for i in range(0, N, 192)] if N % 192 == 0 else \
+                [(i, min(i + 240, N)) for i in range(0, N, 240)]
+            g, bta, mu, var = bn4(bn)
+            return [(c0, c1, ops.pack_conv_general(w_[c0:c1], None, cin_pad=cin_pad, bn=(g[c0:c1], bta[c0:c1], mu[c0:c1], var[c0:c1]),
+                                                   bn_eps=bn.eps)) for c0, c1 in chunks]
+
+        if cache.get("sig") != sig:
+            packs = []
+            for b in blocks:
+                if isinstance(b, _DSConv):
+                    packs.append(dict(dw=pack_dw(b.conv_dw, b.bn1), pwl=pack_pw(b.conv_pw, b.bn2, pad16(b.conv_pw.in_channels))))
+                else:
+                    packs.append(dict(pw=pack_pw(b.conv_pw, b.bn1, pad16(b.conv_pw.in_channels)), dw=pack_dw(b.conv_dw, b.bn2),
+                                      pwl=pack_pw(b.conv_pwl, b.bn3, pad16(b.conv_pwl.in_channels))))
+            cache.clear()
+            cache.update(sig=sig, packs=packs)
+        packs = cache["packs"]
+        dt = L.split_dtype()
+
+        def buf(key, *shape, d=torch.float32):
+            k = (key,) + shape + (str(dev), d)
+            if k not in cache:
+                cache[k] = torch.zeros(*shape, device=dev, dtype=d)
+            return cache[k]
+
+        x2 = self.act1(self.bn1(self.conv_stem(x)))                       # (Bt,32,H/2,W/2) fp32, cuDNN
+        h, w = x2.shape[-2:]
+        cur_f = buf("in", Bt, h, w, 32)
+        ops.nchw_to_nhwc(x2, TS(cur_f, None, None, 0, 32))
+        cur = dict(f=cur_f, hi=None, lo=None, C=32)                      # running map: fp32 (+ 16-bit pair) NHWC
+        outs, bi = [], 0
+        for si, stage in enumerate((self.block0, self.block1, self.block2, self.block3, self.block4)):
+            for seq in stage:
+                for b in seq:
+                    pk = packs[bi]
+                    tag = f"b{bi}"
+                    bi += 1
+                    stride = b.conv_dw.stride[0]
+                    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+                    if isinstance(b, _DSConv):
+                        mid, mid_f, in_max = b.conv_dw.in_channels, cur["f"], 3.0e38
+                    else:
+                        mid = b.conv_pw.out_channels
+                        mid_f = buf(tag + "m", Bt, h, w, mid)
+                        for c0, c1, pw in pk["pw"]:                       # expand 1x1 + BN + ReLU (the min(., 6) is the dw's)
+                            ops.conv2d_ex([TS(None, cur["hi"], cur["lo"], 0, cur["C"])], pw,
+                                          E(L.EPI_LINEAR, TS(mid_f, None, None, c0, c1 - c0), act=L.ACT_RELU, bias=pw.bias), Bt, h, w)
+                        in_max = 6.0
+                    dh, dl = buf(tag + "dh", Bt, ho, wo, mid, d=dt), buf(tag + "dl", Bt, ho, wo, mid, d=dt)
+                    wd, bd = pk["dw"]
+                    src_t, dst_t = TS(mid_f, None, None, 0, mid), TS(None, dh, dl, 0, mid)
+                    L.check(lib.dkt_dwconv3x3(L.C.byref(src_t), wd.data_ptr(), bd.data_ptr(), in_max, 0.0, 6.0, L.C.byref(dst_t),
+                                              Bt, h, w, stride, L.stream_ptr()), "dwconv3x3")
+                    pwl_conv = b.conv_pw if isinstance(b, _DSConv) else b.conv_pwl
+                    co = pwl_conv.out_channels
+                    cop = pad16(co)
+                    of, oh, ol = buf(tag + "of", Bt, ho, wo, cop), buf(tag + "oh", Bt, ho, wo, cop, d=dt), buf(tag + "ol", Bt, ho, wo, cop, d=dt)
+                    (_, _, pwl), = pk["pwl"]
+                    ops.conv2d_ex([TS(None, dh, dl, 0, mid)], pwl,
+                                  E(L.EPI_LINEAR, TS(of, oh, ol, 0, co), bias=pwl.bias, ctx=cur["f"] if b.skip else None), Bt, ho, wo)
+                    cur = dict(f=of, hi=oh, lo=ol, C=cop)
+                    h, w = ho, wo
+            if si >= 1:                                                   # block1..4 -> x4, x8, x16, x32
+                outs.append(ops.nhwc_to_nchw(TS(cur["f"], None, None, 0, co), Bt, h, w, dev))
+        return outs
 
     # ---- U-Net decoder (FeatUp, reference meta_arch/igev_stereo/extractor.py:296-325) on the library's kernels ----------
     def native_decoder_ok(self, x4, x8, x16, x32) -> bool:

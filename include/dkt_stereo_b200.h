@@ -261,6 +261,13 @@ int dkt_softargmin(const float* logits, float* disp, int B, int D, int H, int W,
  *   0 and D+1 of every sample are the zero padding in depth (the caller zeroes them once; never written here).
  * dkt_ndhwc_pad_to_ncdhw : src fp32 (B,D+2,H,W,C), interior planes -> dst (B,C,D,H,W) fp32, multiplied by
  *   sigmoid(att[b,c,y,x]) when att != NULL (FeatureAtt, reference submodule.py:227-240).  B*D*H <= 65535. */
+/* dkt_dwconv3x3 : depthwise 3x3 convolution (padding 1, stride 1 or 2) over an NHWC fp32 slice, for the MobileNetV2 encoder
+ *   of IGEV's feature pyramid (timm conv_dw + BatchNorm + ReLU6, reference meta_arch/igev_stereo/extractor.py:331-342):
+ *   dst[p][c] = clamp(bias[c] + sum_t min(src[p + t][c], in_max) * weight[t][c], out_min, out_max); weight fp32 [9][C] with
+ *   the eval-mode BatchNorm folded in; every non-null precision of dst (B,H,W,.) is written, H = (Hin-1)/stride + 1.
+ *   in_max completes the ReLU6 of the expand conv that produced src (its epilogue applied the ReLU half). */
+int dkt_dwconv3x3(const dkt_tensor* src, const float* weight, const float* bias, float in_max, float out_min, float out_max,
+                  const dkt_tensor* dst, int B, int Hin, int Win, int stride, void* stream);
 int dkt_ncdhw_to_ndhwc_pad(const float* src, uint16_t* hi, uint16_t* lo, int B, int C, int D, int H, int W, void* stream);
 int dkt_ndhwc_pad_to_ncdhw(const float* src, const float* att, float* dst, int B, int C, int D, int H, int W, void* stream);
 
