@@ -7,9 +7,9 @@ contract (``test_mode=True`` -> ``(None, disp_up)``, disp_up = -disparity, refer
 served.
 
 What runs where:
-  PyTorch (cuDNN)  : the MobileNetV2 encoder of the feature pyramid, the 3-channel first conv of stem_2, the 2-D attention
-                     convs of FeatureAtt (reference igev_stereo.py:154-168)  -- SURVEY 8f "next" rows
-  libdkt kernels   : the feature pyramid's decoder (UpFuse x3 + conv4), the rest of stem_2 / stem_4, the matching-feature
+  PyTorch (cuDNN)  : the two 3-channel stem convs (MobileNetV2's conv_stem, stem_2's first conv), the 2-D attention convs
+                     of FeatureAtt (reference igev_stereo.py:154-168)
+  libdkt kernels   : the feature pyramid (MobileNetV2 encoder + UpFuse x3 + conv4), the rest of stem_2 / stem_4, the matching-feature
                      head conv + desc (tensor-core convs, InstanceNorm kernels), cnet + context convs (EncoderEngine),
                      GWC volume, corr_stem (3-D conv + BN + LeakyReLU + feature attention), the 3-D hourglass (32 / 48-channel
                      stride-1 layers on tcgen05), classifier + soft-argmin init disparity (igev_preloop.cu), upsample_disp,
