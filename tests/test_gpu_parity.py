@@ -1353,6 +1353,56 @@ def test_igev_hourglass_golden():
     assert stats(out_t.cpu(), g["out"])[1] < 3e-5 * scale
 
 
+@pytest.mark.parametrize("stride", [1, 2])
+def test_dwconv3x3_vs_torch(stride):
+    """dkt_dwconv3x3 (MobileNetV2 conv_dw + folded BatchNorm + ReLU6, input clamp) against F.conv2d(groups=C): odd sizes,
+    channel slice of a wider source, fp32 and 16-bit (hi, lo) destinations."""
+    import ctypes
+    from dkt_stereo_b200 import _lib as L
+    torch.manual_seed(stride)
+    B, Cs, C, H, W = 2, 40, 24, 13, 21
+    src = torch.randn(B, H, W, Cs, device=dev()) * 4
+    w = torch.randn(C, 1, 3, 3, device=dev())
+    bias = torch.randn(C, device=dev())
+    x = src[..., 8:8 + C].clamp(max=6.0).permute(0, 3, 1, 2)
+    ref = (torch.nn.functional.conv2d(x, w, bias, stride=stride, padding=1, groups=C)).clamp(0, 6).permute(0, 2, 3, 1)
+    Ho, Wo = ref.shape[1:3]
+    of = torch.zeros(B, Ho, Wo, C, device=dev())
+    oh = torch.zeros(B, Ho, Wo, C, device=dev(), dtype=L.split_dtype())
+    ol = torch.zeros_like(oh)
+    wt = w[:, 0].permute(1, 2, 0).reshape(9, C).contiguous()
+    s_t, d_t = L.tensor_slice(src, None, None, 8, C), L.tensor_slice(of, oh, ol, 0, C)
+    L.check(L.load().dkt_dwconv3x3(ctypes.byref(s_t), wt.data_ptr(), bias.data_ptr(), 6.0, 0.0, 6.0, ctypes.byref(d_t),
+                                   B, H, W, stride, L.stream_ptr()), "dwconv3x3")
+    assert stats(of.cpu(), ref.cpu())[1] < 1e-5, stats(of.cpu(), ref.cpu())
+    assert stats((oh.float() + ol.float()).cpu(), ref.cpu())[1] < 1e-4
+
+
+def test_igev_feature_pyramid_native_vs_modules(monkeypatch):
+    """Feature.forward on the library's kernels (MobileNetV2 encoder: folded BatchNorm, depthwise kernel, residual on the
+    project conv; decoder: parity-grouped transposed convs, InstanceNorm kernels) against the same module's PyTorch path
+    (fp32, TF32 off) with non-trivial BatchNorm statistics; the end-to-end goldens pin it against the reference itself."""
+    from dkt_stereo_b200.igev_modules import Feature
+    from dkt_stereo_b200.raft_stereo import _fp32_math
+    torch.manual_seed(3)
+    f = Feature().eval().to(dev())
+    with torch.no_grad():
+        for m in f.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5); m.weight.uniform_(0.7, 1.3); m.bias.normal_(0, 0.1)
+    x = torch.rand(2, 3, 96, 160, device=dev()) * 2 - 1
+    with torch.no_grad(), _fp32_math(True):
+        monkeypatch.setenv("DKT_NATIVE_MBV2", "0"); monkeypatch.setenv("DKT_NATIVE_FEATUP", "0")
+        ref = f(x)
+        monkeypatch.setenv("DKT_NATIVE_MBV2", "1"); monkeypatch.setenv("DKT_NATIVE_FEATUP", "1")
+        for _ in range(2):
+            out = f(x)
+    assert [tuple(o.shape) for o in out] == [tuple(r.shape) for r in ref]
+    for i, (o, r) in enumerate(zip(out, ref)):
+        rng = float(r.abs().max())
+        assert stats(o.cpu(), r.cpu())[1] < 2e-4 * rng, (i, stats(o.cpu(), r.cpu()), rng)
+
+
 @pytest.mark.parametrize("C,shape", [(32, (2, 32, 12, 34, 60)), (48, (1, 48, 6, 17, 30)), (16, (1, 16, 8, 20, 44))])
 def test_hourglass_layer_on_tensor_cores_vs_fp32_kernel(C, shape):
     """Hourglass._k3_tc -- a stride-1 3x3x3 BasicConv + FeatureAtt as one launch of the 2-D tcgen05 conv over the depth planes
