@@ -180,6 +180,8 @@ class Hourglass(nn.Module):
         pack = cache[wkey][1]
         bkey = ("b", B, CI, CO, D, H, W, str(v.device))
         if bkey not in cache:
+            for k in [k for k in cache if k[0] == "b" and k[2:4] == (CI, CO)]:      # a new input shape replaces the old buffers
+                del cache[k]
             dt = L.split_dtype()
             cache[bkey] = (torch.zeros(B, D + 2, H, W, CI, device=v.device, dtype=dt),      # zero planes at d = -1 and d = D
                            torch.zeros(B, D + 2, H, W, CI, device=v.device, dtype=dt),
@@ -360,6 +362,10 @@ class Feature(nn.Module):
             cache.update(sig=sig, packs=packs)
         packs = cache["packs"]
         dt = L.split_dtype()
+        if cache.get("shape") != (tuple(x.shape), str(dev)):              # one input shape's buffers at a time (datasets
+            for k in [k for k in cache if isinstance(k, tuple)]:          # with many image sizes must not pile them up)
+                del cache[k]
+            cache["shape"] = (tuple(x.shape), str(dev))
 
         def buf(key, *shape, d=torch.float32):
             k = (key,) + shape + (str(dev), d)
@@ -444,6 +450,10 @@ class Feature(nn.Module):
             cache.update(sig=sig, w=w)
         w = cache["w"]
         dt = L.split_dtype()
+        if cache.get("shape") != (tuple(x4.shape), str(dev)):
+            for k in [k for k in cache if isinstance(k, tuple)]:
+                del cache[k]
+            cache["shape"] = (tuple(x4.shape), str(dev))
 
         def buf(key, *shape, d=torch.float32):
             k = (key,) + shape + (str(dev), d)
