@@ -273,38 +273,60 @@ to_nchw_kernel(const float* __restrict__ src, int sC, int sc0, float* __restrict
 }
 
 // ---- depthwise 3x3 convolution, NHWC (MobileNetV2 of the IGEV feature pyramid: timm conv_dw + folded BatchNorm + ReLU6) ----
-// thread = (output pixel, group of 4 channels): nine 16-byte loads (zero outside the image), fp32 FMAs, bias, clamp, every
+// thread = (4 consecutive output pixels of a row, group of 4 channels): per filter row the 6 (stride 1) / 9 (stride 2) input
+// columns are loaded once (16-byte loads, zero outside the image) and feed all four outputs; fp32 FMAs, bias, clamp, every
 // non-null precision of dst written.  in_max clamps the INPUT on load: the expand conv that produced it applied ReLU in its
 // epilogue, min(., 6) completes its ReLU6 here.
+template <int STRIDE>
 __global__ void __launch_bounds__(256)
 dwconv3x3_kernel(const float* __restrict__ src, int sC, int sc0, const float* __restrict__ w, const float* __restrict__ bias,
                  float in_max, float out_min, float out_max, dkt_tensor dst, int C4, int Hin, int Win, int H, int W,
-                 int stride, int64_t total) {
+                 int64_t total) {
+    constexpr int XO = 4, NIN = (XO - 1) * STRIDE + 3;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
+    const int WQ = (W + XO - 1) / XO;
     const int g = (int)(t % C4);
-    const int64_t p = t / C4;
-    const int x = (int)(p % W), y = (int)((p / W) % H);
-    const int64_t b = p / ((int64_t)W * H);
-    const int c = g * 4;
-    float4 acc = __ldg(reinterpret_cast<const float4*>(bias + c));
+    const int64_t q = t / C4;
+    const int xq = (int)(q % WQ), y = (int)((q / WQ) % H);
+    const int64_t b = q / ((int64_t)WQ * H);
+    const int c = g * 4, x0 = xq * XO;
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c));
+    float4 acc[XO];
+#pragma unroll
+    for (int i = 0; i < XO; ++i) acc[i] = bv;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-        const int iy = y * stride + ky - 1;
+        const int iy = y * STRIDE + ky - 1;
         if (iy < 0 || iy >= Hin) continue;
+        const float* row = src + ((b * Hin + iy) * (int64_t)Win) * sC + sc0 + c;
+        float4 v[NIN];
+#pragma unroll
+        for (int j = 0; j < NIN; ++j) {
+            const int ix = x0 * STRIDE + j - 1;
+            v[j] = (ix >= 0 && ix < Win) ? __ldg(reinterpret_cast<const float4*>(row + (int64_t)ix * sC)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[j].x = fminf(v[j].x, in_max); v[j].y = fminf(v[j].y, in_max); v[j].z = fminf(v[j].z, in_max); v[j].w = fminf(v[j].w, in_max);
+        }
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-            const int ix = x * stride + kx - 1;
-            if (ix < 0 || ix >= Win) continue;
-            float4 v = __ldg(reinterpret_cast<const float4*>(src + ((b * Hin + iy) * (int64_t)Win + ix) * sC + sc0 + c));
             const float4 k = __ldg(reinterpret_cast<const float4*>(w + (int64_t)(ky * 3 + kx) * C4 * 4 + c));   // [tap][C]
-            v.x = fminf(v.x, in_max); v.y = fminf(v.y, in_max); v.z = fminf(v.z, in_max); v.w = fminf(v.w, in_max);
-            acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y); acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+#pragma unroll
+            for (int i = 0; i < XO; ++i) {
+                const float4 u = v[i * STRIDE + kx];
+                acc[i].x = fmaf(u.x, k.x, acc[i].x); acc[i].y = fmaf(u.y, k.y, acc[i].y);
+                acc[i].z = fmaf(u.z, k.z, acc[i].z); acc[i].w = fmaf(u.w, k.w, acc[i].w);
+            }
         }
     }
-    acc.x = fminf(fmaxf(acc.x, out_min), out_max); acc.y = fminf(fmaxf(acc.y, out_min), out_max);
-    acc.z = fminf(fmaxf(acc.z, out_min), out_max); acc.w = fminf(fmaxf(acc.w, out_min), out_max);
-    store_all4(dst, p, c, acc);
+#pragma unroll
+    for (int i = 0; i < XO; ++i) {
+        const int x = x0 + i;
+        if (x >= W) break;
+        float4 a = acc[i];
+        a.x = fminf(fmaxf(a.x, out_min), out_max); a.y = fminf(fmaxf(a.y, out_min), out_max);
+        a.z = fminf(fmaxf(a.z, out_min), out_max); a.w = fminf(fmaxf(a.w, out_min), out_max);
+        store_all4(dst, (b * H + y) * (int64_t)W + x, c, a);
+    }
 }
 
 // ---- depth-padded NDHWC <-> NCDHW (IGEV hourglass layers on the 2-D tensor-core conv: depth planes are its images) ----
@@ -373,9 +395,13 @@ extern "C" int dkt_dwconv3x3(const dkt_tensor* src, const float* weight, const f
         (reinterpret_cast<uintptr_t>(dst->hi) & 7) || (reinterpret_cast<uintptr_t>(dst->lo) & 7))
         return DKT_E_ALIGNMENT;
     const int H = (Hin - 1) / stride + 1, W = (Win - 1) / stride + 1;        // kernel 3, padding 1
-    const int64_t total = (int64_t)B * H * W * (C / 4);
-    dwconv3x3_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        src->f32, src->C, src->c_begin, weight, bias, in_max, out_min, out_max, *dst, C / 4, Hin, Win, H, W, stride, total);
+    const int64_t total = (int64_t)B * H * ((W + 3) / 4) * (C / 4);
+    if (stride == 1)
+        dwconv3x3_kernel<1><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            src->f32, src->C, src->c_begin, weight, bias, in_max, out_min, out_max, *dst, C / 4, Hin, Win, H, W, total);
+    else
+        dwconv3x3_kernel<2><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            src->f32, src->C, src->c_begin, weight, bias, in_max, out_min, out_max, *dst, C / 4, Hin, Win, H, W, total);
     DKT_RETURN_LAST();
 }
 
