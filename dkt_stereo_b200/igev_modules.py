@@ -358,6 +358,19 @@ class Feature(nn.Module):
                 else:
                     packs.append(dict(pw=pack_pw(b.conv_pw, b.bn1, pad16(b.conv_pw.in_channels)), dw=pack_dw(b.conv_dw, b.bn2),
                                       pwl=pack_pw(b.conv_pwl, b.bn3, pad16(b.conv_pwl.in_channels))))
+            # block0's projection (32 -> 16, linear: BatchNorm, no activation, no skip) is consumed by block1's first expand
+            # conv alone: the two 1x1 convs are ONE 32 -> 96 conv, composed in fp64 here -- the 16-channel map at half
+            # resolution (a quarter K block for the conv that read it: 0.72 ms) never exists
+            b0, b1 = blocks[0], blocks[1]
+            if isinstance(b0, _DSConv) and not b0.skip and not b1.skip:
+                def fold(conv, bn):
+                    s_ = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().double()
+                    return conv.weight.detach().double()[:, :, 0, 0] * s_.view(-1, 1), (bn.bias.detach().double() - bn.running_mean.detach().double() * s_)
+                w1, c1 = fold(b0.conv_pw, b0.bn2)
+                w2, c2 = fold(b1.conv_pw, b1.bn1)
+                wc, cc = (w2 @ w1).float(), (w2 @ c1 + c2).float()
+                packs[1]["pw"] = [(0, wc.shape[0], ops.pack_conv_general(wc.view(wc.shape[0], wc.shape[1], 1, 1), cc))]
+                packs[0]["fused_next"] = True
             cache.clear()
             cache.update(sig=sig, packs=packs)
         packs = cache["packs"]
@@ -401,6 +414,10 @@ class Feature(nn.Module):
                     src_t, dst_t = TS(mid_f, None, None, 0, mid), TS(None, dh, dl, 0, mid)
                     L.check(lib.dkt_dwconv3x3(L.C.byref(src_t), wd.data_ptr(), bd.data_ptr(), in_max, 0.0, 6.0, L.C.byref(dst_t),
                                               Bt, h, w, stride, L.stream_ptr()), "dwconv3x3")
+                    if pk.get("fused_next"):                          # projection composed into the next block's expand conv
+                        cur = dict(f=None, hi=dh, lo=dl, C=mid)
+                        h, w = ho, wo
+                        continue
                     pwl_conv = b.conv_pw if isinstance(b, _DSConv) else b.conv_pwl
                     co = pwl_conv.out_channels
                     cop = pad16(co)
