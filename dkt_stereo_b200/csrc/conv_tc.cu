@@ -1170,6 +1170,7 @@ static int launch_pair_fl(const TcConvParams& prm, unsigned grid, size_t smem_by
         const int fl = epilogue_flags(prm.epi);
         if (fl == EPF_OUT_SPLIT) return launch_pair<KIND, ACT, KB, EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);
         if (fl == EPF_OUT_HI) return launch_pair<KIND, ACT, KB, EPF_OUT_HI>(prm, grid, smem_bytes, st);
+        if (fl == EPF_OUT_F32) return launch_pair<KIND, ACT, KB, EPF_OUT_F32>(prm, grid, smem_bytes, st);      // MobileNetV2 expand convs
         if constexpr (KB == 64) {
             if (fl == (EPF_OUT_HI | EPF_TAIL)) return launch_pair<KIND, ACT, KB, EPF_OUT_HI | EPF_TAIL>(prm, grid, smem_bytes, st);
             if (fl == (EPF_OUT_SPLIT | EPF_RES_SPLIT)) return launch_pair<KIND, ACT, KB, EPF_OUT_SPLIT | EPF_RES_SPLIT>(prm, grid, smem_bytes, st);
@@ -1182,6 +1183,10 @@ static int launch_pair_fl(const TcConvParams& prm, unsigned grid, size_t smem_by
         if (fl == (EPF_OUT_F32 | EPF_STATS)) return launch_pair<KIND, ACT, KB, EPF_OUT_F32 | EPF_STATS>(prm, grid, smem_bytes, st);
         if constexpr (KB == 64) {
             if (fl == EPF_OUT_F32) return launch_pair<KIND, ACT, KB, EPF_OUT_F32>(prm, grid, smem_bytes, st);
+            // MobileNetV2 project convs: fp32 + 16-bit pair out, with / without the linear-bottleneck residual as ctx
+            if (fl == (EPF_OUT_F32 | EPF_OUT_SPLIT)) return launch_pair<KIND, ACT, KB, EPF_OUT_F32 | EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);
+            if (fl == (EPF_OUT_F32 | EPF_OUT_SPLIT | EPF_CTX))
+                return launch_pair<KIND, ACT, KB, EPF_OUT_F32 | EPF_OUT_SPLIT | EPF_CTX>(prm, grid, smem_bytes, st);
         }
     }
     if constexpr (KIND == DKT_EPI_GRU_ZR && KB == 64) {            // tensor-core engine: r*h as a 16-bit pair, or hi only
