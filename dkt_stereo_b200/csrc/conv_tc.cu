@@ -771,7 +771,7 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
 // ---------------------------------------------------------------------------------------------
 constexpr int TCP_MAX_A = 4, TCP_MAX_W = 9;
 
-template <int WK, int KIND, int ACT>
+template <int WK, int KIND, int ACT, int FL = EPF_GENERIC>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
     constexpr bool XMT = false;                      // M row = y * 16 + x
@@ -914,12 +914,125 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
         if constexpr (KIND == DKT_EPI_PROJ)
             conv_tc_epilogue_proj<ACT, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
         else
-            conv_tc_epilogue_warps<KIND, ACT, EPF_GENERIC, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+            conv_tc_epilogue_warps<KIND, ACT, FL, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
     }
 
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, prm.tmem_cols);
+}
+
+// MMA issue loop of the CTA-pair kernel (warp 1 of the leader).  ncu r4a (source page of the full-resolution 64 -> 64
+// encoder convs): at N <= 128 a tap's MMAs take ~400 clocks of tensor time but the single issuing warp needed ~780 clocks
+// per tap -- ~150 dependent instructions: an integer division for (ky, kx), descriptor words rebuilt from byte addresses,
+// run-time operand-mode tests around every UTCHMMA, constant-bank reloads -- and the tensor pipe sat at 50 %.  Here the
+// operand mode (MERGED = TcConvParams::merged_n, A_LO / B_LO = which lo planes exist) is a template parameter, every
+// descriptor is a constant high word + a running 14-bit low word (address >> 4) advanced by additions only, the tap's
+// patch offset is counted, not divided, and full K blocks run without the partial-block test.
+struct PairMmaCtx {
+    uint8_t* a_ring; uint8_t* w_ring;
+    uint64_t* afull; uint64_t* aempty; uint64_t* wfull; uint64_t* wempty; uint64_t* tmem_full_bar; uint64_t* tmem_empty_bar;
+    uint32_t tmem_base;
+    int pair_id, pairs, items;
+};
+
+__device__ __forceinline__ uint64_t desc_words(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+
+template <int KB, bool XMT, int MERGED, bool A_LO, bool B_LO>
+__device__ __forceinline__ void pair_mma_loop(const TcConvParams& prm, const PairMmaCtx& cx) {
+    constexpr uint32_t KROW = KB * 2;
+    constexpr uint32_t KSTEPS = KB / 16;
+    const uint32_t idesc = idesc_bf16_m256((uint32_t)(MERGED ? 2 * prm.Npad : prm.Npad));
+    const uint32_t idesc_n = idesc_bf16_m256((uint32_t)prm.Npad);          // MERGED == 2: the x_lo * w_hi MMA
+    const int ntaps = prm.ygroup;                                          // taps served by one A stage
+    const int kw = prm.kw;
+    const int steps_per_kb = XMT ? 1 : prm.kw * (prm.kh / prm.ygroup);     // A steps per K block
+    const int a_stages = prm.a_stages, w_stages = prm.w_stages, nsrc = prm.nsrc;
+    const uint32_t acc_stages = prm.acc_stages, acc_cols = prm.acc_cols, acc_lo_off = prm.acc_lo_off;
+    const bool w_stream = !prm.w_resident;
+    // descriptor words: low = (address >> 4) | 1 << 16, high = atom stride | version | swizzle (constant per operand)
+    const uint32_t sbo = XMT ? (uint32_t)prm.patch_rows * KROW : 8u * KROW;
+    const uint32_t da_hi = (uint32_t)(smem_desc_kmajor_sbo<KB>(0u, sbo) >> 32), dw_hi = (uint32_t)(smem_desc_kmajor<KB>(0u) >> 32);
+    const uint32_t a_base16 = ((smem_u32(cx.a_ring) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t w_base16 = ((smem_u32(cx.w_ring) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t a_part16 = prm.a_part_bytes >> 4, a_stage16 = ((uint32_t)prm.a_parts * prm.a_part_bytes) >> 4;
+    const uint32_t b16 = ((uint32_t)(prm.Npad >> 1) * KROW) >> 4, w_stage16 = (uint32_t)prm.b_parts * b16;
+    const uint32_t tapx16 = XMT ? ((uint32_t)prm.patch_rows * KROW) >> 4 : (TC_TILE_W * KROW) >> 4;   // next tap in the row (XMT: kx + 1)
+    constexpr uint32_t tapy16 = KROW >> 4;                                                           // XMT: ky + 1
+    int as = 0, ws = 0;
+    uint32_t aph = 0, wph = 0, acs = 0, aphase = 0;
+    uint32_t a16 = a_base16, w16 = w_base16;             // low descriptor words of the current A / W stage
+    bool first = true;
+    for (int item = cx.pair_id; item < cx.items; item += cx.pairs) {
+        mbar_wait(&cx.tmem_empty_bar[acs], aphase ^ 1u);     // both CTAs' epilogues drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tmem_d = cx.tmem_base + acs * acc_cols;
+        const uint32_t tmem_lo = tmem_d + acc_lo_off;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < nsrc; ++s) {
+            const int kblocks = prm.kblocks[s], klast = prm.klast[s];
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const bool full = (kb != kblocks - 1) || klast == (int)KSTEPS;
+                for (int ai = 0; ai < steps_per_kb; ++ai) {
+                    mbar_wait(&cx.afull[as], aph);
+                    tcgen05_fence_after();
+                    uint32_t t16 = a16, row16 = a16;     // this tap's patch start; start of the tap row (XMT)
+                    int kx = 0;
+                    for (int tap = 0; tap < ntaps; ++tap) {
+                        if (w_stream || first) {
+                            mbar_wait(&cx.wfull[ws], wph);
+                            tcgen05_fence_after();
+                        }
+                        if (elect_one()) {
+                            auto step = [&](uint32_t k2, uint32_t acc) {
+                                const uint64_t dah = desc_words(t16 + k2, da_hi), dwh = desc_words(w16 + k2, dw_hi);
+                                umma_bf16_pair(tmem_d, dah, dwh, idesc, acc);
+                                if (MERGED == 2) {
+                                    umma_bf16_pair(tmem_d + 128u, desc_words(t16 + a_part16 + k2, da_hi), dwh, idesc_n, acc);
+                                } else if (MERGED == 0) {
+                                    const uint32_t acc_l = acc_lo_off ? acc : 1u;      // first lo MMA of a tile overwrites
+                                    if (A_LO) umma_bf16_pair(tmem_lo, desc_words(t16 + a_part16 + k2, da_hi), dwh, idesc, acc_l);
+                                    if (B_LO) umma_bf16_pair(tmem_lo, dah, desc_words(w16 + b16 + k2, dw_hi), idesc, A_LO ? 1u : acc_l);
+                                }
+                            };
+                            if (full) {                      // +32 bytes per K16 step = +2 in the address field
+                                step(0u, accumulate);
+#pragma unroll
+                                for (uint32_t k = 1; k < KSTEPS; ++k) step(2u * k, 1u);
+                            } else {
+                                step(0u, accumulate);
+#pragma unroll
+                                for (uint32_t k = 1; k < KSTEPS; ++k) {
+                                    if ((int)k >= klast) break;
+                                    step(2u * k, 1u);
+                                }
+                            }
+                            if (w_stream) umma_commit_pair(&cx.wempty[ws]);
+                        }
+                        accumulate = 1u;
+                        w16 += w_stage16;
+                        if (++ws == w_stages) { ws = 0; wph ^= 1u; w16 = w_base16; }
+                        if (XMT) {                           // tap (ky, kx) = the patch read from row kx * RY + ky
+                            t16 += tapx16;
+                            if (++kx == kw) { kx = 0; row16 += tapy16; t16 = row16; }
+                        } else {
+                            t16 += tapx16;
+                        }
+                    }
+                    if (elect_one()) umma_commit_pair(&cx.aempty[as]);   // both CTAs' patches reusable once every tap's MMAs retire
+                    a16 += a_stage16;
+                    if (++as == a_stages) { as = 0; aph ^= 1u; a16 = a_base16; }
+                }
+            }
+        }
+        if (elect_one()) umma_commit_pair(&cx.tmem_full_bar[acs]);
+        if (++acs == acc_stages) { acs = 0; aphase ^= 1u; }
+        first = false;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1053,66 +1166,16 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
     } else if (warp == 1) {
         if (leader) {
             // ===== MMA issuer (leader): M = 256 over both CTAs' tiles =====
-            const uint32_t idesc = idesc_bf16_m256((uint32_t)(prm.merged_n ? 2 * prm.Npad : prm.Npad));
-            const uint32_t idesc_n = idesc_bf16_m256((uint32_t)prm.Npad);          // merged_n == 2: the x_lo * w_hi MMA
-            int as = 0, ws = 0;
-            uint32_t aph = 0, wph = 0, acs = 0, aphase = 0;
-            const int steps_per_kb = kx_n * ygroups;             // A steps per K block
-            const uint32_t sbo = XMT ? (uint32_t)prm.patch_rows * KROW : 8u * KROW;      // bytes between 8-row atoms of A
+            // one instantiation of the issue loop per operand mode (see pair_mma_loop): what a tap costs THIS warp in
+            // issue slots bounds every conv whose MMAs are short (N <= 128)
             const bool a_lo = prm.a_parts == 2, b_lo = prm.b_parts == 2;
-            bool first = true;
-            for (int item = pair_id; item < items; item += pairs) {
-                mbar_wait(&tmem_empty_bar[acs], aphase ^ 1u);     // both CTAs' epilogues drained this accumulator
-                tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + acs * prm.acc_cols;
-                uint32_t accumulate = 0;
-                for (int s = 0; s < prm.nsrc; ++s)
-                for (int kb = 0; kb < prm.kblocks[s]; ++kb)
-                for (int ai = 0; ai < steps_per_kb; ++ai) {
-                    const int kn = (kb == prm.kblocks[s] - 1) ? prm.klast[s] : KB / 16;   // K16 steps of this block
-                    mbar_wait(&afull[as], aph);
-                    tcgen05_fence_after();
-                    const uint32_t a_hi0 = smem_u32(a_ring + (size_t)as * a_stage_bytes);
-                    for (int kyi = 0; kyi < prm.ygroup; ++kyi) {
-                        uint32_t a_hi;
-                        if (XMT) {                   // tap kyi = (ky, kx): the patch read from row kx * RY + ky
-                            const int ky = kyi / prm.kw, kx = kyi - ky * prm.kw;
-                            a_hi = a_hi0 + (uint32_t)(kx * prm.patch_rows + ky) * KROW;
-                        } else {
-                            a_hi = a_hi0 + (uint32_t)kyi * (TC_TILE_W * KROW);
-                        }
-                        if (!prm.w_resident || first) {
-                            mbar_wait(&wfull[ws], wph);
-                            tcgen05_fence_after();
-                        }
-                        if (elect_one()) {
-                            const uint32_t w_hi = smem_u32(w_ring + (size_t)ws * w_stage_bytes);
-                            const uint64_t dah = smem_desc_kmajor_sbo<KB>(a_hi, sbo), dal = smem_desc_kmajor_sbo<KB>(a_hi + a_part, sbo);
-                            const uint64_t dwh = smem_desc_kmajor<KB>(w_hi), dwl = smem_desc_kmajor<KB>(w_hi + b_bytes);
-#pragma unroll
-                            for (int k = 0; k < KB / 16; ++k) {   // +32 bytes per K16 step = +2 in the address field
-                                if (k >= kn) break;
-                                const uint32_t acc_l = prm.acc_lo_off ? accumulate : 1u;      // first lo MMA of a tile overwrites
-                                umma_bf16_pair(tmem_d, dah + 2 * k, dwh + 2 * k, idesc, accumulate);
-                                if (prm.merged_n == 2) umma_bf16_pair(tmem_d + 128u, dal + 2 * k, dwh + 2 * k, idesc_n, accumulate);
-                                if (!prm.merged_n) {
-                                    if (a_lo) umma_bf16_pair(tmem_d + prm.acc_lo_off, dal + 2 * k, dwh + 2 * k, idesc, acc_l);
-                                    if (b_lo) umma_bf16_pair(tmem_d + prm.acc_lo_off, dah + 2 * k, dwl + 2 * k, idesc, a_lo ? 1u : acc_l);
-                                }
-                                accumulate = 1u;
-                            }
-                            if (!prm.w_resident) umma_commit_pair(&wempty[ws]);
-                        }
-                        accumulate = 1u;
-                        if (++ws == prm.w_stages) { ws = 0; wph ^= 1u; }
-                    }
-                    if (elect_one()) umma_commit_pair(&aempty[as]);   // both CTAs' patches reusable once every tap's MMAs retire
-                    if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
-                }
-                if (elect_one()) umma_commit_pair(&tmem_full_bar[acs]);
-                if (++acs == prm.acc_stages) { acs = 0; aphase ^= 1u; }
-                first = false;
-            }
+            const PairMmaCtx cx{a_ring, w_ring, afull, aempty, wfull, wempty, tmem_full_bar, tmem_empty_bar, tmem_base, pair_id, pairs, items};
+            if (prm.merged_n == 2) pair_mma_loop<KB, XMT, 2, true, true>(prm, cx);
+            else if (prm.merged_n == 1) pair_mma_loop<KB, XMT, 1, false, true>(prm, cx);
+            else if (a_lo && b_lo) pair_mma_loop<KB, XMT, 0, true, true>(prm, cx);
+            else if (b_lo) pair_mma_loop<KB, XMT, 0, false, true>(prm, cx);
+            else if (a_lo) pair_mma_loop<KB, XMT, 0, true, false>(prm, cx);
+            else pair_mma_loop<KB, XMT, 0, false, false>(prm, cx);
         }
     } else {
         const TileWalk tw{pair_id, pairs, items, 2, (int)rank, leader ? 0u : mapa_u32(smem_u32(tmem_empty_bar), 0)};
@@ -1223,6 +1286,13 @@ static int launch_tap_fl(const TcConvParams& prm, unsigned grid, size_t smem_byt
     return launch_tap<KIND, ACT, EPF_GENERIC>(prm, grid, smem_bytes, st);
 }
 
+template <int KIND, int ACT, int FL>
+static int launch_patch64(const TcConvParams& prm, unsigned grid, size_t smem_bytes, cudaStream_t st) {
+    DKT_ENSURE_SMEM(227 * 1024, conv_tc_patch_kernel<64, KIND, ACT, FL>);
+    conv_tc_patch_kernel<64, KIND, ACT, FL><<<grid, TC2_THREADS, smem_bytes, st>>>(prm);
+    DKT_RETURN_LAST();
+}
+
 template <int KIND, int ACT>
 static int launch_conv_ka(ConvFamily fam, const TcConvParams& prm, unsigned grid, size_t smem_bytes, cudaStream_t st) {
     if (fam == FAM_PAIR) return launch_pair_fl<KIND, ACT, 64>(prm, grid, smem_bytes, st);
@@ -1232,6 +1302,19 @@ static int launch_conv_ka(ConvFamily fam, const TcConvParams& prm, unsigned grid
             return launch_pair_fl<KIND, ACT, 32>(prm, grid, smem_bytes, st);
         else
             return DKT_E_UNSUPPORTED;
+    }
+    // row-patch kernel with 64-channel W steps (N <= 128: the encoders' strided convs, whose small MMA phase leaves the
+    // epilogue exposed): the same hot operand combinations as the per-tap kernel get their own instantiation
+    if (fam == FAM_PATCH64) {
+        if constexpr (KIND == DKT_EPI_LINEAR && ACT == DKT_ACT_RELU) {
+            if (epilogue_flags(prm.epi) == EPF_OUT_SPLIT) return launch_patch64<KIND, ACT, EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);
+        }
+        if constexpr (KIND == DKT_EPI_LINEAR && ACT == DKT_ACT_NONE) {
+            const int fl = epilogue_flags(prm.epi);
+            if (fl == (EPF_OUT_F32 | EPF_STATS)) return launch_patch64<KIND, ACT, EPF_OUT_F32 | EPF_STATS>(prm, grid, smem_bytes, st);
+            if (fl == EPF_OUT_SPLIT) return launch_patch64<KIND, ACT, EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);
+            if (fl == EPF_OUT_F32) return launch_patch64<KIND, ACT, EPF_OUT_F32>(prm, grid, smem_bytes, st);
+        }
     }
     DKT_ENSURE_SMEM(227 * 1024, conv_tc_patch_kernel<32, KIND, ACT>);
     DKT_ENSURE_SMEM(227 * 1024, conv_tc_patch_kernel<64, KIND, ACT>);
