@@ -126,6 +126,45 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 // ---- activations.  expf / tanhf (not the __ intrinsics): the recurrence is sensitive ----
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Gate activations of the tensor-core GRU epilogues (-DDKT_FAST_GATES=0: expf / tanhf / IEEE division as above).
+// ncu r4d: with expf + a full division per gate value the epilogue warps of the 1/8- and 1/16-resolution GRUs (one MMA
+// per K16 step) spent a quarter of their samples in sigmoidf_acc and the MMA warp waited for accumulators.  Here:
+// e^x = ex2.approx(t) * (1 + r ln 2) with t + r = x log2(e) carried as a rounded product and its FMA remainder, so the
+// argument error does not grow with |x| (ex2.approx: 2 ulp); 1 / d = rcp.approx + one Newton step (< 1 ulp).  Absolute
+// error of either gate <= ~1.5e-7 (arguments clamped where the fp32 result is saturated anyway).
+#ifndef DKT_FAST_GATES
+#define DKT_FAST_GATES 1
+#endif
+__device__ __forceinline__ float exp_fast(float x) {
+    const float t = x * 1.44269502162933349609375f;
+    float r = fmaf(x, 1.44269502162933349609375f, -t);
+    r = fmaf(x, 1.925963033500011e-8f, r);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return fmaf(e, r * 0.693147182464599609375f, e);
+}
+__device__ __forceinline__ float rcp_fast(float d) {          // d in [1, 2^45]
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return fmaf(r, fmaf(-d, r, 1.0f), r);
+}
+__device__ __forceinline__ float sigmoidf_gate(float x) {
+#if DKT_FAST_GATES
+    x = fminf(fmaxf(x, -30.0f), 30.0f);
+    return rcp_fast(1.0f + exp_fast(-x));
+#else
+    return sigmoidf_acc(x);
+#endif
+}
+__device__ __forceinline__ float tanhf_gate(float x) {
+#if DKT_FAST_GATES
+    x = fminf(fmaxf(x, -15.0f), 15.0f);
+    return fmaf(-2.0f, rcp_fast(1.0f + exp_fast(2.0f * x)), 1.0f);
+#else
+    return tanhf(x);
+#endif
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
     switch (act) {
         case DKT_ACT_RELU:    return fmaxf(x, 0.0f);

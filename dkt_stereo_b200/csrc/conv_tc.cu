@@ -447,8 +447,8 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                                     else { a.y = tv[i4][0]; a.z = tv[i4][1]; a.w = tv[i4][2]; }
                                 }
                             } else if (KIND == DKT_EPI_GRU_ZR) {
-                                a.x = sigmoidf_acc(a.x + cv[i4].x); a.y = sigmoidf_acc(a.y + cv[i4].y);
-                                a.z = sigmoidf_acc(a.z + cv[i4].z); a.w = sigmoidf_acc(a.w + cv[i4].w);
+                                a.x = sigmoidf_gate(a.x + cv[i4].x); a.y = sigmoidf_gate(a.y + cv[i4].y);
+                                a.z = sigmoidf_gate(a.z + cv[i4].z); a.w = sigmoidf_gate(a.w + cv[i4].w);
                                 if (n < Nh) {
                                     *reinterpret_cast<float4*>(e.z.f32 + (p00 + d) * e.z.C + e.z.c_begin + n) = a;
                                     continue;
@@ -456,10 +456,10 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                                 a.x *= hv[i4].x; a.y *= hv[i4].y; a.z *= hv[i4].z; a.w *= hv[i4].w;
                             } else {                     // GRU_Q
                                 const float4 z = zv[i4], h = hv[i4];
-                                a.x = (1.f - z.x) * h.x + z.x * tanhf(a.x + cv[i4].x);
-                                a.y = (1.f - z.y) * h.y + z.y * tanhf(a.y + cv[i4].y);
-                                a.z = (1.f - z.z) * h.z + z.z * tanhf(a.z + cv[i4].z);
-                                a.w = (1.f - z.w) * h.w + z.w * tanhf(a.w + cv[i4].w);
+                                a.x = (1.f - z.x) * h.x + z.x * tanhf_gate(a.x + cv[i4].x);
+                                a.y = (1.f - z.y) * h.y + z.y * tanhf_gate(a.y + cv[i4].y);
+                                a.z = (1.f - z.z) * h.z + z.z * tanhf_gate(a.z + cv[i4].z);
+                                a.w = (1.f - z.w) * h.w + z.w * tanhf_gate(a.w + cv[i4].w);
                             }
                             if (has_stats) {
                                 ssum.x += a.x; ssum.y += a.y; ssum.z += a.z; ssum.w += a.w;
@@ -1106,10 +1106,18 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs): own A patches, own half of the W blocks; bytes counted on the leader =====
+        // (per-tap state -- weight row, ring slot address, barrier address -- advances by additions: with one MMA per
+        // K16 step a tap lasts ~512 clocks and this loop must keep up with it)
         const uint32_t afull_l = mapa_u32(smem_u32(afull), 0), wfull_l = mapa_u32(smem_u32(wfull), 0);
         const int wrow0 = (int)rank * Nh;
+        const int a_stages = prm.a_stages, w_stages = prm.w_stages, ntaps = prm.ygroup, Npad = prm.Npad, nsrc = prm.nsrc;
+        const bool a2 = prm.a_parts == 2, b2 = prm.b_parts == 2 && prm.merged_n != 1, w_stream = !prm.w_resident;
+        const CUtensorMap* const wmap0 = prm.merged_n == 1 ? &prm.wgt[rank] : &prm.wgt[0];   // merged: this CTA's half of B' = [w_hi; w_lo] is one whole plane
+        const int wrow_first = prm.merged_n == 1 ? 0 : wrow0;
+        const uint32_t a_tx2 = 2u * prm.a_tx_bytes, w_tx2 = 2u * w_stage_bytes;
         int as = 0, ws = 0;
         uint32_t aph = 0, wph = 0;
+        uint8_t* wst = w_ring;
         bool first = true;
         for (int item = pair_id; item < items; item += pairs) {
             int tile = 2 * item + (int)rank;
@@ -1118,9 +1126,10 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
             const int r = tile - b * tiles_per_img;
             const int y0 = (r / prm.tiles_x) * TC_TILE_H, x0 = (r % prm.tiles_x) * TC_TILE_W;
             int kofs = 0;
-            for (int s = 0; s < prm.nsrc; ++s) {
-                for (int kb = 0; kb < prm.kblocks[s]; ++kb) {
-                    const int c = prm.c_begin[s] + kb * KB;
+            for (int s = 0; s < nsrc; ++s) {
+                const int kblocks = prm.kblocks[s];
+                int c = prm.c_begin[s], kc = kofs;
+                for (int kb = 0; kb < kblocks; ++kb, c += KB, kc += KB) {
                     for (int kx = 0; kx < kx_n; ++kx) {
                         const int xs = XMT ? x0 - prm.pad_x : x0 + kx - prm.pad_x;
                         for (int yg = 0; yg < ygroups; ++yg) {
@@ -1128,33 +1137,29 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
                             mbar_wait(&aempty[as], aph ^ 1u);
                             if (elect_one()) {
                                 uint8_t* ast = a_ring + (size_t)as * a_stage_bytes;
-                                if (leader) mbar_arrive_expect_tx(&afull[as], 2u * prm.a_tx_bytes);
+                                if (leader) mbar_arrive_expect_tx(&afull[as], a_tx2);
                                 if (XMT) {           // tensor dims ordered {C, y, x, b}
                                     tma_load_4d_pair(ast, &prm.act[s][0], afull_l + as * 8u, c, ys, xs, b);
-                                    if (prm.a_parts == 2) tma_load_4d_pair(ast + a_part, &prm.act[s][1], afull_l + as * 8u, c, ys, xs, b);
+                                    if (a2) tma_load_4d_pair(ast + a_part, &prm.act[s][1], afull_l + as * 8u, c, ys, xs, b);
                                 } else {
                                     tma_load_4d_pair(ast, &prm.act[s][0], afull_l + as * 8u, c, xs, ys, b);
-                                    if (prm.a_parts == 2) tma_load_4d_pair(ast + a_part, &prm.act[s][1], afull_l + as * 8u, c, xs, ys, b);
+                                    if (a2) tma_load_4d_pair(ast + a_part, &prm.act[s][1], afull_l + as * 8u, c, xs, ys, b);
                                 }
                             }
-                            if (++as == prm.a_stages) { as = 0; aph ^= 1u; }
-                            for (int kyi = 0; kyi < prm.ygroup; ++kyi) {
-                                if (!prm.w_resident || first) {
-                                    const int tap = XMT ? kyi : (yg * prm.ygroup + kyi) * prm.kw + kx;
+                            if (++as == a_stages) { as = 0; aph ^= 1u; }
+                            if (w_stream || first) {
+                                int wrow = (XMT ? 0 : (yg * prm.ygroup) * prm.kw + kx) * Npad + wrow_first;   // tap * Npad (+ this CTA's rows)
+                                const int wrow_step = (XMT ? 1 : prm.kw) * Npad;
+                                for (int kyi = 0; kyi < ntaps; ++kyi, wrow += wrow_step) {
                                     mbar_wait(&wempty[ws], wph ^ 1u);
                                     if (elect_one()) {
-                                        uint8_t* wst = w_ring + (size_t)ws * w_stage_bytes;
-                                        if (leader) mbar_arrive_expect_tx(&wfull[ws], 2u * w_stage_bytes);
-                                        const int kc = kofs + kb * KB;
-                                        if (prm.merged_n == 1) {  // this CTA's half of B' = [w_hi; w_lo]: one whole plane
-                                            tma_load_2d_pair(wst, &prm.wgt[rank], wfull_l + ws * 8u, kc, tap * prm.Npad);
-                                        } else {
-                                            tma_load_2d_pair(wst, &prm.wgt[0], wfull_l + ws * 8u, kc, tap * prm.Npad + wrow0);
-                                            if (prm.b_parts == 2) tma_load_2d_pair(wst + b_bytes, &prm.wgt[1], wfull_l + ws * 8u, kc, tap * prm.Npad + wrow0);
-                                        }
+                                        if (leader) mbar_arrive_expect_tx(&wfull[ws], w_tx2);
+                                        tma_load_2d_pair(wst, wmap0, wfull_l + ws * 8u, kc, wrow);
+                                        if (b2) tma_load_2d_pair(wst + b_bytes, &prm.wgt[1], wfull_l + ws * 8u, kc, wrow);
                                     }
+                                    wst += w_stage_bytes;
+                                    if (++ws == w_stages) { ws = 0; wph ^= 1u; wst = w_ring; }
                                 }
-                                if (++ws == prm.w_stages) { ws = 0; wph ^= 1u; }
                             }
                         }
                     }
@@ -1246,11 +1251,17 @@ static int launch_pair_fl(const TcConvParams& prm, unsigned grid, size_t smem_by
         if (fl == (EPF_OUT_F32 | EPF_STATS)) return launch_pair<KIND, ACT, KB, EPF_OUT_F32 | EPF_STATS>(prm, grid, smem_bytes, st);
         if constexpr (KB == 64) {
             if (fl == EPF_OUT_F32) return launch_pair<KIND, ACT, KB, EPF_OUT_F32>(prm, grid, smem_bytes, st);
+            if (fl == EPF_OUT_SPLIT) return launch_pair<KIND, ACT, KB, EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);   // fnet's output conv
             // MobileNetV2 project convs: fp32 + 16-bit pair out, with / without the linear-bottleneck residual as ctx
             if (fl == (EPF_OUT_F32 | EPF_OUT_SPLIT)) return launch_pair<KIND, ACT, KB, EPF_OUT_F32 | EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);
             if (fl == (EPF_OUT_F32 | EPF_OUT_SPLIT | EPF_CTX))
                 return launch_pair<KIND, ACT, KB, EPF_OUT_F32 | EPF_OUT_SPLIT | EPF_CTX>(prm, grid, smem_bytes, st);
         }
+    }
+    if constexpr (KIND == DKT_EPI_LINEAR && ACT == DKT_ACT_TANH && KB == 64) {      // initial hidden states
+        const int fl = epilogue_flags(prm.epi);
+        if (fl == (EPF_OUT_F32 | EPF_OUT_SPLIT)) return launch_pair<KIND, ACT, KB, EPF_OUT_F32 | EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);
+        if (fl == (EPF_OUT_F32 | EPF_OUT_HI)) return launch_pair<KIND, ACT, KB, EPF_OUT_F32 | EPF_OUT_HI>(prm, grid, smem_bytes, st);
     }
     if constexpr (KIND == DKT_EPI_GRU_ZR && KB == 64) {            // tensor-core engine: r*h as a 16-bit pair, or hi only
         if (epilogue_flags(prm.epi) == EPF_OUT_SPLIT) return launch_pair<KIND, ACT, KB, EPF_OUT_SPLIT>(prm, grid, smem_bytes, st);
