@@ -130,8 +130,16 @@ __device__ __noinline__ void tc_epilogue1(const dkt_epilogue& e, int64_t p, int 
 // ---------------------------------------------------------------------------------------------
 // v2: persistent, double-buffered accumulators, coalesced epilogue
 // ---------------------------------------------------------------------------------------------
-constexpr int TC2_THREADS = 320;
+// 12 warps = three warpgroups: warps 0 (TMA producer) and 1 (MMA issuer) + two idle warps, then the eight epilogue warps as
+// two whole warpgroups -- `setmaxnreg` moves registers between warpGROUPS, and the GRU epilogues spilled 50 - 70 registers
+// at the 168 a 10- or 12-warp CTA gets per thread (cuobjdump: 105 LDL + 65 STL in the GRU_Q instantiation)
+constexpr int TC2_THREADS = 384;
 constexpr int TC2_EPI_WARPS = 8;
+constexpr int TC2_EPI_WARP0 = 4;        // first epilogue warp
+constexpr int TC2_ROLE_REGS = 56, TC2_EPI_REGS = 224;      // 128 * 56 + 256 * 224 = 64512 = 384 * 168
+
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr uint32_t TC2_EPI_TILE_BYTES = TC2_EPI_WARPS * 32 * 128;   // one 32 px x 32 ch fp32 tile per warp
 constexpr uint32_t TC2_EPI_BYTES = TC2_EPI_TILE_BYTES + 1024;        // + the conv bias (256 floats, zero beyond N)
 
@@ -201,7 +209,7 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
                                                        uint8_t* epi_smem, int warp, int lane, int tiles_per_img,
                                                        const TileWalk tw) {
     constexpr bool LIN = KIND == DKT_EPI_LINEAR;
-    const int ew = warp - 2;
+    const int ew = warp - TC2_EPI_WARP0;
     const int q = warp & 3;
     const int half = ew >> 2;
     float* ebuf = reinterpret_cast<float*>(epi_smem + (size_t)ew * 4096);
@@ -239,7 +247,7 @@ __device__ __forceinline__ void conv_tc_epilogue_warps(const TcConvParams& prm, 
     // the bias lives in shared memory: a global load here would sit in the latency chain of every chunk
     float* const s_bias = reinterpret_cast<float*>(epi_smem + TC2_EPI_TILE_BYTES);
     if (LIN) {
-        for (int i = (int)threadIdx.x - 64; i < 256; i += TC2_EPI_WARPS * 32) s_bias[i] = (i < N && e.bias) ? __ldg(e.bias + i) : 0.f;
+        for (int i = (int)threadIdx.x - TC2_EPI_WARP0 * 32; i < 256; i += TC2_EPI_WARPS * 32) s_bias[i] = (i < N && e.bias) ? __ldg(e.bias + i) : 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     const bool has_ops = !LIN || has_ctx || has_res || has_res2;     // operands fetched from HBM per pixel
@@ -557,7 +565,7 @@ __device__ __forceinline__ void conv_tc_epilogue_proj(const TcConvParams& prm, u
                                                       uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
                                                       uint8_t* epi_smem, int warp, int lane, int tiles_per_img,
                                                       const TileWalk tw) {
-    const int ew = warp - 2;
+    const int ew = warp - TC2_EPI_WARP0;
     const int q = warp & 3;
     const int half = ew >> 2;
     float* s_w = reinterpret_cast<float*>(epi_smem);            // [256][12]
@@ -566,7 +574,7 @@ __device__ __forceinline__ void conv_tc_epilogue_proj(const TcConvParams& prm, u
     const dkt_epilogue& e = prm.epi;
     const int N = prm.N;
     const float scale = e.scale;
-    const int et = (int)threadIdx.x - 64;
+    const int et = (int)threadIdx.x - TC2_EPI_WARP0 * 32;
     for (int i = et; i < 256 * DKT_PROJ_LD; i += TC2_EPI_WARPS * 32) s_w[i] = (i < N * DKT_PROJ_LD) ? __ldg(e.proj + i) : 0.f;
     for (int i = et; i < 256; i += TC2_EPI_WARPS * 32) s_b[i] = (i < N && e.bias) ? __ldg(e.bias + i) : 0.f;
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -745,7 +753,7 @@ conv_tc_kernel(const __grid_constant__ TcConvParams prm) {
             if (elect_one()) umma_commit(&tmem_full_bar[as]);     // accumulator complete
             if (++as == prm.acc_stages) { as = 0; aphase ^= 1u; }
         }
-    } else {
+    } else if (warp >= TC2_EPI_WARP0) {
         const TileWalk tw{(int)blockIdx.x, (int)gridDim.x, prm.num_tiles, 1, 0, 0u};
         if constexpr (KIND == DKT_EPI_PROJ)
             conv_tc_epilogue_proj<ACT, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
@@ -909,7 +917,7 @@ conv_tc_patch_kernel(const __grid_constant__ TcConvParams prm) {
             if (elect_one()) umma_commit(&tmem_full_bar[acs]);
             if (++acs == prm.acc_stages) { acs = 0; aphase ^= 1u; }
         }
-    } else {
+    } else if (warp >= TC2_EPI_WARP0) {
         const TileWalk tw{(int)blockIdx.x, (int)gridDim.x, prm.num_tiles, 1, 0, 0u};
         if constexpr (KIND == DKT_EPI_PROJ)
             conv_tc_epilogue_proj<ACT, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
@@ -1103,7 +1111,16 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int tiles_per_img = prm.tiles_x * prm.tiles_y;
-
+    if (warp >= TC2_EPI_WARP0) {
+        // ===== epilogue warpgroups: take the registers the role warpgroup gives back =====
+        reg_alloc<TC2_EPI_REGS>();
+        const TileWalk tw{pair_id, pairs, items, 2, (int)rank, leader ? 0u : mapa_u32(smem_u32(tmem_empty_bar), 0)};
+        if constexpr (KIND == DKT_EPI_PROJ)
+            conv_tc_epilogue_proj<ACT, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+        else
+            conv_tc_epilogue_warps<KIND, ACT, FL, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+    } else {
+    reg_dealloc<TC2_ROLE_REGS>();
     if (warp == 0) {
         // ===== TMA producer (both CTAs): own A patches, own half of the W blocks; bytes counted on the leader =====
         // (per-tap state -- weight row, ring slot address, barrier address -- advances by additions: with one MMA per
@@ -1182,12 +1199,7 @@ conv_tc_pair_kernel(const __grid_constant__ TcConvParams prm) {
             else if (a_lo) pair_mma_loop<KB, XMT, 0, true, false>(prm, cx);
             else pair_mma_loop<KB, XMT, 0, false, false>(prm, cx);
         }
-    } else {
-        const TileWalk tw{pair_id, pairs, items, 2, (int)rank, leader ? 0u : mapa_u32(smem_u32(tmem_empty_bar), 0)};
-        if constexpr (KIND == DKT_EPI_PROJ)
-            conv_tc_epilogue_proj<ACT, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
-        else
-            conv_tc_epilogue_warps<KIND, ACT, FL, XMT>(prm, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane, tiles_per_img, tw);
+    }
     }
 
     // neither CTA may leave (or free TMEM) while its peer can still reach its shared memory / barriers
