@@ -8,6 +8,16 @@ trips, reference tools/evaluate_stereo.py:116-134, batched and pipelined).
         disp_host = pipe.step(nxt)                    # (B,1,H,W) pinned fp32 = -disparity of the PREVIOUS prefetch
     disp_host = pipe.step(None)
 
+Throughput form (what ``bench.py``'s ``e2e`` runs): ``step_async`` enqueues the batch's forward AND its read-back and returns
+the result of the call BEFORE it, so the host never waits for the GPU between batches (graph launch and the read-back of
+batch i overlap the forward of batch i + 1); ``drain()`` returns the last one.
+
+    pipe.prefetch(im1_host, im2_host)
+    prev = None
+    for nxt in batches + [None]:
+        out = pipe.step_async(nxt)                    # result of the previous step_async (None on the first call)
+    last = pipe.drain()
+
 PyTorch is used for streams, events and pinned memory only.
 """
 from __future__ import annotations
@@ -26,6 +36,13 @@ class HostPipeline:
         self.cur = 0                       # slot holding the batch the next step() computes
         self.pending = False
         self.out_host: Optional[torch.Tensor] = None
+        # step_async state: read-back stream, staged device copies / pinned results / events per slot
+        self.d2h_stream: Optional[torch.cuda.Stream] = None
+        self.out_dev = [None, None]
+        self.out_hosts = [None, None]
+        self.fwd_done = [None, None]       # forward that read input slot i (and staged its result) finished
+        self.d2h_done = [None, None]
+        self.last_async: Optional[int] = None
 
     def _slot(self, i: int, like: torch.Tensor, dev) -> Tuple[torch.Tensor, torch.Tensor]:
         s = self.slots[i]
@@ -46,8 +63,11 @@ class HostPipeline:
         if self.copy_stream is None:
             self.copy_stream = torch.cuda.Stream(device=dev)
         d1, d2 = self._slot(slot, im1, dev)
-        # the slot's previous reader (the forward two steps ago) finished: step() ends with a stream sync
+        # the slot's previous reader (the forward two steps ago) finished: step() ends with a stream sync; step_async()
+        # leaves that forward's event in fwd_done
         with torch.cuda.stream(self.copy_stream):
+            if self.fwd_done[slot] is not None:
+                self.copy_stream.wait_event(self.fwd_done[slot])
             d1.copy_(im1, non_blocking=True)
             d2.copy_(im2, non_blocking=True)
             ev = torch.cuda.Event()
@@ -76,3 +96,57 @@ class HostPipeline:
         self.cur ^= 1
         self.pending = next_batch is not None
         return self.out_host
+
+    # ---- throughput form -----------------------------------------------------------------------------------------------
+    def step_async(self, next_batch=None) -> Optional[torch.Tensor]:
+        """Enqueue the prefetched batch's forward, the staging of its result and its read-back into pinned memory; start
+        uploading ``next_batch``; return the PREVIOUS call's result (pinned, valid until the call after the next one) or None.
+        Nothing here waits for work enqueued by this call."""
+        assert self.pending, "call prefetch() first"
+        cs = torch.cuda.current_stream()
+        dev = cs.device
+        if self.d2h_stream is None:
+            self.d2h_stream = torch.cuda.Stream(device=dev)
+        k = self.cur
+        cs.wait_event(self.ready[k])
+        d1, d2 = self.slots[k]
+        _, up = self.model(d1, d2, iters=self.iters, test_mode=True)
+        if self.out_dev[k] is None or self.out_dev[k].shape != up.shape:
+            self.out_dev[k] = torch.empty_like(up)
+            self.out_dev[k].record_stream(self.d2h_stream)
+            self.out_hosts[k] = torch.empty(up.shape, dtype=up.dtype, pin_memory=True)
+        if self.d2h_done[k] is not None:
+            cs.wait_event(self.d2h_done[k])                # the read-back that last used this staging buffer
+        self.out_dev[k].copy_(up)                          # the model's output buffer belongs to the next forward
+        ev = torch.cuda.Event()
+        ev.record(cs)
+        self.fwd_done[k] = ev
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(ev)
+            self.out_hosts[k].copy_(self.out_dev[k], non_blocking=True)
+            e2 = torch.cuda.Event()
+            e2.record(self.d2h_stream)
+        self.d2h_done[k] = e2
+        if next_batch is not None:
+            self._upload(k ^ 1, next_batch)                # waits for the forward that last read that slot
+        prev, self.last_async = self.last_async, k
+        self.cur ^= 1
+        self.pending = next_batch is not None
+        if prev is None:
+            return None
+        self.d2h_done[prev].synchronize()
+        return self.out_hosts[prev]
+
+    def drain(self) -> Optional[torch.Tensor]:
+        """Result of the last step_async(); the current stream also waits for the outstanding copies, so an event recorded
+        after drain() covers them."""
+        if self.last_async is None:
+            return None
+        k, self.last_async = self.last_async, None
+        cs = torch.cuda.current_stream()
+        cs.wait_event(self.d2h_done[k])
+        for ev in self.ready:
+            if ev is not None:
+                cs.wait_event(ev)
+        self.d2h_done[k].synchronize()
+        return self.out_hosts[k]

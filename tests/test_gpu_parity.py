@@ -1124,6 +1124,38 @@ def test_host_pipeline_matches_direct_calls():
         assert torch.equal(got, want[i]), (i, float((got - want[i]).abs().max()))
 
 
+def test_host_pipeline_async_matches_direct_calls():
+    """HostPipeline.step_async (the throughput form bench.py's e2e runs: forward + read-back enqueued, the previous call's
+    result returned) delivers exactly the direct forward's maps, one call late, and drain() the last one; seven batches so
+    that every input slot, staging buffer and pinned result is reused while its predecessor's copies may still be in flight."""
+    from dkt_stereo_b200.pipeline import HostPipeline
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    g = load_golden("raft_fwd_small")
+    model = _model("tc", g)
+    n = 7
+    batches = [tuple(t.pin_memory() for t in synthetic_pair(2, 64, 96, seed=300 + i)) for i in range(n)]
+    want = []
+    for a, b in batches:
+        _, up = model(a.to(dev()), b.to(dev()), iters=3, test_mode=True)
+        want.append(up.cpu())
+    pipe = HostPipeline(model, iters=3)
+    pipe.prefetch(*batches[0])
+    got = []
+    for i in range(n):
+        out = pipe.step_async(batches[i + 1] if i + 1 < n else None)
+        assert (out is None) == (i == 0)
+        if out is not None:
+            got.append(out.clone())
+    got.append(pipe.drain().clone())
+    assert pipe.drain() is None
+    assert len(got) == n
+    for i in range(n):
+        assert torch.equal(got[i], want[i]), (i, float((got[i] - want[i]).abs().max()))
+    # the blocking form still works on the same pipeline afterwards
+    pipe.prefetch(*batches[2])
+    assert torch.equal(pipe.step(None), want[2])
+
+
 def test_igev_context_encoder_on_engine(monkeypatch):
     """IGEV-Stereo's cnet + context convs on the tensor-core EncoderEngine (fnet-less mode) vs the same modules in
     PyTorch fp32: same weights, same images -> same disparity within the end-to-end gate."""
