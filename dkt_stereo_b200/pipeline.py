@@ -42,7 +42,7 @@ class HostPipeline:
         self.out_hosts = [None, None]
         self.fwd_done = [None, None]       # forward that read input slot i (and staged its result) finished
         self.d2h_done = [None, None]
-        self.last_async: Optional[int] = None
+        self._last = None                  # (read-back event, pinned result) of the latest step_async
 
     def _slot(self, i: int, like: torch.Tensor, dev) -> Tuple[torch.Tensor, torch.Tensor]:
         s = self.slots[i]
@@ -112,9 +112,13 @@ class HostPipeline:
         d1, d2 = self.slots[k]
         _, up = self.model(d1, d2, iters=self.iters, test_mode=True)
         if self.out_dev[k] is None or self.out_dev[k].shape != up.shape:
-            self.out_dev[k] = torch.empty_like(up)
-            self.out_dev[k].record_stream(self.d2h_stream)
-            self.out_hosts[k] = torch.empty(up.shape, dtype=up.dtype, pin_memory=True)
+            # both slots at once: pinning host memory is slow and synchronises the device -- it must not happen in the
+            # middle of a stream of batches (r4n: the second slot's cudaHostAlloc inside the timed region cost 4 - 20 ms)
+            for j in (0, 1):                 # (after a shape change the previous result stays alive through self._last)
+                self.out_dev[j] = torch.empty_like(up)
+                self.out_dev[j].record_stream(self.d2h_stream)
+                self.out_hosts[j] = torch.empty(up.shape, dtype=up.dtype, pin_memory=True)
+                self.d2h_done[j] = None
         if self.d2h_done[k] is not None:
             cs.wait_event(self.d2h_done[k])                # the read-back that last used this staging buffer
         self.out_dev[k].copy_(up)                          # the model's output buffer belongs to the next forward
@@ -129,24 +133,24 @@ class HostPipeline:
         self.d2h_done[k] = e2
         if next_batch is not None:
             self._upload(k ^ 1, next_batch)                # waits for the forward that last read that slot
-        prev, self.last_async = self.last_async, k
+        prev, self._last = self._last, (e2, self.out_hosts[k])
         self.cur ^= 1
         self.pending = next_batch is not None
         if prev is None:
             return None
-        self.d2h_done[prev].synchronize()
-        return self.out_hosts[prev]
+        prev[0].synchronize()
+        return prev[1]
 
     def drain(self) -> Optional[torch.Tensor]:
         """Result of the last step_async(); the current stream also waits for the outstanding copies, so an event recorded
         after drain() covers them."""
-        if self.last_async is None:
+        if self._last is None:
             return None
-        k, self.last_async = self.last_async, None
+        (ev_last, host), self._last = self._last, None
         cs = torch.cuda.current_stream()
-        cs.wait_event(self.d2h_done[k])
+        cs.wait_event(ev_last)
         for ev in self.ready:
             if ev is not None:
                 cs.wait_event(ev)
-        self.d2h_done[k].synchronize()
-        return self.out_hosts[k]
+        ev_last.synchronize()
+        return host
