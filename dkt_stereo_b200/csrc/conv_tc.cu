@@ -16,7 +16,7 @@
 // blockIdx.x, +gridDim.x, ...  Three pipelines run concurrently inside a CTA:
 //   warp 0      TMA producer      smem ring of (A hi, A lo, W hi, W lo) stages, full/empty mbarriers
 //   warp 1      MMA issuer        two TMEM accumulator stages (2 x Npad columns), tmem_full/empty
-//   warps 2..9  epilogue          tile i is drained while the MMAs of tile i+1 run
+//   warps 4..11 epilogue          tile i is drained while the MMAs of tile i+1 run (warps 2, 3 idle: warpgroup alignment, TC2_EPI_WARP0)
 // The epilogue is coalesced: a warp owns 32 pixels (its TMEM lane quarter); it pulls a 32-column
 // chunk with tcgen05.ld (thread = pixel), transposes it through a swizzled 4 KB smem buffer and
 // continues with lanes = 8 x 16-byte channel groups of 4 pixels, so every global access of the
@@ -173,7 +173,7 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor_sbo(uint32_t addr, uint32_t
 
 __device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
-// Epilogue warps 2..9 of the persistent kernels (see the header comment of this file).
+// Epilogue warps 4..11 of the persistent kernels (see the header comment of this file).
 // TMEM lane quarter = warp % 4; the two warps of a quarter take alternate 32-column chunks.  Per chunk a warp
 // pulls 32 columns with tcgen05.ld (thread = pixel), transposes through a swizzled 4 KB smem buffer and continues
 // with lanes = 8 x 16-byte channel groups of 4 pixels, so every global access is a full 128-byte line.
@@ -1057,7 +1057,7 @@ __device__ __forceinline__ void pair_mma_loop(const TcConvParams& prm, const Pai
 //              counted there (the leader arms 2x the stage bytes), the follower's epilogue warps arrive remotely;
 //              aempty / wempty / tmem_full exist in both CTAs and are signalled by multicast tcgen05.commit.
 //   roles      warp 0 = TMA producer (both CTAs), warp 1 = MMA issuer (leader only; allocates TMEM in both),
-//              warps 2..9 = epilogue of the CTA's own tile (TMEM lanes 0..127 of each CTA = its 128 pixels).
+//              warps 4..11 = epilogue of the CTA's own tile (TMEM lanes 0..127 of each CTA = its 128 pixels).
 // ---------------------------------------------------------------------------------------------
 template <int KIND, int ACT, int KB, int FL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
