@@ -52,6 +52,27 @@ class FakeFeeder:
         return self.predict(im1, im2)
 
 
+class FakeAsyncFeeder(FakeFeeder):
+    """The throughput protocol of HostPipeline: step_async returns the PREVIOUS call's maps, drain() the last ones."""
+
+    def __init__(self):
+        super().__init__()
+        self.last = None
+        self.blocking_calls = 0
+
+    def step(self, nxt=None):
+        self.blocking_calls += 1
+        return super().step(nxt)
+
+    def step_async(self, nxt=None):
+        prev, self.last = self.last, FakeFeeder.step(self, nxt)
+        return prev
+
+    def drain(self):
+        prev, self.last = self.last, None
+        return prev
+
+
 def _reference_style(ds, thr, bound, pool, maxdisp=192):
     """The reference's batch-1 loop, written out literally."""
     from dkt_stereo_b200.utils import InputPadder
@@ -93,6 +114,22 @@ def test_batched_validator_matches_reference_metric_definitions(pool, bound, thr
         assert max(c[0] for c in feeder.calls) == 3 and len(feeder.calls) < len(shapes)
     else:
         assert all(c[0] == 1 for c in feeder.calls)
+
+
+@pytest.mark.parametrize("batch", [1, 3])
+def test_validator_scores_one_batch_late_through_step_async(batch):
+    """With a feeder that offers step_async / drain the validator uses them (never the blocking step) and reports the same
+    metrics: every batch is scored against the maps that belong to it, the last one through drain()."""
+    import evaluate_stereo as E
+    shapes = [(37, 50), (40, 64), (37, 50), (37, 50), (33, 70), (40, 64), (37, 50)]
+    ds = FakeDataset(shapes)
+    feeder = FakeAsyncFeeder()
+    res = E.validate(torch.nn.Identity(), ds, "fake", 2.0, True, None, iters=4, pool="image", batch=batch, feeder=feeder)
+    epe, d1 = _reference_style(ds, 2.0, True, "image")
+    assert res["fake-epe"] == pytest.approx(epe, rel=1e-6)
+    assert res["fake-d1"] == pytest.approx(d1, rel=1e-6)
+    assert feeder.blocking_calls == 0 and feeder.last is None
+    assert sum(c[0] for c in feeder.calls) == len(shapes)
 
 
 def test_missing_nocc_mask_is_an_error():

@@ -1156,6 +1156,31 @@ def test_host_pipeline_async_matches_direct_calls():
     assert torch.equal(pipe.step(None), want[2])
 
 
+def test_host_pipeline_async_across_shape_changes():
+    """The evaluator's use of step_async: consecutive batches of DIFFERENT shapes (ragged datasets).  Input slots, staging
+    buffers and pinned results are re-created per shape while the previous batch's read-back is still owed to the caller."""
+    from dkt_stereo_b200.pipeline import HostPipeline
+    from dkt_stereo_b200.synthetic import synthetic_pair
+    g = load_golden("raft_fwd_small")
+    model = _model("tc", g)
+    shapes = [(2, 64, 96), (1, 96, 128), (1, 96, 128), (2, 64, 96), (3, 64, 64)]
+    batches = [tuple(t.pin_memory() for t in synthetic_pair(b, h, w, seed=400 + i)) for i, (b, h, w) in enumerate(shapes)]
+    want = []
+    for a, b in batches:
+        _, up = model(a.to(dev()), b.to(dev()), iters=3, test_mode=True)
+        want.append(up.cpu())
+    pipe = HostPipeline(model, iters=3)
+    pipe.prefetch(*batches[0])
+    got = []
+    for i in range(len(batches)):
+        out = pipe.step_async(batches[i + 1] if i + 1 < len(batches) else None)
+        if out is not None:
+            got.append(out.clone())
+    got.append(pipe.drain().clone())
+    for i, (gt, wt) in enumerate(zip(got, want)):
+        assert gt.shape == wt.shape and torch.equal(gt, wt), (i, tuple(gt.shape), tuple(wt.shape))
+
+
 def test_igev_context_encoder_on_engine(monkeypatch):
     """IGEV-Stereo's cnet + context convs on the tensor-core EncoderEngine (fnet-less mode) vs the same modules in
     PyTorch fp32: same weights, same images -> same disparity within the end-to-end gate."""

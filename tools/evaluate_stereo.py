@@ -151,7 +151,7 @@ def validate(model, dataset, name: str, thr: float, bound: bool, nocc, iters: in
     and pipelined: same-shape samples ride in one forward of up to ``batch`` pairs; the pinned upload of batch i+1
     overlaps the forward of batch i (``HostPipeline``) and the dataset decoding runs in a background thread.  The
     metrics are the reference's, per sample, in dataset order.  ``feeder``: object with prefetch(im1, im2) / step(next)
-    (default: HostPipeline on the model)."""
+    and, optionally, step_async(next) / drain() (default: HostPipeline on the model, whose step_async is used)."""
     model.eval()
     if feeder is None:
         from dkt_stereo_b200.pipeline import HostPipeline
@@ -159,20 +159,37 @@ def validate(model, dataset, name: str, thr: float, bound: bool, nocc, iters: in
     epes, outs = {}, {}
     t0, pairs = time.perf_counter(), 0
     stream = _batch_stream(dataset, batch, nocc)
-    cur = next(stream, None)
-    if cur is not None:
-        feeder.prefetch(cur.im1, cur.im2)
-    while cur is not None:
-        nxt = next(stream, None)
-        up = feeder.step((nxt.im1, nxt.im2) if nxt is not None else None)      # pinned host (B,1,Hp,Wp), reused next step
-        up = cur.padder.unpad(up)
-        for j, idx in enumerate(cur.idx):
-            flow_gt, valid_gt, occ = cur.gts[j]
+
+    def score(b, up):
+        up = b.padder.unpad(up)
+        for j, idx in enumerate(b.idx):
+            flow_gt, valid_gt, occ = b.gts[j]
             image_epe, flags = sample_metrics(up[j].float(), flow_gt, valid_gt, thr, bound, occ, maxdisp)
             epes[idx] = image_epe
             outs[idx] = flags.numpy() if pool == "pixel" else flags.float().mean().item()
-        pairs += len(cur.idx)
-        cur = nxt
+        return len(b.idx)
+
+    cur = next(stream, None)
+    if cur is not None:
+        feeder.prefetch(cur.im1, cur.im2)
+    if hasattr(feeder, "step_async"):
+        # throughput form: the maps of a batch come back one call late, so the host scores batch i - 1 (and the reader
+        # thread decodes batch i + 1) while the GPU computes batch i
+        waiting = None
+        while cur is not None:
+            nxt = next(stream, None)
+            up = feeder.step_async((nxt.im1, nxt.im2) if nxt is not None else None)
+            if waiting is not None:
+                pairs += score(waiting, up)
+            waiting, cur = cur, nxt
+        if waiting is not None:
+            pairs += score(waiting, feeder.drain())
+    else:
+        while cur is not None:
+            nxt = next(stream, None)
+            up = feeder.step((nxt.im1, nxt.im2) if nxt is not None else None)  # pinned host (B,1,Hp,Wp), reused next step
+            pairs += score(cur, up)
+            cur = nxt
     order = sorted(epes)
     epe = float(np.mean([epes[i] for i in order]))
     if pool == "pixel":
