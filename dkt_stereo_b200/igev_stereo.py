@@ -435,6 +435,12 @@ class IGEVStereo(nn.Module):
             try:
                 with torch.cuda.graph(g):
                     up = self._forward_test(in1, in2, iters)
+            except RuntimeError as e:            # a module of this configuration cannot be captured: keep serving, eagerly
+                import warnings
+                warnings.warn(f"IGEVStereo: whole-forward CUDA graph capture failed ({e}); running eagerly")
+                self.full_graph = False
+                torch.cuda.synchronize()
+                return self._forward_test(image1, image2, iters)
             finally:
                 self._capturing = False
             ent = self._full[key] = (g, in1, in2, up)
